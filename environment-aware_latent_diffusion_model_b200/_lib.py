@@ -1,0 +1,144 @@
+"""ctypes binding of libealdm_b200.so (the C ABI declared in include/ealdm_b200.h).
+
+The library is the product: there is no Python/PyTorch fallback for any operator.  If the shared
+object is missing or the device is not sm_100, loading fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libealdm_b200.so")
+CSRC_DIR = os.path.join(_HERE, "csrc")
+
+F32, BF16 = 0, 1
+ACT_NONE, ACT_SILU, ACT_GEGLU = 0, 1, 2
+IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05 = 0, 1, 2
+
+EXPORTS = [
+    "ealdm_abi_version", "ealdm_last_error", "ealdm_device_check", "ealdm_launch_count",
+    "ealdm_conv", "ealdm_group_norm", "ealdm_layer_norm", "ealdm_attention",
+    "ealdm_timestep_embedding", "ealdm_nchw_to_nhwc", "ealdm_nhwc_to_nchw",
+    "ealdm_upsample_nearest2x", "ealdm_copy2d", "ealdm_softmax_rows", "ealdm_ddim_step",
+    "ealdm_q_sample", "ealdm_cfg_mse",
+]
+
+
+class ConvSrc(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("n", C.c_int64), ("h", C.c_int64), ("w", C.c_int64),
+                ("c", C.c_int64), ("ld", C.c_int64), ("ksize", C.c_int32), ("stride", C.c_int32),
+                ("pad", C.c_int32), ("upsample", C.c_int32)]
+
+
+class ConvArgs(C.Structure):
+    _fields_ = [("dtype", C.c_int32), ("impl", C.c_int32), ("n_src", C.c_int32), ("act", C.c_int32),
+                ("src", ConvSrc * 2), ("weight", C.c_void_p), ("n_out", C.c_int64),
+                ("k_total", C.c_int64), ("h_out", C.c_int64), ("w_out", C.c_int64),
+                ("bias", C.c_void_p), ("rowvec", C.c_void_p), ("ld_rowvec", C.c_int64),
+                ("residual", C.c_void_p), ("ld_res", C.c_int64), ("out", C.c_void_p),
+                ("ld_out", C.c_int64), ("out_f32", C.c_int32), ("reserved", C.c_int32)]
+
+
+class GroupNormArgs(C.Structure):
+    _fields_ = [("dtype", C.c_int32), ("act", C.c_int32), ("x", C.c_void_p), ("n", C.c_int64),
+                ("hw", C.c_int64), ("c", C.c_int64), ("ld_x", C.c_int64), ("groups", C.c_int32),
+                ("eps", C.c_float), ("gamma", C.c_void_p), ("beta", C.c_void_p), ("y", C.c_void_p),
+                ("ld_y", C.c_int64), ("stats", C.c_void_p)]
+
+
+class LayerNormArgs(C.Structure):
+    _fields_ = [("dtype", C.c_int32), ("reserved", C.c_int32), ("x", C.c_void_p),
+                ("rows", C.c_int64), ("c", C.c_int64), ("ld_x", C.c_int64), ("eps", C.c_float),
+                ("reserved2", C.c_int32), ("gamma", C.c_void_p), ("beta", C.c_void_p),
+                ("y", C.c_void_p), ("ld_y", C.c_int64)]
+
+
+class AttentionArgs(C.Structure):
+    _fields_ = [("dtype", C.c_int32), ("impl", C.c_int32), ("q", C.c_void_p), ("k", C.c_void_p),
+                ("v", C.c_void_p), ("ld_q", C.c_int64), ("ld_kv", C.c_int64),
+                ("head_stride_q", C.c_int64), ("head_stride_kv", C.c_int64), ("batch", C.c_int64),
+                ("heads", C.c_int64), ("n_q", C.c_int64), ("n_kv", C.c_int64),
+                ("head_dim", C.c_int64), ("scale", C.c_float), ("reserved", C.c_int32),
+                ("out", C.c_void_p), ("ld_out", C.c_int64)]
+
+
+class DdimStepArgs(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("e_uncond", C.c_void_p), ("e_cond", C.c_void_p),
+                ("noise", C.c_void_p), ("x_prev", C.c_void_p), ("pred_x0", C.c_void_p),
+                ("e_out", C.c_void_p), ("numel", C.c_int64), ("cfg_scale", C.c_float),
+                ("sqrt_one_minus_at", C.c_float), ("sqrt_at", C.c_float),
+                ("sqrt_a_prev", C.c_float), ("dir_coef", C.c_float), ("sigma_t", C.c_float),
+                ("temperature", C.c_float), ("reserved", C.c_int32)]
+
+
+class EaldmError(RuntimeError):
+    pass
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile csrc/*.cu for sm_100a into libealdm_b200.so (in-tree) with nvcc via make."""
+    if force and os.path.exists(LIB_PATH):
+        os.remove(LIB_PATH)
+    r = subprocess.run(["make", "-C", CSRC_DIR, "-j8"], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise EaldmError("building libealdm_b200.so failed:\n" + r.stdout[-4000:] + r.stderr[-4000:])
+    if verbose:
+        print(r.stdout[-2000:])
+    return LIB_PATH
+
+
+_lib = None
+
+
+def _declare(lib):
+    vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+    lib.ealdm_abi_version.restype = C.c_int
+    lib.ealdm_abi_version.argtypes = []
+    lib.ealdm_last_error.restype = C.c_char_p
+    lib.ealdm_last_error.argtypes = []
+    lib.ealdm_device_check.restype = C.c_int
+    lib.ealdm_device_check.argtypes = []
+    lib.ealdm_launch_count.restype = C.c_int64
+    lib.ealdm_launch_count.argtypes = []
+    for name, argt in [
+        ("ealdm_conv", [C.POINTER(ConvArgs), vp]),
+        ("ealdm_group_norm", [C.POINTER(GroupNormArgs), vp]),
+        ("ealdm_layer_norm", [C.POINTER(LayerNormArgs), vp]),
+        ("ealdm_attention", [C.POINTER(AttentionArgs), vp]),
+        ("ealdm_timestep_embedding", [vp, i64, i32, vp, i32, vp, vp]),
+        ("ealdm_nchw_to_nhwc", [vp, i64, i64, i64, i64, i32, vp, i64, vp]),
+        ("ealdm_nhwc_to_nchw", [vp, i64, i32, i64, i64, i64, i64, vp, vp]),
+        ("ealdm_upsample_nearest2x", [vp, i64, i32, i64, i64, i64, i64, vp, i64, vp]),
+        ("ealdm_copy2d", [vp, i64, i32, vp, i64, i32, i64, i64, vp]),
+        ("ealdm_softmax_rows", [vp, i64, i32, i64, i64, f32, vp]),
+        ("ealdm_ddim_step", [C.POINTER(DdimStepArgs), vp]),
+        ("ealdm_q_sample", [vp, vp, vp, vp, vp, i64, i64, vp, vp]),
+        ("ealdm_cfg_mse", [vp, vp, vp, f32, i64, i64, vp, vp]),
+    ]:
+        fn = getattr(lib, name)
+        fn.restype = C.c_int
+        fn.argtypes = argt
+
+
+def load():
+    """Load the shared library (never builds implicitly on a GPU box; see __graft_entry__.build)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise EaldmError(
+                f"{LIB_PATH} not found: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU or PyTorch fallback for the CUDA kernels)")
+        lib = C.CDLL(LIB_PATH)
+        _declare(lib)
+        if lib.ealdm_abi_version() != 1:
+            raise EaldmError("libealdm_b200.so ABI version mismatch")
+        _lib = lib
+    return _lib
+
+
+def check(rc: int):
+    if rc != 0:
+        msg = load().ealdm_last_error().decode("utf-8", "replace")
+        raise EaldmError(f"libealdm_b200 error {rc}: {msg}")

@@ -1,0 +1,219 @@
+// bf16 tensor-core flash attention for head_dim 32 (UNet self-attention: 1024 / 256 / 64 tokens).
+// One warp owns 16 queries; K/V tiles of 64 keys are double-buffered in shared memory with
+// cp.async; S = Q.K^T and O += P.V run on mma.sync m16n8k16 with fp32 accumulation and an online
+// softmax in the exp2 domain.  At d = 32 the kernel is bound by exp throughput (128 tensor FLOPs per
+// exp), not by the tensor pipe, which is why it does not use tcgen05.
+#include "common.cuh"
+
+namespace ealdm {
+namespace attn {
+
+constexpr int KV_TILE = 64;
+constexpr int ROW_PAD = 40;  // bf16 per shared row (80 B): conflict-free ldmatrix
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool pred) {
+  const uint32_t s = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
+  const int sz = pred ? 16 : 0;  // src-size 0 => zero fill
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(sz)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* smem) {
+  const uint32_t s = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(s));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* smem) {
+  const uint32_t s = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(s));
+}
+__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0,
+                                         uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+      "{%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+
+template <int NWARPS>
+__global__ void __launch_bounds__(NWARPS * 32)
+flash_mma_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const bf16* __restrict__ v,
+                 long long ld_q, long long ld_kv, long long hs_q, long long hs_kv, int n_q, int n_kv,
+                 float scale_log2, bf16* __restrict__ out, long long ld_out) {
+  __shared__ __align__(16) bf16 Ks[2][KV_TILE][ROW_PAD];
+  __shared__ __align__(16) bf16 Vs[2][KV_TILE][ROW_PAD];
+  constexpr int NT = NWARPS * 32;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.z, h = blockIdx.y;
+  const int q0 = blockIdx.x * (NWARPS * 16) + warp * 16;
+  const int r0 = q0 + (lane >> 2), r1 = r0 + 8;
+  const int cq = (lane & 3) * 2;
+
+  uint32_t qa[2][4];
+  {
+    const bf16* qb = q + static_cast<long long>(b) * n_q * ld_q + h * hs_q;
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      const int c = ks * 16 + cq;
+      qa[ks][0] = r0 < n_q ? *reinterpret_cast<const uint32_t*>(qb + r0 * ld_q + c) : 0u;
+      qa[ks][1] = r1 < n_q ? *reinterpret_cast<const uint32_t*>(qb + r1 * ld_q + c) : 0u;
+      qa[ks][2] = r0 < n_q ? *reinterpret_cast<const uint32_t*>(qb + r0 * ld_q + c + 8) : 0u;
+      qa[ks][3] = r1 < n_q ? *reinterpret_cast<const uint32_t*>(qb + r1 * ld_q + c + 8) : 0u;
+    }
+  }
+
+  const bf16* kb = k + static_cast<long long>(b) * n_kv * ld_kv + h * hs_kv;
+  const bf16* vb = v + static_cast<long long>(b) * n_kv * ld_kv + h * hs_kv;
+  auto prefetch = [&](int tile, int st) {
+    // 64 rows x 4 chunks of 16 B for K and for V
+    for (int i = threadIdx.x; i < KV_TILE * 4; i += NT) {
+      const int r = i >> 2, c = (i & 3) * 8;
+      const int key = tile * KV_TILE + r;
+      const bool ok = key < n_kv;
+      const long long off = static_cast<long long>(ok ? key : 0) * ld_kv + c;
+      cp_async16(&Ks[st][r][c], kb + off, ok);
+      cp_async16(&Vs[st][r][c], vb + off, ok);
+    }
+  };
+
+  float o[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[i][j] = 0.f;
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+
+  const int ntiles = (n_kv + KV_TILE - 1) / KV_TILE;
+  prefetch(0, 0);
+  cp_async_commit();
+  for (int t = 0; t < ntiles; ++t) {
+    const int st = t & 1;
+    if (t + 1 < ntiles) {
+      prefetch(t + 1, st ^ 1);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+
+    float s[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+      uint32_t kf[4];
+      ldmatrix_x4(kf, &Ks[st][nt * 8 + (lane & 7)][(lane >> 3) * 8]);
+      mma_bf16(s[nt], qa[0], kf[0], kf[1]);
+      mma_bf16(s[nt], qa[1], kf[2], kf[3]);
+    }
+    const bool last = (t + 1) * KV_TILE > n_kv;
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float val = s[nt][j] * scale_log2;
+        if (last) {
+          const int key = t * KV_TILE + nt * 8 + cq + (j & 1);
+          if (key >= n_kv) val = -INFINITY;
+        }
+        s[nt][j] = val;
+      }
+      mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+      mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
+    const float c0 = exp2f(m0 - mn0), c1 = exp2f(m1 - mn1);
+    m0 = mn0; m1 = mn1;
+    l0 *= c0; l1 *= c1;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { o[i][0] *= c0; o[i][1] *= c0; o[i][2] *= c1; o[i][3] *= c1; }
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      s[nt][0] = exp2f(s[nt][0] - mn0);
+      s[nt][1] = exp2f(s[nt][1] - mn0);
+      s[nt][2] = exp2f(s[nt][2] - mn1);
+      s[nt][3] = exp2f(s[nt][3] - mn1);
+      l0 += s[nt][0] + s[nt][1];
+      l1 += s[nt][2] + s[nt][3];
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {  // 16 keys per k-step
+      uint32_t pa[4];
+      pa[0] = pack_bf16(s[2 * j][0], s[2 * j][1]);
+      pa[1] = pack_bf16(s[2 * j][2], s[2 * j][3]);
+      pa[2] = pack_bf16(s[2 * j + 1][0], s[2 * j + 1][1]);
+      pa[3] = pack_bf16(s[2 * j + 1][2], s[2 * j + 1][3]);
+#pragma unroll
+      for (int dp = 0; dp < 2; ++dp) {
+        uint32_t vf[4];
+        ldmatrix_x4_trans(vf, &Vs[st][j * 16 + (lane & 7) + ((lane >> 3) & 1) * 8]
+                                 [dp * 16 + (lane >> 4) * 8]);
+        mma_bf16(o[dp * 2], pa, vf[0], vf[1]);
+        mma_bf16(o[dp * 2 + 1], pa, vf[2], vf[3]);
+      }
+    }
+    __syncthreads();
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+  bf16* ob = out + static_cast<long long>(b) * n_q * ld_out + h * 32;
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) {
+    const int c = nt * 8 + cq;
+    if (r0 < n_q)
+      *reinterpret_cast<uint32_t*>(ob + r0 * ld_out + c) = pack_bf16(o[nt][0] * i0, o[nt][1] * i0);
+    if (r1 < n_q)
+      *reinterpret_cast<uint32_t*>(ob + r1 * ld_out + c) = pack_bf16(o[nt][2] * i1, o[nt][3] * i1);
+  }
+}
+
+int launch_flash_mma(const ealdm_attention_args* a, cudaStream_t st) {
+  EALDM_REQUIRE(a->ld_kv % 8 == 0 && a->head_stride_kv % 8 == 0 &&
+                    (reinterpret_cast<uintptr_t>(a->k) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(a->v) & 15) == 0,
+                "attention(mma): K/V need 16-byte aligned rows");
+  EALDM_REQUIRE(a->ld_q % 2 == 0 && a->head_stride_q % 2 == 0 && a->ld_out % 2 == 0,
+                "attention(mma): q/out pitches must be even");
+  const float scale_log2 = a->scale * 1.4426950408889634f;
+  const bf16* q = reinterpret_cast<const bf16*>(a->q);
+  const bf16* k = reinterpret_cast<const bf16*>(a->k);
+  const bf16* v = reinterpret_cast<const bf16*>(a->v);
+  bf16* o = reinterpret_cast<bf16*>(a->out);
+  if (a->n_q > 64) {
+    dim3 grid(static_cast<unsigned>(ceil_div(a->n_q, 128)), static_cast<unsigned>(a->heads),
+              static_cast<unsigned>(a->batch));
+    flash_mma_kernel<8><<<grid, 256, 0, st>>>(q, k, v, a->ld_q, a->ld_kv, a->head_stride_q,
+                                              a->head_stride_kv, (int)a->n_q, (int)a->n_kv,
+                                              scale_log2, o, a->ld_out);
+  } else {
+    dim3 grid(static_cast<unsigned>(ceil_div(a->n_q, 64)), static_cast<unsigned>(a->heads),
+              static_cast<unsigned>(a->batch));
+    flash_mma_kernel<4><<<grid, 128, 0, st>>>(q, k, v, a->ld_q, a->ld_kv, a->head_stride_q,
+                                              a->head_stride_kv, (int)a->n_q, (int)a->n_kv,
+                                              scale_log2, o, a->ld_out);
+  }
+  EALDM_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace attn
+}  // namespace ealdm

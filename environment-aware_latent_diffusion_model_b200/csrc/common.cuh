@@ -1,0 +1,108 @@
+// Shared host/device helpers for libealdm_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <stdarg.h>
+
+#include "../../include/ealdm_b200.h"
+
+namespace ealdm {
+
+// ---- error plumbing (thread-local message, integer codes across the ABI) -----------------------
+int set_error(int code, const char* fmt, ...);
+void count_launch(int n = 1);
+
+#define EALDM_REQUIRE(cond, ...)                                        \
+  do {                                                                  \
+    if (!(cond)) return ::ealdm::set_error(EALDM_EINVAL, __VA_ARGS__);  \
+  } while (0)
+
+#define EALDM_CUDA(expr)                                                                  \
+  do {                                                                                    \
+    cudaError_t _e = (expr);                                                              \
+    if (_e != cudaSuccess)                                                                \
+      return ::ealdm::set_error(EALDM_ECUDA, "%s failed: %s (%s:%d)", #expr,              \
+                                cudaGetErrorString(_e), __FILE__, __LINE__);              \
+  } while (0)
+
+#define EALDM_LAUNCH_CHECK()                                                              \
+  do {                                                                                    \
+    cudaError_t _e = cudaPeekAtLastError();                                               \
+    if (_e != cudaSuccess)                                                                \
+      return ::ealdm::set_error(EALDM_ECUDA, "kernel launch failed: %s (%s:%d)",          \
+                                cudaGetErrorString(_e), __FILE__, __LINE__);              \
+    ::ealdm::count_launch();                                                              \
+  } while (0)
+
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---- element type helpers ----------------------------------------------------------------------
+typedef __nv_bfloat16 bf16;
+
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(bf16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f32<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ float silu_f(float v) { return v / (1.0f + expf(-v)); }
+// exact-erf GELU (F.gelu default), attention.py:44
+__device__ __forceinline__ float gelu_erf_f(float v) {
+  return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
+}
+
+// 4-element vectors of T (16 B for float, 8 B for bf16)
+template <typename T> struct Vec4;
+template <> struct Vec4<float> {
+  float4 v;
+  __device__ __forceinline__ void load(const float* p) { v = *reinterpret_cast<const float4*>(p); }
+  __device__ __forceinline__ void store(float* p) const { *reinterpret_cast<float4*>(p) = v; }
+  __device__ __forceinline__ void get(float (&f)[4]) const { f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w; }
+  __device__ __forceinline__ void set(const float (&f)[4]) { v = make_float4(f[0], f[1], f[2], f[3]); }
+};
+template <> struct Vec4<bf16> {
+  uint2 v;
+  __device__ __forceinline__ void load(const bf16* p) { v = *reinterpret_cast<const uint2*>(p); }
+  __device__ __forceinline__ void store(bf16* p) const { *reinterpret_cast<uint2*>(p) = v; }
+  __device__ __forceinline__ void get(float (&f)[4]) const {
+    __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&v.x);
+    __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&v.y);
+    f[0] = __low2float(a); f[1] = __high2float(a); f[2] = __low2float(b); f[3] = __high2float(b);
+  }
+  __device__ __forceinline__ void set(const float (&f)[4]) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(f[0], f[1]);
+    __nv_bfloat162 b = __floats2bfloat162_rn(f[2], f[3]);
+    v.x = *reinterpret_cast<uint32_t*>(&a);
+    v.y = *reinterpret_cast<uint32_t*>(&b);
+  }
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ---- epilogue shared by the SIMT and tcgen05 implicit-GEMM kernels ------------------------------
+struct Epilogue {
+  const float* bias;
+  const float* rowvec;
+  long long ld_rowvec;
+  long long rows_per_image;
+  const void* residual;
+  long long ld_res;
+  void* out;
+  long long ld_out;
+  int act;
+  int out_f32;
+};
+
+}  // namespace ealdm

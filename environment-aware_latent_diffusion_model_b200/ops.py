@@ -1,0 +1,277 @@
+"""Torch-tensor front end of the C ABI: every function here is a thin argument marshaller around one
+`ealdm_*` entry point of libealdm_b200.so.  PyTorch only provides device memory and the stream."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib as L
+
+
+def _dt(t: torch.dtype) -> int:
+    if t == torch.float32:
+        return L.F32
+    if t == torch.bfloat16:
+        return L.BF16
+    raise TypeError(f"unsupported dtype {t}")
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+class Act:
+    """An NHWC activation: `c` channels starting at column `c0` of a 2-D [n*h*w, ld] buffer."""
+    __slots__ = ("buf", "n", "h", "w", "c", "c0")
+
+    def __init__(self, buf: torch.Tensor, n: int, h: int, w: int, c: Optional[int] = None, c0: int = 0):
+        assert buf.dim() == 2 and buf.is_contiguous() and buf.shape[0] == n * h * w, \
+            (tuple(buf.shape), n, h, w)
+        self.buf, self.n, self.h, self.w = buf, n, h, w
+        self.c0 = c0
+        self.c = buf.shape[1] - c0 if c is None else c
+        assert self.c0 + self.c <= buf.shape[1]
+
+    @staticmethod
+    def empty(n, h, w, c, dtype, device) -> "Act":
+        return Act(torch.empty((n * h * w, c), dtype=dtype, device=device), n, h, w)
+
+    @property
+    def ld(self) -> int:
+        return self.buf.shape[1]
+
+    @property
+    def rows(self) -> int:
+        return self.n * self.h * self.w
+
+    @property
+    def ptr(self) -> int:
+        return self.buf.data_ptr() + self.c0 * self.buf.element_size()
+
+    @property
+    def dtype(self) -> torch.dtype:
+        return self.buf.dtype
+
+    def cols(self, c0: int, c: int) -> "Act":
+        return Act(self.buf, self.n, self.h, self.w, c, self.c0 + c0)
+
+    def reshape(self, n, h, w) -> "Act":
+        assert n * h * w == self.rows
+        return Act(self.buf, n, h, w, self.c, self.c0)
+
+    def view2d(self) -> torch.Tensor:
+        return self.buf[:, self.c0:self.c0 + self.c]
+
+
+class ConvIn:
+    """One source of an implicit-GEMM convolution."""
+    __slots__ = ("x", "ksize", "stride", "pad", "upsample")
+
+    def __init__(self, x: Act, ksize=1, stride=1, pad=0, upsample=0):
+        self.x, self.ksize, self.stride, self.pad, self.upsample = x, ksize, stride, pad, upsample
+
+
+def conv(srcs: Sequence[ConvIn], weight: torch.Tensor, out: Act, *, bias: Optional[torch.Tensor] = None,
+         rowvec: Optional[torch.Tensor] = None, rowvec_col0: int = 0, residual: Optional[Act] = None,
+         act: int = L.ACT_NONE, impl: int = L.IMPL_AUTO) -> Act:
+    """ealdm_conv: out = epilogue(sum_s im2col(src_s) @ weight[:, seg_s]^T). `weight` is [n_out, k_total]."""
+    lib = L.load()
+    a = L.ConvArgs()
+    x0 = srcs[0].x
+    a.dtype = _dt(x0.dtype)
+    a.impl = impl
+    a.n_src = len(srcs)
+    a.act = act
+    for i, s in enumerate(srcs):
+        d = a.src[i]
+        d.x, d.n, d.h, d.w, d.c, d.ld = s.x.ptr, s.x.n, s.x.h, s.x.w, s.x.c, s.x.ld
+        d.ksize, d.stride, d.pad, d.upsample = s.ksize, s.stride, s.pad, s.upsample
+        assert s.x.dtype == x0.dtype
+    assert weight.dim() == 2 and weight.is_contiguous() and weight.dtype == x0.dtype
+    a.weight = weight.data_ptr()
+    a.n_out, a.k_total = weight.shape
+    a.h_out, a.w_out = out.h, out.w
+    assert out.n == x0.n
+    n_cols = weight.shape[0] // 2 if act == L.ACT_GEGLU else weight.shape[0]
+    assert out.c == n_cols, (out.c, n_cols)
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.numel() == weight.shape[0]
+        a.bias = bias.data_ptr()
+    if rowvec is not None:
+        assert rowvec.dtype == torch.float32 and rowvec.dim() == 2 and rowvec.shape[0] == x0.n
+        a.rowvec = rowvec.data_ptr() + 4 * rowvec_col0
+        a.ld_rowvec = rowvec.shape[1]
+    if residual is not None:
+        assert residual.dtype == x0.dtype and residual.rows == out.rows and residual.c == out.c
+        a.residual = residual.ptr
+        a.ld_res = residual.ld
+    a.out = out.ptr
+    a.ld_out = out.ld
+    a.out_f32 = 1 if (out.dtype == torch.float32 and x0.dtype != torch.float32) else 0
+    if not a.out_f32:
+        assert out.dtype == x0.dtype
+    L.check(lib.ealdm_conv(C.byref(a), _stream()))
+    return out
+
+
+def linear(x: Act, weight: torch.Tensor, out: Act, **kw) -> Act:
+    """nn.Linear over the rows of x (a 1x1 'convolution' with n=1, h=1, w=rows)."""
+    xs = Act(x.buf, 1, 1, x.rows, x.c, x.c0)
+    os_ = Act(out.buf, 1, 1, out.rows, out.c, out.c0)
+    res = kw.pop("residual", None)
+    if res is not None:
+        res = Act(res.buf, 1, 1, res.rows, res.c, res.c0)
+    conv([ConvIn(xs)], weight, os_, residual=res, **kw)
+    return out
+
+
+def group_norm(x: Act, gamma: torch.Tensor, beta: torch.Tensor, eps: float, out: Act, stats: torch.Tensor,
+               *, groups: int = 32, silu: bool = False) -> Act:
+    lib = L.load()
+    a = L.GroupNormArgs()
+    a.dtype = _dt(x.dtype)
+    a.act = L.ACT_SILU if silu else L.ACT_NONE
+    a.x, a.n, a.hw, a.c, a.ld_x = x.ptr, x.n, x.h * x.w, x.c, x.ld
+    a.groups, a.eps = groups, eps
+    assert gamma.dtype == torch.float32 and beta.dtype == torch.float32 and gamma.numel() == x.c
+    a.gamma, a.beta = gamma.data_ptr(), beta.data_ptr()
+    assert out.dtype == x.dtype and out.rows == x.rows and out.c == x.c
+    a.y, a.ld_y = out.ptr, out.ld
+    assert stats.dtype == torch.float64 and stats.numel() >= x.n * groups * 2
+    a.stats = stats.data_ptr()
+    L.check(lib.ealdm_group_norm(C.byref(a), _stream()))
+    return out
+
+
+def layer_norm(x: Act, gamma: torch.Tensor, beta: torch.Tensor, eps: float, out: Act) -> Act:
+    lib = L.load()
+    a = L.LayerNormArgs()
+    a.dtype = _dt(x.dtype)
+    a.x, a.rows, a.c, a.ld_x, a.eps = x.ptr, x.rows, x.c, x.ld, eps
+    assert gamma.dtype == torch.float32 and gamma.numel() == x.c
+    a.gamma, a.beta = gamma.data_ptr(), beta.data_ptr()
+    assert out.dtype == x.dtype and out.rows == x.rows and out.c == x.c
+    a.y, a.ld_y = out.ptr, out.ld
+    L.check(lib.ealdm_layer_norm(C.byref(a), _stream()))
+    return out
+
+
+def attention(q: Act, k: Act, v: Act, out: Act, *, batch: int, heads: int, head_dim: int, n_q: int,
+              n_kv: int, scale: float, head_stride_q: Optional[int] = None,
+              head_stride_kv: Optional[int] = None, impl: int = L.IMPL_AUTO) -> Act:
+    """q/k/v are column windows into [batch*n, ld] buffers; head h of q starts at column h*head_stride_q."""
+    lib = L.load()
+    a = L.AttentionArgs()
+    a.dtype = _dt(q.dtype)
+    a.impl = impl
+    a.q, a.k, a.v = q.ptr, k.ptr, v.ptr
+    assert k.ld == v.ld and q.rows == batch * n_q and k.rows == batch * n_kv
+    a.ld_q, a.ld_kv = q.ld, k.ld
+    a.head_stride_q = head_dim if head_stride_q is None else head_stride_q
+    a.head_stride_kv = head_dim if head_stride_kv is None else head_stride_kv
+    a.batch, a.heads, a.n_q, a.n_kv, a.head_dim = batch, heads, n_q, n_kv, head_dim
+    a.scale = scale
+    assert out.rows == q.rows and out.c == heads * head_dim and out.dtype == q.dtype
+    a.out, a.ld_out = out.ptr, out.ld
+    L.check(lib.ealdm_attention(C.byref(a), _stream()))
+    return out
+
+
+def timestep_embedding(t: torch.Tensor, dim: int, freqs: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    lib = L.load()
+    assert t.dtype == torch.int64 and t.is_contiguous() and freqs.dtype == torch.float32
+    assert out.is_contiguous() and tuple(out.shape) == (t.numel(), dim)
+    L.check(lib.ealdm_timestep_embedding(t.data_ptr(), t.numel(), dim, freqs.data_ptr(), _dt(out.dtype),
+                                         out.data_ptr(), _stream()))
+    return out
+
+
+def nchw_to_nhwc(x: torch.Tensor, out: Act) -> Act:
+    lib = L.load()
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 4
+    n, c, h, w = x.shape
+    assert (out.n, out.h, out.w, out.c) == (n, h, w, c)
+    L.check(lib.ealdm_nchw_to_nhwc(x.data_ptr(), n, c, h, w, _dt(out.dtype), out.ptr, out.ld, _stream()))
+    return out
+
+
+def nhwc_to_nchw(x: Act, out: torch.Tensor) -> torch.Tensor:
+    lib = L.load()
+    assert out.dtype == torch.float32 and out.is_contiguous()
+    assert tuple(out.shape) == (x.n, x.c, x.h, x.w)
+    L.check(lib.ealdm_nhwc_to_nchw(x.ptr, x.ld, _dt(x.dtype), x.n, x.c, x.h, x.w, out.data_ptr(), _stream()))
+    return out
+
+
+def upsample_nearest2x(x: Act, out: Act) -> Act:
+    lib = L.load()
+    assert (out.n, out.h, out.w, out.c) == (x.n, 2 * x.h, 2 * x.w, x.c) and out.dtype == x.dtype
+    L.check(lib.ealdm_upsample_nearest2x(x.ptr, x.ld, _dt(x.dtype), x.n, x.h, x.w, x.c, out.ptr, out.ld,
+                                         _stream()))
+    return out
+
+
+def copy2d(x: Act, out: Act) -> Act:
+    lib = L.load()
+    assert x.rows == out.rows and x.c == out.c
+    L.check(lib.ealdm_copy2d(x.ptr, x.ld, _dt(x.dtype), out.ptr, out.ld, _dt(out.dtype), x.rows, x.c,
+                             _stream()))
+    return out
+
+
+def softmax_rows_(x: Act, scale: float) -> Act:
+    lib = L.load()
+    L.check(lib.ealdm_softmax_rows(x.ptr, x.ld, _dt(x.dtype), x.rows, x.c, scale, _stream()))
+    return x
+
+
+def ddim_step(x, e_cond, *, e_uncond=None, noise=None, cfg_scale=1.0, sqrt_one_minus_at, sqrt_at,
+              sqrt_a_prev, dir_coef, sigma_t, temperature=1.0, want_e=False):
+    """ealdm_ddim_step on contiguous fp32 tensors; returns (x_prev, pred_x0[, e])."""
+    lib = L.load()
+    for t in (x, e_cond, e_uncond, noise):
+        assert t is None or (t.dtype == torch.float32 and t.is_contiguous() and t.numel() == x.numel())
+    x_prev = torch.empty_like(x)
+    pred = torch.empty_like(x)
+    e = torch.empty_like(x) if want_e else None
+    a = L.DdimStepArgs()
+    a.x, a.e_uncond, a.e_cond, a.noise = _ptr(x), _ptr(e_uncond), _ptr(e_cond), _ptr(noise)
+    a.x_prev, a.pred_x0, a.e_out = _ptr(x_prev), _ptr(pred), _ptr(e)
+    a.numel = x.numel()
+    a.cfg_scale = cfg_scale
+    a.sqrt_one_minus_at, a.sqrt_at, a.sqrt_a_prev = sqrt_one_minus_at, sqrt_at, sqrt_a_prev
+    a.dir_coef, a.sigma_t, a.temperature = dir_coef, sigma_t, temperature
+    L.check(lib.ealdm_ddim_step(C.byref(a), _stream()))
+    return (x_prev, pred, e) if want_e else (x_prev, pred)
+
+
+def q_sample(x0, noise, t, sqrt_ac, sqrt_1mac):
+    lib = L.load()
+    assert x0.dtype == torch.float32 and x0.is_contiguous() and noise.is_contiguous()
+    assert t.dtype == torch.int64 and sqrt_ac.dtype == torch.float32 and sqrt_1mac.dtype == torch.float32
+    out = torch.empty_like(x0)
+    b = x0.shape[0]
+    L.check(lib.ealdm_q_sample(x0.data_ptr(), noise.data_ptr(), t.data_ptr(), sqrt_ac.data_ptr(),
+                               sqrt_1mac.data_ptr(), b, x0.numel() // b, out.data_ptr(), _stream()))
+    return out
+
+
+def cfg_mse(e_cond, target, *, e_uncond=None, cfg_scale=1.0):
+    lib = L.load()
+    for t in (e_cond, target, e_uncond):
+        assert t is None or (t.dtype == torch.float32 and t.is_contiguous())
+    b = e_cond.shape[0]
+    out = torch.empty((b,), dtype=torch.float32, device=e_cond.device)
+    L.check(lib.ealdm_cfg_mse(_ptr(e_uncond), e_cond.data_ptr(), target.data_ptr(), cfg_scale, b,
+                              e_cond.numel() // b, out.data_ptr(), _stream()))
+    return out
+
+
+def launch_count() -> int:
+    return int(L.load().ealdm_launch_count())

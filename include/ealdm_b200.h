@@ -1,0 +1,242 @@
+/*
+ * ealdm_b200.h -- C ABI of libealdm_b200.so: hand-written sm_100a kernels for the
+ * latent-diffusion denoising hot path of EALDM
+ * (NasrinKalanat/Environment-Aware_Latent_Diffusion_Model).
+ *
+ * The reference has no FFI for this path: every operator below is, in the reference, a chain of
+ * eager PyTorch ATen calls inside an nn.Module.forward.  Each entry point cites the reference
+ * file:line whose arithmetic it replaces (paths relative to the reference repository root).
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no torch / C++ types cross this boundary;
+ *  - every pointer is a DEVICE pointer unless the parameter name ends in `_host`;
+ *  - activations are NHWC ("channels-last"): element (n,h,w,c) of a tensor with row pitch `ld`
+ *    (elements between consecutive pixels, ld >= c) lives at ((n*H+h)*W+w)*ld + c.  A channel
+ *    concatenation is therefore two producers writing disjoint column ranges of one buffer;
+ *  - `dtype` selects the storage type of activations and weights: EALDM_F32 (parity mode, FFMA
+ *    kernels) or EALDM_BF16 (tcgen05 tensor-core kernels, fp32 accumulation).  Biases, norm
+ *    affine parameters, per-image row vectors and statistics are always fp32/fp64;
+ *  - nothing is allocated or freed inside the library; workspaces are passed in;
+ *  - every function is asynchronous on `stream` (a cudaStream_t), re-entrant per stream, and
+ *    returns 0 on success or a negative EALDM_E* code; ealdm_last_error() returns the message of
+ *    the last failure on the calling thread.
+ */
+#ifndef EALDM_B200_H
+#define EALDM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EALDM_ABI_VERSION 1
+
+typedef void* ealdm_stream_t; /* cudaStream_t */
+
+enum { EALDM_F32 = 0, EALDM_BF16 = 1 };
+enum { EALDM_ACT_NONE = 0, EALDM_ACT_SILU = 1, EALDM_ACT_GEGLU = 2 };
+enum { EALDM_IMPL_AUTO = 0, EALDM_IMPL_SIMT = 1, EALDM_IMPL_TCGEN05 = 2 };
+enum {
+  EALDM_OK = 0,
+  EALDM_EINVAL = -1,   /* bad argument (shape, alignment, unsupported combination) */
+  EALDM_ECUDA = -2,    /* CUDA runtime / driver error */
+  EALDM_EUNSUPPORTED = -3
+};
+
+/* ---- library ------------------------------------------------------------------------------ */
+int ealdm_abi_version(void);
+const char* ealdm_last_error(void);
+/* 0 if the current device is compute capability 10.x (sm_100a code is loadable), else <0. */
+int ealdm_device_check(void);
+/* number of kernel launches issued through this library by the calling process so far */
+int64_t ealdm_launch_count(void);
+
+/* ---- convolution / linear as implicit GEMM ------------------------------------------------- */
+/*
+ * out[m, j] = epilogue( sum_s sum_{kh,kw,c} src_s[n, oh*stride+kh-pad, ow*stride+kw-pad, c]
+ *                                   * weight[j, koff_s + (kh*ksize+kw)*c_s + c] )
+ * with m = (n*h_out+oh)*w_out+ow.  Out-of-range taps read zero.  `upsample` = 1 reads the source
+ * through a nearest-neighbour 2x upsampling (reference: F.interpolate(scale_factor=2)).
+ * Up to two sources are accumulated into one output (a 3x3 conv plus the 1x1 skip conv of a
+ * ResBlock); their weights are concatenated along K in `weight`.
+ * A Linear layer is the case n=1, h=1, w=rows, ksize=1.
+ *
+ * epilogue: v = acc + bias[j] + rowvec[n*ld_rowvec + j]; v = act(v); v += residual[m*ld_res+j];
+ * act == GEGLU: weight rows are pre-interleaved in blocks of 32 (16 value rows then their 16 gate
+ * rows); the output has n_out/2 columns: value * gelu_erf(gate).
+ *
+ * Replaces: nn.Conv2d / nn.Linear and the elementwise ops around them in
+ *   ldm/modules/diffusionmodules/openaimodel.py:255-275 (ResBlock._forward), :109-119, :158-160
+ *   ldm/modules/attention.py:37-64 (GEGLU / FeedForward), :170-193 (to_q/k/v/out), :250-261
+ *   ldm/modules/diffusionmodules/model.py:42-79, :116-141, :175-202
+ */
+typedef struct {
+  const void* x;
+  int64_t n, h, w, c;
+  int64_t ld;
+  int32_t ksize;    /* 1 or 3 */
+  int32_t stride;   /* 1 or 2 */
+  int32_t pad;      /* zero padding on the top/left edge (bottom/right is implied by h_out/w_out) */
+  int32_t upsample; /* 0 or 1 */
+} ealdm_conv_src;
+
+typedef struct {
+  int32_t dtype;
+  int32_t impl;
+  int32_t n_src;
+  int32_t act;
+  ealdm_conv_src src[2];
+  const void* weight; /* [n_out, k_total], row-major, `dtype` */
+  int64_t n_out;
+  int64_t k_total;
+  int64_t h_out, w_out;
+  const float* bias;   /* [n_out] or NULL */
+  const float* rowvec; /* [n, ld_rowvec] or NULL */
+  int64_t ld_rowvec;
+  const void* residual; /* [M, ld_res] `dtype`, or NULL */
+  int64_t ld_res;
+  void* out;
+  int64_t ld_out;
+  int32_t out_f32; /* 1: `out` is float regardless of dtype */
+  int32_t reserved;
+} ealdm_conv_args;
+
+int ealdm_conv(const ealdm_conv_args* a, ealdm_stream_t stream);
+
+/* ---- normalisation -------------------------------------------------------------------------- */
+/*
+ * GroupNorm over (c/groups, hw) per image with biased variance, affine, optional SiLU.
+ * `stats` is a caller-provided workspace of n*groups*2 doubles (sum, sum of squares); the call
+ * zeroes it, accumulates it and consumes it.
+ * Replaces: GroupNorm32 + SiLU, ldm/modules/diffusionmodules/util.py:214-216,
+ *   openaimodel.py:201-205,225-232,682-686; Normalize (eps 1e-6) attention.py:76-77, model.py:38-39.
+ */
+typedef struct {
+  int32_t dtype;
+  int32_t act; /* EALDM_ACT_NONE or EALDM_ACT_SILU */
+  const void* x;
+  int64_t n, hw, c, ld_x;
+  int32_t groups;
+  float eps;
+  const float* gamma;
+  const float* beta;
+  void* y;
+  int64_t ld_y;
+  double* stats;
+} ealdm_group_norm_args;
+
+int ealdm_group_norm(const ealdm_group_norm_args* a, ealdm_stream_t stream);
+
+/* LayerNorm over the last dimension. Replaces nn.LayerNorm in attention.py:203-205,211-215. */
+typedef struct {
+  int32_t dtype;
+  int32_t reserved;
+  const void* x;
+  int64_t rows, c, ld_x;
+  float eps;
+  int32_t reserved2;
+  const float* gamma;
+  const float* beta;
+  void* y;
+  int64_t ld_y;
+} ealdm_layer_norm_args;
+
+int ealdm_layer_norm(const ealdm_layer_norm_args* a, ealdm_stream_t stream);
+
+/* ---- attention -------------------------------------------------------------------------------- */
+/*
+ * out[b,i,h,:] = softmax_j(scale * q[b,i,h,:].k[b,j,h,:]) . v[b,j,h,:]
+ * element (b,i,h,d) of q is at q[(b*n_q+i)*ld_q + h*head_stride_q + d]; k and v likewise with
+ * ld_kv / head_stride_kv; out is [(b*n_q+i)*ld_out + h*head_dim + d].
+ * Replaces: CrossAttention.forward attention.py:170-193 (self- and cross-attention),
+ *   QKVAttentionLegacy.forward openaimodel.py:356-372, AttnBlock model.py:175-199.
+ */
+typedef struct {
+  int32_t dtype;
+  int32_t impl;
+  const void* q;
+  const void* k;
+  const void* v;
+  int64_t ld_q, ld_kv;
+  int64_t head_stride_q, head_stride_kv;
+  int64_t batch, heads, n_q, n_kv, head_dim;
+  float scale;
+  int32_t reserved;
+  void* out;
+  int64_t ld_out;
+} ealdm_attention_args;
+
+int ealdm_attention(const ealdm_attention_args* a, ealdm_stream_t stream);
+
+/* ---- timestep embedding, layout ---------------------------------------------------------------- */
+/*
+ * out[i, :] = [cos(t_i*f) | sin(t_i*f)] with f = freqs[0:dim/2] (device, fp32), util.py:151-171.
+ * The host computes freqs = exp(-ln(max_period)*arange(half)/half) once, exactly as the reference
+ * does, so that the arguments t*f are bit-identical to the reference's.  out is [n, dim] `dtype`.
+ */
+int ealdm_timestep_embedding(const int64_t* t, int64_t n, int32_t dim, const float* freqs,
+                             int32_t dtype, void* out, ealdm_stream_t stream);
+
+/* fp32 NCHW <-> `dtype` NHWC (pitch ld).  The reference keeps NCHW fp32 at every module boundary. */
+int ealdm_nchw_to_nhwc(const float* x, int64_t n, int64_t c, int64_t h, int64_t w, int32_t dtype,
+                       void* y, int64_t ld_y, ealdm_stream_t stream);
+int ealdm_nhwc_to_nchw(const void* x, int64_t ld_x, int32_t dtype, int64_t n, int64_t c, int64_t h,
+                       int64_t w, float* y, ealdm_stream_t stream);
+/* nearest-neighbour 2x upsampling NHWC -> NHWC (openaimodel.py:116, model.py:54) */
+int ealdm_upsample_nearest2x(const void* x, int64_t ld_x, int32_t dtype, int64_t n, int64_t h,
+                             int64_t w, int64_t c, void* y, int64_t ld_y, ealdm_stream_t stream);
+/* strided 2-D copy / cast between dtypes: y[r, 0:c] = x[r, 0:c] */
+int ealdm_copy2d(const void* x, int64_t ld_x, int32_t dtype_x, void* y, int64_t ld_y,
+                 int32_t dtype_y, int64_t rows, int64_t c, ealdm_stream_t stream);
+/* row softmax in place over [rows, c] (pitch ld) after multiplying by `scale` (model.py:190-192) */
+int ealdm_softmax_rows(void* x, int64_t ld, int32_t dtype, int64_t rows, int64_t c, float scale,
+                       ealdm_stream_t stream);
+
+/* ---- sampler / diffusion elementwise (fp32, bit-exact with the reference's op sequence) -------- */
+/*
+ * DDIMSampler.p_sample_ddim, ldm/models/diffusion/ddim.py:173-203, on fp32 tensors of `numel`
+ * elements:
+ *   e      = e_uncond ? e_uncond + cfg_scale*(e_cond - e_uncond) : e_cond
+ *   pred   = (x - sqrt_one_minus_at*e) / sqrt_at
+ *   x_prev = sqrt_a_prev*pred + dir_coef*e + (sigma_t*noise)*temperature
+ * The scalars are computed by the host exactly as the reference does (fp32 torch.full tensors).
+ * noise may be NULL only when sigma_t == 0.  e_out (optional) receives the guided eps.
+ */
+typedef struct {
+  const float* x;
+  const float* e_uncond;
+  const float* e_cond;
+  const float* noise;
+  float* x_prev;
+  float* pred_x0;
+  float* e_out;
+  int64_t numel;
+  float cfg_scale;
+  float sqrt_one_minus_at;
+  float sqrt_at;
+  float sqrt_a_prev;
+  float dir_coef;
+  float sigma_t;
+  float temperature;
+  int32_t reserved;
+} ealdm_ddim_step_args;
+
+int ealdm_ddim_step(const ealdm_ddim_step_args* a, ealdm_stream_t stream);
+
+/* DDPM.q_sample, ldm/models/diffusion/ddpm.py:276-279: out = sa[t[b]]*x0 + s1a[t[b]]*noise */
+int ealdm_q_sample(const float* x0, const float* noise, const int64_t* t,
+                   const float* sqrt_alphas_cumprod, const float* sqrt_one_minus_alphas_cumprod,
+                   int64_t batch, int64_t per_sample, float* out, ealdm_stream_t stream);
+
+/*
+ * LatentDiffusion.p_losses tail, ddpm.py:1040-1060: guided = e_uncond + s*(e_cond-e_uncond)
+ * (or e_cond if e_uncond is NULL); loss_simple[b] = mean((guided - target)^2) over the sample.
+ */
+int ealdm_cfg_mse(const float* e_uncond, const float* e_cond, const float* target, float cfg_scale,
+                  int64_t batch, int64_t per_sample, float* loss_simple, ealdm_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EALDM_B200_H */

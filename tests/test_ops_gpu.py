@@ -1,0 +1,344 @@
+"""Parity of every C-ABI operator against plain PyTorch fp32 on the same seeded inputs (GPU tests).
+
+Tolerances: fp32 kernels 2e-5 relative L2 (summation order only); bf16 tensor-core kernels are
+compared with the fp32 result computed from the SAME bf16-rounded inputs, 1e-2 relative L2 / output
+rounding; the sampler kernels are bit-exact.
+"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from ealdm_b200 import _lib as L  # noqa: E402
+from ealdm_b200 import ops  # noqa: E402
+from ealdm_b200.ops import Act, ConvIn  # noqa: E402
+
+DEV = "cuda"
+
+
+def rel_l2(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def to_act(x_nchw, dtype, ld=None, c0=0):
+    n, c, h, w = x_nchw.shape
+    ld = ld or c
+    buf = torch.zeros((n * h * w, ld), dtype=dtype, device=DEV)
+    buf[:, c0:c0 + c] = x_nchw.permute(0, 2, 3, 1).reshape(-1, c).to(dtype)
+    return Act(buf, n, h, w, c, c0)
+
+
+def from_act(a: Act):
+    return a.view2d().float().reshape(a.n, a.h, a.w, a.c).permute(0, 3, 1, 2).contiguous()
+
+
+def pack_w(w, dtype):  # [O, I, kh, kw] -> [O, kh*kw*I]
+    return w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).contiguous().to(dtype)
+
+
+def g(seed):
+    return torch.Generator(device="cpu").manual_seed(seed)
+
+
+def test_library_and_device():
+    lib = L.load()
+    assert lib.ealdm_abi_version() == 1
+    assert lib.ealdm_device_check() == 0, lib.ealdm_last_error()
+
+
+@pytest.mark.parametrize("dtype,impl", [(torch.float32, L.IMPL_SIMT), (torch.bfloat16, L.IMPL_SIMT),
+                                        (torch.bfloat16, L.IMPL_TCGEN05)])
+@pytest.mark.parametrize("M,K,N", [(256, 256, 256), (300, 512, 384), (128, 1024, 1024), (77, 64, 40),
+                                   (1024, 256, 2048)])
+def test_linear(dtype, impl, M, K, N):
+    if impl == L.IMPL_TCGEN05 and N % 8:
+        pytest.skip("ld_out alignment")
+    x = torch.randn(M, K, generator=g(1)).to(DEV)
+    w = (torch.randn(N, K, generator=g(2)) / math.sqrt(K)).to(DEV)
+    b = torch.randn(N, generator=g(3)).to(DEV)
+    r = torch.randn(M, N, generator=g(4)).to(DEV)
+    xa = Act(x.to(dtype).contiguous(), 1, 1, M)
+    ra = Act(r.to(dtype).contiguous(), 1, 1, M)
+    out = Act.empty(1, 1, M, N, dtype, DEV)
+    ops.linear(xa, w.to(dtype).contiguous(), out, bias=b, residual=ra, impl=impl)
+    ref = F.linear(xa.buf.float(), w.to(dtype).float(), b) + ra.buf.float()
+    tol = 2e-5 if dtype == torch.float32 else 6e-3
+    assert rel_l2(out.buf.float(), ref) < tol
+
+
+@pytest.mark.parametrize("dtype,impl", [(torch.float32, L.IMPL_SIMT), (torch.bfloat16, L.IMPL_TCGEN05)])
+@pytest.mark.parametrize("n,c,h,w,co", [(2, 64, 32, 32, 128), (3, 128, 16, 16, 256), (5, 256, 8, 8, 64),
+                                        (1, 64, 64, 64, 32), (2, 192, 8, 8, 4)])
+def test_conv3x3_bias_rowvec(dtype, impl, n, c, h, w, co):
+    if impl == L.IMPL_TCGEN05 and co % 8:
+        pytest.skip("ld_out alignment handled by the host (padded out buffer)")
+    x = torch.randn(n, c, h, w, generator=g(5)).to(DEV)
+    wt = (torch.randn(co, c, 3, 3, generator=g(6)) / math.sqrt(9 * c)).to(DEV)
+    b = torch.randn(co, generator=g(7)).to(DEV)
+    emb = torch.randn(n, co + 16, generator=g(8)).to(DEV)  # rowvec with a column offset
+    xa = to_act(x, dtype, ld=c + 8, c0=8)  # exercises pitch != channels
+    out = Act.empty(n, h, w, co, dtype, DEV)
+    ops.conv([ConvIn(xa, 3, 1, 1)], pack_w(wt, dtype), out, bias=b, rowvec=emb, rowvec_col0=16, impl=impl)
+    xr = from_act(xa)
+    ref = F.conv2d(xr, wt.to(dtype).float(), b, padding=1) + emb[:, 16:, None, None]
+    tol = 2e-5 if dtype == torch.float32 else 6e-3
+    assert rel_l2(from_act(out), ref) < tol
+
+
+@pytest.mark.parametrize("dtype,impl", [(torch.float32, L.IMPL_SIMT), (torch.bfloat16, L.IMPL_SIMT),
+                                        (torch.bfloat16, L.IMPL_TCGEN05)])
+@pytest.mark.parametrize("pad", [1, 0])
+def test_conv3x3_stride2(dtype, impl, pad):
+    # pad=1: UNet Downsample (openaimodel.py:151); pad=0 with implicit bottom/right zero pad:
+    # autoencoder Downsample, F.pad(x,(0,1,0,1)) + conv s2 p0 (model.py:74-76)
+    n, c, h, w, co = 3, 128, 16, 16, 128
+    x = torch.randn(n, c, h, w, generator=g(9)).to(DEV)
+    wt = (torch.randn(co, c, 3, 3, generator=g(10)) / math.sqrt(9 * c)).to(DEV)
+    b = torch.randn(co, generator=g(11)).to(DEV)
+    xa = to_act(x, dtype)
+    out = Act.empty(n, h // 2, w // 2, co, dtype, DEV)
+    ops.conv([ConvIn(xa, 3, 2, pad)], pack_w(wt, dtype), out, bias=b, impl=impl)
+    xr = from_act(xa)
+    if pad == 1:
+        ref = F.conv2d(xr, wt.to(dtype).float(), b, stride=2, padding=1)
+    else:
+        ref = F.conv2d(F.pad(xr, (0, 1, 0, 1)), wt.to(dtype).float(), b, stride=2, padding=0)
+    tol = 2e-5 if dtype == torch.float32 else 6e-3
+    assert rel_l2(from_act(out), ref) < tol
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_conv3x3_upsample_simt(dtype):
+    n, c, h, w, co = 2, 64, 8, 8, 64
+    x = torch.randn(n, c, h, w, generator=g(12)).to(DEV)
+    wt = (torch.randn(co, c, 3, 3, generator=g(13)) / math.sqrt(9 * c)).to(DEV)
+    xa = to_act(x, dtype)
+    out = Act.empty(n, 2 * h, 2 * w, co, dtype, DEV)
+    ops.conv([ConvIn(xa, 3, 1, 1, upsample=1)], pack_w(wt, dtype), out, impl=L.IMPL_SIMT)
+    ref = F.conv2d(F.interpolate(from_act(xa), scale_factor=2, mode="nearest"), wt.to(dtype).float(), padding=1)
+    tol = 2e-5 if dtype == torch.float32 else 6e-3
+    assert rel_l2(from_act(out), ref) < tol
+    up = Act.empty(n, 2 * h, 2 * w, c, dtype, DEV)
+    ops.upsample_nearest2x(xa, up)
+    assert torch.equal(from_act(up), F.interpolate(from_act(xa), scale_factor=2, mode="nearest"))
+
+
+@pytest.mark.parametrize("dtype,impl", [(torch.float32, L.IMPL_SIMT), (torch.bfloat16, L.IMPL_TCGEN05)])
+def test_conv_two_sources_skip_fused(dtype, impl):
+    # ResBlock tail: conv3x3(h) + conv1x1(x) + biases in ONE accumulator (openaimodel.py:275)
+    n, c1, c2, h, w, co = 2, 128, 192, 16, 16, 128
+    hh = torch.randn(n, c1, h, w, generator=g(14)).to(DEV)
+    x = torch.randn(n, c2, h, w, generator=g(15)).to(DEV)
+    w3 = (torch.randn(co, c1, 3, 3, generator=g(16)) / math.sqrt(9 * c1)).to(DEV)
+    w1 = (torch.randn(co, c2, 1, 1, generator=g(17)) / math.sqrt(c2)).to(DEV)
+    b = torch.randn(co, generator=g(18)).to(DEV)
+    ha, xa = to_act(hh, dtype), to_act(x, dtype)
+    wcat = torch.cat([pack_w(w3, dtype), pack_w(w1, dtype)], dim=1).contiguous()
+    out = Act.empty(n, h, w, co, dtype, DEV)
+    ops.conv([ConvIn(ha, 3, 1, 1), ConvIn(xa, 1, 1, 0)], wcat, out, bias=b, impl=impl)
+    ref = F.conv2d(from_act(ha), w3.to(dtype).float(), b, padding=1) + F.conv2d(from_act(xa), w1.to(dtype).float())
+    tol = 2e-5 if dtype == torch.float32 else 6e-3
+    assert rel_l2(from_act(out), ref) < tol
+
+
+@pytest.mark.parametrize("dtype,impl", [(torch.float32, L.IMPL_SIMT), (torch.bfloat16, L.IMPL_SIMT),
+                                        (torch.bfloat16, L.IMPL_TCGEN05)])
+def test_geglu_linear(dtype, impl):
+    from ealdm_b200.packing import geglu_interleave
+    M, C = 384, 256
+    x = torch.randn(M, C, generator=g(19)).to(DEV)
+    w = (torch.randn(8 * C, C, generator=g(20)) / math.sqrt(C)).to(DEV)
+    b = torch.randn(8 * C, generator=g(21)).to(DEV)
+    xa = Act(x.to(dtype).contiguous(), 1, 1, M)
+    wp, bp = geglu_interleave(w.to(dtype), b)
+    out = Act.empty(1, 1, M, 4 * C, dtype, DEV)
+    ops.linear(xa, wp, out, bias=bp, act=L.ACT_GEGLU, impl=impl)
+    y = F.linear(xa.buf.float(), w.to(dtype).float(), b)
+    val, gate = y.chunk(2, dim=-1)
+    ref = val * F.gelu(gate)
+    tol = 2e-5 if dtype == torch.float32 else 6e-3
+    assert rel_l2(out.buf.float(), ref) < tol
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_silu_epilogue_and_f32_out(dtype):
+    M, K, N = 128, 256, 1024
+    x = torch.randn(M, K, generator=g(22)).to(DEV)
+    w = (torch.randn(N, K, generator=g(23)) / math.sqrt(K)).to(DEV)
+    b = torch.randn(N, generator=g(24)).to(DEV)
+    xa = Act(x.to(dtype).contiguous(), 1, 1, M)
+    out = Act.empty(1, 1, M, N, torch.float32, DEV)
+    ops.linear(xa, w.to(dtype).contiguous(), out, bias=b, act=L.ACT_SILU)
+    ref = F.silu(F.linear(xa.buf.float(), w.to(dtype).float(), b))
+    assert rel_l2(out.buf, ref) < (2e-5 if dtype == torch.float32 else 2e-3)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("n,c,h,w", [(3, 256, 32, 32), (2, 768, 16, 16), (5, 1536, 8, 8), (2, 128, 64, 64),
+                                     (130, 512, 8, 8)])
+@pytest.mark.parametrize("silu", [True, False])
+def test_group_norm(dtype, n, c, h, w, silu):
+    x = (torch.randn(n, c, h, w, generator=g(25)) * 2 + 0.5).to(DEV)
+    gamma = torch.randn(c, generator=g(26)).to(DEV)
+    beta = torch.randn(c, generator=g(27)).to(DEV)
+    xa = to_act(x, dtype, ld=c + 4, c0=4)
+    out = Act.empty(n, h, w, c, dtype, DEV)
+    stats = torch.empty(n * 32 * 2, dtype=torch.float64, device=DEV)
+    ops.group_norm(xa, gamma, beta, 1e-5, out, stats, silu=silu)
+    ref = F.group_norm(from_act(xa), 32, gamma, beta, 1e-5)
+    if silu:
+        ref = F.silu(ref)
+    assert rel_l2(from_act(out), ref) < (2e-5 if dtype == torch.float32 else 4e-3)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("rows,c", [(1000, 256), (513, 512), (64, 1024)])
+def test_layer_norm(dtype, rows, c):
+    x = (torch.randn(rows, c, generator=g(28)) * 3 - 1).to(DEV)
+    gamma = torch.randn(c, generator=g(29)).to(DEV)
+    beta = torch.randn(c, generator=g(30)).to(DEV)
+    xa = Act(x.to(dtype).contiguous(), 1, 1, rows)
+    out = Act.empty(1, 1, rows, c, dtype, DEV)
+    ops.layer_norm(xa, gamma, beta, 1e-5, out)
+    ref = F.layer_norm(xa.buf.float(), (c,), gamma, beta, 1e-5)
+    assert rel_l2(out.buf.float(), ref) < (2e-5 if dtype == torch.float32 else 4e-3)
+
+
+def _attn_ref(q, k, v, scale):  # [b, h, n, d]
+    s = torch.einsum("bhid,bhjd->bhij", q, k) * scale
+    return torch.einsum("bhij,bhjd->bhid", s.softmax(-1), v)
+
+
+@pytest.mark.parametrize("dtype,impl", [(torch.float32, L.IMPL_SIMT), (torch.bfloat16, L.IMPL_SIMT),
+                                        (torch.bfloat16, L.IMPL_AUTO)])
+@pytest.mark.parametrize("b,h,n", [(2, 8, 1024), (3, 16, 256), (4, 32, 64), (1, 2, 200)])
+def test_self_attention_packed_qkv(dtype, impl, b, h, n):
+    d = 32
+    C_ = h * d
+    qkv = torch.randn(b * n, 3 * C_, generator=g(31)).to(DEV).to(dtype).contiguous()
+    buf = Act(qkv, b, 1, n)
+    out = Act.empty(b, 1, n, C_, dtype, DEV)
+    ops.attention(buf.cols(0, C_), buf.cols(C_, C_), buf.cols(2 * C_, C_), out, batch=b, heads=h, head_dim=d,
+                  n_q=n, n_kv=n, scale=d ** -0.5, impl=impl)
+    f = qkv.float().reshape(b, n, 3, h, d)
+    ref = _attn_ref(f[:, :, 0].transpose(1, 2), f[:, :, 1].transpose(1, 2), f[:, :, 2].transpose(1, 2), d ** -0.5)
+    ref = ref.transpose(1, 2).reshape(b * n, C_)
+    assert rel_l2(out.buf.float(), ref) < (2e-5 if dtype == torch.float32 else 1e-2)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_attention_legacy_interleaved_heads(dtype):
+    # QKVAttentionLegacy (openaimodel.py:365): channels are [head][q|k|v][32]
+    b, h, n, d = 2, 8, 256, 32
+    qkv = torch.randn(b * n, 3 * h * d, generator=g(32)).to(DEV).to(dtype).contiguous()
+    buf = Act(qkv, b, 1, n)
+    out = Act.empty(b, 1, n, h * d, dtype, DEV)
+    ops.attention(buf.cols(0, 3 * h * d - 2 * d), buf.cols(d, 3 * h * d - 2 * d), buf.cols(2 * d, 3 * h * d - 2 * d),
+                  out, batch=b, heads=h, head_dim=d, n_q=n, n_kv=n, scale=d ** -0.5,
+                  head_stride_q=3 * d, head_stride_kv=3 * d)
+    f = qkv.float().reshape(b, n, h, 3, d)
+    ref = _attn_ref(f[:, :, :, 0].transpose(1, 2), f[:, :, :, 1].transpose(1, 2), f[:, :, :, 2].transpose(1, 2),
+                    d ** -0.5)
+    ref = ref.transpose(1, 2).reshape(b * n, h * d)
+    assert rel_l2(out.buf.float(), ref) < (2e-5 if dtype == torch.float32 else 1e-2)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("nk", [4, 1, 7])
+def test_cross_attention_small_kv(dtype, nk):
+    b, h, n, d = 3, 16, 256, 32
+    C_ = h * d
+    q = torch.randn(b * n, C_, generator=g(33)).to(DEV).to(dtype).contiguous()
+    kv = torch.randn(b * nk, 2 * C_, generator=g(34)).to(DEV).to(dtype).contiguous()
+    qa, kva = Act(q, b, 1, n), Act(kv, b, 1, nk)
+    out = Act.empty(b, 1, n, C_, dtype, DEV)
+    ops.attention(qa, kva.cols(0, C_), kva.cols(C_, C_), out, batch=b, heads=h, head_dim=d, n_q=n, n_kv=nk,
+                  scale=d ** -0.5)
+    qf = q.float().reshape(b, n, h, d).transpose(1, 2)
+    kf = kv.float()[:, :C_].reshape(b, nk, h, d).transpose(1, 2)
+    vf = kv.float()[:, C_:].reshape(b, nk, h, d).transpose(1, 2)
+    ref = _attn_ref(qf, kf, vf, d ** -0.5).transpose(1, 2).reshape(b * n, C_)
+    assert rel_l2(out.buf.float(), ref) < (2e-5 if dtype == torch.float32 else 4e-3)
+
+
+def test_timestep_embedding_and_layout():
+    t = torch.tensor([1, 501, 981, 0, 999], dtype=torch.int64, device=DEV)
+    half = 128
+    freqs = torch.exp(-math.log(10000) * torch.arange(0, half, dtype=torch.float32) / half)
+    out = torch.empty(5, 256, dtype=torch.float32, device=DEV)
+    ops.timestep_embedding(t, 256, freqs.to(DEV), out)
+    args = t.cpu()[:, None].float() * freqs[None]
+    ref = torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
+    assert (out.cpu() - ref).abs().max() < 2e-6
+    x = torch.randn(3, 4, 32, 32, generator=g(35)).to(DEV)
+    a = Act.empty(3, 32, 32, 4, torch.float32, DEV)
+    ops.nchw_to_nhwc(x, a)
+    assert torch.equal(from_act(a), x)
+    y = torch.empty_like(x)
+    ops.nhwc_to_nchw(a, y)
+    assert torch.equal(y, x)
+    ab = Act.empty(3, 32, 32, 4, torch.bfloat16, DEV)
+    ops.nchw_to_nhwc(x, ab)
+    assert torch.equal(from_act(ab), x.bfloat16().float())
+    c = Act.empty(3, 32, 32, 4, torch.float32, DEV)
+    ops.copy2d(ab, c)
+    assert torch.equal(c.buf, ab.buf.float())
+
+
+def test_softmax_rows():
+    x = torch.randn(300, 1024, generator=g(36)).to(DEV)
+    a = Act(x.clone(), 1, 1, 300)
+    ops.softmax_rows_(a, 0.125)
+    assert rel_l2(a.buf, (x * 0.125).softmax(-1)) < 1e-5
+
+
+@pytest.mark.parametrize("cfg", [True, False])
+@pytest.mark.parametrize("eta", [0.0, 1.0])
+def test_ddim_step_bit_exact(cfg, eta):
+    # the reference's op sequence (ddim.py:173-203) evaluated with torch fp32 on the same device
+    shape = (8, 4, 32, 32)
+    x, eu, ec, nz = (torch.randn(shape, generator=g(40 + i)).to(DEV) for i in range(4))
+    a_t, a_prev = torch.tensor(0.31234567, device=DEV), torch.tensor(0.4456789, device=DEV)
+    sigma = eta * torch.sqrt((1 - a_prev) / (1 - a_t) * (1 - a_t / a_prev))
+    s1 = torch.sqrt(1 - a_t)
+    scale = 2.0
+    e = eu + scale * (ec - eu) if cfg else ec
+    pred_ref = (x - s1 * e) / a_t.sqrt()
+    dir_ref = (1. - a_prev - sigma ** 2).sqrt() * e
+    xprev_ref = a_prev.sqrt() * pred_ref + dir_ref + sigma * nz * 1.0
+    xp, pr, eo = ops.ddim_step(x, ec, e_uncond=eu if cfg else None, noise=nz, cfg_scale=scale,
+                               sqrt_one_minus_at=float(s1), sqrt_at=float(a_t.sqrt()),
+                               sqrt_a_prev=float(a_prev.sqrt()),
+                               dir_coef=float((1. - a_prev - sigma ** 2).sqrt()), sigma_t=float(sigma),
+                               want_e=True)
+    assert torch.equal(eo, e)
+    assert torch.equal(pr, pred_ref)
+    assert torch.equal(xp, xprev_ref)
+
+
+def test_q_sample_bit_exact_and_cfg_mse():
+    b = 16
+    x0, nz, eu, ec = (torch.randn(b, 4, 32, 32, generator=g(50 + i)).to(DEV) for i in range(4))
+    t = torch.randint(0, 1000, (b,), generator=g(54)).to(DEV)
+    ac = torch.linspace(0.999, 0.001, 1000, device=DEV)
+    sa, s1a = ac.sqrt(), (1 - ac).sqrt()
+    out = ops.q_sample(x0, nz, t, sa, s1a)
+    ref = sa[t].reshape(b, 1, 1, 1) * x0 + s1a[t].reshape(b, 1, 1, 1) * nz
+    assert torch.equal(out, ref)
+    ls = ops.cfg_mse(ec, nz, e_uncond=eu, cfg_scale=2.0)
+    guided = eu + 2.0 * (ec - eu)
+    ref = F.mse_loss(nz, guided, reduction="none").mean([1, 2, 3])
+    assert rel_l2(ls, ref) < 1e-6
+    ls2 = ops.cfg_mse(ec, nz)
+    assert rel_l2(ls2, F.mse_loss(nz, ec, reduction="none").mean([1, 2, 3])) < 1e-6
+
+
+def test_errors_are_reported():
+    x = Act(torch.zeros(4, 6, device=DEV), 1, 1, 4)
+    out = Act.empty(1, 1, 4, 6, torch.float32, DEV)
+    with pytest.raises(L.EaldmError):
+        ops.layer_norm(x, torch.ones(6, device=DEV), torch.zeros(6, device=DEV), 1e-5, out)  # c % 4 != 0
