@@ -10,6 +10,10 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200, sm_100a)")
+    # the torch checks must be true fp32: cuDNN/cuBLAS default to TF32 for convolutions on sm_80+
+    import torch
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
 
 
 def pytest_collection_modifyitems(config, items):
