@@ -19,7 +19,7 @@ IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05 = 0, 1, 2
 
 EXPORTS = [
     "ealdm_abi_version", "ealdm_last_error", "ealdm_device_check", "ealdm_launch_count",
-    "ealdm_conv", "ealdm_group_norm", "ealdm_layer_norm", "ealdm_attention",
+    "ealdm_conv", "ealdm_group_norm", "ealdm_group_norm_workspace_bytes", "ealdm_layer_norm", "ealdm_attention",
     "ealdm_timestep_embedding", "ealdm_nchw_to_nhwc", "ealdm_nhwc_to_nchw",
     "ealdm_upsample_nearest2x", "ealdm_copy2d", "ealdm_softmax_rows", "ealdm_ddim_step",
     "ealdm_q_sample", "ealdm_cfg_mse",
@@ -38,18 +38,18 @@ class ConvArgs(C.Structure):
                 ("k_total", C.c_int64), ("h_out", C.c_int64), ("w_out", C.c_int64),
                 ("bias", C.c_void_p), ("rowvec", C.c_void_p), ("ld_rowvec", C.c_int64),
                 ("residual", C.c_void_p), ("ld_res", C.c_int64), ("out", C.c_void_p),
-                ("ld_out", C.c_int64), ("out_f32", C.c_int32), ("reserved", C.c_int32)]
+                ("ld_out", C.c_int64), ("out_f32", C.c_int32), ("res_f32", C.c_int32)]
 
 
 class GroupNormArgs(C.Structure):
     _fields_ = [("dtype", C.c_int32), ("act", C.c_int32), ("x", C.c_void_p), ("n", C.c_int64),
                 ("hw", C.c_int64), ("c", C.c_int64), ("ld_x", C.c_int64), ("groups", C.c_int32),
                 ("eps", C.c_float), ("gamma", C.c_void_p), ("beta", C.c_void_p), ("y", C.c_void_p),
-                ("ld_y", C.c_int64), ("stats", C.c_void_p)]
+                ("ld_y", C.c_int64), ("workspace", C.c_void_p)]
 
 
 class LayerNormArgs(C.Structure):
-    _fields_ = [("dtype", C.c_int32), ("reserved", C.c_int32), ("x", C.c_void_p),
+    _fields_ = [("dtype", C.c_int32), ("x_f32", C.c_int32), ("x", C.c_void_p),
                 ("rows", C.c_int64), ("c", C.c_int64), ("ld_x", C.c_int64), ("eps", C.c_float),
                 ("reserved2", C.c_int32), ("gamma", C.c_void_p), ("beta", C.c_void_p),
                 ("y", C.c_void_p), ("ld_y", C.c_int64)]
@@ -102,6 +102,8 @@ def _declare(lib):
     lib.ealdm_device_check.argtypes = []
     lib.ealdm_launch_count.restype = C.c_int64
     lib.ealdm_launch_count.argtypes = []
+    lib.ealdm_group_norm_workspace_bytes.restype = C.c_int64
+    lib.ealdm_group_norm_workspace_bytes.argtypes = [i64, i64, i64]
     for name, argt in [
         ("ealdm_conv", [C.POINTER(ConvArgs), vp]),
         ("ealdm_group_norm", [C.POINTER(GroupNormArgs), vp]),

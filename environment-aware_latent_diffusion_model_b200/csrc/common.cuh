@@ -103,6 +103,7 @@ struct Epilogue {
   long long ld_out;
   int act;
   int out_f32;
+  int res_f32;
 };
 
 }  // namespace ealdm

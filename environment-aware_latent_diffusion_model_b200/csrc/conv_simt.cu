@@ -172,7 +172,8 @@ __global__ void __launch_bounds__(NT) conv_simt_kernel(const Params p) {
         float v = Cs[rr][blk * 32 + j] * gelu_erf_f(Cs[rr][blk * 32 + 16 + j]);
         const long long ocol = (n0 >> 1) + blk * 16 + j;
         if (ep.residual)
-          v += to_f32(reinterpret_cast<const T*>(ep.residual)[m * ep.ld_res + ocol]);
+          v += ep.res_f32 ? reinterpret_cast<const float*>(ep.residual)[m * ep.ld_res + ocol]
+                          : to_f32(reinterpret_cast<const T*>(ep.residual)[m * ep.ld_res + ocol]);
         reinterpret_cast<TOut*>(ep.out)[m * ep.ld_out + ocol] = from_f32<TOut>(v);
       }
     }
@@ -191,7 +192,9 @@ __global__ void __launch_bounds__(NT) conv_simt_kernel(const Params p) {
       if (ep.bias) v += ep.bias[col];
       if (ep.rowvec) v += ep.rowvec[img * ep.ld_rowvec + col];
       if (ep.act == EALDM_ACT_SILU) v = silu_f(v);
-      if (ep.residual) v += to_f32(reinterpret_cast<const T*>(ep.residual)[m * ep.ld_res + col]);
+      if (ep.residual)
+        v += ep.res_f32 ? reinterpret_cast<const float*>(ep.residual)[m * ep.ld_res + col]
+                        : to_f32(reinterpret_cast<const T*>(ep.residual)[m * ep.ld_res + col]);
       reinterpret_cast<TOut*>(ep.out)[m * ep.ld_out + col] = from_f32<TOut>(v);
     }
   }
@@ -234,6 +237,7 @@ int launch(const ealdm_conv_args* a, cudaStream_t st) {
   p.ep.ld_out = a->ld_out;
   p.ep.act = a->act;
   p.ep.out_f32 = a->out_f32;
+  p.ep.res_f32 = a->res_f32;
   if (a->act == EALDM_ACT_GEGLU)
     EALDM_REQUIRE(a->n_out % 32 == 0, "GEGLU needs n_out %% 32 == 0 (got %lld)", (long long)a->n_out);
 

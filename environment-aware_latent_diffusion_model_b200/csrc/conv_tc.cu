@@ -100,9 +100,15 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&acc)[32], const 
         o[j] = a * gelu_erf_f(b);
       }
       if (ep.residual) {
-        const bf16* r = reinterpret_cast<const bf16*>(ep.residual) + row * ep.ld_res + ocol0 + g * 8;
+        if (ep.res_f32) {
+          const float* r = reinterpret_cast<const float*>(ep.residual) + row * ep.ld_res + ocol0 + g * 8;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] += __bfloat162float(r[j]);
+          for (int j = 0; j < 8; ++j) o[j] += r[j];
+        } else {
+          const bf16* r = reinterpret_cast<const bf16*>(ep.residual) + row * ep.ld_res + ocol0 + g * 8;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] += __bfloat162float(r[j]);
+        }
       }
       store8<TOut>(dst + g * 8, o);
     }
@@ -110,8 +116,12 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&acc)[32], const 
   }
   TOut* dst = reinterpret_cast<TOut*>(ep.out) + row * ep.ld_out + col0;
   const float* rv = ep.rowvec ? ep.rowvec + img * ep.ld_rowvec + col0 : nullptr;
-  const bf16* res =
-      ep.residual ? reinterpret_cast<const bf16*>(ep.residual) + row * ep.ld_res + col0 : nullptr;
+  const bf16* res = (ep.residual && !ep.res_f32)
+                        ? reinterpret_cast<const bf16*>(ep.residual) + row * ep.ld_res + col0
+                        : nullptr;
+  const float* resf = (ep.residual && ep.res_f32)
+                          ? reinterpret_cast<const float*>(ep.residual) + row * ep.ld_res + col0
+                          : nullptr;
   if (vec_ok) {
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
@@ -143,6 +153,12 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&acc)[32], const 
           o[2 * j + 1] += __high2float(h[j]);
         }
       }
+      if (resf) {
+        const float4 r0 = *reinterpret_cast<const float4*>(resf + g * 8);
+        const float4 r1 = *reinterpret_cast<const float4*>(resf + g * 8 + 4);
+        o[0] += r0.x; o[1] += r0.y; o[2] += r0.z; o[3] += r0.w;
+        o[4] += r1.x; o[5] += r1.y; o[6] += r1.z; o[7] += r1.w;
+      }
       store8<TOut>(dst + g * 8, o);
     }
   } else {
@@ -153,6 +169,7 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&acc)[32], const 
       if (rv) o += __ldg(rv + j);
       if (ep.act == EALDM_ACT_SILU) o = silu_f(o);
       if (res) o += __bfloat162float(res[j]);
+      if (resf) o += resf[j];
       dst[j] = from_f32<TOut>(o);
     }
   }
@@ -382,6 +399,7 @@ bool supported(const ealdm_conv_args* a) {
   if ((reinterpret_cast<uintptr_t>(a->out) & 15) != 0 || a->ld_out % 8 != 0) return false;
   if (a->residual && ((reinterpret_cast<uintptr_t>(a->residual) & 15) != 0 || a->ld_res % 8 != 0))
     return false;
+  if (a->act == EALDM_ACT_GEGLU && a->rowvec) return false;
   if (a->act == EALDM_ACT_GEGLU && a->n_out % 32 != 0) return false;
   return true;
 }
@@ -475,6 +493,7 @@ int launch(const ealdm_conv_args* a, cudaStream_t st) {
   p.ep.ld_out = a->ld_out;
   p.ep.act = a->act;
   p.ep.out_f32 = a->out_f32;
+  p.ep.res_f32 = a->res_f32;
 
   switch (BN) {
     case 32: return launch_bn<32>(tmA[0], tmA[1], tmB, p, st);

@@ -1,6 +1,7 @@
 // GroupNorm (+SiLU) and LayerNorm over NHWC activations, plus a row softmax.  HBM-bound kernels:
-// every pixel row is read with consecutive threads on consecutive channels (coalesced), statistics
-// are accumulated fp32 per thread -> fp32 per CTA (shared atomics) -> fp64 per (image, group).
+// every pixel row is read with consecutive threads on consecutive channels (coalesced); GroupNorm
+// statistics go fp32 per thread -> fp32 per (CTA, 4-channel vector) -> fp64 per (image, group) in a
+// fixed summation order (no atomics, bit-reproducible).
 #include "common.cuh"
 
 namespace ealdm {
@@ -9,27 +10,29 @@ namespace norm {
 constexpr int NT = 256;
 constexpr int MAX_GROUPS = 64;
 
-// ---- GroupNorm statistics: stats[n][g] = {sum, sum of squares} ------------------------------------
+// ---- GroupNorm statistics: part[n][chunk][v] = {sum, sum of squares} of 4 channels over the chunk ---
+// No atomics: every (image, pixel chunk, 4-channel vector) partial is produced by exactly one
+// thread (after a fixed-order shared-memory reduction over the CTA's pixel lanes), and the apply
+// kernel combines the partials of a group in a fixed order in fp64 => bit-reproducible.
 template <typename T>
 __global__ void __launch_bounds__(NT)
-gn_stats_kernel(const T* __restrict__ x, long long ld, int hw, int c, int groups, int pix_per_cta,
-                double* __restrict__ stats) {
-  __shared__ float s_sum[MAX_GROUPS], s_sq[MAX_GROUPS];
+gn_stats_kernel(const T* __restrict__ x, long long ld, int hw, int c, int pix_per_cta,
+                float2* __restrict__ part) {
+  __shared__ float2 red[NT];
   const int t = threadIdx.x;
   const int n = blockIdx.y;
-  if (t < groups) { s_sum[t] = 0.f; s_sq[t] = 0.f; }
-  __syncthreads();
   const int vpp = c >> 2;  // vec4 per pixel
-  const int cpg = c / groups;
   const int lanes_v = vpp < NT ? vpp : NT;
   const int pix_lanes = NT / lanes_v;
   const int tv = t % lanes_v, tp = t / lanes_v;
   const int p0 = blockIdx.x * pix_per_cta;
   const int p1 = min(p0 + pix_per_cta, hw);
   const T* base = x + static_cast<long long>(n) * hw * ld;
-  if (tp < pix_lanes) {
-    for (int v = tv; v < vpp; v += lanes_v) {
-      float s = 0.f, ss = 0.f;
+  float2* out = part + (static_cast<long long>(n) * gridDim.x + blockIdx.x) * vpp;
+  for (int v0 = 0; v0 < vpp; v0 += lanes_v) {
+    const int v = v0 + tv;
+    float s = 0.f, ss = 0.f;
+    if (tp < pix_lanes && v < vpp) {
       for (int pix = p0 + tp; pix < p1; pix += pix_lanes) {
         Vec4<T> q;
         q.load(base + static_cast<long long>(pix) * ld + v * 4);
@@ -38,16 +41,16 @@ gn_stats_kernel(const T* __restrict__ x, long long ld, int hw, int c, int groups
 #pragma unroll
         for (int j = 0; j < 4; ++j) { s += f[j]; ss = fmaf(f[j], f[j], ss); }
       }
-      const int g = (v * 4) / cpg;
-      atomicAdd(&s_sum[g], s);
-      atomicAdd(&s_sq[g], ss);
     }
-  }
-  __syncthreads();
-  if (t < groups) {
-    double* d = stats + (static_cast<long long>(n) * groups + t) * 2;
-    atomicAdd(d, static_cast<double>(s_sum[t]));
-    atomicAdd(d + 1, static_cast<double>(s_sq[t]));
+    if (pix_lanes > 1) {
+      __syncthreads();
+      red[t] = make_float2(s, ss);
+      __syncthreads();
+      if (tp == 0 && v < vpp) {
+        for (int k = 1; k < pix_lanes; ++k) { s += red[k * lanes_v + tv].x; ss += red[k * lanes_v + tv].y; }
+      }
+    }
+    if (tp == 0 && v < vpp) out[v] = make_float2(s, ss);
   }
 }
 
@@ -55,23 +58,47 @@ gn_stats_kernel(const T* __restrict__ x, long long ld, int hw, int c, int groups
 template <typename T>
 __global__ void __launch_bounds__(NT)
 gn_apply_kernel(const T* __restrict__ x, long long ld_x, T* __restrict__ y, long long ld_y, int hw,
-                int c, int groups, int pix_per_cta, const double* __restrict__ stats, float eps,
+                int c, int groups, int pix_per_cta, const float2* __restrict__ part, float eps,
                 const float* __restrict__ gamma, const float* __restrict__ beta, int act) {
   __shared__ float s_mean[MAX_GROUPS], s_rstd[MAX_GROUPS];
   const int t = threadIdx.x;
   const int n = blockIdx.y;
   const int cpg = c / groups;
-  if (t < groups) {
-    const double* d = stats + (static_cast<long long>(n) * groups + t) * 2;
-    const double cnt = static_cast<double>(hw) * cpg;
-    const double mean = d[0] / cnt;
-    double var = d[1] / cnt - mean * mean;
-    if (var < 0.0) var = 0.0;
-    s_mean[t] = static_cast<float>(mean);
-    s_rstd[t] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  const int vpp = c >> 2;
+  {
+    // 8 lanes per group sum the group's partials (chunks x cpg/4 vectors) in a fixed order
+    const int chunks = gridDim.x;
+    const int vpg = cpg >> 2;
+    const int terms = chunks * vpg;
+    const float2* pn = part + static_cast<long long>(n) * chunks * vpp;
+    for (int g0 = 0; g0 < groups; g0 += NT / 8) {
+      const int g = g0 + (t >> 3);
+      const int sub = t & 7;
+      double s = 0.0, ss = 0.0;
+      if (g < groups) {
+        for (int k = sub; k < terms; k += 8) {
+          const int ch = k / vpg, vv = k - ch * vpg;
+          const float2 p = pn[static_cast<long long>(ch) * vpp + g * vpg + vv];
+          s += static_cast<double>(p.x);
+          ss += static_cast<double>(p.y);
+        }
+      }
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      }
+      if (g < groups && sub == 0) {
+        const double cnt = static_cast<double>(hw) * cpg;
+        const double mean = s / cnt;
+        double var = ss / cnt - mean * mean;
+        if (var < 0.0) var = 0.0;
+        s_mean[g] = static_cast<float>(mean);
+        s_rstd[g] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+      }
+    }
   }
   __syncthreads();
-  const int vpp = c >> 2;
   const int p0 = blockIdx.x * pix_per_cta;
   const int p1 = min(p0 + pix_per_cta, hw);
   const long long items = static_cast<long long>(p1 - p0) * vpp;
@@ -102,45 +129,53 @@ gn_apply_kernel(const T* __restrict__ x, long long ld_x, T* __restrict__ y, long
   }
 }
 
+// pixel chunking shared by the workspace query and the launch
+static void gn_chunking(long long n, long long hw, int* pix_per_cta, long long* chunks) {
+  // enough CTAs to fill 148 SMs a few times over, at least 16 pixels each
+  long long ch = ceil_div(1184, n);
+  const long long max_chunks = ceil_div(hw, 16);
+  if (ch > max_chunks) ch = max_chunks;
+  if (ch < 1) ch = 1;
+  const int ppc = static_cast<int>(ceil_div(hw, ch));
+  *pix_per_cta = ppc;
+  *chunks = ceil_div(hw, ppc);
+}
+
 template <typename T>
 static int group_norm_t(const ealdm_group_norm_args* a, cudaStream_t st) {
   const int hw = static_cast<int>(a->hw);
   const int n = static_cast<int>(a->n);
-  // enough CTAs to fill 148 SMs a few times over, at least 16 pixels each
-  long long chunks = ceil_div(1184, n);
-  const long long max_chunks = ceil_div(hw, 16);
-  if (chunks > max_chunks) chunks = max_chunks;
-  if (chunks < 1) chunks = 1;
-  const int ppc = static_cast<int>(ceil_div(hw, chunks));
-  chunks = ceil_div(hw, ppc);
+  int ppc;
+  long long chunks;
+  gn_chunking(n, hw, &ppc, &chunks);
   dim3 grid(static_cast<unsigned>(chunks), static_cast<unsigned>(n));
-  EALDM_CUDA(cudaMemsetAsync(a->stats, 0, sizeof(double) * 2 * n * a->groups, st));
+  float2* part = reinterpret_cast<float2*>(a->workspace);
   gn_stats_kernel<T><<<grid, NT, 0, st>>>(reinterpret_cast<const T*>(a->x), a->ld_x, hw,
-                                          static_cast<int>(a->c), a->groups, ppc, a->stats);
+                                          static_cast<int>(a->c), ppc, part);
   EALDM_LAUNCH_CHECK();
   gn_apply_kernel<T><<<grid, NT, 0, st>>>(reinterpret_cast<const T*>(a->x), a->ld_x,
                                           reinterpret_cast<T*>(a->y), a->ld_y, hw,
-                                          static_cast<int>(a->c), a->groups, ppc, a->stats, a->eps,
+                                          static_cast<int>(a->c), a->groups, ppc, part, a->eps,
                                           a->gamma, a->beta, a->act);
   EALDM_LAUNCH_CHECK();
   return 0;
 }
 
 // ---- LayerNorm: one warp per row, two-pass mean / centred variance ------------------------------------
-template <typename T>
+template <typename TX, typename T>
 __global__ void __launch_bounds__(NT)
-layer_norm_kernel(const T* __restrict__ x, long long ld_x, T* __restrict__ y, long long ld_y,
+layer_norm_kernel(const TX* __restrict__ x, long long ld_x, T* __restrict__ y, long long ld_y,
                   long long rows, int c, float eps, const float* __restrict__ gamma,
                   const float* __restrict__ beta) {
   const int lane = threadIdx.x & 31;
   const long long row = static_cast<long long>(blockIdx.x) * (NT / 32) + (threadIdx.x >> 5);
   if (row >= rows) return;
-  const T* xr = x + row * ld_x;
+  const TX* xr = x + row * ld_x;
   T* yr = y + row * ld_y;
   const int vpr = c >> 2;
   float s = 0.f;
   for (int v = lane; v < vpr; v += 32) {
-    Vec4<T> q;
+    Vec4<TX> q;
     q.load(xr + v * 4);
     float f[4];
     q.get(f);
@@ -149,7 +184,7 @@ layer_norm_kernel(const T* __restrict__ x, long long ld_x, T* __restrict__ y, lo
   const float mean = warp_sum(s) / static_cast<float>(c);
   float ss = 0.f;
   for (int v = lane; v < vpr; v += 32) {
-    Vec4<T> q;
+    Vec4<TX> q;
     q.load(xr + v * 4);
     float f[4];
     q.get(f);
@@ -158,10 +193,11 @@ layer_norm_kernel(const T* __restrict__ x, long long ld_x, T* __restrict__ y, lo
   }
   const float rstd = rsqrtf(warp_sum(ss) / static_cast<float>(c) + eps);
   for (int v = lane; v < vpr; v += 32) {
-    Vec4<T> q;
-    q.load(xr + v * 4);
+    Vec4<TX> qx;
+    qx.load(xr + v * 4);
     float f[4];
-    q.get(f);
+    qx.get(f);
+    Vec4<T> q;
     const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + v * 4));
     const float4 be = __ldg(reinterpret_cast<const float4*>(beta + v * 4));
     f[0] = (f[0] - mean) * rstd * ga.x + be.x;
@@ -196,8 +232,16 @@ softmax_rows_kernel(T* __restrict__ x, long long ld, long long rows, int c, floa
 
 using namespace ealdm;
 
+extern "C" int64_t ealdm_group_norm_workspace_bytes(int64_t n, int64_t hw, int64_t c) {
+  if (n <= 0 || hw <= 0 || c <= 0) return 0;
+  int ppc;
+  long long chunks;
+  norm::gn_chunking(n, hw, &ppc, &chunks);
+  return n * chunks * (c / 4) * static_cast<int64_t>(sizeof(float2));
+}
+
 extern "C" int ealdm_group_norm(const ealdm_group_norm_args* a, ealdm_stream_t stream) {
-  EALDM_REQUIRE(a && a->x && a->y && a->stats && a->gamma && a->beta, "group_norm: null argument");
+  EALDM_REQUIRE(a && a->x && a->y && a->workspace && a->gamma && a->beta, "group_norm: null argument");
   EALDM_REQUIRE(a->groups > 0 && a->groups <= norm::MAX_GROUPS && a->c % a->groups == 0,
                 "group_norm: c=%lld not divisible by groups=%d", (long long)a->c, a->groups);
   EALDM_REQUIRE((a->c / a->groups) % 4 == 0 && a->ld_x % 4 == 0 && a->ld_y % 4 == 0,
@@ -218,11 +262,15 @@ extern "C" int ealdm_layer_norm(const ealdm_layer_norm_args* a, ealdm_stream_t s
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const unsigned grid = static_cast<unsigned>(ceil_div(a->rows, norm::NT / 32));
   if (a->dtype == EALDM_F32) {
-    norm::layer_norm_kernel<float><<<grid, norm::NT, 0, st>>>(
+    norm::layer_norm_kernel<float, float><<<grid, norm::NT, 0, st>>>(
         reinterpret_cast<const float*>(a->x), a->ld_x, reinterpret_cast<float*>(a->y), a->ld_y,
         a->rows, (int)a->c, a->eps, a->gamma, a->beta);
+  } else if (a->dtype == EALDM_BF16 && a->x_f32) {
+    norm::layer_norm_kernel<float, bf16><<<grid, norm::NT, 0, st>>>(
+        reinterpret_cast<const float*>(a->x), a->ld_x, reinterpret_cast<bf16*>(a->y), a->ld_y,
+        a->rows, (int)a->c, a->eps, a->gamma, a->beta);
   } else if (a->dtype == EALDM_BF16) {
-    norm::layer_norm_kernel<bf16><<<grid, norm::NT, 0, st>>>(
+    norm::layer_norm_kernel<bf16, bf16><<<grid, norm::NT, 0, st>>>(
         reinterpret_cast<const bf16*>(a->x), a->ld_x, reinterpret_cast<bf16*>(a->y), a->ld_y,
         a->rows, (int)a->c, a->eps, a->gamma, a->beta);
   } else {

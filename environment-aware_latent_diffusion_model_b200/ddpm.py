@@ -1,0 +1,281 @@
+"""`LatentDiffusion` / `DiffusionWrapper` with the reference's public contract for the hot path
+(reference: ldm/models/diffusion/ddpm.py -- DDPM :46-171,276-294; LatentDiffusion :428-566,713-771,
+878-921,1011-1078,1267-1276; DiffusionWrapper :1443-1469).
+
+This is a plain `nn.Module` (the reference derives from pytorch_lightning.LightningModule, which is
+orchestration only): it owns the schedule buffers, routes conditioning to the UNet, and implements
+`q_sample`, `p_losses`, `apply_model`, `encode/decode_first_stage` and `sample_log` with the same
+arithmetic, including EALDM's deviations: classifier-free guidance inside the training loss with a
+hard-coded scale of 2 (ddpm.py:442,1040-1044).  Trainer hooks, logging and dataset plumbing stay in
+the reference (out of scope).
+"""
+from __future__ import annotations
+
+from functools import partial
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import ops
+from .ddim import DDIMSampler
+from .util import count_params, instantiate_from_config, make_beta_schedule
+
+
+def disabled_train(self, mode=True):
+    return self
+
+
+class IdentityFirstStage(nn.Module):
+    """ldm/models/autoencoder.py:426-443"""
+
+    def __init__(self, *args, vq_interface=False, **kwargs):
+        super().__init__()
+        self.vq_interface = vq_interface
+
+    def encode(self, x, *args, **kwargs):
+        return x
+
+    def decode(self, x, *args, **kwargs):
+        return x
+
+    def quantize(self, x, *args, **kwargs):
+        return (x, None, [None, None, None]) if self.vq_interface else x
+
+    def forward(self, x, *args, **kwargs):
+        return x
+
+
+class DiffusionWrapper(nn.Module):
+    """ddpm.py:1443-1469"""
+
+    def __init__(self, diff_model_config, conditioning_key):
+        super().__init__()
+        self.diffusion_model = instantiate_from_config(diff_model_config)
+        self.conditioning_key = conditioning_key
+        assert self.conditioning_key in [None, "concat", "crossattn", "hybrid", "adm"]
+
+    def forward(self, x, t, c_concat: list = None, c_crossattn: list = None):
+        key = self.conditioning_key
+        if key is None:
+            return self.diffusion_model(x, t)
+        if key == "concat":
+            return self.diffusion_model(torch.cat([x] + c_concat, dim=1), t)
+        if key == "crossattn":
+            cc = c_crossattn[0] if len(c_crossattn) == 1 else torch.cat(c_crossattn, 1)
+            return self.diffusion_model(x, t, context=cc)
+        if key == "hybrid":
+            return self.diffusion_model(torch.cat([x] + c_concat, dim=1), t, context=torch.cat(c_crossattn, 1))
+        if key == "adm":
+            return self.diffusion_model(x, t, y=c_crossattn[0])
+        raise NotImplementedError()
+
+
+class LatentDiffusion(nn.Module):
+    def __init__(self, unet_config, first_stage_config=None, cond_stage_config="__is_unconditional__",
+                 num_timesteps_cond=None, cond_stage_key="image", cond_stage_trainable=False, concat_mode=True,
+                 cond_stage_forward=None, conditioning_key=None, scale_factor=1.0, scale_by_std=False,
+                 timesteps=1000, beta_schedule="linear", loss_type="l2", ckpt_path=None, ignore_keys=(),
+                 monitor="val/loss", use_ema=False, first_stage_key="image", image_size=256, channels=3,
+                 log_every_t=100, clip_denoised=True, linear_start=1e-4, linear_end=2e-2, cosine_s=8e-3,
+                 given_betas=None, original_elbo_weight=0., v_posterior=0., l_simple_weight=1.,
+                 parameterization="eps", scheduler_config=None, use_positional_encodings=False,
+                 learn_logvar=False, logvar_init=0., base_learning_rate=None, **unused):
+        super().__init__()
+        assert parameterization in ["eps", "x0"], 'currently only supporting "eps" and "x0"'
+        self.unconditional_guidance_scale = 2.  # ddpm.py:442 (hard-coded in the reference)
+        self.parameterization = parameterization
+        self.num_timesteps_cond = 1 if num_timesteps_cond is None else num_timesteps_cond
+        self.scale_by_std = scale_by_std
+        if conditioning_key is None:
+            conditioning_key = "concat" if concat_mode else "crossattn"
+        if cond_stage_config == "__is_unconditional__":
+            conditioning_key = None
+        self.cond_stage_model = None
+        self.clip_denoised = False
+        self.log_every_t = log_every_t
+        self.first_stage_key, self.cond_stage_key = first_stage_key, cond_stage_key
+        self.image_size, self.channels = image_size, channels
+        self.model = DiffusionWrapper(unet_config, conditioning_key)
+        count_params(self.model, verbose=False)
+        self.use_ema = use_ema
+        if use_ema:
+            raise NotImplementedError("EMA shadow weights are a training-loop neighbour (SURVEY.md 8f rank 2)")
+        self.v_posterior, self.original_elbo_weight, self.l_simple_weight = v_posterior, original_elbo_weight, l_simple_weight
+        self.monitor = monitor
+        self.loss_type = loss_type
+        self.register_schedule(given_betas=given_betas, beta_schedule=beta_schedule, timesteps=timesteps,
+                               linear_start=linear_start, linear_end=linear_end, cosine_s=cosine_s)
+        self.learn_logvar = learn_logvar
+        self.logvar = torch.full(fill_value=logvar_init, size=(self.num_timesteps,))
+        if learn_logvar:
+            self.logvar = nn.Parameter(self.logvar, requires_grad=True)
+        self.concat_mode, self.cond_stage_trainable = concat_mode, cond_stage_trainable
+        self.scale_factor = scale_factor
+        self.cond_stage_forward = cond_stage_forward
+        self.instantiate_first_stage(first_stage_config)
+        self.instantiate_cond_stage(cond_stage_config)
+        if ckpt_path is not None:
+            self.init_from_ckpt(ckpt_path, list(ignore_keys))
+
+    # ---- construction -----------------------------------------------------------------------------
+    @property
+    def device(self):
+        return self.betas.device
+
+    def register_schedule(self, given_betas=None, beta_schedule="linear", timesteps=1000, linear_start=1e-4,
+                          linear_end=2e-2, cosine_s=8e-3):
+        """ddpm.py:119-171: float64 numpy math, float32 buffers."""
+        betas = given_betas if given_betas is not None else make_beta_schedule(
+            beta_schedule, timesteps, linear_start=linear_start, linear_end=linear_end, cosine_s=cosine_s)
+        alphas = 1. - betas
+        ac = np.cumprod(alphas, axis=0)
+        ac_prev = np.append(1., ac[:-1])
+        self.num_timesteps = int(betas.shape[0])
+        self.linear_start, self.linear_end = linear_start, linear_end
+        f32 = partial(torch.tensor, dtype=torch.float32)
+        reg = self.register_buffer
+        reg("betas", f32(betas))
+        reg("alphas_cumprod", f32(ac))
+        reg("alphas_cumprod_prev", f32(ac_prev))
+        reg("sqrt_alphas_cumprod", f32(np.sqrt(ac)))
+        reg("sqrt_one_minus_alphas_cumprod", f32(np.sqrt(1. - ac)))
+        reg("log_one_minus_alphas_cumprod", f32(np.log(1. - ac)))
+        reg("sqrt_recip_alphas_cumprod", f32(np.sqrt(1. / ac)))
+        reg("sqrt_recipm1_alphas_cumprod", f32(np.sqrt(1. / ac - 1)))
+        post_var = (1 - self.v_posterior) * betas * (1. - ac_prev) / (1. - ac) + self.v_posterior * betas
+        reg("posterior_variance", f32(post_var))
+        reg("posterior_log_variance_clipped", f32(np.log(np.maximum(post_var, 1e-20))))
+        reg("posterior_mean_coef1", f32(betas * np.sqrt(ac_prev) / (1. - ac)))
+        reg("posterior_mean_coef2", f32((1. - ac_prev) * np.sqrt(alphas) / (1. - ac)))
+        if self.parameterization == "eps":
+            lvlb = self.betas ** 2 / (2 * self.posterior_variance * f32(alphas) * (1 - self.alphas_cumprod))
+        else:
+            lvlb = 0.5 * np.sqrt(torch.Tensor(ac)) / (2. * 1 - torch.Tensor(ac))
+        lvlb[0] = lvlb[1]
+        reg("lvlb_weights", lvlb, persistent=False)
+        assert not torch.isnan(self.lvlb_weights).all()
+
+    def instantiate_first_stage(self, config):
+        model = IdentityFirstStage() if config is None else instantiate_from_config(config)
+        self.first_stage_model = model.eval()
+        self.first_stage_model.train = disabled_train.__get__(self.first_stage_model)
+        for p in self.first_stage_model.parameters():
+            p.requires_grad = False
+
+    def instantiate_cond_stage(self, config):
+        if config in ("__is_unconditional__", None):
+            self.cond_stage_model = None
+        elif config == "__is_first_stage__":
+            self.cond_stage_model = self.first_stage_model
+        else:
+            self.cond_stage_model = instantiate_from_config(config)
+            if not self.cond_stage_trainable:
+                self.cond_stage_model.eval()
+                for p in self.cond_stage_model.parameters():
+                    p.requires_grad = False
+
+    def init_from_ckpt(self, path, ignore_keys=()):
+        sd = torch.load(path, map_location="cpu")
+        sd = sd.get("state_dict", sd)
+        for k in list(sd.keys()):
+            if any(k.startswith(ik) for ik in ignore_keys):
+                del sd[k]
+        missing, unexpected = self.load_state_dict(sd, strict=False)
+        print(f"Restored from {path} with {len(missing)} missing and {len(unexpected)} unexpected keys")
+
+    # ---- conditioning / first stage -------------------------------------------------------------------
+    def get_learned_conditioning(self, c):
+        """ddpm.py:559-570"""
+        if self.cond_stage_model is None:
+            return c
+        if self.cond_stage_forward is None:
+            if hasattr(self.cond_stage_model, "encode") and callable(self.cond_stage_model.encode):
+                c = self.cond_stage_model.encode(c)
+                if hasattr(c, "mode"):
+                    c = c.mode()
+            else:
+                c = self.cond_stage_model(c)
+        else:
+            c = getattr(self.cond_stage_model, self.cond_stage_forward)(c)
+        return c
+
+    def get_first_stage_encoding(self, encoder_posterior):
+        """ddpm.py:550-557"""
+        z = encoder_posterior.sample() if hasattr(encoder_posterior, "sample") else encoder_posterior
+        return self.scale_factor * z
+
+    @torch.no_grad()
+    def encode_first_stage(self, x):
+        return self.first_stage_model.encode(x)
+
+    @torch.no_grad()
+    def decode_first_stage(self, z, predict_cids=False, force_not_quantize=False):
+        """ddpm.py:713-771 (no split_input_params tiling, which EALDM's configs never set)."""
+        z = 1. / self.scale_factor * z
+        return self.first_stage_model.decode(z)
+
+    # ---- denoiser ---------------------------------------------------------------------------------------
+    def apply_model(self, x_noisy, t, cond, return_ids=False):
+        """ddpm.py:912-921,1011-1016"""
+        if not isinstance(cond, dict):
+            if not isinstance(cond, list):
+                cond = [cond]
+            key = "c_concat" if self.model.conditioning_key == "concat" else "c_crossattn"
+            cond = {key: cond}
+        if self.model.conditioning_key is None:
+            cond = {}
+        x_recon = self.model(x_noisy, t, **cond)
+        if isinstance(x_recon, tuple) and not return_ids:
+            return x_recon[0]
+        return x_recon
+
+    def q_sample(self, x_start, t, noise=None):
+        """ddpm.py:276-279 as one kernel (bit-exact)."""
+        noise = torch.randn_like(x_start) if noise is None else noise
+        return ops.q_sample(x_start.float().contiguous(), noise.float().contiguous(), t.contiguous(),
+                            self.sqrt_alphas_cumprod, self.sqrt_one_minus_alphas_cumprod)
+
+    def forward(self, x, c, *args, **kwargs):
+        """ddpm.py:878-900 for an already encoded conditioning `c` = cat([c_neg, c]) (2B rows)."""
+        t = torch.randint(0, self.num_timesteps, (x.shape[0],), device=self.device).long()
+        return self.p_losses(x, c, t, *args, **kwargs)
+
+    def p_losses(self, x_start, cond, t, noise=None):
+        """ddpm.py:1036-1078: the UNet always sees the doubled batch; the guided eps is regressed on noise."""
+        noise = torch.randn_like(x_start) if noise is None else noise
+        x_noisy = self.q_sample(x_start=x_start, t=t, noise=noise)
+        s = self.unconditional_guidance_scale
+        target = noise if self.parameterization == "eps" else x_start
+        if s != 1.:
+            e_u, e_c = self.apply_model(torch.cat([x_noisy] * 2), torch.cat([t] * 2), cond).chunk(2)
+            loss_simple = ops.cfg_mse(e_c.contiguous(), target.contiguous(), e_uncond=e_u.contiguous(), cfg_scale=s)
+        else:
+            loss_simple = ops.cfg_mse(self.apply_model(x_noisy, t, cond).contiguous(), target.contiguous())
+        prefix = "train" if self.training else "val"
+        loss_dict = {f"{prefix}/loss_simple": loss_simple.mean()}
+        logvar_t = self.logvar.to(self.device)[t]
+        loss = loss_simple / torch.exp(logvar_t) + logvar_t
+        if self.learn_logvar:
+            loss_dict[f"{prefix}/loss_gamma"] = loss.mean()
+            loss_dict["logvar"] = self.logvar.data.mean()
+        loss = self.l_simple_weight * loss.mean()
+        loss_vlb = (self.lvlb_weights[t] * loss_simple).mean()
+        loss_dict[f"{prefix}/loss_vlb"] = loss_vlb
+        loss = loss + self.original_elbo_weight * loss_vlb
+        loss_dict[f"{prefix}/loss"] = loss
+        return loss, loss_dict
+
+    @torch.no_grad()
+    def sample_log(self, cond, batch_size, ddim, ddim_steps, **kwargs):
+        """ddpm.py:1267-1285: DDIM with the model's guidance scale; `cond` is cat([c_neg, c])."""
+        if not ddim:
+            raise NotImplementedError("ancestral DDPM sampling is a 'next' row (SURVEY.md 8f rank 4)")
+        sampler = DDIMSampler(self)
+        shape = (self.channels, self.image_size, self.image_size)
+        if self.unconditional_guidance_scale != 1. and cond is not None:
+            c_neg, c = cond.chunk(2)
+            return sampler.sample(ddim_steps, batch_size, shape, c, verbose=False,
+                                  unconditional_guidance_scale=self.unconditional_guidance_scale,
+                                  unconditional_conditioning=c_neg, **kwargs)
+        return sampler.sample(ddim_steps, batch_size, shape, cond, verbose=False, **kwargs)

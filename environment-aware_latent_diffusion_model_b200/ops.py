@@ -108,9 +108,11 @@ def conv(srcs: Sequence[ConvIn], weight: torch.Tensor, out: Act, *, bias: Option
         a.rowvec = rowvec.data_ptr() + 4 * rowvec_col0
         a.ld_rowvec = rowvec.shape[1]
     if residual is not None:
-        assert residual.dtype == x0.dtype and residual.rows == out.rows and residual.c == out.c
+        assert residual.rows == out.rows and residual.c == out.c
+        assert residual.dtype in (x0.dtype, torch.float32)
         a.residual = residual.ptr
         a.ld_res = residual.ld
+        a.res_f32 = 1 if (residual.dtype == torch.float32 and x0.dtype != torch.float32) else 0
     a.out = out.ptr
     a.ld_out = out.ld
     a.out_f32 = 1 if (out.dtype == torch.float32 and x0.dtype != torch.float32) else 0
@@ -131,8 +133,14 @@ def linear(x: Act, weight: torch.Tensor, out: Act, **kw) -> Act:
     return out
 
 
-def group_norm(x: Act, gamma: torch.Tensor, beta: torch.Tensor, eps: float, out: Act, stats: torch.Tensor,
-               *, groups: int = 32, silu: bool = False) -> Act:
+def group_norm_workspace(n: int, hw: int, c: int, device) -> torch.Tensor:
+    """Scratch for group_norm (ealdm_group_norm_workspace_bytes); reusable across calls on one stream."""
+    nbytes = int(L.load().ealdm_group_norm_workspace_bytes(n, hw, c))
+    return torch.empty((max(nbytes, 8) + 7) // 8, dtype=torch.float64, device=device)
+
+
+def group_norm(x: Act, gamma: torch.Tensor, beta: torch.Tensor, eps: float, out: Act,
+               workspace: Optional[torch.Tensor] = None, *, groups: int = 32, silu: bool = False) -> Act:
     lib = L.load()
     a = L.GroupNormArgs()
     a.dtype = _dt(x.dtype)
@@ -143,8 +151,11 @@ def group_norm(x: Act, gamma: torch.Tensor, beta: torch.Tensor, eps: float, out:
     a.gamma, a.beta = gamma.data_ptr(), beta.data_ptr()
     assert out.dtype == x.dtype and out.rows == x.rows and out.c == x.c
     a.y, a.ld_y = out.ptr, out.ld
-    assert stats.dtype == torch.float64 and stats.numel() >= x.n * groups * 2
-    a.stats = stats.data_ptr()
+    need = int(lib.ealdm_group_norm_workspace_bytes(x.n, x.h * x.w, x.c))
+    if workspace is None:
+        workspace = group_norm_workspace(x.n, x.h * x.w, x.c, x.buf.device)
+    assert workspace.numel() * workspace.element_size() >= need, "group_norm workspace too small"
+    a.workspace = workspace.data_ptr()
     L.check(lib.ealdm_group_norm(C.byref(a), _stream()))
     return out
 
@@ -152,11 +163,12 @@ def group_norm(x: Act, gamma: torch.Tensor, beta: torch.Tensor, eps: float, out:
 def layer_norm(x: Act, gamma: torch.Tensor, beta: torch.Tensor, eps: float, out: Act) -> Act:
     lib = L.load()
     a = L.LayerNormArgs()
-    a.dtype = _dt(x.dtype)
+    a.dtype = _dt(out.dtype)
+    a.x_f32 = 1 if (x.dtype == torch.float32 and out.dtype != torch.float32) else 0
     a.x, a.rows, a.c, a.ld_x, a.eps = x.ptr, x.rows, x.c, x.ld, eps
     assert gamma.dtype == torch.float32 and gamma.numel() == x.c
     a.gamma, a.beta = gamma.data_ptr(), beta.data_ptr()
-    assert out.dtype == x.dtype and out.rows == x.rows and out.c == x.c
+    assert out.rows == x.rows and out.c == x.c and (out.dtype == x.dtype or x.dtype == torch.float32)
     a.y, a.ld_y = out.ptr, out.ld
     L.check(lib.ealdm_layer_norm(C.byref(a), _stream()))
     return out

@@ -1,0 +1,578 @@
+"""Drop-in `UNetModel` for EALDM's `unet_config.target` (reference:
+ldm/modules/diffusionmodules/openaimodel.py:413-742).
+
+The module tree below exists to own the parameters under the reference's names and shapes (so
+reference checkpoints load with strict=True and EMA / optimizers see the same tensors); the leaf
+`nn.Conv2d` / `nn.Linear` / `nn.GroupNorm` / `nn.LayerNorm` objects are never called.  `forward`
+hands the whole network to `UNetEngine`, which packs the weights to kernel layout once and then
+issues libealdm_b200 kernels on NHWC activations (see DESIGN.md for the data layout).
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+from . import ops
+from .ops import Act, ConvIn
+from .packing import geglu_interleave, pack_conv_weight
+
+
+def zero_module(module: nn.Module) -> nn.Module:
+    """Reference initialisation of output convs (openaimodel.py:229-231,312,685; attention.py:244)."""
+    for p in module.parameters():
+        p.detach().zero_()
+    return module
+
+
+# ---- parameter-owning modules (names mirror the reference) -----------------------------------------
+class TimestepEmbedSequential(nn.Sequential):
+    """openaimodel.py:74-88"""
+
+
+class Upsample(nn.Module):
+    """openaimodel.py:91-119: nearest 2x then conv3x3."""
+
+    def __init__(self, channels, use_conv, dims=2, out_channels=None, padding=1):
+        super().__init__()
+        self.channels, self.out_channels, self.use_conv = channels, out_channels or channels, use_conv
+        if not use_conv:
+            raise NotImplementedError("Upsample without convolution (conv_resample=False)")
+        self.conv = nn.Conv2d(channels, self.out_channels, 3, padding=padding)
+
+
+class Downsample(nn.Module):
+    """openaimodel.py:134-160: conv3x3 stride 2 pad 1."""
+
+    def __init__(self, channels, use_conv, dims=2, out_channels=None, padding=1):
+        super().__init__()
+        self.channels, self.out_channels, self.use_conv = channels, out_channels or channels, use_conv
+        if not use_conv:
+            raise NotImplementedError("Downsample without convolution (conv_resample=False)")
+        self.op = nn.Conv2d(channels, self.out_channels, 3, stride=2, padding=padding)
+
+
+class ResBlock(nn.Module):
+    """openaimodel.py:163-275"""
+
+    def __init__(self, channels, emb_channels, dropout, out_channels=None):
+        super().__init__()
+        self.channels, self.out_channels = channels, out_channels or channels
+        self.in_layers = nn.Sequential(nn.GroupNorm(32, channels), nn.SiLU(),
+                                       nn.Conv2d(channels, self.out_channels, 3, padding=1))
+        self.emb_layers = nn.Sequential(nn.SiLU(), nn.Linear(emb_channels, self.out_channels))
+        self.out_layers = nn.Sequential(nn.GroupNorm(32, self.out_channels), nn.SiLU(), nn.Dropout(p=dropout),
+                                        zero_module(nn.Conv2d(self.out_channels, self.out_channels, 3, padding=1)))
+        self.skip_connection = (nn.Identity() if self.out_channels == channels
+                                else nn.Conv2d(channels, self.out_channels, 1))
+
+
+class AttentionBlock(nn.Module):
+    """openaimodel.py:278-324 with QKVAttentionLegacy (:347-372)."""
+
+    def __init__(self, channels, num_heads=1, num_head_channels=-1):
+        super().__init__()
+        self.channels = channels
+        self.num_heads = num_heads if num_head_channels == -1 else channels // num_head_channels
+        self.norm = nn.GroupNorm(32, channels)
+        self.qkv = nn.Conv1d(channels, channels * 3, 1)
+        self.proj_out = zero_module(nn.Conv1d(channels, channels, 1))
+
+
+class CrossAttention(nn.Module):
+    """attention.py:152-193"""
+
+    def __init__(self, query_dim, context_dim=None, heads=8, dim_head=64):
+        super().__init__()
+        inner = dim_head * heads
+        context_dim = query_dim if context_dim is None else context_dim
+        self.heads, self.dim_head, self.scale = heads, dim_head, dim_head ** -0.5
+        self.to_q = nn.Linear(query_dim, inner, bias=False)
+        self.to_k = nn.Linear(context_dim, inner, bias=False)
+        self.to_v = nn.Linear(context_dim, inner, bias=False)
+        self.to_out = nn.Sequential(nn.Linear(inner, query_dim), nn.Dropout(0.0))
+
+
+class GEGLU(nn.Module):
+    """attention.py:37-44"""
+
+    def __init__(self, dim_in, dim_out):
+        super().__init__()
+        self.proj = nn.Linear(dim_in, dim_out * 2)
+
+
+class FeedForward(nn.Module):
+    """attention.py:47-64 (glu=True)"""
+
+    def __init__(self, dim, mult=4):
+        super().__init__()
+        self.net = nn.Sequential(GEGLU(dim, dim * mult), nn.Dropout(0.0), nn.Linear(dim * mult, dim))
+
+
+class BasicTransformerBlock(nn.Module):
+    """attention.py:196-215"""
+
+    def __init__(self, dim, n_heads, d_head, context_dim=None):
+        super().__init__()
+        self.attn1 = CrossAttention(dim, heads=n_heads, dim_head=d_head)
+        self.ff = FeedForward(dim)
+        self.attn2 = CrossAttention(dim, context_dim=context_dim, heads=n_heads, dim_head=d_head)
+        self.norm1, self.norm2, self.norm3 = nn.LayerNorm(dim), nn.LayerNorm(dim), nn.LayerNorm(dim)
+
+
+class SpatialTransformer(nn.Module):
+    """attention.py:218-261"""
+
+    def __init__(self, in_channels, n_heads, d_head, depth=1, context_dim=None):
+        super().__init__()
+        self.in_channels, self.n_heads, self.d_head = in_channels, n_heads, d_head
+        inner = n_heads * d_head
+        self.norm = nn.GroupNorm(32, in_channels, eps=1e-6)
+        self.proj_in = nn.Conv2d(in_channels, inner, 1)
+        self.transformer_blocks = nn.ModuleList(
+            [BasicTransformerBlock(inner, n_heads, d_head, context_dim=context_dim) for _ in range(depth)])
+        self.proj_out = zero_module(nn.Conv2d(inner, in_channels, 1))
+
+
+class UNetModel(nn.Module):
+    """Same constructor contract as the reference UNetModel (openaimodel.py:443-469); combinations the
+    EALDM configs never use raise NotImplementedError instead of silently diverging.
+    Extra keyword (not in the reference): `compute_dtype` in {"bf16", "fp32"} selects the tensor-core
+    path (default) or the fp32 parity path; it can also be switched later with `set_compute_dtype`."""
+
+    def __init__(self, image_size, in_channels, model_channels, out_channels, num_res_blocks,
+                 attention_resolutions, dropout=0, channel_mult=(1, 2, 4, 8), conv_resample=True, dims=2,
+                 num_classes=None, use_checkpoint=False, use_fp16=False, num_heads=-1, num_head_channels=-1,
+                 num_heads_upsample=-1, use_scale_shift_norm=False, resblock_updown=False,
+                 use_new_attention_order=False, use_spatial_transformer=False, transformer_depth=1,
+                 context_dim=None, n_embed=None, legacy=True, compute_dtype="bf16"):
+        super().__init__()
+        if use_spatial_transformer:
+            assert context_dim is not None, "context_dim is required with use_spatial_transformer"
+        if context_dim is not None:
+            assert use_spatial_transformer, "context_dim requires use_spatial_transformer"
+            if not isinstance(context_dim, int):
+                context_dim = list(context_dim)
+                assert len(context_dim) == 1, "one context_dim per transformer depth is not supported"
+                context_dim = context_dim[0]
+        for flag, name in ((dims != 2, "dims != 2"), (num_classes is not None, "num_classes"),
+                           (use_scale_shift_norm, "use_scale_shift_norm"), (resblock_updown, "resblock_updown"),
+                           (use_new_attention_order, "use_new_attention_order"), (n_embed is not None, "n_embed"),
+                           (not conv_resample, "conv_resample=False"), (dropout != 0, "dropout != 0")):
+            if flag:
+                raise NotImplementedError(f"UNetModel option not supported by the B200 path: {name}")
+        if num_heads_upsample == -1:
+            num_heads_upsample = num_heads
+        if num_heads == -1:
+            assert num_head_channels != -1, "Either num_heads or num_head_channels has to be set"
+        if num_head_channels == -1:
+            assert num_heads != -1, "Either num_heads or num_head_channels has to be set"
+
+        self.image_size, self.in_channels, self.model_channels = image_size, in_channels, model_channels
+        self.out_channels, self.num_res_blocks = out_channels, num_res_blocks
+        self.attention_resolutions, self.dropout = attention_resolutions, dropout
+        self.channel_mult, self.conv_resample, self.num_classes = channel_mult, conv_resample, num_classes
+        self.use_checkpoint = use_checkpoint
+        self.dtype = torch.float16 if use_fp16 else torch.float32  # reference attribute (openaimodel.py:500)
+        self.num_heads, self.num_head_channels, self.num_heads_upsample = num_heads, num_head_channels, num_heads_upsample
+        self.predict_codebook_ids = False
+        self.use_spatial_transformer, self.context_dim = use_spatial_transformer, context_dim
+
+        ted = model_channels * 4
+        self.time_embed = nn.Sequential(nn.Linear(model_channels, ted), nn.SiLU(), nn.Linear(ted, ted))
+
+        def attn_layer(ch):
+            nonlocal num_heads
+            if num_head_channels == -1:
+                dim_head = ch // num_heads
+            else:
+                num_heads = ch // num_head_channels
+                dim_head = num_head_channels
+            if legacy:
+                dim_head = ch // num_heads if use_spatial_transformer else num_head_channels
+            if use_spatial_transformer:
+                return SpatialTransformer(ch, num_heads, dim_head, depth=transformer_depth, context_dim=context_dim)
+            return AttentionBlock(ch, num_heads=num_heads, num_head_channels=dim_head)
+
+        self.input_blocks = nn.ModuleList([TimestepEmbedSequential(nn.Conv2d(in_channels, model_channels, 3, padding=1))])
+        chans = [model_channels]
+        ch, ds = model_channels, 1
+        for level, mult in enumerate(channel_mult):
+            for _ in range(num_res_blocks):
+                layers: List[nn.Module] = [ResBlock(ch, ted, dropout, out_channels=mult * model_channels)]
+                ch = mult * model_channels
+                if ds in attention_resolutions:
+                    layers.append(attn_layer(ch))
+                self.input_blocks.append(TimestepEmbedSequential(*layers))
+                chans.append(ch)
+            if level != len(channel_mult) - 1:
+                self.input_blocks.append(TimestepEmbedSequential(Downsample(ch, conv_resample, out_channels=ch)))
+                chans.append(ch)
+                ds *= 2
+        self.middle_block = TimestepEmbedSequential(ResBlock(ch, ted, dropout), attn_layer(ch), ResBlock(ch, ted, dropout))
+        self.output_blocks = nn.ModuleList([])
+        for level, mult in list(enumerate(channel_mult))[::-1]:
+            for i in range(num_res_blocks + 1):
+                ich = chans.pop()
+                layers = [ResBlock(ch + ich, ted, dropout, out_channels=model_channels * mult)]
+                ch = model_channels * mult
+                if ds in attention_resolutions:
+                    layers.append(attn_layer(ch))
+                if level and i == num_res_blocks:
+                    layers.append(Upsample(ch, conv_resample, out_channels=ch))
+                    ds //= 2
+                self.output_blocks.append(TimestepEmbedSequential(*layers))
+        self.out = nn.Sequential(nn.GroupNorm(32, ch), nn.SiLU(),
+                                 zero_module(nn.Conv2d(model_channels, out_channels, 3, padding=1)))
+
+        self._compute_dtype = {"bf16": torch.bfloat16, "fp32": torch.float32}[compute_dtype]
+        self._engine: Optional["UNetEngine"] = None
+        self.register_load_state_dict_post_hook(lambda m, keys: m.invalidate_packed())
+
+    # ---- engine management -------------------------------------------------------------------------
+    def set_compute_dtype(self, name: str) -> "UNetModel":
+        self._compute_dtype = {"bf16": torch.bfloat16, "fp32": torch.float32}[name]
+        self._engine = None
+        return self
+
+    def invalidate_packed(self):
+        """Drop the packed kernel-layout weights (call after modifying parameters in place)."""
+        self._engine = None
+
+    def _apply(self, fn, *a, **k):
+        self._engine = None
+        return super()._apply(fn, *a, **k)
+
+    def convert_to_fp16(self):  # reference stubs (openaimodel.py:694-708): no-ops there as well
+        pass
+
+    def convert_to_fp32(self):
+        pass
+
+    def forward(self, x, timesteps=None, context=None, y=None, **kwargs):
+        """x [N, C, H, W] fp32 (CUDA), timesteps [N] int64, context [N, T, context_dim] -> [N, out_channels, H, W]."""
+        assert (y is not None) == (self.num_classes is not None), \
+            "must specify y if and only if the model is class-conditional"
+        if not x.is_cuda:
+            raise RuntimeError("ealdm_b200.UNetModel runs on CUDA (sm_100a) only; there is no CPU fallback")
+        if self._engine is None:
+            self._engine = UNetEngine(self, self._compute_dtype)
+        return self._engine.forward(x, timesteps, context)
+
+
+# ---- execution engine --------------------------------------------------------------------------------
+class _PackedConv:
+    __slots__ = ("w", "b", "cout")
+
+    def __init__(self, w, b, cout):
+        self.w, self.b, self.cout = w, b, cout
+
+
+class UNetEngine:
+    """Packs a UNetModel's parameters to kernel layout and runs the forward pass as a straight-line
+    sequence of libealdm_b200 launches on the current CUDA stream (CUDA-graph capturable: no host
+    synchronisation, no data-dependent control flow)."""
+
+    def __init__(self, m: UNetModel, dtype: torch.dtype):
+        L.load()
+        self.m, self.dt = m, dtype
+        dev = next(m.parameters()).device
+        assert dev.type == "cuda", "move the model to CUDA before the first forward"
+        self.dev = dev
+        f32 = lambda t: t.detach().float().contiguous()  # noqa: E731
+        pk = lambda conv: pack_conv_weight(conv.weight, dtype)  # noqa: E731
+        half = m.model_channels // 2
+        self.freqs = torch.exp(-math.log(10000) * torch.arange(0, half, dtype=torch.float32) / half).to(dev)
+        self.te0 = _PackedConv(m.time_embed[0].weight.detach().to(dtype).contiguous(), f32(m.time_embed[0].bias), 0)
+        self.te2 = _PackedConv(m.time_embed[2].weight.detach().to(dtype).contiguous(), f32(m.time_embed[2].bias), 0)
+
+        self.blocks = []          # execution list
+        emb_w, emb_b = [], []     # all ResBlock emb_layers stacked into one GEMM
+        kv_w = []                 # all cross-attention to_k / to_v stacked into one GEMM
+        self.emb_cols = 0
+        self.kv_cols = 0
+
+        def pack_res(rb: ResBlock):
+            d = {"kind": "res", "cin": rb.channels, "cout": rb.out_channels}
+            d["gn1"] = (f32(rb.in_layers[0].weight), f32(rb.in_layers[0].bias))
+            d["conv1"] = _PackedConv(pk(rb.in_layers[2]), f32(rb.in_layers[2].bias), rb.out_channels)
+            d["emb_col0"] = self.emb_cols
+            emb_w.append(rb.emb_layers[1].weight.detach())
+            emb_b.append(rb.emb_layers[1].bias.detach())
+            self.emb_cols += rb.out_channels
+            d["gn2"] = (f32(rb.out_layers[0].weight), f32(rb.out_layers[0].bias))
+            w2, b2 = pk(rb.out_layers[3]), f32(rb.out_layers[3].bias)
+            if isinstance(rb.skip_connection, nn.Identity):
+                d["skip"] = False
+            else:  # 1x1 skip conv accumulated in the same GEMM: K = 9*cout + cin
+                w2 = torch.cat([w2, pk(rb.skip_connection)], dim=1).contiguous()
+                b2 = b2 + f32(rb.skip_connection.bias)
+                d["skip"] = True
+            d["conv2"] = _PackedConv(w2, b2, rb.out_channels)
+            return d
+
+        def pack_st(st: SpatialTransformer):
+            C_ = st.in_channels
+            d = {"kind": "st", "c": C_, "heads": st.n_heads, "dh": st.d_head}
+            assert st.d_head in (32, 64), "head_dim must be 32 or 64"
+            d["norm"] = (f32(st.norm.weight), f32(st.norm.bias))
+            d["proj_in"] = _PackedConv(pk(st.proj_in), f32(st.proj_in.bias), C_)
+            d["proj_out"] = _PackedConv(pk(st.proj_out), f32(st.proj_out.bias), C_)
+            d["blocks"] = []
+            for tb in st.transformer_blocks:
+                t = {}
+                for i, ln in ((1, tb.norm1), (2, tb.norm2), (3, tb.norm3)):
+                    t[f"ln{i}"] = (f32(ln.weight), f32(ln.bias))
+                t["qkv"] = torch.cat([tb.attn1.to_q.weight, tb.attn1.to_k.weight, tb.attn1.to_v.weight],
+                                     dim=0).detach().to(dtype).contiguous()
+                t["o1"] = _PackedConv(tb.attn1.to_out[0].weight.detach().to(dtype).contiguous(),
+                                      f32(tb.attn1.to_out[0].bias), C_)
+                t["q2"] = tb.attn2.to_q.weight.detach().to(dtype).contiguous()
+                t["kv_col0"] = self.kv_cols
+                kv_w.append(torch.cat([tb.attn2.to_k.weight, tb.attn2.to_v.weight], dim=0).detach())
+                self.kv_cols += 2 * C_
+                t["o2"] = _PackedConv(tb.attn2.to_out[0].weight.detach().to(dtype).contiguous(),
+                                      f32(tb.attn2.to_out[0].bias), C_)
+                wi, bi = geglu_interleave(tb.ff.net[0].proj.weight.to(dtype), tb.ff.net[0].proj.bias)
+                t["ff1"] = _PackedConv(wi, bi, 4 * C_)
+                t["ff2"] = _PackedConv(tb.ff.net[2].weight.detach().to(dtype).contiguous(), f32(tb.ff.net[2].bias), C_)
+                d["blocks"].append(t)
+            return d
+
+        def pack_ab(ab: AttentionBlock):
+            C_ = ab.channels
+            assert C_ // ab.num_heads in (32, 64), "head_dim must be 32 or 64"
+            return {"kind": "ab", "c": C_, "heads": ab.num_heads, "norm": (f32(ab.norm.weight), f32(ab.norm.bias)),
+                    "qkv": _PackedConv(pk(ab.qkv), f32(ab.qkv.bias), 3 * C_),
+                    "proj": _PackedConv(pk(ab.proj_out), f32(ab.proj_out.bias), C_)}
+
+        def pack_layers(seq):
+            out = []
+            for layer in seq:
+                if isinstance(layer, ResBlock):
+                    out.append(pack_res(layer))
+                elif isinstance(layer, SpatialTransformer):
+                    out.append(pack_st(layer))
+                elif isinstance(layer, AttentionBlock):
+                    out.append(pack_ab(layer))
+                elif isinstance(layer, Downsample):
+                    out.append({"kind": "down", "c": layer.channels,
+                                "conv": _PackedConv(pk(layer.op), f32(layer.op.bias), layer.out_channels)})
+                elif isinstance(layer, Upsample):
+                    out.append({"kind": "up", "c": layer.channels,
+                                "conv": _PackedConv(pk(layer.conv), f32(layer.conv.bias), layer.out_channels)})
+                elif isinstance(layer, nn.Conv2d):
+                    out.append({"kind": "conv_in", "conv": _PackedConv(pk(layer), f32(layer.bias), layer.out_channels)})
+                else:
+                    raise TypeError(type(layer))
+            return out
+
+        self.inp = [pack_layers(b) for b in m.input_blocks]
+        self.mid = pack_layers(m.middle_block)
+        self.outb = [pack_layers(b) for b in m.output_blocks]
+        self.out_norm = (f32(m.out[0].weight), f32(m.out[0].bias))
+        self.out_conv = _PackedConv(pk(m.out[2]), f32(m.out[2].bias), m.out_channels)
+        self.emb_w = torch.cat(emb_w, dim=0).to(dtype).contiguous()
+        self.emb_b = torch.cat(emb_b, dim=0).float().contiguous()
+        self.kv_w = torch.cat(kv_w, dim=0).to(dtype).contiguous() if kv_w else None
+
+        # channel bookkeeping for the zero-copy skip concatenation
+        def block_out_channels(layers, cin):
+            c = cin
+            for d in layers:
+                if d["kind"] in ("res",):
+                    c = d["cout"]
+                elif d["kind"] == "conv_in":
+                    c = d["conv"].cout
+            return c
+
+        self.skip_ch = []
+        c = m.in_channels
+        for layers in self.inp:
+            c = block_out_channels(layers, c)
+            self.skip_ch.append(c)
+        self.mid_ch = c
+
+    # ---- helpers --------------------------------------------------------------------------------------
+    def _new(self, n, h, w, c, dtype=None) -> Act:
+        return Act.empty(n, h, w, c, dtype or self.dt, self.dev)
+
+    def _res(self, d, x: Act, emb_all: torch.Tensor, dest: Optional[Act]) -> Act:
+        hn = self._new(x.n, x.h, x.w, x.c)
+        ops.group_norm(x, d["gn1"][0], d["gn1"][1], 1e-5, hn, self.stats, silu=True)
+        h1 = self._new(x.n, x.h, x.w, d["cout"])
+        ops.conv([ConvIn(hn, 3, 1, 1)], d["conv1"].w, h1, bias=d["conv1"].b, rowvec=emb_all,
+                 rowvec_col0=d["emb_col0"])
+        hn2 = self._new(x.n, x.h, x.w, d["cout"])
+        ops.group_norm(h1, d["gn2"][0], d["gn2"][1], 1e-5, hn2, self.stats, silu=True)
+        out = dest if dest is not None else self._new(x.n, x.h, x.w, d["cout"])
+        if d["skip"]:
+            ops.conv([ConvIn(hn2, 3, 1, 1), ConvIn(x, 1, 1, 0)], d["conv2"].w, out, bias=d["conv2"].b)
+        else:
+            ops.conv([ConvIn(hn2, 3, 1, 1)], d["conv2"].w, out, bias=d["conv2"].b, residual=x)
+        return out
+
+    def _st(self, d, x: Act, kv_all: Optional[Act], n_ctx: int, dest: Optional[Act]) -> Act:
+        C_, heads, dh = d["c"], d["heads"], d["dh"]
+        n, h, w = x.n, x.h, x.w
+        tok = h * w
+        xn = self._new(n, h, w, C_)
+        ops.group_norm(x, d["norm"][0], d["norm"][1], 1e-6, xn, self.stats, silu=False)
+        # the token residual stream t -> t1 -> t2 stays fp32 (as under torch autocast); only GEMM
+        # operands (LayerNorm outputs, attention outputs, the GEGLU product) are bf16
+        f32 = torch.float32
+        t = self._new(n, h, w, C_, f32)
+        ops.linear(xn, d["proj_in"].w, t, bias=d["proj_in"].b)
+        for bi, tb in enumerate(d["blocks"]):
+            a = self._new(n, h, w, C_)
+            ops.layer_norm(t, tb["ln1"][0], tb["ln1"][1], 1e-5, a)
+            qkv = self._new(n, h, w, 3 * C_)
+            ops.linear(a, tb["qkv"], qkv)
+            o = self._new(n, h, w, C_)
+            ops.attention(qkv.cols(0, C_), qkv.cols(C_, C_), qkv.cols(2 * C_, C_), o, batch=n, heads=heads,
+                          head_dim=dh, n_q=tok, n_kv=tok, scale=dh ** -0.5)
+            t1 = self._new(n, h, w, C_, f32)
+            ops.linear(o, tb["o1"].w, t1, bias=tb["o1"].b, residual=t)
+            ops.layer_norm(t1, tb["ln2"][0], tb["ln2"][1], 1e-5, a)
+            q2 = self._new(n, h, w, C_)
+            ops.linear(a, tb["q2"], q2)
+            o2 = self._new(n, h, w, C_)
+            if kv_all is None:
+                raise RuntimeError("SpatialTransformer needs a context tensor")
+            kc = tb["kv_col0"]
+            ops.attention(q2, kv_all.cols(kc, C_), kv_all.cols(kc + C_, C_), o2, batch=n, heads=heads, head_dim=dh,
+                          n_q=tok, n_kv=n_ctx, scale=dh ** -0.5)
+            t2 = self._new(n, h, w, C_, f32)
+            ops.linear(o2, tb["o2"].w, t2, bias=tb["o2"].b, residual=t1)
+            ops.layer_norm(t2, tb["ln3"][0], tb["ln3"][1], 1e-5, a)
+            gg = self._new(n, h, w, 4 * C_)
+            ops.linear(a, tb["ff1"].w, gg, bias=tb["ff1"].b, act=L.ACT_GEGLU)
+            last = bi == len(d["blocks"]) - 1   # the last t feeds proj_out as a GEMM operand -> bf16
+            t = self._new(n, h, w, C_, None if last else f32)
+            ops.linear(gg, tb["ff2"].w, t, bias=tb["ff2"].b, residual=t2)
+        out = dest if dest is not None else self._new(n, h, w, C_)
+        ops.linear(t, d["proj_out"].w, out, bias=d["proj_out"].b, residual=x)
+        return out
+
+    def _ab(self, d, x: Act, dest: Optional[Act]) -> Act:
+        C_, heads = d["c"], d["heads"]
+        dh = C_ // heads
+        n, h, w = x.n, x.h, x.w
+        xn = self._new(n, h, w, C_)
+        ops.group_norm(x, d["norm"][0], d["norm"][1], 1e-5, xn, self.stats, silu=False)
+        qkv = self._new(n, h, w, 3 * C_)
+        ops.linear(xn, d["qkv"].w, qkv, bias=d["qkv"].b)
+        o = self._new(n, h, w, C_)
+        span = 3 * C_ - 2 * dh  # column window that keeps every head's slice inside the buffer
+        ops.attention(qkv.cols(0, span), qkv.cols(dh, span), qkv.cols(2 * dh, span), o, batch=n, heads=heads,
+                      head_dim=dh, n_q=h * w, n_kv=h * w, scale=dh ** -0.5, head_stride_q=3 * dh,
+                      head_stride_kv=3 * dh)
+        out = dest if dest is not None else self._new(n, h, w, C_)
+        ops.linear(o, d["proj"].w, out, bias=d["proj"].b, residual=x)
+        return out
+
+    def _run(self, layers, x: Act, emb_all, kv_all, n_ctx, dest: Optional[Act]) -> Act:
+        for i, d in enumerate(layers):
+            dst = dest if i == len(layers) - 1 else None
+            k = d["kind"]
+            if k == "res":
+                x = self._res(d, x, emb_all, dst)
+            elif k == "st":
+                x = self._st(d, x, kv_all, n_ctx, dst)
+            elif k == "ab":
+                x = self._ab(d, x, dst)
+            elif k == "conv_in":
+                out = dst if dst is not None else self._new(x.n, x.h, x.w, d["conv"].cout)
+                x = ops.conv([ConvIn(x, 3, 1, 1)], d["conv"].w, out, bias=d["conv"].b)
+            elif k == "down":
+                out = dst if dst is not None else self._new(x.n, x.h // 2, x.w // 2, d["conv"].cout)
+                x = ops.conv([ConvIn(x, 3, 2, 1)], d["conv"].w, out, bias=d["conv"].b)
+            elif k == "up":
+                out = dst if dst is not None else self._new(x.n, x.h * 2, x.w * 2, d["conv"].cout)
+                if self.dt == torch.bfloat16:
+                    up = self._new(x.n, x.h * 2, x.w * 2, x.c)
+                    ops.upsample_nearest2x(x, up)
+                    x = ops.conv([ConvIn(up, 3, 1, 1)], d["conv"].w, out, bias=d["conv"].b)
+                else:
+                    x = ops.conv([ConvIn(x, 3, 1, 1, upsample=1)], d["conv"].w, out, bias=d["conv"].b)
+            else:
+                raise ValueError(k)
+        return x
+
+    # ---- forward ----------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor, timesteps: torch.Tensor, context: Optional[torch.Tensor]) -> torch.Tensor:
+        m, dt, dev = self.m, self.dt, self.dev
+        n, cin, H, W = x.shape
+        assert cin == m.in_channels
+        x = x.float().contiguous()
+        timesteps = timesteps.to(device=dev, dtype=torch.int64).contiguous()
+        assert timesteps.shape == (n,)
+        # one GroupNorm scratch for the whole forward, sized for the widest concat at the finest level
+        self.stats = ops.group_norm_workspace(n, H * W, 2 * self.mid_ch, dev)
+
+        # timestep embedding -> time_embed MLP -> SiLU(emb) -> every ResBlock's emb_layers in ONE GEMM
+        temb = torch.empty((n, m.model_channels), dtype=dt, device=dev)
+        ops.timestep_embedding(timesteps, m.model_channels, self.freqs, temb)
+        ted = self.te0.w.shape[0]
+        e1 = Act.empty(1, 1, n, ted, dt, dev)
+        ops.linear(Act(temb, 1, 1, n), self.te0.w, e1, bias=self.te0.b, act=L.ACT_SILU)
+        semb = Act.empty(1, 1, n, ted, dt, dev)
+        ops.linear(e1, self.te2.w, semb, bias=self.te2.b, act=L.ACT_SILU)
+        emb_all = Act.empty(1, 1, n, self.emb_cols, torch.float32, dev)
+        ops.linear(semb, self.emb_w, emb_all, bias=self.emb_b)
+
+        # context -> K/V of every cross-attention layer in ONE GEMM (loop-invariant across DDIM steps)
+        kv_all, n_ctx = None, 0
+        if self.kv_w is not None:
+            if context is None:
+                raise RuntimeError("this UNet was built with context_dim: pass context=[N, T, context_dim]")
+            assert context.shape[0] == n and context.shape[2] == self.kv_w.shape[1]
+            n_ctx = context.shape[1]
+            csrc = Act(context.float().reshape(n * n_ctx, -1).contiguous(), n, 1, n_ctx)
+            ctx = ops.copy2d(csrc, Act.empty(n, 1, n_ctx, csrc.c, dt, dev)) if dt != torch.float32 else csrc
+            kv_all = Act.empty(n, 1, n_ctx, self.kv_cols, dt, dev)
+            ops.linear(ctx, self.kv_w, kv_all)
+
+        # concat buffers of the output blocks: [h | skip]; producers write straight into them
+        n_in = len(self.inp)
+        res = [(H, W)]
+        for layers in self.inp[1:]:
+            hh, ww = res[-1]
+            res.append((hh // 2, ww // 2) if layers[0]["kind"] == "down" else (hh, ww))
+        cat = []
+        h_ch = self.mid_ch
+        for j, layers in enumerate(self.outb):
+            i = n_in - 1 - j                       # skip partner (hs.pop(), openaimodel.py:736)
+            hh, ww = res[i]
+            cat.append(self._new(n, hh, ww, h_ch + self.skip_ch[i]))
+            h_ch = layers[0]["cout"]
+        skip_dst = [cat[n_in - 1 - i].cols(cat[n_in - 1 - i].c - self.skip_ch[i], self.skip_ch[i]) for i in range(n_in)]
+
+        xin = self._new(n, H, W, cin)
+        ops.nchw_to_nhwc(x, xin)
+        h = xin
+        for i, layers in enumerate(self.inp):
+            h = self._run(layers, h, emb_all.buf, kv_all, n_ctx, skip_dst[i])
+        mid_dst = cat[0].cols(0, self.mid_ch)
+        h = self._run(self.mid, h, emb_all.buf, kv_all, n_ctx, mid_dst)
+        for j, layers in enumerate(self.outb):
+            if j + 1 < len(self.outb):
+                nxt = cat[j + 1]
+                dst = nxt.cols(0, nxt.c - self.skip_ch[n_in - 2 - j])
+            else:
+                dst = None
+            h = self._run(layers, cat[j], emb_all.buf, kv_all, n_ctx, dst)
+
+        hn = self._new(n, H, W, h.c)
+        ops.group_norm(h, self.out_norm[0], self.out_norm[1], 1e-5, hn, self.stats, silu=True)
+        co = m.out_channels
+        co_pad = (co + 7) // 8 * 8
+        obuf = Act.empty(n, H, W, co_pad, torch.float32, dev)
+        ops.conv([ConvIn(hn, 3, 1, 1)], self.out_conv.w, obuf.cols(0, co), bias=self.out_conv.b)
+        y = torch.empty((n, co, H, W), dtype=torch.float32, device=dev)
+        ops.nhwc_to_nchw(obuf.cols(0, co), y)
+        return y

@@ -99,7 +99,7 @@ typedef struct {
   void* out;
   int64_t ld_out;
   int32_t out_f32; /* 1: `out` is float regardless of dtype */
-  int32_t reserved;
+  int32_t res_f32; /* 1: `residual` is float regardless of dtype (fp32 residual stream) */
 } ealdm_conv_args;
 
 int ealdm_conv(const ealdm_conv_args* a, ealdm_stream_t stream);
@@ -107,8 +107,9 @@ int ealdm_conv(const ealdm_conv_args* a, ealdm_stream_t stream);
 /* ---- normalisation -------------------------------------------------------------------------- */
 /*
  * GroupNorm over (c/groups, hw) per image with biased variance, affine, optional SiLU.
- * `stats` is a caller-provided workspace of n*groups*2 doubles (sum, sum of squares); the call
- * zeroes it, accumulates it and consumes it.
+ * `workspace` is caller-provided scratch of ealdm_group_norm_workspace_bytes(n, hw, c) bytes holding
+ * per-(image, pixel chunk, 4-channel vector) partial sums; they are combined in a fixed order (fp64),
+ * so the result is bit-reproducible run to run (no atomics).
  * Replaces: GroupNorm32 + SiLU, ldm/modules/diffusionmodules/util.py:214-216,
  *   openaimodel.py:201-205,225-232,682-686; Normalize (eps 1e-6) attention.py:76-77, model.py:38-39.
  */
@@ -123,15 +124,16 @@ typedef struct {
   const float* beta;
   void* y;
   int64_t ld_y;
-  double* stats;
+  void* workspace;
 } ealdm_group_norm_args;
 
+int64_t ealdm_group_norm_workspace_bytes(int64_t n, int64_t hw, int64_t c);
 int ealdm_group_norm(const ealdm_group_norm_args* a, ealdm_stream_t stream);
 
 /* LayerNorm over the last dimension. Replaces nn.LayerNorm in attention.py:203-205,211-215. */
 typedef struct {
-  int32_t dtype;
-  int32_t reserved;
+  int32_t dtype;   /* type of y (and of x unless x_f32) */
+  int32_t x_f32;   /* 1: x is float regardless of dtype (fp32 residual stream -> bf16 GEMM operand) */
   const void* x;
   int64_t rows, c, ld_x;
   float eps;

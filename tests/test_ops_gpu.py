@@ -187,8 +187,10 @@ def test_group_norm(dtype, n, c, h, w, silu):
     beta = torch.randn(c, generator=g(27)).to(DEV)
     xa = to_act(x, dtype, ld=c + 4, c0=4)
     out = Act.empty(n, h, w, c, dtype, DEV)
-    stats = torch.empty(n * 32 * 2, dtype=torch.float64, device=DEV)
-    ops.group_norm(xa, gamma, beta, 1e-5, out, stats, silu=silu)
+    ops.group_norm(xa, gamma, beta, 1e-5, out, silu=silu)
+    out2 = Act.empty(n, h, w, c, dtype, DEV)
+    ops.group_norm(xa, gamma, beta, 1e-5, out2, silu=silu)
+    assert torch.equal(out.buf, out2.buf)  # no atomics: bit-reproducible
     ref = F.group_norm(from_act(xa), 32, gamma, beta, 1e-5)
     if silu:
         ref = F.silu(ref)
