@@ -1,0 +1,371 @@
+#!/usr/bin/env python
+"""Headline benchmark: latent samples/sec of 50-step conditioned DDIM sampling (32x32x4 latent, 256 px,
+classifier-free guidance 2.0) on the stdiff_cin-ldm-vq-f8 environment-conditioned UNet, batch 64 per GPU
+(BASELINE.json configs[1]); synthetic latents / conditioning, random-init weights.
+
+  python bench.py --gpus N --steps K --warmup W           one rank per GPU under torchrun for N > 1
+  python bench.py --impl reference ...                    the reference's CPU implementation (oracle port)
+
+A "step" is ONE full DDIMSampler.sample() call over one batch (50 UNet evaluations at UNet batch 2B
+plus 50 fused DDIM updates) -- the timed region the reference's own throughput print uses
+(scripts/sample_diffusion.py:90-104, first-stage decode excluded).
+Prints one JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "latent samples/sec (50-step DDIM, 256px)"
+UNIT = "samples/s"
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"bf16_sustained": float(p.get("bf16_tflops_sustained", p.get("bf16_tflops"))),
+                "bf16_burst": float(p["bf16_tflops"]), "hbm": float(p["hbm_gbs"]), "source": "measured"}
+    return {"bf16_sustained": 1400.0, "bf16_burst": 1590.0, "hbm": 6650.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        load = [v for v in sm if v > 0.5 * max(sm)] if sm else []
+        return {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path.  The reference is Python and
+    cannot travel to the GPU box, so this times the oracle port (a torch-fp32 restatement pinned against
+    the reference's outputs) on all host cores.  Each step is a bounded sample of the workload: ONE DDIM
+    step (UNet at batch 2B with CFG + update) at B = 2, extrapolated linearly to 50 steps."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import torch
+
+    from ealdm_b200 import configs as CFG
+    from oracle import diffusion as OD
+    from oracle import unet as OU
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    B, S = 2, 50
+    sd = OU.synthetic_state_dict(OU.unet_param_shapes(CFG.UNET_STDIFF), seed=2)
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(B, 4, 32, 32, generator=g)
+    c, uc = torch.randn(B, 4, 512, generator=g), torch.randn(B, 4, 512, generator=g)
+    buf = OD.register_schedule(1000, CFG.DIFFUSION["linear_start"], CFG.DIFFUSION["linear_end"])
+    sched = OD.make_ddim_schedule(buf["alphas_cumprod"], S, 0.0)
+    apply_model = lambda xx, tt, cc: OU.unet_forward(sd, CFG.UNET_STDIFF, xx, tt, cc)  # noqa: E731
+
+    def one_step(i):
+        index = S - 1 - (i % S)
+        t = torch.full((B,), int(sched["ddim_timesteps"][index]), dtype=torch.long)
+        with torch.no_grad():
+            return OD.p_sample_ddim(apply_model, x, c, t, sched, index, torch.zeros_like(x), ugs=2.0, uc=uc)[0]
+
+    for i in range(args.warmup):
+        one_step(i)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        one_step(i)
+    dt = (time.perf_counter() - t0) / max(args.steps, 1)
+    value = B / (dt * S)
+    sample = f"B={B}, one of {S} DDIM steps per timed step (CFG 2.0, UNet batch {2 * B}), fp32, linearly extrapolated to {S} steps"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "stdiff_cin-ldm-vq-f8 UNet, 50-step DDIM, CFG 2.0, 32x32x4 latent", "batch_per_gpu": 64,
+                       "ddim_steps": S, "guidance_scale": 2.0},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def cpu_baseline_leg(budget_s=25.0):
+    """Oracle port on the host cores, bounded: one DDIM step (CFG) at B=2, extrapolated to 50 steps."""
+    import torch
+
+    from ealdm_b200 import configs as CFG
+    from oracle import diffusion as OD
+    from oracle import unet as OU
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    B, S = 2, 50
+    sd = OU.synthetic_state_dict(OU.unet_param_shapes(CFG.UNET_STDIFF), seed=2)
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(B, 4, 32, 32, generator=g)
+    c, uc = torch.randn(B, 4, 512, generator=g), torch.randn(B, 4, 512, generator=g)
+    buf = OD.register_schedule(1000, CFG.DIFFUSION["linear_start"], CFG.DIFFUSION["linear_end"])
+    sched = OD.make_ddim_schedule(buf["alphas_cumprod"], S, 0.0)
+    apply_model = lambda xx, tt, cc: OU.unet_forward(sd, CFG.UNET_STDIFF, xx, tt, cc)  # noqa: E731
+    t = torch.full((B,), 981, dtype=torch.long)
+    times = []
+    t_start = time.perf_counter()
+    with torch.no_grad():
+        OD.p_sample_ddim(apply_model, x, c, t, sched, S - 1, torch.zeros_like(x), ugs=2.0, uc=uc)  # warm-up
+        while len(times) < 3 and time.perf_counter() - t_start < budget_s:
+            t0 = time.perf_counter()
+            OD.p_sample_ddim(apply_model, x, c, t, sched, S - 1, torch.zeros_like(x), ugs=2.0, uc=uc)
+            times.append(time.perf_counter() - t0)
+    dt = min(times)
+    return {"value": B / (dt * S), "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"oracle port (torch fp32 CPU), B={B}, 1 of {S} DDIM steps with CFG (UNet batch {2 * B}), "
+                      f"best of {len(times)}, extrapolated linearly to {S} steps"}
+
+
+# ------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="latent samples per GPU per step")
+    ap.add_argument("--ddim-steps", type=int, default=50)
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    from ealdm_b200 import configs as CFG, ops
+    from ealdm_b200.ddim import DDIMSampler
+    from ealdm_b200.ddpm import LatentDiffusion
+    from ealdm_b200.parallel import gather_batch, shard
+    from ealdm_b200.synthetic import init_synthetic_
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the hot path has no CPU fallback; use --impl reference)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+
+    B, S, ugs = args.batch, args.ddim_steps, 2.0
+    ld = LatentDiffusion(unet_config={"target": "ealdm_b200.unet.UNetModel", "params": dict(CFG.UNET_STDIFF)},
+                         cond_stage_config={"target": "torch.nn.Identity"}, conditioning_key="crossattn",
+                         **CFG.DIFFUSION).to(dev).eval()
+    unet = ld.model.diffusion_model
+    init_synthetic_(unet, seed=0)
+    unet.set_compute_dtype("bf16")
+    unet.enable_cuda_graph(not args.no_graph)
+    sampler = DDIMSampler(ld)
+
+    # global synthetic inputs drawn identically on every rank, then sliced (bit-identical to 1 GPU)
+    g = torch.Generator().manual_seed(1)
+    Bg = B * world
+    x_T_h = torch.randn(Bg, 4, 32, 32, generator=g).pin_memory()
+    cond_h = torch.randn(Bg, 4, 512, generator=g).pin_memory()
+    uc_h = torch.randn(Bg, 4, 512, generator=g).pin_memory()
+    x_T_h, cond_h, uc_h = (shard(t, rank, world).pin_memory() for t in (x_T_h, cond_h, uc_h))
+    out_h = torch.empty(B, 4, 32, 32).pin_memory()
+
+    def sample(x_T, cond, uc):
+        z, _ = sampler.sample(S=S, batch_size=B, shape=(4, 32, 32), conditioning=cond, eta=0.0, x_T=x_T,
+                              verbose=False, unconditional_guidance_scale=ugs, unconditional_conditioning=uc)
+        return z
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n):
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(n):
+            fn()
+        ev1.record()
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    # --- device-resident arm ("value") -------------------------------------------------------------
+    x_T_d, cond_d, uc_d = x_T_h.to(dev), cond_h.to(dev), uc_h.to(dev)
+
+    def step_resident():
+        z = sample(x_T_d, cond_d, uc_d)
+        if world > 1:
+            gather_batch(z, Bg)      # the single NCCL gather of the job
+        return z
+
+    launches0 = ops.launch_count()
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    ms = timed(step_resident, args.steps)
+    clk = clocks.stop() if rank == 0 else None
+    ms_per_step = ms / args.steps
+    value = Bg / (ms_per_step * 1e-3)
+
+    # --- end-to-end arm ("e2e"): host buffers in, host latents out, copies inside the timed region ----
+    def step_e2e():
+        xd = x_T_h.to(dev, non_blocking=True)
+        cd = cond_h.to(dev, non_blocking=True)
+        ud = uc_h.to(dev, non_blocking=True)
+        z = sample(xd, cd, ud)
+        out_h.copy_(z, non_blocking=True)
+        if world > 1:
+            gather_batch(z, Bg)
+        return z
+
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps) / args.steps
+    e2e_value = Bg / (ms_e2e * 1e-3)
+    h2d = (x_T_h.numel() + cond_h.numel() + uc_h.numel()) * 4
+    d2h = out_h.numel() * 4
+
+    # --- roofline of the dominant kernel: the tcgen05 implicit-GEMM conv/linear ----------------------
+    # one eager, instrumented UNet forward at the benchmark's UNet batch: CUDA events around every
+    # ealdm_conv launch on the launching stream; algorithmic FLOPs = 2*M*N*K of each launch.
+    peaks = load_peaks()
+    unet.enable_cuda_graph(False)
+    rec = []
+    orig_conv = ops.conv
+
+    def conv_timed(srcs, weight, out, **kw):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = orig_conv(srcs, weight, out, **kw)
+        e1.record()
+        tc = srcs[0].x.dtype == torch.bfloat16 and all(s.x.c % 64 == 0 and not s.upsample for s in srcs)
+        rec.append((e0, e1, 2.0 * out.rows * weight.shape[0] * weight.shape[1], tc))
+        return r
+
+    xin = torch.cat([x_T_d] * 2)
+    tin = torch.full((2 * B,), 981, device=dev, dtype=torch.long)
+    cin = torch.cat([uc_d, cond_d])
+    unet(xin, tin, context=cin)          # eager warm-up
+    l0 = ops.launch_count()
+    ops.conv = conv_timed
+    import ealdm_b200.unet as _unet_mod
+    _unet_mod.ops.conv = conv_timed
+    torch.cuda.synchronize()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    unet(xin, tin, context=cin)
+    f1.record()
+    torch.cuda.synchronize()
+    ops.conv = orig_conv
+    _unet_mod.ops.conv = orig_conv
+    launches_per_forward = ops.launch_count() - l0
+    tc_ms = sum(e0.elapsed_time(e1) for e0, e1, _, tc in rec if tc)
+    tc_flops = sum(f for _, _, f, tc in rec if tc)
+    n_tc = sum(1 for r_ in rec if r_[3])
+    fwd_ms = f0.elapsed_time(f1)
+    achieved = tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
+    roofline = {"bound": "tensor", "kernel": "ealdm::tc::conv_tc_kernel (tcgen05 implicit-GEMM conv/linear)",
+                "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+                "frac": achieved / peaks["bf16_sustained"], "peak_source": peaks["source"] + " (sustained)",
+                "traffic": None, "launches_per_forward": n_tc, "avg_launch_ms": tc_ms / max(n_tc, 1),
+                "share_of_forward": tc_ms / fwd_ms if fwd_ms > 0 else None,
+                "note": "event-timed eager forward at UNet batch %d; algorithmic FLOPs = 2*M*N*K per launch" % (2 * B)}
+    step_tflops = value / world * S * 2 * CFG.UNET_STDIFF_GFLOP_PER_SAMPLE / 1e3
+
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu_baseline:
+            try:
+                cpu = cpu_baseline_leg()
+            except Exception as ex:  # the oracle is a checker; never let it break the GPU line
+                cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {ex}"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "stdiff_cin-ldm-vq-f8 UNet (394.98 M params, cross-attention on [B,4,512] STDiff "
+                                   "conditioning), 50-step DDIM, CFG 2.0, eta 0, 32x32x4 latent, batch 64 per GPU "
+                                   "(BASELINE.json configs[1])",
+                       "batch_per_gpu": B, "global_batch": Bg, "ddim_steps": S, "guidance_scale": ugs,
+                       "unet_batch": 2 * B, "parallelism": f"batch-sharded x{world}, one final all-gather",
+                       "cuda_graph": not args.no_graph,
+                       "l2": "working set per step (0.79 GB bf16 weights + >4 GB activations per UNet forward) >> 126 MB L2",
+                       "weights": "random-init, BASELINE.md section 4 distribution"},
+            "clocks": clk,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e},
+            "gpu_launches": int(args.steps * S * (launches_per_forward + 1)),
+            "launches_per_unet_forward": int(launches_per_forward),
+            "roofline": roofline,
+            "unet_tflops_per_gpu": step_tflops,
+            "unet_frac_of_sustained_peak": step_tflops / peaks["bf16_sustained"],
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

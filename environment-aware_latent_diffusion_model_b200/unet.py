@@ -230,6 +230,8 @@ class UNetModel(nn.Module):
 
         self._compute_dtype = {"bf16": torch.bfloat16, "fp32": torch.float32}[compute_dtype]
         self._engine: Optional["UNetEngine"] = None
+        self.use_cuda_graph = False   # see enable_cuda_graph
+        self._graphs = {}
         self.register_load_state_dict_post_hook(lambda m, keys: m.invalidate_packed())
 
     # ---- engine management -------------------------------------------------------------------------
@@ -241,10 +243,46 @@ class UNetModel(nn.Module):
     def invalidate_packed(self):
         """Drop the packed kernel-layout weights (call after modifying parameters in place)."""
         self._engine = None
+        self._graphs = {}
+
+    def enable_cuda_graph(self, flag: bool = True) -> "UNetModel":
+        """Replay the forward pass (~300 kernel launches) as ONE CUDA graph per input shape.  The
+        launch sequence has no host synchronisation or data-dependent control flow, so capture is
+        exact; inputs are copied into static buffers and the result is returned as a fresh tensor."""
+        self.use_cuda_graph = flag
+        if not flag:
+            self._graphs = {}
+        return self
 
     def _apply(self, fn, *a, **k):
         self._engine = None
+        self._graphs = {}
         return super()._apply(fn, *a, **k)
+
+    def _forward_graphed(self, x, timesteps, context):
+        key = (tuple(x.shape), None if context is None else tuple(context.shape), self._compute_dtype)
+        ent = self._graphs.get(key)
+        if ent is None:
+            sx = x.detach().float().contiguous().clone()
+            st = timesteps.detach().to(device=x.device, dtype=torch.int64).contiguous().clone()
+            sc = None if context is None else context.detach().float().contiguous().clone()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):       # warm-up outside capture (lazy attributes, allocator)
+                self._engine.forward(sx, st, sc)
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                sy = self._engine.forward(sx, st, sc)
+            ent = (graph, sx, st, sc, sy)
+            self._graphs[key] = ent
+        graph, sx, st, sc, sy = ent
+        sx.copy_(x)
+        st.copy_(timesteps)
+        if sc is not None:
+            sc.copy_(context)
+        graph.replay()
+        return sy.clone()
 
     def convert_to_fp16(self):  # reference stubs (openaimodel.py:694-708): no-ops there as well
         pass
@@ -260,6 +298,8 @@ class UNetModel(nn.Module):
             raise RuntimeError("ealdm_b200.UNetModel runs on CUDA (sm_100a) only; there is no CPU fallback")
         if self._engine is None:
             self._engine = UNetEngine(self, self._compute_dtype)
+        if self.use_cuda_graph and not torch.cuda.is_current_stream_capturing():
+            return self._forward_graphed(x, timesteps, context)
         return self._engine.forward(x, timesteps, context)
 
 

@@ -286,22 +286,35 @@ def unet_param_shapes(cfg: dict) -> List[Tuple[str, Tuple[int, ...]]]:
 
 
 def synthetic_state_dict(shapes: Sequence[Tuple[str, Tuple[int, ...]]], seed: int) -> SD:
-    """Deterministic, reference-independent 'random-init' weights for benchmarks and parity tests:
-    every tensor is drawn from its own torch.Generator(seed, index) stream; weights ~ N(0, 1/fan_in)
-    (so activations stay O(1) through ~100 layers), norm gains ~ 1 + 0.1 N(0,1), biases ~ 0.02 N(0,1).
-    No parameter is left at zero (the reference zero-initialises 34 tensors, which would make the
-    UNet output identically 0 and every relative metric 0/0 -- SURVEY.md section 8c)."""
+    """Deterministic, reference-independent 'random-init' weights with the DISTRIBUTION BASELINE.md
+    section 4 specifies: the reference constructors' initialisation (nn.Conv2d / nn.Linear default =
+    kaiming_uniform(a=sqrt 5), i.e. U(-1/sqrt(fan_in), 1/sqrt(fan_in)) for weights and biases; norm
+    gains 1, norm biases 0) followed by N(0, 0.02) on the tensors the reference zero-initialises
+    (ResBlock.out_layers.3, *.proj_out, out.2 -- openaimodel.py:229-231,312,685; attention.py:244-248),
+    whose biases stay 0.  Without that re-randomisation the UNet output is identically 0 and every
+    relative metric is 0/0.  Each tensor has its own torch.Generator stream
+    (seed, index), so the values do not depend on the reference being importable."""
+    by_name = dict(shapes)
+
+    def zero_init(wname: str) -> bool:
+        return wname.endswith("out_layers.3.weight") or wname.endswith("proj_out.weight") or wname == "out.2.weight"
+
     sd: SD = {}
     for idx, (name, shape) in enumerate(shapes):
         gen = torch.Generator().manual_seed(seed * 100003 + idx)
         if name.endswith(".bias"):
-            t = 0.02 * torch.randn(shape, generator=gen)
+            wshape = by_name.get(name[:-5] + ".weight")
+            if wshape is None or len(wshape) == 1 or zero_init(name[:-5] + ".weight"):
+                t = torch.zeros(shape)
+            else:
+                bound = 1.0 / math.sqrt(math.prod(wshape[1:]))
+                t = (torch.rand(shape, generator=gen) * 2 - 1) * bound
         elif len(shape) == 1:  # norm gain
-            t = 1.0 + 0.1 * torch.randn(shape, generator=gen)
+            t = torch.ones(shape)
+        elif zero_init(name):
+            t = 0.02 * torch.randn(shape, generator=gen)
         else:
-            fan_in = 1
-            for s in shape[1:]:
-                fan_in *= s
-            t = torch.randn(shape, generator=gen) / math.sqrt(fan_in)
+            bound = 1.0 / math.sqrt(math.prod(shape[1:]))
+            t = (torch.rand(shape, generator=gen) * 2 - 1) * bound
         sd[name] = t
     return sd

@@ -1,0 +1,193 @@
+"""CPU tests of the host side: plugin boundary, schedule bit-exactness of the product code, state-dict
+compatibility, C-ABI exports, repository layout rules, and the multi-process sharding logic (gloo)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+import yaml
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+PKG = os.path.join(ROOT, "environment-aware_latent_diffusion_model_b200")
+
+from ealdm_b200 import _lib as L  # noqa: E402
+from ealdm_b200 import configs as CFG  # noqa: E402
+from ealdm_b200.ddim import DDIMSampler  # noqa: E402
+from ealdm_b200.ddpm import LatentDiffusion  # noqa: E402
+from ealdm_b200.util import instantiate_from_config  # noqa: E402
+from oracle import autoencoder as OA  # noqa: E402
+from oracle import unet as OU  # noqa: E402
+
+
+def gold(name):
+    return torch.load(os.path.join(GOLD, name), weights_only=False)
+
+
+def test_abi_library_exports_every_declared_symbol():
+    """No compute calls (no GPU here): the .so loads and exports what include/ealdm_b200.h declares."""
+    L.build()
+    lib = L.load()
+    with open(os.path.join(ROOT, "include", "ealdm_b200.h")) as f:
+        declared = sorted(set(re.findall(r"\b(ealdm_[a-z0-9_]+)\s*\(", f.read())))
+    assert len(declared) >= 18
+    for sym in declared:
+        assert hasattr(lib, sym), sym
+    assert sorted(L.EXPORTS) == declared
+    assert lib.ealdm_abi_version() == 1
+    # argument validation happens before any CUDA call
+    a = L.LayerNormArgs()
+    assert lib.ealdm_layer_norm(ctypes.byref(a), None) == -1
+    assert b"null" in lib.ealdm_last_error()
+    assert lib.ealdm_group_norm_workspace_bytes(128, 1024, 256) == 128 * 10 * 64 * 8
+
+
+def test_struct_layout_matches_the_header():
+    src = '#include <stdio.h>\n#include "ealdm_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu\\n",' \
+          "sizeof(ealdm_conv_src),sizeof(ealdm_conv_args),sizeof(ealdm_group_norm_args),sizeof(ealdm_layer_norm_args)," \
+          "sizeof(ealdm_attention_args),sizeof(ealdm_ddim_step_args));return 0;}"
+    exe = "/tmp/ealdm_sizeof"
+    subprocess.run(["gcc", "-x", "c", "-", "-I", os.path.join(ROOT, "include"), "-o", exe], input=src.encode(), check=True)
+    sizes = [int(v) for v in subprocess.run([exe], capture_output=True, check=True).stdout.split()]
+    assert sizes == [ctypes.sizeof(c) for c in (L.ConvSrc, L.ConvArgs, L.GroupNormArgs, L.LayerNormArgs,
+                                                L.AttentionArgs, L.DdimStepArgs)]
+
+
+def test_product_never_imports_the_oracle_and_has_no_cpu_fallback():
+    for dirpath, _, files in os.walk(PKG):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh")):
+                text = open(os.path.join(dirpath, fn)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", text, re.M), fn
+    from ealdm_b200.unet import UNetModel
+    m = UNetModel(**CFG.UNET_UNCOND)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.zeros(1, 4, 32, 32), torch.zeros(1, dtype=torch.long))
+
+
+def test_instantiate_from_config_yaml_targets():
+    for rel, key in (("configs/latent-diffusion/stdiff_cin-ldm-kl-f8_b200.yaml", 626),
+                     ("configs/latent-diffusion/uncond_cin-ldm-vq-f8_b200.yaml", 306)):
+        cfg = yaml.safe_load(open(os.path.join(ROOT, rel)))["model"]
+        model = instantiate_from_config(cfg)
+        assert type(model).__name__ == "LatentDiffusion"
+        unet = model.model.diffusion_model
+        assert len(unet.state_dict()) == key
+        assert unet.in_channels == 4 and unet.image_size == 32
+    ae = instantiate_from_config(yaml.safe_load(open(os.path.join(ROOT, "configs/autoencoder/autoencoder_kl_32x32x4_b200.yaml")))["model"])
+    assert hasattr(ae, "encode") and hasattr(ae, "decode")
+
+
+@pytest.mark.parametrize("cfg", [CFG.UNET_STDIFF, CFG.UNET_UNCOND])
+def test_unet_state_dict_matches_reference_inventory(cfg):
+    from ealdm_b200.unet import UNetModel
+    m = UNetModel(**cfg)
+    mine = [(k, tuple(v.shape)) for k, v in m.state_dict().items()]
+    assert mine == OU.unet_param_shapes(cfg)          # same names, shapes AND registration order
+    sd = OU.synthetic_state_dict(OU.unet_param_shapes(cfg), seed=5)
+    m.load_state_dict(sd, strict=True)
+    # the reference zero-initialises these (openaimodel.py:229-231,312,685; attention.py:244-248)
+    fresh = UNetModel(**cfg)
+    zeros = [k for k, v in fresh.state_dict().items() if v.dim() >= 2 and float(v.abs().max()) == 0.0]
+    assert len(zeros) == 34
+    for combo in (dict(use_scale_shift_norm=True), dict(resblock_updown=True), dict(num_classes=10), dict(dims=3)):
+        with pytest.raises(NotImplementedError):
+            UNetModel(**{**cfg, **combo})
+
+
+def test_autoencoder_state_dict_matches_reference_inventory():
+    from ealdm_b200.autoencoder import AutoencoderKL
+    ae = AutoencoderKL(ddconfig=dict(CFG.AE_KL_F8_DDCONFIG), embed_dim=4)
+    mine = [(k, tuple(v.shape)) for k, v in ae.state_dict().items()]
+    assert mine == OA.autoencoder_kl_param_shapes(CFG.AE_KL_F8_DDCONFIG, 4)
+
+
+def test_schedules_bit_exact_vs_reference_golden():
+    G = gold("schedule.pt")
+    ld = LatentDiffusion(unet_config={"target": "ealdm_b200.unet.UNetModel", "params": dict(CFG.UNET_UNCOND)},
+                         **CFG.DIFFUSION)
+    for k, v in G["register"].items():
+        assert torch.equal(getattr(ld, k), v), k
+    for S in (10, 50):
+        for eta in (0.0, 1.0):
+            ref = G[f"S{S}_eta{eta}"]
+            s = DDIMSampler(ld)
+            s.make_schedule(S, ddim_eta=eta, verbose=False)
+            assert torch.equal(torch.as_tensor(s.ddim_timesteps), ref["ddim_timesteps"])
+            for k in ("ddim_alphas", "ddim_alphas_prev", "ddim_sigmas", "ddim_sqrt_one_minus_alphas"):
+                assert torch.equal(torch.as_tensor(np.asarray(getattr(s, k)), dtype=torch.float64), ref[k]), (S, eta, k)
+            # per-step fp32 scalars == what the reference's torch.full tensors hold
+            for index in (0, S // 2, S - 1):
+                sc = s.step_scalars(index)
+                a_t = torch.full((), float(ref["ddim_alphas"][index]), dtype=torch.float32)
+                a_p = torch.full((), float(ref["ddim_alphas_prev"][index]), dtype=torch.float32)
+                sg = torch.full((), float(ref["ddim_sigmas"][index]), dtype=torch.float32)
+                assert sc["sqrt_at"] == float(a_t.sqrt()) and sc["sqrt_a_prev"] == float(a_p.sqrt())
+                assert sc["dir_coef"] == float((1. - a_p - sg ** 2).sqrt()) and sc["sigma_t"] == float(sg)
+    s = DDIMSampler(ld)
+    s.make_schedule(50, ddim_eta=1.0, verbose=False)
+    assert list(s.ddim_timesteps[:2]) == [1, 21] and s.ddim_timesteps[-1] == 981
+
+
+def test_geglu_interleave_roundtrip():
+    import torch.nn.functional as F
+    from ealdm_b200.packing import geglu_interleave, pack_conv_weight
+    C = 64
+    w, b, x = torch.randn(8 * C, C), torch.randn(8 * C), torch.randn(7, C)
+    wp, bp = geglu_interleave(w, b)
+    y = F.linear(x, wp, bp).reshape(7, -1, 2, 16)
+    out = (y[:, :, 0] * F.gelu(y[:, :, 1])).reshape(7, 4 * C)
+    val, gate = F.linear(x, w, b).chunk(2, -1)
+    assert torch.allclose(out, val * F.gelu(gate), atol=1e-5)
+    cw = torch.randn(8, 4, 3, 3)
+    pw = pack_conv_weight(cw, torch.float32)
+    assert pw.shape == (8, 36) and torch.equal(pw[:, 4 * (3 * 1 + 2):4 * (3 * 1 + 2) + 4], cw[:, :, 1, 2])
+
+
+def test_shard_bounds_cover_batch_exactly():
+    from ealdm_b200.parallel import shard_bounds
+    for total in (0, 1, 7, 64, 512, 513):
+        for world in (1, 2, 3, 4, 8):
+            spans = [shard_bounds(total, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from ealdm_b200.parallel import sample_sharded
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(3)
+    x_T = torch.randn(7, 4, 8, 8, generator=g)       # ragged: 7 samples over 2 ranks
+    cond = torch.randn(7, 4, 16, generator=g)
+    fake = lambda x, c, u: x * 2 + c.mean(dim=(1, 2))[:, None, None, None]  # noqa: E731  per-sample function
+    out = sample_sharded(fake, x_T, cond, None)
+    q.put((rank, out))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_sampling_gloo_world2_matches_single_process():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    outs = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    g = torch.Generator().manual_seed(3)
+    x_T = torch.randn(7, 4, 8, 8, generator=g)
+    cond = torch.randn(7, 4, 16, generator=g)
+    ref = x_T * 2 + cond.mean(dim=(1, 2))[:, None, None, None]
+    assert torch.equal(outs[0], ref) and torch.equal(outs[1], ref)
