@@ -38,14 +38,15 @@ class ConvArgs(C.Structure):
                 ("k_total", C.c_int64), ("h_out", C.c_int64), ("w_out", C.c_int64),
                 ("bias", C.c_void_p), ("rowvec", C.c_void_p), ("ld_rowvec", C.c_int64),
                 ("residual", C.c_void_p), ("ld_res", C.c_int64), ("out", C.c_void_p),
-                ("ld_out", C.c_int64), ("out_f32", C.c_int32), ("res_f32", C.c_int32)]
+                ("ld_out", C.c_int64), ("out_f32", C.c_int32), ("res_f32", C.c_int32),
+                ("out2", C.c_void_p), ("ld_out2", C.c_int64)]
 
 
 class GroupNormArgs(C.Structure):
     _fields_ = [("dtype", C.c_int32), ("act", C.c_int32), ("x", C.c_void_p), ("n", C.c_int64),
                 ("hw", C.c_int64), ("c", C.c_int64), ("ld_x", C.c_int64), ("groups", C.c_int32),
                 ("eps", C.c_float), ("gamma", C.c_void_p), ("beta", C.c_void_p), ("y", C.c_void_p),
-                ("ld_y", C.c_int64), ("workspace", C.c_void_p)]
+                ("ld_y", C.c_int64), ("workspace", C.c_void_p), ("x_f32", C.c_int32), ("reserved", C.c_int32)]
 
 
 class LayerNormArgs(C.Structure):

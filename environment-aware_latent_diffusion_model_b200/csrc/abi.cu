@@ -53,7 +53,8 @@ extern "C" int ealdm_conv(const ealdm_conv_args* a, ealdm_stream_t stream) {
   EALDM_REQUIRE(a->weight && a->out, "conv: null weight/out");
   EALDM_REQUIRE(a->n_out > 0 && a->k_total > 0 && a->h_out > 0 && a->w_out > 0, "conv: bad sizes");
   EALDM_REQUIRE(a->act >= EALDM_ACT_NONE && a->act <= EALDM_ACT_GEGLU, "conv: bad act %d", a->act);
-  EALDM_REQUIRE(!(a->act == EALDM_ACT_GEGLU && a->rowvec), "conv: GEGLU with rowvec unsupported");
+  EALDM_REQUIRE(!(a->act == EALDM_ACT_GEGLU && (a->rowvec || a->out2)),
+                "conv: GEGLU with rowvec / out2 unsupported");
   for (int s = 0; s < a->n_src; ++s) {
     const ealdm_conv_src& x = a->src[s];
     EALDM_REQUIRE(x.x != nullptr, "conv: src[%d].x is null", s);

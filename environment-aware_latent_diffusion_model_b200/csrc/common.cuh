@@ -104,6 +104,8 @@ struct Epilogue {
   int act;
   int out_f32;
   int res_f32;
+  void* out2;        // optional bf16/T shadow copy of the output
+  long long ld_out2;
 };
 
 }  // namespace ealdm

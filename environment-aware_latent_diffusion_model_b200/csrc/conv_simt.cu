@@ -196,6 +196,7 @@ __global__ void __launch_bounds__(NT) conv_simt_kernel(const Params p) {
         v += ep.res_f32 ? reinterpret_cast<const float*>(ep.residual)[m * ep.ld_res + col]
                         : to_f32(reinterpret_cast<const T*>(ep.residual)[m * ep.ld_res + col]);
       reinterpret_cast<TOut*>(ep.out)[m * ep.ld_out + col] = from_f32<TOut>(v);
+      if (ep.out2) reinterpret_cast<T*>(ep.out2)[m * ep.ld_out2 + col] = from_f32<T>(v);
     }
   }
 }
@@ -238,6 +239,8 @@ int launch(const ealdm_conv_args* a, cudaStream_t st) {
   p.ep.act = a->act;
   p.ep.out_f32 = a->out_f32;
   p.ep.res_f32 = a->res_f32;
+  p.ep.out2 = a->out2;
+  p.ep.ld_out2 = a->ld_out2;
   if (a->act == EALDM_ACT_GEGLU)
     EALDM_REQUIRE(a->n_out % 32 == 0, "GEGLU needs n_out %% 32 == 0 (got %lld)", (long long)a->n_out);
 

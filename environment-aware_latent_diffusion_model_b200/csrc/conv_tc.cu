@@ -160,6 +160,7 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&acc)[32], const 
         o[4] += r1.x; o[5] += r1.y; o[6] += r1.z; o[7] += r1.w;
       }
       store8<TOut>(dst + g * 8, o);
+      if (ep.out2) store8<bf16>(reinterpret_cast<bf16*>(ep.out2) + row * ep.ld_out2 + col0 + g * 8, o);
     }
   } else {
     for (int j = 0; j < 32; ++j) {
@@ -171,6 +172,7 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&acc)[32], const 
       if (res) o += __bfloat162float(res[j]);
       if (resf) o += resf[j];
       dst[j] = from_f32<TOut>(o);
+      if (ep.out2) reinterpret_cast<bf16*>(ep.out2)[row * ep.ld_out2 + col0 + j] = __float2bfloat16_rn(o);
     }
   }
 }
@@ -399,7 +401,8 @@ bool supported(const ealdm_conv_args* a) {
   if ((reinterpret_cast<uintptr_t>(a->out) & 15) != 0 || a->ld_out % 8 != 0) return false;
   if (a->residual && ((reinterpret_cast<uintptr_t>(a->residual) & 15) != 0 || a->ld_res % 8 != 0))
     return false;
-  if (a->act == EALDM_ACT_GEGLU && a->rowvec) return false;
+  if (a->act == EALDM_ACT_GEGLU && (a->rowvec || a->out2)) return false;
+  if (a->out2 && ((reinterpret_cast<uintptr_t>(a->out2) & 15) != 0 || a->ld_out2 % 8 != 0)) return false;
   if (a->act == EALDM_ACT_GEGLU && a->n_out % 32 != 0) return false;
   return true;
 }
@@ -494,6 +497,8 @@ int launch(const ealdm_conv_args* a, cudaStream_t st) {
   p.ep.act = a->act;
   p.ep.out_f32 = a->out_f32;
   p.ep.res_f32 = a->res_f32;
+  p.ep.out2 = a->out2;
+  p.ep.ld_out2 = a->ld_out2;
 
   switch (BN) {
     case 32: return launch_bn<32>(tmA[0], tmA[1], tmB, p, st);

@@ -14,9 +14,9 @@ constexpr int MAX_GROUPS = 64;
 // No atomics: every (image, pixel chunk, 4-channel vector) partial is produced by exactly one
 // thread (after a fixed-order shared-memory reduction over the CTA's pixel lanes), and the apply
 // kernel combines the partials of a group in a fixed order in fp64 => bit-reproducible.
-template <typename T>
+template <typename TX>
 __global__ void __launch_bounds__(NT)
-gn_stats_kernel(const T* __restrict__ x, long long ld, int hw, int c, int pix_per_cta,
+gn_stats_kernel(const TX* __restrict__ x, long long ld, int hw, int c, int pix_per_cta,
                 float2* __restrict__ part) {
   __shared__ float2 red[NT];
   const int t = threadIdx.x;
@@ -27,14 +27,14 @@ gn_stats_kernel(const T* __restrict__ x, long long ld, int hw, int c, int pix_pe
   const int tv = t % lanes_v, tp = t / lanes_v;
   const int p0 = blockIdx.x * pix_per_cta;
   const int p1 = min(p0 + pix_per_cta, hw);
-  const T* base = x + static_cast<long long>(n) * hw * ld;
+  const TX* base = x + static_cast<long long>(n) * hw * ld;
   float2* out = part + (static_cast<long long>(n) * gridDim.x + blockIdx.x) * vpp;
   for (int v0 = 0; v0 < vpp; v0 += lanes_v) {
     const int v = v0 + tv;
     float s = 0.f, ss = 0.f;
     if (tp < pix_lanes && v < vpp) {
       for (int pix = p0 + tp; pix < p1; pix += pix_lanes) {
-        Vec4<T> q;
+        Vec4<TX> q;
         q.load(base + static_cast<long long>(pix) * ld + v * 4);
         float f[4];
         q.get(f);
@@ -55,9 +55,9 @@ gn_stats_kernel(const T* __restrict__ x, long long ld, int hw, int c, int pix_pe
 }
 
 // ---- GroupNorm apply: y = (x - mean) * rstd * gamma + beta, optional SiLU ---------------------------
-template <typename T>
+template <typename TX, typename T>
 __global__ void __launch_bounds__(NT)
-gn_apply_kernel(const T* __restrict__ x, long long ld_x, T* __restrict__ y, long long ld_y, int hw,
+gn_apply_kernel(const TX* __restrict__ x, long long ld_x, T* __restrict__ y, long long ld_y, int hw,
                 int c, int groups, int pix_per_cta, const float2* __restrict__ part, float eps,
                 const float* __restrict__ gamma, const float* __restrict__ beta, int act) {
   __shared__ float s_mean[MAX_GROUPS], s_rstd[MAX_GROUPS];
@@ -102,16 +102,17 @@ gn_apply_kernel(const T* __restrict__ x, long long ld_x, T* __restrict__ y, long
   const int p0 = blockIdx.x * pix_per_cta;
   const int p1 = min(p0 + pix_per_cta, hw);
   const long long items = static_cast<long long>(p1 - p0) * vpp;
-  const T* xb = x + static_cast<long long>(n) * hw * ld_x;
+  const TX* xb = x + static_cast<long long>(n) * hw * ld_x;
   T* yb = y + static_cast<long long>(n) * hw * ld_y;
   for (long long i = t; i < items; i += NT) {
     const int pix = p0 + static_cast<int>(i / vpp);
     const int v = static_cast<int>(i % vpp);
     const int ch = v * 4;
-    Vec4<T> q;
-    q.load(xb + static_cast<long long>(pix) * ld_x + ch);
+    Vec4<TX> qx;
+    qx.load(xb + static_cast<long long>(pix) * ld_x + ch);
     float f[4];
-    q.get(f);
+    qx.get(f);
+    Vec4<T> q;
     const int g = ch / cpg;
     const float mean = s_mean[g], rstd = s_rstd[g];
     const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + ch));
@@ -141,7 +142,7 @@ static void gn_chunking(long long n, long long hw, int* pix_per_cta, long long* 
   *chunks = ceil_div(hw, ppc);
 }
 
-template <typename T>
+template <typename TX, typename T>
 static int group_norm_t(const ealdm_group_norm_args* a, cudaStream_t st) {
   const int hw = static_cast<int>(a->hw);
   const int n = static_cast<int>(a->n);
@@ -150,10 +151,10 @@ static int group_norm_t(const ealdm_group_norm_args* a, cudaStream_t st) {
   gn_chunking(n, hw, &ppc, &chunks);
   dim3 grid(static_cast<unsigned>(chunks), static_cast<unsigned>(n));
   float2* part = reinterpret_cast<float2*>(a->workspace);
-  gn_stats_kernel<T><<<grid, NT, 0, st>>>(reinterpret_cast<const T*>(a->x), a->ld_x, hw,
-                                          static_cast<int>(a->c), ppc, part);
+  gn_stats_kernel<TX><<<grid, NT, 0, st>>>(reinterpret_cast<const TX*>(a->x), a->ld_x, hw,
+                                           static_cast<int>(a->c), ppc, part);
   EALDM_LAUNCH_CHECK();
-  gn_apply_kernel<T><<<grid, NT, 0, st>>>(reinterpret_cast<const T*>(a->x), a->ld_x,
+  gn_apply_kernel<TX, T><<<grid, NT, 0, st>>>(reinterpret_cast<const TX*>(a->x), a->ld_x,
                                           reinterpret_cast<T*>(a->y), a->ld_y, hw,
                                           static_cast<int>(a->c), a->groups, ppc, part, a->eps,
                                           a->gamma, a->beta, a->act);
@@ -249,8 +250,9 @@ extern "C" int ealdm_group_norm(const ealdm_group_norm_args* a, ealdm_stream_t s
   EALDM_REQUIRE(a->n > 0 && a->n <= 65535 && a->hw > 0, "group_norm: bad n/hw");
   EALDM_REQUIRE(a->act == EALDM_ACT_NONE || a->act == EALDM_ACT_SILU, "group_norm: bad act");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (a->dtype == EALDM_F32) return norm::group_norm_t<float>(a, st);
-  if (a->dtype == EALDM_BF16) return norm::group_norm_t<bf16>(a, st);
+  if (a->dtype == EALDM_F32) return norm::group_norm_t<float, float>(a, st);
+  if (a->dtype == EALDM_BF16 && a->x_f32) return norm::group_norm_t<float, bf16>(a, st);
+  if (a->dtype == EALDM_BF16) return norm::group_norm_t<bf16, bf16>(a, st);
   return set_error(EALDM_EINVAL, "group_norm: bad dtype %d", a->dtype);
 }
 

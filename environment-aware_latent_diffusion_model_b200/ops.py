@@ -79,7 +79,7 @@ class ConvIn:
 
 def conv(srcs: Sequence[ConvIn], weight: torch.Tensor, out: Act, *, bias: Optional[torch.Tensor] = None,
          rowvec: Optional[torch.Tensor] = None, rowvec_col0: int = 0, residual: Optional[Act] = None,
-         act: int = L.ACT_NONE, impl: int = L.IMPL_AUTO) -> Act:
+         act: int = L.ACT_NONE, impl: int = L.IMPL_AUTO, out2: Optional[Act] = None) -> Act:
     """ealdm_conv: out = epilogue(sum_s im2col(src_s) @ weight[:, seg_s]^T). `weight` is [n_out, k_total]."""
     lib = L.load()
     a = L.ConvArgs()
@@ -118,6 +118,9 @@ def conv(srcs: Sequence[ConvIn], weight: torch.Tensor, out: Act, *, bias: Option
     a.out_f32 = 1 if (out.dtype == torch.float32 and x0.dtype != torch.float32) else 0
     if not a.out_f32:
         assert out.dtype == x0.dtype
+    if out2 is not None:
+        assert out2.dtype == x0.dtype and out2.rows == out.rows and out2.c == out.c
+        a.out2, a.ld_out2 = out2.ptr, out2.ld
     L.check(lib.ealdm_conv(C.byref(a), _stream()))
     return out
 
@@ -129,7 +132,10 @@ def linear(x: Act, weight: torch.Tensor, out: Act, **kw) -> Act:
     res = kw.pop("residual", None)
     if res is not None:
         res = Act(res.buf, 1, 1, res.rows, res.c, res.c0)
-    conv([ConvIn(xs)], weight, os_, residual=res, **kw)
+    o2 = kw.pop("out2", None)
+    if o2 is not None:
+        o2 = Act(o2.buf, 1, 1, o2.rows, o2.c, o2.c0)
+    conv([ConvIn(xs)], weight, os_, residual=res, out2=o2, **kw)
     return out
 
 
@@ -143,13 +149,14 @@ def group_norm(x: Act, gamma: torch.Tensor, beta: torch.Tensor, eps: float, out:
                workspace: Optional[torch.Tensor] = None, *, groups: int = 32, silu: bool = False) -> Act:
     lib = L.load()
     a = L.GroupNormArgs()
-    a.dtype = _dt(x.dtype)
+    a.dtype = _dt(out.dtype)
+    a.x_f32 = 1 if (x.dtype == torch.float32 and out.dtype != torch.float32) else 0
     a.act = L.ACT_SILU if silu else L.ACT_NONE
     a.x, a.n, a.hw, a.c, a.ld_x = x.ptr, x.n, x.h * x.w, x.c, x.ld
     a.groups, a.eps = groups, eps
     assert gamma.dtype == torch.float32 and beta.dtype == torch.float32 and gamma.numel() == x.c
     a.gamma, a.beta = gamma.data_ptr(), beta.data_ptr()
-    assert out.dtype == x.dtype and out.rows == x.rows and out.c == x.c
+    assert out.rows == x.rows and out.c == x.c and (out.dtype == x.dtype or x.dtype == torch.float32)
     a.y, a.ld_y = out.ptr, out.ld
     need = int(lib.ealdm_group_norm_workspace_bytes(x.n, x.h * x.w, x.c))
     if workspace is None:

@@ -437,33 +437,45 @@ class UNetEngine:
         self.mid_ch = c
 
     # ---- helpers --------------------------------------------------------------------------------------
+    # The residual stream ("trunk": ResBlock / attention-block / resample outputs and the token stream
+    # inside a transformer block) is kept in fp32, as it is under torch.autocast; only GEMM operands
+    # are bf16.  A trunk tensor that is also a GEMM operand (1x1 skip conv, down/up-sampling conv) gets
+    # a bf16 shadow written by the same epilogue (`out2`).  In fp32 mode master and shadow coincide.
     def _new(self, n, h, w, c, dtype=None) -> Act:
         return Act.empty(n, h, w, c, dtype or self.dt, self.dev)
 
-    def _res(self, d, x: Act, emb_all: torch.Tensor, dest: Optional[Act]) -> Act:
-        hn = self._new(x.n, x.h, x.w, x.c)
-        ops.group_norm(x, d["gn1"][0], d["gn1"][1], 1e-5, hn, self.stats, silu=True)
-        h1 = self._new(x.n, x.h, x.w, d["cout"])
+    def _new_dual(self, n, h, w, c) -> "Dual":
+        f = self._new(n, h, w, c, torch.float32)
+        return Dual(f, f if self.dt == torch.float32 else self._new(n, h, w, c))
+
+    def _out2(self, d: "Dual"):
+        return None if d.h is d.f else d.h
+
+    def _res(self, d, x: "Dual", emb_all: torch.Tensor, dest: Optional["Dual"]) -> "Dual":
+        n, h, w = x.f.n, x.f.h, x.f.w
+        hn = self._new(n, h, w, x.f.c)
+        ops.group_norm(x.f, d["gn1"][0], d["gn1"][1], 1e-5, hn, self.stats, silu=True)
+        h1 = self._new(n, h, w, d["cout"], torch.float32)
         ops.conv([ConvIn(hn, 3, 1, 1)], d["conv1"].w, h1, bias=d["conv1"].b, rowvec=emb_all,
                  rowvec_col0=d["emb_col0"])
-        hn2 = self._new(x.n, x.h, x.w, d["cout"])
+        hn2 = self._new(n, h, w, d["cout"])
         ops.group_norm(h1, d["gn2"][0], d["gn2"][1], 1e-5, hn2, self.stats, silu=True)
-        out = dest if dest is not None else self._new(x.n, x.h, x.w, d["cout"])
+        out = dest if dest is not None else self._new_dual(n, h, w, d["cout"])
         if d["skip"]:
-            ops.conv([ConvIn(hn2, 3, 1, 1), ConvIn(x, 1, 1, 0)], d["conv2"].w, out, bias=d["conv2"].b)
+            ops.conv([ConvIn(hn2, 3, 1, 1), ConvIn(x.h, 1, 1, 0)], d["conv2"].w, out.f, bias=d["conv2"].b,
+                     out2=self._out2(out))
         else:
-            ops.conv([ConvIn(hn2, 3, 1, 1)], d["conv2"].w, out, bias=d["conv2"].b, residual=x)
+            ops.conv([ConvIn(hn2, 3, 1, 1)], d["conv2"].w, out.f, bias=d["conv2"].b, residual=x.f,
+                     out2=self._out2(out))
         return out
 
-    def _st(self, d, x: Act, kv_all: Optional[Act], n_ctx: int, dest: Optional[Act]) -> Act:
+    def _st(self, d, x: "Dual", kv_all: Optional[Act], n_ctx: int, dest: Optional["Dual"]) -> "Dual":
         C_, heads, dh = d["c"], d["heads"], d["dh"]
-        n, h, w = x.n, x.h, x.w
+        n, h, w = x.f.n, x.f.h, x.f.w
         tok = h * w
-        xn = self._new(n, h, w, C_)
-        ops.group_norm(x, d["norm"][0], d["norm"][1], 1e-6, xn, self.stats, silu=False)
-        # the token residual stream t -> t1 -> t2 stays fp32 (as under torch autocast); only GEMM
-        # operands (LayerNorm outputs, attention outputs, the GEGLU product) are bf16
         f32 = torch.float32
+        xn = self._new(n, h, w, C_)
+        ops.group_norm(x.f, d["norm"][0], d["norm"][1], 1e-6, xn, self.stats, silu=False)
         t = self._new(n, h, w, C_, f32)
         ops.linear(xn, d["proj_in"].w, t, bias=d["proj_in"].b)
         for bi, tb in enumerate(d["blocks"]):
@@ -490,19 +502,19 @@ class UNetEngine:
             ops.layer_norm(t2, tb["ln3"][0], tb["ln3"][1], 1e-5, a)
             gg = self._new(n, h, w, 4 * C_)
             ops.linear(a, tb["ff1"].w, gg, bias=tb["ff1"].b, act=L.ACT_GEGLU)
-            last = bi == len(d["blocks"]) - 1   # the last t feeds proj_out as a GEMM operand -> bf16
+            last = bi == len(d["blocks"]) - 1   # the last t feeds proj_out as a GEMM operand -> compute dtype
             t = self._new(n, h, w, C_, None if last else f32)
             ops.linear(gg, tb["ff2"].w, t, bias=tb["ff2"].b, residual=t2)
-        out = dest if dest is not None else self._new(n, h, w, C_)
-        ops.linear(t, d["proj_out"].w, out, bias=d["proj_out"].b, residual=x)
+        out = dest if dest is not None else self._new_dual(n, h, w, C_)
+        ops.linear(t, d["proj_out"].w, out.f, bias=d["proj_out"].b, residual=x.f, out2=self._out2(out))
         return out
 
-    def _ab(self, d, x: Act, dest: Optional[Act]) -> Act:
+    def _ab(self, d, x: "Dual", dest: Optional["Dual"]) -> "Dual":
         C_, heads = d["c"], d["heads"]
         dh = C_ // heads
-        n, h, w = x.n, x.h, x.w
+        n, h, w = x.f.n, x.f.h, x.f.w
         xn = self._new(n, h, w, C_)
-        ops.group_norm(x, d["norm"][0], d["norm"][1], 1e-5, xn, self.stats, silu=False)
+        ops.group_norm(x.f, d["norm"][0], d["norm"][1], 1e-5, xn, self.stats, silu=False)
         qkv = self._new(n, h, w, 3 * C_)
         ops.linear(xn, d["qkv"].w, qkv, bias=d["qkv"].b)
         o = self._new(n, h, w, C_)
@@ -510,14 +522,15 @@ class UNetEngine:
         ops.attention(qkv.cols(0, span), qkv.cols(dh, span), qkv.cols(2 * dh, span), o, batch=n, heads=heads,
                       head_dim=dh, n_q=h * w, n_kv=h * w, scale=dh ** -0.5, head_stride_q=3 * dh,
                       head_stride_kv=3 * dh)
-        out = dest if dest is not None else self._new(n, h, w, C_)
-        ops.linear(o, d["proj"].w, out, bias=d["proj"].b, residual=x)
+        out = dest if dest is not None else self._new_dual(n, h, w, C_)
+        ops.linear(o, d["proj"].w, out.f, bias=d["proj"].b, residual=x.f, out2=self._out2(out))
         return out
 
-    def _run(self, layers, x: Act, emb_all, kv_all, n_ctx, dest: Optional[Act]) -> Act:
+    def _run(self, layers, x: "Dual", emb_all, kv_all, n_ctx, dest: Optional["Dual"]) -> "Dual":
         for i, d in enumerate(layers):
             dst = dest if i == len(layers) - 1 else None
             k = d["kind"]
+            n, h, w = x.f.n, x.f.h, x.f.w
             if k == "res":
                 x = self._res(d, x, emb_all, dst)
             elif k == "st":
@@ -525,19 +538,22 @@ class UNetEngine:
             elif k == "ab":
                 x = self._ab(d, x, dst)
             elif k == "conv_in":
-                out = dst if dst is not None else self._new(x.n, x.h, x.w, d["conv"].cout)
-                x = ops.conv([ConvIn(x, 3, 1, 1)], d["conv"].w, out, bias=d["conv"].b)
+                out = dst if dst is not None else self._new_dual(n, h, w, d["conv"].cout)
+                ops.conv([ConvIn(x.h, 3, 1, 1)], d["conv"].w, out.f, bias=d["conv"].b, out2=self._out2(out))
+                x = out
             elif k == "down":
-                out = dst if dst is not None else self._new(x.n, x.h // 2, x.w // 2, d["conv"].cout)
-                x = ops.conv([ConvIn(x, 3, 2, 1)], d["conv"].w, out, bias=d["conv"].b)
+                out = dst if dst is not None else self._new_dual(n, h // 2, w // 2, d["conv"].cout)
+                ops.conv([ConvIn(x.h, 3, 2, 1)], d["conv"].w, out.f, bias=d["conv"].b, out2=self._out2(out))
+                x = out
             elif k == "up":
-                out = dst if dst is not None else self._new(x.n, x.h * 2, x.w * 2, d["conv"].cout)
+                out = dst if dst is not None else self._new_dual(n, h * 2, w * 2, d["conv"].cout)
                 if self.dt == torch.bfloat16:
-                    up = self._new(x.n, x.h * 2, x.w * 2, x.c)
-                    ops.upsample_nearest2x(x, up)
-                    x = ops.conv([ConvIn(up, 3, 1, 1)], d["conv"].w, out, bias=d["conv"].b)
+                    up = self._new(n, h * 2, w * 2, x.h.c)
+                    ops.upsample_nearest2x(x.h, up)
+                    ops.conv([ConvIn(up, 3, 1, 1)], d["conv"].w, out.f, bias=d["conv"].b, out2=self._out2(out))
                 else:
-                    x = ops.conv([ConvIn(x, 3, 1, 1, upsample=1)], d["conv"].w, out, bias=d["conv"].b)
+                    ops.conv([ConvIn(x.h, 3, 1, 1, upsample=1)], d["conv"].w, out.f, bias=d["conv"].b)
+                x = out
             else:
                 raise ValueError(k)
         return x
@@ -583,32 +599,34 @@ class UNetEngine:
         for layers in self.inp[1:]:
             hh, ww = res[-1]
             res.append((hh // 2, ww // 2) if layers[0]["kind"] == "down" else (hh, ww))
-        cat = []
+        cat: List[Dual] = []
         h_ch = self.mid_ch
         for j, layers in enumerate(self.outb):
             i = n_in - 1 - j                       # skip partner (hs.pop(), openaimodel.py:736)
             hh, ww = res[i]
-            cat.append(self._new(n, hh, ww, h_ch + self.skip_ch[i]))
+            cat.append(self._new_dual(n, hh, ww, h_ch + self.skip_ch[i]))
             h_ch = layers[0]["cout"]
-        skip_dst = [cat[n_in - 1 - i].cols(cat[n_in - 1 - i].c - self.skip_ch[i], self.skip_ch[i]) for i in range(n_in)]
+
+        def window(j, c0, c):
+            return Dual(cat[j].f.cols(c0, c), cat[j].f.cols(c0, c) if cat[j].h is cat[j].f else cat[j].h.cols(c0, c))
+
+        skip_dst = [window(n_in - 1 - i, cat[n_in - 1 - i].f.c - self.skip_ch[i], self.skip_ch[i]) for i in range(n_in)]
 
         xin = self._new(n, H, W, cin)
         ops.nchw_to_nhwc(x, xin)
-        h = xin
+        h = Dual(xin, xin)
         for i, layers in enumerate(self.inp):
             h = self._run(layers, h, emb_all.buf, kv_all, n_ctx, skip_dst[i])
-        mid_dst = cat[0].cols(0, self.mid_ch)
-        h = self._run(self.mid, h, emb_all.buf, kv_all, n_ctx, mid_dst)
+        h = self._run(self.mid, h, emb_all.buf, kv_all, n_ctx, window(0, 0, self.mid_ch))
         for j, layers in enumerate(self.outb):
             if j + 1 < len(self.outb):
-                nxt = cat[j + 1]
-                dst = nxt.cols(0, nxt.c - self.skip_ch[n_in - 2 - j])
+                dst = window(j + 1, 0, cat[j + 1].f.c - self.skip_ch[n_in - 2 - j])
             else:
                 dst = None
             h = self._run(layers, cat[j], emb_all.buf, kv_all, n_ctx, dst)
 
-        hn = self._new(n, H, W, h.c)
-        ops.group_norm(h, self.out_norm[0], self.out_norm[1], 1e-5, hn, self.stats, silu=True)
+        hn = self._new(n, H, W, h.f.c)
+        ops.group_norm(h.f, self.out_norm[0], self.out_norm[1], 1e-5, hn, self.stats, silu=True)
         co = m.out_channels
         co_pad = (co + 7) // 8 * 8
         obuf = Act.empty(n, H, W, co_pad, torch.float32, dev)
@@ -616,3 +634,11 @@ class UNetEngine:
         y = torch.empty((n, co, H, W), dtype=torch.float32, device=dev)
         ops.nhwc_to_nchw(obuf.cols(0, co), y)
         return y
+
+
+class Dual:
+    """A residual-stream activation: fp32 master `f` and compute-dtype operand shadow `h` (same object in fp32 mode)."""
+    __slots__ = ("f", "h")
+
+    def __init__(self, f: Act, h: Act):
+        self.f, self.h = f, h

@@ -100,6 +100,9 @@ typedef struct {
   int64_t ld_out;
   int32_t out_f32; /* 1: `out` is float regardless of dtype */
   int32_t res_f32; /* 1: `residual` is float regardless of dtype (fp32 residual stream) */
+  void* out2;      /* optional second copy of the result in `dtype` (the bf16 operand shadow of an
+                      fp32 residual-stream tensor), pitch ld_out2; NULL if unused */
+  int64_t ld_out2;
 } ealdm_conv_args;
 
 int ealdm_conv(const ealdm_conv_args* a, ealdm_stream_t stream);
@@ -114,17 +117,19 @@ int ealdm_conv(const ealdm_conv_args* a, ealdm_stream_t stream);
  *   openaimodel.py:201-205,225-232,682-686; Normalize (eps 1e-6) attention.py:76-77, model.py:38-39.
  */
 typedef struct {
-  int32_t dtype;
-  int32_t act; /* EALDM_ACT_NONE or EALDM_ACT_SILU */
+  int32_t dtype; /* type of y (and of x unless x_f32) */
+  int32_t act;   /* EALDM_ACT_NONE or EALDM_ACT_SILU */
   const void* x;
   int64_t n, hw, c, ld_x;
-  int32_t groups;
+  int32_t groups; /* bit 31 clear; see x_f32 below */
   float eps;
   const float* gamma;
   const float* beta;
   void* y;
   int64_t ld_y;
   void* workspace;
+  int32_t x_f32; /* 1: x is float regardless of dtype (fp32 residual stream -> bf16 GEMM operand) */
+  int32_t reserved;
 } ealdm_group_norm_args;
 
 int64_t ealdm_group_norm_workspace_bytes(int64_t n, int64_t hw, int64_t c);
