@@ -19,6 +19,7 @@ from . import _lib as L
 from . import ops
 from .ops import Act, ConvIn
 from .packing import pack_conv_weight
+from .unet import Dual
 from .util import instantiate_from_config
 
 
@@ -298,32 +299,45 @@ class AutoencoderEngine:
         self.quant = pc(m.quant_conv)
         self.post_quant = pc(m.post_quant_conv, pad_cin_to=4)
 
+    # Residual stream in fp32 with compute-dtype operand shadows, exactly as in unet.UNetEngine.
     def _new(self, n, h, w, c, dtype=None) -> Act:
         return Act.empty(n, h, w, c, dtype or self.dt, self.dev)
+
+    def _new_dual(self, n, h, w, c) -> Dual:
+        f = self._new(n, h, w, c, torch.float32)
+        return Dual(f, f if self.dt == torch.float32 else self._new(n, h, w, c))
+
+    @staticmethod
+    def _out2(d: Dual):
+        return None if d.h is d.f else d.h
 
     def _gn(self, x: Act, wb, silu: bool) -> Act:
         out = self._new(x.n, x.h, x.w, x.c)
         return ops.group_norm(x, wb[0], wb[1], 1e-6, out, self.stats, silu=silu)
 
-    def _res(self, d, x: Act) -> Act:
-        h1 = self._new(x.n, x.h, x.w, d["cout"])
-        ops.conv([ConvIn(self._gn(x, d["gn1"], True), 3, 1, 1)], d["conv1"][0], h1, bias=d["conv1"][1])
+    def _res(self, d, x: Dual) -> Dual:
+        n, h, w = x.f.n, x.f.h, x.f.w
+        h1 = self._new(n, h, w, d["cout"], torch.float32)
+        ops.conv([ConvIn(self._gn(x.f, d["gn1"], True), 3, 1, 1)], d["conv1"][0], h1, bias=d["conv1"][1])
         hn2 = self._gn(h1, d["gn2"], True)
-        out = self._new(x.n, x.h, x.w, d["cout"])
+        out = self._new_dual(n, h, w, d["cout"])
         if d["skip"]:
-            ops.conv([ConvIn(hn2, 3, 1, 1), ConvIn(x, 1, 1, 0)], d["conv2"][0], out, bias=d["conv2"][1])
+            ops.conv([ConvIn(hn2, 3, 1, 1), ConvIn(x.h, 1, 1, 0)], d["conv2"][0], out.f, bias=d["conv2"][1],
+                     out2=self._out2(out))
         else:
-            ops.conv([ConvIn(hn2, 3, 1, 1)], d["conv2"][0], out, bias=d["conv2"][1], residual=x)
+            ops.conv([ConvIn(hn2, 3, 1, 1)], d["conv2"][0], out.f, bias=d["conv2"][1], residual=x.f,
+                     out2=self._out2(out))
         return out
 
-    def _attn(self, d, x: Act) -> Act:
+    def _attn(self, d, x: Dual) -> Dual:
         """Single-head attention over all channels (d = C = 512): GEMM -> row softmax -> GEMM per image."""
-        C_, n, tok = d["c"], x.n, x.h * x.w
-        xn = self._gn(x, d["norm"], False)
-        q, k = self._new(n, x.h, x.w, C_), self._new(n, x.h, x.w, C_)
+        C_, n, hh, ww = d["c"], x.f.n, x.f.h, x.f.w
+        tok = hh * ww
+        xn = self._gn(x.f, d["norm"], False)
+        q, k = self._new(n, hh, ww, C_), self._new(n, hh, ww, C_)
         ops.linear(xn, d["q"][0], q, bias=d["q"][1])
         ops.linear(xn, d["k"][0], k, bias=d["k"][1])
-        o = self._new(n, x.h, x.w, C_)
+        o = self._new(n, hh, ww, C_)
         s = Act.empty(1, 1, tok, tok, self.dt, self.dev)
         vt = Act.empty(1, 1, C_, tok, self.dt, self.dev)
         wv = Act(d["v"][0], 1, 1, C_)
@@ -336,23 +350,27 @@ class AutoencoderEngine:
             ops.linear(wv, xb, vt)                                 # V^T = Wv xn^T (bias added below)
             ob = Act(o.buf[rows], 1, 1, tok)
             ops.linear(s, vt.buf, ob, bias=d["v"][1])              # P (V + 1 bv^T) = P V + bv (rows of P sum to 1)
-        out = self._new(n, x.h, x.w, C_)
-        ops.linear(o, d["proj"][0], out, bias=d["proj"][1], residual=x)
+        out = self._new_dual(n, hh, ww, C_)
+        ops.linear(o, d["proj"][0], out.f, bias=d["proj"][1], residual=x.f, out2=self._out2(out))
         return out
 
-    def _conv3(self, x: Act, wb, cout, stride=1, pad=1, upsample=False, out: Optional[Act] = None) -> Act:
+    def _conv3(self, x: Act, wb, cout, stride=1, pad=1, upsample=False) -> Dual:
+        """3x3 conv of a compute-dtype operand into a fresh residual-stream tensor."""
         if stride == 2:
             ho, wo = x.h // 2, x.w // 2
         elif upsample:
             ho, wo = x.h * 2, x.w * 2
         else:
             ho, wo = x.h, x.w
-        out = out if out is not None else self._new(x.n, ho, wo, cout)
+        out = self._new_dual(x.n, ho, wo, cout)
         if upsample and self.dt == torch.bfloat16:
             up = self._new(x.n, ho, wo, x.c)
             ops.upsample_nearest2x(x, up)
-            return ops.conv([ConvIn(up, 3, 1, 1)], wb[0], out, bias=wb[1])
-        return ops.conv([ConvIn(x, 3, stride, pad, upsample=1 if upsample else 0)], wb[0], out, bias=wb[1])
+            ops.conv([ConvIn(up, 3, 1, 1)], wb[0], out.f, bias=wb[1], out2=self._out2(out))
+        else:
+            ops.conv([ConvIn(x, 3, stride, pad, upsample=1 if upsample else 0)], wb[0], out.f, bias=wb[1],
+                     out2=self._out2(out))
+        return out
 
     def _input(self, x: torch.Tensor) -> Act:
         n, c, h, w = x.shape
@@ -361,7 +379,7 @@ class AutoencoderEngine:
         ops.nchw_to_nhwc(x.float().contiguous(), a)
         return Act(buf, n, h, w, 4, 0)
 
-    def _output(self, h: Act, wb, cout) -> torch.Tensor:
+    def _output(self, h: Act, wb, cout) -> Act:
         co_pad = (cout + 7) // 8 * 8
         obuf = Act.empty(h.n, h.h, h.w, co_pad, torch.float32, self.dev)
         ops.conv([ConvIn(h, 3, 1, 1)], wb[0], obuf.cols(0, cout), bias=wb[1])
@@ -380,18 +398,18 @@ class AutoencoderEngine:
                 if lvl["attn"]:
                     h = self._attn(lvl["attn"][i], h)
             if "resample" in lvl:
-                h = self._conv3(h, lvl["resample"], h.c, stride=2, pad=0)
+                h = self._conv3(h.h, lvl["resample"], h.f.c, stride=2, pad=0)
         h = self._res(E["mid1"], h)
         h = self._attn(E["attn"], h)
         h = self._res(E["mid2"], h)
-        hn = self._gn(h, E["norm_out"], True)
+        hn = self._gn(h.f, E["norm_out"], True)
         zc = E["conv_out"][0].shape[0]
-        hz = self._new(h.n, h.h, h.w, zc)
+        hz = self._new(hn.n, hn.h, hn.w, zc)
         ops.conv([ConvIn(hn, 3, 1, 1)], E["conv_out"][0], hz, bias=E["conv_out"][1])
         mo = self.quant[0].shape[0]
-        mbuf = Act.empty(h.n, h.h, h.w, (mo + 7) // 8 * 8, torch.float32, self.dev)
+        mbuf = Act.empty(hn.n, hn.h, hn.w, (mo + 7) // 8 * 8, torch.float32, self.dev)
         ops.linear(hz, self.quant[0], mbuf.cols(0, mo), bias=self.quant[1])
-        y = torch.empty((h.n, mo, h.h, h.w), dtype=torch.float32, device=self.dev)
+        y = torch.empty((hn.n, mo, hn.h, hn.w), dtype=torch.float32, device=self.dev)
         return ops.nhwc_to_nchw(mbuf.cols(0, mo), y)
 
     @torch.no_grad()
@@ -415,8 +433,8 @@ class AutoencoderEngine:
                 if lvl["attn"]:
                     h = self._attn(lvl["attn"][i], h)
             if "resample" in lvl:
-                h = self._conv3(h, lvl["resample"], h.c, upsample=True)
-        hn = self._gn(h, D["norm_out"], True)
+                h = self._conv3(h.h, lvl["resample"], h.f.c, upsample=True)
+        hn = self._gn(h.f, D["norm_out"], True)
         co = D["conv_out"][0].shape[0]
         o = self._output(hn, D["conv_out"], co)
         y = torch.empty((o.n, co, o.h, o.w), dtype=torch.float32, device=self.dev)
