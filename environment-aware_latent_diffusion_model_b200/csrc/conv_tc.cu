@@ -12,7 +12,8 @@
 // Persistent, warp-specialised CTA (one per SM):
 //   warp 0      TMA producer (one elected lane)         smem ring of STAGES x (A 16 KiB + B BN*128 B)
 //   warp 1      TMEM allocator + tcgen05.mma issuer     2 accumulator stages of BN fp32 columns
-//   warps 2..5  epilogue: tcgen05.ld -> bias / per-image row vector / SiLU / GEGLU / residual -> global
+//   warps 2..9  epilogue: tcgen05.ld -> smem transpose -> bias / per-image row vector / SiLU / GEGLU /
+//               (prefetched) residual -> coalesced global stores (+ optional bf16 shadow copy)
 // so the epilogue of tile i overlaps the main loop of tile i+1.
 #include "common.cuh"
 #include "ptx.cuh"
@@ -26,7 +27,10 @@ namespace tc {
 constexpr int BM = 128;
 constexpr int BK = 64;  // bf16 per K block = 128 B = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 192;
+constexpr int EPI_WARPS = 8;                      // two per TMEM lane quadrant (even / odd 32-column chunks)
+constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int STG_STRIDE = 33;                    // floats per staged row (conflict-free transpose)
+constexpr int STG_BYTES = 32 * STG_STRIDE * 4;    // per epilogue warp
 
 struct Segment {
   int kblocks;  // taps * cblk
@@ -55,129 +59,173 @@ struct Cfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
-  static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;
+  static constexpr int BAR_BYTES = 256;  // (2*STAGES + 4) mbarriers + the TMEM base slot
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + EPI_WARPS * STG_BYTES + 1024;
+  static_assert((2 * STAGES + 4) * 8 + 4 <= BAR_BYTES, "barrier block too small");
+  static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KiB dynamic shared memory limit");
 };
 
-// ---- epilogue for one row x 32 accumulator columns ------------------------------------------------
-template <typename TOut>
-__device__ __forceinline__ void store8(TOut* dst, const float (&o)[8]);
-template <>
-__device__ __forceinline__ void store8<float>(float* dst, const float (&o)[8]) {
-  reinterpret_cast<float4*>(dst)[0] = make_float4(o[0], o[1], o[2], o[3]);
-  reinterpret_cast<float4*>(dst)[1] = make_float4(o[4], o[5], o[6], o[7]);
-}
-template <>
-__device__ __forceinline__ void store8<bf16>(bf16* dst, const float (&o)[8]) {
-  uint4 u;
-  __nv_bfloat162 t;
-  t = __floats2bfloat162_rn(o[0], o[1]); u.x = *reinterpret_cast<uint32_t*>(&t);
-  t = __floats2bfloat162_rn(o[2], o[3]); u.y = *reinterpret_cast<uint32_t*>(&t);
-  t = __floats2bfloat162_rn(o[4], o[5]); u.z = *reinterpret_cast<uint32_t*>(&t);
-  t = __floats2bfloat162_rn(o[6], o[7]); u.w = *reinterpret_cast<uint32_t*>(&t);
-  *reinterpret_cast<uint4*>(dst) = u;
+// ---- epilogue ----------------------------------------------------------------------------------------
+// tcgen05.ld hands every thread one accumulator ROW (32 consecutive columns).  Writing / reading
+// global memory in that layout makes each warp-level access touch 32 different 128-byte lines, which
+// is what bounded the small-K GEMMs of the transformer blocks (LSU wavefronts, not HBM).  The chunk is
+// therefore transposed through a per-warp shared-memory tile so that 8 lanes cover 32 consecutive
+// columns of one row: residual loads, output stores and the bf16 shadow stores are fully coalesced
+// (4 rows x 128 B per warp instruction), and the residual of the NEXT chunk is prefetched into
+// registers while the current one is processed (the first one before the accumulator is even ready).
+// GELU for the bf16 tensor-core path: erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, far below
+// bf16 resolution) -- ~3x fewer instructions than erff in the epilogue's critical path.  The fp32
+// parity path (conv_simt.cu) keeps the exact erff.
+__device__ __forceinline__ float gelu_fast(float v) {
+  const float x = fabsf(v) * 0.70710678118654752440f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, x, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float erf_abs = 1.0f - poly * t * __expf(-x * x);
+  const float erf_v = copysignf(erf_abs, v);
+  return 0.5f * v * (1.0f + erf_v);
 }
 
-template <typename TOut>
-__device__ __forceinline__ void epilogue_chunk(const uint32_t (&acc)[32], const Epilogue& ep,
-                                               long long row, long long img, int col0, int N) {
-  const bool vec_ok = (col0 + 32 <= N);
-  if (ep.act == EALDM_ACT_GEGLU) {
-    // columns [0,16) are values, [16,32) their gates; output column = col0/2 + j
-    const int ocol0 = col0 >> 1;
-    TOut* dst = reinterpret_cast<TOut*>(ep.out) + row * ep.ld_out + ocol0;
-#pragma unroll
-    for (int g = 0; g < 2; ++g) {
-      float o[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float a = __uint_as_float(acc[g * 8 + j]);
-        float b = __uint_as_float(acc[16 + g * 8 + j]);
-        if (ep.bias) {
-          a += __ldg(ep.bias + col0 + g * 8 + j);
-          b += __ldg(ep.bias + col0 + 16 + g * 8 + j);
-        }
-        o[j] = a * gelu_erf_f(b);
-      }
-      if (ep.residual) {
-        if (ep.res_f32) {
-          const float* r = reinterpret_cast<const float*>(ep.residual) + row * ep.ld_res + ocol0 + g * 8;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] += r[j];
-        } else {
-          const bf16* r = reinterpret_cast<const bf16*>(ep.residual) + row * ep.ld_res + ocol0 + g * 8;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] += __bfloat162float(r[j]);
-        }
-      }
-      store8<TOut>(dst + g * 8, o);
-    }
+struct RowSet {          // the 8 output rows this thread touches in the coalesced layout
+  long long row[8];
+  int img[8];
+  unsigned valid;        // bit i: row i exists
+};
+
+// rare paths (N not a multiple of 4 at the right edge) are kept out of line to keep the hot code small
+__device__ __noinline__ float4 ld_res4_edge(const Epilogue& ep, long long row, int col, int N) {
+  float t[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int e = 0; e < 4 && col + e < N; ++e)
+    t[e] = ep.res_f32 ? reinterpret_cast<const float*>(ep.residual)[row * ep.ld_res + col + e]
+                      : __bfloat162float(reinterpret_cast<const bf16*>(ep.residual)[row * ep.ld_res + col + e]);
+  return make_float4(t[0], t[1], t[2], t[3]);
+}
+
+__device__ __forceinline__ float4 ld_res4(const Epilogue& ep, long long row, int col, int N, bool ok) {
+  float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (!ok || col >= N) return r;
+  if (col + 4 > N) return ld_res4_edge(ep, row, col, N);
+  if (ep.res_f32) {
+    r = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(ep.residual) + row * ep.ld_res + col);
+  } else {
+    const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(ep.residual) +
+                                                    row * ep.ld_res + col);
+    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&u.x);
+    const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
+    r = make_float4(__low2float(a), __high2float(a), __low2float(b), __high2float(b));
+  }
+  return r;
+}
+
+__device__ __forceinline__ uint2 pack4_bf16(const float4& v) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y);
+  __nv_bfloat162 b = __floats2bfloat162_rn(v.z, v.w);
+  uint2 u;
+  u.x = *reinterpret_cast<uint32_t*>(&a);
+  u.y = *reinterpret_cast<uint32_t*>(&b);
+  return u;
+}
+
+__device__ __noinline__ void st_out4_edge(const Epilogue& ep, long long row, int col, int N, float4 v) {
+  const float t[4] = {v.x, v.y, v.z, v.w};
+  for (int e = 0; e < 4 && col + e < N; ++e) {
+    if (ep.out_f32)
+      reinterpret_cast<float*>(ep.out)[row * ep.ld_out + col + e] = t[e];
+    else
+      reinterpret_cast<bf16*>(ep.out)[row * ep.ld_out + col + e] = __float2bfloat16_rn(t[e]);
+    if (ep.out2) reinterpret_cast<bf16*>(ep.out2)[row * ep.ld_out2 + col + e] = __float2bfloat16_rn(t[e]);
+  }
+}
+
+__device__ __forceinline__ void st_out4(const Epilogue& ep, long long row, int col, int N, const float4& v) {
+  if (col + 4 > N) {
+    st_out4_edge(ep, row, col, N, v);
     return;
   }
-  TOut* dst = reinterpret_cast<TOut*>(ep.out) + row * ep.ld_out + col0;
-  const float* rv = ep.rowvec ? ep.rowvec + img * ep.ld_rowvec + col0 : nullptr;
-  const bf16* res = (ep.residual && !ep.res_f32)
-                        ? reinterpret_cast<const bf16*>(ep.residual) + row * ep.ld_res + col0
-                        : nullptr;
-  const float* resf = (ep.residual && ep.res_f32)
-                          ? reinterpret_cast<const float*>(ep.residual) + row * ep.ld_res + col0
-                          : nullptr;
-  if (vec_ok) {
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      float o[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = __uint_as_float(acc[g * 8 + j]);
-      if (ep.bias) {
-        const float4 b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + g * 8));
-        const float4 b1 = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + g * 8 + 4));
-        o[0] += b0.x; o[1] += b0.y; o[2] += b0.z; o[3] += b0.w;
-        o[4] += b1.x; o[5] += b1.y; o[6] += b1.z; o[7] += b1.w;
-      }
-      if (rv) {
-        const float4 b0 = __ldg(reinterpret_cast<const float4*>(rv + g * 8));
-        const float4 b1 = __ldg(reinterpret_cast<const float4*>(rv + g * 8 + 4));
-        o[0] += b0.x; o[1] += b0.y; o[2] += b0.z; o[3] += b0.w;
-        o[4] += b1.x; o[5] += b1.y; o[6] += b1.z; o[7] += b1.w;
-      }
-      if (ep.act == EALDM_ACT_SILU) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = silu_f(o[j]);
-      }
-      if (res) {
-        const uint4 u = *reinterpret_cast<const uint4*>(res + g * 8);
-        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          o[2 * j] += __low2float(h[j]);
-          o[2 * j + 1] += __high2float(h[j]);
-        }
-      }
-      if (resf) {
-        const float4 r0 = *reinterpret_cast<const float4*>(resf + g * 8);
-        const float4 r1 = *reinterpret_cast<const float4*>(resf + g * 8 + 4);
-        o[0] += r0.x; o[1] += r0.y; o[2] += r0.z; o[3] += r0.w;
-        o[4] += r1.x; o[5] += r1.y; o[6] += r1.z; o[7] += r1.w;
-      }
-      store8<TOut>(dst + g * 8, o);
-      if (ep.out2) store8<bf16>(reinterpret_cast<bf16*>(ep.out2) + row * ep.ld_out2 + col0 + g * 8, o);
-    }
-  } else {
-    for (int j = 0; j < 32; ++j) {
-      if (col0 + j >= N) break;
-      float o = __uint_as_float(acc[j]);
-      if (ep.bias) o += __ldg(ep.bias + col0 + j);
-      if (rv) o += __ldg(rv + j);
-      if (ep.act == EALDM_ACT_SILU) o = silu_f(o);
-      if (res) o += __bfloat162float(res[j]);
-      if (resf) o += resf[j];
-      dst[j] = from_f32<TOut>(o);
-      if (ep.out2) reinterpret_cast<bf16*>(ep.out2)[row * ep.ld_out2 + col0 + j] = __float2bfloat16_rn(o);
-    }
-  }
+  if (ep.out_f32)
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + row * ep.ld_out + col) = v;
+  else
+    *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(ep.out) + row * ep.ld_out + col) = pack4_bf16(v);
+  if (ep.out2)
+    *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(ep.out2) + row * ep.ld_out2 + col) = pack4_bf16(v);
 }
 
-template <int BN>
+// 4 consecutive fp32 of a per-column vector (bias / per-image row vector), bounds-safe
+__device__ __noinline__ float4 ld_vec4_edge(const float* p, int col, int N) {
+  float t[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int e = 0; e < 4 && col + e < N; ++e) t[e] = __ldg(p + col + e);
+  return make_float4(t[0], t[1], t[2], t[3]);
+}
+__device__ __forceinline__ float4 ld_vec4(const float* p, int col, int N) {
+  if (p == nullptr || col >= N) return make_float4(0.f, 0.f, 0.f, 0.f);
+  if (col + 4 <= N) return __ldg(reinterpret_cast<const float4*>(p + col));
+  return ld_vec4_edge(p, col, N);
+}
+
+// `b4` = bias (+ the per-image row vector when all rows of the warp belong to one image: rv_uniform)
+__device__ __forceinline__ void epilogue_chunk(const uint32_t (&acc)[32], float* stg, int lane,
+                                               const Epilogue& ep, const RowSet& rs, const float4 (&res)[8],
+                                               const float4& b4, bool rv_uniform, int col0, int N) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) stg[lane * STG_STRIDE + j] = __uint_as_float(acc[j]);
+  __syncwarp();
+  const int cc = (lane & 7) * 4;
+  const int col = col0 + cc;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int rr = i * 4 + (lane >> 3);
+    const float* sp = stg + rr * STG_STRIDE + cc;
+    float4 v = make_float4(sp[0] + b4.x, sp[1] + b4.y, sp[2] + b4.z, sp[3] + b4.w);
+    if (((rs.valid >> i) & 1u) && col < N) {
+      if (ep.rowvec && !rv_uniform) {
+        const float4 r4 = ld_vec4(ep.rowvec + static_cast<long long>(rs.img[i]) * ep.ld_rowvec, col, N);
+        v.x += r4.x; v.y += r4.y; v.z += r4.z; v.w += r4.w;
+      }
+      if (ep.act == EALDM_ACT_SILU) {
+        v.x = silu_f(v.x); v.y = silu_f(v.y); v.z = silu_f(v.z); v.w = silu_f(v.w);
+      }
+      v.x += res[i].x; v.y += res[i].y; v.z += res[i].z; v.w += res[i].w;
+      st_out4(ep, rs.row[i], col, N, v);
+    }
+  }
+  __syncwarp();
+}
+
+// GEGLU chunk: columns [0,16) are values, [16,32) their gates -> 16 output columns at col0/2.
+// The raw accumulators are staged, then 4 lanes x 4 columns finish one row: bias pairs `bv`/`bg`
+// (prefetched per tile) stay in registers.
+__device__ __forceinline__ void epilogue_chunk_geglu(const uint32_t (&acc)[32], float* stg, int lane,
+                                                     const Epilogue& ep, const long long (&row4)[4],
+                                                     unsigned valid4, const float4& bv, const float4& bg,
+                                                     int col0) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) stg[lane * STG_STRIDE + j] = __uint_as_float(acc[j]);
+  __syncwarp();
+  const int c4 = (lane & 3) * 4;
+  const int oc = (col0 >> 1) + c4;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int rr = i * 8 + (lane >> 2);
+    const float* sp = stg + rr * STG_STRIDE + c4;
+    float4 v;
+    v.x = (sp[0] + bv.x) * gelu_fast(sp[16] + bg.x);
+    v.y = (sp[1] + bv.y) * gelu_fast(sp[17] + bg.y);
+    v.z = (sp[2] + bv.z) * gelu_fast(sp[18] + bg.z);
+    v.w = (sp[3] + bv.w) * gelu_fast(sp[19] + bg.w);
+    if ((valid4 >> i) & 1u) {
+      if (ep.residual) {
+        const float4 r4 = ld_res4(ep, row4[i], oc, 1 << 30, true);
+        v.x += r4.x; v.y += r4.y; v.z += r4.z; v.w += r4.w;
+      }
+      st_out4(ep, row4[i], oc, 1 << 30, v);
+    }
+  }
+  __syncwarp();
+}
+
+template <int BN, bool GEGLU>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ Params p) {
@@ -190,6 +238,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   uint64_t* tmem_full = empty_bar + C::STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint8_t* stg_base = smem + C::STAGES * C::STAGE_BYTES + C::BAR_BYTES;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -204,7 +253,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tmem_full[a], 1);
-      ptx::mbar_init(&tmem_empty[a], 4);
+      ptx::mbar_init(&tmem_empty[a], EPI_WARPS);
     }
     ptx::fence_mbar_init();
   }
@@ -284,12 +333,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       if (acc == 0) acc_phase ^= 1u;
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
-    const int quad = warp & 3;  // TMEM lane quadrant this warp may read
-    const int r = quad * 32 + lane;
-    const int bw_i = r % p.bw;
-    const int bh_i = (r / p.bw) % p.bh;
-    const int bn_i = r / (p.bw * p.bh);
+    // ===================== epilogue (warps 2..9) =====================
+    const int quad = warp & 3;             // TMEM lane quadrant this warp may read
+    const int part = (warp - 2) >> 2;      // 0: even 32-column chunks, 1: odd chunks
+    float* stg = reinterpret_cast<float*>(stg_base + (warp - 2) * STG_BYTES);
+    const bool has_res = p.ep.residual != nullptr;
+    constexpr int NCH = (BN + 63) / 64;    // chunks per epilogue warp
+    const int cc = (lane & 7) * 4;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -298,25 +348,105 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       const int tw = mt % p.tiles_w;
       const int th = (mt / p.tiles_w) % p.tiles_h;
       const int tn = mt / (p.tiles_w * p.tiles_h);
-      const int w = tw * p.bw + bw_i, h = th * p.bh + bh_i, n = tn * p.bn + bn_i;
-      const bool valid = (w < p.Wout) && (h < p.Hout) && (n < p.Nimg);
-      const long long row = (static_cast<long long>(n) * p.Hout + h) * p.Wout + w;
-
-      ptx::mbar_wait(&tmem_full[acc], acc_phase);
-      ptx::tc_fence_after();
+      auto decode = [&](int r, long long& row, int& img) -> bool {
+        const int w = tw * p.bw + r % p.bw;
+        const int h = th * p.bh + (r / p.bw) % p.bh;
+        const int n = tn * p.bn + r / (p.bw * p.bh);
+        row = (static_cast<long long>(n) * p.Hout + h) * p.Wout + w;
+        img = n;
+        return (w < p.Wout) && (h < p.Hout) && (n < p.Nimg);
+      };
       const uint32_t taddr0 =
           tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * BN);
+
+      if constexpr (GEGLU) {
+        long long row4[4];
+        unsigned valid4 = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          int img;
+          if (decode(quad * 32 + i * 8 + (lane >> 2), row4[i], img)) valid4 |= 1u << i;
+        }
+        // (value, gate) bias pair of the first chunk, fetched before the accumulator is ready;
+        // the next chunk's pair is prefetched while the current chunk is processed
+        const int c4 = (lane & 3) * 4;
+        float4 bv_n = ld_vec4(p.ep.bias, nt * BN + part * 32 + c4, p.N);
+        float4 bg_n = ld_vec4(p.ep.bias, nt * BN + part * 32 + 16 + c4, p.N);
+        ptx::mbar_wait(&tmem_full[acc], acc_phase);
+        ptx::tc_fence_after();
 #pragma unroll 1
-      for (int ch = 0; ch < BN / 32; ++ch) {
-        uint32_t v[32];
-        ptx::tmem_ld_32x32(taddr0 + ch * 32, v);
-        ptx::tmem_ld_wait();
-        const int col0 = nt * BN + ch * 32;
-        if (valid && col0 < p.N) {
-          if (p.ep.out_f32)
-            epilogue_chunk<float>(v, p.ep, row, n, col0, p.N);
-          else
-            epilogue_chunk<bf16>(v, p.ep, row, n, col0, p.N);
+        for (int ch = part; ch < BN / 32; ch += 2) {
+          uint32_t v[32];
+          ptx::tmem_ld_32x32(taddr0 + ch * 32, v);
+          const float4 bv = bv_n, bg = bg_n;
+          const int col0 = nt * BN + ch * 32;
+          if (ch + 2 < BN / 32) {
+            bv_n = ld_vec4(p.ep.bias, col0 + 64 + c4, p.N);
+            bg_n = ld_vec4(p.ep.bias, col0 + 64 + 16 + c4, p.N);
+          }
+          ptx::tmem_ld_wait();
+          if (col0 < p.N) epilogue_chunk_geglu(v, stg, lane, p.ep, row4, valid4, bv, bg, col0);
+        }
+      } else {
+        RowSet rs;
+        rs.valid = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (decode(quad * 32 + i * 4 + (lane >> 3), rs.row[i], rs.img[i])) rs.valid |= 1u << i;
+        // bias (+ per-image row vector when this thread's rows share one image) and residual of the
+        // FIRST chunk are fetched before the accumulator is ready; those of the next chunk while the
+        // current one is processed: no global-load latency between tcgen05.ld and the stores
+        bool rv_uniform = false;
+        const float* rv0 = nullptr;
+        if (p.ep.rowvec) {
+          rv_uniform = true;
+          int img0 = 0;
+          bool first = true;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            if ((rs.valid >> i) & 1u) {
+              if (first) { img0 = rs.img[i]; first = false; }
+              else if (rs.img[i] != img0) rv_uniform = false;
+            }
+          }
+          if (rv_uniform) rv0 = p.ep.rowvec + static_cast<long long>(img0) * p.ep.ld_rowvec;
+        }
+        auto load_bias = [&](int c0) -> float4 {
+          float4 b = ld_vec4(p.ep.bias, c0, p.N);
+          const float4 r4 = ld_vec4(rv0, c0, p.N);
+          b.x += r4.x; b.y += r4.y; b.z += r4.z; b.w += r4.w;
+          return b;
+        };
+        float4 b_n = load_bias(nt * BN + part * 32 + cc);
+        float4 rnext[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) rnext[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (has_res) {
+          const int c0 = nt * BN + part * 32 + cc;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) rnext[i] = ld_res4(p.ep, rs.row[i], c0, p.N, (rs.valid >> i) & 1u);
+        }
+        ptx::mbar_wait(&tmem_full[acc], acc_phase);
+        ptx::tc_fence_after();
+#pragma unroll 1
+        for (int ch = part; ch < BN / 32; ch += 2) {
+          uint32_t v[32];
+          ptx::tmem_ld_32x32(taddr0 + ch * 32, v);
+          float4 rcur[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) rcur[i] = rnext[i];
+          const float4 b4 = b_n;
+          const int col0 = nt * BN + ch * 32;
+          if (ch + 2 < BN / 32) {
+            b_n = load_bias(col0 + 64 + cc);
+            if (has_res) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                rnext[i] = ld_res4(p.ep, rs.row[i], col0 + 64 + cc, p.N, (rs.valid >> i) & 1u);
+            }
+          }
+          ptx::tmem_ld_wait();
+          if (col0 < p.N) epilogue_chunk(v, stg, lane, p.ep, rs, rcur, b4, rv_uniform, col0, p.N);
         }
       }
       ptx::tc_fence_before();
@@ -366,19 +496,19 @@ static int pow2_ceil(long long v) {
   return p;
 }
 
-template <int BN>
+template <int BN, bool GEGLU>
 static int launch_bn(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
                      const Params& p, cudaStream_t st) {
   using C = Cfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
-    EALDM_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    EALDM_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, GEGLU>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     C::SMEM_BYTES));
     attr_set = true;
   }
   const int total = p.m_tiles * p.n_tiles;
   const int grid = total < num_sms() ? total : num_sms();
-  conv_tc_kernel<BN><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(a0, a1, b, p);
+  conv_tc_kernel<BN, GEGLU><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(a0, a1, b, p);
   EALDM_LAUNCH_CHECK();
   return 0;
 }
@@ -428,7 +558,7 @@ int launch(const ealdm_conv_args* a, cudaStream_t st) {
 
   // choose the N tile: fewest (waves x tile cost)
   int BN;
-  if (a->n_out <= 32) {
+  if (a->n_out <= 32 && a->act != EALDM_ACT_GEGLU) {
     BN = 32;
   } else if (a->n_out <= 128) {
     BN = 128;
@@ -500,10 +630,15 @@ int launch(const ealdm_conv_args* a, cudaStream_t st) {
   p.ep.out2 = a->out2;
   p.ep.ld_out2 = a->ld_out2;
 
+  const bool geglu = a->act == EALDM_ACT_GEGLU;
   switch (BN) {
-    case 32: return launch_bn<32>(tmA[0], tmA[1], tmB, p, st);
-    case 128: return launch_bn<128>(tmA[0], tmA[1], tmB, p, st);
-    default: return launch_bn<256>(tmA[0], tmA[1], tmB, p, st);
+    case 32: return launch_bn<32, false>(tmA[0], tmA[1], tmB, p, st);
+    case 128:
+      return geglu ? launch_bn<128, true>(tmA[0], tmA[1], tmB, p, st)
+                   : launch_bn<128, false>(tmA[0], tmA[1], tmB, p, st);
+    default:
+      return geglu ? launch_bn<256, true>(tmA[0], tmA[1], tmB, p, st)
+                   : launch_bn<256, false>(tmA[0], tmA[1], tmB, p, st);
   }
 }
 

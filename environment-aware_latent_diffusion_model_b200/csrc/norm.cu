@@ -99,34 +99,41 @@ gn_apply_kernel(const TX* __restrict__ x, long long ld_x, T* __restrict__ y, lon
     }
   }
   __syncthreads();
+  // same thread -> (4-channel vector, pixel lane) mapping as the statistics kernel: consecutive threads
+  // on consecutive channels (coalesced), no integer divisions in the pixel loop
+  const int lanes_v = vpp < NT ? vpp : NT;
+  const int pix_lanes = NT / lanes_v;
+  const int tv = t % lanes_v, tp = t / lanes_v;
   const int p0 = blockIdx.x * pix_per_cta;
   const int p1 = min(p0 + pix_per_cta, hw);
-  const long long items = static_cast<long long>(p1 - p0) * vpp;
   const TX* xb = x + static_cast<long long>(n) * hw * ld_x;
   T* yb = y + static_cast<long long>(n) * hw * ld_y;
-  for (long long i = t; i < items; i += NT) {
-    const int pix = p0 + static_cast<int>(i / vpp);
-    const int v = static_cast<int>(i % vpp);
-    const int ch = v * 4;
-    Vec4<TX> qx;
-    qx.load(xb + static_cast<long long>(pix) * ld_x + ch);
-    float f[4];
-    qx.get(f);
-    Vec4<T> q;
-    const int g = ch / cpg;
-    const float mean = s_mean[g], rstd = s_rstd[g];
-    const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + ch));
-    const float4 be = __ldg(reinterpret_cast<const float4*>(beta + ch));
-    const float gv[4] = {ga.x, ga.y, ga.z, ga.w};
-    const float bv[4] = {be.x, be.y, be.z, be.w};
+  if (tp < pix_lanes) {
+    for (int v = tv; v < vpp; v += lanes_v) {
+      const int ch = v * 4;
+      const int g = ch / cpg;
+      const float mean = s_mean[g], rstd = s_rstd[g];
+      const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + ch));
+      const float4 be = __ldg(reinterpret_cast<const float4*>(beta + ch));
+      // y = x * a + b with a = rstd * gamma, b = beta - mean * a
+      const float a0 = rstd * ga.x, a1 = rstd * ga.y, a2 = rstd * ga.z, a3 = rstd * ga.w;
+      const float b0 = be.x - mean * a0, b1 = be.y - mean * a1, b2 = be.z - mean * a2, b3 = be.w - mean * a3;
+#pragma unroll 4
+      for (int pix = p0 + tp; pix < p1; pix += pix_lanes) {
+        Vec4<TX> qx;
+        qx.load(xb + static_cast<long long>(pix) * ld_x + ch);
+        float f[4];
+        qx.get(f);
+        f[0] = fmaf(f[0], a0, b0); f[1] = fmaf(f[1], a1, b1); f[2] = fmaf(f[2], a2, b2); f[3] = fmaf(f[3], a3, b3);
+        if (act == EALDM_ACT_SILU) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float o = (f[j] - mean) * rstd * gv[j] + bv[j];
-      if (act == EALDM_ACT_SILU) o = silu_f(o);
-      f[j] = o;
+          for (int j = 0; j < 4; ++j) f[j] = silu_f(f[j]);
+        }
+        Vec4<T> q;
+        q.set(f);
+        q.store(yb + static_cast<long long>(pix) * ld_y + ch);
+      }
     }
-    q.set(f);
-    q.store(yb + static_cast<long long>(pix) * ld_y + ch);
   }
 }
 
@@ -162,7 +169,51 @@ static int group_norm_t(const ealdm_group_norm_args* a, cudaStream_t st) {
   return 0;
 }
 
-// ---- LayerNorm: one warp per row, two-pass mean / centred variance ------------------------------------
+// ---- LayerNorm: one warp per row; the row lives in registers (one global read), two-pass variance ----
+template <typename TX, typename T, int NV>   // NV = float4 per lane: c == NV * 128
+__global__ void __launch_bounds__(NT)
+layer_norm_reg_kernel(const TX* __restrict__ x, long long ld_x, T* __restrict__ y, long long ld_y,
+                      long long rows, float eps, const float* __restrict__ gamma,
+                      const float* __restrict__ beta) {
+  constexpr int C_ = NV * 128;
+  const int lane = threadIdx.x & 31;
+  const long long row = static_cast<long long>(blockIdx.x) * (NT / 32) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const TX* xr = x + row * ld_x;
+  T* yr = y + row * ld_y;
+  float f[NV][4];
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    Vec4<TX> q;
+    q.load(xr + (k * 32 + lane) * 4);
+    q.get(f[k]);
+    s += (f[k][0] + f[k][1]) + (f[k][2] + f[k][3]);
+  }
+  const float mean = warp_sum(s) / static_cast<float>(C_);
+  float ss = 0.f;
+#pragma unroll
+  for (int k = 0; k < NV; ++k)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { const float d = f[k][j] - mean; ss = fmaf(d, d, ss); }
+  const float rstd = rsqrtf(warp_sum(ss) / static_cast<float>(C_) + eps);
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int c = (k * 32 + lane) * 4;
+    const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + c));
+    const float4 be = __ldg(reinterpret_cast<const float4*>(beta + c));
+    float o[4];
+    o[0] = (f[k][0] - mean) * rstd * ga.x + be.x;
+    o[1] = (f[k][1] - mean) * rstd * ga.y + be.y;
+    o[2] = (f[k][2] - mean) * rstd * ga.z + be.z;
+    o[3] = (f[k][3] - mean) * rstd * ga.w + be.w;
+    Vec4<T> q;
+    q.set(o);
+    q.store(yr + c);
+  }
+}
+
+// generic fallback (any c % 4 == 0): three passes over the row, served from L1 after the first
 template <typename TX, typename T>
 __global__ void __launch_bounds__(NT)
 layer_norm_kernel(const TX* __restrict__ x, long long ld_x, T* __restrict__ y, long long ld_y,
@@ -198,16 +249,36 @@ layer_norm_kernel(const TX* __restrict__ x, long long ld_x, T* __restrict__ y, l
     qx.load(xr + v * 4);
     float f[4];
     qx.get(f);
-    Vec4<T> q;
     const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + v * 4));
     const float4 be = __ldg(reinterpret_cast<const float4*>(beta + v * 4));
     f[0] = (f[0] - mean) * rstd * ga.x + be.x;
     f[1] = (f[1] - mean) * rstd * ga.y + be.y;
     f[2] = (f[2] - mean) * rstd * ga.z + be.z;
     f[3] = (f[3] - mean) * rstd * ga.w + be.w;
+    Vec4<T> q;
     q.set(f);
     q.store(yr + v * 4);
   }
+}
+
+template <typename TX, typename T>
+static void layer_norm_launch(const ealdm_layer_norm_args* a, cudaStream_t st) {
+  const unsigned grid = static_cast<unsigned>(ceil_div(a->rows, NT / 32));
+  const TX* x = reinterpret_cast<const TX*>(a->x);
+  T* y = reinterpret_cast<T*>(a->y);
+#define EALDM_LN_REG(NV)                                                                         \
+  layer_norm_reg_kernel<TX, T, NV><<<grid, NT, 0, st>>>(x, a->ld_x, y, a->ld_y, a->rows, a->eps, \
+                                                        a->gamma, a->beta)
+  switch (a->c) {
+    case 128: EALDM_LN_REG(1); break;
+    case 256: EALDM_LN_REG(2); break;
+    case 512: EALDM_LN_REG(4); break;
+    case 1024: EALDM_LN_REG(8); break;
+    default:
+      layer_norm_kernel<TX, T><<<grid, NT, 0, st>>>(x, a->ld_x, y, a->ld_y, a->rows, (int)a->c, a->eps,
+                                                    a->gamma, a->beta);
+  }
+#undef EALDM_LN_REG
 }
 
 // ---- in-place row softmax(scale * x), one warp per row ---------------------------------------------------
@@ -262,19 +333,12 @@ extern "C" int ealdm_layer_norm(const ealdm_layer_norm_args* a, ealdm_stream_t s
                 "layer_norm: c, ld_x, ld_y must be multiples of 4");
   if (a->rows == 0) return 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const unsigned grid = static_cast<unsigned>(ceil_div(a->rows, norm::NT / 32));
   if (a->dtype == EALDM_F32) {
-    norm::layer_norm_kernel<float, float><<<grid, norm::NT, 0, st>>>(
-        reinterpret_cast<const float*>(a->x), a->ld_x, reinterpret_cast<float*>(a->y), a->ld_y,
-        a->rows, (int)a->c, a->eps, a->gamma, a->beta);
+    norm::layer_norm_launch<float, float>(a, st);
   } else if (a->dtype == EALDM_BF16 && a->x_f32) {
-    norm::layer_norm_kernel<float, bf16><<<grid, norm::NT, 0, st>>>(
-        reinterpret_cast<const float*>(a->x), a->ld_x, reinterpret_cast<bf16*>(a->y), a->ld_y,
-        a->rows, (int)a->c, a->eps, a->gamma, a->beta);
+    norm::layer_norm_launch<float, bf16>(a, st);
   } else if (a->dtype == EALDM_BF16) {
-    norm::layer_norm_kernel<bf16, bf16><<<grid, norm::NT, 0, st>>>(
-        reinterpret_cast<const bf16*>(a->x), a->ld_x, reinterpret_cast<bf16*>(a->y), a->ld_y,
-        a->rows, (int)a->c, a->eps, a->gamma, a->beta);
+    norm::layer_norm_launch<bf16, bf16>(a, st);
   } else {
     return set_error(EALDM_EINVAL, "layer_norm: bad dtype %d", a->dtype);
   }
