@@ -12,9 +12,16 @@
 // Persistent, warp-specialised CTA (one per SM):
 //   warp 0      TMA producer (one elected lane)         smem ring of STAGES x (A 16 KiB + B BN*128 B)
 //   warp 1      TMEM allocator + tcgen05.mma issuer     2 accumulator stages of BN fp32 columns
-//   warps 2..9  epilogue: tcgen05.ld -> smem transpose -> bias / per-image row vector / SiLU / GEGLU /
-//               (prefetched) residual -> coalesced global stores (+ optional bf16 shadow copy)
+//   warps 2..9  epilogue, two per TMEM lane quadrant (even / odd 32-column units)
 // so the epilogue of tile i overlaps the main loop of tile i+1.
+//
+// Epilogue data movement is TMA in both directions: every epilogue warp owns [32 rows x 32 columns]
+// units of the tile.  The residual unit is prefetched by a TMA box load (issued one unit ahead, across
+// tile boundaries) into a swizzled shared-memory buffer; the thread that owns accumulator row r
+// (tcgen05.ld hands every thread one row) reads row r of it, adds bias / per-image row vector /
+// activation, writes the result back into the same buffer and one lane issues the TMA store (plus a
+// second store of the bf16 operand shadow).  No thread computes a global address, every global access
+// is a full 128-byte (fp32) or 64-byte (bf16) row segment, and M / N edges are clipped by the TMA unit.
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -27,10 +34,11 @@ namespace tc {
 constexpr int BM = 128;
 constexpr int BK = 64;  // bf16 per K block = 128 B = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int EPI_WARPS = 8;                      // two per TMEM lane quadrant (even / odd 32-column chunks)
+constexpr int EPI_WARPS = 8;
 constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
-constexpr int STG_STRIDE = 33;                    // floats per staged row (conflict-free transpose)
-constexpr int STG_BYTES = 32 * STG_STRIDE * 4;    // per epilogue warp
+constexpr int EBUF_BYTES = 4096;                  // one [32 x 32] fp32 unit (bf16 units use half)
+constexpr int O2BUF_BYTES = 2048;                 // bf16 shadow of a unit
+constexpr int EPI_WARP_BYTES = 2 * EBUF_BYTES + O2BUF_BYTES;
 
 struct Segment {
   int kblocks;  // taps * cblk
@@ -49,7 +57,14 @@ struct Params {
   int Wout, Hout, Nimg;
   int N;  // logical accumulator columns
   int m_tiles, n_tiles;
-  Epilogue ep;
+  // epilogue
+  const float* bias;
+  const float* rowvec;
+  long long ld_rowvec;
+  int act;
+  int out_f32;
+  int has_res, res_f32;
+  int has_out2;
 };
 
 template <int BN>
@@ -57,196 +72,119 @@ struct Cfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
+  static constexpr int STAGES = (BN >= 256) ? 3 : (BN >= 128 ? 4 : 6);
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
-  static constexpr int BAR_BYTES = 256;  // (2*STAGES + 4) mbarriers + the TMEM base slot
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + EPI_WARPS * STG_BYTES + 1024;
-  static_assert((2 * STAGES + 4) * 8 + 4 <= BAR_BYTES, "barrier block too small");
+  static constexpr int EPI_OFF = STAGES * STAGE_BYTES;                 // 1024-aligned
+  static constexpr int BIAS_OFF = EPI_OFF + EPI_WARPS * EPI_WARP_BYTES;
+  static constexpr int BIAS_BYTES = 2 * BN * 4;                        // per accumulator stage
+  static constexpr int BAR_OFF = BIAS_OFF + BIAS_BYTES;
+  static constexpr int BAR_BYTES = 512;  // (2*STAGES + 4 + 2*EPI_WARPS) mbarriers + the TMEM base slot
+  static constexpr int SMEM_BYTES = BAR_OFF + BAR_BYTES;
+  static_assert((2 * STAGES + 4 + 2 * EPI_WARPS) * 8 + 4 <= BAR_BYTES, "barrier block too small");
   static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KiB dynamic shared memory limit");
+  static_assert(EPI_OFF % 1024 == 0 && EPI_WARP_BYTES % 1024 == 0 && BAR_OFF % 8 == 0, "alignment");
 };
 
-// ---- epilogue ----------------------------------------------------------------------------------------
-// tcgen05.ld hands every thread one accumulator ROW (32 consecutive columns).  Writing / reading
-// global memory in that layout makes each warp-level access touch 32 different 128-byte lines, which
-// is what bounded the small-K GEMMs of the transformer blocks (LSU wavefronts, not HBM).  The chunk is
-// therefore transposed through a per-warp shared-memory tile so that 8 lanes cover 32 consecutive
-// columns of one row: residual loads, output stores and the bf16 shadow stores are fully coalesced
-// (4 rows x 128 B per warp instruction), and the residual of the NEXT chunk is prefetched into
-// registers while the current one is processed (the first one before the accumulator is even ready).
-// GELU for the bf16 tensor-core path: erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, far below
-// bf16 resolution) -- ~3x fewer instructions than erff in the epilogue's critical path.  The fp32
-// parity path (conv_simt.cu) keeps the exact erff.
+// ---- shared-memory unit buffers ---------------------------------------------------------------------
+// A unit is 32 rows; fp32 rows are 128 B with the TMA 128-byte swizzle (16-byte chunk j of row r lives
+// at chunk j ^ (r & 7)), bf16 rows are 64 B with the 64-byte swizzle (chunk j ^ ((r >> 1) & 3)).  One
+// thread touches one row, so each quarter-warp phase covers 8 distinct 16-byte bank groups.
+__device__ __forceinline__ void lds_row_f32(const uint8_t* buf, int lane, float (&r)[32]) {
+  const uint8_t* row = buf + lane * 128;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 t = *reinterpret_cast<const float4*>(row + ((j ^ (lane & 7)) << 4));
+    r[4 * j] = t.x; r[4 * j + 1] = t.y; r[4 * j + 2] = t.z; r[4 * j + 3] = t.w;
+  }
+}
+__device__ __forceinline__ void sts_row_f32(uint8_t* buf, int lane, const float (&v)[32]) {
+  uint8_t* row = buf + lane * 128;
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    *reinterpret_cast<float4*>(row + ((j ^ (lane & 7)) << 4)) =
+        make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+}
+__device__ __forceinline__ uint32_t pack2_bf16(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ void lds_row_bf16(const uint8_t* buf, int lane, float (&r)[32]) {
+  const uint8_t* row = buf + lane * 64;
+  const int sw = (lane >> 1) & 3;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint4 u = *reinterpret_cast<const uint4*>(row + ((j ^ sw) << 4));
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      r[8 * j + 2 * e] = __uint_as_float(w[e] << 16);
+      r[8 * j + 2 * e + 1] = __uint_as_float(w[e] & 0xffff0000u);
+    }
+  }
+}
+// 8 consecutive bf16 (one 16-byte chunk `j` of row `lane`)
+__device__ __forceinline__ void sts_chunk_bf16(uint8_t* buf, int lane, int j, const float* v) {
+  uint4 u;
+  u.x = pack2_bf16(v[0], v[1]);
+  u.y = pack2_bf16(v[2], v[3]);
+  u.z = pack2_bf16(v[4], v[5]);
+  u.w = pack2_bf16(v[6], v[7]);
+  *reinterpret_cast<uint4*>(buf + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = u;
+}
+__device__ __forceinline__ void sts_row_bf16(uint8_t* buf, int lane, const float (&v)[32]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) sts_chunk_bf16(buf, lane, j, &v[8 * j]);
+}
+
+// exact-erf GELU for the bf16 tensor-core path: erf by Abramowitz-Stegun 7.1.28,
+//   erf(x) = 1 - (1 + a1 x + ... + a6 x^6)^-16,  |error| <= 3e-7 (1.7e-6 in fp32 arithmetic),
+// far below bf16 resolution; ONE MUFU (rcp) per element instead of erff's branches.  The fp32 parity
+// path (conv_simt.cu) keeps erff.
 __device__ __forceinline__ float gelu_fast(float v) {
   const float x = fabsf(v) * 0.70710678118654752440f;
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, x, 1.0f));
-  float poly = fmaf(1.061405429f, t, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  const float erf_abs = 1.0f - poly * t * __expf(-x * x);
-  const float erf_v = copysignf(erf_abs, v);
-  return 0.5f * v * (1.0f + erf_v);
-}
-
-struct RowSet {          // the 8 output rows this thread touches in the coalesced layout
-  long long row[8];
-  int img[8];
-  unsigned valid;        // bit i: row i exists
-};
-
-// rare paths (N not a multiple of 4 at the right edge) are kept out of line to keep the hot code small
-__device__ __noinline__ float4 ld_res4_edge(const Epilogue& ep, long long row, int col, int N) {
-  float t[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int e = 0; e < 4 && col + e < N; ++e)
-    t[e] = ep.res_f32 ? reinterpret_cast<const float*>(ep.residual)[row * ep.ld_res + col + e]
-                      : __bfloat162float(reinterpret_cast<const bf16*>(ep.residual)[row * ep.ld_res + col + e]);
-  return make_float4(t[0], t[1], t[2], t[3]);
-}
-
-__device__ __forceinline__ float4 ld_res4(const Epilogue& ep, long long row, int col, int N, bool ok) {
-  float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (!ok || col >= N) return r;
-  if (col + 4 > N) return ld_res4_edge(ep, row, col, N);
-  if (ep.res_f32) {
-    r = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(ep.residual) + row * ep.ld_res + col);
-  } else {
-    const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(ep.residual) +
-                                                    row * ep.ld_res + col);
-    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&u.x);
-    const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
-    r = make_float4(__low2float(a), __high2float(a), __low2float(b), __high2float(b));
-  }
-  return r;
-}
-
-__device__ __forceinline__ uint2 pack4_bf16(const float4& v) {
-  __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y);
-  __nv_bfloat162 b = __floats2bfloat162_rn(v.z, v.w);
-  uint2 u;
-  u.x = *reinterpret_cast<uint32_t*>(&a);
-  u.y = *reinterpret_cast<uint32_t*>(&b);
-  return u;
-}
-
-__device__ __noinline__ void st_out4_edge(const Epilogue& ep, long long row, int col, int N, float4 v) {
-  const float t[4] = {v.x, v.y, v.z, v.w};
-  for (int e = 0; e < 4 && col + e < N; ++e) {
-    if (ep.out_f32)
-      reinterpret_cast<float*>(ep.out)[row * ep.ld_out + col + e] = t[e];
-    else
-      reinterpret_cast<bf16*>(ep.out)[row * ep.ld_out + col + e] = __float2bfloat16_rn(t[e]);
-    if (ep.out2) reinterpret_cast<bf16*>(ep.out2)[row * ep.ld_out2 + col + e] = __float2bfloat16_rn(t[e]);
-  }
-}
-
-__device__ __forceinline__ void st_out4(const Epilogue& ep, long long row, int col, int N, const float4& v) {
-  if (col + 4 > N) {
-    st_out4_edge(ep, row, col, N, v);
-    return;
-  }
-  if (ep.out_f32)
-    *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + row * ep.ld_out + col) = v;
-  else
-    *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(ep.out) + row * ep.ld_out + col) = pack4_bf16(v);
-  if (ep.out2)
-    *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(ep.out2) + row * ep.ld_out2 + col) = pack4_bf16(v);
-}
-
-// 4 consecutive fp32 of a per-column vector (bias / per-image row vector), bounds-safe
-__device__ __noinline__ float4 ld_vec4_edge(const float* p, int col, int N) {
-  float t[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int e = 0; e < 4 && col + e < N; ++e) t[e] = __ldg(p + col + e);
-  return make_float4(t[0], t[1], t[2], t[3]);
-}
-__device__ __forceinline__ float4 ld_vec4(const float* p, int col, int N) {
-  if (p == nullptr || col >= N) return make_float4(0.f, 0.f, 0.f, 0.f);
-  if (col + 4 <= N) return __ldg(reinterpret_cast<const float4*>(p + col));
-  return ld_vec4_edge(p, col, N);
-}
-
-// `b4` = bias (+ the per-image row vector when all rows of the warp belong to one image: rv_uniform)
-__device__ __forceinline__ void epilogue_chunk(const uint32_t (&acc)[32], float* stg, int lane,
-                                               const Epilogue& ep, const RowSet& rs, const float4 (&res)[8],
-                                               const float4& b4, bool rv_uniform, int col0, int N) {
-#pragma unroll
-  for (int j = 0; j < 32; ++j) stg[lane * STG_STRIDE + j] = __uint_as_float(acc[j]);
-  __syncwarp();
-  const int cc = (lane & 7) * 4;
-  const int col = col0 + cc;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int rr = i * 4 + (lane >> 3);
-    const float* sp = stg + rr * STG_STRIDE + cc;
-    float4 v = make_float4(sp[0] + b4.x, sp[1] + b4.y, sp[2] + b4.z, sp[3] + b4.w);
-    if (((rs.valid >> i) & 1u) && col < N) {
-      if (ep.rowvec && !rv_uniform) {
-        const float4 r4 = ld_vec4(ep.rowvec + static_cast<long long>(rs.img[i]) * ep.ld_rowvec, col, N);
-        v.x += r4.x; v.y += r4.y; v.z += r4.z; v.w += r4.w;
-      }
-      if (ep.act == EALDM_ACT_SILU) {
-        v.x = silu_f(v.x); v.y = silu_f(v.y); v.z = silu_f(v.z); v.w = silu_f(v.w);
-      }
-      v.x += res[i].x; v.y += res[i].y; v.z += res[i].z; v.w += res[i].w;
-      st_out4(ep, rs.row[i], col, N, v);
-    }
-  }
-  __syncwarp();
-}
-
-// GEGLU chunk: columns [0,16) are values, [16,32) their gates -> 16 output columns at col0/2.
-// The raw accumulators are staged, then 4 lanes x 4 columns finish one row: bias pairs `bv`/`bg`
-// (prefetched per tile) stay in registers.
-__device__ __forceinline__ void epilogue_chunk_geglu(const uint32_t (&acc)[32], float* stg, int lane,
-                                                     const Epilogue& ep, const long long (&row4)[4],
-                                                     unsigned valid4, const float4& bv, const float4& bg,
-                                                     int col0) {
-#pragma unroll
-  for (int j = 0; j < 32; ++j) stg[lane * STG_STRIDE + j] = __uint_as_float(acc[j]);
-  __syncwarp();
-  const int c4 = (lane & 3) * 4;
-  const int oc = (col0 >> 1) + c4;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int rr = i * 8 + (lane >> 2);
-    const float* sp = stg + rr * STG_STRIDE + c4;
-    float4 v;
-    v.x = (sp[0] + bv.x) * gelu_fast(sp[16] + bg.x);
-    v.y = (sp[1] + bv.y) * gelu_fast(sp[17] + bg.y);
-    v.z = (sp[2] + bv.z) * gelu_fast(sp[18] + bg.z);
-    v.w = (sp[3] + bv.w) * gelu_fast(sp[19] + bg.w);
-    if ((valid4 >> i) & 1u) {
-      if (ep.residual) {
-        const float4 r4 = ld_res4(ep, row4[i], oc, 1 << 30, true);
-        v.x += r4.x; v.y += r4.y; v.z += r4.z; v.w += r4.w;
-      }
-      st_out4(ep, row4[i], oc, 1 << 30, v);
-    }
-  }
-  __syncwarp();
+  float p = fmaf(0.0000430638f, x, 0.0002765672f);
+  p = fmaf(p, x, 0.0001520143f);
+  p = fmaf(p, x, 0.0092705272f);
+  p = fmaf(p, x, 0.0422820123f);
+  p = fmaf(p, x, 0.0705230784f);
+  p = fmaf(p, x, 1.0f);
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(p));
+  r *= r; r *= r; r *= r; r *= r;
+  const float erf_v = copysignf(1.0f - r, v);
+  const float hv = 0.5f * v;
+  return fmaf(hv, erf_v, hv);
 }
 
 template <int BN, bool GEGLU>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-               const __grid_constant__ CUtensorMap tmB, const __grid_constant__ Params p) {
+               const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
+               const __grid_constant__ CUtensorMap tmOut2, const __grid_constant__ CUtensorMap tmRes,
+               const __grid_constant__ Params p) {
   using C = Cfg<BN>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::BAR_OFF);
   uint64_t* empty_bar = full_bar + C::STAGES;
   uint64_t* tmem_full = empty_bar + C::STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  uint8_t* stg_base = smem + C::STAGES * C::STAGE_BYTES + C::BAR_BYTES;
+  uint64_t* res_bar = tmem_empty + 2;  // [EPI_WARPS][2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 2 * EPI_WARPS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
+    if ((ptx::smem_u32(smem) & 1023u) != 0) {
+      printf("ealdm: dynamic shared memory base is not 1024-byte aligned\n");
+      __trap();
+    }
     ptx::prefetch_tensormap(&tmA0);
     if (p.nseg > 1) ptx::prefetch_tensormap(&tmA1);
     ptx::prefetch_tensormap(&tmB);
+    ptx::prefetch_tensormap(&tmOut);
+    if (p.has_out2) ptx::prefetch_tensormap(&tmOut2);
+    if (p.has_res) ptx::prefetch_tensormap(&tmRes);
     for (int s = 0; s < C::STAGES; ++s) {
       ptx::mbar_init(&full_bar[s], 1);
       ptx::mbar_init(&empty_bar[s], 1);
@@ -255,6 +193,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       ptx::mbar_init(&tmem_full[a], 1);
       ptx::mbar_init(&tmem_empty[a], EPI_WARPS);
     }
+    for (int a = 0; a < 2 * EPI_WARPS; ++a) ptx::mbar_init(&res_bar[a], 1);
     ptx::fence_mbar_init();
   }
   if (warp == 1) {
@@ -334,120 +273,153 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     }
   } else {
     // ===================== epilogue (warps 2..9) =====================
-    const int quad = warp & 3;             // TMEM lane quadrant this warp may read
-    const int part = (warp - 2) >> 2;      // 0: even 32-column chunks, 1: odd chunks
-    float* stg = reinterpret_cast<float*>(stg_base + (warp - 2) * STG_BYTES);
-    const bool has_res = p.ep.residual != nullptr;
-    constexpr int NCH = (BN + 63) / 64;    // chunks per epilogue warp
-    const int cc = (lane & 7) * 4;
+    const int ew = warp - 2;
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may read
+    const int part = ew >> 2;   // 0: even units, 1: odd units
+    const int etid = threadIdx.x - 64;
+    uint8_t* ebuf = smem + C::EPI_OFF + ew * EPI_WARP_BYTES;
+    uint8_t* o2buf = ebuf + 2 * EBUF_BYTES;
+    float* bias_s = reinterpret_cast<float*>(smem + C::BIAS_OFF);
+    uint64_t* rbar = res_bar + 2 * ew;
+    // a unit: 32 accumulator columns (GEGLU: 64 -> 32 output columns)
+    constexpr int UNITS = GEGLU ? BN / 64 : BN / 32;
+    constexpr int OUT_PER_TILE = GEGLU ? BN / 2 : BN;
+    // this warp's 32 rows inside the (bw, bh, bn) output box of the tile
+    const int r0 = quad * 32;
+    const int sw0 = r0 % p.bw, sh0 = (r0 / p.bw) % p.bh, sn0 = r0 / (p.bw * p.bh);
+    const int my_dn = (r0 + lane) / (p.bw * p.bh);
+    const uint32_t res_bytes = p.res_f32 ? 4096u : 2048u;
+
+    auto unit_origin = [&](int tile, int& nt, int& w, int& h, int& n) {
+      const int mt = tile / p.n_tiles;
+      nt = tile - mt * p.n_tiles;
+      w = (mt % p.tiles_w) * p.bw + sw0;
+      h = ((mt / p.tiles_w) % p.tiles_h) * p.bh + sh0;
+      n = (mt / (p.tiles_w * p.tiles_h)) * p.bn + sn0;
+    };
+    auto issue_res = [&](int tile, int ku, int b) {  // lane 0 only
+      int nt, w, h, n;
+      unit_origin(tile, nt, w, h, n);
+      ptx::mbar_arrive_expect_tx(&rbar[b], res_bytes);
+      ptx::tma_load_4d(ebuf + b * EBUF_BYTES, &tmRes, &rbar[b], nt * OUT_PER_TILE + ku * 32, w, h, n);
+    };
+
+    uint32_t it = 0;  // units processed by this warp: buffer = it & 1, mbarrier parity = (it >> 1) & 1
+    if (!GEGLU && p.has_res && lane == 0 && part < UNITS && static_cast<int>(blockIdx.x) < total_tiles)
+      issue_res(blockIdx.x, part, 0);
+
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int mt = tile / p.n_tiles;
-      const int nt = tile - mt * p.n_tiles;
-      const int tw = mt % p.tiles_w;
-      const int th = (mt / p.tiles_w) % p.tiles_h;
-      const int tn = mt / (p.tiles_w * p.tiles_h);
-      auto decode = [&](int r, long long& row, int& img) -> bool {
-        const int w = tw * p.bw + r % p.bw;
-        const int h = th * p.bh + (r / p.bw) % p.bh;
-        const int n = tn * p.bn + r / (p.bw * p.bh);
-        row = (static_cast<long long>(n) * p.Hout + h) * p.Wout + w;
-        img = n;
-        return (w < p.Wout) && (h < p.Hout) && (n < p.Nimg);
-      };
+      int nt, w, h, n;
+      unit_origin(tile, nt, w, h, n);
+      // bias of this tile's BN columns -> shared memory (one value per epilogue thread)
+      if (etid < BN) {
+        const int col = nt * BN + etid;
+        bias_s[acc * BN + etid] = (p.bias != nullptr && col < p.N) ? __ldg(p.bias + col) : 0.f;
+      }
+      ptx::named_bar_sync(1, 32 * EPI_WARPS);
+      const float* bs = bias_s + acc * BN;
+      const float* rv = nullptr;
+      if (!GEGLU && p.rowvec != nullptr) {
+        int img = (n - sn0) + my_dn;
+        if (img >= p.Nimg) img = p.Nimg - 1;
+        rv = p.rowvec + static_cast<long long>(img) * p.ld_rowvec + nt * BN;
+      }
       const uint32_t taddr0 =
           tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * BN);
+      ptx::mbar_wait(&tmem_full[acc], acc_phase);
+      ptx::tc_fence_after();
 
-      if constexpr (GEGLU) {
-        long long row4[4];
-        unsigned valid4 = 0;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          int img;
-          if (decode(quad * 32 + i * 8 + (lane >> 2), row4[i], img)) valid4 |= 1u << i;
-        }
-        // (value, gate) bias pair of the first chunk, fetched before the accumulator is ready;
-        // the next chunk's pair is prefetched while the current chunk is processed
-        const int c4 = (lane & 3) * 4;
-        float4 bv_n = ld_vec4(p.ep.bias, nt * BN + part * 32 + c4, p.N);
-        float4 bg_n = ld_vec4(p.ep.bias, nt * BN + part * 32 + 16 + c4, p.N);
-        ptx::mbar_wait(&tmem_full[acc], acc_phase);
-        ptx::tc_fence_after();
 #pragma unroll 1
-        for (int ch = part; ch < BN / 32; ch += 2) {
-          uint32_t v[32];
-          ptx::tmem_ld_32x32(taddr0 + ch * 32, v);
-          const float4 bv = bv_n, bg = bg_n;
-          const int col0 = nt * BN + ch * 32;
-          if (ch + 2 < BN / 32) {
-            bv_n = ld_vec4(p.ep.bias, col0 + 64 + c4, p.N);
-            bg_n = ld_vec4(p.ep.bias, col0 + 64 + 16 + c4, p.N);
+      for (int ku = part; ku < UNITS; ku += 2) {
+        const int b = it & 1;
+        uint8_t* eb = ebuf + b * EBUF_BYTES;
+        if constexpr (GEGLU) {
+          if (lane == 0) ptx::bulk_wait_read<0>();
+          __syncwarp();
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            const int ch = 2 * ku + half;
+            uint32_t v[32];
+            ptx::tmem_ld_32x32(taddr0 + ch * 32, v);
+            float bv[16], bg[16];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 t = *reinterpret_cast<const float4*>(bs + ch * 32 + 4 * j);
+              bv[4 * j] = t.x; bv[4 * j + 1] = t.y; bv[4 * j + 2] = t.z; bv[4 * j + 3] = t.w;
+              const float4 g = *reinterpret_cast<const float4*>(bs + ch * 32 + 16 + 4 * j);
+              bg[4 * j] = g.x; bg[4 * j + 1] = g.y; bg[4 * j + 2] = g.z; bg[4 * j + 3] = g.w;
+            }
+            ptx::tmem_ld_wait();
+            float o[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              o[j] = (__uint_as_float(v[j]) + bv[j]) * gelu_fast(__uint_as_float(v[16 + j]) + bg[j]);
+            sts_chunk_bf16(eb, lane, 2 * half, &o[0]);
+            sts_chunk_bf16(eb, lane, 2 * half + 1, &o[8]);
           }
-          ptx::tmem_ld_wait();
-          if (col0 < p.N) epilogue_chunk_geglu(v, stg, lane, p.ep, row4, valid4, bv, bg, col0);
-        }
-      } else {
-        RowSet rs;
-        rs.valid = 0;
+        } else {
+          float r[32];
+          if (p.has_res) {
+            ptx::mbar_wait(&rbar[b], (it >> 1) & 1u);
+            if (p.res_f32) lds_row_f32(eb, lane, r);
+            else lds_row_bf16(eb, lane, r);
+          } else {
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          if (decode(quad * 32 + i * 4 + (lane >> 3), rs.row[i], rs.img[i])) rs.valid |= 1u << i;
-        // bias (+ per-image row vector when this thread's rows share one image) and residual of the
-        // FIRST chunk are fetched before the accumulator is ready; those of the next chunk while the
-        // current one is processed: no global-load latency between tcgen05.ld and the stores
-        bool rv_uniform = false;
-        const float* rv0 = nullptr;
-        if (p.ep.rowvec) {
-          rv_uniform = true;
-          int img0 = 0;
-          bool first = true;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            if ((rs.valid >> i) & 1u) {
-              if (first) { img0 = rs.img[i]; first = false; }
-              else if (rs.img[i] != img0) rv_uniform = false;
+            for (int j = 0; j < 32; ++j) r[j] = 0.f;
+          }
+          if (lane == 0) {
+            // the other unit buffer and the shadow buffer are free once their stores have read them
+            ptx::bulk_wait_read<0>();
+            if (p.has_res) {
+              if (ku + 2 < UNITS) issue_res(tile, ku + 2, b ^ 1);
+              else if (tile + static_cast<int>(gridDim.x) < total_tiles) issue_res(tile + gridDim.x, part, b ^ 1);
             }
           }
-          if (rv_uniform) rv0 = p.ep.rowvec + static_cast<long long>(img0) * p.ep.ld_rowvec;
-        }
-        auto load_bias = [&](int c0) -> float4 {
-          float4 b = ld_vec4(p.ep.bias, c0, p.N);
-          const float4 r4 = ld_vec4(rv0, c0, p.N);
-          b.x += r4.x; b.y += r4.y; b.z += r4.z; b.w += r4.w;
-          return b;
-        };
-        float4 b_n = load_bias(nt * BN + part * 32 + cc);
-        float4 rnext[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) rnext[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (has_res) {
-          const int c0 = nt * BN + part * 32 + cc;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) rnext[i] = ld_res4(p.ep, rs.row[i], c0, p.N, (rs.valid >> i) & 1u);
-        }
-        ptx::mbar_wait(&tmem_full[acc], acc_phase);
-        ptx::tc_fence_after();
-#pragma unroll 1
-        for (int ch = part; ch < BN / 32; ch += 2) {
+          __syncwarp();
           uint32_t v[32];
-          ptx::tmem_ld_32x32(taddr0 + ch * 32, v);
-          float4 rcur[8];
+          ptx::tmem_ld_32x32(taddr0 + ku * 32, v);
+          if (p.act == EALDM_ACT_NONE) {  // bias (+ per-image row vector) folded into r while the load flies
 #pragma unroll
-          for (int i = 0; i < 8; ++i) rcur[i] = rnext[i];
-          const float4 b4 = b_n;
-          const int col0 = nt * BN + ch * 32;
-          if (ch + 2 < BN / 32) {
-            b_n = load_bias(col0 + 64 + cc);
-            if (has_res) {
+            for (int j = 0; j < 8; ++j) {
+              const float4 t = *reinterpret_cast<const float4*>(bs + ku * 32 + 4 * j);
+              r[4 * j] += t.x; r[4 * j + 1] += t.y; r[4 * j + 2] += t.z; r[4 * j + 3] += t.w;
+            }
+            if (rv != nullptr) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i)
-                rnext[i] = ld_res4(p.ep, rs.row[i], col0 + 64 + cc, p.N, (rs.valid >> i) & 1u);
+              for (int j = 0; j < 8; ++j) {
+                if (nt * BN + ku * 32 + 4 * j < p.N) {
+                  const float4 t = __ldg(reinterpret_cast<const float4*>(rv + ku * 32 + 4 * j));
+                  r[4 * j] += t.x; r[4 * j + 1] += t.y; r[4 * j + 2] += t.z; r[4 * j + 3] += t.w;
+                }
+              }
+            }
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) r[j] += __uint_as_float(v[j]);
+          } else {  // SiLU (time-embedding MLP): act(acc + bias + rowvec) + residual
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float f = __uint_as_float(v[j]) + bs[ku * 32 + j];
+              if (rv != nullptr && nt * BN + ku * 32 + j < p.N) f += __ldg(rv + ku * 32 + j);
+              r[j] += silu_f(f);
             }
           }
-          ptx::tmem_ld_wait();
-          if (col0 < p.N) epilogue_chunk(v, stg, lane, p.ep, rs, rcur, b4, rv_uniform, col0, p.N);
+          if (p.out_f32) sts_row_f32(eb, lane, r);
+          else sts_row_bf16(eb, lane, r);
+          if (p.has_out2) sts_row_bf16(o2buf, lane, r);
         }
+        ptx::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          const int c0 = nt * OUT_PER_TILE + ku * 32;
+          ptx::tma_store_4d(&tmOut, eb, c0, w, h, n);
+          if (!GEGLU && p.has_out2) ptx::tma_store_4d(&tmOut2, o2buf, c0, w, h, n);
+          ptx::bulk_commit();
+        }
+        ++it;
       }
       ptx::tc_fence_before();
       __syncwarp();
@@ -455,6 +427,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
+    if (lane == 0) ptx::bulk_wait_read<0>();  // shared memory must outlive the last TMA stores
   }
 
   ptx::tc_fence_before();
@@ -497,8 +470,7 @@ static int pow2_ceil(long long v) {
 }
 
 template <int BN, bool GEGLU>
-static int launch_bn(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
-                     const Params& p, cudaStream_t st) {
+static int launch_bn(const CUtensorMap* tm, const Params& p, cudaStream_t st) {
   using C = Cfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -508,9 +480,13 @@ static int launch_bn(const CUtensorMap& a0, const CUtensorMap& a1, const CUtenso
   }
   const int total = p.m_tiles * p.n_tiles;
   const int grid = total < num_sms() ? total : num_sms();
-  conv_tc_kernel<BN, GEGLU><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(a0, a1, b, p);
+  conv_tc_kernel<BN, GEGLU><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], p);
   EALDM_LAUNCH_CHECK();
   return 0;
+}
+
+static bool aligned_2d(const void* ptr, long long ld, int elem_bytes) {
+  return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (ld * elem_bytes) % 16 == 0;
 }
 
 // returns 1 if the tcgen05 path can run this problem
@@ -519,26 +495,44 @@ bool supported(const ealdm_conv_args* a) {
   if (a->n_src < 1 || a->n_src > 2) return false;
   for (int s = 0; s < a->n_src; ++s) {
     const ealdm_conv_src& x = a->src[s];
-    if (x.c % BK != 0 || x.ld % 8 != 0) return false;
-    if ((reinterpret_cast<uintptr_t>(x.x) & 15) != 0) return false;
+    if (x.c % BK != 0 || !aligned_2d(x.x, x.ld, 2)) return false;
     if (x.upsample) return false;
     if (x.ksize != 1 && x.ksize != 3) return false;
     if (x.stride != 1 && x.stride != 2) return false;
     if (x.n != a->src[0].n) return false;
   }
-  if (a->k_total % 8 != 0) return false;
-  if ((reinterpret_cast<uintptr_t>(a->weight) & 15) != 0) return false;
-  if ((reinterpret_cast<uintptr_t>(a->out) & 15) != 0 || a->ld_out % 8 != 0) return false;
-  if (a->residual && ((reinterpret_cast<uintptr_t>(a->residual) & 15) != 0 || a->ld_res % 8 != 0))
+  if (!aligned_2d(a->weight, a->k_total, 2)) return false;
+  if (!aligned_2d(a->out, a->ld_out, a->out_f32 ? 4 : 2)) return false;
+  if (a->residual && !aligned_2d(a->residual, a->ld_res, a->res_f32 ? 4 : 2)) return false;
+  if (a->out2 && !aligned_2d(a->out2, a->ld_out2, 2)) return false;
+  if (a->rowvec && ((reinterpret_cast<uintptr_t>(a->rowvec) & 15) != 0 || a->ld_rowvec % 4 != 0 ||
+                    a->n_out % 4 != 0))
     return false;
-  if (a->act == EALDM_ACT_GEGLU && (a->rowvec || a->out2)) return false;
-  if (a->out2 && ((reinterpret_cast<uintptr_t>(a->out2) & 15) != 0 || a->ld_out2 % 8 != 0)) return false;
-  if (a->act == EALDM_ACT_GEGLU && a->n_out % 32 != 0) return false;
+  if (a->act == EALDM_ACT_GEGLU && (a->rowvec || a->out2 || a->residual || a->n_out % 32 != 0)) return false;
   return true;
 }
 
+// 4-D (C, W, H, N) tensor map over an NHWC output-space tensor with a [32 columns x 32 rows] box
+static int encode_unit_map(PFN_cuTensorMapEncodeTiled_v12000 encode, CUtensorMap* tm, const void* base,
+                           bool f32, long long cols, long long ld, const ealdm_conv_args* a, const int (&sub)[3]) {
+  const cuuint64_t es = f32 ? 4 : 2;
+  cuuint64_t gdim[4] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(a->w_out),
+                        static_cast<cuuint64_t>(a->h_out), static_cast<cuuint64_t>(a->src[0].n)};
+  cuuint64_t gstr[3] = {static_cast<cuuint64_t>(ld) * es, static_cast<cuuint64_t>(ld) * es * gdim[1],
+                        static_cast<cuuint64_t>(ld) * es * gdim[1] * gdim[2]};
+  cuuint32_t box[4] = {32, static_cast<cuuint32_t>(sub[0]), static_cast<cuuint32_t>(sub[1]),
+                       static_cast<cuuint32_t>(sub[2])};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = encode(tm, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
+                      const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(EALDM_ECUDA, "cuTensorMapEncodeTiled(epilogue) failed: %d", (int)r);
+  return 0;
+}
+
 int launch(const ealdm_conv_args* a, cudaStream_t st) {
-  EALDM_REQUIRE(supported(a), "tcgen05 conv: unsupported shape/alignment (c%%64, ld%%8, 16 B pointers)");
+  EALDM_REQUIRE(supported(a), "tcgen05 conv: unsupported shape/alignment (c%%64, 16-byte rows and pointers)");
   PFN_cuTensorMapEncodeTiled_v12000 encode = get_encode();
   if (!encode) return set_error(EALDM_ECUDA, "cuTensorMapEncodeTiled entry point not available");
 
@@ -555,10 +549,16 @@ int launch(const ealdm_conv_args* a, cudaStream_t st) {
   p.tiles_w = static_cast<int>(ceil_div(a->w_out, p.bw));
   p.tiles_h = static_cast<int>(ceil_div(a->h_out, p.bh));
   p.m_tiles = p.tiles_w * p.tiles_h * static_cast<int>(ceil_div(p.Nimg, p.bn));
+  // the 32 rows of one epilogue warp form a (sub_w, sub_h, sub_n) sub-box of the tile
+  int sub[3];
+  sub[0] = p.bw < 32 ? p.bw : 32;
+  sub[1] = p.bh < 32 / sub[0] ? p.bh : 32 / sub[0];
+  sub[2] = 32 / (sub[0] * sub[1]);
 
   // choose the N tile: fewest (waves x tile cost)
+  const bool geglu = a->act == EALDM_ACT_GEGLU;
   int BN;
-  if (a->n_out <= 32 && a->act != EALDM_ACT_GEGLU) {
+  if (a->n_out <= 32 && !geglu) {
     BN = 32;
   } else if (a->n_out <= 128) {
     BN = 128;
@@ -571,8 +571,8 @@ int launch(const ealdm_conv_args* a, cudaStream_t st) {
   }
   p.n_tiles = static_cast<int>(ceil_div(a->n_out, BN));
 
-  CUtensorMap tmA[2], tmB;
-  memset(tmA, 0, sizeof(tmA));
+  CUtensorMap tm[6];  // A0, A1, W, out, out2, residual
+  memset(tm, 0, sizeof(tm));
   int koff = 0;
   for (int s = 0; s < a->n_src; ++s) {
     const ealdm_conv_src& x = a->src[s];
@@ -594,7 +594,7 @@ int launch(const ealdm_conv_args* a, cudaStream_t st) {
                          static_cast<cuuint32_t>(p.bh * x.stride), static_cast<cuuint32_t>(p.bn)};
     cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(x.stride), static_cast<cuuint32_t>(x.stride),
                           1};
-    CUresult r = encode(&tmA[s], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x.x), gdim,
+    CUresult r = encode(&tm[s], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x.x), gdim,
                         gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS)
@@ -602,43 +602,43 @@ int launch(const ealdm_conv_args* a, cudaStream_t st) {
   }
   EALDM_REQUIRE(koff == a->k_total, "k_total %lld does not match the sources (%d)",
                 (long long)a->k_total, koff);
-  if (a->n_src == 1) tmA[1] = tmA[0];
+  if (a->n_src == 1) tm[1] = tm[0];
   {
     cuuint64_t gdim[2] = {static_cast<cuuint64_t>(a->k_total), static_cast<cuuint64_t>(a->n_out)};
     cuuint64_t gstr[1] = {static_cast<cuuint64_t>(a->k_total) * 2};
     cuuint32_t box[2] = {BK, static_cast<cuuint32_t>(BN)};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(a->weight),
+    CUresult r = encode(&tm[2], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(a->weight),
                         gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS)
       return set_error(EALDM_ECUDA, "cuTensorMapEncodeTiled(W) failed: %d", (int)r);
   }
+  const long long out_cols = geglu ? a->n_out / 2 : a->n_out;
+  if (int e = encode_unit_map(encode, &tm[3], a->out, a->out_f32 != 0, out_cols, a->ld_out, a, sub)) return e;
+  tm[4] = tm[3];
+  tm[5] = tm[3];
+  if (a->out2)
+    if (int e = encode_unit_map(encode, &tm[4], a->out2, false, out_cols, a->ld_out2, a, sub)) return e;
+  if (a->residual)
+    if (int e = encode_unit_map(encode, &tm[5], a->residual, a->res_f32 != 0, out_cols, a->ld_res, a, sub)) return e;
 
-  p.ep.bias = a->bias;
-  p.ep.rowvec = a->rowvec;
-  p.ep.ld_rowvec = a->ld_rowvec;
-  p.ep.rows_per_image = a->h_out * a->w_out;
-  p.ep.residual = a->residual;
-  p.ep.ld_res = a->ld_res;
-  p.ep.out = a->out;
-  p.ep.ld_out = a->ld_out;
-  p.ep.act = a->act;
-  p.ep.out_f32 = a->out_f32;
-  p.ep.res_f32 = a->res_f32;
-  p.ep.out2 = a->out2;
-  p.ep.ld_out2 = a->ld_out2;
+  p.bias = a->bias;
+  p.rowvec = a->rowvec;
+  p.ld_rowvec = a->ld_rowvec;
+  p.act = a->act;
+  p.out_f32 = a->out_f32;
+  p.has_res = a->residual != nullptr;
+  p.res_f32 = a->res_f32;
+  p.has_out2 = a->out2 != nullptr;
 
-  const bool geglu = a->act == EALDM_ACT_GEGLU;
   switch (BN) {
-    case 32: return launch_bn<32, false>(tmA[0], tmA[1], tmB, p, st);
+    case 32: return launch_bn<32, false>(tm, p, st);
     case 128:
-      return geglu ? launch_bn<128, true>(tmA[0], tmA[1], tmB, p, st)
-                   : launch_bn<128, false>(tmA[0], tmA[1], tmB, p, st);
+      return geglu ? launch_bn<128, true>(tm, p, st) : launch_bn<128, false>(tm, p, st);
     default:
-      return geglu ? launch_bn<256, true>(tmA[0], tmA[1], tmB, p, st)
-                   : launch_bn<256, false>(tmA[0], tmA[1], tmB, p, st);
+      return geglu ? launch_bn<256, true>(tm, p, st) : launch_bn<256, false>(tm, p, st);
   }
 }
 
