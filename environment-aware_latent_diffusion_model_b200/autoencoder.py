@@ -317,7 +317,7 @@ class AutoencoderEngine:
 
     def _res(self, d, x: Dual) -> Dual:
         n, h, w = x.f.n, x.f.h, x.f.w
-        h1 = self._new(n, h, w, d["cout"], torch.float32)
+        h1 = self._new(n, h, w, d["cout"], torch.float32)   # bf16 here costs the encoder its 1e-2 bound (measured 1.03e-2)
         ops.conv([ConvIn(self._gn(x.f, d["gn1"], True), 3, 1, 1)], d["conv1"][0], h1, bias=d["conv1"][1])
         hn2 = self._gn(h1, d["gn2"], True)
         out = self._new_dual(n, h, w, d["cout"])

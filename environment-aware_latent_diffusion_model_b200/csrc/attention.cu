@@ -190,6 +190,132 @@ smallkv_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __rest
   }
 }
 
+// ---- cross-attention on a handful of context tokens, bf16, head_dim 32: HBM-bound --------------------
+// Q and the output are streamed exactly once with fully coalesced 16-byte accesses: consecutive threads
+// own consecutive 16-byte chunks (8 channels) of the token row, so 4 neighbouring lanes share one
+// (token, head) and combine their partial dot products with two shuffles.  A thread keeps the SAME
+// chunk position for all the rows it visits, so its slice of K and V (n_kv x 8 channels each) is
+// loaded once into registers and reused for every row.
+constexpr int XKV_MAX = 4;       // context tokens (register-resident K / V slices)
+constexpr int XKV_THREADS = 256;
+constexpr int XKV_ROWS = 8;      // rows per thread, all loads in flight before the first use
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    f[2 * e] = __uint_as_float(w[e] << 16);
+    f[2 * e + 1] = __uint_as_float(w[e] & 0xffff0000u);
+  }
+}
+
+template <int NKV>
+__global__ void __launch_bounds__(XKV_THREADS)
+xattn_bf16_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const bf16* __restrict__ v,
+                  long long ld_q, long long ld_kv, int c, int n_q, float scale_log2,
+                  bf16* __restrict__ out, long long ld_out) {
+  const int b = blockIdx.y;
+  const int cpr = c >> 3;                      // 16-byte chunks per token row; divides XKV_THREADS
+  const int cc = threadIdx.x % cpr;            // this thread's chunk position
+  const int rstep = XKV_THREADS / cpr;         // rows covered by one pass of the CTA
+  const int row0 = blockIdx.x * (rstep * XKV_ROWS) + threadIdx.x / cpr;
+  const bf16* qb = q + static_cast<long long>(b) * n_q * ld_q + cc * 8;
+  bf16* ob = out + static_cast<long long>(b) * n_q * ld_out + cc * 8;
+  uint4 qv[XKV_ROWS];
+#pragma unroll
+  for (int u = 0; u < XKV_ROWS; ++u) {
+    const int row = row0 + u * rstep;
+    qv[u] = row < n_q ? __ldg(reinterpret_cast<const uint4*>(qb + static_cast<long long>(row) * ld_q))
+                      : make_uint4(0, 0, 0, 0);
+  }
+  float kf[NKV][8], vf[NKV][8];
+  {
+    const bf16* kb = k + static_cast<long long>(b) * NKV * ld_kv + cc * 8;
+    const bf16* vb = v + static_cast<long long>(b) * NKV * ld_kv + cc * 8;
+#pragma unroll
+    for (int j = 0; j < NKV; ++j) {
+      unpack8(__ldg(reinterpret_cast<const uint4*>(kb + static_cast<long long>(j) * ld_kv)), kf[j]);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(vb + static_cast<long long>(j) * ld_kv)), vf[j]);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) kf[j][e] *= scale_log2;   // fold softmax scale and log2(e) into K
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < XKV_ROWS; ++u) {
+    float qf[8];
+    unpack8(qv[u], qf);
+    float s[NKV];
+#pragma unroll
+    for (int j = 0; j < NKV; ++j) {
+      float acc = qf[0] * kf[j][0];
+#pragma unroll
+      for (int e = 1; e < 8; ++e) acc = fmaf(qf[e], kf[j][e], acc);
+      // the 4 lanes holding the 32 channels of this (token, head)
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      s[j] = acc;
+    }
+    float m = s[0];
+#pragma unroll
+    for (int j = 1; j < NKV; ++j) m = fmaxf(m, s[j]);
+    float l = 0.f;
+#pragma unroll
+    for (int j = 0; j < NKV; ++j) { s[j] = exp2f(s[j] - m); l += s[j]; }
+    const float inv = __fdividef(1.0f, l);
+    float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < NKV; ++j) {
+      const float pj = s[j] * inv;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = fmaf(pj, vf[j][e], o[e]);
+    }
+    const int row = row0 + u * rstep;
+    if (row < n_q) {
+      uint4 w;
+      __nv_bfloat162 t;
+      t = __floats2bfloat162_rn(o[0], o[1]); w.x = *reinterpret_cast<uint32_t*>(&t);
+      t = __floats2bfloat162_rn(o[2], o[3]); w.y = *reinterpret_cast<uint32_t*>(&t);
+      t = __floats2bfloat162_rn(o[4], o[5]); w.z = *reinterpret_cast<uint32_t*>(&t);
+      t = __floats2bfloat162_rn(o[6], o[7]); w.w = *reinterpret_cast<uint32_t*>(&t);
+      *reinterpret_cast<uint4*>(ob + static_cast<long long>(row) * ld_out) = w;
+    }
+  }
+}
+
+// usable when heads are packed (head h = columns [32h, 32h+32)), rows are 16-byte aligned and the
+// chunks of a row tile the CTA evenly
+static bool xattn_bf16_ok(const ealdm_attention_args* a) {
+  const long long cpr = a->heads * 4;
+  return a->dtype == EALDM_BF16 && a->head_dim == 32 && a->n_kv <= XKV_MAX && a->head_stride_q == 32 &&
+         a->head_stride_kv == 32 && a->ld_q % 8 == 0 && a->ld_kv % 8 == 0 && a->ld_out % 8 == 0 &&
+         ((reinterpret_cast<uintptr_t>(a->q) | reinterpret_cast<uintptr_t>(a->k) |
+           reinterpret_cast<uintptr_t>(a->v) | reinterpret_cast<uintptr_t>(a->out)) & 15) == 0 &&
+         cpr <= XKV_THREADS && XKV_THREADS % cpr == 0;
+}
+
+static int launch_xattn_bf16(const ealdm_attention_args* a, cudaStream_t st) {
+  const int c = static_cast<int>(a->heads * 32);
+  const int rows_per_cta = XKV_THREADS / (c / 8) * XKV_ROWS;
+  dim3 grid(static_cast<unsigned>(ceil_div(a->n_q, rows_per_cta)), static_cast<unsigned>(a->batch));
+  const float sl2 = a->scale * 1.4426950408889634f;
+  const bf16* q = reinterpret_cast<const bf16*>(a->q);
+  const bf16* k = reinterpret_cast<const bf16*>(a->k);
+  const bf16* v = reinterpret_cast<const bf16*>(a->v);
+  bf16* o = reinterpret_cast<bf16*>(a->out);
+#define EALDM_XATTN(NKV)                                                                           \
+  case NKV:                                                                                        \
+    xattn_bf16_kernel<NKV><<<grid, XKV_THREADS, 0, st>>>(q, k, v, a->ld_q, a->ld_kv, c, (int)a->n_q, \
+                                                         sl2, o, a->ld_out);                       \
+    break
+  switch (a->n_kv) {
+    EALDM_XATTN(1); EALDM_XATTN(2); EALDM_XATTN(3); EALDM_XATTN(4);
+    default: return set_error(EALDM_EINVAL, "xattn: n_kv %lld > %d", (long long)a->n_kv, XKV_MAX);
+  }
+#undef EALDM_XATTN
+  EALDM_LAUNCH_CHECK();
+  return 0;
+}
+
 template <typename T, int D>
 static int launch_t(const ealdm_attention_args* a, cudaStream_t st) {
   const T* q = reinterpret_cast<const T*>(a->q);
@@ -230,6 +356,7 @@ extern "C" int ealdm_attention(const ealdm_attention_args* a, ealdm_stream_t str
   if (a->dtype == EALDM_BF16 && a->head_dim == 32 && a->n_kv > attn::MAX_SMALL_KV &&
       a->impl != EALDM_IMPL_SIMT)
     return attn::launch_flash_mma(a, st);
+  if (a->impl != EALDM_IMPL_SIMT && attn::xattn_bf16_ok(a)) return attn::launch_xattn_bf16(a, st);
   if (a->dtype == EALDM_F32) {
     return a->head_dim == 32 ? attn::launch_t<float, 32>(a, st) : attn::launch_t<float, 64>(a, st);
   } else if (a->dtype == EALDM_BF16) {

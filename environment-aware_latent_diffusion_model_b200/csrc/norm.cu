@@ -3,6 +3,11 @@
 // statistics go fp32 per thread -> fp32 per (CTA, 4-channel vector) -> fp64 per (image, group) in a
 // fixed summation order (no atomics, bit-reproducible).
 #include "common.cuh"
+#include "ptx.cuh"
+
+#include <cooperative_groups.h>
+
+namespace cg = cooperative_groups;
 
 namespace ealdm {
 namespace norm {
@@ -33,13 +38,23 @@ gn_stats_kernel(const TX* __restrict__ x, long long ld, int hw, int c, int pix_p
     const int v = v0 + tv;
     float s = 0.f, ss = 0.f;
     if (tp < pix_lanes && v < vpp) {
-      for (int pix = p0 + tp; pix < p1; pix += pix_lanes) {
-        Vec4<TX> q;
-        q.load(base + static_cast<long long>(pix) * ld + v * 4);
-        float f[4];
-        q.get(f);
+      constexpr int U = 8;
+      for (int pix0 = p0 + tp; pix0 < p1; pix0 += U * pix_lanes) {
+        Vec4<TX> q[U];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { s += f[j]; ss = fmaf(f[j], f[j], ss); }
+        for (int u = 0; u < U; ++u) {
+          const int pix = pix0 + u * pix_lanes;
+          if (pix < p1) q[u].load(base + static_cast<long long>(pix) * ld + v * 4);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (pix0 + u * pix_lanes < p1) {
+            float f[4];
+            q[u].get(f);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { s += f[j]; ss = fmaf(f[j], f[j], ss); }
+          }
+        }
       }
     }
     if (pix_lanes > 1) {
@@ -60,6 +75,8 @@ __global__ void __launch_bounds__(NT)
 gn_apply_kernel(const TX* __restrict__ x, long long ld_x, T* __restrict__ y, long long ld_y, int hw,
                 int c, int groups, int pix_per_cta, const float2* __restrict__ part, float eps,
                 const float* __restrict__ gamma, const float* __restrict__ beta, int act) {
+  // bf16 outputs: SiLU with the fast exp / divide intrinsics (error far below bf16 resolution)
+  constexpr bool SILU_FAST = sizeof(T) == 2;
   __shared__ float s_mean[MAX_GROUPS], s_rstd[MAX_GROUPS];
   const int t = threadIdx.x;
   const int n = blockIdx.y;
@@ -118,20 +135,31 @@ gn_apply_kernel(const TX* __restrict__ x, long long ld_x, T* __restrict__ y, lon
       // y = x * a + b with a = rstd * gamma, b = beta - mean * a
       const float a0 = rstd * ga.x, a1 = rstd * ga.y, a2 = rstd * ga.z, a3 = rstd * ga.w;
       const float b0 = be.x - mean * a0, b1 = be.y - mean * a1, b2 = be.z - mean * a2, b3 = be.w - mean * a3;
-#pragma unroll 4
-      for (int pix = p0 + tp; pix < p1; pix += pix_lanes) {
-        Vec4<TX> qx;
-        qx.load(xb + static_cast<long long>(pix) * ld_x + ch);
-        float f[4];
-        qx.get(f);
-        f[0] = fmaf(f[0], a0, b0); f[1] = fmaf(f[1], a1, b1); f[2] = fmaf(f[2], a2, b2); f[3] = fmaf(f[3], a3, b3);
-        if (act == EALDM_ACT_SILU) {
+      // 8 independent 16-byte loads in flight per thread before any of them is consumed
+      constexpr int U = 8;
+      for (int pix0 = p0 + tp; pix0 < p1; pix0 += U * pix_lanes) {
+        Vec4<TX> qx[U];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) f[j] = silu_f(f[j]);
+        for (int u = 0; u < U; ++u) {
+          const int pix = pix0 + u * pix_lanes;
+          if (pix < p1) qx[u].load(xb + static_cast<long long>(pix) * ld_x + ch);
         }
-        Vec4<T> q;
-        q.set(f);
-        q.store(yb + static_cast<long long>(pix) * ld_y + ch);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int pix = pix0 + u * pix_lanes;
+          if (pix < p1) {
+            float f[4];
+            qx[u].get(f);
+            f[0] = fmaf(f[0], a0, b0); f[1] = fmaf(f[1], a1, b1); f[2] = fmaf(f[2], a2, b2); f[3] = fmaf(f[3], a3, b3);
+            if (act == EALDM_ACT_SILU) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) f[j] = SILU_FAST ? __fdividef(f[j], 1.0f + __expf(-f[j])) : silu_f(f[j]);
+            }
+            Vec4<T> q;
+            q.set(f);
+            q.store(yb + static_cast<long long>(pix) * ld_y + ch);
+          }
+        }
       }
     }
   }
@@ -139,8 +167,8 @@ gn_apply_kernel(const TX* __restrict__ x, long long ld_x, T* __restrict__ y, lon
 
 // pixel chunking shared by the workspace query and the launch
 static void gn_chunking(long long n, long long hw, int* pix_per_cta, long long* chunks) {
-  // enough CTAs to fill 148 SMs a few times over, at least 16 pixels each
-  long long ch = ceil_div(1184, n);
+  // enough CTAs to fill 148 SMs (8 resident CTAs each) twice over, at least 16 pixels each
+  long long ch = ceil_div(2368, n);
   const long long max_chunks = ceil_div(hw, 16);
   if (ch > max_chunks) ch = max_chunks;
   if (ch < 1) ch = 1;
@@ -150,7 +178,23 @@ static void gn_chunking(long long n, long long hw, int* pix_per_cta, long long* 
 }
 
 template <typename TX, typename T>
+static int gn_cluster_plan(const ealdm_group_norm_args* a, int* ppc_out, size_t* smem_out, int* nsplit_out);
+template <typename TX, typename T>
+static int group_norm_cluster(const ealdm_group_norm_args* a, int cl, int ppc, size_t smem, int nsplit,
+                              cudaStream_t st, bool* launched);
+
+template <typename TX, typename T>
 static int group_norm_t(const ealdm_group_norm_args* a, cudaStream_t st) {
+  {
+    int ppc_c = 0, nsplit = 1;
+    size_t smem = 0;
+    const int cl = gn_cluster_plan<TX, T>(a, &ppc_c, &smem, &nsplit);
+    if (cl > 0) {
+      bool launched = false;
+      if (int e = group_norm_cluster<TX, T>(a, cl, ppc_c, smem, nsplit, st, &launched)) return e;
+      if (launched) return 0;
+    }
+  }
   const int hw = static_cast<int>(a->hw);
   const int n = static_cast<int>(a->n);
   int ppc;
@@ -166,6 +210,237 @@ static int group_norm_t(const ealdm_group_norm_args* a, cudaStream_t st) {
                                           static_cast<int>(a->c), a->groups, ppc, part, a->eps,
                                           a->gamma, a->beta, a->act);
   EALDM_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---- single-pass GroupNorm on a thread-block cluster ---------------------------------------------------
+// One cluster per image; CTA r of the cluster pulls its slab of pixel rows into shared memory with bulk
+// TMA copies (one per row, all in flight at once), so x crosses HBM exactly once.  Statistics: fp32 per
+// thread -> fp64 per (CTA, group) in a fixed order -> fp64 over the cluster's CTAs through distributed
+// shared memory, rank 0 first (bit-reproducible, identical in every CTA).  The affine transform (+SiLU)
+// is then applied from shared memory.
+constexpr int CNT = 256;
+
+__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      :
+      : "r"(ptx::smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(ptx::smem_u32(bar))
+      : "memory");
+}
+
+template <typename TX, typename T>
+__global__ void __launch_bounds__(CNT)
+gn_cluster_kernel(const TX* __restrict__ x, long long ld_x, T* __restrict__ y, long long ld_y, int hw,
+                  int c, int groups, int ppc, float eps, const float* __restrict__ gamma,
+                  const float* __restrict__ beta, int act) {
+  // blockIdx.z selects a channel range of `c` channels (`groups` whole groups) of the image
+  x += static_cast<long long>(blockIdx.z) * c;
+  y += static_cast<long long>(blockIdx.z) * c;
+  gamma += static_cast<long long>(blockIdx.z) * c;
+  beta += static_cast<long long>(blockIdx.z) * c;
+  constexpr bool SILU_FAST = sizeof(T) == 2;
+  extern __shared__ __align__(16) uint8_t gsm[];
+  const int row_bytes = c * static_cast<int>(sizeof(TX));
+  TX* slab = reinterpret_cast<TX*>(gsm);
+  uint8_t* tail = gsm + static_cast<size_t>(ppc) * row_bytes;
+  double* gpart = reinterpret_cast<double*>(tail);                       // [MAX_GROUPS][2]
+  float2* red = reinterpret_cast<float2*>(tail + MAX_GROUPS * 16);       // [CNT]
+  float* s_mean = reinterpret_cast<float*>(tail + MAX_GROUPS * 16 + CNT * 8);
+  float* s_rstd = s_mean + MAX_GROUPS;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(s_rstd + MAX_GROUPS);
+
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = static_cast<int>(cluster.block_rank());
+  const int nranks = static_cast<int>(cluster.num_blocks());
+  const int t = threadIdx.x;
+  const int n = blockIdx.y;
+  const int p0 = rank * ppc;
+  const TX* xb = x + (static_cast<long long>(n) * hw + p0) * ld_x;
+  T* yb = y + (static_cast<long long>(n) * hw + p0) * ld_y;
+
+  if (t == 0) {
+    ptx::mbar_init(bar, 1);
+    ptx::fence_mbar_init();
+    ptx::mbar_arrive_expect_tx(bar, static_cast<uint32_t>(ppc) * row_bytes);
+  }
+  __syncthreads();
+  for (int r = t; r < ppc; r += CNT)
+    bulk_copy_g2s(reinterpret_cast<uint8_t*>(slab) + static_cast<size_t>(r) * row_bytes,
+                  xb + static_cast<long long>(r) * ld_x, row_bytes, bar);
+  ptx::mbar_wait(bar, 0);
+
+  const int cpg = c / groups;
+  const int vpg = cpg >> 2;
+  const int vpp = c >> 2;
+  const int lanes_v = vpp <= CNT ? vpp : (CNT / vpg) * vpg;
+  const int pix_lanes = vpp <= CNT ? CNT / vpp : 1;
+  const int tv = t % lanes_v, tp = t / lanes_v;
+  for (int v0 = 0; v0 < vpp; v0 += lanes_v) {
+    const int v = v0 + tv;
+    float s = 0.f, ss = 0.f;
+    if (tp < pix_lanes && v < vpp) {
+#pragma unroll 4
+      for (int pix = tp; pix < ppc; pix += pix_lanes) {
+        Vec4<TX> q;
+        q.load(slab + static_cast<size_t>(pix) * c + v * 4);
+        float f[4];
+        q.get(f);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { s += f[j]; ss = fmaf(f[j], f[j], ss); }
+      }
+    }
+    red[t] = make_float2(s, ss);
+    __syncthreads();
+    const int nv = min(lanes_v, vpp - v0);
+    if (t < nv / vpg) {
+      double S = 0.0, SS = 0.0;
+      for (int k = 0; k < pix_lanes; ++k)
+        for (int vv = 0; vv < vpg; ++vv) {
+          const float2 e = red[k * lanes_v + t * vpg + vv];
+          S += static_cast<double>(e.x);
+          SS += static_cast<double>(e.y);
+        }
+      gpart[2 * (v0 / vpg + t)] = S;
+      gpart[2 * (v0 / vpg + t) + 1] = SS;
+    }
+    __syncthreads();
+  }
+  cluster.sync();
+  if (t < groups) {
+    // every rank's partials with independent remote loads (one DSMEM round trip), summed in rank order
+    double2 rp[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r)
+      rp[r] = r < nranks ? *reinterpret_cast<const double2*>(cluster.map_shared_rank(gpart, r) + 2 * t)
+                         : make_double2(0.0, 0.0);
+    double S = 0.0, SS = 0.0;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      S += rp[r].x;
+      SS += rp[r].y;
+    }
+    const double cnt = static_cast<double>(hw) * cpg;
+    const double mean = S / cnt;
+    double var = SS / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    s_mean[t] = static_cast<float>(mean);
+    s_rstd[t] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  }
+  __syncthreads();
+  // this CTA is done reading its peers: arrive now (no global stores outstanding yet, so the release
+  // fence is free) and wait only at the very end -- shared memory must outlive the peers' reads
+  cluster.barrier_arrive();
+  for (int v0 = 0; v0 < vpp; v0 += lanes_v) {
+    const int v = v0 + tv;
+    if (tp < pix_lanes && v < vpp) {
+      const int ch = v * 4;
+      const int g = ch / cpg;
+      const float mean = s_mean[g], rstd = s_rstd[g];
+      const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + ch));
+      const float4 be = __ldg(reinterpret_cast<const float4*>(beta + ch));
+      const float a0 = rstd * ga.x, a1 = rstd * ga.y, a2 = rstd * ga.z, a3 = rstd * ga.w;
+      const float b0 = be.x - mean * a0, b1 = be.y - mean * a1, b2 = be.z - mean * a2, b3 = be.w - mean * a3;
+#pragma unroll 4
+      for (int pix = tp; pix < ppc; pix += pix_lanes) {
+        Vec4<TX> qx;
+        qx.load(slab + static_cast<size_t>(pix) * c + ch);
+        float f[4];
+        qx.get(f);
+        f[0] = fmaf(f[0], a0, b0); f[1] = fmaf(f[1], a1, b1); f[2] = fmaf(f[2], a2, b2); f[3] = fmaf(f[3], a3, b3);
+        if (act == EALDM_ACT_SILU) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) f[j] = SILU_FAST ? __fdividef(f[j], 1.0f + __expf(-f[j])) : silu_f(f[j]);
+        }
+        Vec4<T> q;
+        q.set(f);
+        q.store(yb + static_cast<long long>(pix) * ld_y + ch);
+      }
+    }
+  }
+  cluster.barrier_wait();
+}
+
+constexpr int GN_CLUSTER_TAIL = MAX_GROUPS * 16 + CNT * 8 + MAX_GROUPS * 8 + 16;
+
+// (cluster size, channel split) for the single-pass kernel: the smallest launch whose per-CTA slab lets
+// 3 CTAs share an SM (loads of one CTA overlap the reduction / stores of its neighbours); 0 if none.
+template <typename TX, typename T>
+static int gn_cluster_plan(const ealdm_group_norm_args* a, int* ppc_out, size_t* smem_out, int* nsplit_out) {
+  if ((a->c * static_cast<long long>(sizeof(TX))) % 16 != 0 ||
+      (a->ld_x * static_cast<long long>(sizeof(TX))) % 16 != 0 || (reinterpret_cast<uintptr_t>(a->x) & 15) != 0)
+    return 0;
+  const int cpg = static_cast<int>(a->c / a->groups);
+  const int vpg = cpg >> 2;
+  if (vpg < 1 || vpg > CNT) return 0;
+  const long long limit = 74 * 1024;
+  for (int ns = 1; ns <= 8; ns *= 2) {
+    if (a->groups % ns != 0) break;
+    const long long row_bytes = (a->c / ns) * static_cast<long long>(sizeof(TX));
+    if (row_bytes % 16 != 0) break;
+    for (int cl = 1; cl <= 16; cl *= 2) {
+      if (a->hw % cl != 0) break;
+      const long long ppc = a->hw / cl;
+      const long long smem = ppc * row_bytes + GN_CLUSTER_TAIL;
+      if (smem > limit) continue;
+      *ppc_out = static_cast<int>(ppc);
+      *smem_out = static_cast<size_t>(smem);
+      *nsplit_out = ns;
+      return cl;
+    }
+  }
+  return 0;
+}
+
+template <typename TX, typename T>
+static int group_norm_cluster(const ealdm_group_norm_args* a, int cl, int ppc, size_t smem, int nsplit,
+                              cudaStream_t st, bool* launched) {
+  *launched = false;
+  auto kern = gn_cluster_kernel<TX, T>;
+  static size_t smem_set = 0;
+  static bool nonportable_set = false;
+  if (smem > smem_set) {
+    EALDM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    smem_set = smem;
+  }
+  if (cl > 8 && !nonportable_set) {
+    EALDM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    nonportable_set = true;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(static_cast<unsigned>(cl), static_cast<unsigned>(a->n), static_cast<unsigned>(nsplit));
+  cfg.blockDim = dim3(CNT, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = static_cast<unsigned>(cl);
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  // the cluster shape must be placeable on this device (checked once per shape)
+  static int ok_cl[17] = {0};
+  static size_t ok_smem[17] = {0};
+  if (ok_cl[cl] == 0 || smem > ok_smem[cl]) {
+    int nclusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&nclusters, kern, &cfg) != cudaSuccess || nclusters < 1) {
+      cudaGetLastError();
+      ok_cl[cl] = -1;
+    } else {
+      ok_cl[cl] = 1;
+    }
+    ok_smem[cl] = smem;
+  }
+  if (ok_cl[cl] < 0) return 0;
+  const TX* x = reinterpret_cast<const TX*>(a->x);
+  T* y = reinterpret_cast<T*>(a->y);
+  const int hw = static_cast<int>(a->hw), c = static_cast<int>(a->c / nsplit);
+  EALDM_CUDA(cudaLaunchKernelEx(&cfg, kern, x, a->ld_x, y, a->ld_y, hw, c, a->groups / nsplit, ppc, a->eps,
+                                a->gamma, a->beta, a->act));
+  count_launch();
+  *launched = true;
   return 0;
 }
 

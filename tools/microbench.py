@@ -138,6 +138,7 @@ CASES = {
     "xattn_l2": lambda: make_xattn(N, 32, 64),
     # norms
     "gn_256_l0": lambda: make_gn(N, 1024, 256),
+    "gn_256_l0_bf16in": lambda: make_gn(N, 1024, 256, x_dt=BF),
     "gn_512_l0": lambda: make_gn(N, 1024, 512),
     "gn_768_l0": lambda: make_gn(N, 1024, 768),
     "gn_1024_l1": lambda: make_gn(N, 256, 1024),
