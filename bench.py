@@ -178,6 +178,8 @@ def main():
     ap.add_argument("--ddim-steps", type=int, default=50)
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ncu-window", action="store_true",
+                    help="cudaProfilerStart/Stop around the timed region (for `ncu --profile-from-start off`)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -261,7 +263,11 @@ def main():
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
+    if args.ncu_window:
+        torch.cuda.cudart().cudaProfilerStart()
     ms = timed(step_resident, args.steps)
+    if args.ncu_window:
+        torch.cuda.cudart().cudaProfilerStop()
     clk = clocks.stop() if rank == 0 else None
     ms_per_step = ms / args.steps
     value = Bg / (ms_per_step * 1e-3)
