@@ -23,7 +23,14 @@ EXPORTS = [
     "ealdm_timestep_embedding", "ealdm_nchw_to_nhwc", "ealdm_nhwc_to_nchw",
     "ealdm_upsample_nearest2x", "ealdm_copy2d", "ealdm_softmax_rows", "ealdm_ddim_step",
     "ealdm_q_sample", "ealdm_cfg_mse",
+    # backward pass
+    "ealdm_conv_wgrad", "ealdm_conv_wgrad_workspace_bytes", "ealdm_group_norm_bwd",
+    "ealdm_group_norm_bwd_workspace_bytes", "ealdm_layer_norm_bwd", "ealdm_layer_norm_bwd_workspace_bytes",
+    "ealdm_attention_bwd", "ealdm_attention_bwd_workspace_bytes", "ealdm_geglu", "ealdm_geglu_bwd",
+    "ealdm_silu", "ealdm_silu_bwd", "ealdm_colsum", "ealdm_colsum_workspace_bytes", "ealdm_zero_insert2x",
+    "ealdm_sumpool2x2", "ealdm_cfg_mse_bwd",
 ]
+WGRAD_PACKED, WGRAD_OIHW = 0, 1
 
 
 class ConvSrc(C.Structure):
@@ -46,7 +53,8 @@ class GroupNormArgs(C.Structure):
     _fields_ = [("dtype", C.c_int32), ("act", C.c_int32), ("x", C.c_void_p), ("n", C.c_int64),
                 ("hw", C.c_int64), ("c", C.c_int64), ("ld_x", C.c_int64), ("groups", C.c_int32),
                 ("eps", C.c_float), ("gamma", C.c_void_p), ("beta", C.c_void_p), ("y", C.c_void_p),
-                ("ld_y", C.c_int64), ("workspace", C.c_void_p), ("x_f32", C.c_int32), ("reserved", C.c_int32)]
+                ("ld_y", C.c_int64), ("workspace", C.c_void_p), ("x_f32", C.c_int32), ("reserved", C.c_int32),
+                ("stats_out", C.c_void_p)]
 
 
 class LayerNormArgs(C.Structure):
@@ -72,6 +80,42 @@ class DdimStepArgs(C.Structure):
                 ("sqrt_one_minus_at", C.c_float), ("sqrt_at", C.c_float),
                 ("sqrt_a_prev", C.c_float), ("dir_coef", C.c_float), ("sigma_t", C.c_float),
                 ("temperature", C.c_float), ("reserved", C.c_int32)]
+
+
+class ConvWgradArgs(C.Structure):
+    _fields_ = [("dtype", C.c_int32), ("impl", C.c_int32), ("src", ConvSrc), ("dy", C.c_void_p),
+                ("ld_dy", C.c_int64), ("n_out", C.c_int64), ("h_out", C.c_int64), ("w_out", C.c_int64),
+                ("dw", C.c_void_p), ("ld_dw", C.c_int64), ("layout", C.c_int32), ("accumulate", C.c_int32),
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64)]
+
+
+class GroupNormBwdArgs(C.Structure):
+    _fields_ = [("dtype", C.c_int32), ("act", C.c_int32), ("x", C.c_void_p), ("n", C.c_int64),
+                ("hw", C.c_int64), ("c", C.c_int64), ("ld_x", C.c_int64), ("groups", C.c_int32),
+                ("x_f32", C.c_int32), ("stats", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p),
+                ("dy", C.c_void_p), ("ld_dy", C.c_int64), ("add", C.c_void_p), ("ld_add", C.c_int64),
+                ("add2", C.c_void_p), ("ld_add2", C.c_int64), ("dx", C.c_void_p), ("ld_dx", C.c_int64),
+                ("dx_f32", C.c_int32), ("reserved", C.c_int32), ("dx2", C.c_void_p), ("ld_dx2", C.c_int64),
+                ("dgamma", C.c_void_p), ("dbeta", C.c_void_p), ("workspace", C.c_void_p)]
+
+
+class LayerNormBwdArgs(C.Structure):
+    _fields_ = [("dtype", C.c_int32), ("x_f32", C.c_int32), ("x", C.c_void_p), ("rows", C.c_int64),
+                ("c", C.c_int64), ("ld_x", C.c_int64), ("eps", C.c_float), ("dx_f32", C.c_int32),
+                ("gamma", C.c_void_p), ("dy", C.c_void_p), ("ld_dy", C.c_int64), ("add", C.c_void_p),
+                ("ld_add", C.c_int64), ("dx", C.c_void_p), ("ld_dx", C.c_int64), ("dx2", C.c_void_p),
+                ("ld_dx2", C.c_int64), ("dgamma", C.c_void_p), ("dbeta", C.c_void_p), ("workspace", C.c_void_p)]
+
+
+class AttentionBwdArgs(C.Structure):
+    _fields_ = [("dtype", C.c_int32), ("impl", C.c_int32), ("q", C.c_void_p), ("k", C.c_void_p),
+                ("v", C.c_void_p), ("out", C.c_void_p), ("dout", C.c_void_p), ("ld_q", C.c_int64),
+                ("ld_kv", C.c_int64), ("ld_out", C.c_int64), ("ld_dout", C.c_int64),
+                ("head_stride_q", C.c_int64), ("head_stride_kv", C.c_int64), ("batch", C.c_int64),
+                ("heads", C.c_int64), ("n_q", C.c_int64), ("n_kv", C.c_int64), ("head_dim", C.c_int64),
+                ("scale", C.c_float), ("reserved", C.c_int32), ("dq", C.c_void_p), ("ld_dq", C.c_int64),
+                ("head_stride_dq", C.c_int64), ("dk", C.c_void_p), ("dv", C.c_void_p), ("ld_dkv", C.c_int64),
+                ("head_stride_dkv", C.c_int64), ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64)]
 
 
 class EaldmError(RuntimeError):
@@ -106,6 +150,16 @@ def _declare(lib):
     lib.ealdm_group_norm_workspace_bytes.restype = C.c_int64
     lib.ealdm_group_norm_workspace_bytes.argtypes = [i64, i64, i64]
     for name, argt in [
+        ("ealdm_conv_wgrad_workspace_bytes", [C.POINTER(ConvWgradArgs)]),
+        ("ealdm_group_norm_bwd_workspace_bytes", [i64, i64, i64]),
+        ("ealdm_layer_norm_bwd_workspace_bytes", [i64, i64]),
+        ("ealdm_attention_bwd_workspace_bytes", [C.POINTER(AttentionBwdArgs)]),
+        ("ealdm_colsum_workspace_bytes", [i64, i64, i64]),
+    ]:
+        fn = getattr(lib, name)
+        fn.restype = C.c_int64
+        fn.argtypes = argt
+    for name, argt in [
         ("ealdm_conv", [C.POINTER(ConvArgs), vp]),
         ("ealdm_group_norm", [C.POINTER(GroupNormArgs), vp]),
         ("ealdm_layer_norm", [C.POINTER(LayerNormArgs), vp]),
@@ -119,6 +173,18 @@ def _declare(lib):
         ("ealdm_ddim_step", [C.POINTER(DdimStepArgs), vp]),
         ("ealdm_q_sample", [vp, vp, vp, vp, vp, i64, i64, vp, vp]),
         ("ealdm_cfg_mse", [vp, vp, vp, f32, i64, i64, vp, vp]),
+        ("ealdm_conv_wgrad", [C.POINTER(ConvWgradArgs), vp]),
+        ("ealdm_group_norm_bwd", [C.POINTER(GroupNormBwdArgs), vp]),
+        ("ealdm_layer_norm_bwd", [C.POINTER(LayerNormBwdArgs), vp]),
+        ("ealdm_attention_bwd", [C.POINTER(AttentionBwdArgs), vp]),
+        ("ealdm_geglu", [vp, i64, i32, i64, i64, vp, i64, vp]),
+        ("ealdm_geglu_bwd", [vp, i64, vp, i64, i32, i64, i64, vp, i64, vp]),
+        ("ealdm_silu", [vp, i64, i64, i64, i32, vp, i64, vp]),
+        ("ealdm_silu_bwd", [vp, i64, vp, i64, i32, i64, i64, vp, i64, vp]),
+        ("ealdm_colsum", [vp, i64, i32, i64, i64, i64, vp, i64, i32, vp, vp]),
+        ("ealdm_zero_insert2x", [vp, i64, i32, i64, i64, i64, i64, vp, i64, vp]),
+        ("ealdm_sumpool2x2", [vp, i64, i32, i64, i64, i64, i64, vp, i64, vp, i64, vp, i64, vp]),
+        ("ealdm_cfg_mse_bwd", [vp, vp, vp, vp, f32, i64, i64, vp, vp, vp]),
     ]:
         fn = getattr(lib, name)
         fn.restype = C.c_int
@@ -135,7 +201,7 @@ def load():
                 "(there is no CPU or PyTorch fallback for the CUDA kernels)")
         lib = C.CDLL(LIB_PATH)
         _declare(lib)
-        if lib.ealdm_abi_version() != 1:
+        if lib.ealdm_abi_version() != 2:
             raise EaldmError("libealdm_b200.so ABI version mismatch")
         _lib = lib
     return _lib

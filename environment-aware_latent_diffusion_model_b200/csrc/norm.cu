@@ -74,7 +74,8 @@ template <typename TX, typename T>
 __global__ void __launch_bounds__(NT)
 gn_apply_kernel(const TX* __restrict__ x, long long ld_x, T* __restrict__ y, long long ld_y, int hw,
                 int c, int groups, int pix_per_cta, const float2* __restrict__ part, float eps,
-                const float* __restrict__ gamma, const float* __restrict__ beta, int act) {
+                const float* __restrict__ gamma, const float* __restrict__ beta, int act,
+                float* __restrict__ stats_out) {
   // bf16 outputs: SiLU with the fast exp / divide intrinsics (error far below bf16 resolution)
   constexpr bool SILU_FAST = sizeof(T) == 2;
   __shared__ float s_mean[MAX_GROUPS], s_rstd[MAX_GROUPS];
@@ -112,6 +113,10 @@ gn_apply_kernel(const TX* __restrict__ x, long long ld_x, T* __restrict__ y, lon
         if (var < 0.0) var = 0.0;
         s_mean[g] = static_cast<float>(mean);
         s_rstd[g] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+        if (stats_out != nullptr && blockIdx.x == 0) {
+          stats_out[(static_cast<long long>(n) * groups + g) * 2] = s_mean[g];
+          stats_out[(static_cast<long long>(n) * groups + g) * 2 + 1] = s_rstd[g];
+        }
       }
     }
   }
@@ -208,7 +213,7 @@ static int group_norm_t(const ealdm_group_norm_args* a, cudaStream_t st) {
   gn_apply_kernel<TX, T><<<grid, NT, 0, st>>>(reinterpret_cast<const TX*>(a->x), a->ld_x,
                                           reinterpret_cast<T*>(a->y), a->ld_y, hw,
                                           static_cast<int>(a->c), a->groups, ppc, part, a->eps,
-                                          a->gamma, a->beta, a->act);
+                                          a->gamma, a->beta, a->act, a->stats_out);
   EALDM_LAUNCH_CHECK();
   return 0;
 }
@@ -233,7 +238,7 @@ template <typename TX, typename T>
 __global__ void __launch_bounds__(CNT)
 gn_cluster_kernel(const TX* __restrict__ x, long long ld_x, T* __restrict__ y, long long ld_y, int hw,
                   int c, int groups, int ppc, float eps, const float* __restrict__ gamma,
-                  const float* __restrict__ beta, int act) {
+                  const float* __restrict__ beta, int act, float* __restrict__ stats_out) {
   // blockIdx.z selects a channel range of `c` channels (`groups` whole groups) of the image
   x += static_cast<long long>(blockIdx.z) * c;
   y += static_cast<long long>(blockIdx.z) * c;
@@ -326,6 +331,11 @@ gn_cluster_kernel(const TX* __restrict__ x, long long ld_x, T* __restrict__ y, l
     if (var < 0.0) var = 0.0;
     s_mean[t] = static_cast<float>(mean);
     s_rstd[t] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    if (stats_out != nullptr && rank == 0) {
+      const long long gi = (static_cast<long long>(n) * gridDim.z + blockIdx.z) * groups + t;
+      stats_out[gi * 2] = s_mean[t];
+      stats_out[gi * 2 + 1] = s_rstd[t];
+    }
   }
   __syncthreads();
   // this CTA is done reading its peers: arrive now (no global stores outstanding yet, so the release
@@ -438,7 +448,7 @@ static int group_norm_cluster(const ealdm_group_norm_args* a, int cl, int ppc, s
   T* y = reinterpret_cast<T*>(a->y);
   const int hw = static_cast<int>(a->hw), c = static_cast<int>(a->c / nsplit);
   EALDM_CUDA(cudaLaunchKernelEx(&cfg, kern, x, a->ld_x, y, a->ld_y, hw, c, a->groups / nsplit, ppc, a->eps,
-                                a->gamma, a->beta, a->act));
+                                a->gamma, a->beta, a->act, a->stats_out));
   count_launch();
   *launched = true;
   return 0;

@@ -103,6 +103,26 @@ cfg_mse_kernel(const float* __restrict__ eu, const float* __restrict__ ec,
   }
 }
 
+// gradient of sum_b w[b] * mean_i (guided - target)^2 w.r.t. e_cond / e_uncond
+__global__ void __launch_bounds__(NT)
+cfg_mse_bwd_kernel(const float* __restrict__ eu, const float* __restrict__ ec, const float* __restrict__ target,
+                   const float* __restrict__ w, float cfg_scale, long long per_sample, long long total,
+                   float* __restrict__ deu, float* __restrict__ dec) {
+  for (long long i = blockIdx.x * static_cast<long long>(NT) + threadIdx.x; i < total;
+       i += static_cast<long long>(NT) * gridDim.x) {
+    const long long b = i / per_sample;
+    const float c = ec[i];
+    const float g = eu ? __fadd_rn(eu[i], __fmul_rn(cfg_scale, __fsub_rn(c, eu[i]))) : c;
+    const float d = 2.0f * w[b] / static_cast<float>(per_sample) * (g - target[i]);
+    if (eu) {
+      dec[i] = cfg_scale * d;
+      deu[i] = (1.0f - cfg_scale) * d;
+    } else {
+      dec[i] = d;
+    }
+  }
+}
+
 }  // namespace sampler
 }  // namespace ealdm
 
@@ -156,6 +176,21 @@ extern "C" int ealdm_cfg_mse(const float* e_uncond, const float* e_cond, const f
   sampler::cfg_mse_kernel<<<static_cast<unsigned>(batch), sampler::NT, 0,
                             static_cast<cudaStream_t>(stream)>>>(e_uncond, e_cond, target, cfg_scale,
                                                                  per_sample, loss_simple);
+  EALDM_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ealdm_cfg_mse_bwd(const float* e_uncond, const float* e_cond, const float* target, const float* w,
+                                 float cfg_scale, int64_t batch, int64_t per_sample, float* de_uncond,
+                                 float* de_cond, ealdm_stream_t stream) {
+  EALDM_REQUIRE(e_cond && target && w && de_cond, "cfg_mse_bwd: null argument");
+  EALDM_REQUIRE((e_uncond == nullptr) == (de_uncond == nullptr), "cfg_mse_bwd: e_uncond and de_uncond go together");
+  EALDM_REQUIRE(batch > 0 && per_sample > 0, "cfg_mse_bwd: bad sizes");
+  const long long total = batch * per_sample;
+  const long long blocks = ceil_div(total, sampler::NT);
+  sampler::cfg_mse_bwd_kernel<<<static_cast<unsigned>(blocks < 2368 ? blocks : 2368), sampler::NT, 0,
+                                static_cast<cudaStream_t>(stream)>>>(e_uncond, e_cond, target, w, cfg_scale,
+                                                                     per_sample, total, de_uncond, de_cond);
   EALDM_LAUNCH_CHECK();
   return 0;
 }

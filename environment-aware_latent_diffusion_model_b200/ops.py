@@ -146,7 +146,8 @@ def group_norm_workspace(n: int, hw: int, c: int, device) -> torch.Tensor:
 
 
 def group_norm(x: Act, gamma: torch.Tensor, beta: torch.Tensor, eps: float, out: Act,
-               workspace: Optional[torch.Tensor] = None, *, groups: int = 32, silu: bool = False) -> Act:
+               workspace: Optional[torch.Tensor] = None, *, groups: int = 32, silu: bool = False,
+               stats_out: Optional[torch.Tensor] = None) -> Act:
     lib = L.load()
     a = L.GroupNormArgs()
     a.dtype = _dt(out.dtype)
@@ -163,6 +164,9 @@ def group_norm(x: Act, gamma: torch.Tensor, beta: torch.Tensor, eps: float, out:
         workspace = group_norm_workspace(x.n, x.h * x.w, x.c, x.buf.device)
     assert workspace.numel() * workspace.element_size() >= need, "group_norm workspace too small"
     a.workspace = workspace.data_ptr()
+    if stats_out is not None:
+        assert stats_out.dtype == torch.float32 and stats_out.is_contiguous() and stats_out.numel() == x.n * groups * 2
+        a.stats_out = stats_out.data_ptr()
     L.check(lib.ealdm_group_norm(C.byref(a), _stream()))
     return out
 
@@ -290,6 +294,211 @@ def cfg_mse(e_cond, target, *, e_uncond=None, cfg_scale=1.0):
     L.check(lib.ealdm_cfg_mse(_ptr(e_uncond), e_cond.data_ptr(), target.data_ptr(), cfg_scale, b,
                               e_cond.numel() // b, out.data_ptr(), _stream()))
     return out
+
+
+# ---- backward pass ------------------------------------------------------------------------------------
+class Workspace:
+    """A grow-only scratch buffer for the backward kernels (one per stream of execution)."""
+
+    def __init__(self, device):
+        self.device, self.buf = device, None
+
+    def get(self, nbytes: int) -> torch.Tensor:
+        n = (max(int(nbytes), 16) + 15) // 16 * 2
+        if self.buf is None or self.buf.numel() < n:
+            self.buf = torch.empty(n, dtype=torch.float64, device=self.device)
+        return self.buf
+
+
+def conv_wgrad(x: Act, dy: Act, dw: torch.Tensor, ws: Workspace, *, ksize=1, stride=1, pad=0, col0: int = 0,
+               layout: int = L.WGRAD_OIHW, accumulate: bool = True, impl: int = L.IMPL_AUTO) -> None:
+    """ealdm_conv_wgrad: dw (+)= dy^T * im2col(x).  `dw` is a 2-D fp32 view [n_out, ld]; with the PACKED layout
+    the result goes to columns [col0, col0 + ksize^2 * c)."""
+    lib = L.load()
+    a = L.ConvWgradArgs()
+    a.dtype, a.impl = _dt(x.dtype), impl
+    d = a.src
+    d.x, d.n, d.h, d.w, d.c, d.ld = x.ptr, x.n, x.h, x.w, x.c, x.ld
+    d.ksize, d.stride, d.pad, d.upsample = ksize, stride, pad, 0
+    assert dy.dtype == x.dtype and dy.n == x.n
+    a.dy, a.ld_dy, a.n_out, a.h_out, a.w_out = dy.ptr, dy.ld, dy.c, dy.h, dy.w
+    assert dw.dtype == torch.float32 and dw.dim() == 2 and dw.stride(1) == 1 and dw.shape[0] == dy.c
+    a.dw = dw.data_ptr() + 4 * col0
+    a.ld_dw = dw.stride(0)
+    assert col0 + ksize * ksize * x.c <= dw.shape[1]
+    a.layout, a.accumulate = layout, 1 if accumulate else 0
+    need = int(lib.ealdm_conv_wgrad_workspace_bytes(C.byref(a)))
+    if need < 0:
+        L.check(-1)
+    w = ws.get(need)
+    a.workspace, a.workspace_bytes = w.data_ptr(), w.numel() * 8
+    L.check(lib.ealdm_conv_wgrad(C.byref(a), _stream()))
+
+
+def linear_wgrad(x: Act, dy: Act, dw: torch.Tensor, ws: Workspace, **kw) -> None:
+    xs = Act(x.buf, 1, 1, x.rows, x.c, x.c0)
+    ds = Act(dy.buf, 1, 1, dy.rows, dy.c, dy.c0)
+    conv_wgrad(xs, ds, dw, ws, **kw)
+
+
+def group_norm_bwd(x: Act, dy: Act, stats: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, dx: Act,
+                   ws: Workspace, *, groups: int = 32, silu: bool = False, add: Optional[Act] = None,
+                   add2: Optional[Act] = None, dx2: Optional[Act] = None, dgamma: Optional[torch.Tensor] = None,
+                   dbeta: Optional[torch.Tensor] = None) -> Act:
+    lib = L.load()
+    a = L.GroupNormBwdArgs()
+    a.dtype = _dt(dy.dtype)
+    a.act = L.ACT_SILU if silu else L.ACT_NONE
+    a.x, a.n, a.hw, a.c, a.ld_x = x.ptr, x.n, x.h * x.w, x.c, x.ld
+    a.groups = groups
+    a.x_f32 = 1 if (x.dtype == torch.float32 and dy.dtype != torch.float32) else 0
+    assert stats.dtype == torch.float32 and stats.numel() == x.n * groups * 2
+    a.stats, a.gamma, a.beta = stats.data_ptr(), gamma.data_ptr(), beta.data_ptr()
+    assert dy.rows == x.rows and dy.c == x.c and dx.rows == x.rows and dx.c == x.c
+    a.dy, a.ld_dy = dy.ptr, dy.ld
+    for name, t in (("add", add), ("add2", add2)):
+        if t is not None:
+            assert t.dtype == torch.float32 and t.rows == x.rows and t.c == x.c
+            setattr(a, name, t.ptr)
+            setattr(a, "ld_" + name, t.ld)
+    a.dx, a.ld_dx = dx.ptr, dx.ld
+    a.dx_f32 = 1 if (dx.dtype == torch.float32 and dy.dtype != torch.float32) else 0
+    assert dx.dtype in (dy.dtype, torch.float32)
+    if dx2 is not None:
+        assert dx2.dtype == dy.dtype and dx2.rows == x.rows and dx2.c == x.c
+        a.dx2, a.ld_dx2 = dx2.ptr, dx2.ld
+    for name, t in (("dgamma", dgamma), ("dbeta", dbeta)):
+        if t is not None:
+            assert t.dtype == torch.float32 and t.is_contiguous() and t.numel() == x.c
+            setattr(a, name, t.data_ptr())
+    a.workspace = ws.get(int(lib.ealdm_group_norm_bwd_workspace_bytes(x.n, x.h * x.w, x.c))).data_ptr()
+    L.check(lib.ealdm_group_norm_bwd(C.byref(a), _stream()))
+    return dx
+
+
+def layer_norm_bwd(x: Act, dy: Act, gamma: torch.Tensor, eps: float, dx: Act, ws: Workspace, *,
+                   add: Optional[Act] = None, dx2: Optional[Act] = None, dgamma: Optional[torch.Tensor] = None,
+                   dbeta: Optional[torch.Tensor] = None) -> Act:
+    lib = L.load()
+    a = L.LayerNormBwdArgs()
+    a.dtype = _dt(dy.dtype)
+    a.x_f32 = 1 if (x.dtype == torch.float32 and dy.dtype != torch.float32) else 0
+    a.dx_f32 = 1 if (dx.dtype == torch.float32 and dy.dtype != torch.float32) else 0
+    a.x, a.rows, a.c, a.ld_x, a.eps = x.ptr, x.rows, x.c, x.ld, eps
+    a.gamma = gamma.data_ptr()
+    assert dy.rows == x.rows and dy.c == x.c and dx.rows == x.rows and dx.c == x.c
+    a.dy, a.ld_dy, a.dx, a.ld_dx = dy.ptr, dy.ld, dx.ptr, dx.ld
+    if add is not None:
+        assert add.dtype == torch.float32 and add.rows == x.rows and add.c == x.c
+        a.add, a.ld_add = add.ptr, add.ld
+    if dx2 is not None:
+        assert dx2.dtype == dy.dtype
+        a.dx2, a.ld_dx2 = dx2.ptr, dx2.ld
+    for name, t in (("dgamma", dgamma), ("dbeta", dbeta)):
+        if t is not None:
+            assert t.dtype == torch.float32 and t.is_contiguous() and t.numel() == x.c
+            setattr(a, name, t.data_ptr())
+    a.workspace = ws.get(int(lib.ealdm_layer_norm_bwd_workspace_bytes(x.rows, x.c))).data_ptr()
+    L.check(lib.ealdm_layer_norm_bwd(C.byref(a), _stream()))
+    return dx
+
+
+def attention_bwd(q: Act, k: Act, v: Act, out: Act, dout: Act, dq: Act, dk: Act, dv: Act, ws: Workspace, *,
+                  batch: int, heads: int, head_dim: int, n_q: int, n_kv: int, scale: float,
+                  head_stride_q: Optional[int] = None, head_stride_kv: Optional[int] = None,
+                  head_stride_dq: Optional[int] = None, head_stride_dkv: Optional[int] = None) -> None:
+    lib = L.load()
+    a = L.AttentionBwdArgs()
+    a.dtype = _dt(q.dtype)
+    a.q, a.k, a.v, a.out, a.dout = q.ptr, k.ptr, v.ptr, out.ptr, dout.ptr
+    assert k.ld == v.ld and dk.ld == dv.ld and q.rows == batch * n_q and k.rows == batch * n_kv
+    a.ld_q, a.ld_kv, a.ld_out, a.ld_dout = q.ld, k.ld, out.ld, dout.ld
+    a.head_stride_q = head_dim if head_stride_q is None else head_stride_q
+    a.head_stride_kv = head_dim if head_stride_kv is None else head_stride_kv
+    a.batch, a.heads, a.n_q, a.n_kv, a.head_dim, a.scale = batch, heads, n_q, n_kv, head_dim, scale
+    a.dq, a.ld_dq = dq.ptr, dq.ld
+    a.head_stride_dq = head_dim if head_stride_dq is None else head_stride_dq
+    a.dk, a.dv, a.ld_dkv = dk.ptr, dv.ptr, dk.ld
+    a.head_stride_dkv = head_dim if head_stride_dkv is None else head_stride_dkv
+    need = int(lib.ealdm_attention_bwd_workspace_bytes(C.byref(a)))
+    w = ws.get(need)
+    a.workspace, a.workspace_bytes = w.data_ptr(), w.numel() * 8
+    L.check(lib.ealdm_attention_bwd(C.byref(a), _stream()))
+
+
+def geglu(pre: Act, out: Act) -> Act:
+    lib = L.load()
+    assert pre.c == 2 * out.c and pre.rows == out.rows and pre.dtype == out.dtype
+    L.check(lib.ealdm_geglu(pre.ptr, pre.ld, _dt(pre.dtype), pre.rows, out.c, out.ptr, out.ld, _stream()))
+    return out
+
+
+def geglu_bwd(pre: Act, dout: Act, dpre: Act) -> Act:
+    lib = L.load()
+    assert pre.c == 2 * dout.c == dpre.c and pre.dtype == dout.dtype == dpre.dtype
+    L.check(lib.ealdm_geglu_bwd(pre.ptr, pre.ld, dout.ptr, dout.ld, _dt(pre.dtype), pre.rows, dout.c, dpre.ptr,
+                                dpre.ld, _stream()))
+    return dpre
+
+
+def silu(x: Act, out: Act) -> Act:
+    lib = L.load()
+    assert x.dtype == torch.float32 and x.rows == out.rows and x.c == out.c
+    L.check(lib.ealdm_silu(x.ptr, x.ld, x.rows, x.c, _dt(out.dtype), out.ptr, out.ld, _stream()))
+    return out
+
+
+def silu_bwd(x: Act, dy: Act, dx: Act) -> Act:
+    lib = L.load()
+    assert x.dtype == torch.float32 and dy.dtype == dx.dtype and x.rows == dy.rows == dx.rows
+    L.check(lib.ealdm_silu_bwd(x.ptr, x.ld, dy.ptr, dy.ld, _dt(dy.dtype), x.rows, x.c, dx.ptr, dx.ld, _stream()))
+    return dx
+
+
+def colsum(x: Act, out: torch.Tensor, ws: Workspace, *, segs: int = 1, col0: int = 0,
+           accumulate: bool = True) -> torch.Tensor:
+    """out[s, col0:col0+c] (+)= sum over the rows of segment s of x (segs equal row segments)."""
+    lib = L.load()
+    assert out.dtype == torch.float32 and x.rows % segs == 0
+    o2 = out if out.dim() == 2 else out.view(1, -1)
+    assert o2.shape[0] == segs and o2.stride(1) == 1 and col0 + x.c <= o2.shape[1]
+    w = ws.get(int(lib.ealdm_colsum_workspace_bytes(segs, x.rows // segs, x.c)))
+    L.check(lib.ealdm_colsum(x.ptr, x.ld, _dt(x.dtype), segs, x.rows // segs, x.c, o2.data_ptr() + 4 * col0,
+                             o2.stride(0), 1 if accumulate else 0, w.data_ptr(), _stream()))
+    return out
+
+
+def zero_insert2x(dy: Act, z: Act) -> Act:
+    lib = L.load()
+    assert (z.n, z.h, z.w, z.c) == (dy.n, 2 * dy.h, 2 * dy.w, dy.c) and z.dtype == dy.dtype
+    L.check(lib.ealdm_zero_insert2x(dy.ptr, dy.ld, _dt(dy.dtype), dy.n, dy.h, dy.w, dy.c, z.ptr, z.ld, _stream()))
+    return z
+
+
+def sumpool2x2(dup: Act, dx: Act, *, add: Optional[Act] = None, dx2: Optional[Act] = None) -> Act:
+    lib = L.load()
+    assert (dup.n, dup.h, dup.w, dup.c) == (dx.n, 2 * dx.h, 2 * dx.w, dx.c) and dx.dtype == torch.float32
+    if add is not None:
+        assert add.dtype == torch.float32 and add.rows == dx.rows and add.c == dx.c
+    if dx2 is not None:
+        assert dx2.dtype == dup.dtype
+    L.check(lib.ealdm_sumpool2x2(dup.ptr, dup.ld, _dt(dup.dtype), dx.n, dx.h, dx.w, dx.c,
+                                 None if add is None else add.ptr, 0 if add is None else add.ld, dx.ptr, dx.ld,
+                                 None if dx2 is None else dx2.ptr, 0 if dx2 is None else dx2.ld, _stream()))
+    return dx
+
+
+def cfg_mse_bwd(e_cond, target, w, *, e_uncond=None, cfg_scale=1.0):
+    """Gradients of sum_b w[b] * loss_simple[b] w.r.t. (e_uncond, e_cond)."""
+    lib = L.load()
+    for t in (e_cond, target, e_uncond, w):
+        assert t is None or (t.dtype == torch.float32 and t.is_contiguous())
+    b = e_cond.shape[0]
+    de_c = torch.empty_like(e_cond)
+    de_u = torch.empty_like(e_cond) if e_uncond is not None else None
+    L.check(lib.ealdm_cfg_mse_bwd(_ptr(e_uncond), e_cond.data_ptr(), target.data_ptr(), w.data_ptr(), cfg_scale, b,
+                                  e_cond.numel() // b, _ptr(de_u), de_c.data_ptr(), _stream()))
+    return de_u, de_c
 
 
 def launch_count() -> int:

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define EALDM_ABI_VERSION 1
+#define EALDM_ABI_VERSION 2
 
 typedef void* ealdm_stream_t; /* cudaStream_t */
 
@@ -130,6 +130,7 @@ typedef struct {
   void* workspace;
   int32_t x_f32; /* 1: x is float regardless of dtype (fp32 residual stream -> bf16 GEMM operand) */
   int32_t reserved;
+  float* stats_out; /* optional [n, groups, 2] = (mean, rstd) per (image, group), saved for the backward */
 } ealdm_group_norm_args;
 
 int64_t ealdm_group_norm_workspace_bytes(int64_t n, int64_t hw, int64_t c);
@@ -242,6 +243,169 @@ int ealdm_q_sample(const float* x0, const float* noise, const int64_t* t,
  */
 int ealdm_cfg_mse(const float* e_uncond, const float* e_cond, const float* target, float cfg_scale,
                   int64_t batch, int64_t per_sample, float* loss_simple, ealdm_stream_t stream);
+
+/* ======================================================================================================
+ * Backward pass (LatentDiffusion.p_losses -> loss.backward(), ldm/models/diffusion/ddpm.py:1036-1078;
+ * the reference gets every adjoint below from torch.autograd over the modules cited at the forward
+ * entry points).  Data gradients of conv / linear layers reuse ealdm_conv with transposed (and, for
+ * 3x3, spatially flipped) weights; the entry points here are the remaining adjoints.
+ * Parameter gradients are fp32 and, where stated, ACCUMULATE into the destination (.grad semantics).
+ * ====================================================================================================== */
+
+enum { EALDM_WGRAD_PACKED = 0, EALDM_WGRAD_OIHW = 1 };
+
+/*
+ * Weight gradient of ealdm_conv for one source:
+ *   dw[j, (kh, kw, ci)] = sum_{n, oh, ow} dy[(n, oh, ow), j] * x[n, oh*stride+kh-pad, ow*stride+kw-pad, ci]
+ * layout PACKED: dw[j*ld_dw + (kh*ksize+kw)*c + ci] (the K-major layout of ealdm_conv's `weight`, so the two
+ *   sources of a fused 3x3 + 1x1-skip convolution write disjoint column windows of one matrix);
+ * layout OIHW:   dw[j*ld_dw + (ci*ksize+kh)*ksize+kw] (nn.Conv2d.weight / nn.Linear.weight).
+ * `workspace` holds the per-split partial sums (ealdm_conv_wgrad_workspace_bytes); the splits are added
+ * in a fixed order (no atomics).  A Linear layer is n=1, h=1, w=rows, ksize=1.
+ * Replaces: the weight gradient of nn.Conv2d / nn.Linear (see ealdm_conv for the module list).
+ */
+typedef struct {
+  int32_t dtype; /* storage type of x and dy */
+  int32_t impl;
+  ealdm_conv_src src; /* the forward input with the forward conv's ksize / stride / pad; upsample = 0 */
+  const void* dy;     /* [n*h_out*w_out, ld_dy] */
+  int64_t ld_dy;
+  int64_t n_out;
+  int64_t h_out, w_out;
+  float* dw;
+  int64_t ld_dw;
+  int32_t layout;
+  int32_t accumulate; /* 1: dw += result */
+  void* workspace;
+  int64_t workspace_bytes;
+} ealdm_conv_wgrad_args;
+
+int64_t ealdm_conv_wgrad_workspace_bytes(const ealdm_conv_wgrad_args* a);
+int ealdm_conv_wgrad(const ealdm_conv_wgrad_args* a, ealdm_stream_t stream);
+
+/*
+ * GroupNorm(+SiLU) backward.  dx = d(loss)/dx (+ add + add2, fp32 gradients of parallel branches that join
+ * at x: the residual connection and the UNet skip concatenation); dx2 = optional `dtype` shadow of dx.
+ * dgamma / dbeta accumulate.  `stats` is the forward's stats_out.
+ */
+typedef struct {
+  int32_t dtype; /* type of dy and dx2; of x unless x_f32; of dx unless dx_f32 */
+  int32_t act;
+  const void* x;
+  int64_t n, hw, c, ld_x;
+  int32_t groups;
+  int32_t x_f32;
+  const float* stats;
+  const float* gamma;
+  const float* beta;
+  const void* dy;
+  int64_t ld_dy;
+  const float* add;
+  int64_t ld_add;
+  const float* add2;
+  int64_t ld_add2;
+  void* dx;
+  int64_t ld_dx;
+  int32_t dx_f32;
+  int32_t reserved;
+  void* dx2;
+  int64_t ld_dx2;
+  float* dgamma;
+  float* dbeta;
+  void* workspace; /* ealdm_group_norm_bwd_workspace_bytes(n, hw, c) */
+} ealdm_group_norm_bwd_args;
+
+int64_t ealdm_group_norm_bwd_workspace_bytes(int64_t n, int64_t hw, int64_t c);
+int ealdm_group_norm_bwd(const ealdm_group_norm_bwd_args* a, ealdm_stream_t stream);
+
+/* LayerNorm backward (mean / rstd recomputed from x); same add / dx2 / accumulate conventions. */
+typedef struct {
+  int32_t dtype;
+  int32_t x_f32;
+  const void* x;
+  int64_t rows, c, ld_x;
+  float eps;
+  int32_t dx_f32;
+  const float* gamma;
+  const void* dy;
+  int64_t ld_dy;
+  const float* add;
+  int64_t ld_add;
+  void* dx;
+  int64_t ld_dx;
+  void* dx2;
+  int64_t ld_dx2;
+  float* dgamma;
+  float* dbeta;
+  void* workspace; /* ealdm_layer_norm_bwd_workspace_bytes(rows, c) */
+} ealdm_layer_norm_bwd_args;
+
+int64_t ealdm_layer_norm_bwd_workspace_bytes(int64_t rows, int64_t c);
+int ealdm_layer_norm_bwd(const ealdm_layer_norm_bwd_args* a, ealdm_stream_t stream);
+
+/*
+ * Attention backward: dq, dk, dv of ealdm_attention given out and dout (same addressing as the forward;
+ * dq is laid out like q with head_stride_dq, dk / dv like k / v with head_stride_dkv).
+ */
+typedef struct {
+  int32_t dtype;
+  int32_t impl;
+  const void* q;
+  const void* k;
+  const void* v;
+  const void* out;
+  const void* dout;
+  int64_t ld_q, ld_kv, ld_out, ld_dout;
+  int64_t head_stride_q, head_stride_kv;
+  int64_t batch, heads, n_q, n_kv, head_dim;
+  float scale;
+  int32_t reserved;
+  void* dq;
+  int64_t ld_dq, head_stride_dq;
+  void* dk;
+  void* dv;
+  int64_t ld_dkv, head_stride_dkv;
+  void* workspace;
+  int64_t workspace_bytes;
+} ealdm_attention_bwd_args;
+
+int64_t ealdm_attention_bwd_workspace_bytes(const ealdm_attention_bwd_args* a);
+int ealdm_attention_bwd(const ealdm_attention_bwd_args* a, ealdm_stream_t stream);
+
+/* GEGLU on the natural [value | gate] layout (attention.py:37-44): out = value * gelu_erf(gate), and its
+ * adjoint dpre = [dout * gelu(gate) | dout * value * gelu'(gate)].  pre / dpre are [rows, 2*inner]. */
+int ealdm_geglu(const void* pre, int64_t ld_pre, int32_t dtype, int64_t rows, int64_t inner, void* out,
+                int64_t ld_out, ealdm_stream_t stream);
+int ealdm_geglu_bwd(const void* pre, int64_t ld_pre, const void* dout, int64_t ld_dout, int32_t dtype,
+                    int64_t rows, int64_t inner, void* dpre, int64_t ld_dpre, ealdm_stream_t stream);
+
+/* y = silu(x) and dx = dy * silu'(x) for an fp32 pre-activation x (time_embed / emb_layers MLP). */
+int ealdm_silu(const float* x, int64_t ld_x, int64_t rows, int64_t c, int32_t dtype, void* y, int64_t ld_y,
+               ealdm_stream_t stream);
+int ealdm_silu_bwd(const float* x, int64_t ld_x, const void* dy, int64_t ld_dy, int32_t dtype, int64_t rows,
+                   int64_t c, void* dx, int64_t ld_dx, ealdm_stream_t stream);
+
+/* out[s, 0:c] (+)= column sums of rows [s*rows_per_seg, (s+1)*rows_per_seg) of x: bias gradients (segs = 1)
+ * and the per-image timestep-embedding gradient of a ResBlock (segs = n). */
+int64_t ealdm_colsum_workspace_bytes(int64_t segs, int64_t rows_per_seg, int64_t c);
+int ealdm_colsum(const void* x, int64_t ld_x, int32_t dtype, int64_t segs, int64_t rows_per_seg, int64_t c,
+                 float* out, int64_t ld_out, int32_t accumulate, void* workspace, ealdm_stream_t stream);
+
+/* z[n, 2*oh, 2*ow, :] = dy[n, oh, ow, :], zero elsewhere: the data gradient of a stride-2 convolution is a
+ * stride-1 convolution of z with the flipped weights (openaimodel.py:134-160 backward). */
+int ealdm_zero_insert2x(const void* dy, int64_t ld_dy, int32_t dtype, int64_t n, int64_t h, int64_t w,
+                        int64_t c, void* z, int64_t ld_z, ealdm_stream_t stream);
+/* dx = 2x2 block sums of dup (+ add): adjoint of nearest-2x upsampling (openaimodel.py:116 backward). */
+int ealdm_sumpool2x2(const void* dup, int64_t ld_dup, int32_t dtype, int64_t n, int64_t h, int64_t w,
+                     int64_t c, const float* add, int64_t ld_add, float* dx, int64_t ld_dx, void* dx2,
+                     int64_t ld_dx2, ealdm_stream_t stream);
+
+/* d(loss)/d(e_uncond), d(loss)/d(e_cond) of the p_losses tail (ealdm_cfg_mse) for
+ * loss = sum_b w[b] * loss_simple[b]:  g = 2*w[b]/per_sample * (guided - target);
+ * de_cond = s*g, de_uncond = (1-s)*g (de_uncond NULL when there is no guidance). */
+int ealdm_cfg_mse_bwd(const float* e_uncond, const float* e_cond, const float* target, const float* w,
+                      float cfg_scale, int64_t batch, int64_t per_sample, float* de_uncond, float* de_cond,
+                      ealdm_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -38,7 +38,7 @@ def test_abi_library_exports_every_declared_symbol():
     for sym in declared:
         assert hasattr(lib, sym), sym
     assert sorted(L.EXPORTS) == declared
-    assert lib.ealdm_abi_version() == 1
+    assert lib.ealdm_abi_version() == 2
     # argument validation happens before any CUDA call
     a = L.LayerNormArgs()
     assert lib.ealdm_layer_norm(ctypes.byref(a), None) == -1

@@ -46,7 +46,7 @@ def g(seed):
 
 def test_library_and_device():
     lib = L.load()
-    assert lib.ealdm_abi_version() == 1
+    assert lib.ealdm_abi_version() == 2
     assert lib.ealdm_device_check() == 0, lib.ealdm_last_error()
 
 
