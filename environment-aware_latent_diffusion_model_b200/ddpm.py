@@ -46,6 +46,25 @@ class IdentityFirstStage(nn.Module):
         return x
 
 
+class _CfgMse(torch.autograd.Function):
+    """loss_simple[b] = mean((e_u + s (e_c - e_u) - target)^2) as one kernel each way (ddpm.py:1040-1060)."""
+
+    @staticmethod
+    def forward(ctx, e_u, e_c, target, s):
+        e_c, target = e_c.contiguous(), target.contiguous()
+        e_u = None if e_u is None else e_u.contiguous()
+        ctx.save_for_backward(e_c, target, *(() if e_u is None else (e_u,)))
+        ctx.s = s
+        return ops.cfg_mse(e_c, target, e_uncond=e_u, cfg_scale=s)
+
+    @staticmethod
+    def backward(ctx, w):
+        e_c, target, *rest = ctx.saved_tensors
+        e_u = rest[0] if rest else None
+        de_u, de_c = ops.cfg_mse_bwd(e_c, target, w.float().contiguous(), e_uncond=e_u, cfg_scale=ctx.s)
+        return de_u, de_c, None, None
+
+
 class DiffusionWrapper(nn.Module):
     """ddpm.py:1443-1469"""
 
@@ -249,9 +268,9 @@ class LatentDiffusion(nn.Module):
         target = noise if self.parameterization == "eps" else x_start
         if s != 1.:
             e_u, e_c = self.apply_model(torch.cat([x_noisy] * 2), torch.cat([t] * 2), cond).chunk(2)
-            loss_simple = ops.cfg_mse(e_c.contiguous(), target.contiguous(), e_uncond=e_u.contiguous(), cfg_scale=s)
+            loss_simple = _CfgMse.apply(e_u, e_c, target, s)
         else:
-            loss_simple = ops.cfg_mse(self.apply_model(x_noisy, t, cond).contiguous(), target.contiguous())
+            loss_simple = _CfgMse.apply(None, self.apply_model(x_noisy, t, cond), target, 1.0)
         prefix = "train" if self.training else "val"
         loss_dict = {f"{prefix}/loss_simple": loss_simple.mean()}
         logvar_t = self.logvar.to(self.device)[t]

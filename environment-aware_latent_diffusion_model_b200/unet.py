@@ -296,6 +296,10 @@ class UNetModel(nn.Module):
             "must specify y if and only if the model is class-conditional"
         if not x.is_cuda:
             raise RuntimeError("ealdm_b200.UNetModel runs on CUDA (sm_100a) only; there is no CPU fallback")
+        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            # training step: forward with saved activations + hand-written backward (train.py)
+            from .train import unet_forward_train
+            return unet_forward_train(self, x, timesteps, context)
         if self._engine is None:
             self._engine = UNetEngine(self, self._compute_dtype)
         if self.use_cuda_graph and not torch.cuda.is_current_stream_capturing():

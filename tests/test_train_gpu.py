@@ -1,0 +1,135 @@
+"""Training step (BASELINE.json configs[4]): LatentDiffusion.p_losses forward +
+the hand-written backward, against golden gradients made by the UNMODIFIED reference (autograd through
+its own modules on CPU fp32; oracle/gen_golden_grads.py -> tests/golden/p_losses_grads.pt).
+
+Tolerances (stated here; the north star only fixes the eps tolerances 1e-4 / 1e-2):
+  fp32 mode: every parameter gradient within 5e-4 relative L2 (norm, random projection, and full tensors);
+  bf16 mode: within 5e-2 relative L2 (bf16 GEMM operands in both passes, fp32 accumulation, fp32 residual
+  and gradient streams) -- the same order as torch.autocast(bf16) training.
+"""
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from ealdm_b200 import configs as CFG  # noqa: E402
+from ealdm_b200.ddpm import LatentDiffusion  # noqa: E402
+from oracle import unet as OU  # noqa: E402  (checker only)
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+TOL = {"fp32": 5e-4, "bf16": 5e-2}
+
+
+def gold(name):
+    return torch.load(os.path.join(GOLD, name), weights_only=False)
+
+
+def rel_l2(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def direction(i, shape):
+    return torch.randn(shape, generator=torch.Generator().manual_seed(1000 + i))
+
+
+_ld = {}
+
+
+def make_ld():
+    if "ld" not in _ld:
+        ld = LatentDiffusion(unet_config={"target": "ealdm_b200.unet.UNetModel", "params": dict(CFG.UNET_STDIFF)},
+                             cond_stage_config={"target": "torch.nn.Identity"}, conditioning_key="crossattn",
+                             **CFG.DIFFUSION)
+        sd = OU.synthetic_state_dict(OU.unet_param_shapes(CFG.UNET_STDIFF), seed=2)
+        ld.model.diffusion_model.load_state_dict(sd, strict=True)
+        _ld["ld"] = ld.cuda()
+    return _ld["ld"]
+
+
+def run_step(mode):
+    G = gold("p_losses.pt")
+    ld = make_ld().train()
+    unet = ld.model.diffusion_model.set_compute_dtype(mode)
+    for p in unet.parameters():
+        p.grad = None
+    c2 = G["cond2"].cuda().requires_grad_(True)
+    loss, _ = ld.p_losses(G["x0"].cuda(), c2, G["t"].cuda(), noise=G["noise"].cuda())
+    loss.backward()
+    return ld, unet, loss, c2
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_p_losses_gradients_vs_reference_golden(mode):
+    GG = gold("p_losses_grads.pt")
+    ld, unet, loss, c2 = run_step(mode)
+    tol = TOL[mode]
+    assert abs(float(loss) - float(GG["loss"])) <= tol * abs(float(GG["loss"]))
+    names = [n for n, _ in unet.named_parameters()]
+    assert names == GG["names"]
+    worst_n, worst_p = (0.0, ""), (0.0, "")
+    for i, (name, p) in enumerate(unet.named_parameters()):
+        assert p.grad is not None, f"no gradient for {name}"
+        gr = p.grad.double().cpu()
+        ref_n = GG["norm"][name]
+        en = abs(float(gr.norm()) - ref_n) / max(ref_n, 1e-30)
+        # <g - g_ref, r> ~ N(0, ||g - g_ref||^2) for a unit-variance direction r: 4 sigma
+        ep = abs(float((gr * direction(i, gr.shape).double()).sum()) - GG["proj"][name]) / max(ref_n, 1e-30) / 4.0
+        worst_n = max(worst_n, (en, name))
+        worst_p = max(worst_p, (ep, name))
+    print(f"train {mode}: worst |norm| error {worst_n[0]:.3e} ({worst_n[1]}), worst projection error "
+          f"{worst_p[0]:.3e} ({worst_p[1]})")
+    assert worst_n[0] < tol, worst_n
+    assert worst_p[0] < tol, worst_p
+    sd = dict(unet.named_parameters())
+    worst_f = (0.0, "")
+    for name, ref in GG["full"].items():
+        worst_f = max(worst_f, (rel_l2(sd[name].grad, ref), name))
+    print(f"train {mode}: worst full-tensor gradient rel_l2 {worst_f[0]:.3e} ({worst_f[1]})")
+    assert worst_f[0] < tol, worst_f
+    e = rel_l2(c2.grad, GG["dcond"])
+    print(f"train {mode}: d(loss)/d(conditioning) rel_l2 {e:.3e}")
+    assert e < tol
+    ld.eval()
+
+
+def test_backward_is_deterministic_and_accumulates():
+    ld, unet, loss, _ = run_step("bf16")
+    g1 = {n: p.grad.clone() for n, p in unet.named_parameters()}
+    ld, unet, loss2, _ = run_step("bf16")
+    assert float(loss) == float(loss2)
+    for n, p in unet.named_parameters():
+        assert torch.equal(p.grad, g1[n]), n
+    # a second backward without zeroing accumulates (PyTorch .grad semantics)
+    G = gold("p_losses.pt")
+    l3, _ = ld.p_losses(G["x0"].cuda(), G["cond2"].cuda(), G["t"].cuda(), noise=G["noise"].cuda())
+    l3.backward()
+    for n, p in list(unet.named_parameters())[::37]:
+        assert rel_l2(p.grad, 2 * g1[n]) < 1e-6, n
+    ld.eval()
+
+
+def test_adamw_steps_reduce_the_loss():
+    """Three AdamW steps (the reference's optimizer, ddpm.py:1409-1431) on one fixed batch."""
+    G = gold("p_losses.pt")
+    ld = make_ld().train()
+    unet = ld.model.diffusion_model.set_compute_dtype("bf16")
+    saved = {n: p.detach().clone() for n, p in unet.named_parameters()}
+    opt = torch.optim.AdamW(unet.parameters(), lr=2e-5)
+    x0, c2, t, noise = G["x0"].cuda(), G["cond2"].cuda(), G["t"].cuda(), G["noise"].cuda()
+    losses = []
+    for _ in range(4):
+        opt.zero_grad(set_to_none=True)
+        loss, _ = ld.p_losses(x0, c2, t, noise=noise)
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+    print("losses:", losses)
+    assert losses[-1] < losses[0]
+    with torch.no_grad():
+        for n, p in unet.named_parameters():
+            p.copy_(saved[n])
+    unet.invalidate_packed()
+    ld.eval()
