@@ -168,8 +168,127 @@ def cpu_baseline_leg(budget_s=25.0):
 
 
 # ------------------------------------------------------------------------------------------------------
+def run_train(args):
+    """--workload train: BASELINE.json configs[4] -- one optimisation step of LatentDiffusion on the stdiff UNet:
+    q_sample, UNet forward at 2B (classifier-free guidance inside the loss, ddpm.py:1040-1044), eps loss, the
+    hand-written backward, the bucketed NCCL gradient all-reduce overlapped with it, AdamW (the reference's
+    optimizer, ddpm.py:1409-1431).  Batch 32 per GPU, bf16 operands / fp32 accumulation and master weights."""
+    import torch
+    import torch.distributed as dist
+
+    from ealdm_b200 import configs as CFG, ops
+    from ealdm_b200.ddpm import LatentDiffusion
+    from ealdm_b200.synthetic import init_synthetic_
+    from ealdm_b200.train import FusedTrainStep
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch if args.batch != 64 else 32
+    ld = LatentDiffusion(unet_config={"target": "ealdm_b200.unet.UNetModel", "params": dict(CFG.UNET_STDIFF)},
+                         cond_stage_config={"target": "torch.nn.Identity"}, conditioning_key="crossattn",
+                         **CFG.DIFFUSION).to(dev).train()
+    unet = ld.model.diffusion_model
+    init_synthetic_(unet, seed=0)
+    unet.set_compute_dtype("bf16")
+    fused = FusedTrainStep(ld, use_graph=not args.no_graph, bucket_mb=64.0)
+    gb = fused.buckets
+    lr = 1.0e-6 * world * B      # main.py:741-745: accumulate * ngpu * bs * base_lr
+    opt = torch.optim.AdamW(unet.parameters(), lr=lr, fused=True)
+    g = torch.Generator().manual_seed(100 + rank)
+    x0_h = torch.randn(B, 4, 32, 32, generator=g).pin_memory()
+    c2_h = torch.randn(2 * B, 4, 512, generator=g).pin_memory()
+    t = torch.randint(0, 1000, (B,), generator=g).to(dev)
+    noise = torch.randn(B, 4, 32, 32, generator=g).to(dev)
+    phases = {"fwd(+bwd if fused)": [], "bwd/allreduce": [], "opt": []}
+
+    def step(record=False):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        x0 = x0_h.to(dev, non_blocking=True)
+        c2 = c2_h.to(dev, non_blocking=True)
+        gb.zero_()
+        ev[0].record()
+        if args.autograd:           # the drop-in path: p_losses under torch.autograd
+            loss, _ = ld.p_losses(x0, c2, t, noise=noise)
+            ev[1].record()
+            loss.backward()
+        else:                       # the fused step (one CUDA graph unless --no-graph)
+            loss = fused(x0, c2, t, noise)
+            ev[1].record()
+        gb.finish()
+        ev[2].record()
+        opt.step()
+        ev[3].record()
+        lv = float(loss)            # device -> host read of the step's result
+        if record:
+            torch.cuda.synchronize()
+            for k, (a, b) in zip(phases.keys(), ((0, 1), (1, 2), (2, 3))):
+                phases[k].append(ev[a].elapsed_time(ev[b]))
+        return lv
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    l0 = ops.launch_count()
+    for _ in range(max(args.warmup, 3)):
+        step()
+    launches = (ops.launch_count() - l0) // max(args.warmup, 3)
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        lv = step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        tt = torch.tensor([ms], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+    clk = clocks.stop() if rank == 0 else None
+    for _ in range(2):
+        step(record=True)
+    ms_per_step = ms / args.steps
+    peaks = load_peaks()
+    model_tf = 3 * 2 * B * CFG.UNET_STDIFF_GFLOP_PER_SAMPLE / 1e3     # fwd + dgrad + wgrad, per GPU per step
+    if rank == 0:
+        line = {"metric": "training samples/sec (UNet fwd+bwd, eps loss, AdamW)", "value": B * world / (ms_per_step * 1e-3),
+                "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": "stdiff_cin-ldm-vq-f8 training step, batch 32 per GPU (UNet batch 64), CFG inside "
+                                       "the loss, AdamW, bucketed NCCL gradient all-reduce (BASELINE.json configs[4])",
+                           "batch_per_gpu": B, "global_batch": B * world, "lr": lr,
+                           "step": "autograd (p_losses + loss.backward())" if args.autograd else
+                                   ("fused step, one CUDA graph" if not args.no_graph else "fused step, eager launches"),
+                           "parallelism": f"data-parallel x{world}, 64 MiB gradient buckets"},
+                "clocks": clk, "loss": lv, "gpu_launches": int(launches * args.steps), "launches_per_step": int(launches),
+                "phases_ms": {k: sum(v) / len(v) for k, v in phases.items()},
+                "model_tflops_per_gpu": model_tf / (ms_per_step * 1e-3),
+                "frac_of_sustained_peak": model_tf / (ms_per_step * 1e-3) / peaks["bf16_sustained"],
+                "e2e": {"value": B * world / (ms_per_step * 1e-3), "unit": "samples/s",
+                        "h2d_bytes_per_step": (x0_h.numel() + c2_h.numel()) * 4, "d2h_bytes_per_step": 4,
+                        "note": "the timed step already copies its batch from pinned host memory and reads the loss back"}}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--workload", default="sample", choices=["sample", "train"],
+                    help="sample: the headline metric (default); train: BASELINE.json configs[4]")
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
@@ -177,12 +296,15 @@ def main():
     ap.add_argument("--batch", type=int, default=64, help="latent samples per GPU per step")
     ap.add_argument("--ddim-steps", type=int, default=50)
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
+    ap.add_argument("--autograd", action="store_true", help="train workload: p_losses under torch.autograd")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ncu-window", action="store_true",
                     help="cudaProfilerStart/Stop around the timed region (for `ncu --profile-from-start off`)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "train":
+        return run_train(args)
 
     import torch
     import torch.distributed as dist

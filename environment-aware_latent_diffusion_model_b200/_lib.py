@@ -70,7 +70,7 @@ class AttentionArgs(C.Structure):
                 ("head_stride_q", C.c_int64), ("head_stride_kv", C.c_int64), ("batch", C.c_int64),
                 ("heads", C.c_int64), ("n_q", C.c_int64), ("n_kv", C.c_int64),
                 ("head_dim", C.c_int64), ("scale", C.c_float), ("reserved", C.c_int32),
-                ("out", C.c_void_p), ("ld_out", C.c_int64)]
+                ("out", C.c_void_p), ("ld_out", C.c_int64), ("lse", C.c_void_p)]
 
 
 class DdimStepArgs(C.Structure):
@@ -115,7 +115,8 @@ class AttentionBwdArgs(C.Structure):
                 ("heads", C.c_int64), ("n_q", C.c_int64), ("n_kv", C.c_int64), ("head_dim", C.c_int64),
                 ("scale", C.c_float), ("reserved", C.c_int32), ("dq", C.c_void_p), ("ld_dq", C.c_int64),
                 ("head_stride_dq", C.c_int64), ("dk", C.c_void_p), ("dv", C.c_void_p), ("ld_dkv", C.c_int64),
-                ("head_stride_dkv", C.c_int64), ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64)]
+                ("head_stride_dkv", C.c_int64), ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
+                ("lse", C.c_void_p)]
 
 
 class EaldmError(RuntimeError):

@@ -356,6 +356,7 @@ extern "C" int ealdm_attention(const ealdm_attention_args* a, ealdm_stream_t str
   if (a->dtype == EALDM_BF16 && a->head_dim == 32 && a->n_kv > attn::MAX_SMALL_KV &&
       a->impl != EALDM_IMPL_SIMT)
     return attn::launch_flash_mma(a, st);
+  EALDM_REQUIRE(a->lse == nullptr, "attention: lse is only produced by the bf16 tensor-core path (head_dim 32)");
   if (a->impl != EALDM_IMPL_SIMT && attn::xattn_bf16_ok(a)) return attn::launch_xattn_bf16(a, st);
   if (a->dtype == EALDM_F32) {
     return a->head_dim == 32 ? attn::launch_t<float, 32>(a, st) : attn::launch_t<float, 64>(a, st);

@@ -209,6 +209,13 @@ static int run(const ealdm_attention_bwd_args* a, cudaStream_t st) {
 }  // namespace attn_bwd
 }  // namespace ealdm
 
+namespace ealdm {
+namespace attn {
+bool bwd_mma_ok(const ealdm_attention_bwd_args* a);                   // attention_bwd_mma.cu
+int launch_bwd_mma(const ealdm_attention_bwd_args* a, cudaStream_t st);
+}  // namespace attn
+}  // namespace ealdm
+
 using namespace ealdm;
 
 extern "C" int64_t ealdm_attention_bwd_workspace_bytes(const ealdm_attention_bwd_args* a) {
@@ -230,6 +237,9 @@ extern "C" int ealdm_attention_bwd(const ealdm_attention_bwd_args* a, ealdm_stre
                 "attention_bwd: pitches and head strides must be multiples of 4");
   EALDM_REQUIRE(a->workspace_bytes >= ealdm_attention_bwd_workspace_bytes(a), "attention_bwd: workspace too small");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (attn::bwd_mma_ok(a)) return attn::launch_bwd_mma(a, st);
+  EALDM_REQUIRE(a->impl != EALDM_IMPL_TCGEN05,
+                "attention_bwd: the tensor-core path needs bf16, head_dim 32, lse, n_q and n_kv multiples of 64");
   if (a->dtype == EALDM_F32)
     return a->head_dim == 32 ? attn_bwd::run<float, 32>(a, st) : attn_bwd::run<float, 64>(a, st);
   EALDM_REQUIRE(a->dtype == EALDM_BF16, "attention_bwd: bad dtype");

@@ -4,47 +4,10 @@
 // softmax in the exp2 domain.  At d = 32 the kernel is bound by exp throughput (128 tensor FLOPs per
 // exp), not by the tensor pipe, which is why it does not use tcgen05.
 #include "common.cuh"
+#include "mma.cuh"
 
 namespace ealdm {
 namespace attn {
-
-constexpr int KV_TILE = 64;
-constexpr int ROW_PAD = 40;  // bf16 per shared row (80 B): conflict-free ldmatrix
-
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool pred) {
-  const uint32_t s = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
-  const int sz = pred ? 16 : 0;  // src-size 0 => zero fill
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(sz)
-               : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* smem) {
-  const uint32_t s = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
-               : "r"(s));
-}
-__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* smem) {
-  const uint32_t s = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
-               : "r"(s));
-}
-__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0,
-                                         uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
-      "{%0,%1,%2,%3};"
-      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
-  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<uint32_t*>(&t);
-}
 
 template <int NWARPS>
 __global__ void __launch_bounds__(NWARPS * 32)
@@ -192,17 +155,12 @@ flash_mma_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const b
 //   * softmax scale, log2(e) and the running max folded into ONE FFMA feeding ex2: p = 2^(s*c - m*c);
 //   * the row sums are produced by the tensor core: the P.V MMA gets a fifth 8-column tile whose
 //     column 0 is all ones, so l accumulates (and is rescaled) exactly like O.
-__device__ __forceinline__ float ex2_approx(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
 
 template <int NWARPS>
 __global__ void __launch_bounds__(NWARPS * 32)
 flash_mma_even_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const bf16* __restrict__ v,
                       long long ld_q, long long ld_kv, long long hs_q, long long hs_kv, int n_q, int n_kv,
-                      float scale_log2, bf16* __restrict__ out, long long ld_out) {
+                      float scale_log2, bf16* __restrict__ out, long long ld_out, float* __restrict__ lse) {
   __shared__ __align__(16) bf16 Ks[2][KV_TILE][ROW_PAD];
   __shared__ __align__(16) bf16 Vs[2][KV_TILE][ROW_PAD];
   constexpr int NT = NWARPS * 32;
@@ -308,6 +266,12 @@ flash_mma_even_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, co
   const float l0 = __shfl_sync(0xffffffffu, o[4][0], lane & ~3);
   const float l1 = __shfl_sync(0xffffffffu, o[4][2], lane & ~3);
   const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+  if (lse != nullptr && (lane & 3) == 0) {
+    // log2-domain log-sum-exp of the scaled scores, saved for the backward: p_ij = 2^(s_ij * c - lse_i)
+    float* lp = lse + (static_cast<long long>(b) * gridDim.y + h) * n_q;
+    if (r0 < n_q) lp[r0] = fmaf(m0, scale_log2, log2f(l0));
+    if (r1 < n_q) lp[r1] = fmaf(m1, scale_log2, log2f(l1));
+  }
   bf16* ob = out + static_cast<long long>(b) * n_q * ld_out + h * 32;
 #pragma unroll
   for (int nt = 0; nt < 4; ++nt) {
@@ -331,19 +295,21 @@ int launch_flash_mma(const ealdm_attention_args* a, cudaStream_t st) {
   const bf16* k = reinterpret_cast<const bf16*>(a->k);
   const bf16* v = reinterpret_cast<const bf16*>(a->v);
   bf16* o = reinterpret_cast<bf16*>(a->out);
+  EALDM_REQUIRE(a->lse == nullptr || (a->n_kv % KV_TILE == 0 && a->scale > 0.f),
+                "attention(mma): lse output needs n_kv %% 64 == 0");
   if (a->n_kv % KV_TILE == 0 && a->scale > 0.f) {
     if (a->n_q > 64) {
       dim3 grid(static_cast<unsigned>(ceil_div(a->n_q, 128)), static_cast<unsigned>(a->heads),
                 static_cast<unsigned>(a->batch));
       flash_mma_even_kernel<8><<<grid, 256, 0, st>>>(q, k, v, a->ld_q, a->ld_kv, a->head_stride_q,
                                                      a->head_stride_kv, (int)a->n_q, (int)a->n_kv,
-                                                     scale_log2, o, a->ld_out);
+                                                     scale_log2, o, a->ld_out, a->lse);
     } else {
       dim3 grid(static_cast<unsigned>(ceil_div(a->n_q, 64)), static_cast<unsigned>(a->heads),
                 static_cast<unsigned>(a->batch));
       flash_mma_even_kernel<4><<<grid, 128, 0, st>>>(q, k, v, a->ld_q, a->ld_kv, a->head_stride_q,
                                                      a->head_stride_kv, (int)a->n_q, (int)a->n_kv,
-                                                     scale_log2, o, a->ld_out);
+                                                     scale_log2, o, a->ld_out, a->lse);
     }
   } else if (a->n_q > 64) {
     dim3 grid(static_cast<unsigned>(ceil_div(a->n_q, 128)), static_cast<unsigned>(a->heads),

@@ -410,46 +410,100 @@ silu_bwd_kernel(const TX* __restrict__ x, long long ld_x, const TD* __restrict__
 }
 
 // ---- column sums per segment: out[s][col] (+)= sum over the segment's rows of x[row][col] -------------------
+static void colsum_chunking(long long segs, long long rows_per_seg, int* rows_per_cta, long long* chunks) {
+  long long ch = ceil_div(592, segs);   // ~4 CTAs per SM over all segments
+  const long long max_chunks = ceil_div(rows_per_seg, 32);
+  if (ch > max_chunks) ch = max_chunks;
+  if (ch < 1) ch = 1;
+  const int rpc = static_cast<int>(ceil_div(rows_per_seg, ch));
+  *rows_per_cta = rpc;
+  *chunks = ceil_div(rows_per_seg, rpc);
+}
+
+// 4 consecutive columns per thread (16 B of fp32 / 8 B of bf16 per load), 8 independent loads in flight
 template <typename T>
 __global__ void __launch_bounds__(NT)
 colsum_partial_kernel(const T* __restrict__ x, long long ld, long long rows_per_seg, int c, int rows_per_cta,
                       float* __restrict__ part) {
-  __shared__ float red[NT];
+  __shared__ float4 red[NT];
   const int t = threadIdx.x;
   const int seg = blockIdx.y;
-  const int lanes_c = c < NT ? c : NT;
-  const int row_lanes = NT / lanes_c;
-  const int tc = t % lanes_c, tr = t / lanes_c;
+  const int vpr = (c + 3) >> 2;                 // vec4 per row (the last one may be ragged)
+  const int lanes_v = vpr < NT ? vpr : NT;
+  const int row_lanes = NT / lanes_v;
+  const int tv = t % lanes_v, tr = t / lanes_v;
   const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_cta;
   const long long r1 = min(r0 + rows_per_cta, rows_per_seg);
   const T* xb = x + static_cast<long long>(seg) * rows_per_seg * ld;
   float* out = part + (static_cast<long long>(seg) * gridDim.x + blockIdx.x) * c;
-  for (int c0 = 0; c0 < c; c0 += lanes_c) {
-    const int col = c0 + tc;
-    float s = 0.f;
-    if (tr < row_lanes && col < c)
-      for (long long r = r0 + tr; r < r1; r += row_lanes) s += to_f32(xb[r * ld + col]);
+  const bool vec_ok = (c & 3) == 0;             // host guarantees ld % 4 == 0 and aligned base in that case
+  for (int v0 = 0; v0 < vpr; v0 += lanes_v) {
+    const int v = v0 + tv;
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+    if (tr < row_lanes && v < vpr) {
+      const int col = v * 4;
+      if (vec_ok) {
+        constexpr int U = 8;
+        for (long long r = r0 + tr; r < r1; r += static_cast<long long>(U) * row_lanes) {
+          Vec4<T> q[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const long long rr = r + static_cast<long long>(u) * row_lanes;
+            if (rr < r1) q[u].load(xb + rr * ld + col);
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            if (r + static_cast<long long>(u) * row_lanes < r1) {
+              float f[4];
+              q[u].get(f);
+              s[0] += f[0]; s[1] += f[1]; s[2] += f[2]; s[3] += f[3];
+            }
+          }
+        }
+      } else {
+        for (long long r = r0 + tr; r < r1; r += row_lanes)
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (col + j < c) s[j] += to_f32(xb[r * ld + col + j]);
+      }
+    }
     if (row_lanes > 1) {
       __syncthreads();
-      red[t] = s;
+      red[t] = make_float4(s[0], s[1], s[2], s[3]);
       __syncthreads();
-      if (tr == 0 && col < c)
-        for (int k = 1; k < row_lanes; ++k) s += red[k * lanes_c + tc];
+      if (tr == 0 && v < vpr)
+        for (int k = 1; k < row_lanes; ++k) {
+          const float4 e = red[k * lanes_v + tv];
+          s[0] += e.x; s[1] += e.y; s[2] += e.z; s[3] += e.w;
+        }
     }
-    if (tr == 0 && col < c) out[col] = s;
+    if (tr == 0 && v < vpr) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (v * 4 + j < c) out[v * 4 + j] = s[j];
+    }
   }
 }
+// 32 columns x 8 chunk lanes per CTA; lanes are combined in a fixed order
 __global__ void __launch_bounds__(NT)
 colsum_final_kernel(const float* __restrict__ part, int chunks, int c, float* __restrict__ out, long long ld_out,
                     int accumulate) {
-  const int col = blockIdx.x * NT + threadIdx.x;
+  __shared__ float red[8][32];
+  const int tc = threadIdx.x & 31, tk = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + tc;
   const int seg = blockIdx.y;
-  if (col >= c) return;
   const float* p = part + static_cast<long long>(seg) * chunks * c;
   float s = 0.f;
-  for (int k = 0; k < chunks; ++k) s += p[static_cast<long long>(k) * c + col];
-  float* o = out + static_cast<long long>(seg) * ld_out + col;
-  *o = accumulate ? *o + s : s;
+  if (col < c)
+    for (int k = tk; k < chunks; k += 8) s += p[static_cast<long long>(k) * c + col];
+  red[tk][tc] = s;
+  __syncthreads();
+  if (tk == 0 && col < c) {
+#pragma unroll
+    for (int k = 1; k < 8; ++k) s += red[k][tc];
+    float* o = out + static_cast<long long>(seg) * ld_out + col;
+    *o = accumulate ? *o + s : s;
+  }
 }
 
 // ---- resampling adjoints ------------------------------------------------------------------------------------
@@ -704,17 +758,19 @@ extern "C" int64_t ealdm_colsum_workspace_bytes(int64_t segs, int64_t rows_per_s
   if (segs <= 0 || rows_per_seg <= 0 || c <= 0) return 0;
   int ppc;
   long long chunks;
-  bwd::chunking(segs, rows_per_seg, &ppc, &chunks);
+  bwd::colsum_chunking(segs, rows_per_seg, &ppc, &chunks);
   return segs * chunks * c * 4;
 }
 
 extern "C" int ealdm_colsum(const void* x, int64_t ld_x, int32_t dtype, int64_t segs, int64_t rows_per_seg, int64_t c,
                             float* out, int64_t ld_out, int32_t accumulate, void* workspace, ealdm_stream_t stream) {
   EALDM_REQUIRE(x && out && workspace && segs > 0 && segs <= 65535 && rows_per_seg > 0 && c > 0, "colsum: bad arguments");
+  EALDM_REQUIRE(c % 4 != 0 || (ld_x % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & (dtype == EALDM_F32 ? 15 : 7)) == 0),
+                "colsum: with c %% 4 == 0 the rows must be 4-element aligned");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int ppc;
   long long chunks;
-  bwd::chunking(segs, rows_per_seg, &ppc, &chunks);
+  bwd::colsum_chunking(segs, rows_per_seg, &ppc, &chunks);
   dim3 grid(static_cast<unsigned>(chunks), static_cast<unsigned>(segs));
   float* part = reinterpret_cast<float*>(workspace);
   if (dtype == EALDM_F32)
@@ -724,7 +780,7 @@ extern "C" int ealdm_colsum(const void* x, int64_t ld_x, int32_t dtype, int64_t 
     bwd::colsum_partial_kernel<bf16><<<grid, bwd::NT, 0, st>>>(reinterpret_cast<const bf16*>(x), ld_x, rows_per_seg,
                                                                (int)c, ppc, part);
   EALDM_LAUNCH_CHECK();
-  dim3 g2(static_cast<unsigned>(ceil_div(c, bwd::NT)), static_cast<unsigned>(segs));
+  dim3 g2(static_cast<unsigned>(ceil_div(c, 32)), static_cast<unsigned>(segs));
   bwd::colsum_final_kernel<<<g2, bwd::NT, 0, st>>>(part, static_cast<int>(chunks), (int)c, out, ld_out, accumulate);
   EALDM_LAUNCH_CHECK();
   return 0;

@@ -187,7 +187,8 @@ def layer_norm(x: Act, gamma: torch.Tensor, beta: torch.Tensor, eps: float, out:
 
 def attention(q: Act, k: Act, v: Act, out: Act, *, batch: int, heads: int, head_dim: int, n_q: int,
               n_kv: int, scale: float, head_stride_q: Optional[int] = None,
-              head_stride_kv: Optional[int] = None, impl: int = L.IMPL_AUTO) -> Act:
+              head_stride_kv: Optional[int] = None, impl: int = L.IMPL_AUTO,
+              lse: Optional[torch.Tensor] = None) -> Act:
     """q/k/v are column windows into [batch*n, ld] buffers; head h of q starts at column h*head_stride_q."""
     lib = L.load()
     a = L.AttentionArgs()
@@ -202,6 +203,9 @@ def attention(q: Act, k: Act, v: Act, out: Act, *, batch: int, heads: int, head_
     a.scale = scale
     assert out.rows == q.rows and out.c == heads * head_dim and out.dtype == q.dtype
     a.out, a.ld_out = out.ptr, out.ld
+    if lse is not None:
+        assert lse.dtype == torch.float32 and lse.is_contiguous() and lse.numel() == batch * heads * n_q
+        a.lse = lse.data_ptr()
     L.check(lib.ealdm_attention(C.byref(a), _stream()))
     return out
 
@@ -406,7 +410,8 @@ def layer_norm_bwd(x: Act, dy: Act, gamma: torch.Tensor, eps: float, dx: Act, ws
 def attention_bwd(q: Act, k: Act, v: Act, out: Act, dout: Act, dq: Act, dk: Act, dv: Act, ws: Workspace, *,
                   batch: int, heads: int, head_dim: int, n_q: int, n_kv: int, scale: float,
                   head_stride_q: Optional[int] = None, head_stride_kv: Optional[int] = None,
-                  head_stride_dq: Optional[int] = None, head_stride_dkv: Optional[int] = None) -> None:
+                  head_stride_dq: Optional[int] = None, head_stride_dkv: Optional[int] = None,
+                  lse: Optional[torch.Tensor] = None, impl: int = L.IMPL_AUTO) -> None:
     lib = L.load()
     a = L.AttentionBwdArgs()
     a.dtype = _dt(q.dtype)
@@ -420,6 +425,10 @@ def attention_bwd(q: Act, k: Act, v: Act, out: Act, dout: Act, dq: Act, dk: Act,
     a.head_stride_dq = head_dim if head_stride_dq is None else head_stride_dq
     a.dk, a.dv, a.ld_dkv = dk.ptr, dv.ptr, dk.ld
     a.head_stride_dkv = head_dim if head_stride_dkv is None else head_stride_dkv
+    a.impl = impl
+    if lse is not None:
+        assert lse.dtype == torch.float32 and lse.is_contiguous() and lse.numel() == batch * heads * n_q
+        a.lse = lse.data_ptr()
     need = int(lib.ealdm_attention_bwd_workspace_bytes(C.byref(a)))
     w = ws.get(need)
     a.workspace, a.workspace_bytes = w.data_ptr(), w.numel() * 8

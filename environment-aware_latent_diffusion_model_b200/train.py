@@ -188,8 +188,11 @@ class UNetTrainEngine(UNetEngine):
             s["a1"] = ops.layer_norm(t, tb["ln1"][0], tb["ln1"][1], 1e-5, self._new(n, h, w, C_))
             s["qkv"] = ops.linear(s["a1"], tb["qkv"], self._new(n, h, w, 3 * C_))
             q = s["qkv"]
+            # the tensor-core backward re-creates the probabilities from the forward's log-sum-exp
+            s["lse"] = (torch.empty((n, heads, tok), dtype=f32, device=self.dev)
+                        if (self.dt == torch.bfloat16 and dh == 32 and tok % 64 == 0) else None)
             s["o"] = ops.attention(q.cols(0, C_), q.cols(C_, C_), q.cols(2 * C_, C_), self._new(n, h, w, C_), batch=n,
-                                   heads=heads, head_dim=dh, n_q=tok, n_kv=tok, scale=dh ** -0.5)
+                                   heads=heads, head_dim=dh, n_q=tok, n_kv=tok, scale=dh ** -0.5, lse=s["lse"])
             s["t1"] = ops.linear(s["o"], tb["o1"].w, self._new(n, h, w, C_, f32), bias=tb["o1"].b, residual=t)
             s["a2"] = ops.layer_norm(s["t1"], tb["ln2"][0], tb["ln2"][1], 1e-5, self._new(n, h, w, C_))
             s["q2"] = ops.linear(s["a2"], tb["q2"], self._new(n, h, w, C_))
@@ -252,7 +255,7 @@ class UNetTrainEngine(UNetEngine):
                 dqkv = nd(3 * C_)
                 ops.attention_bwd(q.cols(0, C_), q.cols(C_, C_), q.cols(2 * C_, C_), s["o"], do, dqkv.cols(0, C_),
                                   dqkv.cols(C_, C_), dqkv.cols(2 * C_, C_), ws, batch=n, heads=heads, head_dim=dh,
-                                  n_q=tok, n_kv=tok, scale=dh ** -0.5)
+                                  n_q=tok, n_kv=tok, scale=dh ** -0.5, lse=s["lse"])
                 for j, lin in enumerate((mod.attn1.to_q, mod.attn1.to_k, mod.attn1.to_v)):
                     ops.linear_wgrad(s["a1"], dqkv.cols(j * C_, C_), _grad2d(lin.weight), ws)
                 da1 = ops.linear(dqkv, tb["wd_qkv"], nd(C_))
@@ -455,6 +458,9 @@ class UNetTrainEngine(UNetEngine):
         g = self._gdual(n, H, W, h_last.f.c)
         ops.group_norm_bwd(h_last.f, dhn, s["st_out"], self.out_norm[0], self.out_norm[1], g.f, ws, silu=True,
                            dx2=self._out2(g), dgamma=_grad1d(m.out[0].weight), dbeta=_grad1d(m.out[0].bias))
+        hook = getattr(m, "grad_ready_hook", None)   # parallel.GradBuckets: overlap the all-reduce with the backward
+        if hook is not None:
+            hook("head", 0)
 
         def window(dl: Dual, c0, c):
             return Dual(dl.f.cols(c0, c), dl.f.cols(c0, c) if dl.h is dl.f else dl.h.cols(c0, c))
@@ -477,6 +483,8 @@ class UNetTrainEngine(UNetEngine):
                 g = run_block(t0, t1, g, dskip[n_in - 1])
             else:
                 g = run_block(t0, t1, g, dskip[idx - 1] if idx > 0 else None)
+            if hook is not None:
+                hook(kind, idx)
         dx = None
         if need_dx and g is not None:
             dx = torch.empty((n, s["cin"], H, W), dtype=f32, device=dev)
@@ -551,3 +559,76 @@ def unet_forward_train(model: UNetModel, x, timesteps, context):
     engine = UNetTrainEngine(model, model._compute_dtype)
     anchor = next(p for p in model.parameters() if p.requires_grad)
     return _UNetFunction.apply(anchor, x, context, timesteps, engine)
+
+
+class FusedTrainStep:
+    """One optimisation step's forward + backward of `LatentDiffusion.p_losses` (ddpm.py:1036-1078) as a straight
+    sequence of libealdm_b200 launches -- q_sample, UNet forward at 2B, guided-eps MSE, its adjoint, UNet backward,
+    including the per-step weight packing -- with no autograd graph in between, so that the WHOLE step can be
+    captured once and replayed as one CUDA graph (~1800 launches; eager Python issue time would otherwise be a
+    third of the step).  Gradients accumulate into the flat buffer of `parallel.GradBuckets` (created here);
+    call `buckets.zero_()` before and `buckets.finish()` after the step (finish() runs the data-parallel
+    all-reduce: overlapped with the backward in eager mode, after the replay in graph mode)."""
+
+    def __init__(self, ld, use_graph: bool = True, bucket_mb: float = 64.0, group=None):
+        from .parallel import GradBuckets
+        self.ld = ld
+        self.unet: UNetModel = ld.model.diffusion_model
+        self.use_graph = use_graph
+        self.buckets = GradBuckets(self.unet, bucket_mb=bucket_mb, group=group)
+        self._graphs = {}
+        dev = ld.betas.device
+        self._logvar = ld.logvar.detach().to(dev).float()
+
+    def _run(self, x0, c2, t, noise):
+        ld, unet = self.ld, self.unet
+        B = x0.shape[0]
+        engine = UNetTrainEngine(unet, unet._compute_dtype)
+        x_noisy = ops.q_sample(x0, noise, t, ld.sqrt_alphas_cumprod, ld.sqrt_one_minus_alphas_cumprod)
+        target = noise if ld.parameterization == "eps" else x0
+        s = float(ld.unconditional_guidance_scale)
+        if s != 1.0:
+            eps = engine.forward(torch.cat([x_noisy] * 2), torch.cat([t] * 2), c2)
+            e_u, e_c = eps[:B], eps[B:]
+        else:
+            e_u, e_c = None, engine.forward(x_noisy, t, c2)
+        loss_simple = ops.cfg_mse(e_c, target, e_uncond=e_u, cfg_scale=s)
+        logvar_t = self._logvar[t]
+        lvlb_t = ld.lvlb_weights[t]
+        loss = ld.l_simple_weight * (loss_simple / torch.exp(logvar_t) + logvar_t).mean() \
+            + ld.original_elbo_weight * (lvlb_t * loss_simple).mean()
+        w = ((ld.l_simple_weight / torch.exp(logvar_t) + ld.original_elbo_weight * lvlb_t) / B).float().contiguous()
+        de_u, de_c = ops.cfg_mse_bwd(e_c, target, w, e_uncond=e_u, cfg_scale=s)
+        engine.backward(de_c if de_u is None else torch.cat([de_u, de_c]))
+        return loss
+
+    @torch.no_grad()
+    def __call__(self, x0, cond, t, noise):
+        """x0 [B,4,H,W], cond [2B,T,D] = cat([c_neg, c]) (or [B,T,D] without guidance), t [B] int64, noise like x0.
+        Returns the loss (a device tensor); parameter gradients are accumulated."""
+        x0, noise = x0.float().contiguous(), noise.float().contiguous()
+        cond, t = cond.float().contiguous(), t.to(torch.int64).contiguous()
+        if not self.use_graph:
+            return self._run(x0, cond, t, noise)
+        key = (tuple(x0.shape), tuple(cond.shape), self.unet._compute_dtype)
+        ent = self._graphs.get(key)
+        if ent is None:
+            sx, sc, st, sn = x0.clone(), cond.clone(), t.clone(), noise.clone()
+            hook, self.unet.grad_ready_hook = self.unet.grad_ready_hook, None   # no collectives inside the capture
+            keep = self.buckets.flat.clone()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):     # eager warm-up: lazy kernel attributes, allocator, workspace growth
+                self._run(sx, sc, st, sn)
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                loss = self._run(sx, sc, st, sn)
+            self.buckets.flat.copy_(keep)     # the warm-up accumulated one extra gradient: undo it
+            self.unet.grad_ready_hook = hook
+            ent = (graph, sx, sc, st, sn, loss)
+            self._graphs[key] = ent
+        graph, sx, sc, st, sn, loss = ent
+        sx.copy_(x0); sc.copy_(cond); st.copy_(t); sn.copy_(noise)
+        graph.replay()
+        return loss

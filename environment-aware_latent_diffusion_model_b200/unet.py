@@ -231,6 +231,7 @@ class UNetModel(nn.Module):
         self._compute_dtype = {"bf16": torch.bfloat16, "fp32": torch.float32}[compute_dtype]
         self._engine: Optional["UNetEngine"] = None
         self.use_cuda_graph = False   # see enable_cuda_graph
+        self.grad_ready_hook = None   # set by parallel.GradBuckets (data-parallel training)
         self._graphs = {}
         self.register_load_state_dict_post_hook(lambda m, keys: m.invalidate_packed())
 
@@ -329,7 +330,13 @@ class UNetEngine:
         f32 = lambda t: t.detach().float().contiguous()  # noqa: E731
         pk = lambda conv: pack_conv_weight(conv.weight, dtype)  # noqa: E731
         half = m.model_channels // 2
-        self.freqs = torch.exp(-math.log(10000) * torch.arange(0, half, dtype=torch.float32) / half).to(dev)
+        # computed on the host exactly as the reference does (util.py:160-162), cached on the module so that
+        # building an engine issues no host->device copy (engines are rebuilt inside CUDA-graph captures)
+        fr = getattr(m, "_freqs_cache", None)
+        if fr is None or fr.device != dev:
+            fr = torch.exp(-math.log(10000) * torch.arange(0, half, dtype=torch.float32) / half).to(dev)
+            m._freqs_cache = fr
+        self.freqs = fr
         self.te0 = _PackedConv(m.time_embed[0].weight.detach().to(dtype).contiguous(), f32(m.time_embed[0].bias), 0)
         self.te2 = _PackedConv(m.time_embed[2].weight.detach().to(dtype).contiguous(), f32(m.time_embed[2].bias), 0)
 

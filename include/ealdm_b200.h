@@ -173,6 +173,8 @@ typedef struct {
   int32_t reserved;
   void* out;
   int64_t ld_out;
+  float* lse; /* optional [batch, heads, n_q]: log2 of sum_j 2^(scale*log2(e)*q_i.k_j), saved for the backward
+                 (bf16 tensor-core path with n_kv % 64 == 0 only; NULL otherwise) */
 } ealdm_attention_args;
 
 int ealdm_attention(const ealdm_attention_args* a, ealdm_stream_t stream);
@@ -367,6 +369,8 @@ typedef struct {
   int64_t ld_dkv, head_stride_dkv;
   void* workspace;
   int64_t workspace_bytes;
+  const float* lse; /* optional: the forward's lse; enables the tensor-core backward (bf16, head_dim 32,
+                       n_q and n_kv multiples of 64); without it the log-sum-exp is recomputed (SIMT path) */
 } ealdm_attention_bwd_args;
 
 int64_t ealdm_attention_bwd_workspace_bytes(const ealdm_attention_bwd_args* a);

@@ -213,9 +213,12 @@ def test_layer_norm_bwd(dtype, rows, c):
 
 
 # ---- attention ---------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("dtype", [F32, BF16])
-@pytest.mark.parametrize("b,heads,n_q,n_kv", [(2, 8, 256, 256), (3, 16, 64, 64), (2, 8, 1024, 4), (1, 4, 100, 37)])
-def test_attention_bwd(dtype, b, heads, n_q, n_kv):
+@pytest.mark.parametrize("dtype,tc", [(F32, False), (BF16, False), (BF16, True)])
+@pytest.mark.parametrize("b,heads,n_q,n_kv", [(2, 8, 256, 256), (3, 16, 64, 64), (2, 8, 1024, 4), (1, 4, 100, 37),
+                                               (2, 8, 1024, 1024), (1, 3, 128, 320)])
+def test_attention_bwd(dtype, tc, b, heads, n_q, n_kv):
+    if tc and (n_q % 64 or n_kv % 64):
+        pytest.skip("tensor-core backward: self-attention shapes only (multiples of 64)")
     hd = 32
     C = heads * hd
     scale = hd ** -0.5
@@ -234,18 +237,23 @@ def test_attention_bwd(dtype, b, heads, n_q, n_kv):
     qa = Act(q, b, 1, n_q)
     kva = Act(kv, b, 1, n_kv)
     out = Act.empty(b, 1, n_q, C, dtype, DEV)
+    lse = torch.empty(b, heads, n_q, device=DEV) if tc else None
     ops.attention(qa, kva.cols(0, C), kva.cols(C, C), out, batch=b, heads=heads, head_dim=hd, n_q=n_q, n_kv=n_kv,
-                  scale=scale)
+                  scale=scale, lse=lse)
+    if tc:   # the forward's log2-domain log-sum-exp
+        ref_lse = torch.logsumexp(qr.detach() @ kr.detach().transpose(-1, -2) * scale, dim=-1) / math.log(2.0)
+        assert float((lse - ref_lse).abs().max()) < 2e-2
     dq = Act.empty(b, 1, n_q, C, dtype, DEV)
     dkv = Act.empty(b, 1, n_kv, 2 * C, dtype, DEV)
     ops.attention_bwd(qa, kva.cols(0, C), kva.cols(C, C), out, Act(dout, b, 1, n_q), dq, dkv.cols(0, C),
                       dkv.cols(C, C), ops.Workspace(DEV), batch=b, heads=heads, head_dim=hd, n_q=n_q, n_kv=n_kv,
-                      scale=scale)
+                      scale=scale, lse=lse, impl=L.IMPL_TCGEN05 if tc else L.IMPL_SIMT)
 
     def flat(t, n):
         return t.permute(0, 2, 1, 3).reshape(b * n, C)
 
-    t = 3e-5 if dtype == F32 else 1.2e-2   # bf16: `out` itself is bf16-rounded before D = dO.O
+    # bf16: `out` is bf16-rounded before D = dO.O; the tensor-core path also rounds P and dS to bf16 (as FA2 does)
+    t = 3e-5 if dtype == F32 else (2e-2 if tc else 1.2e-2)
     assert rel_l2(dq.buf.float(), flat(qr.grad, n_q)) < t
     assert rel_l2(dkv.buf[:, :C].float(), flat(kr.grad, n_kv)) < t
     assert rel_l2(dkv.buf[:, C:].float(), flat(vr.grad, n_kv)) < t

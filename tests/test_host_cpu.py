@@ -192,3 +192,58 @@ def test_sharded_sampling_gloo_world2_matches_single_process():
     cond = torch.randn(7, 4, 16, generator=g)
     ref = x_T * 2 + cond.mean(dim=(1, 2))[:, None, None, None]
     assert torch.equal(outs[0], ref) and torch.equal(outs[1], ref)
+
+
+TINY_UNET = dict(image_size=8, in_channels=4, model_channels=32, out_channels=4, num_res_blocks=1,
+                 attention_resolutions=[1, 2], channel_mult=(1, 2), num_head_channels=32,
+                 use_spatial_transformer=True, transformer_depth=1, context_dim=64)
+
+
+def _grad_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from ealdm_b200.parallel import GradBuckets
+    from ealdm_b200.unet import UNetModel
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    unet = UNetModel(**TINY_UNET)
+    gb = GradBuckets(unet, bucket_mb=0.05)          # many small buckets
+    assert len(gb.bounds) > 4
+    # every parameter got a view of the flat buffer, exactly once
+    assert sum(p.numel() for p in unet.parameters()) == gb.flat.numel()
+    for _ in range(2):                              # two "steps": zero_() must re-arm the buckets
+        gb.zero_()
+        for i, p in enumerate(unet.parameters()):
+            assert p.grad.data_ptr() >= gb.flat.data_ptr()
+            p.grad.add_(float(i + 1) * (rank + 1))
+        # the order UNetTrainEngine.backward reports blocks in
+        gb.block_done("head", 0)
+        for j in reversed(range(len(unet.output_blocks))):
+            gb.block_done("out", j)
+        gb.block_done("mid", 0)
+        launched_before_inputs = gb._next
+        for i in reversed(range(len(unet.input_blocks))):
+            gb.block_done("in", i)
+        gb.finish()
+    vals = [float(p.grad.flatten()[0]) for p in unet.parameters()]
+    q.put((rank, vals, launched_before_inputs, len(gb.bounds)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gradient_buckets_gloo_world2_average_and_overlap_order():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_grad_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    outs = [q.get(timeout=180) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, vals, early, nb in outs:
+        # mean over ranks of (i+1)*(rank+1) = 1.5*(i+1)
+        assert vals == [1.5 * (i + 1) for i in range(len(vals))]
+        assert 0 < early < nb      # buckets were launched while "backward" was still running
