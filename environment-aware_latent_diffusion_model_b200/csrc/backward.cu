@@ -313,19 +313,28 @@ ln_bwd_kernel(const TX* __restrict__ x, long long ld_x, const TD* __restrict__ d
   for (int col = threadIdx.x; col < C_; col += NT) part[static_cast<long long>(blockIdx.x) * C_ + col] = acc_s[col];
 }
 
+// 32 columns x 8 partial lanes per CTA, lanes combined in a fixed order
 __global__ void __launch_bounds__(NT)
 ln_bwd_param_kernel(const float2* __restrict__ part, int nparts, int c, float* __restrict__ dgamma,
                     float* __restrict__ dbeta) {
-  const int ch = blockIdx.x * NT + threadIdx.x;
-  if (ch >= c) return;
+  __shared__ float2 red[8][32];
+  const int tc = threadIdx.x & 31, tk = threadIdx.x >> 5;
+  const int ch = blockIdx.x * 32 + tc;
   float sg = 0.f, sb = 0.f;
-  for (int i = 0; i < nparts; ++i) {
-    const float2 e = part[static_cast<long long>(i) * c + ch];
-    sg += e.x;
-    sb += e.y;
+  if (ch < c)
+    for (int i = tk; i < nparts; i += 8) {
+      const float2 e = part[static_cast<long long>(i) * c + ch];
+      sg += e.x;
+      sb += e.y;
+    }
+  red[tk][tc] = make_float2(sg, sb);
+  __syncthreads();
+  if (tk == 0 && ch < c) {
+#pragma unroll
+    for (int k = 1; k < 8; ++k) { sg += red[k][tc].x; sb += red[k][tc].y; }
+    if (dgamma) dgamma[ch] += sg;
+    if (dbeta) dbeta[ch] += sb;
   }
-  if (dgamma) dgamma[ch] += sg;
-  if (dbeta) dbeta[ch] += sb;
 }
 
 // ---- GEGLU (natural [value | gate] layout, attention.py:37-44) ------------------------------------------
@@ -628,7 +637,7 @@ static int layer_norm_bwd_t(const ealdm_layer_norm_bwd_args* a, int nparts, cuda
 #undef EALDM_LN_BWD
   EALDM_LAUNCH_CHECK();
   if (a->dgamma || a->dbeta) {
-    ln_bwd_param_kernel<<<static_cast<unsigned>(ceil_div(a->c, NT)), NT, 0, st>>>(part, nparts, static_cast<int>(a->c),
+    ln_bwd_param_kernel<<<static_cast<unsigned>(ceil_div(a->c, 32)), NT, 0, st>>>(part, nparts, static_cast<int>(a->c),
                                                                                   a->dgamma, a->dbeta);
     EALDM_LAUNCH_CHECK();
   }

@@ -242,23 +242,60 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant_
 // ---- split reduction + layout permutation -----------------------------------------------------------
 // dst[j][perm(k)] (+)= sum_s ws[s][j][k], k = tap*c + ci.  layout 0: perm = identity (packed K-major,
 // pitch ld_dw); layout 1: PyTorch OIHW, perm(k) = ci*taps + tap.
+// One CTA per (output channel j, 64-channel block): the partials are read tap by tap along ci (coalesced),
+// transposed through shared memory, and the [64 ci x taps] block of dw -- contiguous in OIHW -- is updated
+// with coalesced accesses.
 __global__ void __launch_bounds__(256)
 wgrad_reduce_kernel(const float* __restrict__ ws, int splits, long long n_out, long long ktot, int c, int taps,
                     float* __restrict__ dw, long long ld_dw, int layout, int accumulate) {
+  __shared__ float tile[9][65];
+  const long long j = blockIdx.y;
+  const int ci0 = blockIdx.x * 64;
+  const int nci = min(64, c - ci0);
   const long long total = n_out * ktot;
-  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += 256LL * gridDim.x) {
-    const long long j = i / ktot;
-    const int k = static_cast<int>(i - j * ktot);
+  const float* src = ws + j * ktot;
+  for (int i = threadIdx.x; i < taps * 64; i += 256) {
+    const int tap = i >> 6, cl = i & 63;
     float s = 0.f;
-    for (int sp = 0; sp < splits; ++sp) s += ws[sp * total + i];
-    long long o;
-    if (layout == 0) {
-      o = j * ld_dw + k;
-    } else {
-      const int tap = k / c, ci = k - tap * c;
-      o = j * ld_dw + static_cast<long long>(ci) * taps + tap;
+    if (cl < nci) {
+      const long long o = static_cast<long long>(tap) * c + ci0 + cl;
+      for (int sp = 0; sp < splits; ++sp) s += src[sp * total + o];
+      if (layout == 0) {
+        float* d = dw + j * ld_dw + o;
+        *d = accumulate ? *d + s : s;
+      }
     }
-    dw[o] = accumulate ? dw[o] + s : s;
+    tile[tap][cl] = s;
+  }
+  if (layout == 0) return;
+  __syncthreads();
+  float* d = dw + j * ld_dw + static_cast<long long>(ci0) * taps;
+  for (int i = threadIdx.x; i < nci * taps; i += 256) {
+    const int cl = i / taps, tap = i - cl * taps;
+    d[i] = accumulate ? d[i] + tile[tap][cl] : tile[tap][cl];
+  }
+}
+
+// identity permutation (1x1 / linear layers, or the packed layout): 4 consecutive k per thread
+__global__ void __launch_bounds__(256)
+wgrad_reduce_flat_kernel(const float* __restrict__ ws, int splits, long long n_out, long long ktot,
+                         float* __restrict__ dw, long long ld_dw, int accumulate) {
+  const long long total = n_out * ktot;
+  const long long kv = ktot >> 2;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n_out * kv; i += 256LL * gridDim.x) {
+    const long long j = i / kv;
+    const long long k = (i - j * kv) << 2;
+    float4 s = *reinterpret_cast<const float4*>(ws + j * ktot + k);
+    for (int sp = 1; sp < splits; ++sp) {
+      const float4 e = *reinterpret_cast<const float4*>(ws + sp * total + j * ktot + k);
+      s.x += e.x; s.y += e.y; s.z += e.z; s.w += e.w;
+    }
+    float4* d = reinterpret_cast<float4*>(dw + j * ld_dw + k);
+    if (accumulate) {
+      const float4 o = *d;
+      s.x += o.x; s.y += o.y; s.z += o.z; s.w += o.w;
+    }
+    *d = s;
   }
 }
 
@@ -518,10 +555,19 @@ extern "C" int ealdm_conv_wgrad(const ealdm_conv_wgrad_args* a, ealdm_stream_t s
           pl.p.ws, ktot, pl.splits);
     EALDM_LAUNCH_CHECK();
   }
-  const long long total = a->n_out * ktot;
-  const int blocks = static_cast<int>(ceil_div(total, 256) < 4096 ? ceil_div(total, 256) : 4096);
-  wgrad::wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(pl.p.ws, pl.splits, a->n_out, ktot, pl.p.c, pl.p.taps, a->dw,
-                                                     a->ld_dw, a->layout, a->accumulate);
+  if ((pl.p.taps == 1 || a->layout == EALDM_WGRAD_PACKED) && ktot % 4 == 0 && a->ld_dw % 4 == 0 &&
+      (reinterpret_cast<uintptr_t>(a->dw) & 15) == 0) {
+    const long long work = a->n_out * (ktot / 4);
+    const int blocks = static_cast<int>(ceil_div(work, 256) < 2368 ? ceil_div(work, 256) : 2368);
+    wgrad::wgrad_reduce_flat_kernel<<<blocks, 256, 0, st>>>(pl.p.ws, pl.splits, a->n_out, ktot, a->dw, a->ld_dw,
+                                                            a->accumulate);
+    EALDM_LAUNCH_CHECK();
+    return 0;
+  }
+  EALDM_REQUIRE(a->n_out <= 65535, "conv_wgrad: n_out too large");
+  dim3 rgrid(static_cast<unsigned>(ceil_div(pl.p.c, 64)), static_cast<unsigned>(a->n_out));
+  wgrad::wgrad_reduce_kernel<<<rgrid, 256, 0, st>>>(pl.p.ws, pl.splits, a->n_out, ktot, pl.p.c, pl.p.taps, a->dw,
+                                                    a->ld_dw, a->layout, a->accumulate);
   EALDM_LAUNCH_CHECK();
   return 0;
 }

@@ -12,7 +12,8 @@ def pack_conv_weight(w: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
     if w.dim() == 3:  # conv1d 1x1 (AttentionBlock.qkv / proj_out, openaimodel.py:304,312)
         w = w[..., None]
     o = w.shape[0]
-    return w.detach().permute(0, 2, 3, 1).reshape(o, -1).to(dtype).contiguous()
+    # cast first: the permuting copy then moves half the bytes
+    return w.detach().to(dtype).permute(0, 2, 3, 1).reshape(o, -1).contiguous()
 
 
 def geglu_interleave(w: torch.Tensor, b: torch.Tensor):

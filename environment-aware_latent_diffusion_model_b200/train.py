@@ -46,12 +46,13 @@ def _grad1d(p: torch.Tensor) -> torch.Tensor:
 def _pack_dgrad(w: torch.Tensor, dtype) -> torch.Tensor:
     """[O, I, kh, kw] -> [I, (kh', kw', O)] with the taps flipped: the weight matrix of the data gradient.
     Linear / 1x1: [O, I] -> [I, O]."""
+    w = w.detach().to(dtype)     # cast first: the permuting copies then move half the bytes
     if w.dim() == 2:
-        return w.detach().t().to(dtype).contiguous()
+        return w.t().contiguous()
     if w.dim() == 3:
         w = w[..., None]
     i = w.shape[1]
-    return w.detach().flip(2, 3).permute(1, 2, 3, 0).reshape(i, -1).to(dtype).contiguous()
+    return w.flip(2, 3).permute(1, 2, 3, 0).reshape(i, -1).contiguous()
 
 
 class UNetTrainEngine(UNetEngine):
@@ -68,7 +69,11 @@ class UNetTrainEngine(UNetEngine):
     def _attach_params(self):
         """Attach to every packed layer dict the parameters it came from and the transposed weights."""
         m, dt = self.m, self.dt
-        pd = lambda p: _pack_dgrad(p, dt)  # noqa: E731
+        def pd(p):
+            base = p._base if (p._base is not None and p.dim() == 2) else None   # [:, :, 0, 0] view of a 1x1 conv
+            if base is not None:
+                return _pack_dgrad(self._c(base)[:, :, 0, 0], dt)
+            return _pack_dgrad(self._c(p), dt)
 
         def walk(seq, packed):
             for layer, d in zip(seq, packed):
@@ -88,7 +93,7 @@ class UNetTrainEngine(UNetEngine):
                         t["wd_o1"] = pd(tb.attn1.to_out[0].weight)
                         t["wd_q2"] = pd(tb.attn2.to_q.weight)
                         t["wd_o2"] = pd(tb.attn2.to_out[0].weight)
-                        t["ff1n"] = tb.ff.net[0].proj.weight.detach().to(dt).contiguous()
+                        t["ff1n"] = self._c(tb.ff.net[0].proj.weight)
                         t["ff1n_b"] = tb.ff.net[0].proj.bias.detach().float().contiguous()
                         t["wd_ff1"] = t["ff1n"].t().contiguous()
                         t["wd_ff2"] = pd(tb.ff.net[2].weight)

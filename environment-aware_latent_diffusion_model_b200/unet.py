@@ -328,7 +328,8 @@ class UNetEngine:
         assert dev.type == "cuda", "move the model to CUDA before the first forward"
         self.dev = dev
         f32 = lambda t: t.detach().float().contiguous()  # noqa: E731
-        pk = lambda conv: pack_conv_weight(conv.weight, dtype)  # noqa: E731
+        self._cast_cache = {}     # parameter -> compute-dtype copy (shared by the forward and dgrad packings)
+        pk = lambda conv: pack_conv_weight(self._c(conv.weight), dtype)  # noqa: E731
         half = m.model_channels // 2
         # computed on the host exactly as the reference does (util.py:160-162), cached on the module so that
         # building an engine issues no host->device copy (engines are rebuilt inside CUDA-graph captures)
@@ -337,8 +338,8 @@ class UNetEngine:
             fr = torch.exp(-math.log(10000) * torch.arange(0, half, dtype=torch.float32) / half).to(dev)
             m._freqs_cache = fr
         self.freqs = fr
-        self.te0 = _PackedConv(m.time_embed[0].weight.detach().to(dtype).contiguous(), f32(m.time_embed[0].bias), 0)
-        self.te2 = _PackedConv(m.time_embed[2].weight.detach().to(dtype).contiguous(), f32(m.time_embed[2].bias), 0)
+        self.te0 = _PackedConv(self._c(m.time_embed[0].weight), f32(m.time_embed[0].bias), 0)
+        self.te2 = _PackedConv(self._c(m.time_embed[2].weight), f32(m.time_embed[2].bias), 0)
 
         self.blocks = []          # execution list
         emb_w, emb_b = [], []     # all ResBlock emb_layers stacked into one GEMM
@@ -351,7 +352,7 @@ class UNetEngine:
             d["gn1"] = (f32(rb.in_layers[0].weight), f32(rb.in_layers[0].bias))
             d["conv1"] = _PackedConv(pk(rb.in_layers[2]), f32(rb.in_layers[2].bias), rb.out_channels)
             d["emb_col0"] = self.emb_cols
-            emb_w.append(rb.emb_layers[1].weight.detach())
+            emb_w.append(self._c(rb.emb_layers[1].weight))
             emb_b.append(rb.emb_layers[1].bias.detach())
             self.emb_cols += rb.out_channels
             d["gn2"] = (f32(rb.out_layers[0].weight), f32(rb.out_layers[0].bias))
@@ -377,19 +378,19 @@ class UNetEngine:
                 t = {}
                 for i, ln in ((1, tb.norm1), (2, tb.norm2), (3, tb.norm3)):
                     t[f"ln{i}"] = (f32(ln.weight), f32(ln.bias))
-                t["qkv"] = torch.cat([tb.attn1.to_q.weight, tb.attn1.to_k.weight, tb.attn1.to_v.weight],
-                                     dim=0).detach().to(dtype).contiguous()
-                t["o1"] = _PackedConv(tb.attn1.to_out[0].weight.detach().to(dtype).contiguous(),
+                t["qkv"] = torch.cat([self._c(tb.attn1.to_q.weight), self._c(tb.attn1.to_k.weight),
+                                      self._c(tb.attn1.to_v.weight)], dim=0)
+                t["o1"] = _PackedConv(self._c(tb.attn1.to_out[0].weight),
                                       f32(tb.attn1.to_out[0].bias), C_)
-                t["q2"] = tb.attn2.to_q.weight.detach().to(dtype).contiguous()
+                t["q2"] = self._c(tb.attn2.to_q.weight)
                 t["kv_col0"] = self.kv_cols
-                kv_w.append(torch.cat([tb.attn2.to_k.weight, tb.attn2.to_v.weight], dim=0).detach())
+                kv_w.append(torch.cat([self._c(tb.attn2.to_k.weight), self._c(tb.attn2.to_v.weight)], dim=0))
                 self.kv_cols += 2 * C_
-                t["o2"] = _PackedConv(tb.attn2.to_out[0].weight.detach().to(dtype).contiguous(),
+                t["o2"] = _PackedConv(self._c(tb.attn2.to_out[0].weight),
                                       f32(tb.attn2.to_out[0].bias), C_)
-                wi, bi = geglu_interleave(tb.ff.net[0].proj.weight.to(dtype), tb.ff.net[0].proj.bias)
+                wi, bi = geglu_interleave(self._c(tb.ff.net[0].proj.weight), tb.ff.net[0].proj.bias)
                 t["ff1"] = _PackedConv(wi, bi, 4 * C_)
-                t["ff2"] = _PackedConv(tb.ff.net[2].weight.detach().to(dtype).contiguous(), f32(tb.ff.net[2].bias), C_)
+                t["ff2"] = _PackedConv(self._c(tb.ff.net[2].weight), f32(tb.ff.net[2].bias), C_)
                 d["blocks"].append(t)
             return d
 
@@ -426,9 +427,9 @@ class UNetEngine:
         self.outb = [pack_layers(b) for b in m.output_blocks]
         self.out_norm = (f32(m.out[0].weight), f32(m.out[0].bias))
         self.out_conv = _PackedConv(pk(m.out[2]), f32(m.out[2].bias), m.out_channels)
-        self.emb_w = torch.cat(emb_w, dim=0).to(dtype).contiguous()
+        self.emb_w = torch.cat(emb_w, dim=0)
         self.emb_b = torch.cat(emb_b, dim=0).float().contiguous()
-        self.kv_w = torch.cat(kv_w, dim=0).to(dtype).contiguous() if kv_w else None
+        self.kv_w = torch.cat(kv_w, dim=0) if kv_w else None
 
         # channel bookkeeping for the zero-copy skip concatenation
         def block_out_channels(layers, cin):
@@ -446,6 +447,14 @@ class UNetEngine:
             c = block_out_channels(layers, c)
             self.skip_ch.append(c)
         self.mid_ch = c
+
+    def _c(self, w: torch.Tensor) -> torch.Tensor:
+        """Compute-dtype copy of a parameter, made once per engine."""
+        t = self._cast_cache.get(id(w))
+        if t is None:
+            t = w.detach().to(self.dt)
+            self._cast_cache[id(w)] = t
+        return t
 
     # ---- helpers --------------------------------------------------------------------------------------
     # The residual stream ("trunk": ResBlock / attention-block / resample outputs and the token stream
