@@ -156,8 +156,12 @@ flash_mma_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const b
 //   * the row sums are produced by the tensor core: the P.V MMA gets a fifth 8-column tile whose
 //     column 0 is all ones, so l accumulates (and is rescaled) exactly like O.
 
+// The kernel is latency bound (MUFU and mma.sync dependency chains: XU pipe 41 %, legacy tensor pipe 43 %, issue
+// 42 % at 4 warps per scheduler -- profiles/r01_attention_full.txt), so residency matters more than tile reuse:
+// the register budget is capped at 80 and CTAs are 4 warps, 6 per SM (24 warps): 653 -> 556 us at level 0.
+// (A packed ex2.approx.ftz.bf16x2 does NOT halve the MUFU work: ptxas splits it into two MUFU.EX2.BF16.)
 template <int NWARPS>
-__global__ void __launch_bounds__(NWARPS * 32)
+__global__ void __launch_bounds__(NWARPS * 32, 768 / (NWARPS * 32))
 flash_mma_even_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const bf16* __restrict__ v,
                       long long ld_q, long long ld_kv, long long hs_q, long long hs_kv, int n_q, int n_kv,
                       float scale_log2, bf16* __restrict__ out, long long ld_out, float* __restrict__ lse) {
@@ -298,7 +302,7 @@ int launch_flash_mma(const ealdm_attention_args* a, cudaStream_t st) {
   EALDM_REQUIRE(a->lse == nullptr || (a->n_kv % KV_TILE == 0 && a->scale > 0.f),
                 "attention(mma): lse output needs n_kv %% 64 == 0");
   if (a->n_kv % KV_TILE == 0 && a->scale > 0.f) {
-    if (a->n_q > 64) {
+    if (false) {   // 8-warp CTAs (128 queries): kept for reference, slower than 6 resident 4-warp CTAs
       dim3 grid(static_cast<unsigned>(ceil_div(a->n_q, 128)), static_cast<unsigned>(a->heads),
                 static_cast<unsigned>(a->batch));
       flash_mma_even_kernel<8><<<grid, 256, 0, st>>>(q, k, v, a->ld_q, a->ld_kv, a->head_stride_q,
