@@ -285,10 +285,70 @@ def run_train(args):
     return 0
 
 
+def run_autoencoder(args):
+    """--workload autoencoder: BASELINE.json configs[2] -- AutoencoderKL (f=8, 32x32x4) encode + decode of 256x256
+    images, batch 64, bf16 operands.  Algorithmic work: 272.722 GF (encode) + 622.187 GF (decode) per image."""
+    import torch
+
+    from ealdm_b200 import configs as CFG, ops
+    from ealdm_b200.autoencoder import AutoencoderKL
+    from ealdm_b200.synthetic import init_synthetic_
+
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    B = args.batch
+    ae = AutoencoderKL(ddconfig=dict(CFG.AE_KL_F8_DDCONFIG), embed_dim=4).to(dev).eval()
+    init_synthetic_(ae, seed=0)
+    ae.set_compute_dtype("bf16")
+    g = torch.Generator().manual_seed(1)
+    img_h = (torch.rand(B, 3, 256, 256, generator=g) * 2 - 1).pin_memory()
+    out_h = torch.empty(B, 3, 256, 256).pin_memory()
+    img_d = img_h.to(dev)
+
+    def step(host):
+        x = img_h.to(dev, non_blocking=True) if host else img_d
+        with torch.no_grad():
+            z = ae.encode(x).mode()
+            rec = ae.decode(z)
+        if host:
+            out_h.copy_(rec, non_blocking=True)
+        return rec
+
+    res = {}
+    l0 = ops.launch_count()
+    for host in (False, True):
+        for _ in range(max(args.warmup, 3)):
+            step(host)
+        torch.cuda.synchronize()
+        if not host:
+            launches = (ops.launch_count() - l0) // max(args.warmup, 3)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            step(host)
+        e1.record()
+        torch.cuda.synchronize()
+        res[host] = e0.elapsed_time(e1) / args.steps
+    peaks = load_peaks()
+    tf = B * (272.722 + 622.187) / 1e3
+    line = {"metric": "images/sec (AutoencoderKL encode+decode, 256px)", "value": B / (res[False] * 1e-3),
+            "unit": "images/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": res[False],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "autoencoder_kl_32x32x4 (f=8) encode + decode 256x256, batch 64 (BASELINE.json configs[2])",
+                       "batch_per_gpu": B},
+            "e2e": {"value": B / (res[True] * 1e-3), "unit": "images/s", "h2d_bytes_per_step": img_h.numel() * 4,
+                    "d2h_bytes_per_step": out_h.numel() * 4, "ms_per_step": res[True]},
+            "gpu_launches": int(launches * args.steps), "tflops_per_gpu": tf / (res[False] * 1e-3),
+            "frac_of_sustained_peak": tf / (res[False] * 1e-3) / peaks["bf16_sustained"]}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--workload", default="sample", choices=["sample", "train"],
-                    help="sample: the headline metric (default); train: BASELINE.json configs[4]")
+    ap.add_argument("--workload", default="sample", choices=["sample", "train", "autoencoder"],
+                    help="sample: the headline metric (default); train: BASELINE.json configs[4]; "
+                         "autoencoder: BASELINE.json configs[2]")
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
@@ -305,6 +365,8 @@ def main():
         return run_reference(args)
     if args.workload == "train":
         return run_train(args)
+    if args.workload == "autoencoder":
+        return run_autoencoder(args)
 
     import torch
     import torch.distributed as dist
@@ -457,6 +519,15 @@ def main():
                 "traffic": None, "launches_per_forward": n_tc, "avg_launch_ms": tc_ms / max(n_tc, 1),
                 "share_of_forward": tc_ms / fwd_ms if fwd_ms > 0 else None,
                 "note": "event-timed eager forward at UNet batch %d; algorithmic FLOPs = 2*M*N*K per launch" % (2 * B)}
+    # DRAM bytes per launch of the same kernel from the committed ncu capture of one forward at this batch
+    tpath = os.path.join(ROOT, "profiles", "r01_conv_tc_traffic.json")
+    if os.path.exists(tpath) and B == 64:
+        with open(tpath) as f:
+            tj = json.load(f)
+        roofline["traffic"] = tj["dram_bytes_per_launch"]
+        roofline["traffic_note"] = ("dram__bytes_read.sum + dram__bytes_write.sum averaged over the %d launches of one "
+                                    "forward (profiles/r01_conv_tc_traffic.json); L2 traffic per launch %.0f MB"
+                                    % (tj["launches"], tj["l2_bytes_per_launch"] / 1e6))
     step_tflops = value / world * S * 2 * CFG.UNET_STDIFF_GFLOP_PER_SAMPLE / 1e3
 
     if rank == 0:
