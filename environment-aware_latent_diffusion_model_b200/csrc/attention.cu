@@ -6,6 +6,8 @@
 //                          one thread per (query, head), K/V served from L1/L2.
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace ealdm {
 namespace attn {
 
@@ -341,6 +343,13 @@ static int launch_t(const ealdm_attention_args* a, cudaStream_t st) {
 }  // namespace attn
 }  // namespace ealdm
 
+namespace ealdm {
+namespace attn_tc {
+bool supported(const ealdm_attention_args* a);                             // attention_tc.cu
+int launch(const ealdm_attention_args* a, cudaStream_t st, bool wide);
+}  // namespace attn_tc
+}  // namespace ealdm
+
 using namespace ealdm;
 
 extern "C" int ealdm_attention(const ealdm_attention_args* a, ealdm_stream_t stream) {
@@ -353,6 +362,17 @@ extern "C" int ealdm_attention(const ealdm_attention_args* a, ealdm_stream_t str
   EALDM_REQUIRE(a->head_dim == 32 || a->head_dim == 64,
                 "attention: head_dim %lld unsupported (32 or 64)", (long long)a->head_dim);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  {
+    // tcgen05 / TMEM flash attention (n_q, n_kv multiples of 128); EALDM_ATTN_TC = off | wide | narrow (tuning)
+    static const char* mode = getenv("EALDM_ATTN_TC");
+    const bool off = mode != nullptr && mode[0] == 'o';
+    const bool wide = mode != nullptr && mode[0] == 'w';
+    if (a->impl == EALDM_IMPL_TCGEN05 || (a->impl == EALDM_IMPL_AUTO && !off)) {
+      if (attn_tc::supported(a)) return attn_tc::launch(a, st, wide);
+      EALDM_REQUIRE(a->impl != EALDM_IMPL_TCGEN05,
+                    "attention: the tcgen05 path needs bf16, head_dim 32, n_q and n_kv multiples of 128");
+    }
+  }
   if (a->dtype == EALDM_BF16 && a->head_dim == 32 && a->n_kv > attn::MAX_SMALL_KV &&
       a->impl != EALDM_IMPL_SIMT)
     return attn::launch_flash_mma(a, st);

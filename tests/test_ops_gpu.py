@@ -232,6 +232,32 @@ def test_self_attention_packed_qkv(dtype, impl, b, h, n):
     assert rel_l2(out.buf.float(), ref) < (2e-5 if dtype == torch.float32 else 1e-2)
 
 
+@pytest.mark.parametrize("b,h,n", [(2, 8, 1024), (3, 16, 256), (1, 1, 128), (5, 4, 384)])
+@pytest.mark.parametrize("ramp", [0.0, 6.0])
+def test_self_attention_tcgen05_lazy_rescale_and_lse(b, h, n, ramp):
+    """The tcgen05 / TMEM kernel, forced.  ramp > 0 makes the logits grow along the key axis (q.k up to ~ramp*30),
+    so the row maximum keeps rising across key tiles and the lazy O rescaling in TMEM actually runs."""
+    d = 32
+    C_ = h * d
+    qkv = torch.randn(b * n, 3 * C_, generator=g(35)).to(DEV)
+    if ramp:
+        x = qkv.reshape(b, n, 3, h, d)
+        x[:, :, 0] = x[:, :, 0].abs() * 0.5 + 0.5                                   # q > 0
+        x[:, :, 1] += (torch.arange(n, device=DEV).float() / n * ramp)[None, :, None, None]   # k drifts upwards
+    qkv = qkv.to(torch.bfloat16).contiguous()
+    buf = Act(qkv, b, 1, n)
+    out = Act.empty(b, 1, n, C_, torch.bfloat16, DEV)
+    lse = torch.empty(b, h, n, device=DEV)
+    ops.attention(buf.cols(0, C_), buf.cols(C_, C_), buf.cols(2 * C_, C_), out, batch=b, heads=h, head_dim=d,
+                  n_q=n, n_kv=n, scale=d ** -0.5, impl=L.IMPL_TCGEN05, lse=lse)
+    f = qkv.float().reshape(b, n, 3, h, d)
+    q, k, v = (f[:, :, i].transpose(1, 2) for i in range(3))
+    ref = _attn_ref(q, k, v, d ** -0.5).transpose(1, 2).reshape(b * n, C_)
+    assert rel_l2(out.buf.float(), ref) < 1e-2
+    ref_lse = torch.logsumexp(torch.einsum("bhid,bhjd->bhij", q, k) * d ** -0.5, dim=-1) / math.log(2.0)
+    assert float((lse - ref_lse).abs().max()) < 2e-3 * max(1.0, float(ref_lse.abs().max()))
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_attention_legacy_interleaved_heads(dtype):
     # QKVAttentionLegacy (openaimodel.py:365): channels are [head][q|k|v][32]
