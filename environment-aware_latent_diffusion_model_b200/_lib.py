@@ -28,7 +28,7 @@ EXPORTS = [
     "ealdm_group_norm_bwd_workspace_bytes", "ealdm_layer_norm_bwd", "ealdm_layer_norm_bwd_workspace_bytes",
     "ealdm_attention_bwd", "ealdm_attention_bwd_workspace_bytes", "ealdm_geglu", "ealdm_geglu_bwd",
     "ealdm_silu", "ealdm_silu_bwd", "ealdm_colsum", "ealdm_colsum_workspace_bytes", "ealdm_zero_insert2x",
-    "ealdm_sumpool2x2", "ealdm_cfg_mse_bwd",
+    "ealdm_sumpool2x2", "ealdm_cfg_mse_bwd", "ealdm_gn_partial",
 ]
 WGRAD_PACKED, WGRAD_OIHW = 0, 1
 
@@ -46,7 +46,7 @@ class ConvArgs(C.Structure):
                 ("bias", C.c_void_p), ("rowvec", C.c_void_p), ("ld_rowvec", C.c_int64),
                 ("residual", C.c_void_p), ("ld_res", C.c_int64), ("out", C.c_void_p),
                 ("ld_out", C.c_int64), ("out_f32", C.c_int32), ("res_f32", C.c_int32),
-                ("out2", C.c_void_p), ("ld_out2", C.c_int64)]
+                ("out2", C.c_void_p), ("ld_out2", C.c_int64), ("gn_partial", C.c_void_p), ("gn_ld", C.c_int64)]
 
 
 class GroupNormArgs(C.Structure):
@@ -54,7 +54,7 @@ class GroupNormArgs(C.Structure):
                 ("hw", C.c_int64), ("c", C.c_int64), ("ld_x", C.c_int64), ("groups", C.c_int32),
                 ("eps", C.c_float), ("gamma", C.c_void_p), ("beta", C.c_void_p), ("y", C.c_void_p),
                 ("ld_y", C.c_int64), ("workspace", C.c_void_p), ("x_f32", C.c_int32), ("reserved", C.c_int32),
-                ("stats_out", C.c_void_p)]
+                ("stats_out", C.c_void_p), ("partial", C.c_void_p), ("partial_ld", C.c_int64)]
 
 
 class LayerNormArgs(C.Structure):
@@ -186,6 +186,7 @@ def _declare(lib):
         ("ealdm_zero_insert2x", [vp, i64, i32, i64, i64, i64, i64, vp, i64, vp]),
         ("ealdm_sumpool2x2", [vp, i64, i32, i64, i64, i64, i64, vp, i64, vp, i64, vp, i64, vp]),
         ("ealdm_cfg_mse_bwd", [vp, vp, vp, vp, f32, i64, i64, vp, vp, vp]),
+        ("ealdm_gn_partial", [vp, i64, i32, i64, i64, i64, vp, i64, vp]),
     ]:
         fn = getattr(lib, name)
         fn.restype = C.c_int

@@ -65,6 +65,10 @@ struct Params {
   int out_f32;
   int has_res, res_f32;
   int has_out2;
+  // GroupNorm partial statistics of the output (optional)
+  float2* gn_partial;
+  int gn_ld;       // octets per (image, chunk) row
+  int gn_chunks;   // 32-pixel chunks per image
 };
 
 template <int BN>
@@ -407,6 +411,47 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
               r[j] += silu_f(f);
             }
           }
+          if (p.gn_partial != nullptr) {
+            // {sum, sum of squares} of the 4 channel octets of this unit over the warp's 32 pixel rows (one 32-pixel
+            // chunk of one image): 8 values per thread, folded across the lanes in a fixed order with 9 shuffles
+            float v8[8];
+            const bool valid = (n - sn0) + my_dn < p.Nimg;
+#pragma unroll
+            for (int o = 0; o < 4; ++o) {
+              float a = 0.f, b = 0.f;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) { a += r[8 * o + j]; b = fmaf(r[8 * o + j], r[8 * o + j], b); }
+              v8[2 * o] = valid ? a : 0.f;
+              v8[2 * o + 1] = valid ? b : 0.f;
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {   // lanes 16..31 keep values 4..7
+              const float send = (lane & 16) ? v8[i] : v8[i + 4];
+              const float keep = (lane & 16) ? v8[i + 4] : v8[i];
+              v8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const float send = (lane & 8) ? v8[i] : v8[i + 2];
+              const float keep = (lane & 8) ? v8[i + 2] : v8[i];
+              v8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+            }
+            {
+              const float send = (lane & 4) ? v8[0] : v8[1];
+              const float keep = (lane & 4) ? v8[1] : v8[0];
+              v8[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+            }
+            v8[0] += __shfl_xor_sync(0xffffffffu, v8[0], 2);
+            v8[0] += __shfl_xor_sync(0xffffffffu, v8[0], 1);
+            const int col0 = nt * BN + ku * 32;
+            if ((lane & 3) == 0 && n < p.Nimg && col0 < p.N) {
+              const int vi = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);  // value index 0..7
+              const int chunk = (h * p.Wout + w) >> 5;
+              float* dst = reinterpret_cast<float*>(p.gn_partial + (static_cast<long long>(n) * p.gn_chunks + chunk) * p.gn_ld +
+                                                    (col0 >> 3) + (vi >> 1));
+              dst[vi & 1] = v8[0];
+            }
+          }
           if (p.out_f32) sts_row_f32(eb, lane, r);
           else sts_row_bf16(eb, lane, r);
           if (p.has_out2) sts_row_bf16(o2buf, lane, r);
@@ -509,6 +554,13 @@ bool supported(const ealdm_conv_args* a) {
                     a->n_out % 4 != 0))
     return false;
   if (a->act == EALDM_ACT_GEGLU && (a->rowvec || a->out2 || a->residual || a->n_out % 32 != 0)) return false;
+  if (a->gn_partial) {
+    const long long hw = a->h_out * a->w_out;
+    if (a->act == EALDM_ACT_GEGLU || hw % 32 != 0 || (a->w_out & (a->w_out - 1)) != 0 ||
+        (a->h_out & (a->h_out - 1)) != 0 || a->n_out % 32 != 0)
+      return false;
+    if (a->w_out < 32 && (32 % a->w_out != 0 || a->h_out % (32 / a->w_out) != 0)) return false;
+  }
   return true;
 }
 
@@ -632,6 +684,9 @@ int launch(const ealdm_conv_args* a, cudaStream_t st) {
   p.has_res = a->residual != nullptr;
   p.res_f32 = a->res_f32;
   p.has_out2 = a->out2 != nullptr;
+  p.gn_partial = reinterpret_cast<float2*>(a->gn_partial);
+  p.gn_ld = static_cast<int>(a->gn_ld);
+  p.gn_chunks = static_cast<int>(a->h_out * a->w_out / 32);
 
   switch (BN) {
     case 32: return launch_bn<32, false>(tm, p, st);

@@ -5,6 +5,8 @@
 #include "common.cuh"
 #include "ptx.cuh"
 
+#include <stdlib.h>
+
 #include <cooperative_groups.h>
 
 namespace cg = cooperative_groups;
@@ -170,6 +172,130 @@ gn_apply_kernel(const TX* __restrict__ x, long long ld_x, T* __restrict__ y, lon
   }
 }
 
+// ---- GroupNorm from partial statistics: a pure streaming pass ------------------------------------------------
+// The producing convolution's epilogue (conv_tc.cu) or gn_partial_kernel has already written, for every
+// (image, 32-pixel chunk, 8-channel octet), {sum, sum of squares}.  Every CTA folds the partials of its image in a
+// fixed order (fp64: bit-reproducible), then streams its pixel rows once: no reduction pass over x, no barrier
+// between a load and its store.
+template <typename TX, typename T>
+__global__ void __launch_bounds__(NT)
+gn_apply_partial_kernel(const TX* __restrict__ x, long long ld_x, T* __restrict__ y, long long ld_y, int hw, int c,
+                        int groups, int pix_per_cta, const float2* __restrict__ partial, long long pld, float eps,
+                        const float* __restrict__ gamma, const float* __restrict__ beta, int act,
+                        float* __restrict__ stats_out) {
+  constexpr bool SILU_FAST = sizeof(T) == 2;
+  __shared__ float s_mean[MAX_GROUPS], s_rstd[MAX_GROUPS];
+  const int t = threadIdx.x;
+  const int n = blockIdx.y;
+  const int cpg = c / groups;
+  const int vpp = c >> 2;
+  {
+    const int chunks = hw >> 5;
+    const int opg = cpg >> 3;            // octets per group
+    const int terms = chunks * opg;
+    const float2* pn = partial + static_cast<long long>(n) * chunks * pld;
+    for (int g0 = 0; g0 < groups; g0 += NT / 8) {
+      const int g = g0 + (t >> 3);
+      const int sub = t & 7;
+      double s = 0.0, ss = 0.0;
+      if (g < groups) {
+        for (int k = sub; k < terms; k += 8) {
+          const int ch = k / opg, oo = k - ch * opg;
+          const float2 p = pn[static_cast<long long>(ch) * pld + g * opg + oo];
+          s += static_cast<double>(p.x);
+          ss += static_cast<double>(p.y);
+        }
+      }
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      }
+      if (g < groups && sub == 0) {
+        const double cnt = static_cast<double>(hw) * cpg;
+        const double mean = s / cnt;
+        double var = ss / cnt - mean * mean;
+        if (var < 0.0) var = 0.0;
+        s_mean[g] = static_cast<float>(mean);
+        s_rstd[g] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+        if (stats_out != nullptr && blockIdx.x == 0) {
+          stats_out[(static_cast<long long>(n) * groups + g) * 2] = s_mean[g];
+          stats_out[(static_cast<long long>(n) * groups + g) * 2 + 1] = s_rstd[g];
+        }
+      }
+    }
+  }
+  __syncthreads();
+  const int lanes_v = vpp < NT ? vpp : NT;
+  const int pix_lanes = NT / lanes_v;
+  const int tv = t % lanes_v, tp = t / lanes_v;
+  const int p0 = blockIdx.x * pix_per_cta;
+  const int p1 = min(p0 + pix_per_cta, hw);
+  const TX* xb = x + static_cast<long long>(n) * hw * ld_x;
+  T* yb = y + static_cast<long long>(n) * hw * ld_y;
+  if (tp >= pix_lanes) return;
+  for (int v = tv; v < vpp; v += lanes_v) {
+    const int ch = v * 4;
+    const int g = ch / cpg;
+    const float mean = s_mean[g], rstd = s_rstd[g];
+    const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + ch));
+    const float4 be = __ldg(reinterpret_cast<const float4*>(beta + ch));
+    const float a0 = rstd * ga.x, a1 = rstd * ga.y, a2 = rstd * ga.z, a3 = rstd * ga.w;
+    const float b0 = be.x - mean * a0, b1 = be.y - mean * a1, b2 = be.z - mean * a2, b3 = be.w - mean * a3;
+    constexpr int U = 8;
+    for (int pix0 = p0 + tp; pix0 < p1; pix0 += U * pix_lanes) {
+      Vec4<TX> qx[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int pix = pix0 + u * pix_lanes;
+        if (pix < p1) qx[u].load(xb + static_cast<long long>(pix) * ld_x + ch);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int pix = pix0 + u * pix_lanes;
+        if (pix < p1) {
+          float f[4];
+          qx[u].get(f);
+          f[0] = fmaf(f[0], a0, b0); f[1] = fmaf(f[1], a1, b1); f[2] = fmaf(f[2], a2, b2); f[3] = fmaf(f[3], a3, b3);
+          if (act == EALDM_ACT_SILU) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) f[j] = SILU_FAST ? __fdividef(f[j], 1.0f + __expf(-f[j])) : silu_f(f[j]);
+          }
+          Vec4<T> q;
+          q.set(f);
+          q.store(yb + static_cast<long long>(pix) * ld_y + ch);
+        }
+      }
+    }
+  }
+}
+
+// stand-alone producer of the partials: one CTA per (32-pixel chunk, image), one thread per octet
+template <typename TX>
+__global__ void __launch_bounds__(NT)
+gn_partial_kernel(const TX* __restrict__ x, long long ld_x, int hw, int c, float2* __restrict__ partial,
+                  long long pld) {
+  const int n = blockIdx.y, chunk = blockIdx.x;
+  const TX* xb = x + (static_cast<long long>(n) * hw + chunk * 32) * ld_x;
+  float2* out = partial + (static_cast<long long>(n) * (hw >> 5) + chunk) * pld;
+  for (int o = threadIdx.x; o < (c >> 3); o += NT) {
+    float s = 0.f, ss = 0.f;
+    for (int p = 0; p < 32; ++p) {
+      Vec4<TX> q0, q1;
+      q0.load(xb + static_cast<long long>(p) * ld_x + o * 8);
+      q1.load(xb + static_cast<long long>(p) * ld_x + o * 8 + 4);
+      float f[4], h[4];
+      q0.get(f);
+      q1.get(h);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { s += f[j]; ss = fmaf(f[j], f[j], ss); }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { s += h[j]; ss = fmaf(h[j], h[j], ss); }
+    }
+    out[o] = make_float2(s, ss);
+  }
+}
+
 // pixel chunking shared by the workspace query and the launch
 static void gn_chunking(long long n, long long hw, int* pix_per_cta, long long* chunks) {
   // enough CTAs to fill 148 SMs (8 resident CTAs each) twice over, at least 16 pixels each
@@ -190,6 +316,18 @@ static int group_norm_cluster(const ealdm_group_norm_args* a, int cl, int ppc, s
 
 template <typename TX, typename T>
 static int group_norm_t(const ealdm_group_norm_args* a, cudaStream_t st) {
+  if (a->partial != nullptr) {
+    int ppc;
+    long long chunks;
+    gn_chunking(a->n, a->hw, &ppc, &chunks);
+    dim3 grid(static_cast<unsigned>(chunks), static_cast<unsigned>(a->n));
+    gn_apply_partial_kernel<TX, T><<<grid, NT, 0, st>>>(
+        reinterpret_cast<const TX*>(a->x), a->ld_x, reinterpret_cast<T*>(a->y), a->ld_y, static_cast<int>(a->hw),
+        static_cast<int>(a->c), a->groups, ppc, reinterpret_cast<const float2*>(a->partial), a->partial_ld, a->eps,
+        a->gamma, a->beta, a->act, a->stats_out);
+    EALDM_LAUNCH_CHECK();
+    return 0;
+  }
   {
     int ppc_c = 0, nsplit = 1;
     size_t smem = 0;
@@ -383,12 +521,17 @@ static int gn_cluster_plan(const ealdm_group_norm_args* a, int* ppc_out, size_t*
   const int cpg = static_cast<int>(a->c / a->groups);
   const int vpg = cpg >> 2;
   if (vpg < 1 || vpg > CNT) return 0;
-  const long long limit = 74 * 1024;
+  static const char* e_off = getenv("EALDM_GN_OFF");       // tuning switches
+  static const char* e_cl = getenv("EALDM_GN_MAXCL");
+  static const char* e_lim = getenv("EALDM_GN_LIMIT_KB");
+  if (e_off != nullptr) return 0;
+  const int max_cl = e_cl ? atoi(e_cl) : 16;
+  const long long limit = (e_lim ? atoi(e_lim) : 74) * 1024LL;
   for (int ns = 1; ns <= 8; ns *= 2) {
     if (a->groups % ns != 0) break;
     const long long row_bytes = (a->c / ns) * static_cast<long long>(sizeof(TX));
     if (row_bytes % 16 != 0) break;
-    for (int cl = 1; cl <= 16; cl *= 2) {
+    for (int cl = 1; cl <= max_cl; cl *= 2) {
       if (a->hw % cl != 0) break;
       const long long ppc = a->hw / cl;
       const long long smem = ppc * row_bytes + GN_CLUSTER_TAIL;
@@ -604,6 +747,8 @@ extern "C" int ealdm_group_norm(const ealdm_group_norm_args* a, ealdm_stream_t s
   EALDM_REQUIRE((a->c / a->groups) % 4 == 0 && a->ld_x % 4 == 0 && a->ld_y % 4 == 0,
                 "group_norm: channels per group, ld_x and ld_y must be multiples of 4");
   EALDM_REQUIRE(a->n > 0 && a->n <= 65535 && a->hw > 0, "group_norm: bad n/hw");
+  EALDM_REQUIRE(a->partial == nullptr || (a->hw % 32 == 0 && (a->c / a->groups) % 8 == 0 && a->partial_ld >= a->c / 8),
+                "group_norm: partial statistics need hw %% 32 == 0 and channels per group %% 8 == 0");
   EALDM_REQUIRE(a->act == EALDM_ACT_NONE || a->act == EALDM_ACT_SILU, "group_norm: bad act");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (a->dtype == EALDM_F32) return norm::group_norm_t<float, float>(a, st);
@@ -645,6 +790,23 @@ extern "C" int ealdm_softmax_rows(void* x, int64_t ld, int32_t dtype, int64_t ro
                                                                (int)c, scale);
   else
     return set_error(EALDM_EINVAL, "softmax_rows: bad dtype %d", dtype);
+  EALDM_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ealdm_gn_partial(const void* x, int64_t ld_x, int32_t dtype, int64_t n, int64_t hw, int64_t c,
+                                float* partial, int64_t partial_ld, ealdm_stream_t stream) {
+  EALDM_REQUIRE(x && partial && n > 0 && n <= 65535 && hw > 0 && hw % 32 == 0 && c > 0 && c % 8 == 0 &&
+                    ld_x % 4 == 0 && partial_ld >= c / 8,
+                "gn_partial: bad arguments (hw %% 32, c %% 8, ld_x %% 4)");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  dim3 grid(static_cast<unsigned>(hw / 32), static_cast<unsigned>(n));
+  if (dtype == EALDM_F32)
+    norm::gn_partial_kernel<float><<<grid, norm::NT, 0, st>>>(reinterpret_cast<const float*>(x), ld_x, (int)hw, (int)c,
+                                                              reinterpret_cast<float2*>(partial), partial_ld);
+  else
+    norm::gn_partial_kernel<bf16><<<grid, norm::NT, 0, st>>>(reinterpret_cast<const bf16*>(x), ld_x, (int)hw, (int)c,
+                                                             reinterpret_cast<float2*>(partial), partial_ld);
   EALDM_LAUNCH_CHECK();
   return 0;
 }

@@ -10,6 +10,11 @@ import torch
 from . import _lib as L
 
 
+import os as _os
+
+_NO_GN_PARTIAL = bool(_os.environ.get("EALDM_NO_GN_PARTIAL"))   # A/B switch: GroupNorm with its own statistics pass
+
+
 def _dt(t: torch.dtype) -> int:
     if t == torch.float32:
         return L.F32
@@ -27,16 +32,22 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
 
 
 class Act:
-    """An NHWC activation: `c` channels starting at column `c0` of a 2-D [n*h*w, ld] buffer."""
-    __slots__ = ("buf", "n", "h", "w", "c", "c0")
+    """An NHWC activation: `c` channels starting at column `c0` of a 2-D [n*h*w, ld] buffer.
+    `gp` (optional) is the GroupNorm partial-statistics buffer of the WHOLE underlying buffer,
+    [n*h*w/32, ld/8, 2] fp32 = {sum, sum of squares} per (32-pixel chunk, 8-channel octet): a tcgen05 convolution
+    that writes this activation fills its column window of `gp`, and a GroupNorm that reads the activation then
+    skips its statistics pass."""
+    __slots__ = ("buf", "n", "h", "w", "c", "c0", "gp")
 
-    def __init__(self, buf: torch.Tensor, n: int, h: int, w: int, c: Optional[int] = None, c0: int = 0):
+    def __init__(self, buf: torch.Tensor, n: int, h: int, w: int, c: Optional[int] = None, c0: int = 0,
+                 gp: Optional[torch.Tensor] = None):
         assert buf.dim() == 2 and buf.is_contiguous() and buf.shape[0] == n * h * w, \
             (tuple(buf.shape), n, h, w)
         self.buf, self.n, self.h, self.w = buf, n, h, w
         self.c0 = c0
         self.c = buf.shape[1] - c0 if c is None else c
         assert self.c0 + self.c <= buf.shape[1]
+        self.gp = gp
 
     @staticmethod
     def empty(n, h, w, c, dtype, device) -> "Act":
@@ -59,11 +70,26 @@ class Act:
         return self.buf.dtype
 
     def cols(self, c0: int, c: int) -> "Act":
-        return Act(self.buf, self.n, self.h, self.w, c, self.c0 + c0)
+        return Act(self.buf, self.n, self.h, self.w, c, self.c0 + c0, self.gp)
 
     def reshape(self, n, h, w) -> "Act":
         assert n * h * w == self.rows
         return Act(self.buf, n, h, w, self.c, self.c0)
+
+    def with_gn_partial(self) -> "Act":
+        """Attach a (not yet filled) partial-statistics buffer; None if the shape does not qualify."""
+        if _NO_GN_PARTIAL:
+            return self
+        hw = self.h * self.w
+        pow2 = lambda v: v & (v - 1) == 0  # noqa: E731
+        if (hw % 32 == 0 and pow2(self.w) and pow2(self.h) and self.ld % 32 == 0 and self.c0 % 32 == 0
+                and self.c % 32 == 0 and (self.w >= 32 or self.h % (32 // self.w) == 0)):
+            self.gp = torch.empty((self.rows // 32, self.ld // 8, 2), dtype=torch.float32, device=self.buf.device)
+        return self
+
+    @property
+    def gp_ptr(self) -> int:
+        return self.gp.data_ptr() + (self.c0 // 8) * 8
 
     def view2d(self) -> torch.Tensor:
         return self.buf[:, self.c0:self.c0 + self.c]
@@ -121,12 +147,21 @@ def conv(srcs: Sequence[ConvIn], weight: torch.Tensor, out: Act, *, bias: Option
     if out2 is not None:
         assert out2.dtype == x0.dtype and out2.rows == out.rows and out2.c == out.c
         a.out2, a.ld_out2 = out2.ptr, out2.ld
+    if out.gp is not None:     # the epilogue also produces the GroupNorm partial statistics of `out`
+        assert x0.dtype == torch.bfloat16 and act != L.ACT_GEGLU
+        a.gn_partial, a.gn_ld = out.gp_ptr, out.gp.shape[1]
+        if impl == L.IMPL_AUTO:
+            a.impl = L.IMPL_TCGEN05   # only the tcgen05 epilogue writes them: fail loudly rather than skip silently
     L.check(lib.ealdm_conv(C.byref(a), _stream()))
     return out
 
 
 def linear(x: Act, weight: torch.Tensor, out: Act, **kw) -> Act:
     """nn.Linear over the rows of x (a 1x1 'convolution' with n=1, h=1, w=rows)."""
+    if out.gp is not None:
+        # keep the image geometry: the epilogue's GroupNorm partials are per (image, 32-pixel chunk)
+        assert (x.n, x.h, x.w) == (out.n, out.h, out.w)
+        return conv([ConvIn(x)], weight, out, **kw)
     xs = Act(x.buf, 1, 1, x.rows, x.c, x.c0)
     os_ = Act(out.buf, 1, 1, out.rows, out.c, out.c0)
     res = kw.pop("residual", None)
@@ -167,8 +202,18 @@ def group_norm(x: Act, gamma: torch.Tensor, beta: torch.Tensor, eps: float, out:
     if stats_out is not None:
         assert stats_out.dtype == torch.float32 and stats_out.is_contiguous() and stats_out.numel() == x.n * groups * 2
         a.stats_out = stats_out.data_ptr()
+    if x.gp is not None and (x.c // groups) % 8 == 0:
+        a.partial, a.partial_ld = x.gp_ptr, x.gp.shape[1]
     L.check(lib.ealdm_group_norm(C.byref(a), _stream()))
     return out
+
+
+def gn_partial(x: Act) -> Act:
+    """Fill x.gp with a stand-alone kernel (for activations that did not come out of the tcgen05 epilogue)."""
+    lib = L.load()
+    assert x.gp is not None
+    L.check(lib.ealdm_gn_partial(x.ptr, x.ld, _dt(x.dtype), x.n, x.h * x.w, x.c, x.gp_ptr, x.gp.shape[1], _stream()))
+    return x
 
 
 def layer_norm(x: Act, gamma: torch.Tensor, beta: torch.Tensor, eps: float, out: Act) -> Act:

@@ -119,7 +119,7 @@ class UNetTrainEngine(UNetEngine):
         return torch.empty((n, 32, 2), dtype=torch.float32, device=self.dev)
 
     def _gdual(self, n, h, w, c) -> Dual:
-        return self._new_dual(n, h, w, c)
+        return self._new_dual(n, h, w, c, gn=False)   # gradients need no GroupNorm statistics
 
     # ---- layers: forward that records its backward -----------------------------------------------------------
     def _res(self, d, x: Dual, emb_all, dest: Optional[Dual]) -> Dual:
@@ -130,6 +130,8 @@ class UNetTrainEngine(UNetEngine):
         hn = self._new(n, h, w, cin)
         ops.group_norm(x.f, d["gn1"][0], d["gn1"][1], 1e-5, hn, self.stats, silu=True, stats_out=st1)
         h1 = self._new(n, h, w, cout, torch.float32)
+        if self.dt == torch.bfloat16:
+            h1.with_gn_partial()
         ops.conv([ConvIn(hn, 3, 1, 1)], d["conv1"].w, h1, bias=d["conv1"].b, rowvec=emb_all, rowvec_col0=d["emb_col0"])
         hn2 = self._new(n, h, w, cout)
         ops.group_norm(h1, d["gn2"][0], d["gn2"][1], 1e-5, hn2, self.stats, silu=True, stats_out=st2)
@@ -305,7 +307,7 @@ class UNetTrainEngine(UNetEngine):
         conv = d["mod"]
         n, h, w = x.f.n, x.f.h, x.f.w
         out = dst if dst is not None else self._new_dual(n, h, w, d["conv"].cout)
-        ops.conv([ConvIn(x.h, 3, 1, 1)], d["conv"].w, out.f, bias=d["conv"].b, out2=self._out2(out))
+        self._conv_first(d, x, out)
 
         def bwd(g: Dual, extra):
             ops.colsum(g.h, _grad1d(conv.bias), self.ws)

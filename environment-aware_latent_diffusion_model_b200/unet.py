@@ -464,9 +464,21 @@ class UNetEngine:
     def _new(self, n, h, w, c, dtype=None) -> Act:
         return Act.empty(n, h, w, c, dtype or self.dt, self.dev)
 
-    def _new_dual(self, n, h, w, c) -> "Dual":
+    def _new_dual(self, n, h, w, c, gn: bool = True) -> "Dual":
+        """A residual-stream tensor.  In bf16 mode its fp32 master carries a GroupNorm partial-statistics buffer
+        that the producing tcgen05 epilogue fills, so the GroupNorm reading it is a single streaming pass."""
         f = self._new(n, h, w, c, torch.float32)
+        if gn and self.dt == torch.bfloat16:
+            f.with_gn_partial()
         return Dual(f, f if self.dt == torch.float32 else self._new(n, h, w, c))
+
+    def _conv_first(self, d, x: "Dual", out: "Dual") -> "Dual":
+        """input_blocks.0: the 4-channel conv runs on the SIMT kernel, which has no statistics epilogue."""
+        plain = Act(out.f.buf, out.f.n, out.f.h, out.f.w, out.f.c, out.f.c0)
+        ops.conv([ConvIn(x.h, 3, 1, 1)], d["conv"].w, plain, bias=d["conv"].b, out2=self._out2(out))
+        if out.f.gp is not None:
+            ops.gn_partial(out.f)
+        return out
 
     def _out2(self, d: "Dual"):
         return None if d.h is d.f else d.h
@@ -476,6 +488,8 @@ class UNetEngine:
         hn = self._new(n, h, w, x.f.c)
         ops.group_norm(x.f, d["gn1"][0], d["gn1"][1], 1e-5, hn, self.stats, silu=True)
         h1 = self._new(n, h, w, d["cout"], torch.float32)   # bf16 here costs ~40 % of the 1e-2 eps budget (measured)
+        if self.dt == torch.bfloat16:
+            h1.with_gn_partial()
         ops.conv([ConvIn(hn, 3, 1, 1)], d["conv1"].w, h1, bias=d["conv1"].b, rowvec=emb_all,
                  rowvec_col0=d["emb_col0"])
         hn2 = self._new(n, h, w, d["cout"])
@@ -559,8 +573,7 @@ class UNetEngine:
                 x = self._ab(d, x, dst)
             elif k == "conv_in":
                 out = dst if dst is not None else self._new_dual(n, h, w, d["conv"].cout)
-                ops.conv([ConvIn(x.h, 3, 1, 1)], d["conv"].w, out.f, bias=d["conv"].b, out2=self._out2(out))
-                x = out
+                x = self._conv_first(d, x, out)
             elif k == "down":
                 out = dst if dst is not None else self._new_dual(n, h // 2, w // 2, d["conv"].cout)
                 ops.conv([ConvIn(x.h, 3, 2, 1)], d["conv"].w, out.f, bias=d["conv"].b, out2=self._out2(out))

@@ -103,6 +103,13 @@ typedef struct {
   void* out2;      /* optional second copy of the result in `dtype` (the bf16 operand shadow of an
                       fp32 residual-stream tensor), pitch ld_out2; NULL if unused */
   int64_t ld_out2;
+  /* optional GroupNorm partial statistics of the result, produced by the epilogue (tcgen05 path only, h_out*w_out a
+     multiple of 32, w_out a power of two): gn_partial[((img*(hw/32) + chunk)*gn_ld + j/8)*2 + {0,1}] = {sum, sum of
+     squares} of output channels [8*(j/8), 8*(j/8)+8) over the 32 pixels [32*chunk, 32*chunk+32) of image img.
+     gn_partial points at the octet of output column 0; a later ealdm_group_norm that is given the same buffer
+     skips its statistics pass.  Replaces the first half of GroupNorm32 (util.py:214-216). */
+  float* gn_partial;
+  int64_t gn_ld; /* octets (float2 entries) per (image, chunk) row of the partial buffer */
 } ealdm_conv_args;
 
 int ealdm_conv(const ealdm_conv_args* a, ealdm_stream_t stream);
@@ -131,9 +138,15 @@ typedef struct {
   int32_t x_f32; /* 1: x is float regardless of dtype (fp32 residual stream -> bf16 GEMM operand) */
   int32_t reserved;
   float* stats_out; /* optional [n, groups, 2] = (mean, rstd) per (image, group), saved for the backward */
+  const float* partial; /* optional: partial statistics of x written by the producing ealdm_conv (gn_partial) or by
+                           ealdm_gn_partial; the kernel then only streams x once (no reduction pass) */
+  int64_t partial_ld;
 } ealdm_group_norm_args;
 
 int64_t ealdm_group_norm_workspace_bytes(int64_t n, int64_t hw, int64_t c);
+/* stand-alone producer of the partial statistics (for tensors that did not come out of the tcgen05 epilogue) */
+int ealdm_gn_partial(const void* x, int64_t ld_x, int32_t dtype, int64_t n, int64_t hw, int64_t c, float* partial,
+                     int64_t partial_ld, ealdm_stream_t stream);
 int ealdm_group_norm(const ealdm_group_norm_args* a, ealdm_stream_t stream);
 
 /* LayerNorm over the last dimension. Replaces nn.LayerNorm in attention.py:203-205,211-215. */

@@ -370,3 +370,44 @@ def test_errors_are_reported():
     out = Act.empty(1, 1, 4, 6, torch.float32, DEV)
     with pytest.raises(L.EaldmError):
         ops.layer_norm(x, torch.ones(6, device=DEV), torch.zeros(6, device=DEV), 1e-5, out)  # c % 4 != 0
+
+
+@pytest.mark.parametrize("n,c,h,w,co", [(2, 128, 32, 32, 256), (3, 256, 16, 16, 512), (5, 512, 8, 8, 1024),
+                                        (2, 64, 64, 64, 128)])
+@pytest.mark.parametrize("silu", [True, False])
+def test_conv_epilogue_groupnorm_partials(n, c, h, w, co, silu):
+    """The tcgen05 conv epilogue writes {sum, sum of squares} per (image, 32-pixel chunk, 8-channel octet); a
+    GroupNorm given that buffer is one streaming pass and must equal GroupNorm of the stored fp32 output.  The
+    output is a column window of a wider (concat) buffer whose other half is filled by the stand-alone kernel."""
+    dtype = torch.bfloat16
+    x = torch.randn(n, c, h, w, generator=g(61)).to(DEV)
+    wt = (torch.randn(co, c, 3, 3, generator=g(62)) / math.sqrt(9 * c)).to(DEV)
+    b = torch.randn(co, generator=g(63)).to(DEV)
+    other = torch.randn(n, 64, h, w, generator=g(64)).to(DEV)
+    cat = Act.empty(n, h, w, co + 64, torch.float32, DEV).with_gn_partial()
+    assert cat.gp is not None
+    left, right = cat.cols(0, co), cat.cols(co, 64)
+    ops.conv([ConvIn(to_act(x, dtype), 3, 1, 1)], pack_w(wt, dtype), left, bias=b)
+    right.view2d().copy_(other.permute(0, 2, 3, 1).reshape(-1, 64))
+    ops.gn_partial(right)
+    # the partials themselves
+    full = from_act(cat)                                      # [n, co+64, h, w] fp32 as stored
+    ref_p = full.reshape(n, (co + 64) // 8, 8, h * w // 32, 32)
+    ref_sum = ref_p.sum(dim=(2, 4)).permute(0, 2, 1).reshape(-1, (co + 64) // 8)
+    ref_sq = (ref_p ** 2).sum(dim=(2, 4)).permute(0, 2, 1).reshape(-1, (co + 64) // 8)
+    assert rel_l2(cat.gp[..., 0], ref_sum) < 1e-5 and rel_l2(cat.gp[..., 1], ref_sq) < 1e-5
+    # GroupNorm over the whole concat buffer (groups of (co+64)/32 channels) and over the left window alone
+    for view in (cat, left):
+        cc = view.c
+        if (cc // 32) % 8:
+            continue
+        gamma = (1 + 0.2 * torch.randn(cc, generator=g(65))).to(DEV)
+        beta = (0.2 * torch.randn(cc, generator=g(66))).to(DEV)
+        y = Act.empty(n, h, w, cc, dtype, DEV)
+        stats = torch.empty(n, 32, 2, device=DEV)
+        ops.group_norm(view, gamma, beta, 1e-5, y, silu=silu, stats_out=stats)
+        xr = from_act(view)
+        ref = F.group_norm(xr, 32, gamma, beta, 1e-5)
+        ref = F.silu(ref) if silu else ref
+        assert rel_l2(from_act(y), ref) < 6e-3
+        assert rel_l2(stats[..., 0], xr.reshape(n, 32, -1).mean(-1)) < 1e-4

@@ -98,6 +98,19 @@ def make_gn(n, hw, c, x_dt=F32, silu=True):
     return run, 0.0, bsz(x.buf) + bsz(y.buf)
 
 
+def make_gn_partial(n, hw, c, silu=True):
+    """GroupNorm fed by the conv epilogue's partial statistics: a single streaming pass."""
+    side = int(hw ** 0.5)
+    x = Act(rnd(n * hw, c, F32), n, side, side).with_gn_partial()
+    ops.gn_partial(x)
+    y = Act.empty(n, side, side, c, BF, DEV)
+    gamma, beta = torch.ones(c, device=DEV), torch.zeros(c, device=DEV)
+
+    def run():
+        ops.group_norm(x, gamma, beta, 1e-5, y, silu=silu)
+    return run, 0.0, bsz(x.buf) + bsz(y.buf)
+
+
 def make_ln(rows, c, x_dt=F32):
     x = Act(rnd(rows, c, x_dt), 1, 1, rows)
     y = Act(torch.empty(rows, c, device=DEV, dtype=BF), 1, 1, rows)
@@ -138,6 +151,10 @@ CASES = {
     "xattn_l2": lambda: make_xattn(N, 32, 64),
     # norms
     "gn_256_l0": lambda: make_gn(N, 1024, 256),
+    "gn_256_l0_partial": lambda: make_gn_partial(N, 1024, 256),
+    "gn_512_l0_partial": lambda: make_gn_partial(N, 1024, 512),
+    "gn_1024_l1_partial": lambda: make_gn_partial(N, 256, 1024),
+    "gn_2048_l2_partial": lambda: make_gn_partial(N, 64, 2048),
     "gn_256_l0_bf16in": lambda: make_gn(N, 1024, 256, x_dt=BF),
     "gn_512_l0": lambda: make_gn(N, 1024, 512),
     "gn_768_l0": lambda: make_gn(N, 1024, 768),
