@@ -135,14 +135,15 @@ def test_adamw_steps_reduce_the_loss():
     ld.eval()
 
 
-@pytest.mark.parametrize("use_graph", [False, True])
+@pytest.mark.parametrize("use_graph", [False, True, "segments"])
 def test_fused_step_matches_autograd_path(use_graph):
     """FusedTrainStep (the CUDA-graph-capturable trainer loop) == p_losses + loss.backward(), bit for bit."""
     from ealdm_b200.train import FusedTrainStep
     ld, unet, loss, _ = run_step("bf16")
     ref = {n: p.grad.clone() for n, p in unet.named_parameters()}
     G = gold("p_losses.pt")
-    fused = FusedTrainStep(ld, use_graph=use_graph)
+    fused = FusedTrainStep(ld, use_graph=bool(use_graph))
+    fused.force_segments = use_graph == "segments"     # the multi-GPU capture layout (5 graphs), on one rank
     args = (G["x0"].cuda(), G["cond2"].cuda(), G["t"].cuda(), G["noise"].cuda())
     for it in range(3 if use_graph else 1):      # graph: capture, then two replays
         fused.buckets.zero_()
@@ -151,6 +152,8 @@ def test_fused_step_matches_autograd_path(use_graph):
         assert float(l2) == float(loss)
         for n, p in unet.named_parameters():
             assert torch.equal(p.grad, ref[n]), (it, n)
+    if use_graph == "segments":
+        assert len(next(iter(fused._graphs.values()))[0]) == 5
     unet.grad_ready_hook = None
     for p in unet.parameters():
         p.grad = None
