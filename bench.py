@@ -198,7 +198,11 @@ def run_train(args):
     fused = FusedTrainStep(ld, use_graph=not args.no_graph, bucket_mb=64.0)
     gb = fused.buckets
     lr = 1.0e-6 * world * B      # main.py:741-745: accumulate * ngpu * bs * base_lr
-    opt = torch.optim.AdamW(unet.parameters(), lr=lr, fused=True)
+    if args.torch_optim:         # torch.optim.AdamW(fused=True), no EMA
+        opt = torch.optim.AdamW(unet.parameters(), lr=lr, fused=True)
+    else:                        # AdamW + EMA shadow (use_ema: True in the reference config) + bf16 weights, one kernel
+        from ealdm_b200.optim import FusedAdamWEMA
+        opt = FusedAdamWEMA(gb, lr=lr)
     g = torch.Generator().manual_seed(100 + rank)
     x0_h = torch.randn(B, 4, 32, 32, generator=g).pin_memory()
     c2_h = torch.randn(2 * B, 4, 512, generator=g).pin_memory()
@@ -219,9 +223,14 @@ def run_train(args):
         else:                       # the fused step (one CUDA graph unless --no-graph)
             loss = fused(x0, c2, t, noise)
             ev[1].record()
-        gb.finish()
-        ev[2].record()
-        opt.step()
+        if args.torch_optim:
+            gb.finish()
+            ev[2].record()
+            opt.step()
+        else:
+            gb.finish(average=False)
+            ev[2].record()
+            opt.step(grads_are_sums=True)
         ev[3].record()
         lv = float(loss)            # device -> host read of the step's result
         if record:
@@ -261,7 +270,7 @@ def run_train(args):
     peaks = load_peaks()
     model_tf = 3 * 2 * B * CFG.UNET_STDIFF_GFLOP_PER_SAMPLE / 1e3     # fwd + dgrad + wgrad, per GPU per step
     if rank == 0:
-        line = {"metric": "training samples/sec (UNet fwd+bwd, eps loss, AdamW)", "value": B * world / (ms_per_step * 1e-3),
+        line = {"metric": "training samples/sec (UNet fwd+bwd, eps loss, AdamW + EMA)", "value": B * world / (ms_per_step * 1e-3),
                 "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "bf16", "data": "synthetic",
@@ -269,7 +278,11 @@ def run_train(args):
                                        "the loss, AdamW, bucketed NCCL gradient all-reduce (BASELINE.json configs[4])",
                            "batch_per_gpu": B, "global_batch": B * world, "lr": lr,
                            "step": "autograd (p_losses + loss.backward())" if args.autograd else
-                                   ("fused step, one CUDA graph" if not args.no_graph else "fused step, eager launches"),
+                                   ("fused step, eager launches" if args.no_graph else
+                                    ("fused step, one CUDA graph" if world == 1 else
+                                     "fused step, 5 CUDA-graph segments with the all-reduce launched between them")),
+                           "optimizer": "torch.optim.AdamW(fused=True)" if args.torch_optim else
+                                        "ealdm_adamw_ema_step (AdamW + EMA + bf16 weights in one pass)",
                            "parallelism": f"data-parallel x{world}, 64 MiB gradient buckets"},
                 "clocks": clk, "loss": lv, "gpu_launches": int(launches * args.steps), "launches_per_step": int(launches),
                 "phases_ms": {k: sum(v) / len(v) for k, v in phases.items()},
@@ -357,6 +370,7 @@ def main():
     ap.add_argument("--ddim-steps", type=int, default=50)
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--autograd", action="store_true", help="train workload: p_losses under torch.autograd")
+    ap.add_argument("--torch-optim", action="store_true", help="train workload: torch.optim.AdamW(fused=True), no EMA")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ncu-window", action="store_true",
                     help="cudaProfilerStart/Stop around the timed region (for `ncu --profile-from-start off`)")

@@ -28,7 +28,7 @@ EXPORTS = [
     "ealdm_group_norm_bwd_workspace_bytes", "ealdm_layer_norm_bwd", "ealdm_layer_norm_bwd_workspace_bytes",
     "ealdm_attention_bwd", "ealdm_attention_bwd_workspace_bytes", "ealdm_geglu", "ealdm_geglu_bwd",
     "ealdm_silu", "ealdm_silu_bwd", "ealdm_colsum", "ealdm_colsum_workspace_bytes", "ealdm_zero_insert2x",
-    "ealdm_sumpool2x2", "ealdm_cfg_mse_bwd", "ealdm_gn_partial",
+    "ealdm_sumpool2x2", "ealdm_cfg_mse_bwd", "ealdm_gn_partial", "ealdm_adamw_ema_step",
 ]
 WGRAD_PACKED, WGRAD_OIHW = 0, 1
 
@@ -119,6 +119,14 @@ class AttentionBwdArgs(C.Structure):
                 ("lse", C.c_void_p)]
 
 
+class AdamWArgs(C.Structure):
+    _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
+                ("ema", C.c_void_p), ("param_bf16", C.c_void_p), ("numel", C.c_int64), ("step", C.c_int64),
+                ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
+                ("weight_decay", C.c_float), ("grad_scale", C.c_float), ("ema_decay", C.c_float),
+                ("reserved", C.c_int32)]
+
+
 class EaldmError(RuntimeError):
     pass
 
@@ -187,6 +195,7 @@ def _declare(lib):
         ("ealdm_sumpool2x2", [vp, i64, i32, i64, i64, i64, i64, vp, i64, vp, i64, vp, i64, vp]),
         ("ealdm_cfg_mse_bwd", [vp, vp, vp, vp, f32, i64, i64, vp, vp, vp]),
         ("ealdm_gn_partial", [vp, i64, i32, i64, i64, i64, vp, i64, vp]),
+        ("ealdm_adamw_ema_step", [C.POINTER(AdamWArgs), vp]),
     ]:
         fn = getattr(lib, name)
         fn.restype = C.c_int

@@ -82,8 +82,8 @@ class GradBuckets:
                 seen.add(id(p))
                 order.append(p)
 
-        def offset():
-            return sum(p.numel() for p in order)
+        def offset():   # every tensor starts on a multiple of 8 elements (16-byte aligned bf16 views for TMA)
+            return sum((p.numel() + 7) // 8 * 8 for p in order)
 
         take(unet.out)
         self.ready_at[("head", 0)] = offset()
@@ -103,10 +103,12 @@ class GradBuckets:
         total = offset()
         dev = order[0].device
         self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.offsets = []
         off = 0
         for p in order:
+            self.offsets.append(off)
             p.grad = self.flat[off:off + p.numel()].view_as(p)
-            off += p.numel()
+            off += (p.numel() + 7) // 8 * 8
         step = max(1, int(bucket_mb * (1 << 20) / 4))
         self.bounds = [(lo, min(lo + step, total)) for lo in range(0, total, step)]
         self._next, self._works = 0, []
@@ -128,11 +130,12 @@ class GradBuckets:
     def block_done(self, kind: str, idx: int):
         self._launch_upto(self.ready_at.get((kind, idx), 0))
 
-    def finish(self):
-        """Reduce whatever is left, wait for every bucket, and turn the sums into means."""
+    def finish(self, average: bool = True):
+        """Reduce whatever is left, wait for every bucket, and (unless the optimizer folds the division into its own
+        pass, optim.FusedAdamWEMA.step(grads_are_sums=True)) turn the sums into means."""
         self._launch_upto(self.flat.numel())
         for w in self._works:
             w.wait()
         self._works = []
-        if self.world > 1:
+        if self.world > 1 and average:
             self.flat.mul_(1.0 / self.world)

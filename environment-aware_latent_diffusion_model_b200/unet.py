@@ -452,7 +452,8 @@ class UNetEngine:
         """Compute-dtype copy of a parameter, made once per engine."""
         t = self._cast_cache.get(id(w))
         if t is None:
-            t = w.detach().to(self.dt)
+            view = getattr(w, "_bf16_view", None)     # optim.FusedAdamWEMA keeps a bf16 copy of every parameter
+            t = view if (view is not None and self.dt == torch.bfloat16) else w.detach().to(self.dt)
             self._cast_cache[id(w)] = t
         return t
 

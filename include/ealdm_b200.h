@@ -424,6 +424,29 @@ int ealdm_cfg_mse_bwd(const float* e_uncond, const float* e_cond, const float* t
                       float cfg_scale, int64_t batch, int64_t per_sample, float* de_uncond, float* de_cond,
                       ealdm_stream_t stream);
 
+/*
+ * One optimizer step over flat fp32 buffers of `numel` elements: AdamW exactly as torch.optim.AdamW (decoupled weight
+ * decay, bias correction with the 1-based `step`; reference: configure_optimizers, ddpm.py:1409-1431), then the EMA
+ * shadow update shadow -= (1 - ema_decay) * (shadow - param) (LitEma.forward, ldm/modules/ema.py:25-44; the caller
+ * computes ema_decay = min(decay, (1 + num_updates) / (10 + num_updates))), then the bf16 copy of the new weights.
+ * `grad` is multiplied by grad_scale first (1 / world size when the buffer holds the all-reduced SUM).
+ * ema and param_bf16 may be NULL.
+ */
+typedef struct {
+  float* param;
+  const float* grad;
+  float* exp_avg;
+  float* exp_avg_sq;
+  float* ema;
+  void* param_bf16;
+  int64_t numel;
+  int64_t step;
+  float lr, beta1, beta2, eps, weight_decay, grad_scale, ema_decay;
+  int32_t reserved;
+} ealdm_adamw_args;
+
+int ealdm_adamw_ema_step(const ealdm_adamw_args* a, ealdm_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

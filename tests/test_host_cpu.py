@@ -210,7 +210,7 @@ def _grad_worker(rank, world, port, q):
     gb = GradBuckets(unet, bucket_mb=0.05)          # many small buckets
     assert len(gb.bounds) > 4
     # every parameter got a view of the flat buffer, exactly once
-    assert sum(p.numel() for p in unet.parameters()) == gb.flat.numel()
+    assert sum((p.numel() + 7) // 8 * 8 for p in unet.parameters()) == gb.flat.numel()
     for _ in range(2):                              # two "steps": zero_() must re-arm the buckets
         gb.zero_()
         for i, p in enumerate(unet.parameters()):

@@ -158,3 +158,42 @@ def test_fused_step_matches_autograd_path(use_graph):
     for p in unet.parameters():
         p.grad = None
     ld.eval()
+
+
+def test_fused_adamw_ema_matches_torch_adamw_and_litema():
+    """ealdm_adamw_ema_step == torch.optim.AdamW (single-tensor reference math) + the LitEma update, on the flat
+    buffers of a small UNet; the bf16 copy equals the cast of the new weights."""
+    from ealdm_b200.optim import FusedAdamWEMA
+    from ealdm_b200.parallel import GradBuckets
+    from ealdm_b200.unet import UNetModel
+    tiny = dict(image_size=8, in_channels=4, model_channels=64, out_channels=4, num_res_blocks=1,
+                attention_resolutions=[1, 2], channel_mult=(1, 2), num_head_channels=32,
+                use_spatial_transformer=True, transformer_depth=1, context_dim=64)
+    torch.manual_seed(0)
+    unet = UNetModel(**tiny).cuda()
+    ref = UNetModel(**tiny).cuda()
+    ref.load_state_dict(unet.state_dict())
+    gb = GradBuckets(unet, bucket_mb=1.0)
+    opt = FusedAdamWEMA(gb, lr=3e-4, weight_decay=1e-2, ema_decay=0.9999)
+    ropt = torch.optim.AdamW(ref.parameters(), lr=3e-4, weight_decay=1e-2, foreach=False, fused=False)
+    shadow = {n: p.detach().clone() for n, p in ref.named_parameters()}
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    for step in range(1, 4):
+        gb.zero_()
+        for (n, p), (_, q) in zip(unet.named_parameters(), ref.named_parameters()):
+            gr = torch.randn(p.shape, generator=gen, device="cuda") * 0.1
+            p.grad.copy_(gr)
+            q.grad = gr.clone()
+        gb.finish()
+        opt.step()
+        ropt.step()
+        decay = min(0.9999, (1 + step) / (10 + step))
+        for n, q in ref.named_parameters():
+            shadow[n].sub_((1.0 - decay) * (shadow[n] - q.detach()))
+    ema = opt.ema_views()
+    worst = 0.0
+    for (n, p), (_, q) in zip(unet.named_parameters(), ref.named_parameters()):
+        worst = max(worst, rel_l2(p.detach(), q.detach()), rel_l2(ema[id(p)], shadow[n]))
+        assert torch.equal(p._bf16_view, p.detach().to(torch.bfloat16)), n
+    print(f"fused AdamW+EMA vs torch: worst rel_l2 {worst:.3e}")
+    assert worst < 1e-6
