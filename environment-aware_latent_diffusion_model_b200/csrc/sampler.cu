@@ -103,6 +103,36 @@ cfg_mse_kernel(const float* __restrict__ eu, const float* __restrict__ ec,
   }
 }
 
+// PLMS (pseudo linear multistep) eps combination, plms.py:213-231, in the reference's fp32 operation order:
+//   e_t = e_uncond + s*(e_cond - e_uncond)   (or e_cond)
+//   mode 1: (e_t + o1) / 2   mode 2: (3 e_t - o1) / 2   mode 3: (23 e_t - 16 o1 + 5 o2) / 12
+//   mode 4: (55 e_t - 59 o1 + 37 o2 - 9 o3) / 24
+__global__ void __launch_bounds__(NT)
+plms_eps_kernel(const float* __restrict__ eu, const float* __restrict__ ec, float cfg_scale,
+                const float* __restrict__ o1, const float* __restrict__ o2, const float* __restrict__ o3, int mode,
+                float* __restrict__ e_t_out, float* __restrict__ e_prime_out, long long numel) {
+  for (long long i = blockIdx.x * static_cast<long long>(NT) + threadIdx.x; i < numel;
+       i += static_cast<long long>(NT) * gridDim.x) {
+    const float c = ec[i];
+    const float e = eu ? __fadd_rn(eu[i], __fmul_rn(cfg_scale, __fsub_rn(c, eu[i]))) : c;
+    if (e_t_out) e_t_out[i] = e;
+    float r = e;
+    if (mode == 1) {
+      r = __fdiv_rn(__fadd_rn(e, o1[i]), 2.0f);
+    } else if (mode == 2) {
+      r = __fdiv_rn(__fsub_rn(__fmul_rn(3.0f, e), o1[i]), 2.0f);
+    } else if (mode == 3) {
+      r = __fdiv_rn(__fadd_rn(__fsub_rn(__fmul_rn(23.0f, e), __fmul_rn(16.0f, o1[i])), __fmul_rn(5.0f, o2[i])), 12.0f);
+    } else if (mode == 4) {
+      r = __fdiv_rn(__fsub_rn(__fadd_rn(__fsub_rn(__fmul_rn(55.0f, e), __fmul_rn(59.0f, o1[i])),
+                                        __fmul_rn(37.0f, o2[i])),
+                              __fmul_rn(9.0f, o3[i])),
+                    24.0f);
+    }
+    if (e_prime_out) e_prime_out[i] = r;
+  }
+}
+
 // gradient of sum_b w[b] * mean_i (guided - target)^2 w.r.t. e_cond / e_uncond
 __global__ void __launch_bounds__(NT)
 cfg_mse_bwd_kernel(const float* __restrict__ eu, const float* __restrict__ ec, const float* __restrict__ target,
@@ -191,6 +221,19 @@ extern "C" int ealdm_cfg_mse_bwd(const float* e_uncond, const float* e_cond, con
   sampler::cfg_mse_bwd_kernel<<<static_cast<unsigned>(blocks < 2368 ? blocks : 2368), sampler::NT, 0,
                                 static_cast<cudaStream_t>(stream)>>>(e_uncond, e_cond, target, w, cfg_scale,
                                                                      per_sample, total, de_uncond, de_cond);
+  EALDM_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ealdm_plms_eps(const float* e_uncond, const float* e_cond, float cfg_scale, const float* old1,
+                              const float* old2, const float* old3, int32_t mode, float* e_t_out, float* e_prime_out,
+                              int64_t numel, ealdm_stream_t stream) {
+  EALDM_REQUIRE(e_cond && numel > 0 && mode >= 0 && mode <= 4, "plms_eps: bad arguments");
+  EALDM_REQUIRE((mode < 1 || old1) && (mode < 3 || old2) && (mode < 4 || old3), "plms_eps: missing eps history");
+  const long long blocks = ceil_div(numel, sampler::NT);
+  sampler::plms_eps_kernel<<<static_cast<unsigned>(blocks < 2368 ? blocks : 2368), sampler::NT, 0,
+                             static_cast<cudaStream_t>(stream)>>>(e_uncond, e_cond, cfg_scale, old1, old2, old3, mode,
+                                                                  e_t_out, e_prime_out, numel);
   EALDM_LAUNCH_CHECK();
   return 0;
 }

@@ -323,6 +323,18 @@ def ddim_step(x, e_cond, *, e_uncond=None, noise=None, cfg_scale=1.0, sqrt_one_m
     return (x_prev, pred, e) if want_e else (x_prev, pred)
 
 
+def plms_eps(e_cond, *, e_uncond=None, cfg_scale=1.0, old=(), mode=0):
+    """ealdm_plms_eps: returns (e_t, e_prime); `old` = (old_eps[-1], old_eps[-2], old_eps[-3]) as far as needed."""
+    lib = L.load()
+    for t in (e_cond, e_uncond) + tuple(old):
+        assert t is None or (t.dtype == torch.float32 and t.is_contiguous() and t.numel() == e_cond.numel())
+    e_t, e_p = torch.empty_like(e_cond), torch.empty_like(e_cond)
+    o = list(old) + [None] * (3 - len(old))
+    L.check(lib.ealdm_plms_eps(_ptr(e_uncond), e_cond.data_ptr(), cfg_scale, _ptr(o[0]), _ptr(o[1]), _ptr(o[2]), mode,
+                               e_t.data_ptr(), e_p.data_ptr(), e_cond.numel(), _stream()))
+    return e_t, e_p
+
+
 def q_sample(x0, noise, t, sqrt_ac, sqrt_1mac):
     lib = L.load()
     assert x0.dtype == torch.float32 and x0.is_contiguous() and noise.is_contiguous()

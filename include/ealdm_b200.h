@@ -425,6 +425,17 @@ int ealdm_cfg_mse_bwd(const float* e_uncond, const float* e_cond, const float* t
                       ealdm_stream_t stream);
 
 /*
+ * PLMSSampler.p_sample_plms eps arithmetic (ldm/models/diffusion/plms.py:178-231), fp32, the reference's operation order:
+ * e_t = e_uncond + cfg_scale*(e_cond - e_uncond) (e_cond when e_uncond is NULL) -> e_t_out (the history entry);
+ * e_prime_out by `mode`: 0 = e_t, 1 = (e_t + old1)/2 (pseudo improved Euler, old1 = eps at the next timestep),
+ * 2 = (3 e_t - old1)/2, 3 = (23 e_t - 16 old1 + 5 old2)/12, 4 = (55 e_t - 59 old1 + 37 old2 - 9 old3)/24.
+ * The x_prev / pred_x0 update that follows is ealdm_ddim_step with e_cond = e_prime and sigma = 0.
+ */
+int ealdm_plms_eps(const float* e_uncond, const float* e_cond, float cfg_scale, const float* old1, const float* old2,
+                   const float* old3, int32_t mode, float* e_t_out, float* e_prime_out, int64_t numel,
+                   ealdm_stream_t stream);
+
+/*
  * One optimizer step over flat fp32 buffers of `numel` elements: AdamW exactly as torch.optim.AdamW (decoupled weight
  * decay, bias correction with the 1-based `step`; reference: configure_optimizers, ddpm.py:1409-1431), then the EMA
  * shadow update shadow -= (1 - ema_decay) * (shadow - param) (LitEma.forward, ldm/modules/ema.py:25-44; the caller

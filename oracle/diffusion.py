@@ -121,6 +121,51 @@ def ddim_sample(apply_model: Callable, alphas_cumprod_f32: torch.Tensor, S: int,
     return img, trace
 
 
+# ---- plms.py:120-236 -------------------------------------------------------------------------------------
+def plms_sample(apply_model: Callable, alphas_cumprod_f32: torch.Tensor, S: int, x_T: torch.Tensor, cond=None,
+                ugs: float = 1.0, uc=None):
+    """PLMSSampler.plms_sampling + p_sample_plms (eta = 0): pseudo improved Euler on the first step, then
+    Adams-Bashforth of order 2, 3, 4 on the eps history.  Returns (x_0, trace of per-step x_prev / pred_x0 / e_t)."""
+    sched = make_ddim_schedule(alphas_cumprod_f32, S, 0.0)
+    ts = np.flip(sched["ddim_timesteps"])
+    total = ts.shape[0]
+    b = x_T.shape[0]
+    img, old_eps, trace = x_T, [], []
+
+    def model_eps(x, t):
+        if uc is None or ugs == 1.0:
+            return apply_model(x, t, cond)
+        e_u, e_c = apply_model(torch.cat([x] * 2), torch.cat([t] * 2), torch.cat([uc, cond])).chunk(2)
+        return e_u + ugs * (e_c - e_u)
+
+    def x_prev_and_x0(x, e, index):
+        a_t, a_prev, sigma_t, s1 = ddim_step_scalars(sched, index)
+        pred_x0 = (x - s1 * e) / a_t.sqrt()
+        dir_xt = (1.0 - a_prev - sigma_t ** 2).sqrt() * e
+        return a_prev.sqrt() * pred_x0 + dir_xt, pred_x0
+
+    for i, step in enumerate(ts):
+        index = total - i - 1
+        t = torch.full((b,), int(step), dtype=torch.long)
+        t_next = torch.full((b,), int(ts[min(i + 1, total - 1)]), dtype=torch.long)
+        e_t = model_eps(img, t)
+        if len(old_eps) == 0:
+            x_prev, _ = x_prev_and_x0(img, e_t, index)
+            e_prime = (e_t + model_eps(x_prev, t_next)) / 2
+        elif len(old_eps) == 1:
+            e_prime = (3 * e_t - old_eps[-1]) / 2
+        elif len(old_eps) == 2:
+            e_prime = (23 * e_t - 16 * old_eps[-1] + 5 * old_eps[-2]) / 12
+        else:
+            e_prime = (55 * e_t - 59 * old_eps[-1] + 37 * old_eps[-2] - 9 * old_eps[-3]) / 24
+        img, pred_x0 = x_prev_and_x0(img, e_prime, index)
+        old_eps.append(e_t)
+        if len(old_eps) >= 4:
+            old_eps.pop(0)
+        trace.append({"t": int(step), "e_t": e_t, "x_prev": img, "pred_x0": pred_x0})
+    return img, trace
+
+
 # ---- ddpm.py:276-279, util.py:96-99 ---------------------------------------------------------------------
 def q_sample(buf: Dict[str, torch.Tensor], x0: torch.Tensor, t: torch.Tensor, noise: torch.Tensor) -> torch.Tensor:
     b = t.shape[0]

@@ -138,6 +138,19 @@ def test_ddim_trajectory_stdiff_cfg_eta1(sd_stdiff):
     assert rel_l2(x0, G["samples"]) < 5e-5
 
 
+def test_plms_trajectory_uncond(sd_uncond):
+    """PLMSSampler (plms.py): the oracle's restatement against the reference's own 10-step trajectory."""
+    G = gold("plms_traj.pt")["uncond_B2_S10"]
+    buf = OD.register_schedule(1000, CFG.DIFFUSION["linear_start"], CFG.DIFFUSION["linear_end"])
+    apply_model = lambda x, t, c: OU.unet_forward(sd_uncond, CFG.UNET_UNCOND, x, t)  # noqa: E731
+    with torch.no_grad():
+        x0, trace = OD.plms_sample(apply_model, buf["alphas_cumprod"], 10, G["x_T"])
+    for i, step in enumerate(trace):
+        assert rel_l2(step["x_prev"], G["x_prev"][i]) < 2e-5, i
+        assert rel_l2(step["pred_x0"], G["pred_x0"][i]) < 2e-5, i
+    assert rel_l2(x0, G["samples"]) < 2e-5
+
+
 def test_p_losses_and_q_sample(sd_stdiff):
     G = gold("p_losses.pt")
     buf = OD.register_schedule(1000, CFG.DIFFUSION["linear_start"], CFG.DIFFUSION["linear_end"])

@@ -140,3 +140,35 @@ def test_p_losses_vs_reference_golden(mode):
     tol = 2e-4 if mode == "fp32" else 2e-2
     assert abs(float(loss) - float(G["loss"])) <= tol * abs(float(G["loss"]))
     assert abs(float(d["val/loss_vlb"]) - float(G["loss_dict"]["val/loss_vlb"])) <= tol * abs(float(G["loss_dict"]["val/loss_vlb"]))
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("case", ["uncond_B2_S10", "stdiff_B2_S8_cfg2"])
+def test_plms_trajectory_vs_reference_golden(case, mode):
+    """PLMSSampler against the reference PLMSSampler's trajectory: pseudo improved Euler
+    first step (two UNet evaluations), then Adams-Bashforth orders 2-4 on the eps history."""
+    from ealdm_b200.plms import PLMSSampler
+    G = gold("plms_traj.pt")[case]
+    ld = make_ld("uncond" if case.startswith("uncond") else "stdiff")
+    ld.model.diffusion_model.set_compute_dtype(mode)
+    sampler = PLMSSampler(ld)
+    xs, ps = [], []
+    orig = sampler.p_sample_plms
+
+    def wrap(*a, **k):
+        out = orig(*a, **k)
+        xs.append(out[0]); ps.append(out[1])
+        return out
+
+    sampler.p_sample_plms = wrap
+    cuda = lambda t: None if t is None else t.cuda()  # noqa: E731
+    samples, inter = sampler.sample(S=G["S"], batch_size=2, shape=(4, 32, 32), conditioning=cuda(G["cond"]), eta=0.0,
+                                    x_T=G["x_T"].cuda(), verbose=False, unconditional_guidance_scale=G["ugs"],
+                                    unconditional_conditioning=cuda(G["uc"]))
+    errs = [rel_l2(xs[i], G["x_prev"][i]) for i in range(G["S"])]
+    print(f"plms {case} {mode}: x_prev rel_l2 per step = {['%.2e' % e for e in errs]}")
+    tol = TOL[mode] * (1 if mode == "fp32" else 2)
+    assert max(errs) < tol and rel_l2(samples, G["samples"]) < tol
+    assert max(rel_l2(ps[i], G["pred_x0"][i]) for i in range(G["S"])) < tol * 3
+    with pytest.raises(ValueError):
+        sampler.make_schedule(10, ddim_eta=0.5, verbose=False)
