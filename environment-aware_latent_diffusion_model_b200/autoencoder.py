@@ -250,6 +250,85 @@ class AutoencoderKL(nn.Module):
         return self.decode(z), posterior
 
 
+class VectorQuantizer(nn.Module):
+    """taming-transformers `VectorQuantizer2` as the reference instantiates it (autoencoder.py:39-41: beta 0.25,
+    remap None, sane_index_shape False, legacy True): owns `embedding.weight` [n_e, e_dim]; forward returns
+    (z_q, loss, (perplexity, min_encodings, min_encoding_indices)) with the nearest-code search in one kernel.
+    The commitment loss is a training quantity of the (frozen) first stage and is returned as None."""
+
+    def __init__(self, n_e, e_dim, beta=0.25, remap=None, unknown_index="random", sane_index_shape=False, legacy=True):
+        super().__init__()
+        if remap is not None:
+            raise NotImplementedError("VectorQuantizer remap")
+        self.n_e, self.e_dim, self.beta, self.legacy = n_e, e_dim, beta, legacy
+        self.sane_index_shape = sane_index_shape
+        self.embedding = nn.Embedding(n_e, e_dim)
+        self.embedding.weight.data.uniform_(-1.0 / n_e, 1.0 / n_e)
+
+    @torch.no_grad()
+    def forward(self, z, temp=None, rescale_logits=False, return_logits=False):
+        if not z.is_cuda:
+            raise RuntimeError("ealdm_b200.VectorQuantizer runs on CUDA (sm_100a) only; there is no CPU fallback")
+        zq, idx = ops.vq_nearest(z.float().contiguous(), self.embedding.weight.detach().float().contiguous())
+        if self.sane_index_shape:
+            idx = idx.reshape(z.shape[0], z.shape[2], z.shape[3])
+        return zq, None, (None, None, idx)
+
+    def get_codebook_entry(self, indices, shape):
+        z_q = self.embedding(indices)
+        if shape is not None:
+            z_q = z_q.view(shape).permute(0, 3, 1, 2).contiguous()
+        return z_q
+
+
+class VQModelInterface(AutoencoderKL):
+    """VQModelInterface / VQModel (autoencoder.py:14-110,263-282), the first stage of the shipped EALDM configs
+    (stdiff_cin-ldm-vq-f8.yaml:37-60): `encode` returns the pre-quantisation latent, `decode` quantises (unless
+    force_not_quantize), applies post_quant_conv and the decoder.  State-dict names are the reference's
+    (`encoder.*`, `decoder.*`, `quantize.embedding.weight`, `quant_conv.*`, `post_quant_conv.*`)."""
+
+    def __init__(self, embed_dim, ddconfig=None, lossconfig=None, n_embed=None, ckpt_path=None, ignore_keys=(),
+                 image_key="image", colorize_nlabels=None, monitor=None, batch_resize_range=None,
+                 scheduler_config=None, lr_g_factor=1.0, remap=None, sane_index_shape=False, use_ema=False,
+                 compute_dtype="bf16"):
+        nn.Module.__init__(self)
+        if use_ema:
+            raise NotImplementedError("EMA of the first stage (training of the autoencoder is out of scope)")
+        self.embed_dim, self.n_embed, self.image_key = embed_dim, n_embed, image_key
+        self.encoder = Encoder(**ddconfig)
+        self.decoder = Decoder(**ddconfig)
+        self.loss = instantiate_from_config(lossconfig) if lossconfig else nn.Identity()
+        self.quantize = VectorQuantizer(n_embed, embed_dim, beta=0.25, remap=remap, sane_index_shape=sane_index_shape)
+        self.quant_conv = nn.Conv2d(ddconfig["z_channels"], embed_dim, 1)
+        self.post_quant_conv = nn.Conv2d(embed_dim, ddconfig["z_channels"], 1)
+        if monitor is not None:
+            self.monitor = monitor
+        self._compute_dtype = {"bf16": torch.bfloat16, "fp32": torch.float32}[compute_dtype]
+        self._engine = None
+        self.register_load_state_dict_post_hook(lambda m, keys: m.invalidate_packed())
+        if ckpt_path is not None:
+            sd = torch.load(ckpt_path, map_location="cpu")["state_dict"]
+            for k in list(sd.keys()):
+                if any(k.startswith(ik) for ik in ignore_keys):
+                    del sd[k]
+            self.load_state_dict(sd, strict=False)
+
+    @torch.no_grad()
+    def encode(self, x):
+        return self._eng(x).encode_moments(x)       # encoder + quant_conv: the continuous latent h
+
+    @torch.no_grad()
+    def decode(self, h, force_not_quantize=False):
+        quant = h if force_not_quantize else self.quantize(h)[0]
+        return self._eng(h).decode(quant)
+
+    def forward(self, input, return_pred_indices=False):
+        h = self.encode(input)
+        quant, _, (_, _, ind) = self.quantize(h)
+        dec = self._eng(h).decode(quant)
+        return (dec, None, ind) if return_pred_indices else (dec, None)
+
+
 # ---- execution engine ------------------------------------------------------------------------------------
 class AutoencoderEngine:
     def __init__(self, m: AutoencoderKL, dtype: torch.dtype):

@@ -18,6 +18,11 @@ AE_KL_F8_DDCONFIG = dict(
     double_z=True, z_channels=4, resolution=256, in_channels=3, out_ch=3, ch=128, ch_mult=[1, 2, 4, 4],
     num_res_blocks=2, attn_resolutions=[], dropout=0.0)
 AE_KL_F8_EMBED_DIM = 4
+# first stage of the shipped EALDM configs (configs/latent-diffusion/stdiff_cin-ldm-vq-f8.yaml:37-60)
+VQ_F8_DDCONFIG = dict(
+    double_z=False, z_channels=4, resolution=256, in_channels=3, out_ch=3, ch=128, ch_mult=[1, 2, 2, 4],
+    num_res_blocks=2, attn_resolutions=[32], dropout=0.0)
+VQ_F8_N_EMBED, VQ_F8_EMBED_DIM = 16384, 4
 
 DIFFUSION = dict(linear_start=0.0015, linear_end=0.0195, timesteps=1000, image_size=32, channels=4)
 

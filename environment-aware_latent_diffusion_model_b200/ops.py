@@ -567,5 +567,18 @@ def cfg_mse_bwd(e_cond, target, w, *, e_uncond=None, cfg_scale=1.0):
     return de_u, de_c
 
 
+def vq_nearest(z: torch.Tensor, codebook: torch.Tensor):
+    """ealdm_vq_nearest on an NCHW fp32 latent; returns (z_q NCHW fp32, indices int64 [n*h*w])."""
+    lib = L.load()
+    assert z.dtype == torch.float32 and z.is_contiguous() and z.dim() == 4
+    assert codebook.dtype == torch.float32 and codebook.is_contiguous() and codebook.shape[1] == z.shape[1]
+    n, e, h, w = z.shape
+    zq = torch.empty_like(z)
+    idx = torch.empty((n * h * w,), dtype=torch.int64, device=z.device)
+    L.check(lib.ealdm_vq_nearest(z.data_ptr(), n, e, h * w, codebook.data_ptr(), codebook.shape[0], zq.data_ptr(),
+                                 idx.data_ptr(), _stream()))
+    return zq, idx
+
+
 def launch_count() -> int:
     return int(L.load().ealdm_launch_count())

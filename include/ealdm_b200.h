@@ -425,6 +425,16 @@ int ealdm_cfg_mse_bwd(const float* e_uncond, const float* e_cond, const float* t
                       ealdm_stream_t stream);
 
 /*
+ * Nearest-codebook quantisation of an NCHW fp32 latent z [n, e_dim, hw] against codebook [n_e, e_dim]:
+ * indices[(n, p)] = argmin_j (|z|^2 + |e_j|^2 - 2 z.e_j) (first minimum), zq = codebook[indices] (NCHW).
+ * Replaces VQModelInterface.decode's `self.quantize(h)` (ldm/models/autoencoder.py:274-279), i.e. taming-transformers
+ * VectorQuantizer2.forward (un-vendored dependency, environment.yaml:25; its inference arithmetic is restated in
+ * oracle/vq.py).
+ */
+int ealdm_vq_nearest(const float* z, int64_t n, int64_t e_dim, int64_t hw, const float* codebook, int64_t n_e,
+                     float* zq, int64_t* indices, ealdm_stream_t stream);
+
+/*
  * PLMSSampler.p_sample_plms eps arithmetic (ldm/models/diffusion/plms.py:178-231), fp32, the reference's operation order:
  * e_t = e_uncond + cfg_scale*(e_cond - e_uncond) (e_cond when e_uncond is NULL) -> e_t_out (the history entry);
  * e_prime_out by `mode`: 0 = e_t, 1 = (e_t + old1)/2 (pseudo improved Euler, old1 = eps at the next timestep),

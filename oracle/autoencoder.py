@@ -104,6 +104,28 @@ def decode_first_stage(sd: SD, dd: dict, z: torch.Tensor, scale_factor: float = 
     return kl_decode(sd, dd, 1.0 / scale_factor * z)
 
 
+def vq_decode(sd: SD, dd: dict, h: torch.Tensor, force_not_quantize: bool = False) -> torch.Tensor:
+    """VQModelInterface.decode, autoencoder.py:274-282: quantize (oracle/vq.py) -> post_quant_conv -> Decoder."""
+    from .vq import vq_nearest
+    quant = h if force_not_quantize else vq_nearest(h, sd["quantize.embedding.weight"])[0]
+    return decoder_forward(sd, dd, F.conv2d(quant, sd["post_quant_conv.weight"], sd["post_quant_conv.bias"]))
+
+
+def vq_encode(sd: SD, dd: dict, x: torch.Tensor) -> torch.Tensor:
+    """VQModelInterface.encode, autoencoder.py:268-271: encoder -> quant_conv (no quantisation)."""
+    return F.conv2d(encoder_forward(sd, dd, x), sd["quant_conv.weight"], sd["quant_conv.bias"])
+
+
+def vq_param_shapes(dd: dict, embed_dim: int, n_embed: int) -> List[Tuple[str, Tuple[int, ...]]]:
+    """VQModel registration order (autoencoder.py:35-43): encoder, decoder, quantize, quant_conv, post_quant_conv."""
+    kl = autoencoder_kl_param_shapes(dict(dd, double_z=False), embed_dim)
+    body = [e for e in kl if not e[0].startswith(("quant_conv", "post_quant_conv"))]
+    zc = dd["z_channels"]
+    return body + [("quantize.embedding.weight", (n_embed, embed_dim)),
+                   ("quant_conv.weight", (embed_dim, zc, 1, 1)), ("quant_conv.bias", (embed_dim,)),
+                   ("post_quant_conv.weight", (zc, embed_dim, 1, 1)), ("post_quant_conv.bias", (zc,))]
+
+
 # ---- parameter inventory (registration order of the reference constructors) ---------------------------
 def _res_shapes(p, cin, cout):
     s = [(p + "norm1.weight", (cin,)), (p + "norm1.bias", (cin,)),

@@ -76,3 +76,47 @@ def test_decode_batch_of_three_matches_single():
     d3 = ae.decode(z3)
     d1 = ae.decode(z)
     assert rel_l2(d3[:1], d1) < 2e-3 and rel_l2(d3[2:], d1) < 2e-3
+
+
+# ---- VQ first stage ---------------------------------------------------------------
+def make_vq():
+    if "vq" not in _ae:
+        from ealdm_b200.autoencoder import VQModelInterface
+        m = VQModelInterface(embed_dim=CFG.VQ_F8_EMBED_DIM, n_embed=CFG.VQ_F8_N_EMBED, ddconfig=dict(CFG.VQ_F8_DDCONFIG))
+        sd = OU.synthetic_state_dict(OA.vq_param_shapes(CFG.VQ_F8_DDCONFIG, CFG.VQ_F8_EMBED_DIM, CFG.VQ_F8_N_EMBED), seed=4)
+        sd["quantize.embedding.weight"] = torch.randn(CFG.VQ_F8_N_EMBED, CFG.VQ_F8_EMBED_DIM,
+                                                      generator=torch.Generator().manual_seed(81)) * 1.2
+        m.load_state_dict(sd, strict=True)
+        _ae["vq"] = m.cuda().eval()
+    return _ae["vq"]
+
+
+def test_vq_nearest_indices_exact_vs_reference_golden():
+    G = torch.load(os.path.join(GOLD, "vq_f8.pt"), weights_only=False)
+    m = make_vq()
+    zq, _, (_, _, idx) = m.quantize(G["h"].cuda())
+    assert torch.equal(idx.cpu(), G["indices"])                                  # integer work: exact
+    assert torch.equal(zq.cpu(), m.quantize.embedding.weight.detach().cpu()[G["indices"]].reshape(1, 32, 32, 4).permute(0, 3, 1, 2))
+    # a batch: every pixel independent
+    z = torch.randn(3, 4, 16, 16, generator=torch.Generator().manual_seed(5)).cuda()
+    cb = m.quantize.embedding.weight.detach()
+    d = ((z.permute(0, 2, 3, 1).reshape(-1, 1, 4).double() - cb.double()[None]) ** 2).sum(-1)
+    _, _, (_, _, idx3) = m.quantize(z)
+    assert float((d.argmin(1) == idx3).float().mean()) > 0.999
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_vq_decode_encode_vs_reference_golden(mode):
+    G = torch.load(os.path.join(GOLD, "vq_f8.pt"), weights_only=False)
+    m = make_vq().set_compute_dtype(mode)
+    for key, kw in (("dec", {}), ("dec_noquant", {"force_not_quantize": True})):
+        dec = m.decode(G["h"].cuda(), **kw)
+        err = rel_l2(dec, G[key])
+        a = ((dec.cpu().clamp(-1, 1) + 1) / 2).double()
+        b = ((G[key].clamp(-1, 1) + 1) / 2).double()
+        mse = float(((a - b) ** 2).mean())
+        psnr = 99.0 if mse == 0 else 10 * math.log10(1.0 / mse)
+        print(f"vq decode[{key}] {mode}: rel_l2 = {err:.3e}, PSNR = {psnr:.1f} dB")
+        assert err < (TOL[mode] if mode == "fp32" else 2e-2) and psnr >= 40.0
+    enc = m.encode(G["img"].cuda())
+    assert rel_l2(enc, G["enc"]) < TOL[mode] * (1 if mode == "fp32" else 1.5)

@@ -107,6 +107,15 @@ def test_autoencoder_state_dict_matches_reference_inventory():
     assert mine == OA.autoencoder_kl_param_shapes(CFG.AE_KL_F8_DDCONFIG, 4)
 
 
+def test_vq_first_stage_state_dict_matches_reference_inventory():
+    from ealdm_b200.autoencoder import VQModelInterface
+    m = VQModelInterface(embed_dim=CFG.VQ_F8_EMBED_DIM, n_embed=CFG.VQ_F8_N_EMBED, ddconfig=dict(CFG.VQ_F8_DDCONFIG))
+    mine = [(k, tuple(v.shape)) for k, v in m.state_dict().items()]
+    assert mine == OA.vq_param_shapes(CFG.VQ_F8_DDCONFIG, CFG.VQ_F8_EMBED_DIM, CFG.VQ_F8_N_EMBED)
+    with pytest.raises(RuntimeError):
+        m.decode(torch.zeros(1, 4, 8, 8))        # CPU tensor: no fallback
+
+
 def test_schedules_bit_exact_vs_reference_golden():
     G = gold("schedule.pt")
     ld = LatentDiffusion(unet_config={"target": "ealdm_b200.unet.UNetModel", "params": dict(CFG.UNET_UNCOND)},

@@ -173,3 +173,25 @@ def test_autoencoder_kl():
     mean, logvar, std = OA.gaussian_from_moments(mom)
     assert rel_l2(mean, G["mean"]) < 1e-5 and rel_l2(std, G["std"]) < 1e-5
     assert rel_l2(dec, G["dec"]) < 1e-5
+
+
+def test_vq_first_stage_decode_and_quantizer():
+    """VQ first stage (vq-f8: attention at 32x32, 16384 x 4 codebook): the oracle's Decoder / quantiser restatement
+    against the reference VQModelInterface run with the restated taming quantiser (parity unpinned for the quantiser
+    itself, see oracle/vq.py)."""
+    from oracle import vq as OV
+    G = gold("vq_f8.pt")
+    shapes = OA.vq_param_shapes(CFG.VQ_F8_DDCONFIG, CFG.VQ_F8_EMBED_DIM, CFG.VQ_F8_N_EMBED)
+    sd = OU.synthetic_state_dict(shapes, seed=4)
+    sd["quantize.embedding.weight"] = torch.randn(CFG.VQ_F8_N_EMBED, CFG.VQ_F8_EMBED_DIM,
+                                                  generator=torch.Generator().manual_seed(81)) * 1.2
+    zq, idx = OV.vq_nearest(G["h"], sd["quantize.embedding.weight"])
+    assert torch.equal(idx, G["indices"])
+    # brute-force definition of the nearest code (float64)
+    d = ((G["h"].permute(0, 2, 3, 1).reshape(-1, 1, 4).double() - sd["quantize.embedding.weight"].double()[None]) ** 2).sum(-1)
+    assert float((d.argmin(1) == idx).float().mean()) > 0.999
+    with torch.no_grad():
+        dec = OA.vq_decode(sd, CFG.VQ_F8_DDCONFIG, G["h"])
+        enc = OA.vq_encode(sd, CFG.VQ_F8_DDCONFIG, G["img"])
+    assert rel_l2(dec, G["dec"]) < 2e-5
+    assert rel_l2(enc, G["enc"]) < 2e-5
