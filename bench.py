@@ -325,6 +325,7 @@ def run_autoencoder(args):
             rec = ae.decode(z)
         if host:
             out_h.copy_(rec, non_blocking=True)
+            torch.cuda.current_stream().synchronize()    # the caller consumes the host images of every step
         return rec
 
     res = {}
@@ -479,6 +480,7 @@ def main():
         out_h.copy_(z, non_blocking=True)
         if world > 1:
             gather_batch(z, Bg)
+        torch.cuda.current_stream().synchronize()        # the caller consumes the host latents of every step
         return z
 
     for _ in range(2):

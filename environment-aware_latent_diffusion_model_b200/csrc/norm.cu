@@ -319,7 +319,17 @@ static int group_norm_t(const ealdm_group_norm_args* a, cudaStream_t st) {
   if (a->partial != nullptr) {
     int ppc;
     long long chunks;
-    gn_chunking(a->n, a->hw, &ppc, &chunks);
+    {
+      // fewer, fatter CTAs than the two-pass kernels: every CTA first folds the partial statistics of its image
+      // (measured at batch 128: 296 CTAs 45 us, 1184 CTAs 49 us, 2368 CTAs 53 us, 4736 CTAs 63 us at level 0)
+      const long long target = 296;
+      long long ch = ceil_div(target, a->n);
+      const long long max_chunks = ceil_div(a->hw, 16);
+      if (ch > max_chunks) ch = max_chunks;
+      if (ch < 1) ch = 1;
+      ppc = static_cast<int>(ceil_div(a->hw, ch));
+      chunks = ceil_div(a->hw, ppc);
+    }
     dim3 grid(static_cast<unsigned>(chunks), static_cast<unsigned>(a->n));
     gn_apply_partial_kernel<TX, T><<<grid, NT, 0, st>>>(
         reinterpret_cast<const TX*>(a->x), a->ld_x, reinterpret_cast<T*>(a->y), a->ld_y, static_cast<int>(a->hw),
