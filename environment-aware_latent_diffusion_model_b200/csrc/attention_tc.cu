@@ -47,7 +47,7 @@ struct Cfg {
   static constexpr int Q_OFF = 0;
   static constexpr int KV_OFF = Q_OFF + Q_BYTES;
   static constexpr int P_OFF = KV_OFF + 2 * STAGE_BYTES;
-  static constexpr int BAR_OFF = P_OFF + P_BYTES;
+  static constexpr int BAR_OFF = P_OFF + 2 * P_BYTES;   // P is double buffered
   static constexpr int SMEM_BYTES = BAR_OFF + 128;
   static_assert(KV_OFF % 1024 == 0 && P_OFF % 1024 == 0, "alignment");
 };
@@ -188,7 +188,7 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
         for (int k = 0; k < BN / 16; ++k) {
           // A: P sub-tile (k >> 2) of [128 x 64] bf16 (16 KB), 32 B per k-step inside the swizzle row
-          const uint64_t adesc = make_desc(p_addr + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024, 2);
+          const uint64_t adesc = make_desc(p_addr + (t & 1) * C::P_BYTES + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024, 2);
           // B: V rows 16k .. 16k+15 (MN-major: 16 rows of ROW_BYTES)
           const uint64_t bdesc = make_desc(v_addr + k * 16 * C::ROW_BYTES, 16, SBO, LT);
           ptx::umma_bf16(d_tmem, adesc, bdesc, idesc_o, (t | k) != 0 ? 1u : 0u);
@@ -203,60 +203,77 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
-    uint8_t* pbuf = smem + C::P_OFF;
     const float c = p.scale_log2;
     float m_ref = -INFINITY;   // reference maximum (raw score units) the probabilities of this row are relative to
     float l = 0.f;
 
     for (int t = 0; t < ntiles; ++t) {
+      // P is double buffered: buffer t&1 was last read by the P V product of tile t-2, which precedes S_t in the
+      // tensor pipe, so it is free as soon as S_t is
+      uint8_t* pbuf = smem + C::P_OFF + (t & 1) * C::P_BYTES;
       ptx::mbar_wait(s_full, t & 1);
       ptx::tc_fence_after();
-      // the whole row of scores, read from TMEM exactly once
-      uint32_t sv[4][32];
-#pragma unroll
-      for (int ch = 0; ch < 4; ++ch) ptx::tmem_ld_32x32(t_lane + ch * 32, sv[ch]);
-      ptx::tmem_ld_wait();
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(s_free);   // S is free: the next Q K^T overlaps the exponentials below
-      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-      for (int ch = 0; ch < 4; ++ch)
-#pragma unroll
-        for (int j = 0; j < 32; ++j) mx4[j & 3] = fmaxf(mx4[j & 3], __uint_as_float(sv[ch][j]));
-      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
-      // lazy rescaling: move the reference only when the row maximum outgrew it by more than the threshold
-      const bool grow = (mx - m_ref) * c > RESCALE_THRESHOLD;   // always true on the first tile (m_ref = -inf)
-      const float m_new = grow ? mx : m_ref;
-      // the previous P V product has finished: P buffer free, O consistent
-      if (t > 0) {
-        ptx::mbar_wait(&pv_done[(t - 1) & 1], ((t - 1) >> 1) & 1);
-        ptx::tc_fence_after();
-        if (__any_sync(0xffffffffu, grow)) {
-          const float corr = ex2f((m_ref - m_new) * c);   // 1 for the rows that keep their reference
-          uint32_t vo[32];
-          ptx::tmem_ld_32x32(t_lane + O_COL, vo);
-          ptx::tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) vo[j] = __float_as_uint(__uint_as_float(vo[j]) * corr);
-          ptx::tmem_st_32x32(t_lane + O_COL, vo);
-          ptx::tmem_st_wait();
-          l *= corr;
-        }
-      }
-      m_ref = m_new;
-      const float ms = -m_new * c;
-      // probabilities -> bf16 -> shared memory (K-major SWIZZLE_128B, 64 keys per sub-tile)
-      float s4[4] = {0.f, 0.f, 0.f, 0.f};
+      uint32_t sv[2][32];
+      ptx::tmem_ld_32x32(t_lane, sv[0]);
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch) {
+        // the TMEM load of chunk ch+1 flies under the exponentials of chunk ch (S is read exactly once)
+        ptx::tmem_ld_wait();
+        if (ch + 1 < 4) {
+          ptx::tmem_ld_32x32(t_lane + (ch + 1) * 32, sv[(ch + 1) & 1]);
+        } else {
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(s_free);   // S is consumed: the next Q K^T overlaps the rest of this tile
+        }
+        const uint32_t(&v)[32] = sv[ch & 1];
+        float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int j = 0; j < 32; ++j) mx4[j & 3] = fmaxf(mx4[j & 3], __uint_as_float(v[j]));
+        const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+        // lazy rescaling at chunk granularity: the reference only moves when a score outgrows it by more than 2^8
+        const bool grow = (mx - m_ref) * c > RESCALE_THRESHOLD;   // always true for the first chunk (m_ref = -inf)
+        if (__any_sync(0xffffffffu, grow)) {
+          const float m_new = grow ? mx : m_ref;
+          const float corr = ex2f((m_ref - m_new) * c);           // 1 for the rows that keep their reference
+          m_ref = m_new;
+          l *= corr;
+          if (t > 0) {                                            // O (all previous tiles) lives in TMEM
+            ptx::mbar_wait(&pv_done[(t - 1) & 1], ((t - 1) >> 1) & 1);
+            ptx::tc_fence_after();
+            uint32_t vo[32];
+            ptx::tmem_ld_32x32(t_lane + O_COL, vo);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) vo[j] = __float_as_uint(__uint_as_float(vo[j]) * corr);
+            ptx::tmem_st_32x32(t_lane + O_COL, vo);
+            ptx::tmem_st_wait();
+            if (ch + 1 < 4) {   // the wait above also retired the prefetch of the next chunk: nothing to redo
+            }
+          }
+          for (int pc = 0; pc < ch; ++pc) {                       // probabilities of this tile already written
+            uint8_t* prow = pbuf + (pc >> 1) * 16384 + row * 128;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4* q = reinterpret_cast<uint4*>(prow + ((((pc & 1) * 4 + j) ^ (row & 7)) << 4));
+              uint4 u = *q;
+              uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                w[i] = pack2(__uint_as_float(w[i] << 16) * corr, __uint_as_float(w[i] & 0xffff0000u) * corr);
+              *q = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+          }
+        }
+        const float ms = -m_ref * c;
+        float s4[4] = {0.f, 0.f, 0.f, 0.f};
         uint8_t* prow = pbuf + (ch >> 1) * 16384 + row * 128;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           float e[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            e[i] = ex2f(fmaf(__uint_as_float(sv[ch][8 * j + i]), c, ms));
+            e[i] = ex2f(fmaf(__uint_as_float(v[8 * j + i]), c, ms));
             s4[i & 3] += e[i];
           }
           uint4 u;
@@ -267,9 +284,8 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           const int chunk = (ch & 1) * 4 + j;
           *reinterpret_cast<uint4*>(prow + ((chunk ^ (row & 7)) << 4)) = u;
         }
+        l += (s4[0] + s4[1]) + (s4[2] + s4[3]);
       }
-      l += (s4[0] + s4[1]) + (s4[2] + s4[3]);
-      ptx::tc_fence_before();
       ptx::fence_proxy_async();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(p_ready);
