@@ -46,7 +46,8 @@ class ConvArgs(C.Structure):
                 ("bias", C.c_void_p), ("rowvec", C.c_void_p), ("ld_rowvec", C.c_int64),
                 ("residual", C.c_void_p), ("ld_res", C.c_int64), ("out", C.c_void_p),
                 ("ld_out", C.c_int64), ("out_f32", C.c_int32), ("res_f32", C.c_int32),
-                ("out2", C.c_void_p), ("ld_out2", C.c_int64), ("gn_partial", C.c_void_p), ("gn_ld", C.c_int64)]
+                ("out2", C.c_void_p), ("ld_out2", C.c_int64), ("gn_partial", C.c_void_p), ("gn_ld", C.c_int64),
+                ("weight_adjoint", C.c_int32), ("reserved2", C.c_int32), ("ld_weight", C.c_int64)]
 
 
 class GroupNormArgs(C.Structure):

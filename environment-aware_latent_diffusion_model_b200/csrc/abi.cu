@@ -70,6 +70,11 @@ extern "C" int ealdm_conv(const ealdm_conv_args* a, ealdm_stream_t stream) {
                   (long long)a->w_out);
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (a->weight_adjoint) {
+    EALDM_REQUIRE(a->impl != EALDM_IMPL_SIMT && a->dtype == EALDM_BF16 && tc::supported(a),
+                  "conv: weight_adjoint needs the tcgen05 path (bf16, one source, c %% 64 == 0, n_out %% 64 == 0)");
+    return tc::launch(a, st);
+  }
   if (a->impl == EALDM_IMPL_SIMT) return simt::launch(a, st);
   if (a->impl == EALDM_IMPL_TCGEN05) return tc::launch(a, st);
   if (a->dtype == EALDM_BF16 && tc::supported(a)) return tc::launch(a, st);

@@ -69,6 +69,8 @@ struct Params {
   float2* gn_partial;
   int gn_ld;       // octets per (image, chunk) row
   int gn_chunks;   // 32-pixel chunks per image
+  // adjoint mode: B is read MN-major from the forward-packed matrix [K rows = src channels, taps * N columns]
+  int b_mn;
 };
 
 template <int BN>
@@ -236,7 +238,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             uint8_t* sa = smem + stage * C::STAGE_BYTES;
             ptx::tma_load_4d(sa, tmA, &full_bar[stage], cb * BK, w0 * sg.stride + kw - sg.pad,
                              h0 * sg.stride + kh - sg.pad, n0);
-            ptx::tma_load_2d(sa + C::A_BYTES, &tmB, &full_bar[stage], sg.bkoff + kb * BK, nt * BN);
+            if (p.b_mn) {
+              // adjoint: rows = 64 source channels (K), columns = N of the flipped tap, 64 at a time (one SW128 atom)
+              const int tcol = (sg.ksize * sg.ksize - 1 - tap) * p.N + nt * BN;
+#pragma unroll
+              for (int g = 0; g < BN / 64; ++g)
+                ptx::tma_load_2d(sa + C::A_BYTES + g * 8192, &tmB, &full_bar[stage], tcol + g * 64, cb * BK);
+            } else {
+              ptx::tma_load_2d(sa + C::A_BYTES, &tmB, &full_bar[stage], sg.bkoff + kb * BK, nt * BN);
+            }
             if (++cb == sg.cblk) { cb = 0; ++tap; }
             if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
           }
@@ -245,7 +255,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = ptx::make_idesc_bf16(BM, BN);
+    const uint32_t idesc = ptx::make_idesc_bf16(BM, BN) | (p.b_mn ? (1u << 16) : 0u);   // bit 16: B is MN-major
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
@@ -260,11 +270,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         if (lane == 0) {
           const uint32_t sa = ptx::smem_u32(smem + stage * C::STAGE_BYTES);
           const uint64_t adesc = ptx::make_sw128_kmajor_desc(sa);
-          const uint64_t bdesc = ptx::make_sw128_kmajor_desc(sa + C::A_BYTES);
+          if (p.b_mn) {
+            // MN-major B: 64-column groups 8192 B apart (LBO), 8-row K groups 1024 B apart; 16 K rows = 2048 B
+            const uint64_t bdesc = ptx::make_sw128_mnmajor_desc(sa + C::A_BYTES, 8192);
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            // advancing K by 16 bf16 = 32 B inside the swizzle row = +2 in 16-byte units
-            ptx::umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BK / UMMA_K; ++k)
+              ptx::umma_bf16(d_tmem, adesc + 2 * k, bdesc + 128 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          } else {
+            const uint64_t bdesc = ptx::make_sw128_kmajor_desc(sa + C::A_BYTES);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              // advancing K by 16 bf16 = 32 B inside the swizzle row = +2 in 16-byte units
+              ptx::umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
           }
           ptx::umma_commit(&empty_bar[stage]);
           if (kb == kblocks_total - 1) ptx::umma_commit(&tmem_full[acc]);
@@ -546,7 +564,13 @@ bool supported(const ealdm_conv_args* a) {
     if (x.stride != 1 && x.stride != 2) return false;
     if (x.n != a->src[0].n) return false;
   }
-  if (!aligned_2d(a->weight, a->k_total, 2)) return false;
+  if (a->weight_adjoint) {
+    if (a->n_src != 1 || a->act == EALDM_ACT_GEGLU || a->n_out % 64 != 0) return false;
+    const long long ldw = a->ld_weight ? a->ld_weight : a->n_out * a->src[0].ksize * a->src[0].ksize;
+    if (!aligned_2d(a->weight, ldw, 2)) return false;
+  } else if (!aligned_2d(a->weight, a->k_total, 2)) {
+    return false;
+  }
   if (!aligned_2d(a->out, a->ld_out, a->out_f32 ? 4 : 2)) return false;
   if (a->residual && !aligned_2d(a->residual, a->ld_res, a->res_f32 ? 4 : 2)) return false;
   if (a->out2 && !aligned_2d(a->out2, a->ld_out2, 2)) return false;
@@ -610,7 +634,7 @@ int launch(const ealdm_conv_args* a, cudaStream_t st) {
   // choose the N tile: fewest (waves x tile cost)
   const bool geglu = a->act == EALDM_ACT_GEGLU;
   int BN;
-  if (a->n_out <= 32 && !geglu) {
+  if (a->n_out <= 32 && !geglu && !a->weight_adjoint) {
     BN = 32;
   } else if (a->n_out <= 128) {
     BN = 128;
@@ -655,7 +679,19 @@ int launch(const ealdm_conv_args* a, cudaStream_t st) {
   EALDM_REQUIRE(koff == a->k_total, "k_total %lld does not match the sources (%d)",
                 (long long)a->k_total, koff);
   if (a->n_src == 1) tm[1] = tm[0];
-  {
+  if (a->weight_adjoint) {
+    const ealdm_conv_src& x = a->src[0];
+    const long long wcols = a->n_out * x.ksize * x.ksize;
+    const long long ldw = a->ld_weight ? a->ld_weight : wcols;
+    cuuint64_t gdim[2] = {static_cast<cuuint64_t>(wcols), static_cast<cuuint64_t>(x.c)};
+    cuuint64_t gstr[1] = {static_cast<cuuint64_t>(ldw) * 2};
+    cuuint32_t box[2] = {64, BK};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(&tm[2], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(a->weight), gdim, gstr, box,
+                        estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(EALDM_ECUDA, "cuTensorMapEncodeTiled(W adjoint) failed: %d", (int)r);
+  } else {
     cuuint64_t gdim[2] = {static_cast<cuuint64_t>(a->k_total), static_cast<cuuint64_t>(a->n_out)};
     cuuint64_t gstr[1] = {static_cast<cuuint64_t>(a->k_total) * 2};
     cuuint32_t box[2] = {BK, static_cast<cuuint32_t>(BN)};
@@ -687,6 +723,7 @@ int launch(const ealdm_conv_args* a, cudaStream_t st) {
   p.gn_partial = reinterpret_cast<float2*>(a->gn_partial);
   p.gn_ld = static_cast<int>(a->gn_ld);
   p.gn_chunks = static_cast<int>(a->h_out * a->w_out / 32);
+  p.b_mn = a->weight_adjoint ? 1 : 0;
 
   switch (BN) {
     case 32: return launch_bn<32, false>(tm, p, st);

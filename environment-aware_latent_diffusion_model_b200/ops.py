@@ -105,8 +105,10 @@ class ConvIn:
 
 def conv(srcs: Sequence[ConvIn], weight: torch.Tensor, out: Act, *, bias: Optional[torch.Tensor] = None,
          rowvec: Optional[torch.Tensor] = None, rowvec_col0: int = 0, residual: Optional[Act] = None,
-         act: int = L.ACT_NONE, impl: int = L.IMPL_AUTO, out2: Optional[Act] = None) -> Act:
-    """ealdm_conv: out = epilogue(sum_s im2col(src_s) @ weight[:, seg_s]^T). `weight` is [n_out, k_total]."""
+         act: int = L.ACT_NONE, impl: int = L.IMPL_AUTO, out2: Optional[Act] = None, adjoint: bool = False) -> Act:
+    """ealdm_conv: out = epilogue(sum_s im2col(src_s) @ weight[:, seg_s]^T). `weight` is [n_out, k_total].
+    adjoint=True: data gradient of a forward layer -- `weight` is that layer's own packed matrix
+    [src channels, ksize^2 * out.c] (may be a column window of a wider matrix); nothing is transposed or flipped."""
     lib = L.load()
     a = L.ConvArgs()
     x0 = srcs[0].x
@@ -119,15 +121,23 @@ def conv(srcs: Sequence[ConvIn], weight: torch.Tensor, out: Act, *, bias: Option
         d.x, d.n, d.h, d.w, d.c, d.ld = s.x.ptr, s.x.n, s.x.h, s.x.w, s.x.c, s.x.ld
         d.ksize, d.stride, d.pad, d.upsample = s.ksize, s.stride, s.pad, s.upsample
         assert s.x.dtype == x0.dtype
-    assert weight.dim() == 2 and weight.is_contiguous() and weight.dtype == x0.dtype
+    assert weight.dim() == 2 and weight.dtype == x0.dtype
     a.weight = weight.data_ptr()
-    a.n_out, a.k_total = weight.shape
     a.h_out, a.w_out = out.h, out.w
     assert out.n == x0.n
-    n_cols = weight.shape[0] // 2 if act == L.ACT_GEGLU else weight.shape[0]
+    if adjoint:
+        taps = srcs[0].ksize ** 2
+        assert len(srcs) == 1 and weight.stride(1) == 1 and weight.shape == (x0.c, taps * out.c), \
+            (tuple(weight.shape), x0.c, taps, out.c)
+        a.n_out, a.k_total = out.c, taps * x0.c
+        a.weight_adjoint, a.ld_weight = 1, weight.stride(0)
+    else:
+        assert weight.is_contiguous()
+        a.n_out, a.k_total = weight.shape
+    n_cols = a.n_out // 2 if act == L.ACT_GEGLU else a.n_out
     assert out.c == n_cols, (out.c, n_cols)
     if bias is not None:
-        assert bias.dtype == torch.float32 and bias.numel() == weight.shape[0]
+        assert bias.dtype == torch.float32 and bias.numel() == a.n_out
         a.bias = bias.data_ptr()
     if rowvec is not None:
         assert rowvec.dtype == torch.float32 and rowvec.dim() == 2 and rowvec.shape[0] == x0.n

@@ -59,6 +59,8 @@ class UNetTrainEngine(UNetEngine):
     """Forward + backward on the C ABI.  The packed weights are derived from the parameters at construction:
     build a new engine (UNetModel does so automatically) after every optimizer step."""
 
+    _fused_geglu = False
+
     def __init__(self, m: UNetModel, dtype: torch.dtype):
         super().__init__(m, dtype)
         self.ws = ops.Workspace(self.dev)
@@ -75,31 +77,40 @@ class UNetTrainEngine(UNetEngine):
                 return _pack_dgrad(self._c(base)[:, :, 0, 0], dt)
             return _pack_dgrad(self._c(p), dt)
 
+        # Data-gradient weights.  bf16 (tcgen05): the forward-packed matrix itself, read MN-major by the adjoint
+        # mode of ealdm_conv -- nothing is transposed, flipped or copied.  fp32 (SIMT parity mode): the transposed,
+        # tap-flipped copy.  `adj` records (tensor, is_adjoint).
+        tc = dt == torch.bfloat16
+
+        def adj(fwd, param):
+            return (fwd, True) if tc else (pd(param), False)
+
         def walk(seq, packed):
             for layer, d in zip(seq, packed):
                 k = d["kind"]
                 d["mod"] = layer
                 if k == "res":
-                    d["wd1"] = pd(layer.in_layers[2].weight)
-                    d["wd2"] = pd(layer.out_layers[3].weight)
+                    co = d["cout"]
+                    d["wd1"] = adj(d["conv1"].w, layer.in_layers[2].weight)
+                    d["wd2"] = adj(d["conv2"].w[:, :9 * co], layer.out_layers[3].weight)
                     if d["skip"]:
-                        d["wds"] = pd(layer.skip_connection.weight[:, :, 0, 0])
+                        d["wds"] = adj(d["conv2"].w[:, 9 * co:], layer.skip_connection.weight[:, :, 0, 0])
                 elif k == "st":
-                    d["wd_pi"] = pd(layer.proj_in.weight[:, :, 0, 0])
-                    d["wd_po"] = pd(layer.proj_out.weight[:, :, 0, 0])
+                    d["wd_pi"] = adj(d["proj_in"].w, layer.proj_in.weight[:, :, 0, 0])
+                    d["wd_po"] = adj(d["proj_out"].w, layer.proj_out.weight[:, :, 0, 0])
                     for tb, t in zip(layer.transformer_blocks, d["blocks"]):
                         t["mod"] = tb
-                        t["wd_qkv"] = t["qkv"].t().contiguous()
-                        t["wd_o1"] = pd(tb.attn1.to_out[0].weight)
-                        t["wd_q2"] = pd(tb.attn2.to_q.weight)
-                        t["wd_o2"] = pd(tb.attn2.to_out[0].weight)
+                        t["wd_qkv"] = (t["qkv"], True) if tc else (t["qkv"].t().contiguous(), False)
+                        t["wd_o1"] = adj(t["o1"].w, tb.attn1.to_out[0].weight)
+                        t["wd_q2"] = adj(t["q2"], tb.attn2.to_q.weight)
+                        t["wd_o2"] = adj(t["o2"].w, tb.attn2.to_out[0].weight)
                         t["ff1n"] = self._c(tb.ff.net[0].proj.weight)
                         t["ff1n_b"] = tb.ff.net[0].proj.bias.detach().float().contiguous()
-                        t["wd_ff1"] = t["ff1n"].t().contiguous()
-                        t["wd_ff2"] = pd(tb.ff.net[2].weight)
+                        t["wd_ff1"] = (t["ff1n"], True) if tc else (t["ff1n"].t().contiguous(), False)
+                        t["wd_ff2"] = adj(t["ff2"].w, tb.ff.net[2].weight)
                 elif k in ("down", "up", "conv_in"):
                     conv = layer.op if k == "down" else (layer.conv if k == "up" else layer)
-                    d["wd"] = pd(conv.weight)
+                    d["wd"] = adj(d["conv"].w, conv.weight) if k != "conv_in" else (pd(conv.weight), False)
                 elif k == "ab":
                     raise NotImplementedError("training through AttentionBlock (uncond_cin config) is not built; "
                                               "EALDM trains the SpatialTransformer UNet (stdiff config)")
@@ -109,11 +120,19 @@ class UNetTrainEngine(UNetEngine):
         walk(m.middle_block, self.mid)
         for blk, packed in zip(m.output_blocks, self.outb):
             walk(blk, packed)
-        self.wd_out = pd(m.out[2].weight)
-        self.wd_te0 = pd(m.time_embed[0].weight)
-        self.wd_te2 = pd(m.time_embed[2].weight)
-        self.wd_emb = self.emb_w.t().contiguous()
-        self.wd_kv = self.kv_w.t().contiguous() if self.kv_w is not None else None
+        self.wd_out = (pd(m.out[2].weight), False)          # 4-channel gradient: SIMT kernel, transposed copy
+        self.wd_te2 = adj(self.te2.w, m.time_embed[2].weight)
+        self.wd_emb = (self.emb_w, True) if tc else (self.emb_w.t().contiguous(), False)
+        self.wd_kv = None if self.kv_w is None else ((self.kv_w, True) if tc else (self.kv_w.t().contiguous(), False))
+
+    def _dconv(self, src: Act, wd, out: Act, ksize: int = 3, **kw) -> Act:
+        """Data gradient of a 3x3 (pad 1) / 1x1 convolution: conv of the output gradient with the adjoint weights."""
+        w, is_adj = wd
+        return ops.conv([ConvIn(src, ksize, 1, ksize // 2)], w, out, adjoint=is_adj, **kw)
+
+    def _dlinear(self, src: Act, wd, out: Act, **kw) -> Act:
+        w, is_adj = wd
+        return ops.linear(src, w, out, adjoint=is_adj, **kw)
 
     def _stats(self, n):
         return torch.empty((n, 32, 2), dtype=torch.float32, device=self.dev)
@@ -148,7 +167,7 @@ class UNetTrainEngine(UNetEngine):
             ops.colsum(g.h, _grad1d(rb.out_layers[3].bias), ws)
             ops.conv_wgrad(hn2, g.h, _grad2d(rb.out_layers[3].weight), ws, ksize=3, pad=1)
             d_hn2 = self._new(n, h, w, cout)
-            ops.conv([ConvIn(g.h, 3, 1, 1)], d["wd2"], d_hn2)
+            self._dconv(g.h, d["wd2"], d_hn2)
             d_h1 = self._new(n, h, w, cout)
             ops.group_norm_bwd(h1, d_hn2, st2, d["gn2"][0], d["gn2"][1], d_h1, ws, silu=True,
                                dgamma=_grad1d(rb.out_layers[0].weight), dbeta=_grad1d(rb.out_layers[0].bias))
@@ -156,7 +175,7 @@ class UNetTrainEngine(UNetEngine):
             ops.colsum(d_h1, self.d_emb_all, ws, segs=n, col0=d["emb_col0"], accumulate=False)
             ops.conv_wgrad(hn, d_h1, _grad2d(rb.in_layers[2].weight), ws, ksize=3, pad=1)
             d_hn = self._new(n, h, w, cin)
-            ops.conv([ConvIn(d_h1, 3, 1, 1)], d["wd1"], d_hn)
+            self._dconv(d_h1, d["wd1"], d_hn)
             dx = self._gdual(n, h, w, cin)
             gn1 = dict(silu=True, dgamma=_grad1d(rb.in_layers[0].weight), dbeta=_grad1d(rb.in_layers[0].bias))
             if d["skip"]:
@@ -164,7 +183,7 @@ class UNetTrainEngine(UNetEngine):
                 ops.conv_wgrad(x.h, g.h, _grad2d(rb.skip_connection.weight), ws, ksize=1)
                 tmp = self._new(n, h, w, cin, torch.float32)
                 ops.group_norm_bwd(x.f, d_hn, st1, d["gn1"][0], d["gn1"][1], tmp, ws, add=extra, **gn1)
-                ops.conv([ConvIn(g.h, 1, 1, 0)], d["wds"], dx.f, residual=tmp, out2=self._out2(dx))
+                self._dconv(g.h, d["wds"], dx.f, ksize=1, residual=tmp, out2=self._out2(dx))
             else:
                 ops.group_norm_bwd(x.f, d_hn, st1, d["gn1"][0], d["gn1"][1], dx.f, ws, add=g.f, add2=extra,
                                    dx2=self._out2(dx), **gn1)
@@ -226,38 +245,38 @@ class UNetTrainEngine(UNetEngine):
             ops.colsum(g.h, _grad1d(st.proj_out.bias), ws)
             ops.linear_wgrad(t_op, g.h, _grad2d(st.proj_out.weight), ws)
             dt_ = self._gdual(n, h, w, C_)
-            ops.linear(g.h, d["wd_po"], dt_.f, out2=self._out2(dt_))
+            self._dlinear(g.h, d["wd_po"], dt_.f, out2=self._out2(dt_))
             for tb, s in zip(reversed(d["blocks"]), reversed(saved)):
                 mod = tb["mod"]
                 # feed-forward
                 ops.colsum(dt_.h, _grad1d(mod.ff.net[2].bias), ws)
                 ops.linear_wgrad(s["gg"], dt_.h, _grad2d(mod.ff.net[2].weight), ws)
-                dgg = ops.linear(dt_.h, tb["wd_ff2"], nd(4 * C_))
+                dgg = self._dlinear(dt_.h, tb["wd_ff2"], nd(4 * C_))
                 dpre = ops.geglu_bwd(s["pre"], dgg, nd(8 * C_))
                 ops.colsum(dpre, _grad1d(mod.ff.net[0].proj.bias), ws)
                 ops.linear_wgrad(s["a3"], dpre, _grad2d(mod.ff.net[0].proj.weight), ws)
-                da3 = ops.linear(dpre, tb["wd_ff1"], nd(C_))
+                da3 = self._dlinear(dpre, tb["wd_ff1"], nd(C_))
                 dt2 = self._gdual(n, h, w, C_)
                 ops.layer_norm_bwd(s["t2"], da3, tb["ln3"][0], 1e-5, dt2.f, ws, add=dt_.f, dx2=self._out2(dt2),
                                    dgamma=_grad1d(mod.norm3.weight), dbeta=_grad1d(mod.norm3.bias))
                 # cross-attention
                 ops.colsum(dt2.h, _grad1d(mod.attn2.to_out[0].bias), ws)
                 ops.linear_wgrad(s["o2"], dt2.h, _grad2d(mod.attn2.to_out[0].weight), ws)
-                do2 = ops.linear(dt2.h, tb["wd_o2"], nd(C_))
+                do2 = self._dlinear(dt2.h, tb["wd_o2"], nd(C_))
                 kc = tb["kv_col0"]
                 dq2 = nd(C_)
                 ops.attention_bwd(s["q2"], kv_all.cols(kc, C_), kv_all.cols(kc + C_, C_), s["o2"], do2, dq2,
                                   self.d_kv_all.cols(kc, C_), self.d_kv_all.cols(kc + C_, C_), ws, batch=n,
                                   heads=heads, head_dim=dh, n_q=tok, n_kv=n_ctx, scale=dh ** -0.5)
                 ops.linear_wgrad(s["a2"], dq2, _grad2d(mod.attn2.to_q.weight), ws)
-                da2 = ops.linear(dq2, tb["wd_q2"], nd(C_))
+                da2 = self._dlinear(dq2, tb["wd_q2"], nd(C_))
                 dt1 = self._gdual(n, h, w, C_)
                 ops.layer_norm_bwd(s["t1"], da2, tb["ln2"][0], 1e-5, dt1.f, ws, add=dt2.f, dx2=self._out2(dt1),
                                    dgamma=_grad1d(mod.norm2.weight), dbeta=_grad1d(mod.norm2.bias))
                 # self-attention
                 ops.colsum(dt1.h, _grad1d(mod.attn1.to_out[0].bias), ws)
                 ops.linear_wgrad(s["o"], dt1.h, _grad2d(mod.attn1.to_out[0].weight), ws)
-                do = ops.linear(dt1.h, tb["wd_o1"], nd(C_))
+                do = self._dlinear(dt1.h, tb["wd_o1"], nd(C_))
                 q = s["qkv"]
                 dqkv = nd(3 * C_)
                 ops.attention_bwd(q.cols(0, C_), q.cols(C_, C_), q.cols(2 * C_, C_), s["o"], do, dqkv.cols(0, C_),
@@ -265,14 +284,14 @@ class UNetTrainEngine(UNetEngine):
                                   n_q=tok, n_kv=tok, scale=dh ** -0.5, lse=s["lse"])
                 for j, lin in enumerate((mod.attn1.to_q, mod.attn1.to_k, mod.attn1.to_v)):
                     ops.linear_wgrad(s["a1"], dqkv.cols(j * C_, C_), _grad2d(lin.weight), ws)
-                da1 = ops.linear(dqkv, tb["wd_qkv"], nd(C_))
+                da1 = self._dlinear(dqkv, tb["wd_qkv"], nd(C_))
                 dt0 = self._gdual(n, h, w, C_)
                 ops.layer_norm_bwd(s["t0"], da1, tb["ln1"][0], 1e-5, dt0.f, ws, add=dt1.f, dx2=self._out2(dt0),
                                    dgamma=_grad1d(mod.norm1.weight), dbeta=_grad1d(mod.norm1.bias))
                 dt_ = dt0
             ops.colsum(dt_.h, _grad1d(st.proj_in.bias), ws)
             ops.linear_wgrad(xn, dt_.h, _grad2d(st.proj_in.weight), ws)
-            dxn = ops.linear(dt_.h, d["wd_pi"], nd(C_))
+            dxn = self._dlinear(dt_.h, d["wd_pi"], nd(C_))
             dx = self._gdual(n, h, w, C_)
             ops.group_norm_bwd(x.f, dxn, stn, d["norm"][0], d["norm"][1], dx.f, ws, silu=False, add=g.f, add2=extra,
                                dx2=self._out2(dx), dgamma=_grad1d(st.norm.weight), dbeta=_grad1d(st.norm.bias))
@@ -315,7 +334,7 @@ class UNetTrainEngine(UNetEngine):
             if not self.need_dx:
                 return None
             dx = self._new(n, h, w, x.h.c, torch.float32)
-            ops.conv([ConvIn(g.h, 3, 1, 1)], d["wd"], dx)
+            self._dconv(g.h, d["wd"], dx)
             return Dual(dx, dx)
 
         self.tape.append(bwd)
@@ -332,7 +351,7 @@ class UNetTrainEngine(UNetEngine):
             ops.conv_wgrad(x.h, g.h, _grad2d(conv.weight), self.ws, ksize=3, stride=2, pad=1)
             z = ops.zero_insert2x(g.h, self._new(n, h, w, g.h.c))
             dx = self._gdual(n, h, w, x.f.c)
-            ops.conv([ConvIn(z, 3, 1, 1)], d["wd"], dx.f, residual=extra, out2=self._out2(dx))
+            self._dconv(z, d["wd"], dx.f, residual=extra, out2=self._out2(dx))
             return dx
 
         self.tape.append(bwd)
@@ -349,7 +368,7 @@ class UNetTrainEngine(UNetEngine):
             ops.colsum(g.h, _grad1d(conv.bias), self.ws)
             ops.conv_wgrad(up, g.h, _grad2d(conv.weight), self.ws, ksize=3, pad=1)
             dup = self._new(n, 2 * h, 2 * w, x.h.c)
-            ops.conv([ConvIn(g.h, 3, 1, 1)], d["wd"], dup)
+            self._dconv(g.h, d["wd"], dup)
             dx = self._gdual(n, h, w, x.f.c)
             ops.sumpool2x2(dup, dx.f, add=extra, dx2=self._out2(dx))
             return dx
@@ -460,7 +479,7 @@ class UNetTrainEngine(UNetEngine):
         ops.colsum(dyo, _grad1d(m.out[2].bias), ws)
         ops.conv_wgrad(s["hn"], dyo, _grad2d(m.out[2].weight), ws, ksize=3, pad=1)
         dhn = self._new(n, H, W, s["hn"].c)
-        ops.conv([ConvIn(dyo, 3, 1, 1)], self.wd_out, dhn)
+        self._dconv(dyo, self.wd_out, dhn)
         h_last: Dual = s["h_last"]
         g = self._gdual(n, H, W, h_last.f.c)
         ops.group_norm_bwd(h_last.f, dhn, s["st_out"], self.out_norm[0], self.out_norm[1], g.f, ws, silu=True,
@@ -514,11 +533,11 @@ class UNetTrainEngine(UNetEngine):
             ops.colsum(d_emb.cols(c0, cc), _grad1d(rb.emb_layers[1].bias), ws)
             ops.colsum(d_emb.cols(c0, cc), _grad1d(rb.in_layers[2].bias), ws)
         ted = self.te0.w.shape[0]
-        d_semb = ops.linear(d_emb_h, self.wd_emb, Act.empty(1, 1, n, ted, dt, dev))
+        d_semb = self._dlinear(d_emb_h, self.wd_emb, Act.empty(1, 1, n, ted, dt, dev))
         d_e2 = ops.silu_bwd(s["e2"], d_semb, Act.empty(1, 1, n, ted, dt, dev))
         ops.linear_wgrad(s["e1"], d_e2, _grad2d(m.time_embed[2].weight), ws)
         ops.colsum(d_e2, _grad1d(m.time_embed[2].bias), ws)
-        d_e1 = ops.linear(d_e2, self.wd_te2, Act.empty(1, 1, n, ted, dt, dev))
+        d_e1 = self._dlinear(d_e2, self.wd_te2, Act.empty(1, 1, n, ted, dt, dev))
         d_e0 = ops.silu_bwd(s["e0"], d_e1, Act.empty(1, 1, n, ted, dt, dev))
         ops.linear_wgrad(s["temb"], d_e0, _grad2d(m.time_embed[0].weight), ws)
         ops.colsum(d_e0, _grad1d(m.time_embed[0].bias), ws)
@@ -537,7 +556,7 @@ class UNetTrainEngine(UNetEngine):
                         ops.linear_wgrad(s["ctx"], self.d_kv_all.cols(kc + C_, C_),
                                          _grad2d(tb["mod"].attn2.to_v.weight), ws)
             if need_dcontext:
-                dc = ops.linear(self.d_kv_all, self.wd_kv, Act.empty(n, 1, s["n_ctx"], self.wd_kv.shape[0], f32, dev))
+                dc = self._dlinear(self.d_kv_all, self.wd_kv, Act.empty(n, 1, s["n_ctx"], self.kv_w.shape[1], f32, dev))
                 dcontext = dc.buf.reshape(n, s["n_ctx"], -1)
         self.tape = []
         self._saved = None

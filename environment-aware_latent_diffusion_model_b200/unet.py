@@ -320,6 +320,7 @@ class UNetEngine:
     """Packs a UNetModel's parameters to kernel layout and runs the forward pass as a straight-line
     sequence of libealdm_b200 launches on the current CUDA stream (CUDA-graph capturable: no host
     synchronisation, no data-dependent control flow)."""
+    _fused_geglu = True   # the training engine keeps the GEGLU pre-activation instead (train.py)
 
     def __init__(self, m: UNetModel, dtype: torch.dtype):
         L.load()
@@ -388,8 +389,9 @@ class UNetEngine:
                 self.kv_cols += 2 * C_
                 t["o2"] = _PackedConv(self._c(tb.attn2.to_out[0].weight),
                                       f32(tb.attn2.to_out[0].bias), C_)
-                wi, bi = geglu_interleave(self._c(tb.ff.net[0].proj.weight), tb.ff.net[0].proj.bias)
-                t["ff1"] = _PackedConv(wi, bi, 4 * C_)
+                if self._fused_geglu:   # inference: value/gate rows interleaved for the fused GEGLU epilogue
+                    wi, bi = geglu_interleave(self._c(tb.ff.net[0].proj.weight), tb.ff.net[0].proj.bias)
+                    t["ff1"] = _PackedConv(wi, bi, 4 * C_)
                 t["ff2"] = _PackedConv(self._c(tb.ff.net[2].weight), f32(tb.ff.net[2].bias), C_)
                 d["blocks"].append(t)
             return d

@@ -110,6 +110,14 @@ typedef struct {
      skips its statistics pass.  Replaces the first half of GroupNorm32 (util.py:214-216). */
   float* gn_partial;
   int64_t gn_ld; /* octets (float2 entries) per (image, chunk) row of the partial buffer */
+  /* weight_adjoint = 1 (tcgen05 path, n_src = 1): the call computes the DATA GRADIENT of a forward layer whose packed
+     matrix is given unchanged: `weight` is the forward [src.c rows, ksize^2 * n_out columns] matrix (row pitch
+     ld_weight, so a column window of a fused 3x3 + 1x1 matrix works) and
+       out[m, j] = sum_{tap, c} src[..tap.., c] * weight[c, (ksize^2 - 1 - tap) * n_out + j]
+     i.e. the transposed, tap-flipped weights are never materialised (the B operand is read MN-major). */
+  int32_t weight_adjoint;
+  int32_t reserved2;
+  int64_t ld_weight;
 } ealdm_conv_args;
 
 int ealdm_conv(const ealdm_conv_args* a, ealdm_stream_t stream);

@@ -142,6 +142,39 @@ def test_dgrad_is_conv_with_flipped_weights():
     assert rel_l2(from_act(dx2), ref) < 8e-3
 
 
+@pytest.mark.parametrize("n,c,h,w,co", [(2, 128, 16, 16, 192), (3, 256, 8, 8, 512), (1, 64, 32, 32, 64)])
+def test_dgrad_adjoint_mode_reads_forward_weights(n, c, h, w, co):
+    """weight_adjoint: the data gradient straight from the FORWARD-packed matrix (MN-major B operand), including a
+    column window of a fused 3x3 + 1x1-skip matrix; equals autograd's dX of conv2d."""
+    dtype = BF16
+    skip_c = 128
+    x = torch.randn(n, c, h, w, generator=g(40)).to(DEV).to(dtype).float().requires_grad_(True)
+    xs = torch.randn(n, skip_c, h, w, generator=g(41)).to(DEV).to(dtype).float().requires_grad_(True)
+    wt = (torch.randn(co, c, 3, 3, generator=g(42)) / math.sqrt(9 * c)).to(DEV).to(dtype).float()
+    ws = (torch.randn(co, skip_c, 1, 1, generator=g(43)) / math.sqrt(skip_c)).to(DEV).to(dtype).float()
+    dy = torch.randn(n, co, h, w, generator=g(44)).to(DEV)
+    dya = to_act(dy, dtype)
+    (F.conv2d(x, wt, padding=1) + F.conv2d(xs, ws)).backward(from_act(dya))
+    # the forward engine's fused matrix: [co, 9*c | skip_c]
+    fused = torch.cat([wt.permute(0, 2, 3, 1).reshape(co, -1), ws.reshape(co, skip_c)], dim=1).to(dtype).contiguous()
+    dx = Act.empty(n, h, w, c, F32, DEV)
+    ops.conv([ConvIn(dya, 3, 1, 1)], fused[:, :9 * c], dx, adjoint=True)
+    assert rel_l2(from_act(dx), x.grad) < 8e-3
+    res = torch.randn(n * h * w, skip_c, generator=g(45)).to(DEV)
+    dxs = Act.empty(n, h, w, skip_c, F32, DEV)
+    dxs2 = Act.empty(n, h, w, skip_c, dtype, DEV)
+    ops.conv([ConvIn(dya, 1, 1, 0)], fused[:, 9 * c:], dxs, adjoint=True, residual=Act(res, n, h, w), out2=dxs2)
+    ref = xs.grad + res.reshape(n, h, w, skip_c).permute(0, 3, 1, 2)
+    assert rel_l2(from_act(dxs), ref) < 8e-3 and rel_l2(from_act(dxs2), ref) < 8e-3
+    # a Linear layer: dX = dY W
+    M, K, N = 640, 256, 512
+    wl = (torch.randn(N, K, generator=g(46)) / math.sqrt(K)).to(DEV).to(dtype)
+    dyl = torch.randn(M, N, generator=g(47)).to(DEV).to(dtype)
+    dxl = Act.empty(1, 1, M, K, F32, DEV)
+    ops.linear(Act(dyl, 1, 1, M), wl, dxl, adjoint=True)
+    assert rel_l2(dxl.buf, dyl.float() @ wl.float()) < 8e-3
+
+
 # ---- normalisation -------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("dtype,x_f32", [(F32, False), (BF16, True), (BF16, False)])
 @pytest.mark.parametrize("silu", [True, False])
@@ -213,12 +246,14 @@ def test_layer_norm_bwd(dtype, rows, c):
 
 
 # ---- attention ---------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("dtype,tc", [(F32, False), (BF16, False), (BF16, True)])
+@pytest.mark.parametrize("dtype,tc", [(F32, False), (BF16, False), (BF16, True), (BF16, "auto")])
 @pytest.mark.parametrize("b,heads,n_q,n_kv", [(2, 8, 256, 256), (3, 16, 64, 64), (2, 8, 1024, 4), (1, 4, 100, 37),
                                                (2, 8, 1024, 1024), (1, 3, 128, 320)])
 def test_attention_bwd(dtype, tc, b, heads, n_q, n_kv):
-    if tc and (n_q % 64 or n_kv % 64):
+    if tc is True and (n_q % 64 or n_kv % 64):
         pytest.skip("tensor-core backward: self-attention shapes only (multiples of 64)")
+    auto = tc == "auto"     # the dispatcher's own choice: register-resident cross-attention kernel for n_kv <= 4
+    tc = tc is True
     hd = 32
     C = heads * hd
     scale = hd ** -0.5
@@ -247,7 +282,7 @@ def test_attention_bwd(dtype, tc, b, heads, n_q, n_kv):
     dkv = Act.empty(b, 1, n_kv, 2 * C, dtype, DEV)
     ops.attention_bwd(qa, kva.cols(0, C), kva.cols(C, C), out, Act(dout, b, 1, n_q), dq, dkv.cols(0, C),
                       dkv.cols(C, C), ops.Workspace(DEV), batch=b, heads=heads, head_dim=hd, n_q=n_q, n_kv=n_kv,
-                      scale=scale, lse=lse, impl=L.IMPL_TCGEN05 if tc else L.IMPL_SIMT)
+                      scale=scale, lse=lse, impl=L.IMPL_AUTO if auto else (L.IMPL_TCGEN05 if tc else L.IMPL_SIMT))
 
     def flat(t, n):
         return t.permute(0, 2, 1, 3).reshape(b * n, C)
