@@ -373,6 +373,7 @@ def main():
     ap.add_argument("--autograd", action="store_true", help="train workload: p_losses under torch.autograd")
     ap.add_argument("--torch-optim", action="store_true", help="train workload: torch.optim.AdamW(fused=True), no EMA")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-decode", action="store_true", help="skip the decode-inclusive images/s figure")
     ap.add_argument("--ncu-window", action="store_true",
                     help="cudaProfilerStart/Stop around the timed region (for `ncu --profile-from-start off`)")
     args = ap.parse_args()
@@ -490,6 +491,22 @@ def main():
     h2d = (x_T_h.numel() + cond_h.numel() + uc_h.numel()) * 4
     d2h = out_h.numel() * 4
 
+    # --- decode-inclusive images/s (reported separately from the headline) -------
+    # AutoencoderKL (f=8, 32x32x4 -> 256x256x3) decode of the step's latents, device resident, after sampling
+    with_decode = None
+    if not args.no_decode:
+        from ealdm_b200.autoencoder import AutoencoderKL
+        ae = AutoencoderKL(ddconfig=dict(CFG.AE_KL_F8_DDCONFIG), embed_dim=CFG.AE_KL_F8_EMBED_DIM).to(dev).eval()
+        init_synthetic_(ae, seed=3)
+        ae.set_compute_dtype("bf16")
+        zlat = step_resident()
+        for _ in range(2):
+            ae.decode(zlat)
+        ms_dec = timed(lambda: ae.decode(zlat), 3) / 3
+        with_decode = {"value": Bg / ((ms_per_step + ms_dec) * 1e-3), "unit": "images/s", "decode_ms": ms_dec,
+                       "first_stage": "AutoencoderKL f=8 (autoencoder_kl_32x32x4), bf16, 256x256x3 output"}
+        del ae
+
     # --- roofline of the dominant kernel: the tcgen05 implicit-GEMM conv/linear ----------------------
     # one eager, instrumented UNet forward at the benchmark's UNet batch: CUDA events around every
     # ealdm_conv launch on the launching stream; algorithmic FLOPs = 2*M*N*K of each launch.
@@ -574,6 +591,7 @@ def main():
             "unet_tflops_per_gpu": step_tflops,
             "unet_frac_of_sustained_peak": step_tflops / peaks["bf16_sustained"],
             "cpu_baseline": cpu,
+            "with_decode": with_decode,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
