@@ -28,7 +28,7 @@ EXPORTS = [
     "ealdm_group_norm_bwd_workspace_bytes", "ealdm_layer_norm_bwd", "ealdm_layer_norm_bwd_workspace_bytes",
     "ealdm_attention_bwd", "ealdm_attention_bwd_workspace_bytes", "ealdm_geglu", "ealdm_geglu_bwd",
     "ealdm_silu", "ealdm_silu_bwd", "ealdm_colsum", "ealdm_colsum_workspace_bytes", "ealdm_zero_insert2x",
-    "ealdm_sumpool2x2", "ealdm_cfg_mse_bwd", "ealdm_gn_partial", "ealdm_adamw_ema_step", "ealdm_plms_eps", "ealdm_vq_nearest",
+    "ealdm_sumpool2x2", "ealdm_cfg_mse_bwd", "ealdm_gn_partial", "ealdm_adamw_ema_step", "ealdm_plms_eps", "ealdm_vq_nearest", "ealdm_ddpm_step",
 ]
 WGRAD_PACKED, WGRAD_OIHW = 0, 1
 
@@ -199,6 +199,7 @@ def _declare(lib):
         ("ealdm_adamw_ema_step", [C.POINTER(AdamWArgs), vp]),
         ("ealdm_plms_eps", [vp, vp, f32, vp, vp, vp, i32, vp, vp, i64, vp]),
         ("ealdm_vq_nearest", [vp, i64, i64, i64, vp, i64, vp, vp, vp]),
+        ("ealdm_ddpm_step", [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, f32, i64, i64, vp, vp, vp]),
     ]:
         fn = getattr(lib, name)
         fn.restype = C.c_int

@@ -103,6 +103,30 @@ cfg_mse_kernel(const float* __restrict__ eu, const float* __restrict__ ec,
   }
 }
 
+// DDPM ancestral step, ddpm.py:1081-1140 (eps parameterisation), per sample b with t = t[b], in the reference's
+// fp32 operation order:
+//   x0   = sqrt_recip_ac[t]*x - sqrt_recipm1_ac[t]*eps;  optional clamp to [-1, 1]
+//   mean = coef1[t]*x0 + coef2[t]*x;   x_prev = mean + (t != 0) * exp(0.5*logvar[t]) * (noise*temperature)
+__global__ void __launch_bounds__(NT)
+ddpm_step_kernel(const float* __restrict__ x, const float* __restrict__ eps, const float* __restrict__ noise,
+                 const long long* __restrict__ t, const float* __restrict__ sqrt_recip_ac,
+                 const float* __restrict__ sqrt_recipm1_ac, const float* __restrict__ coef1,
+                 const float* __restrict__ coef2, const float* __restrict__ logvar, int clip, float temperature,
+                 long long per_sample, long long total, float* __restrict__ x_prev, float* __restrict__ x0_out) {
+  for (long long i = blockIdx.x * static_cast<long long>(NT) + threadIdx.x; i < total;
+       i += static_cast<long long>(NT) * gridDim.x) {
+    const long long tb = t[i / per_sample];
+    float x0 = __fsub_rn(__fmul_rn(sqrt_recip_ac[tb], x[i]), __fmul_rn(sqrt_recipm1_ac[tb], eps[i]));
+    if (clip) x0 = fminf(fmaxf(x0, -1.0f), 1.0f);
+    const float mean = __fadd_rn(__fmul_rn(coef1[tb], x0), __fmul_rn(coef2[tb], x[i]));
+    const float mask = tb == 0 ? 0.0f : 1.0f;
+    const float sd = expf(__fmul_rn(0.5f, logvar[tb]));
+    const float nz = __fmul_rn(noise[i], temperature);
+    x_prev[i] = __fadd_rn(mean, __fmul_rn(__fmul_rn(mask, sd), nz));
+    if (x0_out) x0_out[i] = x0;
+  }
+}
+
 // PLMS (pseudo linear multistep) eps combination, plms.py:213-231, in the reference's fp32 operation order:
 //   e_t = e_uncond + s*(e_cond - e_uncond)   (or e_cond)
 //   mode 1: (e_t + o1) / 2   mode 2: (3 e_t - o1) / 2   mode 3: (23 e_t - 16 o1 + 5 o2) / 12
@@ -234,6 +258,26 @@ extern "C" int ealdm_plms_eps(const float* e_uncond, const float* e_cond, float 
   sampler::plms_eps_kernel<<<static_cast<unsigned>(blocks < 2368 ? blocks : 2368), sampler::NT, 0,
                              static_cast<cudaStream_t>(stream)>>>(e_uncond, e_cond, cfg_scale, old1, old2, old3, mode,
                                                                   e_t_out, e_prime_out, numel);
+  EALDM_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ealdm_ddpm_step(const float* x, const float* eps, const float* noise, const int64_t* t,
+                               const float* sqrt_recip_alphas_cumprod, const float* sqrt_recipm1_alphas_cumprod,
+                               const float* posterior_mean_coef1, const float* posterior_mean_coef2,
+                               const float* posterior_log_variance_clipped, int32_t clip_denoised, float temperature,
+                               int64_t batch, int64_t per_sample, float* x_prev, float* x0_out, ealdm_stream_t stream) {
+  EALDM_REQUIRE(x && eps && noise && t && sqrt_recip_alphas_cumprod && sqrt_recipm1_alphas_cumprod &&
+                    posterior_mean_coef1 && posterior_mean_coef2 && posterior_log_variance_clipped && x_prev,
+                "ddpm_step: null argument");
+  EALDM_REQUIRE(batch > 0 && per_sample > 0, "ddpm_step: bad sizes");
+  const long long total = batch * per_sample;
+  const long long blocks = ceil_div(total, sampler::NT);
+  sampler::ddpm_step_kernel<<<static_cast<unsigned>(blocks < 2368 ? blocks : 2368), sampler::NT, 0,
+                              static_cast<cudaStream_t>(stream)>>>(
+      x, eps, noise, reinterpret_cast<const long long*>(t), sqrt_recip_alphas_cumprod, sqrt_recipm1_alphas_cumprod,
+      posterior_mean_coef1, posterior_mean_coef2, posterior_log_variance_clipped, clip_denoised, temperature,
+      per_sample, total, x_prev, x0_out);
   EALDM_LAUNCH_CHECK();
   return 0;
 }

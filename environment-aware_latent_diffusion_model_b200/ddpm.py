@@ -285,11 +285,69 @@ class LatentDiffusion(nn.Module):
         loss_dict[f"{prefix}/loss"] = loss
         return loss, loss_dict
 
+    # ---- DDPM ancestral sampling (ddpm.py:1081-1266) ----------------------------------------------------------
+    @torch.no_grad()
+    def p_sample(self, x, c, t, clip_denoised=False, repeat_noise=False, return_codebook_ids=False,
+                 quantize_denoised=False, return_x0=False, temperature=1., noise_dropout=0., score_corrector=None,
+                 corrector_kwargs=None, noise=None):
+        """ddpm.py:1111-1140: UNet eps, then predict_start_from_noise + q_posterior + the noise term as ONE kernel
+        (`ealdm_ddpm_step`).  `noise` (not in the reference) replaces the torch.randn draw, for tests."""
+        if return_codebook_ids or quantize_denoised or score_corrector is not None or noise_dropout > 0. or repeat_noise:
+            raise NotImplementedError("p_sample options outside the eps / Gaussian-noise path")
+        assert self.parameterization == "eps"
+        eps = self.apply_model(x, t, c).contiguous()
+        nz = torch.randn(x.shape, device=x.device) if noise is None else noise
+        bufs = (self.sqrt_recip_alphas_cumprod, self.sqrt_recipm1_alphas_cumprod, self.posterior_mean_coef1,
+                self.posterior_mean_coef2, self.posterior_log_variance_clipped)
+        return ops.ddpm_step(x.float().contiguous(), eps, nz.float().contiguous(), t.contiguous(), bufs,
+                             clip_denoised=clip_denoised, temperature=temperature, want_x0=return_x0)
+
+    @torch.no_grad()
+    def p_sample_loop(self, cond, shape, return_intermediates=False, x_T=None, verbose=True, callback=None,
+                      timesteps=None, quantize_denoised=False, mask=None, x0=None, img_callback=None, start_T=None,
+                      log_every_t=None, noises=None):
+        """ddpm.py:1190-1247.  `noises` (not in the reference): per-iteration noise tensors for tests."""
+        log_every_t = log_every_t or self.log_every_t
+        device = self.betas.device
+        b = shape[0]
+        img = torch.randn(shape, device=device) if x_T is None else x_T
+        intermediates = [img]
+        timesteps = self.num_timesteps if timesteps is None else timesteps
+        if start_T is not None:
+            timesteps = min(timesteps, start_T)
+        if mask is not None:
+            assert x0 is not None and x0.shape[2:3] == mask.shape[2:3]
+        for k, i in enumerate(reversed(range(0, timesteps))):
+            ts = torch.full((b,), i, device=device, dtype=torch.long)
+            img = self.p_sample(img, cond, ts, clip_denoised=self.clip_denoised, quantize_denoised=quantize_denoised,
+                                noise=None if noises is None else noises[k])
+            if mask is not None:
+                img = self.q_sample(x0, ts) * mask + (1. - mask) * img
+            if i % log_every_t == 0 or i == timesteps - 1:
+                intermediates.append(img)
+            if callback:
+                callback(i)
+            if img_callback:
+                img_callback(img, i)
+        return (img, intermediates) if return_intermediates else img
+
+    @torch.no_grad()
+    def sample(self, cond, batch_size=16, return_intermediates=False, x_T=None, verbose=True, timesteps=None,
+               quantize_denoised=False, mask=None, x0=None, shape=None, **kwargs):
+        """ddpm.py:1249-1265"""
+        if shape is None:
+            shape = (batch_size, self.channels, self.image_size, self.image_size)
+        if cond is not None and not isinstance(cond, dict):
+            cond = [c[:batch_size] for c in cond] if isinstance(cond, list) else cond[:batch_size]
+        return self.p_sample_loop(cond, shape, return_intermediates=return_intermediates, x_T=x_T, verbose=verbose,
+                                  timesteps=timesteps, quantize_denoised=quantize_denoised, mask=mask, x0=x0)
+
     @torch.no_grad()
     def sample_log(self, cond, batch_size, ddim, ddim_steps, **kwargs):
-        """ddpm.py:1267-1285: DDIM with the model's guidance scale; `cond` is cat([c_neg, c])."""
+        """ddpm.py:1267-1285: DDIM with the model's guidance scale (or ancestral sampling); `cond` is cat([c_neg, c])."""
         if not ddim:
-            raise NotImplementedError("ancestral DDPM sampling is a 'next' row (SURVEY.md 8f rank 4)")
+            samples, intermediates = self.sample(cond=cond, batch_size=batch_size, return_intermediates=True, **kwargs)
+            return samples, intermediates
         sampler = DDIMSampler(self)
         shape = (self.channels, self.image_size, self.image_size)
         if self.unconditional_guidance_scale != 1. and cond is not None:

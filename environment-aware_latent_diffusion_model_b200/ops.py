@@ -345,6 +345,22 @@ def plms_eps(e_cond, *, e_uncond=None, cfg_scale=1.0, old=(), mode=0):
     return e_t, e_p
 
 
+def ddpm_step(x, eps, noise, t, bufs, *, clip_denoised=False, temperature=1.0, want_x0=False):
+    """ealdm_ddpm_step; `bufs` = (sqrt_recip_alphas_cumprod, sqrt_recipm1_alphas_cumprod, posterior_mean_coef1,
+    posterior_mean_coef2, posterior_log_variance_clipped), fp32 device tensors."""
+    lib = L.load()
+    for v in (x, eps, noise) + tuple(bufs):
+        assert v.dtype == torch.float32 and v.is_contiguous() and v.is_cuda
+    assert t.dtype == torch.int64 and t.is_contiguous()
+    x_prev = torch.empty_like(x)
+    x0 = torch.empty_like(x) if want_x0 else None
+    b = x.shape[0]
+    L.check(lib.ealdm_ddpm_step(x.data_ptr(), eps.data_ptr(), noise.data_ptr(), t.data_ptr(), *[v.data_ptr() for v in bufs],
+                                1 if clip_denoised else 0, float(temperature), b, x.numel() // b, x_prev.data_ptr(),
+                                _ptr(x0), _stream()))
+    return (x_prev, x0) if want_x0 else x_prev
+
+
 def q_sample(x0, noise, t, sqrt_ac, sqrt_1mac):
     lib = L.load()
     assert x0.dtype == torch.float32 and x0.is_contiguous() and noise.is_contiguous()

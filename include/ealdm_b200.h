@@ -443,6 +443,18 @@ int ealdm_vq_nearest(const float* z, int64_t n, int64_t e_dim, int64_t hw, const
                      float* zq, int64_t* indices, ealdm_stream_t stream);
 
 /*
+ * DDPM ancestral sampling step LatentDiffusion.p_sample (ldm/models/diffusion/ddpm.py:1081-1140, eps parameterisation):
+ * predict_start_from_noise (:218-222), optional clamp, q_posterior mean (:224-231), x_prev = mean + (t != 0) *
+ * exp(0.5 * posterior_log_variance_clipped[t]) * noise * temperature, with the schedule buffers gathered per sample.
+ * x0_out (optional) receives the x0 prediction (return_x0).  fp32, the reference's operation order.
+ */
+int ealdm_ddpm_step(const float* x, const float* eps, const float* noise, const int64_t* t,
+                    const float* sqrt_recip_alphas_cumprod, const float* sqrt_recipm1_alphas_cumprod,
+                    const float* posterior_mean_coef1, const float* posterior_mean_coef2,
+                    const float* posterior_log_variance_clipped, int32_t clip_denoised, float temperature,
+                    int64_t batch, int64_t per_sample, float* x_prev, float* x0_out, ealdm_stream_t stream);
+
+/*
  * PLMSSampler.p_sample_plms eps arithmetic (ldm/models/diffusion/plms.py:178-231), fp32, the reference's operation order:
  * e_t = e_uncond + cfg_scale*(e_cond - e_uncond) (e_cond when e_uncond is NULL) -> e_t_out (the history entry);
  * e_prime_out by `mode`: 0 = e_t, 1 = (e_t + old1)/2 (pseudo improved Euler, old1 = eps at the next timestep),

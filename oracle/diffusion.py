@@ -121,6 +121,22 @@ def ddim_sample(apply_model: Callable, alphas_cumprod_f32: torch.Tensor, S: int,
     return img, trace
 
 
+# ---- ddpm.py:1081-1140, :218-231 --------------------------------------------------------------------------
+def p_sample_ddpm(apply_model: Callable, buf: Dict[str, torch.Tensor], x: torch.Tensor, c, t: torch.Tensor,
+                  noise: torch.Tensor, clip_denoised: bool = False, temperature: float = 1.0):
+    """LatentDiffusion.p_sample (eps parameterisation): returns (x_prev, x0)."""
+    b = x.shape[0]
+    ex = lambda a: a[t].reshape(b, 1, 1, 1)  # noqa: E731  (extract_into_tensor, util.py:96-99)
+    eps = apply_model(x, t, c)
+    x0 = ex(buf["sqrt_recip_alphas_cumprod"]) * x - ex(buf["sqrt_recipm1_alphas_cumprod"]) * eps
+    if clip_denoised:
+        x0 = x0.clamp(-1.0, 1.0)
+    mean = ex(buf["posterior_mean_coef1"]) * x0 + ex(buf["posterior_mean_coef2"]) * x
+    logvar = ex(buf["posterior_log_variance_clipped"])
+    nonzero_mask = (1 - (t == 0).float()).reshape(b, 1, 1, 1)
+    return mean + nonzero_mask * (0.5 * logvar).exp() * (noise * temperature), x0
+
+
 # ---- plms.py:120-236 -------------------------------------------------------------------------------------
 def plms_sample(apply_model: Callable, alphas_cumprod_f32: torch.Tensor, S: int, x_T: torch.Tensor, cond=None,
                 ugs: float = 1.0, uc=None):

@@ -151,6 +151,20 @@ def test_plms_trajectory_uncond(sd_uncond):
     assert rel_l2(x0, G["samples"]) < 2e-5
 
 
+def test_ddpm_ancestral_steps(sd_stdiff):
+    """LatentDiffusion.p_sample_loop (timesteps 5..0): the oracle's p_sample restatement against the reference."""
+    G = gold("ddpm_ancestral.pt")
+    buf = OD.register_schedule(1000, CFG.DIFFUSION["linear_start"], CFG.DIFFUSION["linear_end"])
+    apply_model = lambda x, t, c: OU.unet_forward(sd_stdiff, CFG.UNET_STDIFF, x, t, c)  # noqa: E731
+    img = G["x_T"]
+    with torch.no_grad():
+        for k, i in enumerate(reversed(range(6))):
+            t = torch.full((2,), i, dtype=torch.long)
+            img, _ = OD.p_sample_ddpm(apply_model, buf, img, G["cond"], t, G["noise"][k], clip_denoised=G["clip_denoised"])
+            assert rel_l2(img, G["imgs"][k]) < 2e-5, i
+    assert rel_l2(img, G["out"]) < 2e-5
+
+
 def test_p_losses_and_q_sample(sd_stdiff):
     G = gold("p_losses.pt")
     buf = OD.register_schedule(1000, CFG.DIFFUSION["linear_start"], CFG.DIFFUSION["linear_end"])

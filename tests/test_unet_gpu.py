@@ -172,3 +172,18 @@ def test_plms_trajectory_vs_reference_golden(case, mode):
     assert max(rel_l2(ps[i], G["pred_x0"][i]) for i in range(G["S"])) < tol * 3
     with pytest.raises(ValueError):
         sampler.make_schedule(10, ddim_eta=0.5, verbose=False)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_ddpm_ancestral_sampling_vs_reference_golden(mode):
+    """LatentDiffusion.p_sample_loop (ddpm.py:1190-1247): the last six ancestral steps incl. the t == 0 branch."""
+    G = gold("ddpm_ancestral.pt")
+    ld = make_ld("stdiff")
+    ld.model.diffusion_model.set_compute_dtype(mode)
+    assert bool(ld.clip_denoised) == G["clip_denoised"]
+    imgs = []
+    out = ld.p_sample_loop(G["cond"].cuda(), (2, 4, 32, 32), x_T=G["x_T"].cuda(), verbose=False, timesteps=6,
+                           noises=[n.cuda() for n in G["noise"]], img_callback=lambda img, i: imgs.append(img))
+    errs = [rel_l2(imgs[k], G["imgs"][k]) for k in range(6)]
+    print(f"ddpm ancestral {mode}: x_prev rel_l2 per step = {['%.2e' % e for e in errs]}")
+    assert max(errs) < TOL[mode] and rel_l2(out, G["out"]) < TOL[mode]
