@@ -358,9 +358,82 @@ def run_autoencoder(args):
     return 0
 
 
+def run_config1(args):
+    """--workload config1: BASELINE.json configs[0], the reference's own CPU-runnable case, run EXACTLY (no
+    extrapolation) on both sides: uncond_cin-ldm-vq-f8 UNet (AttentionBlock at every level), 10-step DDIM, batch 4,
+    32x32x4 latent, eta 0.  GPU: the module API in fp32 parity mode (SIMT kernels) and in bf16 (tcgen05);
+    CPU: the oracle port in fp32 on all host cores, the full 10 steps."""
+    import torch
+
+    from ealdm_b200 import configs as CFG, ops
+    from ealdm_b200.ddim import DDIMSampler
+    from ealdm_b200.ddpm import LatentDiffusion
+    from oracle import diffusion as OD   # cpu_baseline leg only
+    from oracle import unet as OU
+
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    B, S = 4, 10
+    ld = LatentDiffusion(unet_config={"target": "ealdm_b200.unet.UNetModel", "params": dict(CFG.UNET_UNCOND)},
+                         **CFG.DIFFUSION)
+    sd = OU.synthetic_state_dict(OU.unet_param_shapes(CFG.UNET_UNCOND), seed=1)
+    ld.model.diffusion_model.load_state_dict(sd, strict=True)
+    ld = ld.to(dev).eval()
+    unet = ld.model.diffusion_model
+    sampler = DDIMSampler(ld)
+    x_T_h = torch.randn(B, 4, 32, 32, generator=torch.Generator().manual_seed(1)).pin_memory()
+    out_h = torch.empty(B, 4, 32, 32).pin_memory()
+    res = {}
+    l0 = ops.launch_count()
+    for mode in ("fp32", "bf16"):
+        unet.set_compute_dtype(mode)
+        unet.enable_cuda_graph(True)
+
+        def step():
+            z, _ = sampler.sample(S=S, batch_size=B, shape=(4, 32, 32), eta=0.0, x_T=x_T_h.to(dev, non_blocking=True),
+                                  verbose=False)
+            out_h.copy_(z, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return z
+
+        for _ in range(max(args.warmup, 3)):
+            z = step()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            z = step()
+        e1.record()
+        torch.cuda.synchronize()
+        res[mode] = (e0.elapsed_time(e1) / args.steps, z.cpu())
+    launches = ops.launch_count() - l0
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    buf = OD.register_schedule(1000, CFG.DIFFUSION["linear_start"], CFG.DIFFUSION["linear_end"])
+    apply_model = lambda xx, tt, cc: OU.unet_forward(sd, CFG.UNET_UNCOND, xx, tt)  # noqa: E731
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        ref, _ = OD.ddim_sample(apply_model, buf["alphas_cumprod"], S, x_T_h.clone(), eta=0.0)
+    cpu_s = time.perf_counter() - t0
+    rel = lambda a: float((a.double() - ref.double()).norm() / ref.double().norm())  # noqa: E731
+    line = {"metric": "latent samples/sec (10-step DDIM, config 1)", "value": B / (res["fp32"][0] * 1e-3), "unit": "samples/s",
+            "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": res["fp32"][0],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "uncond_cin-ldm-vq-f8 UNet, 10-step DDIM, batch 4, 32x32x4 latent, eta 0, random-init "
+                                   "weights, fp32 parity mode (BASELINE.json configs[0]); host x_T in, host latents out"},
+            "bf16": {"value": B / (res["bf16"][0] * 1e-3), "unit": "samples/s", "ms_per_step": res["bf16"][0],
+                     "rel_l2_vs_cpu_oracle": rel(res["bf16"][1])},
+            "rel_l2_vs_cpu_oracle": rel(res["fp32"][1]), "gpu_launches": int(launches),
+            "e2e": {"value": B / (res["fp32"][0] * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": x_T_h.numel() * 4,
+                    "d2h_bytes_per_step": out_h.numel() * 4},
+            "cpu_baseline": {"value": B / cpu_s, "unit": "samples/s", "cores": cores, "kind": "port",
+                             "sample": "the complete workload: oracle port (torch fp32 CPU), B=4, all 10 DDIM steps"}}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--workload", default="sample", choices=["sample", "train", "autoencoder"],
+    ap.add_argument("--workload", default="sample", choices=["sample", "train", "autoencoder", "config1"],
                     help="sample: the headline metric (default); train: BASELINE.json configs[4]; "
                          "autoencoder: BASELINE.json configs[2]")
     ap.add_argument("--gpus", type=int, default=1)
@@ -383,6 +456,8 @@ def main():
         return run_train(args)
     if args.workload == "autoencoder":
         return run_autoencoder(args)
+    if args.workload == "config1":
+        return run_config1(args)
 
     import torch
     import torch.distributed as dist
