@@ -27,6 +27,7 @@
 
 #include <cuda.h>
 #include <cudaTypedefs.h>
+#include <stdlib.h>
 
 namespace ealdm {
 namespace tc {
@@ -71,14 +72,20 @@ struct Params {
   int gn_chunks;   // 32-pixel chunks per image
   // adjoint mode: B is read MN-major from the forward-packed matrix [K rows = src channels, taps * N columns]
   int b_mn;
+  // tuning: L2 prefetch distance in tiles for 1x1 / linear A operands and residual units (0 = off); relaxed
+  // epilogue store wait (one TMA store group may stay in flight when no buffer is reused by the next unit)
+  int pf_tiles;
+  int relaxed_wait;
+  int diag;  // timing experiments only (EALDM_TC_DIAG): 1 = skip the TMA stores
 };
 
-template <int BN>
+// CTA2: the tile is 256 x BN over a CTA pair (cta_group::2); each CTA stages its 128 A rows and BN/2 B rows
+template <int BN, bool CTA2 = false>
 struct Cfg {
   static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_BYTES = (CTA2 ? BN / 2 : BN) * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN >= 256) ? 3 : (BN >= 128 ? 4 : 6);
+  static constexpr int STAGES = CTA2 ? 4 : ((BN >= 256) ? 3 : (BN >= 128 ? 4 : 6));
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
   static constexpr int EPI_OFF = STAGES * STAGE_BYTES;                 // 1024-aligned
   static constexpr int BIAS_OFF = EPI_OFF + EPI_WARPS * EPI_WARP_BYTES;
@@ -146,29 +153,80 @@ __device__ __forceinline__ void sts_row_bf16(uint8_t* buf, int lane, const float
 //   erf(x) = 1 - (1 + a1 x + ... + a6 x^6)^-16,  |error| <= 3e-7 (1.7e-6 in fp32 arithmetic),
 // far below bf16 resolution; ONE MUFU (rcp) per element instead of erff's branches.  The fp32 parity
 // path (conv_simt.cu) keeps erff.
-__device__ __forceinline__ float gelu_fast(float v) {
-  const float x = fabsf(v) * 0.70710678118654752440f;
-  float p = fmaf(0.0000430638f, x, 0.0002765672f);
-  p = fmaf(p, x, 0.0001520143f);
-  p = fmaf(p, x, 0.0092705272f);
-  p = fmaf(p, x, 0.0422820123f);
-  p = fmaf(p, x, 0.0705230784f);
-  p = fmaf(p, x, 1.0f);
+//
+// The GEGLU epilogue is bound by instruction issue (ncu: 62 % issue-active from the 8 epilogue warps, 24
+// instructions per output), so the arithmetic runs on PAIRS of fp32 values with the packed sm_100 instructions
+// (FFMA2 / FMUL2 / FADD2: one issue slot for two lanes).  With z = -|g| and the 1/sqrt(2) of erf(g/sqrt(2))
+// folded into the coefficients, p = 1 - b1 z + b2 z^2 - ... (Horner in z), r = p^-16 and
+//   gelu(g) = g Phi(g) = 0.5 ((g + |g|) - |g| r) = 0.5 ((g - z) + z r),
+// the 0.5 being folded into the value operand ((0.5 v + 0.5 bias_v), bias pre-halved in shared memory).
+__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
   float r;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(p));
-  r *= r; r *= r; r *= r; r *= r;
-  const float erf_v = copysignf(1.0f - r, v);
-  const float hv = 0.5f * v;
-  return fmaf(hv, erf_v, hv);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+// (value pair) * gelu(gate pair); `val` already holds 0.5 * (v + bias_v), `g` holds gate + bias_g
+__device__ __forceinline__ uint64_t geglu2(uint64_t val, uint64_t g) {
+  constexpr float S = 0.70710678118654752440f;
+  constexpr float B1 = -0.0705230784f * S;
+  constexpr float B2 = 0.0422820123f * S * S;
+  constexpr float B3 = -0.0092705272f * S * S * S;
+  constexpr float B4 = 0.0001520143f * S * S * S * S;
+  constexpr float B5 = -0.0002765672f * S * S * S * S * S;
+  constexpr float B6 = 0.0000430638f * S * S * S * S * S * S;
+  float g0, g1;
+  upk2(g, g0, g1);
+  const uint64_t z = pk2(__uint_as_float(__float_as_uint(g0) | 0x80000000u),
+                         __uint_as_float(__float_as_uint(g1) | 0x80000000u));
+  uint64_t p = fma2(pk2(B6, B6), z, pk2(B5, B5));
+  p = fma2(p, z, pk2(B4, B4));
+  p = fma2(p, z, pk2(B3, B3));
+  p = fma2(p, z, pk2(B2, B2));
+  p = fma2(p, z, pk2(B1, B1));
+  p = fma2(p, z, pk2(1.0f, 1.0f));
+  float p0, p1;
+  upk2(p, p0, p1);
+  uint64_t r = pk2(rcp_approx(p0), rcp_approx(p1));
+  r = mul2(r, r); r = mul2(r, r); r = mul2(r, r); r = mul2(r, r);
+  const uint64_t u = fma2(z, r, sub2(g, z));
+  return mul2(val, u);
 }
 
-template <int BN, bool GEGLU>
+template <int BN, bool GEGLU, bool CTA2>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
                const __grid_constant__ CUtensorMap tmOut2, const __grid_constant__ CUtensorMap tmRes,
                const __grid_constant__ Params p) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, CTA2>;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::BAR_OFF);
   uint64_t* empty_bar = full_bar + C::STAGES;
@@ -179,6 +237,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // CTA pair: rank 0 (leader) owns the full barriers and issues the MMAs of both CTAs
+  const uint32_t cta_rank = CTA2 ? ptx::cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
 
   if (warp == 0 && lane == 0) {
     if ((ptx::smem_u32(smem) & 1023u) != 0) {
@@ -197,45 +258,90 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tmem_full[a], 1);
-      ptx::mbar_init(&tmem_empty[a], EPI_WARPS);
+      ptx::mbar_init(&tmem_empty[a], CTA2 ? 2 * EPI_WARPS : EPI_WARPS);
     }
     for (int a = 0; a < 2 * EPI_WARPS; ++a) ptx::mbar_init(&res_bar[a], 1);
     ptx::fence_mbar_init();
   }
   if (warp == 1) {
-    ptx::tmem_alloc(tmem_slot, C::TMEM_COLS);
-    ptx::tmem_relinquish();
+    if constexpr (CTA2) {
+      ptx::tmem_alloc_2sm(tmem_slot, C::TMEM_COLS);
+      ptx::tmem_relinquish_2sm();
+    } else {
+      ptx::tmem_alloc(tmem_slot, C::TMEM_COLS);
+      ptx::tmem_relinquish();
+    }
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if constexpr (CTA2) ptx::cluster_sync_all();  // the peer's barriers exist before anything remote touches them
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int total_tiles = p.m_tiles * p.n_tiles;
+  // work items: tiles (one CTA each) or, for CTA pairs, super-tiles of two consecutive M tiles and one N tile
+  const int tile_first = CTA2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int tile_step = CTA2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  const int total_tiles = (CTA2 ? (p.m_tiles + 1) / 2 : p.m_tiles) * p.n_tiles;
   const int kblocks_total = p.seg[0].kblocks + (p.nseg > 1 ? p.seg[1].kblocks : 0);
+  auto tile_mn = [&](int tile, int& mt, int& nt) {
+    const int q = tile / p.n_tiles;
+    nt = tile - q * p.n_tiles;
+    mt = CTA2 ? 2 * q + static_cast<int>(cta_rank) : q;  // mt == m_tiles (odd tail): every box is out of range
+  };
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int mt = tile / p.n_tiles;
-        const int nt = tile - mt * p.n_tiles;
+      const uint32_t full0 = CTA2 ? ptx::mapa_u32(&full_bar[0], 0) : 0u;  // the leader's full barriers
+      for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
+        int mt, nt;
+        tile_mn(tile, mt, nt);
         const int tw = mt % p.tiles_w;
         const int th = (mt / p.tiles_w) % p.tiles_h;
         const int tn = mt / (p.tiles_w * p.tiles_h);
         const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn;
+        if (p.pf_tiles > 0) {
+          // pull the A boxes of a later tile of this CTA into L2 now (1x1 segments only: a 3x3 tap walk re-reads
+          // its neighbourhood from L2 anyway)
+          const int ptile = tile + p.pf_tiles * tile_step;
+          int pmt, pnt;
+          tile_mn(ptile, pmt, pnt);
+          if (ptile < total_tiles && pnt == 0) {  // one CTA per M tile asks
+            const int pw0 = (pmt % p.tiles_w) * p.bw, ph0 = ((pmt / p.tiles_w) % p.tiles_h) * p.bh;
+            const int pn0 = (pmt / (p.tiles_w * p.tiles_h)) * p.bn;
+            for (int s = 0; s < p.nseg; ++s) {
+              const Segment sg = p.seg[s];
+              if (sg.ksize != 1) continue;
+              const CUtensorMap* tmA = (s == 0) ? &tmA0 : &tmA1;
+              for (int cb = 0; cb < sg.cblk; ++cb)
+                ptx::tma_prefetch_4d(tmA, cb * BK, pw0 * sg.stride - sg.pad, ph0 * sg.stride - sg.pad, pn0);
+            }
+          }
+        }
         for (int s = 0; s < p.nseg; ++s) {
           const Segment sg = p.seg[s];
           const CUtensorMap* tmA = (s == 0) ? &tmA0 : &tmA1;
           int tap = 0, cb = 0;
           for (int kb = 0; kb < sg.kblocks; ++kb) {
             ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
-            ptx::mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
             const int kh = tap / sg.ksize;
             const int kw = tap - kh * sg.ksize;
             uint8_t* sa = smem + stage * C::STAGE_BYTES;
+            if constexpr (CTA2) {
+              // both CTAs' boxes complete on the LEADER's full barrier, which expects the bytes of the pair
+              if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
+              const uint32_t fb = full0 + static_cast<uint32_t>(stage) * 8u;
+              ptx::tma_load_4d_2sm(sa, tmA, fb, cb * BK, w0 * sg.stride + kw - sg.pad, h0 * sg.stride + kh - sg.pad,
+                                   n0);
+              ptx::tma_load_2d_2sm(sa + C::A_BYTES, &tmB, fb, sg.bkoff + kb * BK,
+                                   nt * BN + static_cast<int>(cta_rank) * (BN / 2));
+              if (++cb == sg.cblk) { cb = 0; ++tap; }
+              if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+              continue;
+            }
+            ptx::mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
             ptx::tma_load_4d(sa, tmA, &full_bar[stage], cb * BK, w0 * sg.stride + kw - sg.pad,
                              h0 * sg.stride + kh - sg.pad, n0);
             if (p.b_mn) {
@@ -254,13 +360,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    const uint32_t idesc = ptx::make_idesc_bf16(BM, BN) | (p.b_mn ? (1u << 16) : 0u);   // bit 16: B is MN-major
+    // ===================== MMA issuer (CTA pairs: the leader only) =====================
+    const uint32_t idesc =
+        ptx::make_idesc_bf16(CTA2 ? 2 * BM : BM, BN) | (p.b_mn ? (1u << 16) : 0u);  // bit 16: B is MN-major
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = tile_first; tile < total_tiles && leader; tile += tile_step) {
       ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
       ptx::tc_fence_after();
       const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
@@ -270,7 +377,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         if (lane == 0) {
           const uint32_t sa = ptx::smem_u32(smem + stage * C::STAGE_BYTES);
           const uint64_t adesc = ptx::make_sw128_kmajor_desc(sa);
-          if (p.b_mn) {
+          if constexpr (CTA2) {
+            const uint64_t bdesc = ptx::make_sw128_kmajor_desc(sa + C::A_BYTES);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k)
+              ptx::umma_bf16_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            ptx::umma_commit_2sm(&empty_bar[stage], 3);  // frees this stage in both CTAs
+            if (kb == kblocks_total - 1) ptx::umma_commit_2sm(&tmem_full[acc], 3);
+          } else if (p.b_mn) {
             // MN-major B: 64-column groups 8192 B apart (LBO), 8-row K groups 1024 B apart; 16 K rows = 2048 B
             const uint64_t bdesc = ptx::make_sw128_mnmajor_desc(sa + C::A_BYTES, 8192);
 #pragma unroll
@@ -284,8 +398,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
               ptx::umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
             }
           }
-          ptx::umma_commit(&empty_bar[stage]);
-          if (kb == kblocks_total - 1) ptx::umma_commit(&tmem_full[acc]);
+          if constexpr (!CTA2) {
+            ptx::umma_commit(&empty_bar[stage]);
+            if (kb == kblocks_total - 1) ptx::umma_commit(&tmem_full[acc]);
+          }
         }
         __syncwarp();
         if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
@@ -312,9 +428,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     const int my_dn = (r0 + lane) / (p.bw * p.bh);
     const uint32_t res_bytes = p.res_f32 ? 4096u : 2048u;
 
+    const uint32_t tmem_empty0 = CTA2 ? ptx::mapa_u32(&tmem_empty[0], 0) : 0u;  // the leader's barriers
     auto unit_origin = [&](int tile, int& nt, int& w, int& h, int& n) {
-      const int mt = tile / p.n_tiles;
-      nt = tile - mt * p.n_tiles;
+      int mt;
+      tile_mn(tile, mt, nt);
       w = (mt % p.tiles_w) * p.bw + sw0;
       h = ((mt / p.tiles_w) % p.tiles_h) * p.bh + sh0;
       n = (mt / (p.tiles_w * p.tiles_h)) * p.bn + sn0;
@@ -327,18 +444,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     };
 
     uint32_t it = 0;  // units processed by this warp: buffer = it & 1, mbarrier parity = (it >> 1) & 1
-    if (!GEGLU && p.has_res && lane == 0 && part < UNITS && static_cast<int>(blockIdx.x) < total_tiles)
-      issue_res(blockIdx.x, part, 0);
+    if (!GEGLU && p.has_res && lane == 0 && part < UNITS && tile_first < total_tiles)
+      issue_res(tile_first, part, 0);
 
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
       int nt, w, h, n;
       unit_origin(tile, nt, w, h, n);
       // bias of this tile's BN columns -> shared memory (one value per epilogue thread)
       if (etid < BN) {
         const int col = nt * BN + etid;
-        bias_s[acc * BN + etid] = (p.bias != nullptr && col < p.N) ? __ldg(p.bias + col) : 0.f;
+        float bv0 = (p.bias != nullptr && col < p.N) ? __ldg(p.bias + col) : 0.f;
+        if (GEGLU && (etid & 16) == 0) bv0 *= 0.5f;  // value columns: the epilogue computes 0.5 v + 0.5 bias (geglu2)
+        bias_s[acc * BN + etid] = bv0;
       }
       ptx::named_bar_sync(1, 32 * EPI_WARPS);
       const float* bs = bias_s + acc * BN;
@@ -347,6 +466,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         int img = (n - sn0) + my_dn;
         if (img >= p.Nimg) img = p.Nimg - 1;
         rv = p.rowvec + static_cast<long long>(img) * p.ld_rowvec + nt * BN;
+      }
+      if (!GEGLU && p.has_res && p.pf_tiles > 0 && lane == 0) {
+        // residual units of a later tile of this CTA -> L2 (the shared-memory prefetch is only one unit deep)
+        const int ptile = tile + p.pf_tiles * tile_step;
+        if (ptile < total_tiles) {
+          int pnt, pw, ph, pn;
+          unit_origin(ptile, pnt, pw, ph, pn);
+          for (int ku = part; ku < UNITS; ku += 2)
+            ptx::tma_prefetch_4d(&tmRes, pnt * OUT_PER_TILE + ku * 32, pw, ph, pn);
+        }
       }
       const uint32_t taddr0 =
           tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * BN);
@@ -358,26 +487,34 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const int b = it & 1;
         uint8_t* eb = ebuf + b * EBUF_BYTES;
         if constexpr (GEGLU) {
-          if (lane == 0) ptx::bulk_wait_read<0>();
+          if (lane == 0) {  // buffer b was last read by the store issued two units ago
+            if (p.relaxed_wait) ptx::bulk_wait_read<1>();
+            else ptx::bulk_wait_read<0>();
+          }
           __syncwarp();
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
             const int ch = 2 * ku + half;
             uint32_t v[32];
             ptx::tmem_ld_32x32(taddr0 + ch * 32, v);
-            float bv[16], bg[16];
+            uint64_t bv[8], bg[8];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const float4 t = *reinterpret_cast<const float4*>(bs + ch * 32 + 4 * j);
-              bv[4 * j] = t.x; bv[4 * j + 1] = t.y; bv[4 * j + 2] = t.z; bv[4 * j + 3] = t.w;
+              bv[2 * j] = pk2(t.x, t.y); bv[2 * j + 1] = pk2(t.z, t.w);
               const float4 g = *reinterpret_cast<const float4*>(bs + ch * 32 + 16 + 4 * j);
-              bg[4 * j] = g.x; bg[4 * j + 1] = g.y; bg[4 * j + 2] = g.z; bg[4 * j + 3] = g.w;
+              bg[2 * j] = pk2(g.x, g.y); bg[2 * j + 1] = pk2(g.z, g.w);
             }
             ptx::tmem_ld_wait();
             float o[16];
+            const uint64_t half2 = pk2(0.5f, 0.5f);
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-              o[j] = (__uint_as_float(v[j]) + bv[j]) * gelu_fast(__uint_as_float(v[16 + j]) + bg[j]);
+            for (int j = 0; j < 8; ++j) {
+              const uint64_t val =
+                  fma2(pk2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), half2, bv[j]);
+              const uint64_t g = add2(pk2(__uint_as_float(v[16 + 2 * j]), __uint_as_float(v[17 + 2 * j])), bg[j]);
+              upk2(geglu2(val, g), o[2 * j], o[2 * j + 1]);
+            }
             sts_chunk_bf16(eb, lane, 2 * half, &o[0]);
             sts_chunk_bf16(eb, lane, 2 * half + 1, &o[8]);
           }
@@ -392,11 +529,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             for (int j = 0; j < 32; ++j) r[j] = 0.f;
           }
           if (lane == 0) {
-            // the other unit buffer and the shadow buffer are free once their stores have read them
-            ptx::bulk_wait_read<0>();
+            // the other unit buffer (next residual prefetch) and the single shadow buffer are free once their stores
+            // have read them; without either, only the store issued two units ago (same buffer) must be done
+            if (p.relaxed_wait && !p.has_res && !p.has_out2) ptx::bulk_wait_read<1>();
+            else ptx::bulk_wait_read<0>();
             if (p.has_res) {
               if (ku + 2 < UNITS) issue_res(tile, ku + 2, b ^ 1);
-              else if (tile + static_cast<int>(gridDim.x) < total_tiles) issue_res(tile + gridDim.x, part, b ^ 1);
+              else if (tile + tile_step < total_tiles) issue_res(tile + tile_step, part, b ^ 1);
             }
           }
           __syncwarp();
@@ -476,7 +615,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         }
         ptx::fence_proxy_async();
         __syncwarp();
-        if (lane == 0) {
+        if (lane == 0 && p.diag != 1) {
           const int c0 = nt * OUT_PER_TILE + ku * 32;
           ptx::tma_store_4d(&tmOut, eb, c0, w, h, n);
           if (!GEGLU && p.has_out2) ptx::tma_store_4d(&tmOut2, o2buf, c0, w, h, n);
@@ -486,7 +625,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       }
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
+      if (lane == 0) {
+        if constexpr (CTA2) ptx::mbar_arrive_cluster(tmem_empty0 + static_cast<uint32_t>(acc) * 8u);
+        else ptx::mbar_arrive(&tmem_empty[acc]);
+      }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
@@ -495,9 +637,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 
   ptx::tc_fence_before();
   __syncthreads();
+  if constexpr (CTA2) ptx::cluster_sync_all();  // neither CTA may leave (or free TMEM) while the pair still works
   if (warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, C::TMEM_COLS);
+    if constexpr (CTA2) ptx::tmem_dealloc_2sm(tmem_base, C::TMEM_COLS);
+    else ptx::tmem_dealloc(tmem_base, C::TMEM_COLS);
   }
 }
 
@@ -537,15 +681,59 @@ static int launch_bn(const CUtensorMap* tm, const Params& p, cudaStream_t st) {
   using C = Cfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
-    EALDM_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, GEGLU>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    EALDM_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, GEGLU, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     C::SMEM_BYTES));
     attr_set = true;
   }
   const int total = p.m_tiles * p.n_tiles;
   const int grid = total < num_sms() ? total : num_sms();
-  conv_tc_kernel<BN, GEGLU><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], p);
+  conv_tc_kernel<BN, GEGLU, false><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5],
+                                                                             p);
   EALDM_LAUNCH_CHECK();
   return 0;
+}
+
+// CTA pairs: a persistent grid of 2-CTA clusters, as many as the device can hold at once (one CTA per SM)
+template <int BN, bool GEGLU>
+static int launch_pair(const CUtensorMap* tm, const Params& p, cudaStream_t st) {
+  using C = Cfg<BN, true>;
+  static int max_clusters = 0;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = st;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (!max_clusters) {
+    EALDM_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, GEGLU, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    C::SMEM_BYTES));
+    cfg.gridDim = dim3(num_sms() & ~1);
+    int n = 0;
+    EALDM_CUDA(cudaOccupancyMaxActiveClusters(&n, conv_tc_kernel<BN, GEGLU, true>, &cfg));
+    EALDM_REQUIRE(n > 0, "tcgen05 conv: no 2-CTA cluster fits on this device");
+    max_clusters = n < num_sms() / 2 ? n : num_sms() / 2;
+  }
+  const int total = ((p.m_tiles + 1) / 2) * p.n_tiles;
+  const int clusters = total < max_clusters ? total : max_clusters;
+  cfg.gridDim = dim3(2 * clusters);
+  EALDM_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, GEGLU, true>, tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], p));
+  return 0;
+}
+
+// 0: never pair CTAs, 1 (default): pair them where the shape allows
+static int cta2_mode() {
+  static int m = -1;
+  if (m < 0) {
+    const char* e = getenv("EALDM_TC_CTA2");
+    m = e ? atoi(e) : 1;
+  }
+  return m;
 }
 
 static bool aligned_2d(const void* ptr, long long ld, int elem_bytes) {
@@ -646,6 +834,11 @@ int launch(const ealdm_conv_args* a, cudaStream_t st) {
     BN = (c256 <= c128) ? 256 : 128;
   }
   p.n_tiles = static_cast<int>(ceil_div(a->n_out, BN));
+  // CTA pairs (256 x 256 tiles, a third less operand traffic per SM) for every problem with an even number of M tiles
+  // and a reduction long enough (K >= 1024) to amortise the pair's cross-CTA barrier latency (measured: K = 256 / 512
+  // GEMMs lose 5-25 % as pairs, K >= 1024 GEMMs and all 3x3 convs gain 3-12 %); EALDM_TC_CTA2=2 pairs regardless of K
+  const bool pair = BN == 256 && !a->weight_adjoint && cta2_mode() != 0 && p.m_tiles >= 2 && p.m_tiles % 2 == 0 &&
+                    (a->k_total >= 1024 || cta2_mode() == 2);
 
   CUtensorMap tm[6];  // A0, A1, W, out, out2, residual
   memset(tm, 0, sizeof(tm));
@@ -694,7 +887,7 @@ int launch(const ealdm_conv_args* a, cudaStream_t st) {
   } else {
     cuuint64_t gdim[2] = {static_cast<cuuint64_t>(a->k_total), static_cast<cuuint64_t>(a->n_out)};
     cuuint64_t gstr[1] = {static_cast<cuuint64_t>(a->k_total) * 2};
-    cuuint32_t box[2] = {BK, static_cast<cuuint32_t>(BN)};
+    cuuint32_t box[2] = {BK, static_cast<cuuint32_t>(pair ? BN / 2 : BN)};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = encode(&tm[2], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(a->weight),
                         gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -724,12 +917,27 @@ int launch(const ealdm_conv_args* a, cudaStream_t st) {
   p.gn_ld = static_cast<int>(a->gn_ld);
   p.gn_chunks = static_cast<int>(a->h_out * a->w_out / 32);
   p.b_mn = a->weight_adjoint ? 1 : 0;
+  {
+    static int pf = -1, rw = -1;
+    if (pf < 0) {
+      const char* e = getenv("EALDM_TC_PREFETCH_TILES");
+      pf = e ? atoi(e) : 0;
+      const char* w = getenv("EALDM_TC_RELAXED_WAIT");
+      rw = w ? atoi(w) : 1;
+    }
+    p.pf_tiles = pf;
+    p.relaxed_wait = rw;
+    static int dg = -1;
+    if (dg < 0) { const char* d = getenv("EALDM_TC_DIAG"); dg = d ? atoi(d) : 0; }
+    p.diag = dg;
+  }
 
   switch (BN) {
     case 32: return launch_bn<32, false>(tm, p, st);
     case 128:
       return geglu ? launch_bn<128, true>(tm, p, st) : launch_bn<128, false>(tm, p, st);
     default:
+      if (pair) return geglu ? launch_pair<256, true>(tm, p, st) : launch_pair<256, false>(tm, p, st);
       return geglu ? launch_bn<256, true>(tm, p, st) : launch_bn<256, false>(tm, p, st);
   }
 }
