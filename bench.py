@@ -625,8 +625,12 @@ def main():
                 "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                 "frac": achieved / peaks["bf16_sustained"], "peak_source": peaks["source"] + " (sustained)",
                 "traffic": None, "launches_per_forward": n_tc, "avg_launch_ms": tc_ms / max(n_tc, 1),
-                "share_of_forward": tc_ms / fwd_ms if fwd_ms > 0 else None,
-                "note": "event-timed eager forward at UNet batch %d; algorithmic FLOPs = 2*M*N*K per launch" % (2 * B)}
+                # share of one DDIM step of the timed (CUDA-graph) run; the instrumented eager forward itself is
+                # host-bound (an event pair per launch), so its own duration is reported separately
+                "share_of_forward": tc_ms / (ms_per_step / S) if ms_per_step > 0 else None,
+                "eager_instrumented_forward_ms": fwd_ms,
+                "note": "event-timed eager forward at UNet batch %d; algorithmic FLOPs = 2*M*N*K per launch; "
+                        "share_of_forward = summed launch time / (ms_per_step / ddim_steps)" % (2 * B)}
     # DRAM bytes per launch of the same kernel from the committed ncu capture of one forward at this batch
     tpath = os.path.join(ROOT, "profiles", "r01_conv_tc_traffic.json")
     if os.path.exists(tpath) and B == 64:

@@ -16,9 +16,10 @@ CSRC_DIR = os.path.join(_HERE, "csrc")
 F32, BF16 = 0, 1
 ACT_NONE, ACT_SILU, ACT_GEGLU = 0, 1, 2
 IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05 = 0, 1, 2
+TC_OPT_CTA2, TC_OPT_WIDE, TC_OPT_RELAXED_WAIT, TC_OPT_BN = 0, 1, 2, 3
 
 EXPORTS = [
-    "ealdm_abi_version", "ealdm_last_error", "ealdm_device_check", "ealdm_launch_count",
+    "ealdm_abi_version", "ealdm_last_error", "ealdm_device_check", "ealdm_launch_count", "ealdm_tc_set_option",
     "ealdm_conv", "ealdm_group_norm", "ealdm_group_norm_workspace_bytes", "ealdm_layer_norm", "ealdm_attention",
     "ealdm_timestep_embedding", "ealdm_nchw_to_nhwc", "ealdm_nhwc_to_nchw",
     "ealdm_upsample_nearest2x", "ealdm_copy2d", "ealdm_softmax_rows", "ealdm_ddim_step",
@@ -157,6 +158,8 @@ def _declare(lib):
     lib.ealdm_device_check.argtypes = []
     lib.ealdm_launch_count.restype = C.c_int64
     lib.ealdm_launch_count.argtypes = []
+    lib.ealdm_tc_set_option.restype = C.c_int
+    lib.ealdm_tc_set_option.argtypes = [C.c_int, C.c_int]
     lib.ealdm_group_norm_workspace_bytes.restype = C.c_int64
     lib.ealdm_group_norm_workspace_bytes.argtypes = [i64, i64, i64]
     for name, argt in [

@@ -20,6 +20,7 @@ void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 namespace tc {
 bool supported(const ealdm_conv_args* a);
 int launch(const ealdm_conv_args* a, cudaStream_t st);
+int set_option(int option, int value);
 }  // namespace tc
 namespace simt {
 int launch(const ealdm_conv_args* a, cudaStream_t st);
@@ -32,6 +33,8 @@ using namespace ealdm;
 extern "C" int ealdm_abi_version(void) { return EALDM_ABI_VERSION; }
 extern "C" const char* ealdm_last_error(void) { return g_err; }
 extern "C" int64_t ealdm_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+extern "C" int ealdm_tc_set_option(int option, int value) { return tc::set_option(option, value); }
 
 extern "C" int ealdm_device_check(void) {
   int dev = 0;

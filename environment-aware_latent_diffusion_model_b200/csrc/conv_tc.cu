@@ -72,11 +72,11 @@ struct Params {
   int gn_chunks;   // 32-pixel chunks per image
   // adjoint mode: B is read MN-major from the forward-packed matrix [K rows = src channels, taps * N columns]
   int b_mn;
-  // tuning: L2 prefetch distance in tiles for 1x1 / linear A operands and residual units (0 = off); relaxed
-  // epilogue store wait (one TMA store group may stay in flight when no buffer is reused by the next unit)
-  int pf_tiles;
+  // relaxed epilogue store wait: one TMA store group may stay in flight when the next unit reuses no buffer
   int relaxed_wait;
-  int diag;  // timing experiments only (EALDM_TC_DIAG): 1 = skip the TMA stores
+  // wide epilogue passes (BN = 256, no residual, no shadow): every warp fills [32 rows x 128 B] boxes for 64 (fp32) or
+  // 128 (bf16) columns and pays ONE wait / fence / store-issue sequence for them instead of one per 32 columns
+  int wide;
 };
 
 // CTA2: the tile is 256 x BN over a CTA pair (cta_group::2); each CTA stages its 128 A rows and BN/2 B rows
@@ -143,6 +143,15 @@ __device__ __forceinline__ void sts_chunk_bf16(uint8_t* buf, int lane, int j, co
   u.z = pack2_bf16(v[4], v[5]);
   u.w = pack2_bf16(v[6], v[7]);
   *reinterpret_cast<uint4*>(buf + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = u;
+}
+// 8 consecutive bf16 into 16-byte chunk j (0..7) of row `lane` of a [32 rows x 128 B] SWIZZLE_128B box
+__device__ __forceinline__ void sts_chunk_bf16_sw128(uint8_t* buf, int lane, int j, const float* v) {
+  uint4 u;
+  u.x = pack2_bf16(v[0], v[1]);
+  u.y = pack2_bf16(v[2], v[3]);
+  u.z = pack2_bf16(v[4], v[5]);
+  u.w = pack2_bf16(v[6], v[7]);
+  *reinterpret_cast<uint4*>(buf + lane * 128 + ((j ^ (lane & 7)) << 4)) = u;
 }
 __device__ __forceinline__ void sts_row_bf16(uint8_t* buf, int lane, const float (&v)[32]) {
 #pragma unroll
@@ -218,6 +227,48 @@ __device__ __forceinline__ uint64_t geglu2(uint64_t val, uint64_t g) {
   r = mul2(r, r); r = mul2(r, r); r = mul2(r, r); r = mul2(r, r);
   const uint64_t u = fma2(z, r, sub2(g, z));
   return mul2(val, u);
+}
+
+// GroupNorm partial statistics of one [32 pixels x 32 channels] unit held one row per lane (see Params::gn_partial)
+__device__ __forceinline__ void gn_partial_unit(const Params& p, const float (&r)[32], int lane, bool valid, int n,
+                                                int h, int w, int col0) {
+  // {sum, sum of squares} of the 4 channel octets of this unit over the warp's 32 pixel rows (one 32-pixel
+  // chunk of one image): 8 values per thread, folded across the lanes in a fixed order with 9 shuffles
+  float v8[8];
+#pragma unroll
+  for (int o = 0; o < 4; ++o) {
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { a += r[8 * o + j]; b = fmaf(r[8 * o + j], r[8 * o + j], b); }
+    v8[2 * o] = valid ? a : 0.f;
+    v8[2 * o + 1] = valid ? b : 0.f;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {   // lanes 16..31 keep values 4..7
+    const float send = (lane & 16) ? v8[i] : v8[i + 4];
+    const float keep = (lane & 16) ? v8[i + 4] : v8[i];
+    v8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float send = (lane & 8) ? v8[i] : v8[i + 2];
+    const float keep = (lane & 8) ? v8[i + 2] : v8[i];
+    v8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+  {
+    const float send = (lane & 4) ? v8[0] : v8[1];
+    const float keep = (lane & 4) ? v8[1] : v8[0];
+    v8[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  v8[0] += __shfl_xor_sync(0xffffffffu, v8[0], 2);
+  v8[0] += __shfl_xor_sync(0xffffffffu, v8[0], 1);
+  if ((lane & 3) == 0 && n < p.Nimg && col0 < p.N) {
+    const int vi = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);  // value index 0..7
+    const int chunk = (h * p.Wout + w) >> 5;
+    float* dst = reinterpret_cast<float*>(p.gn_partial + (static_cast<long long>(n) * p.gn_chunks + chunk) * p.gn_ld +
+                                          (col0 >> 3) + (vi >> 1));
+    dst[vi & 1] = v8[0];
+  }
 }
 
 template <int BN, bool GEGLU, bool CTA2>
@@ -302,24 +353,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const int th = (mt / p.tiles_w) % p.tiles_h;
         const int tn = mt / (p.tiles_w * p.tiles_h);
         const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn;
-        if (p.pf_tiles > 0) {
-          // pull the A boxes of a later tile of this CTA into L2 now (1x1 segments only: a 3x3 tap walk re-reads
-          // its neighbourhood from L2 anyway)
-          const int ptile = tile + p.pf_tiles * tile_step;
-          int pmt, pnt;
-          tile_mn(ptile, pmt, pnt);
-          if (ptile < total_tiles && pnt == 0) {  // one CTA per M tile asks
-            const int pw0 = (pmt % p.tiles_w) * p.bw, ph0 = ((pmt / p.tiles_w) % p.tiles_h) * p.bh;
-            const int pn0 = (pmt / (p.tiles_w * p.tiles_h)) * p.bn;
-            for (int s = 0; s < p.nseg; ++s) {
-              const Segment sg = p.seg[s];
-              if (sg.ksize != 1) continue;
-              const CUtensorMap* tmA = (s == 0) ? &tmA0 : &tmA1;
-              for (int cb = 0; cb < sg.cblk; ++cb)
-                ptx::tma_prefetch_4d(tmA, cb * BK, pw0 * sg.stride - sg.pad, ph0 * sg.stride - sg.pad, pn0);
-            }
-          }
-        }
         for (int s = 0; s < p.nseg; ++s) {
           const Segment sg = p.seg[s];
           const CUtensorMap* tmA = (s == 0) ? &tmA0 : &tmA1;
@@ -467,23 +500,121 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         if (img >= p.Nimg) img = p.Nimg - 1;
         rv = p.rowvec + static_cast<long long>(img) * p.ld_rowvec + nt * BN;
       }
-      if (!GEGLU && p.has_res && p.pf_tiles > 0 && lane == 0) {
-        // residual units of a later tile of this CTA -> L2 (the shared-memory prefetch is only one unit deep)
-        const int ptile = tile + p.pf_tiles * tile_step;
-        if (ptile < total_tiles) {
-          int pnt, pw, ph, pn;
-          unit_origin(ptile, pnt, pw, ph, pn);
-          for (int ku = part; ku < UNITS; ku += 2)
-            ptx::tma_prefetch_4d(&tmRes, pnt * OUT_PER_TILE + ku * 32, pw, ph, pn);
-        }
-      }
       const uint32_t taddr0 =
           tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * BN);
       ptx::mbar_wait(&tmem_full[acc], acc_phase);
       ptx::tc_fence_after();
 
+      bool wide_done = false;
+      if constexpr (BN == 256) {
+        if (p.wide) {
+          wide_done = true;
+          if constexpr (GEGLU) {
+            // one pass per warp and tile: 128 accumulator columns -> 64 outputs = one [32 rows x 128 B] box
+            if (lane == 0) ptx::bulk_wait_read<0>();
+            __syncwarp();
+            uint32_t v[2][32];
+            ptx::tmem_ld_32x32(taddr0 + (part * 4) * 32, v[0]);
+            const uint64_t half2 = pk2(0.5f, 0.5f);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const int ch = part * 4 + c;
+              ptx::tmem_ld_wait();
+              if (c + 1 < 4) ptx::tmem_ld_32x32(taddr0 + (ch + 1) * 32, v[(c + 1) & 1]);  // flies under the math
+              const uint32_t(&vc)[32] = v[c & 1];
+              float o[16];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float4 t = *reinterpret_cast<const float4*>(bs + ch * 32 + 4 * j);
+                const float4 g = *reinterpret_cast<const float4*>(bs + ch * 32 + 16 + 4 * j);
+                const uint64_t val0 = fma2(pk2(__uint_as_float(vc[4 * j]), __uint_as_float(vc[4 * j + 1])), half2,
+                                           pk2(t.x, t.y));
+                const uint64_t val1 = fma2(pk2(__uint_as_float(vc[4 * j + 2]), __uint_as_float(vc[4 * j + 3])), half2,
+                                           pk2(t.z, t.w));
+                const uint64_t g0 =
+                    add2(pk2(__uint_as_float(vc[16 + 4 * j]), __uint_as_float(vc[17 + 4 * j])), pk2(g.x, g.y));
+                const uint64_t g1 =
+                    add2(pk2(__uint_as_float(vc[18 + 4 * j]), __uint_as_float(vc[19 + 4 * j])), pk2(g.z, g.w));
+                upk2(geglu2(val0, g0), o[4 * j], o[4 * j + 1]);
+                upk2(geglu2(val1, g1), o[4 * j + 2], o[4 * j + 3]);
+              }
+              sts_chunk_bf16_sw128(ebuf, lane, 2 * c, &o[0]);
+              sts_chunk_bf16_sw128(ebuf, lane, 2 * c + 1, &o[8]);
+            }
+            ptx::fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              ptx::tma_store_4d(&tmOut, ebuf, nt * OUT_PER_TILE + part * 64, w, h, n);
+              ptx::bulk_commit();
+            }
+          } else {
+            // a pass = two [32 rows x 128 B] boxes: 2 x 32 fp32 columns or 2 x 64 bf16 columns
+            const int cpp = p.out_f32 ? 2 : 4;  // 32-column accumulator chunks per pass
 #pragma unroll 1
-      for (int ku = part; ku < UNITS; ku += 2) {
+            for (int ps = part; ps < (BN / 32) / cpp; ps += 2) {
+              if (lane == 0) ptx::bulk_wait_read<0>();
+              __syncwarp();
+              uint32_t v[2][32];
+              ptx::tmem_ld_32x32(taddr0 + (ps * cpp) * 32, v[0]);
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                if (c < cpp) {
+                  const int ku = ps * cpp + c;
+                  ptx::tmem_ld_wait();
+                  if (c + 1 < cpp) ptx::tmem_ld_32x32(taddr0 + (ku + 1) * 32, v[(c + 1) & 1]);
+                  const uint32_t(&vc)[32] = v[c & 1];
+                  float r[32];
+                  if (p.act == EALDM_ACT_NONE) {  // (bias + row vector) + accumulator: the narrow path's order
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                      const float4 t = *reinterpret_cast<const float4*>(bs + ku * 32 + 4 * j);
+                      r[4 * j] = 0.f + t.x; r[4 * j + 1] = 0.f + t.y; r[4 * j + 2] = 0.f + t.z; r[4 * j + 3] = 0.f + t.w;
+                    }
+                    if (rv != nullptr) {
+#pragma unroll
+                      for (int j = 0; j < 8; ++j) {
+                        if (nt * BN + ku * 32 + 4 * j < p.N) {
+                          const float4 t = __ldg(reinterpret_cast<const float4*>(rv + ku * 32 + 4 * j));
+                          r[4 * j] += t.x; r[4 * j + 1] += t.y; r[4 * j + 2] += t.z; r[4 * j + 3] += t.w;
+                        }
+                      }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) r[j] += __uint_as_float(vc[j]);
+                  } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                      float f = __uint_as_float(vc[j]) + bs[ku * 32 + j];
+                      if (rv != nullptr && nt * BN + ku * 32 + j < p.N) f += __ldg(rv + ku * 32 + j);
+                      r[j] = silu_f(f);
+                    }
+                  }
+                  if (p.gn_partial != nullptr)
+                    gn_partial_unit(p, r, lane, (n - sn0) + my_dn < p.Nimg, n, h, w, nt * BN + ku * 32);
+                  if (p.out_f32) {
+                    sts_row_f32(ebuf + c * EBUF_BYTES, lane, r);
+                  } else {
+                    uint8_t* box = ebuf + (c >> 1) * EBUF_BYTES;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) sts_chunk_bf16_sw128(box, lane, 4 * (c & 1) + j, &r[8 * j]);
+                  }
+                }
+              }
+              ptx::fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) {
+                const int c0 = nt * BN + ps * cpp * 32;
+                ptx::tma_store_4d(&tmOut, ebuf, c0, w, h, n);
+                ptx::tma_store_4d(&tmOut, ebuf + EBUF_BYTES, c0 + (p.out_f32 ? 32 : 64), w, h, n);
+                ptx::bulk_commit();
+              }
+            }
+          }
+        }
+      }
+
+#pragma unroll 1
+      for (int ku = part; ku < UNITS && !wide_done; ku += 2) {
         const int b = it & 1;
         uint8_t* eb = ebuf + b * EBUF_BYTES;
         if constexpr (GEGLU) {
@@ -568,54 +699,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
               r[j] += silu_f(f);
             }
           }
-          if (p.gn_partial != nullptr) {
-            // {sum, sum of squares} of the 4 channel octets of this unit over the warp's 32 pixel rows (one 32-pixel
-            // chunk of one image): 8 values per thread, folded across the lanes in a fixed order with 9 shuffles
-            float v8[8];
-            const bool valid = (n - sn0) + my_dn < p.Nimg;
-#pragma unroll
-            for (int o = 0; o < 4; ++o) {
-              float a = 0.f, b = 0.f;
-#pragma unroll
-              for (int j = 0; j < 8; ++j) { a += r[8 * o + j]; b = fmaf(r[8 * o + j], r[8 * o + j], b); }
-              v8[2 * o] = valid ? a : 0.f;
-              v8[2 * o + 1] = valid ? b : 0.f;
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {   // lanes 16..31 keep values 4..7
-              const float send = (lane & 16) ? v8[i] : v8[i + 4];
-              const float keep = (lane & 16) ? v8[i + 4] : v8[i];
-              v8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-            }
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-              const float send = (lane & 8) ? v8[i] : v8[i + 2];
-              const float keep = (lane & 8) ? v8[i + 2] : v8[i];
-              v8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-            }
-            {
-              const float send = (lane & 4) ? v8[0] : v8[1];
-              const float keep = (lane & 4) ? v8[1] : v8[0];
-              v8[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-            }
-            v8[0] += __shfl_xor_sync(0xffffffffu, v8[0], 2);
-            v8[0] += __shfl_xor_sync(0xffffffffu, v8[0], 1);
-            const int col0 = nt * BN + ku * 32;
-            if ((lane & 3) == 0 && n < p.Nimg && col0 < p.N) {
-              const int vi = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);  // value index 0..7
-              const int chunk = (h * p.Wout + w) >> 5;
-              float* dst = reinterpret_cast<float*>(p.gn_partial + (static_cast<long long>(n) * p.gn_chunks + chunk) * p.gn_ld +
-                                                    (col0 >> 3) + (vi >> 1));
-              dst[vi & 1] = v8[0];
-            }
-          }
+          if (p.gn_partial != nullptr) gn_partial_unit(p, r, lane, (n - sn0) + my_dn < p.Nimg, n, h, w, nt * BN + ku * 32);
           if (p.out_f32) sts_row_f32(eb, lane, r);
           else sts_row_bf16(eb, lane, r);
           if (p.has_out2) sts_row_bf16(o2buf, lane, r);
         }
         ptx::fence_proxy_async();
         __syncwarp();
-        if (lane == 0 && p.diag != 1) {
+        if (lane == 0) {
           const int c0 = nt * OUT_PER_TILE + ku * 32;
           ptx::tma_store_4d(&tmOut, eb, c0, w, h, n);
           if (!GEGLU && p.has_out2) ptx::tma_store_4d(&tmOut2, o2buf, c0, w, h, n);
@@ -723,17 +814,33 @@ static int launch_pair(const CUtensorMap* tm, const Params& p, cudaStream_t st) 
   const int clusters = total < max_clusters ? total : max_clusters;
   cfg.gridDim = dim3(2 * clusters);
   EALDM_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, GEGLU, true>, tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], p));
+  EALDM_LAUNCH_CHECK();
   return 0;
 }
 
-// 0: never pair CTAs, 1 (default): pair them where the shape allows
+// schedule switches (ealdm_tc_set_option); defaults from the environment, read once
+static int g_opt[4] = {-1, -1, -1, -1};
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+static void init_options() {
+  if (g_opt[0] >= 0) return;
+  g_opt[EALDM_TC_OPT_CTA2] = env_int("EALDM_TC_CTA2", 1);
+  g_opt[EALDM_TC_OPT_WIDE] = env_int("EALDM_TC_WIDE", 1);
+  g_opt[EALDM_TC_OPT_RELAXED_WAIT] = env_int("EALDM_TC_RELAXED_WAIT", 1);
+  g_opt[EALDM_TC_OPT_BN] = env_int("EALDM_TC_BN", 0);
+}
+int set_option(int option, int value) {
+  init_options();
+  if (option < 0 || option > 3) return set_error(EALDM_EINVAL, "tcgen05 conv: unknown option %d", option);
+  const int prev = g_opt[option];
+  g_opt[option] = value;
+  return prev;
+}
 static int cta2_mode() {
-  static int m = -1;
-  if (m < 0) {
-    const char* e = getenv("EALDM_TC_CTA2");
-    m = e ? atoi(e) : 1;
-  }
-  return m;
+  init_options();
+  return g_opt[EALDM_TC_OPT_CTA2];
 }
 
 static bool aligned_2d(const void* ptr, long long ld, int elem_bytes) {
@@ -778,18 +885,20 @@ bool supported(const ealdm_conv_args* a) {
 
 // 4-D (C, W, H, N) tensor map over an NHWC output-space tensor with a [32 columns x 32 rows] box
 static int encode_unit_map(PFN_cuTensorMapEncodeTiled_v12000 encode, CUtensorMap* tm, const void* base,
-                           bool f32, long long cols, long long ld, const ealdm_conv_args* a, const int (&sub)[3]) {
+                           bool f32, long long cols, long long ld, const ealdm_conv_args* a, const int (&sub)[3],
+                           bool wide_bf16 = false) {
   const cuuint64_t es = f32 ? 4 : 2;
   cuuint64_t gdim[4] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(a->w_out),
                         static_cast<cuuint64_t>(a->h_out), static_cast<cuuint64_t>(a->src[0].n)};
   cuuint64_t gstr[3] = {static_cast<cuuint64_t>(ld) * es, static_cast<cuuint64_t>(ld) * es * gdim[1],
                         static_cast<cuuint64_t>(ld) * es * gdim[1] * gdim[2]};
-  cuuint32_t box[4] = {32, static_cast<cuuint32_t>(sub[0]), static_cast<cuuint32_t>(sub[1]),
+  // box rows are 128 B (32 fp32, or 64 bf16 in the wide epilogue) or 64 B (32 bf16)
+  cuuint32_t box[4] = {wide_bf16 ? 64u : 32u, static_cast<cuuint32_t>(sub[0]), static_cast<cuuint32_t>(sub[1]),
                        static_cast<cuuint32_t>(sub[2])};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = encode(tm, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
                       const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                      f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                      (f32 || wide_bf16) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(EALDM_ECUDA, "cuTensorMapEncodeTiled(epilogue) failed: %d", (int)r);
   return 0;
@@ -797,6 +906,7 @@ static int encode_unit_map(PFN_cuTensorMapEncodeTiled_v12000 encode, CUtensorMap
 
 int launch(const ealdm_conv_args* a, cudaStream_t st) {
   EALDM_REQUIRE(supported(a), "tcgen05 conv: unsupported shape/alignment (c%%64, 16-byte rows and pointers)");
+  init_options();
   PFN_cuTensorMapEncodeTiled_v12000 encode = get_encode();
   if (!encode) return set_error(EALDM_ECUDA, "cuTensorMapEncodeTiled entry point not available");
 
@@ -832,6 +942,7 @@ int launch(const ealdm_conv_args* a, cudaStream_t st) {
     const long long c256 = ceil_div(t256, num_sms()) * (256 + 48);
     const long long c128 = ceil_div(t128, num_sms()) * (128 + 48);
     BN = (c256 <= c128) ? 256 : 128;
+    if (g_opt[EALDM_TC_OPT_BN] == 128 || g_opt[EALDM_TC_OPT_BN] == 256) BN = g_opt[EALDM_TC_OPT_BN];
   }
   p.n_tiles = static_cast<int>(ceil_div(a->n_out, BN));
   // CTA pairs (256 x 256 tiles, a third less operand traffic per SM) for every problem with an even number of M tiles
@@ -897,7 +1008,13 @@ int launch(const ealdm_conv_args* a, cudaStream_t st) {
       return set_error(EALDM_ECUDA, "cuTensorMapEncodeTiled(W) failed: %d", (int)r);
   }
   const long long out_cols = geglu ? a->n_out / 2 : a->n_out;
-  if (int e = encode_unit_map(encode, &tm[3], a->out, a->out_f32 != 0, out_cols, a->ld_out, a, sub)) return e;
+  // (measured: the GEGLU pass gains 3 % at K = 256 and loses 4 % at K >= 512, where the stores of the narrow units
+  // overlap the longer main loop better)
+  const bool wide = g_opt[EALDM_TC_OPT_WIDE] != 0 && BN == 256 &&
+                    (geglu ? a->k_total <= 256 : (!a->residual && !a->out2));
+  if (int e = encode_unit_map(encode, &tm[3], a->out, a->out_f32 != 0, out_cols, a->ld_out, a, sub,
+                              wide && !a->out_f32))
+    return e;
   tm[4] = tm[3];
   tm[5] = tm[3];
   if (a->out2)
@@ -917,20 +1034,8 @@ int launch(const ealdm_conv_args* a, cudaStream_t st) {
   p.gn_ld = static_cast<int>(a->gn_ld);
   p.gn_chunks = static_cast<int>(a->h_out * a->w_out / 32);
   p.b_mn = a->weight_adjoint ? 1 : 0;
-  {
-    static int pf = -1, rw = -1;
-    if (pf < 0) {
-      const char* e = getenv("EALDM_TC_PREFETCH_TILES");
-      pf = e ? atoi(e) : 0;
-      const char* w = getenv("EALDM_TC_RELAXED_WAIT");
-      rw = w ? atoi(w) : 1;
-    }
-    p.pf_tiles = pf;
-    p.relaxed_wait = rw;
-    static int dg = -1;
-    if (dg < 0) { const char* d = getenv("EALDM_TC_DIAG"); dg = d ? atoi(d) : 0; }
-    p.diag = dg;
-  }
+  p.wide = wide ? 1 : 0;
+  p.relaxed_wait = g_opt[EALDM_TC_OPT_RELAXED_WAIT];
 
   switch (BN) {
     case 32: return launch_bn<32, false>(tm, p, st);

@@ -95,15 +95,6 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* m, uin
       : "memory");
 }
 
-// L2 prefetch of a TMA box (no shared-memory destination, no barrier): turns the later tma_load of the same box into
-// an L2 hit.  Used one tile ahead by the short-K GEMMs, whose 3-stage ring cannot cover the HBM latency.
-__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* m, int c0, int c1, int c2, int c3) {
-  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
-               :
-               : "l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-               : "memory");
-}
-
 // TMA store: shared (already fenced into the async proxy) -> global; out-of-range elements are dropped
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* src, int c0, int c1,
                                              int c2, int c3) {

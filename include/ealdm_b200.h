@@ -51,6 +51,21 @@ const char* ealdm_last_error(void);
 int ealdm_device_check(void);
 /* number of kernel launches issued through this library by the calling process so far */
 int64_t ealdm_launch_count(void);
+/*
+ * Schedule switches of the tcgen05 conv / linear kernel (results are identical in every setting; they exist for
+ * A/B measurements and for the parity tests that pin one schedule against the other).  The defaults come from the
+ * environment variables named below, read once.  Returns the previous value, or EALDM_EINVAL for an unknown option.
+ */
+enum {
+  EALDM_TC_OPT_CTA2 = 0,         /* EALDM_TC_CTA2: 0 one CTA per tile, 1 (default) CTA pairs (cta_group::2) where
+                                    the reduction is long enough (K >= 1024), 2 pairs for every even tile count */
+  EALDM_TC_OPT_WIDE = 1,         /* EALDM_TC_WIDE: 1 (default) 128-byte-row epilogue passes when there is no
+                                    residual / shadow output, 0 one 32-column unit per TMA store */
+  EALDM_TC_OPT_RELAXED_WAIT = 2, /* EALDM_TC_RELAXED_WAIT: 1 (default) one TMA store group may stay in flight */
+  EALDM_TC_OPT_BN = 3            /* EALDM_TC_BN: 0 (default) N tile chosen by wave count, 128 / 256 forced (for
+                                    n_out > 128), so that small test problems reach the 256-wide paths */
+};
+int ealdm_tc_set_option(int option, int value);
 
 /* ---- convolution / linear as implicit GEMM ------------------------------------------------- */
 /*

@@ -411,3 +411,131 @@ def test_conv_epilogue_groupnorm_partials(n, c, h, w, co, silu):
         ref = F.silu(ref) if silu else ref
         assert rel_l2(from_act(y), ref) < 6e-3
         assert rel_l2(stats[..., 0], xr.reshape(n, 32, -1).mean(-1)) < 1e-4
+
+
+# ---- schedules of the tcgen05 conv (ealdm_tc_set_option): every setting must give the same numbers ----------------
+class _tc_option:
+    """Sets one schedule switch and forces the 256-column N tile (small problems would pick 128 by wave count and
+    never reach the CTA-pair / wide-epilogue code)."""
+
+    def __init__(self, opt, val, bn=256):
+        self.opt, self.val, self.bn = opt, val, bn
+
+    def __enter__(self):
+        lib = L.load()
+        self.prev = lib.ealdm_tc_set_option(self.opt, self.val)
+        self.prev_bn = lib.ealdm_tc_set_option(L.TC_OPT_BN, self.bn)
+        assert self.prev >= 0 and self.prev_bn >= 0
+
+    def __exit__(self, *a):
+        lib = L.load()
+        lib.ealdm_tc_set_option(self.opt, self.prev)
+        lib.ealdm_tc_set_option(L.TC_OPT_BN, self.prev_bn)
+
+
+@pytest.mark.parametrize("n,c,h,w,co,res", [(4, 256, 16, 16, 256, False),    # 8 M tiles, K = 2304
+                                            (6, 128, 16, 16, 512, True),     # 12 M tiles, 2 N tiles, fp32 residual
+                                            (3, 128, 16, 16, 320, False),    # 6 M tiles, ragged N (320 = 256 + 64)
+                                            (5, 64, 8, 8, 256, False)])      # 3 M tiles: odd -> pairs must decline
+def test_conv_cta_pairs_match_single_cta(n, c, h, w, co, res):
+    """cta_group::2 (256 x 256 tiles over a 2-CTA cluster, B split between the CTAs) against one CTA per tile:
+    same k-block order, same fp32 accumulation -> bit-identical outputs; both against F.conv2d."""
+    dtype = torch.bfloat16
+    x = torch.randn(n, c, h, w, generator=g(70)).to(DEV)
+    wt = (torch.randn(co, c, 3, 3, generator=g(71)) / math.sqrt(9 * c)).to(DEV)
+    b = torch.randn(co, generator=g(72)).to(DEV)
+    r = torch.randn(n, co, h, w, generator=g(73)).to(DEV)
+    xa = to_act(x, dtype)
+    ra = to_act(r, torch.float32) if res else None
+    outs = []
+    for mode in (0, 2):
+        out = Act.empty(n, h, w, co, torch.float32, DEV)
+        with _tc_option(L.TC_OPT_CTA2, mode):
+            ops.conv([ConvIn(xa, 3, 1, 1)], pack_w(wt, dtype), out, bias=b, residual=ra, impl=L.IMPL_TCGEN05)
+        torch.cuda.synchronize()
+        outs.append(from_act(out))
+    ref = F.conv2d(from_act(xa), wt.to(dtype).float(), b, padding=1) + (r if res else 0)
+    assert rel_l2(outs[0], ref) < 2e-5 and rel_l2(outs[1], ref) < 2e-5   # fp32 out of bf16 operands: only sum order
+    assert torch.equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize("M,K,N", [(4096, 1024, 512), (2048, 2048, 1024)])
+def test_geglu_cta_pairs_match_single_cta(M, K, N):
+    from ealdm_b200.packing import geglu_interleave
+    dtype = torch.bfloat16
+    x = torch.randn(M, K, generator=g(74)).to(DEV)
+    w = (torch.randn(2 * N, K, generator=g(75)) / math.sqrt(K)).to(DEV)
+    b = torch.randn(2 * N, generator=g(76)).to(DEV)
+    xa = Act(x.to(dtype).contiguous(), 1, 1, M)
+    wp, bp = geglu_interleave(w.to(dtype), b)
+    outs = []
+    for mode in (0, 2):
+        out = Act.empty(1, 1, M, N, dtype, DEV)
+        with _tc_option(L.TC_OPT_CTA2, mode):
+            ops.linear(xa, wp, out, bias=bp, act=L.ACT_GEGLU, impl=L.IMPL_TCGEN05)
+        torch.cuda.synchronize()
+        outs.append(out.buf.float())
+    y = F.linear(xa.buf.float(), w.to(dtype).float(), b)
+    val, gate = y.chunk(2, dim=-1)
+    assert rel_l2(outs[0], val * F.gelu(gate)) < 6e-3
+    assert torch.equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize("out_dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("M,K,N", [(2048, 256, 768), (1024, 256, 256), (640, 512, 320)])
+def test_linear_wide_epilogue_matches_narrow(out_dtype, M, K, N):
+    """128-byte-row epilogue passes (one fence / TMA store sequence per 64 or 128 columns) against the
+    32-column units: identical arithmetic per element -> bit-identical outputs, ragged M and N included."""
+    x = torch.randn(M, K, generator=g(77)).to(DEV).to(torch.bfloat16).contiguous()
+    w = (torch.randn(N, K, generator=g(78)) / math.sqrt(K)).to(DEV).to(torch.bfloat16).contiguous()
+    b = torch.randn(N, generator=g(79)).to(DEV)
+    xa = Act(x, 1, 1, M)
+    outs = []
+    for mode in (0, 1):
+        out = Act.empty(1, 1, M, N, out_dtype, DEV)
+        with _tc_option(L.TC_OPT_WIDE, mode):
+            ops.linear(xa, w, out, bias=b, impl=L.IMPL_TCGEN05)
+        torch.cuda.synchronize()
+        outs.append(out.buf.float())
+    ref = F.linear(x.float(), w.float(), b)
+    assert rel_l2(outs[0], ref) < (2e-5 if out_dtype == torch.float32 else 6e-3)
+    assert torch.equal(outs[0], outs[1])
+
+
+def test_geglu_wide_epilogue_matches_narrow():
+    from ealdm_b200.packing import geglu_interleave
+    M, C = 1024, 256
+    x = torch.randn(M, C, generator=g(80)).to(DEV)
+    w = (torch.randn(8 * C, C, generator=g(81)) / math.sqrt(C)).to(DEV)
+    b = torch.randn(8 * C, generator=g(82)).to(DEV)
+    xa = Act(x.to(torch.bfloat16).contiguous(), 1, 1, M)
+    wp, bp = geglu_interleave(w.to(torch.bfloat16), b)
+    outs = []
+    for mode in (0, 1):
+        out = Act.empty(1, 1, M, 4 * C, torch.bfloat16, DEV)
+        with _tc_option(L.TC_OPT_WIDE, mode):
+            ops.linear(xa, wp, out, bias=bp, act=L.ACT_GEGLU, impl=L.IMPL_TCGEN05)
+        torch.cuda.synchronize()
+        outs.append(out.buf.float())
+    assert torch.equal(outs[0], outs[1])
+
+
+def test_conv_cta_pairs_natural_tile_choice():
+    """A problem large enough that the wave-count rule itself picks 256-column tiles and CTA pairs (no forcing):
+    160 M tiles x 2 N tiles, K = 1152, checked against F.conv2d and against the single-CTA schedule."""
+    dtype = torch.bfloat16
+    n, c, h, w, co = 20, 128, 32, 32, 512
+    x = torch.randn(n, c, h, w, generator=g(83)).to(DEV)
+    wt = (torch.randn(co, c, 3, 3, generator=g(84)) / math.sqrt(9 * c)).to(DEV)
+    b = torch.randn(co, generator=g(85)).to(DEV)
+    xa = to_act(x, dtype)
+    outs = []
+    for mode in (0, 1):
+        out = Act.empty(n, h, w, co, torch.float32, DEV)
+        with _tc_option(L.TC_OPT_CTA2, mode, bn=0):
+            ops.conv([ConvIn(xa, 3, 1, 1)], pack_w(wt, dtype), out, bias=b, impl=L.IMPL_TCGEN05)
+        torch.cuda.synchronize()
+        outs.append(from_act(out))
+    ref = F.conv2d(from_act(xa), wt.to(dtype).float(), b, padding=1)
+    assert rel_l2(outs[1], ref) < 2e-5
+    assert torch.equal(outs[0], outs[1])

@@ -62,6 +62,30 @@ def test_unet_forward_vs_reference_golden(kind, mode):
     assert err < TOL[mode]
 
 
+@pytest.mark.parametrize("kind", ["uncond", "stdiff"])
+def test_unet_forward_bench_schedules_vs_reference_golden(kind):
+    """The schedules the BENCHMARK batch selects (256-column N tiles, CTA pairs, wide epilogue passes) forced onto the
+    golden batch of 2, where the wave-count rule alone would pick 128-column tiles: same tolerance, and bit-identical to
+    the default schedule (every schedule accumulates the same k-blocks in the same order)."""
+    from ealdm_b200 import _lib as L
+    G = gold(f"unet_{kind}_fwd.pt")
+    unet = make_ld(kind).model.diffusion_model.set_compute_dtype("bf16")
+    ctx = None if G["context"] is None else G["context"].cuda()
+    base = unet(G["x"].cuda(), G["t"].cuda(), context=ctx)
+    lib = L.load()
+    prev = [lib.ealdm_tc_set_option(o, v) for o, v in ((L.TC_OPT_BN, 256), (L.TC_OPT_CTA2, 2))]
+    try:
+        eps = unet(G["x"].cuda(), G["t"].cuda(), context=ctx)
+        torch.cuda.synchronize()
+    finally:
+        lib.ealdm_tc_set_option(L.TC_OPT_BN, prev[0])
+        lib.ealdm_tc_set_option(L.TC_OPT_CTA2, prev[1])
+    err = rel_l2(eps, G["eps"])
+    print(f"unet {kind} bf16, forced BN=256 + CTA pairs: rel_l2 = {err:.3e}")
+    assert err < TOL["bf16"]
+    assert torch.equal(eps, base)
+
+
 def test_unet_is_deterministic_and_batch_independent():
     G = gold("unet_stdiff_fwd.pt")
     unet = make_ld("stdiff").model.diffusion_model.set_compute_dtype("bf16")
