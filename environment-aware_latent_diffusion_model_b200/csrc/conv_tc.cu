@@ -368,8 +368,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
               const uint32_t fb = full0 + static_cast<uint32_t>(stage) * 8u;
               ptx::tma_load_4d_2sm(sa, tmA, fb, cb * BK, w0 * sg.stride + kw - sg.pad, h0 * sg.stride + kh - sg.pad,
                                    n0);
-              ptx::tma_load_2d_2sm(sa + C::A_BYTES, &tmB, fb, sg.bkoff + kb * BK,
-                                   nt * BN + static_cast<int>(cta_rank) * (BN / 2));
+              if (p.b_mn) {
+                // adjoint: this CTA's half of the N columns as BN/128 MN-major atoms of [64 K rows x 64 columns]
+                const int tcol = (sg.ksize * sg.ksize - 1 - tap) * p.N + nt * BN + static_cast<int>(cta_rank) * (BN / 2);
+#pragma unroll
+                for (int g = 0; g < BN / 128; ++g)
+                  ptx::tma_load_2d_2sm(sa + C::A_BYTES + g * 8192, &tmB, fb, tcol + g * 64, cb * BK);
+              } else {
+                ptx::tma_load_2d_2sm(sa + C::A_BYTES, &tmB, fb, sg.bkoff + kb * BK,
+                                     nt * BN + static_cast<int>(cta_rank) * (BN / 2));
+              }
               if (++cb == sg.cblk) { cb = 0; ++tap; }
               if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
               continue;
@@ -411,10 +419,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           const uint32_t sa = ptx::smem_u32(smem + stage * C::STAGE_BYTES);
           const uint64_t adesc = ptx::make_sw128_kmajor_desc(sa);
           if constexpr (CTA2) {
-            const uint64_t bdesc = ptx::make_sw128_kmajor_desc(sa + C::A_BYTES);
+            const uint64_t bdesc = p.b_mn ? ptx::make_sw128_mnmajor_desc(sa + C::A_BYTES, 8192)
+                                          : ptx::make_sw128_kmajor_desc(sa + C::A_BYTES);
+            const uint64_t bstep = p.b_mn ? 128 : 2;  // 16 K rows of an MN-major atom = 2048 B, of a K-major one 32 B
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k)
-              ptx::umma_bf16_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              ptx::umma_bf16_2sm(d_tmem, adesc + 2 * k, bdesc + bstep * k, idesc, (kb | k) != 0 ? 1u : 0u);
             ptx::umma_commit_2sm(&empty_bar[stage], 3);  // frees this stage in both CTAs
             if (kb == kblocks_total - 1) ptx::umma_commit_2sm(&tmem_full[acc], 3);
           } else if (p.b_mn) {
@@ -948,7 +958,7 @@ int launch(const ealdm_conv_args* a, cudaStream_t st) {
   // CTA pairs (256 x 256 tiles, a third less operand traffic per SM) for every problem with an even number of M tiles
   // and a reduction long enough (K >= 1024) to amortise the pair's cross-CTA barrier latency (measured: K = 256 / 512
   // GEMMs lose 5-25 % as pairs, K >= 1024 GEMMs and all 3x3 convs gain 3-12 %); EALDM_TC_CTA2=2 pairs regardless of K
-  const bool pair = BN == 256 && !a->weight_adjoint && cta2_mode() != 0 && p.m_tiles >= 2 && p.m_tiles % 2 == 0 &&
+  const bool pair = BN == 256 && cta2_mode() != 0 && p.m_tiles >= 2 && p.m_tiles % 2 == 0 &&
                     (a->k_total >= 1024 || cta2_mode() == 2);
 
   CUtensorMap tm[6];  // A0, A1, W, out, out2, residual

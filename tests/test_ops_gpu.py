@@ -539,3 +539,25 @@ def test_conv_cta_pairs_natural_tile_choice():
     ref = F.conv2d(from_act(xa), wt.to(dtype).float(), b, padding=1)
     assert rel_l2(outs[1], ref) < 2e-5
     assert torch.equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize("n,c,h,w,co", [(4, 256, 16, 16, 256), (2, 128, 16, 16, 192), (6, 512, 8, 8, 320)])
+def test_dgrad_cta_pairs_match_single_cta(n, c, h, w, co):
+    """weight_adjoint mode (data gradient from the forward-packed matrix, MN-major B operand) as CTA pairs: each CTA
+    stages its half of the MN-major atoms; equals autograd's dX and the single-CTA schedule bit for bit."""
+    dtype = torch.bfloat16
+    x = torch.randn(n, c, h, w, generator=g(86)).to(DEV).to(dtype).float().requires_grad_(True)
+    wt = (torch.randn(co, c, 3, 3, generator=g(87)) / math.sqrt(9 * c)).to(DEV).to(dtype).float()
+    dy = torch.randn(n, co, h, w, generator=g(88)).to(DEV)
+    dya = to_act(dy, dtype)
+    F.conv2d(x, wt, padding=1).backward(from_act(dya))
+    packed = wt.permute(0, 2, 3, 1).reshape(co, -1).to(dtype).contiguous()
+    outs = []
+    for mode in (0, 2):
+        dx = Act.empty(n, h, w, c, torch.float32, DEV)
+        with _tc_option(L.TC_OPT_CTA2, mode):
+            ops.conv([ConvIn(dya, 3, 1, 1)], packed, dx, adjoint=True)
+        torch.cuda.synchronize()
+        outs.append(from_act(dx))
+    assert rel_l2(outs[1], x.grad) < 8e-3
+    assert torch.equal(outs[0], outs[1])

@@ -73,5 +73,38 @@ def launches(path):
         print(f"  {tot[k] / 1e3:9.3f} ms  {100 * tot[k] / total:5.1f} %  x{cnt[k]:<5d} {k}")
 
 
+def traffic(path):
+    """DRAM / L2 bytes per launch of the tcgen05 conv kernel from a `--metrics dram__bytes_read.sum,
+    dram__bytes_write.sum,gpu__time_duration.sum,lts__t_bytes.sum --csv` launch list -> JSON (bench.py reads
+    profiles/r01_conv_tc_traffic.json for roofline.traffic)."""
+    import json
+    with open(path) as f:
+        lines = [ln for ln in f if ln.startswith('"')]
+    rows = list(csv.reader(lines))
+    hdr = rows[0]
+    i_id, i_name, i_metric, i_val, i_unit = (hdr.index(k) for k in ("ID", "Kernel Name", "Metric Name", "Metric Value",
+                                                                   "Metric Unit"))
+    unit_scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}
+    tot = defaultdict(float)
+    ids, pairs = set(), set()
+    for r in rows[1:]:
+        if "conv_tc_kernel" not in r[i_name]:
+            continue
+        ids.add(r[i_id])
+        if r[i_name].split("(")[0].rstrip(">").endswith(", 1"):
+            pairs.add(r[i_id])
+        tot[r[i_metric]] += float(r[i_val].replace(",", "")) * unit_scale.get(r[i_unit], 1.0)
+    n = len(ids)
+    out = {"kernel": "ealdm::tc::conv_tc_kernel", "launches": n, "launches_as_cta_pairs": len(pairs),
+           "dram_read_bytes_total": tot["dram__bytes_read.sum"], "dram_write_bytes_total": tot["dram__bytes_write.sum"],
+           "dram_bytes_per_launch": (tot["dram__bytes_read.sum"] + tot["dram__bytes_write.sum"]) / max(n, 1),
+           "l2_bytes_per_launch": tot["lts__t_bytes.sum"] / max(n, 1),
+           "duration_ms_total_under_ncu": tot["gpu__time_duration.sum"],
+           "command": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,lts__t_bytes.sum "
+                      "--clock-control none --profile-from-start off -k regex:conv_tc_kernel --csv python "
+                      "tools/profile_forward.py  (one eager UNet forward, stdiff config, UNet batch 128)"}
+    print(json.dumps(out, indent=1))
+
+
 if __name__ == "__main__":
-    {"report": report, "launches": launches}[sys.argv[1]](sys.argv[2])
+    {"report": report, "launches": launches, "traffic": traffic}[sys.argv[1]](sys.argv[2])
