@@ -337,6 +337,7 @@ class AutoencoderEngine:
         self.dev = next(m.parameters()).device
         assert self.dev.type == "cuda"
         f32 = lambda t: t.detach().float().contiguous()  # noqa: E731
+        self._cin_pad = 64 if dtype == torch.bfloat16 else 4
 
         def pc(conv, pad_cin_to=None):
             w = conv.weight.detach()
@@ -361,7 +362,8 @@ class AutoencoderEngine:
                     "q": pc(ab.q), "k": pc(ab.k), "v": pc(ab.v), "proj": pc(ab.proj_out)}
 
         def coder(net, is_enc):
-            d = {"conv_in": pc(net.conv_in, pad_cin_to=4), "mid1": res(net.mid.block_1), "attn": attn(net.mid.attn_1),
+            # bf16: input channels zero-padded to one 64-channel K block, so that conv_in runs on the tcgen05 kernel
+            d = {"conv_in": pc(net.conv_in, pad_cin_to=self._cin_pad), "mid1": res(net.mid.block_1), "attn": attn(net.mid.attn_1),
                  "mid2": res(net.mid.block_2), "norm_out": (f32(net.norm_out.weight), f32(net.norm_out.bias)),
                  "conv_out": pc(net.conv_out), "levels": []}
             for lvl in (net.down if is_enc else net.up):
@@ -451,12 +453,13 @@ class AutoencoderEngine:
                      out2=self._out2(out))
         return out
 
-    def _input(self, x: torch.Tensor) -> Act:
+    def _input(self, x: torch.Tensor, cp: Optional[int] = None) -> Act:
         n, c, h, w = x.shape
-        buf = torch.zeros((n * h * w, 4), dtype=self.dt, device=self.dev)  # channels padded to 4 (zero weights)
+        cp = cp or self._cin_pad
+        buf = torch.zeros((n * h * w, cp), dtype=self.dt, device=self.dev)  # channels zero-padded (zero weights)
         a = Act(buf, n, h, w, c, 0)
         ops.nchw_to_nhwc(x.float().contiguous(), a)
-        return Act(buf, n, h, w, 4, 0)
+        return Act(buf, n, h, w, cp, 0)
 
     def _output(self, h: Act, wb, cout) -> Act:
         co_pad = (cout + 7) // 8 * 8
@@ -498,11 +501,12 @@ class AutoencoderEngine:
         n = z.shape[0]
         up = 2 ** (self.m.decoder.num_resolutions - 1)
         self.stats = ops.group_norm_workspace(n, z.shape[2] * up * z.shape[3] * up, 4 * self.m.decoder.ch, self.dev)
-        zin = self._input(z)
+        zin = self._input(z, 4)
         zc = self.post_quant[0].shape[0]
-        zq = Act(torch.zeros((zin.rows, 4), dtype=self.dt, device=self.dev), zin.n, zin.h, zin.w, zc, 0)
+        cp = self._cin_pad
+        zq = Act(torch.zeros((zin.rows, cp), dtype=self.dt, device=self.dev), zin.n, zin.h, zin.w, zc, 0)
         ops.linear(zin, self.post_quant[0], zq, bias=self.post_quant[1])
-        h = self._conv3(Act(zq.buf, zq.n, zq.h, zq.w, 4, 0), D["conv_in"], D["conv_in"][0].shape[0])
+        h = self._conv3(Act(zq.buf, zq.n, zq.h, zq.w, cp, 0), D["conv_in"], D["conv_in"][0].shape[0])
         h = self._res(D["mid1"], h)
         h = self._attn(D["attn"], h)
         h = self._res(D["mid2"], h)

@@ -85,7 +85,7 @@ struct Cfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = (CTA2 ? BN / 2 : BN) * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = CTA2 ? 4 : ((BN >= 256) ? 3 : (BN >= 128 ? 4 : 6));
+  static constexpr int STAGES = CTA2 ? (BN >= 256 ? 4 : 6) : ((BN >= 256) ? 3 : (BN >= 128 ? 4 : 6));
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
   static constexpr int EPI_OFF = STAGES * STAGE_BYTES;                 // 1024-aligned
   static constexpr int BIAS_OFF = EPI_OFF + EPI_WARPS * EPI_WARP_BYTES;
@@ -958,8 +958,8 @@ int launch(const ealdm_conv_args* a, cudaStream_t st) {
   // CTA pairs (256 x 256 tiles, a third less operand traffic per SM) for every problem with an even number of M tiles
   // and a reduction long enough (K >= 1024) to amortise the pair's cross-CTA barrier latency (measured: K = 256 / 512
   // GEMMs lose 5-25 % as pairs, K >= 1024 GEMMs and all 3x3 convs gain 3-12 %); EALDM_TC_CTA2=2 pairs regardless of K
-  const bool pair = BN == 256 && cta2_mode() != 0 && p.m_tiles >= 2 && p.m_tiles % 2 == 0 &&
-                    (a->k_total >= 1024 || cta2_mode() == 2);
+  const bool pair = (BN == 256 || (BN == 128 && !geglu && cta2_mode() >= 2)) && cta2_mode() != 0 && p.m_tiles >= 2 && p.m_tiles % 2 == 0 &&
+                    (a->k_total >= 1024 || cta2_mode() == 2);  // 3: the K rule, 128-column tiles included
 
   CUtensorMap tm[6];  // A0, A1, W, out, out2, residual
   memset(tm, 0, sizeof(tm));
@@ -1050,6 +1050,7 @@ int launch(const ealdm_conv_args* a, cudaStream_t st) {
   switch (BN) {
     case 32: return launch_bn<32, false>(tm, p, st);
     case 128:
+      if (pair) return launch_pair<128, false>(tm, p, st);
       return geglu ? launch_bn<128, true>(tm, p, st) : launch_bn<128, false>(tm, p, st);
     default:
       if (pair) return geglu ? launch_pair<256, true>(tm, p, st) : launch_pair<256, false>(tm, p, st);

@@ -437,7 +437,8 @@ class _tc_option:
                                             (6, 128, 16, 16, 512, True),     # 12 M tiles, 2 N tiles, fp32 residual
                                             (3, 128, 16, 16, 320, False),    # 6 M tiles, ragged N (320 = 256 + 64)
                                             (5, 64, 8, 8, 256, False)])      # 3 M tiles: odd -> pairs must decline
-def test_conv_cta_pairs_match_single_cta(n, c, h, w, co, res):
+@pytest.mark.parametrize("bn", [256, 128])
+def test_conv_cta_pairs_match_single_cta(n, c, h, w, co, res, bn):
     """cta_group::2 (256 x 256 tiles over a 2-CTA cluster, B split between the CTAs) against one CTA per tile:
     same k-block order, same fp32 accumulation -> bit-identical outputs; both against F.conv2d."""
     dtype = torch.bfloat16
@@ -450,7 +451,7 @@ def test_conv_cta_pairs_match_single_cta(n, c, h, w, co, res):
     outs = []
     for mode in (0, 2):
         out = Act.empty(n, h, w, co, torch.float32, DEV)
-        with _tc_option(L.TC_OPT_CTA2, mode):
+        with _tc_option(L.TC_OPT_CTA2, mode, bn=bn):
             ops.conv([ConvIn(xa, 3, 1, 1)], pack_w(wt, dtype), out, bias=b, residual=ra, impl=L.IMPL_TCGEN05)
         torch.cuda.synchronize()
         outs.append(from_act(out))
