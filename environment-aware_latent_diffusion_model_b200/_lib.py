@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libealdm_b200.so")
 CSRC_DIR = os.path.join(_HERE, "csrc")
 
 F32, BF16 = 0, 1
-ACT_NONE, ACT_SILU, ACT_GEGLU = 0, 1, 2
+ACT_NONE, ACT_SILU, ACT_GEGLU, ACT_RELU = 0, 1, 2, 3
 IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05 = 0, 1, 2
 TC_OPT_CTA2, TC_OPT_WIDE, TC_OPT_RELAXED_WAIT, TC_OPT_BN = 0, 1, 2, 3
 
@@ -30,6 +30,8 @@ EXPORTS = [
     "ealdm_attention_bwd", "ealdm_attention_bwd_workspace_bytes", "ealdm_geglu", "ealdm_geglu_bwd",
     "ealdm_silu", "ealdm_silu_bwd", "ealdm_colsum", "ealdm_colsum_workspace_bytes", "ealdm_zero_insert2x",
     "ealdm_sumpool2x2", "ealdm_cfg_mse_bwd", "ealdm_gn_partial", "ealdm_adamw_ema_step", "ealdm_plms_eps", "ealdm_vq_nearest", "ealdm_ddpm_step",
+    # conditioner
+    "ealdm_fourier_style", "ealdm_lstm_cell", "ealdm_adain", "ealdm_batch_norm_relu",
 ]
 WGRAD_PACKED, WGRAD_OIHW = 0, 1
 
@@ -203,6 +205,10 @@ def _declare(lib):
         ("ealdm_plms_eps", [vp, vp, f32, vp, vp, vp, i32, vp, vp, i64, vp]),
         ("ealdm_vq_nearest", [vp, i64, i64, i64, vp, i64, vp, vp, vp]),
         ("ealdm_ddpm_step", [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, f32, i64, i64, vp, vp, vp]),
+        ("ealdm_fourier_style", [vp, i64, vp, i32, i32, f32, vp, i64, f32, vp, vp, vp]),
+        ("ealdm_lstm_cell", [vp, i64, i64, i64, vp, vp, vp, vp, vp, i64, vp, i64, vp, vp]),
+        ("ealdm_adain", [vp, i64, i64, i64, i64, vp, i64, f32, vp, i64, vp]),
+        ("ealdm_batch_norm_relu", [vp, i64, i64, i64, vp, vp, vp, vp, i32, f32, i32, vp, i64, vp, vp]),
     ]:
         fn = getattr(lib, name)
         fn.restype = C.c_int

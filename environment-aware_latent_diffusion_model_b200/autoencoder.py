@@ -470,6 +470,17 @@ class AutoencoderEngine:
     @torch.no_grad()
     def encode_moments(self, x: torch.Tensor) -> torch.Tensor:
         """Encoder.forward (model.py:434-459) + quant_conv (autoencoder.py:324-327) -> moments [N, 2*embed, h, w]."""
+        hz = self.encoder_features(x)
+        mo = self.quant[0].shape[0]
+        mbuf = Act.empty(hz.n, hz.h, hz.w, (mo + 7) // 8 * 8, torch.float32, self.dev)
+        ops.linear(hz, self.quant[0], mbuf.cols(0, mo), bias=self.quant[1])
+        y = torch.empty((hz.n, mo, hz.h, hz.w), dtype=torch.float32, device=self.dev)
+        return ops.nhwc_to_nchw(mbuf.cols(0, mo), y)
+
+    @torch.no_grad()
+    def encoder_features(self, x: torch.Tensor) -> Act:
+        """Encoder.forward alone (model.py:434-459), NHWC in the compute dtype: what quant_conv reads, and what the EALDM
+        conditioner takes from its `convs.encoder` (STDiff/models.py:515)."""
         E = self.enc
         n = x.shape[0]
         self.stats = ops.group_norm_workspace(n, x.shape[2] * x.shape[3], 4 * self.m.encoder.ch, self.dev)
@@ -488,11 +499,7 @@ class AutoencoderEngine:
         zc = E["conv_out"][0].shape[0]
         hz = self._new(hn.n, hn.h, hn.w, zc)
         ops.conv([ConvIn(hn, 3, 1, 1)], E["conv_out"][0], hz, bias=E["conv_out"][1])
-        mo = self.quant[0].shape[0]
-        mbuf = Act.empty(hn.n, hn.h, hn.w, (mo + 7) // 8 * 8, torch.float32, self.dev)
-        ops.linear(hz, self.quant[0], mbuf.cols(0, mo), bias=self.quant[1])
-        y = torch.empty((hn.n, mo, hn.h, hn.w), dtype=torch.float32, device=self.dev)
-        return ops.nhwc_to_nchw(mbuf.cols(0, mo), y)
+        return hz
 
     @torch.no_grad()
     def decode(self, z: torch.Tensor) -> torch.Tensor:

@@ -55,7 +55,7 @@ extern "C" int ealdm_conv(const ealdm_conv_args* a, ealdm_stream_t stream) {
   EALDM_REQUIRE(a->n_src == 1 || a->n_src == 2, "conv: n_src must be 1 or 2");
   EALDM_REQUIRE(a->weight && a->out, "conv: null weight/out");
   EALDM_REQUIRE(a->n_out > 0 && a->k_total > 0 && a->h_out > 0 && a->w_out > 0, "conv: bad sizes");
-  EALDM_REQUIRE(a->act >= EALDM_ACT_NONE && a->act <= EALDM_ACT_GEGLU, "conv: bad act %d", a->act);
+  EALDM_REQUIRE(a->act >= EALDM_ACT_NONE && a->act <= EALDM_ACT_RELU, "conv: bad act %d", a->act);
   EALDM_REQUIRE(!(a->act == EALDM_ACT_GEGLU && (a->rowvec || a->out2)),
                 "conv: GEGLU with rowvec / out2 unsupported");
   for (int s = 0; s < a->n_src; ++s) {

@@ -192,6 +192,7 @@ __global__ void __launch_bounds__(NT) conv_simt_kernel(const Params p) {
       if (ep.bias) v += ep.bias[col];
       if (ep.rowvec) v += ep.rowvec[img * ep.ld_rowvec + col];
       if (ep.act == EALDM_ACT_SILU) v = silu_f(v);
+      else if (ep.act == EALDM_ACT_RELU) v = fmaxf(v, 0.f);
       if (ep.residual)
         v += ep.res_f32 ? reinterpret_cast<const float*>(ep.residual)[m * ep.ld_res + col]
                         : to_f32(reinterpret_cast<const T*>(ep.residual)[m * ep.ld_res + col]);

@@ -596,7 +596,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                     for (int j = 0; j < 32; ++j) {
                       float f = __uint_as_float(vc[j]) + bs[ku * 32 + j];
                       if (rv != nullptr && nt * BN + ku * 32 + j < p.N) f += __ldg(rv + ku * 32 + j);
-                      r[j] = silu_f(f);
+                      r[j] = p.act == EALDM_ACT_RELU ? fmaxf(f, 0.f) : silu_f(f);
                     }
                   }
                   if (p.gn_partial != nullptr)
@@ -706,7 +706,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             for (int j = 0; j < 32; ++j) {
               float f = __uint_as_float(v[j]) + bs[ku * 32 + j];
               if (rv != nullptr && nt * BN + ku * 32 + j < p.N) f += __ldg(rv + ku * 32 + j);
-              r[j] += silu_f(f);
+              r[j] += p.act == EALDM_ACT_RELU ? fmaxf(f, 0.f) : silu_f(f);
             }
           }
           if (p.gn_partial != nullptr) gn_partial_unit(p, r, lane, (n - sn0) + my_dn < p.Nimg, n, h, w, nt * BN + ku * 32);

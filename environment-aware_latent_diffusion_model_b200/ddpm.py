@@ -193,6 +193,9 @@ class LatentDiffusion(nn.Module):
                 self.cond_stage_model.eval()
                 for p in self.cond_stage_model.parameters():
                     p.requires_grad = False
+            if self.cond_stage_key == "mixed" and hasattr(self.cond_stage_model, "convs"):
+                # the EALDM conditioner encodes its frames with the first stage (ddpm.py:535-536)
+                self.cond_stage_model.convs = self.first_stage_model
 
     def init_from_ckpt(self, path, ignore_keys=()):
         sd = torch.load(path, map_location="cpu")

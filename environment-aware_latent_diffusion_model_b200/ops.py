@@ -608,3 +608,62 @@ def vq_nearest(z: torch.Tensor, codebook: torch.Tensor):
 
 def launch_count() -> int:
     return int(L.load().ealdm_launch_count())
+
+
+# ---- EALDM conditioner (csrc/cond.cu) ------------------------------------------------------------------------
+def fourier_style(time: torch.Tensor, freqs: torch.Tensor, include_lin: bool, lin_lr: float, weight: torch.Tensor,
+                  gain: float, out: torch.Tensor, features: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """ealdm_fourier_style: ConditioningTransform + CondScale of the time stamp -> out [T, n_out] (fp32)."""
+    lib = L.load()
+    for t in (time, freqs, weight, out):
+        assert t.dtype == torch.float32 and t.is_contiguous() and t.is_cuda
+    T, nf = time.numel(), freqs.numel()
+    assert weight.shape[1] == 2 * nf and tuple(out.shape) == (T, weight.shape[0])
+    if features is not None:
+        assert features.dtype == torch.float32 and features.is_contiguous() and tuple(features.shape) == (T, 2 * nf)
+    L.check(lib.ealdm_fourier_style(time.data_ptr(), T, freqs.data_ptr(), nf, int(include_lin), float(lin_lr),
+                                    weight.data_ptr(), weight.shape[0], float(gain), _ptr(features), out.data_ptr(),
+                                    _stream()))
+    return out
+
+
+def lstm_cell(x: torch.Tensor, w_ih: torch.Tensor, b_ih: torch.Tensor, b_hh: torch.Tensor, h_out: torch.Tensor,
+              c_out: torch.Tensor, rec: Optional[torch.Tensor] = None, c_prev: Optional[torch.Tensor] = None) -> None:
+    """ealdm_lstm_cell: one nn.LSTM step for x [B, in] (a strided view is fine); rec = W_hh h_prev [B, 4H] or None."""
+    lib = L.load()
+    B, n_in = x.shape
+    H = w_ih.shape[0] // 4
+    assert x.dtype == torch.float32 and x.stride(1) == 1 and w_ih.is_contiguous() and w_ih.shape[1] == n_in
+    assert h_out.stride(1) == 1 and tuple(h_out.shape) == (B, H) and c_out.is_contiguous() and tuple(c_out.shape) == (B, H)
+    if rec is not None:
+        assert rec.is_contiguous() and tuple(rec.shape) == (B, 4 * H)
+    if c_prev is not None:
+        assert c_prev.is_contiguous() and tuple(c_prev.shape) == (B, H)
+    L.check(lib.ealdm_lstm_cell(x.data_ptr(), x.stride(0), B, n_in, w_ih.data_ptr(), b_ih.data_ptr(), b_hh.data_ptr(),
+                                _ptr(rec), _ptr(c_prev), H, h_out.data_ptr(), h_out.stride(0), c_out.data_ptr(),
+                                _stream()))
+
+
+def adain(x: Act, style: torch.Tensor, out: Act, eps: float = 1e-5) -> Act:
+    """ealdm_adain: instance norm + x * (1 + gamma) + beta, style [n, 2c] = [gamma | beta]; fp32, c <= 32."""
+    lib = L.load()
+    assert x.dtype == torch.float32 and out.dtype == torch.float32 and x.c == out.c and x.rows == out.rows
+    assert style.dtype == torch.float32 and style.stride(1) == 1 and tuple(style.shape) == (x.n, 2 * x.c)
+    L.check(lib.ealdm_adain(x.ptr, x.ld, x.n, x.h * x.w, x.c, style.data_ptr(), style.stride(0), float(eps), out.ptr,
+                            out.ld, _stream()))
+    return out
+
+
+def batch_norm_relu(x: Act, gamma: torch.Tensor, beta: torch.Tensor, running_mean: torch.Tensor,
+                    running_var: torch.Tensor, out: Act, *, training: bool, eps: float = 1e-5, relu: bool = True,
+                    batch_stats: Optional[torch.Tensor] = None) -> Act:
+    """ealdm_batch_norm_relu over the rows of an NHWC map (c <= 32); training=True: statistics of the batch, written
+    to batch_stats [2, c] = {mean, biased variance} when given."""
+    lib = L.load()
+    assert x.dtype == torch.float32 and out.dtype == torch.float32 and x.c == out.c and x.rows == out.rows
+    if batch_stats is not None:
+        assert batch_stats.dtype == torch.float32 and batch_stats.is_contiguous() and batch_stats.numel() == 2 * x.c
+    L.check(lib.ealdm_batch_norm_relu(x.ptr, x.ld, x.rows, x.c, gamma.data_ptr(), beta.data_ptr(),
+                                      running_mean.data_ptr(), running_var.data_ptr(), int(training), float(eps),
+                                      int(relu), out.ptr, out.ld, _ptr(batch_stats), _stream()))
+    return out

@@ -35,7 +35,7 @@ extern "C" {
 typedef void* ealdm_stream_t; /* cudaStream_t */
 
 enum { EALDM_F32 = 0, EALDM_BF16 = 1 };
-enum { EALDM_ACT_NONE = 0, EALDM_ACT_SILU = 1, EALDM_ACT_GEGLU = 2 };
+enum { EALDM_ACT_NONE = 0, EALDM_ACT_SILU = 1, EALDM_ACT_GEGLU = 2, EALDM_ACT_RELU = 3 };
 enum { EALDM_IMPL_AUTO = 0, EALDM_IMPL_SIMT = 1, EALDM_IMPL_TCGEN05 = 2 };
 enum {
   EALDM_OK = 0,
@@ -238,6 +238,33 @@ int ealdm_copy2d(const void* x, int64_t ld_x, int32_t dtype_x, void* y, int64_t 
 /* row softmax in place over [rows, c] (pitch ld) after multiplying by `scale` (model.py:190-192) */
 int ealdm_softmax_rows(void* x, int64_t ld, int32_t dtype, int64_t rows, int64_t c, float scale,
                        ealdm_stream_t stream);
+
+/* ---- EALDM conditioner `UnetCond` (STDiff/models.py:411-539), fp32 ----------------------------------- */
+/*
+ * ConditioningTransform.forward + CondScale.forward (models.py:203-236, 298-309): features[t] = [cos, sin] pairs of
+ * 2 pi freqs[i] time[t] (include_lin: pair 0 = (1, lin_lr * time[t])), out[t, j] = sum_k features[t, k] * weight[j, k]
+ * * gain.  `features` ([t_count, 2 * n_freq]) may be NULL.
+ */
+int ealdm_fourier_style(const float* time, int64_t t_count, const float* freqs, int32_t n_freq, int32_t include_lin,
+                        float lin_lr, const float* weight, int64_t n_out, float gain, float* features, float* out,
+                        ealdm_stream_t stream);
+/*
+ * One torch.nn.LSTM step (WeatherLSTM, models.py:312-336) for `batch` sequences: gates = w_ih x + b_ih + rec + b_hh with
+ * gate order i, f, g, o; rec = w_hh h_prev [batch, 4 * hidden] (from ealdm_conv as a linear layer) or NULL at step 0,
+ * c_prev NULL = zero state.  n_in <= 64.
+ */
+int ealdm_lstm_cell(const float* x, int64_t ld_x, int64_t batch, int64_t n_in, const float* w_ih, const float* b_ih,
+                    const float* b_hh, const float* rec, const float* c_prev, int64_t hidden, float* h_out,
+                    int64_t ld_h, float* c_out, ealdm_stream_t stream);
+/* AdaIN.forward (models.py:362-377) on an NHWC map [n, hw, c]: InstanceNorm2d (biased variance, eps) then
+ * x * (1 + gamma) + beta, style[n] = [gamma(c) | beta(c)]; c <= 32. */
+int ealdm_adain(const float* x, int64_t ld_x, int64_t n, int64_t hw, int64_t c, const float* style, int64_t ld_style,
+                float eps, float* y, int64_t ld_y, ealdm_stream_t stream);
+/* nn.BatchNorm2d (+ ReLU) of conv_cat (models.py:480-483) over [rows, c], c <= 32: training != 0 normalises with the
+ * statistics of the batch and writes {mean(c), biased var(c)} to batch_stats (may be NULL), else the running buffers. */
+int ealdm_batch_norm_relu(const float* x, int64_t ld_x, int64_t rows, int64_t c, const float* gamma, const float* beta,
+                          const float* running_mean, const float* running_var, int32_t training, float eps,
+                          int32_t relu, float* y, int64_t ld_y, float* batch_stats, ealdm_stream_t stream);
 
 /* ---- sampler / diffusion elementwise (fp32, bit-exact with the reference's op sequence) -------- */
 /*

@@ -83,6 +83,22 @@ def test_instantiate_from_config_yaml_targets():
     assert hasattr(ae, "encode") and hasattr(ae, "decode")
 
 
+def test_shipped_stdiff_config_wires_conditioner_to_first_stage():
+    """configs/latent-diffusion/stdiff_cin-ldm-vq-f8_b200.yaml = the reference's shipped config with all four targets
+    switched: VQ first stage, UnetCond conditioner whose `convs` IS the first stage (ddpm.py:535-536), same values."""
+    from oracle import conditioner as OC
+    cfg = yaml.safe_load(open(os.path.join(ROOT, "configs/latent-diffusion/stdiff_cin-ldm-vq-f8_b200.yaml")))["model"]
+    model = instantiate_from_config(cfg)
+    assert type(model.first_stage_model).__name__ == "VQModelInterface"
+    cond = model.cond_stage_model
+    assert type(cond).__name__ == "UnetCond" and cond.convs is model.first_stage_model
+    own = [(k, tuple(v.shape)) for k, v in cond.state_dict().items() if not k.startswith("convs.")]
+    assert own == OC.param_shapes()
+    assert dict(cond.cond_args)["f_manual"] == OC.COND_ARGS["f_manual"] and cond.cond_args.lin_lr == 0.01
+    with pytest.raises(RuntimeError):          # no CPU fallback
+        cond((torch.zeros(2, 3, 8, 8), torch.zeros(2, 1, 1), torch.zeros(2, 1, 16), torch.zeros(2, 1)))
+
+
 @pytest.mark.parametrize("cfg", [CFG.UNET_STDIFF, CFG.UNET_UNCOND])
 def test_unet_state_dict_matches_reference_inventory(cfg):
     from ealdm_b200.unet import UNetModel

@@ -209,3 +209,24 @@ def test_vq_first_stage_decode_and_quantizer():
         enc = OA.vq_encode(sd, CFG.VQ_F8_DDCONFIG, G["img"])
     assert rel_l2(dec, G["dec"]) < 2e-5
     assert rel_l2(enc, G["enc"]) < 2e-5
+
+
+def test_conditioner_oracle_matches_reference_golden():
+    """oracle/conditioner.py against tests/golden/conditioner.pt, produced by the reference's own UnetCond with the
+    reference's VQModelInterface as `convs` (oracle/gen_golden_cond.py): context in eval mode and with BatchNorm on
+    batch statistics, the three styles, the fourier features, and a 4-step LSTM recurrence."""
+    from oracle import conditioner as OC
+    G = gold("conditioner.pt")
+    sd = OC.synthetic_state_dict()
+    assert [k for k, _ in OC.param_shapes()] == list(sd.keys()) and len(sd) == 36
+    rel = lambda a, b: float((a.double() - b.double()).norm() / b.double().norm())  # noqa: E731
+    assert torch.equal(OC.fourier_features(G["time"]), G["fourier"])
+    o = OC.unet_cond_forward(sd, G["z"], G["flow"], G["weather"], G["time"], bn_training=False)
+    assert o["context"].shape == G["context_eval"].shape == (G["T"], 4, 512)
+    assert rel(o["context"], G["context_eval"]) < 1e-5
+    assert rel(o["time_style"], G["time_style"]) < 1e-6
+    assert rel(o["flow_style"], G["flow_style"]) < 1e-6 and rel(o["weather_style"], G["weather_style"]) < 1e-6
+    ob = OC.unet_cond_forward(sd, G["z"], G["flow"], G["weather"], G["time"], bn_training=True)
+    assert rel(ob["context"], G["context_bn_train"]) < 1e-5
+    assert rel(ob["context"], o["context"]) > 1e-3          # the two BatchNorm modes really differ
+    assert rel(OC.lstm_mlp(sd, "w_mlp", G["lstm_seq_in"]), G["lstm_seq_out"]) < 1e-6
