@@ -106,6 +106,7 @@ class UnetCond(nn.Module):
         self.register_buffer("_freqs", torch.from_numpy(np.sort(freqs).astype(np.float32)), persistent=False)
         assert 2 * len(freqs) == t_dim, "t_dim must equal cond_args.dims = 2 * #frequencies"
         self._packed = None
+        self._warned = False
         self.register_load_state_dict_post_hook(lambda m, keys: m.invalidate_packed())
         if device is not None and str(device) != "cpu":
             self.to(device)
@@ -195,6 +196,13 @@ class UnetCond(nn.Module):
         dev = self.out_layer[1].weight.device
         if dev.type != "cuda":
             raise RuntimeError("ealdm_b200.UnetCond runs on CUDA (sm_100a) only; there is no CPU fallback")
+        if self.training and not self._warned and any(p.requires_grad for p in self.out_layer.parameters()):
+            # be loud: a `cond_stage_trainable: true` run would otherwise train the UNet only without saying so
+            import warnings
+            warnings.warn("ealdm_b200.UnetCond: only the forward pass is built; the conditioner's parameters receive no "
+                          "gradients (DESIGN.md section 7). Freeze it (cond_stage_trainable: false) or train it with the "
+                          "reference module.", RuntimeWarning, stacklevel=2)
+            self._warned = True
         P = self._pack()
         img = img.squeeze(0).to(dev)
         z = self._encoder_features(img)                                        # [B, 32, 32, mid] NHWC fp32
