@@ -12,8 +12,17 @@
 // Persistent, warp-specialised CTA (one per SM):
 //   warp 0      TMA producer (one elected lane)         smem ring of STAGES x (A 16 KiB + B BN*128 B)
 //   warp 1      TMEM allocator + tcgen05.mma issuer     2 accumulator stages of BN fp32 columns
-//   warps 2..9  epilogue, two per TMEM lane quadrant (even / odd 32-column units)
+//   warps 2..9  epilogue, two per TMEM lane quadrant (even / odd 32-column units, or -- "wide" passes, when there is
+//               no residual and no shadow output -- the two 128-column halves with 128-byte rows per TMA store)
 // so the epilogue of tile i overlaps the main loop of tile i+1.
+//
+// CTA pairs (template parameter CTA2, chosen for K >= 1024 and an even number of M tiles): the grid is a persistent
+// set of 2-CTA clusters and a work item is a 256 x BN super-tile.  Each CTA stages its own 128 A rows and HALF of the B
+// tile; the leader (cluster rank 0) issues `tcgen05.mma.cta_group::2` for both, its full barriers collect the TMA
+// transactions of both CTAs (the peer's loads name the leader's mbarrier), `tcgen05.commit ... multicast::cluster`
+// releases the stage and publishes the accumulator in both CTAs, and the peer's epilogue warps arrive remotely on the
+// leader's tmem_empty barrier.  Each CTA's epilogue is unchanged: it drains its own 128 TMEM lanes.  Operand traffic
+// per SM and k-block drops from 48 KB to 32 KB, which is what bounds the single-CTA kernel.
 //
 // Epilogue data movement is TMA in both directions: every epilogue warp owns [32 rows x 32 columns]
 // units of the tile.  The residual unit is prefetched by a TMA box load (issued one unit ahead, across
