@@ -562,3 +562,87 @@ def test_dgrad_cta_pairs_match_single_cta(n, c, h, w, co):
         outs.append(from_act(dx))
     assert rel_l2(outs[1], x.grad) < 8e-3
     assert torch.equal(outs[0], outs[1])
+
+
+def _sweep_cases():
+    import random
+    rnd = random.Random(1234)
+    cases = []
+    for i in range(28):
+        n = rnd.choice([1, 2, 3, 5, 6])
+        hw = rnd.choice([(8, 8), (16, 16), (32, 32), (16, 8), (4, 32)])
+        c = rnd.choice([64, 128, 192, 256])
+        co = rnd.choice([64, 96, 160, 256, 320, 512])
+        cases.append(dict(i=i, n=n, h=hw[0], w=hw[1], c=c, co=co, ksize=rnd.choice([1, 3, 3]),
+                          stride=rnd.choice([1, 1, 1, 2]), skip_c=rnd.choice([0, 0, 64, 128]),
+                          res=rnd.choice([None, "f32", "bf16"]), out_f32=rnd.choice([True, False]),
+                          out2=rnd.choice([False, True]), rowvec=rnd.choice([False, True]),
+                          gn=rnd.choice([False, True]), bias=rnd.choice([True, True, False])))
+    return cases
+
+
+@pytest.mark.parametrize("case", _sweep_cases(), ids=lambda c: f"case{c['i']}")
+def test_conv_feature_sweep_all_schedules(case):
+    """Seeded sweep over the conv epilogue's feature combinations (two sources, stride 2, fp32 / bf16 residual, fp32 /
+    bf16 output, shadow output, per-image row vector, GroupNorm partial statistics, ragged N and M) run under every
+    schedule -- default tile choice, forced 256-column tiles with and without CTA pairs, 128-column tiles as pairs --
+    against F.conv2d; all schedules must agree bit for bit (same k-block order, same epilogue arithmetic)."""
+    cs = dict(case)
+    n, h, w, c, co, ks, stride = cs["n"], cs["h"], cs["w"], cs["c"], cs["co"], cs["ksize"], cs["stride"]
+    if stride == 2 and (ks == 1 or h % 2 or w % 2):
+        stride = 1
+    ho, wo = h // stride, w // stride
+    gn = cs["gn"] and cs["out_f32"] and co % 32 == 0 and (ho * wo) % 32 == 0
+    out2 = cs["out2"] and cs["out_f32"]
+    dt = torch.bfloat16
+    x = torch.randn(n, c, h, w, generator=g(200 + cs["i"])).to(DEV)
+    wt = (torch.randn(co, c, ks, ks, generator=g(300 + cs["i"])) / math.sqrt(ks * ks * c)).to(DEV)
+    xa = to_act(x, dt)
+    srcs = [ConvIn(xa, ks, stride, ks // 2)]
+    wp = pack_w(wt, dt)
+    ref = F.conv2d(from_act(xa), wt.to(dt).float(), stride=stride, padding=ks // 2)
+    if cs["skip_c"] and stride == 1:
+        xs = torch.randn(n, cs["skip_c"], h, w, generator=g(400 + cs["i"])).to(DEV)
+        ws_ = (torch.randn(co, cs["skip_c"], 1, 1, generator=g(500 + cs["i"])) / math.sqrt(cs["skip_c"])).to(DEV)
+        xsa = to_act(xs, dt)
+        srcs.append(ConvIn(xsa, 1, 1, 0))
+        wp = torch.cat([wp, pack_w(ws_, dt)], dim=1).contiguous()
+        ref = ref + F.conv2d(from_act(xsa), ws_.to(dt).float())
+    bias = torch.randn(co, generator=g(600 + cs["i"])).to(DEV) if cs["bias"] else None
+    if bias is not None:
+        ref = ref + bias[None, :, None, None]
+    emb = None
+    if cs["rowvec"] and co % 4 == 0:
+        emb = torch.randn(n, co, generator=g(700 + cs["i"])).to(DEV)
+        ref = ref + emb[:, :, None, None]
+    ra = None
+    if cs["res"] is not None:
+        r = torch.randn(n, co, ho, wo, generator=g(800 + cs["i"])).to(DEV)
+        ra = to_act(r, torch.float32 if cs["res"] == "f32" else dt)
+        ref = ref + from_act(ra)
+    odt = torch.float32 if cs["out_f32"] else dt
+    results = []
+    for bn, mode in ((0, 1), (256, 0), (256, 2), (128, 2)):
+        out = Act.empty(n, ho, wo, co, odt, DEV)
+        if gn:
+            out.with_gn_partial()
+        o2 = Act.empty(n, ho, wo, co, dt, DEV) if out2 else None
+        with _tc_option(L.TC_OPT_CTA2, mode, bn=bn):
+            ops.conv(srcs, wp, out, bias=bias, rowvec=emb, residual=ra, out2=o2, impl=L.IMPL_TCGEN05)
+        torch.cuda.synchronize()
+        results.append((from_act(out), None if o2 is None else from_act(o2),
+                        out.gp.clone() if out.gp is not None else None))
+    tol = 3e-5 if cs["out_f32"] else 6e-3
+    assert rel_l2(results[0][0], ref) < tol
+    for other in results[1:]:
+        assert torch.equal(results[0][0], other[0])
+        if out2:
+            assert torch.equal(results[0][1], other[1]) and rel_l2(other[1], ref) < 6e-3
+        if results[0][2] is not None:
+            assert torch.equal(results[0][2], other[2])
+    if results[0][2] is not None:   # the partial statistics really are the sums of the output
+        o = results[0][0]
+        sums = results[0][2].view(n, -1, co // 8, 2).sum(dim=1)           # [n, octet, {sum, sumsq}]
+        ref_s = o.reshape(n, co // 8, 8, -1).sum(dim=(2, 3))
+        ref_ss = (o * o).reshape(n, co // 8, 8, -1).sum(dim=(2, 3))
+        assert rel_l2(sums[..., 0], ref_s) < 1e-4 and rel_l2(sums[..., 1], ref_ss) < 1e-4
