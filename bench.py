@@ -28,6 +28,8 @@ if ROOT not in sys.path:
 
 METRIC = "latent samples/sec (50-step DDIM, 256px)"
 UNIT = "samples/s"
+WORKLOAD = ("stdiff_cin-ldm-vq-f8 UNet (394.98 M params, cross-attention on [B,4,512] STDiff conditioning), 50-step DDIM, "
+            "CFG 2.0, eta 0, 32x32x4 latent, batch 64 per GPU (BASELINE.json configs[1])")
 
 
 def load_peaks():
@@ -123,12 +125,15 @@ def run_reference(args):
         one_step(i)
     dt = (time.perf_counter() - t0) / max(args.steps, 1)
     value = B / (dt * S)
-    sample = f"B={B}, one of {S} DDIM steps per timed step (CFG 2.0, UNet batch {2 * B}), fp32, linearly extrapolated to {S} steps"
+    sample = (f"bounded sample of the workload: B={B} (not 64), ONE of the {S} DDIM steps per timed step (CFG 2.0, UNet batch "
+              f"{2 * B}), fp32, oracle port on {cores} host threads; value = B / (step time x {S}), i.e. linearly "
+              f"extrapolated in the step count; per-sample cost at B=64 on a CPU is the same or lower")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "stdiff_cin-ldm-vq-f8 UNet, 50-step DDIM, CFG 2.0, 32x32x4 latent", "batch_per_gpu": 64,
-                       "ddim_steps": S, "guidance_scale": 2.0},
+            "config": {"workload": WORKLOAD, "timed_batch": B, "timed_ddim_steps_per_step": 1, "ddim_steps": S,
+                       "guidance_scale": 2.0, "same_config": False,
+                       "note": "the full workload (B=64, 50 steps) is ~27 min of CPU time per step; see cpu_baseline.sample"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -167,6 +172,55 @@ def cpu_baseline_leg(budget_s=25.0):
                       f"best of {len(times)}, extrapolated linearly to {S} steps"}
 
 
+def torch_gpu_baseline_leg(dev, B, S):
+    """The GPU-side comparison bar of BASELINE.md section 4: eager PyTorch (cuDNN / cuBLAS kernels, the arithmetic
+    provider of the reference) on the SAME B200 -- the oracle port's functional restatement of the reference UNet run
+    on cuda for ONE DDIM step's UNet evaluation at the benchmark's UNet batch (2B with CFG), in fp32 with TF32 off,
+    fp32 with TF32 on, and under torch.autocast(bf16).  Outside every timed region; reported like cpu_baseline
+    (`value` = B / (50 x forward time): the DDIM update is not included, which favours the baseline)."""
+    import torch
+
+    from ealdm_b200 import configs as CFG
+    from oracle import unet as OU   # checker code, used here as the eager-PyTorch baseline only
+
+    sd = {k: v.to(dev) for k, v in OU.synthetic_state_dict(OU.unet_param_shapes(CFG.UNET_STDIFF), seed=2).items()}
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(2 * B, 4, 32, 32, generator=g).to(dev)
+    c = torch.randn(2 * B, 4, 512, generator=g).to(dev)
+    t = torch.full((2 * B,), 981, dtype=torch.long, device=dev)
+    out = {"unit": UNIT, "unet_batch": 2 * B, "kind": "eager PyTorch (cuDNN/cuBLAS) on this GPU, oracle port of the "
+           "reference UNet, one UNet evaluation timed and scaled by the 50 DDIM steps"}
+    saved = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+
+    def timed(ctx):
+        with torch.no_grad(), ctx:
+            OU.unet_forward(sd, CFG.UNET_STDIFF, x, t, c)          # warm-up (cuDNN heuristics, allocator)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(2):
+                OU.unet_forward(sd, CFG.UNET_STDIFF, x, t, c)
+            e1.record()
+            torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / 2
+
+    import contextlib
+    try:
+        for name, tf32, ctx in (("fp32", False, contextlib.nullcontext()), ("tf32", True, contextlib.nullcontext()),
+                                ("autocast_bf16", True, torch.autocast("cuda", dtype=torch.bfloat16))):
+            torch.backends.cudnn.allow_tf32 = tf32
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            ms = timed(ctx)
+            out[name] = {"unet_forward_ms": ms, "value": B / (ms * 1e-3 * S)}
+    except Exception as ex:   # a baseline must never break the product line
+        out["error"] = f"{type(ex).__name__}: {ex}"
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = saved
+        del sd
+        torch.cuda.empty_cache()
+    return out
+
+
 # ------------------------------------------------------------------------------------------------------
 def run_train(args):
     """--workload train: BASELINE.json configs[4] -- one optimisation step of LatentDiffusion on the stdiff UNet:
@@ -186,7 +240,8 @@ def run_train(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    if world > 1:
+    own_group = world > 1 and not dist.is_initialized()
+    if own_group:
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch if args.batch != 64 else 32
     ld = LatentDiffusion(unet_config={"target": "ealdm_b200.unet.UNetModel", "params": dict(CFG.UNET_STDIFF)},
@@ -291,11 +346,15 @@ def run_train(args):
                 "e2e": {"value": B * world / (ms_per_step * 1e-3), "unit": "samples/s",
                         "h2d_bytes_per_step": (x0_h.numel() + c2_h.numel()) * 4, "d2h_bytes_per_step": 4,
                         "note": "the timed step already copies its batch from pinned host memory and reads the loss back"}}
-        print(json.dumps(line), flush=True)
-    if world > 1:
+        if not getattr(args, "quiet", False):
+            print(json.dumps(line), flush=True)
+    else:
+        line = None
+    unet.grad_ready_hook = None
+    if own_group:
         dist.barrier()
         dist.destroy_process_group()
-    return 0
+    return line
 
 
 def run_autoencoder(args):
@@ -354,8 +413,9 @@ def run_autoencoder(args):
                     "d2h_bytes_per_step": out_h.numel() * 4, "ms_per_step": res[True]},
             "gpu_launches": int(launches * args.steps), "tflops_per_gpu": tf / (res[False] * 1e-3),
             "frac_of_sustained_peak": tf / (res[False] * 1e-3) / peaks["bf16_sustained"]}
-    print(json.dumps(line), flush=True)
-    return 0
+    if not getattr(args, "quiet", False):
+        print(json.dumps(line), flush=True)
+    return line
 
 
 def run_config1(args):
@@ -441,6 +501,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="latent samples per GPU per step")
+    ap.add_argument("--global-batch", type=int, default=0,
+                    help="BASELINE.json configs[3]: a FIXED global batch (512) sharded over the ranks -> strong scaling")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the torch-GPU baseline and the configs[2] / configs[4] sub-results of the default line")
     ap.add_argument("--ddim-steps", type=int, default=50)
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--autograd", action="store_true", help="train workload: p_losses under torch.autograd")
@@ -453,9 +517,11 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
     if args.workload == "train":
-        return run_train(args)
+        run_train(args)
+        return 0
     if args.workload == "autoencoder":
-        return run_autoencoder(args)
+        run_autoencoder(args)
+        return 0
     if args.workload == "config1":
         return run_config1(args)
 
@@ -475,11 +541,23 @@ def main():
         raise SystemExit("bench.py: no CUDA device (the hot path has no CPU fallback; use --impl reference)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # the CPU baseline runs at N = 1 only, BEFORE any GPU work or process group exists: nothing else competes for the
+    # host cores (round 1 ran it on rank 0 while the other ranks polled a barrier, which corrupted the N > 1 lines)
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            cpu = cpu_baseline_leg()
+        except Exception as ex:  # the oracle is a checker; never let it break the GPU line
+            cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {ex}"}
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
 
     B, S, ugs = args.batch, args.ddim_steps, 2.0
+    strong = args.global_batch > 0
+    if strong:
+        assert args.global_batch % world == 0, "--global-batch must divide by the number of ranks"
+        B = args.global_batch // world
     ld = LatentDiffusion(unet_config={"target": "ealdm_b200.unet.UNetModel", "params": dict(CFG.UNET_STDIFF)},
                          cond_stage_config={"target": "torch.nn.Identity"}, conditioning_key="crossattn",
                          **CFG.DIFFUSION).to(dev).eval()
@@ -596,7 +674,19 @@ def main():
         r = orig_conv(srcs, weight, out, **kw)
         e1.record()
         tc = srcs[0].x.dtype == torch.bfloat16 and all(s.x.c % 64 == 0 and not s.upsample for s in srcs)
-        rec.append((e0, e1, 2.0 * out.rows * weight.shape[0] * weight.shape[1], tc))
+        # algorithmic bytes of the launch: every operand once -- A (each source read once, NOT once per filter tap),
+        # W, bias / row vector, residual, output and its bf16 shadow
+        nbytes = sum(s.x.rows * s.x.c * s.x.buf.element_size() for s in srcs) + weight.numel() * weight.element_size()
+        nbytes += out.rows * out.c * out.buf.element_size()
+        for key in ("residual", "out2"):
+            t_ = kw.get(key)
+            if t_ is not None:
+                nbytes += t_.rows * t_.c * t_.buf.element_size()
+        if kw.get("bias") is not None:
+            nbytes += kw["bias"].numel() * 4
+        if kw.get("rowvec") is not None:
+            nbytes += srcs[0].x.n * weight.shape[0] * 4
+        rec.append((e0, e1, 2.0 * out.rows * weight.shape[0] * weight.shape[1], tc, nbytes))
         return r
 
     xin = torch.cat([x_T_d] * 2)
@@ -616,46 +706,65 @@ def main():
     ops.conv = orig_conv
     _unet_mod.ops.conv = orig_conv
     launches_per_forward = ops.launch_count() - l0
-    tc_ms = sum(e0.elapsed_time(e1) for e0, e1, _, tc in rec if tc)
-    tc_flops = sum(f for _, _, f, tc in rec if tc)
+    tc_ms = sum(e0.elapsed_time(e1) for e0, e1, _, tc, _ in rec if tc)
+    tc_flops = sum(f for _, _, f, tc, _ in rec if tc)
+    tc_bytes = sum(nb for _, _, _, tc, nb in rec if tc)
     n_tc = sum(1 for r_ in rec if r_[3])
     fwd_ms = f0.elapsed_time(f1)
     achieved = tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
     roofline = {"bound": "tensor", "kernel": "ealdm::tc::conv_tc_kernel (tcgen05 implicit-GEMM conv/linear)",
                 "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                 "frac": achieved / peaks["bf16_sustained"], "peak_source": peaks["source"] + " (sustained)",
-                "traffic": None, "launches_per_forward": n_tc, "avg_launch_ms": tc_ms / max(n_tc, 1),
+                "traffic": None, "algorithmic_bytes": tc_bytes / max(n_tc, 1),
+                "algorithmic_bytes_per_forward": tc_bytes, "algorithmic_flops_per_forward": tc_flops,
+                "launches_per_forward": n_tc, "avg_launch_ms": tc_ms / max(n_tc, 1),
                 # share of one DDIM step of the timed (CUDA-graph) run; the instrumented eager forward itself is
                 # host-bound (an event pair per launch), so its own duration is reported separately
                 "share_of_forward": tc_ms / (ms_per_step / S) if ms_per_step > 0 else None,
                 "eager_instrumented_forward_ms": fwd_ms,
                 "note": "event-timed eager forward at UNet batch %d; algorithmic FLOPs = 2*M*N*K per launch; "
-                        "share_of_forward = summed launch time / (ms_per_step / ddim_steps)" % (2 * B)}
+                        "algorithmic_bytes = A + W + bias/rowvec + residual + out (+ bf16 shadow), every operand once, "
+                        "per-launch average like `traffic`; share_of_forward = summed launch time / (ms_per_step / "
+                        "ddim_steps)" % (2 * B)}
     # DRAM bytes per launch of the same kernel from the committed ncu capture of one forward at this batch
-    tpath = os.path.join(ROOT, "profiles", "r01_conv_tc_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r02_conv_tc_traffic.json")
+    if not os.path.exists(tpath):
+        tpath = os.path.join(ROOT, "profiles", "r01_conv_tc_traffic.json")
     if os.path.exists(tpath) and B == 64:
         with open(tpath) as f:
             tj = json.load(f)
         roofline["traffic"] = tj["dram_bytes_per_launch"]
         roofline["traffic_note"] = ("dram__bytes_read.sum + dram__bytes_write.sum averaged over the %d launches of one "
-                                    "forward (profiles/r01_conv_tc_traffic.json); L2 traffic per launch %.0f MB"
-                                    % (tj["launches"], tj["l2_bytes_per_launch"] / 1e6))
+                                    "forward (%s); L2 traffic per launch %.0f MB"
+                                    % (tj["launches"], os.path.relpath(tpath, ROOT), tj["l2_bytes_per_launch"] / 1e6))
     step_tflops = value / world * S * 2 * CFG.UNET_STDIFF_GFLOP_PER_SAMPLE / 1e3
 
-    if rank == 0:
-        cpu = None
-        if not args.no_cpu_baseline:
+    # --- extras of the default line (N = 1): the eager-PyTorch GPU bar and BASELINE.json configs[2] / configs[4] -----
+    extras = {}
+    if world == 1 and not args.no_extras and not args.ncu_window:
+        unet.invalidate_packed()           # drops the packed weights and the CUDA graphs (their memory pool)
+        torch.cuda.empty_cache()
+        extras["torch_gpu_baseline"] = torch_gpu_baseline_leg(dev, B, S)
+        sub = argparse.Namespace(**vars(args))
+        sub.quiet, sub.steps, sub.warmup, sub.batch = True, 3, 3, 64
+        for key, fn in (("config3_autoencoder", run_autoencoder), ("config5_train", run_train)):
             try:
-                cpu = cpu_baseline_leg()
-            except Exception as ex:  # the oracle is a checker; never let it break the GPU line
-                cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {ex}"}
+                r = fn(sub)
+                extras[key] = {k: r[k] for k in ("metric", "value", "unit", "ms_per_step", "e2e", "config", "gpu_launches",
+                                                 "frac_of_sustained_peak") if k in r}
+            except Exception as ex:
+                extras[key] = {"error": f"{type(ex).__name__}: {ex}"}
+            torch.cuda.empty_cache()
+
+    if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong" if strong else "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "stdiff_cin-ldm-vq-f8 UNet (394.98 M params, cross-attention on [B,4,512] STDiff "
-                                   "conditioning), 50-step DDIM, CFG 2.0, eta 0, 32x32x4 latent, batch 64 per GPU "
-                                   "(BASELINE.json configs[1])",
+            "config": {"workload": WORKLOAD if not strong else
+                       (f"stdiff_cin-ldm-vq-f8 conditioned DDIM sampling with classifier-free guidance, FIXED global batch "
+                        f"{Bg} sharded over {world} GPU(s) = {B} per GPU (BASELINE.json configs[3]), 50-step DDIM, CFG 2.0"),
                        "batch_per_gpu": B, "global_batch": Bg, "ddim_steps": S, "guidance_scale": ugs,
                        "unet_batch": 2 * B, "parallelism": f"batch-sharded x{world}, one final all-gather",
                        "cuda_graph": not args.no_graph,
@@ -672,6 +781,7 @@ def main():
             "cpu_baseline": cpu,
             "with_decode": with_decode,
         }
+        line.update(extras)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -48,8 +48,36 @@ class DiagonalGaussianDistribution(object):
         return 0.5 * torch.sum(torch.pow(self.mean - other.mean, 2) / other.var + self.var / other.var
                                - 1.0 - self.logvar + other.logvar, dim=[1, 2, 3])
 
+    def nll(self, sample, dims=(1, 2, 3)):
+        """distributions.py:54-60"""
+        if self.deterministic:
+            return torch.Tensor([0.])
+        import math
+        return 0.5 * torch.sum(math.log(2.0 * math.pi) + self.logvar + torch.pow(sample - self.mean, 2) / self.var,
+                               dim=list(dims))
+
     def mode(self):
         return self.mean
+
+
+_posterior_classes = {}
+
+
+def posterior_class():
+    """The class `AutoencoderKL.encode` instantiates.  The reference decides by `isinstance(encoder_posterior,
+    DiagonalGaussianDistribution)` (ldm/models/diffusion/ddpm.py:550-557) and raises otherwise, so when this first
+    stage is hosted by the reference's LatentDiffusion -- i.e. the reference's distributions module is loaded in this
+    process -- the returned object must also be an instance of THAT class."""
+    import sys
+    ref = sys.modules.get("ldm.modules.distributions.distributions")
+    ref_cls = getattr(ref, "DiagonalGaussianDistribution", None) if ref is not None else None
+    if ref_cls is None or ref_cls is DiagonalGaussianDistribution:
+        return DiagonalGaussianDistribution
+    cls = _posterior_classes.get(ref_cls)
+    if cls is None:
+        cls = type("DiagonalGaussianDistribution", (DiagonalGaussianDistribution, ref_cls), {})
+        _posterior_classes[ref_cls] = cls
+    return cls
 
 
 def Normalize(c):  # model.py:38-39
@@ -232,13 +260,18 @@ class AutoencoderKL(nn.Module):
     def _eng(self, x):
         if not x.is_cuda:
             raise RuntimeError("ealdm_b200.AutoencoderKL runs on CUDA (sm_100a) only; there is no CPU fallback")
+        # the engine caches kernel-layout weights: compare the parameters' version counters (see unet.UNetModel)
+        if self._engine is not None and sum(p._version for p in self._plist) != self._engine_fp:
+            self._engine = None
         if self._engine is None:
+            self._plist = list(self.parameters())
             self._engine = AutoencoderEngine(self, self._compute_dtype)
+            self._engine_fp = sum(p._version for p in self._plist)
         return self._engine
 
     @torch.no_grad()
     def encode(self, x):
-        return DiagonalGaussianDistribution(self._eng(x).encode_moments(x))
+        return posterior_class()(self._eng(x).encode_moments(x))
 
     @torch.no_grad()
     def decode(self, z):

@@ -127,8 +127,11 @@ class UnetCond(nn.Module):
 
     # ---- kernel-layout copies of the parameters (made once; call invalidate_packed() after an optimizer step) --------
     def _pack(self):
-        if self._packed is not None:
+        own = [p for n, p in self.named_parameters() if not n.startswith("convs.")]
+        fp = sum(p._version for p in own)
+        if self._packed is not None and fp == self._packed_fp:
             return self._packed
+        self._packed_fp = fp
         f32 = lambda t: t.detach().float().contiguous()  # noqa: E731
         P = {}
         for name in ("w_mlp", "f_mlp"):

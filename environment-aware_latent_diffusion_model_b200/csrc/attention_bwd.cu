@@ -336,10 +336,10 @@ static int launch_xattn_bwd(const ealdm_attention_bwd_args* a, cudaStream_t st) 
   bf16* dq = reinterpret_cast<bf16*>(a->dq);
 #define EALDM_XB(NKV)                                                                                              \
   case NKV: {                                                                                                      \
-    static bool attr = false;                                                                                      \
-    if (!attr) {                                                                                                   \
+    static DeviceOnce attr;                                                                                        \
+    if (attr.pending()) {                                                                                          \
       EALDM_CUDA(cudaFuncSetAttribute(xattn_bwd_kernel<NKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536)); \
-      attr = true;                                                                                                 \
+      attr.done();                                                                                                 \
     }                                                                                                              \
     xattn_bwd_kernel<NKV><<<grid, XB_THREADS, smem, st>>>(q, k, v, d_o, a->ld_q, a->ld_kv, a->ld_dout, c,        \
                                                            (int)a->n_q, a->scale, dq, a->ld_dq, part);            \

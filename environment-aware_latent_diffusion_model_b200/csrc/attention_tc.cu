@@ -367,10 +367,10 @@ bool supported(const ealdm_attention_args* a) {
 template <bool WIDE>
 static int launch_t(const ealdm_attention_args* a, cudaStream_t st) {
   using C = Cfg<WIDE>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;
+  if (attr_set.pending()) {
     EALDM_CUDA(cudaFuncSetAttribute(flash_tc_kernel<WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    attr_set = true;
+    attr_set.done();
   }
   CUtensorMap tq, tk, tv;
   const long long qcols = (a->heads - 1) * a->head_stride_q + 32;

@@ -9,6 +9,8 @@
 
 #include "../../include/ealdm_b200.h"
 
+#include <atomic>
+
 namespace ealdm {
 
 // ---- error plumbing (thread-local message, integer codes across the ABI) -----------------------
@@ -38,6 +40,19 @@ void count_launch(int n = 1);
   } while (0)
 
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// One-time per-DEVICE work (cudaFuncSetAttribute is per device; one process may drive several GPUs, from several
+// threads): a bit per device ordinal, set after the work succeeded.  Doing the work twice in a race is harmless.
+struct DeviceOnce {
+  std::atomic<unsigned long long> bits{0};
+  static int device() {
+    int d = 0;
+    cudaGetDevice(&d);
+    return d & 63;
+  }
+  bool pending() const { return ((bits.load(std::memory_order_acquire) >> device()) & 1ull) == 0; }
+  void done() { bits.fetch_or(1ull << device(), std::memory_order_release); }
+};
 
 // ---- element type helpers ----------------------------------------------------------------------
 typedef __nv_bfloat16 bf16;

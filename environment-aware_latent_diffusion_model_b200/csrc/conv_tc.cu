@@ -789,11 +789,11 @@ static int pow2_ceil(long long v) {
 template <int BN, bool GEGLU>
 static int launch_bn(const CUtensorMap* tm, const Params& p, cudaStream_t st) {
   using C = Cfg<BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;
+  if (attr_set.pending()) {
     EALDM_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, GEGLU, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     C::SMEM_BYTES));
-    attr_set = true;
+    attr_set.done();
   }
   const int total = p.m_tiles * p.n_tiles;
   const int grid = total < num_sms() ? total : num_sms();
@@ -807,7 +807,8 @@ static int launch_bn(const CUtensorMap* tm, const Params& p, cudaStream_t st) {
 template <int BN, bool GEGLU>
 static int launch_pair(const CUtensorMap* tm, const Params& p, cudaStream_t st) {
   using C = Cfg<BN, true>;
-  static int max_clusters = 0;
+  static int max_clusters = 0;   // devices of one process are assumed to be the same model
+  static DeviceOnce attr_set;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cudaLaunchAttribute attr[1];
@@ -820,9 +821,12 @@ static int launch_pair(const CUtensorMap* tm, const Params& p, cudaStream_t st) 
   cfg.stream = st;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  if (!max_clusters) {
+  if (attr_set.pending()) {
     EALDM_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, GEGLU, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     C::SMEM_BYTES));
+    attr_set.done();
+  }
+  if (!max_clusters) {
     cfg.gridDim = dim3(num_sms() & ~1);
     int n = 0;
     EALDM_CUDA(cudaOccupancyMaxActiveClusters(&n, conv_tc_kernel<BN, GEGLU, true>, &cfg));

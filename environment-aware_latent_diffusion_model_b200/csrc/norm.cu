@@ -560,15 +560,18 @@ static int group_norm_cluster(const ealdm_group_norm_args* a, int cl, int ppc, s
                               cudaStream_t st, bool* launched) {
   *launched = false;
   auto kern = gn_cluster_kernel<TX, T>;
-  static size_t smem_set = 0;
-  static bool nonportable_set = false;
-  if (smem > smem_set) {
-    EALDM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    smem_set = smem;
+  // per device: opt in to the largest dynamic shared memory a CTA may use (once) and to non-portable cluster sizes
+  static DeviceOnce smem_set, nonportable_set;
+  if (smem_set.pending()) {
+    int dev = 0, optin = 0;
+    EALDM_CUDA(cudaGetDevice(&dev));
+    EALDM_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    EALDM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+    smem_set.done();
   }
-  if (cl > 8 && !nonportable_set) {
+  if (cl > 8 && nonportable_set.pending()) {
     EALDM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    nonportable_set = true;
+    nonportable_set.done();
   }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));

@@ -446,11 +446,11 @@ static void make_plan(const ealdm_conv_wgrad_args* a, Plan* pl) {
 template <int BN>
 static int launch_tc(const CUtensorMap& tmDy, const CUtensorMap& tmX, const Params& p, cudaStream_t st) {
   using C = Cfg<BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;
+  if (attr_set.pending()) {
     EALDM_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     C::SMEM_BYTES));
-    attr_set = true;
+    attr_set.done();
   }
   const int total = p.m_tiles * p.taps * p.cblocks * p.splits;
   const int grid = total < num_sms() ? total : num_sms();

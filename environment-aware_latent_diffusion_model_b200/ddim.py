@@ -13,7 +13,7 @@ import numpy as np
 import torch
 
 from . import ops
-from .util import make_ddim_sampling_parameters, make_ddim_timesteps
+from .util import make_ddim_sampling_parameters, make_ddim_timesteps, revalidate_packed
 
 
 class DDIMSampler(object):
@@ -81,6 +81,7 @@ class DDIMSampler(object):
             if cbs != batch_size:
                 print(f"Warning: Got {cbs} conditionings but batch-size is {batch_size}")
         self.make_schedule(ddim_num_steps=S, ddim_eta=eta, verbose=verbose)
+        revalidate_packed(self.model)
         C, H, W = shape
         size = (batch_size, C, H, W)
         if verbose:

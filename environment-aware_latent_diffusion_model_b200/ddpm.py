@@ -11,6 +11,8 @@ the reference (out of scope).
 """
 from __future__ import annotations
 
+import copy
+from contextlib import contextmanager
 from functools import partial
 
 import numpy as np
@@ -19,7 +21,8 @@ import torch.nn as nn
 
 from . import ops
 from .ddim import DDIMSampler
-from .util import count_params, instantiate_from_config, make_beta_schedule
+from .ema import LitEma, invalidate_packed_modules
+from .util import count_params, instantiate_from_config, make_beta_schedule, revalidate_packed
 
 
 def disabled_train(self, mode=True):
@@ -117,9 +120,16 @@ class LatentDiffusion(nn.Module):
         self.image_size, self.channels = image_size, channels
         self.model = DiffusionWrapper(unet_config, conditioning_key)
         count_params(self.model, verbose=False)
-        self.use_ema = use_ema
-        if use_ema:
-            raise NotImplementedError("EMA shadow weights are a training-loop neighbour (SURVEY.md 8f rank 2)")
+        self.use_ema = use_ema          # NB: the reference's default is True (ddpm.py:57); its shipped yaml leaves it on
+        if use_ema:                     # `model_ema.*` buffers in the reference's checkpoint layout (ema.py:5-23)
+            self.model_ema = LitEma(self.model)
+        self.use_scheduler = scheduler_config is not None
+        if self.use_scheduler:
+            self.scheduler_config = scheduler_config
+        self.learning_rate = base_learning_rate      # main.py:741-745 overwrites it with ngpu * bs * base_lr
+        self.shorten_cond_schedule = self.num_timesteps_cond > 1
+        if self.shorten_cond_schedule:
+            raise NotImplementedError("num_timesteps_cond > 1 (the shortened conditioning schedule, ddpm.py:497-505)")
         self.v_posterior, self.original_elbo_weight, self.l_simple_weight = v_posterior, original_elbo_weight, l_simple_weight
         self.monitor = monitor
         self.loss_type = loss_type
@@ -197,14 +207,56 @@ class LatentDiffusion(nn.Module):
                 # the EALDM conditioner encodes its frames with the first stage (ddpm.py:535-536)
                 self.cond_stage_model.convs = self.first_stage_model
 
-    def init_from_ckpt(self, path, ignore_keys=()):
+    def init_from_ckpt(self, path, ignore_keys=(), only_model=False):
+        """ddpm.py:188-201.  With `use_ema=True` the checkpoint's `model_ema.*` buffers load into `self.model_ema`; with
+        `use_ema=False` they would be dropped by strict=False, so say so instead of sampling raw weights silently."""
         sd = torch.load(path, map_location="cpu")
         sd = sd.get("state_dict", sd)
         for k in list(sd.keys()):
             if any(k.startswith(ik) for ik in ignore_keys):
                 del sd[k]
-        missing, unexpected = self.load_state_dict(sd, strict=False)
+        target = self.model if only_model else self
+        missing, unexpected = target.load_state_dict(sd, strict=False)
         print(f"Restored from {path} with {len(missing)} missing and {len(unexpected)} unexpected keys")
+        if not self.use_ema and any(k.startswith("model_ema.") for k in unexpected):
+            print("WARNING: the checkpoint holds EMA weights (model_ema.*) but use_ema=False: they were NOT loaded and "
+                  "ema_scope() is a no-op; construct the model with use_ema=True to sample under the EMA weights")
+
+    @contextmanager
+    def ema_scope(self, context=None):
+        """ddpm.py:173-186: run the body under the EMA weights.  The packed kernel-layout weights (and CUDA graphs) of
+        the UNet are dropped on both switches (ema.LitEma.copy_to / restore)."""
+        if self.use_ema:
+            self.model_ema.store(self.model.parameters())
+            self.model_ema.copy_to(self.model)
+            if context is not None:
+                print(f"{context}: Switched to EMA weights")
+        try:
+            yield None
+        finally:
+            if self.use_ema:
+                self.model_ema.restore(self.model.parameters(), self.model)
+                if context is not None:
+                    print(f"{context}: Restored training weights")
+
+    def on_train_batch_end(self, *args, **kwargs):
+        """ddpm.py:370-372 (a no-op once the shadows are bound to optim.FusedAdamWEMA, whose kernel updates them)."""
+        if self.use_ema and self.model_ema._fused is None:
+            self.model_ema(self.model)
+
+    def configure_optimizers(self):
+        """ddpm.py:1409-1431: AdamW over the UNet (+ the conditioner when trainable, + logvar when learned)."""
+        params = list(self.model.parameters())
+        if self.cond_stage_trainable:
+            params = params + list(self.cond_stage_model.parameters())
+        if self.learn_logvar:
+            params.append(self.logvar)
+        opt = torch.optim.AdamW(params, lr=self.learning_rate)
+        if self.use_scheduler:
+            from torch.optim.lr_scheduler import LambdaLR
+            scheduler = instantiate_from_config(self.scheduler_config)
+            return [opt], [{"scheduler": LambdaLR(opt, lr_lambda=scheduler.schedule), "interval": "step", "frequency": 1}]
+        return opt
 
     # ---- conditioning / first stage -------------------------------------------------------------------
     def get_learned_conditioning(self, c):
@@ -234,8 +286,67 @@ class LatentDiffusion(nn.Module):
     @torch.no_grad()
     def decode_first_stage(self, z, predict_cids=False, force_not_quantize=False):
         """ddpm.py:713-771 (no split_input_params tiling, which EALDM's configs never set)."""
+        if predict_cids:                                   # ddpm.py:715-719
+            if z.dim() == 4:
+                z = torch.argmax(z.exp(), dim=1).long()
+            z = self.first_stage_model.quantize.get_codebook_entry(z, shape=None)
+            z = z.permute(0, 3, 1, 2).contiguous()
         z = 1. / self.scale_factor * z
+        if hasattr(self.first_stage_model, "quantize") and not isinstance(self.first_stage_model, IdentityFirstStage):
+            # VQModelInterface (ddpm.py:768-769): callers may ask for the un-quantised latent
+            return self.first_stage_model.decode(z, force_not_quantize=predict_cids or force_not_quantize)
         return self.first_stage_model.decode(z)
+
+    # ---- data plumbing of the trainer (ddpm.py:330-343, 662-711, 873-876) ----------------------------------------
+    def _get_input_base(self, batch, k):
+        x = batch[k]
+        if len(x.shape) == 3:
+            x = x[..., None]
+        elif len(x.shape) == 5:
+            x = x.squeeze(0)
+        return x.to(memory_format=torch.contiguous_format).float()
+
+    @torch.no_grad()
+    def get_input(self, batch, k, return_first_stage_outputs=False, force_c_encode=False, cond_key=None,
+                  return_original_cond=False, bs=None):
+        x = self._get_input_base(batch, k)
+        if bs is not None:
+            x = x[:bs]
+        x = x.to(self.device)
+        z = self.get_first_stage_encoding(self.encode_first_stage(x)).detach()
+        c, xc = None, None
+        if self.model.conditioning_key is not None:
+            cond_key = self.cond_stage_key if cond_key is None else cond_key
+            if cond_key != self.first_stage_key:
+                if cond_key in ("caption", "coordinates_bbox", "mixed"):
+                    xc = batch[cond_key]
+                elif cond_key == "class_label":
+                    xc = batch
+                else:
+                    xc = self._get_input_base(batch, cond_key).to(self.device)
+            else:
+                xc = x
+            if not self.cond_stage_trainable or force_c_encode:
+                c = self.get_learned_conditioning(xc if isinstance(xc, (dict, list)) else xc.to(self.device))
+            else:
+                c = xc
+            if bs is not None:
+                c = c[:bs]
+        out = [z, c]
+        if return_first_stage_outputs:
+            out.extend([x, self.decode_first_stage(z)])
+        if return_original_cond:
+            out.append(xc)
+        return out
+
+    def shared_step(self, batch, **kwargs):
+        x, c = self.get_input(batch, self.first_stage_key)
+        return self(x, c)
+
+    def training_step(self, batch, batch_idx=0):
+        """ddpm.py:345-358 without the Lightning logging calls."""
+        loss, _ = self.shared_step(batch)
+        return loss
 
     # ---- denoiser ---------------------------------------------------------------------------------------
     def apply_model(self, x_noisy, t, cond, return_ids=False):
@@ -259,8 +370,23 @@ class LatentDiffusion(nn.Module):
                             self.sqrt_alphas_cumprod, self.sqrt_one_minus_alphas_cumprod)
 
     def forward(self, x, c, *args, **kwargs):
-        """ddpm.py:878-900 for an already encoded conditioning `c` = cat([c_neg, c]) (2B rows)."""
+        """ddpm.py:878-900.  With a trainable conditioner `c` is the raw `batch['mixed']` list: the NEGATIVE conditioning
+        is the same list with the frames replaced by its last entry (the negative frames) and that entry set to None
+        (ddpm.py:886-888), both go through the conditioner and the UNet sees cat([c_neg, c]).  With a frozen conditioner
+        `c` is already encoded (get_input) -- for the guided loss the caller passes cat([c_neg, c]) (2B rows)."""
         t = torch.randint(0, self.num_timesteps, (x.shape[0],), device=self.device).long()
+        if self.model.conditioning_key is not None:
+            assert c is not None
+            if self.cond_stage_trainable:
+                if self.unconditional_guidance_scale != 1.:
+                    c_neg = copy.copy(c) if isinstance(c, list) else copy.deepcopy(c)
+                    c_neg[0] = c_neg[-1]
+                    c_neg[-1] = None
+                    c_neg = self.get_learned_conditioning(c_neg)
+                    c = self.get_learned_conditioning(c)
+                    c = torch.cat([c_neg, c])
+                else:
+                    c = self.get_learned_conditioning(c)
         return self.p_losses(x, c, t, *args, **kwargs)
 
     def p_losses(self, x_start, cond, t, noise=None):
@@ -312,6 +438,7 @@ class LatentDiffusion(nn.Module):
         """ddpm.py:1190-1247.  `noises` (not in the reference): per-iteration noise tensors for tests."""
         log_every_t = log_every_t or self.log_every_t
         device = self.betas.device
+        revalidate_packed(self)
         b = shape[0]
         img = torch.randn(shape, device=device) if x_T is None else x_T
         intermediates = [img]

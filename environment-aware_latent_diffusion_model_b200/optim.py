@@ -24,6 +24,7 @@ class FusedAdamWEMA:
                  use_num_updates: bool = True):
         self.buckets = buckets
         self.params = buckets.params
+        self.unet = getattr(buckets, "unet", None)      # whose packed inference weights every update invalidates
         self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
         self.ema_decay, self.use_ema = ema_decay, use_ema
         self.step_count = 0
@@ -46,9 +47,15 @@ class FusedAdamWEMA:
         for p, off in zip(self.params, self.buckets.offsets):
             p._bf16_view = self.flat_bf16[off:off + p.numel()].view_as(p)
 
+    def _invalidate(self):
+        """The UNet caches kernel-layout weights (and CUDA graphs over them) for inference; they are stale now."""
+        if self.unet is not None:
+            self.unet.invalidate_packed()
+
     def refresh(self):
         """Call after changing parameters outside `step()` (load_state_dict, manual edits)."""
         self.flat_bf16.copy_(self.flat_param)
+        self._invalidate()
 
     def zero_grad(self):
         self.buckets.zero_()
@@ -72,6 +79,44 @@ class FusedAdamWEMA:
         a.grad_scale = 1.0 / self.buckets.world if grads_are_sums else 1.0
         a.ema_decay = decay
         L.check(L.load().ealdm_adamw_ema_step(C.byref(a), torch.cuda.current_stream().cuda_stream))
+        self._invalidate()
+
+    # ---- checkpointing: the per-parameter layout of torch.optim.AdamW.state_dict() ------------------------------
+    def state_dict(self) -> dict:
+        """Same structure as `torch.optim.AdamW(params).state_dict()` over `self.params` (in this optimizer's
+        parameter order): state[i] = {step, exp_avg, exp_avg_sq}, one param group with the hyper-parameters; plus
+        `ema` = {num_updates, decay} (the EMA shadow itself is checkpointed as `model_ema.*` by ema.LitEma.bind)."""
+        state = {}
+        for i, (p, off) in enumerate(zip(self.params, self.buckets.offsets)):
+            n = p.numel()
+            state[i] = {"step": torch.tensor(float(self.step_count)),
+                        "exp_avg": self.exp_avg[off:off + n].view_as(p).clone(),
+                        "exp_avg_sq": self.exp_avg_sq[off:off + n].view_as(p).clone()}
+        group = {"lr": self.lr, "betas": tuple(self.betas), "eps": self.eps, "weight_decay": self.weight_decay,
+                 "amsgrad": False, "params": list(range(len(self.params)))}
+        return {"state": state, "param_groups": [group],
+                "ema": {"num_updates": self.num_updates, "decay": self.ema_decay}}
+
+    @torch.no_grad()
+    def load_state_dict(self, sd: dict) -> None:
+        group = sd["param_groups"][0]
+        assert len(group["params"]) == len(self.params), "optimizer state does not match the parameter list"
+        self.lr, self.betas = group["lr"], tuple(group["betas"])
+        self.eps, self.weight_decay = group["eps"], group["weight_decay"]
+        steps = set()
+        for i, (p, off) in enumerate(zip(self.params, self.buckets.offsets)):
+            st = sd["state"].get(i, sd["state"].get(str(i)))
+            if st is None:
+                continue
+            n = p.numel()
+            self.exp_avg[off:off + n].copy_(st["exp_avg"].reshape(-1))
+            self.exp_avg_sq[off:off + n].copy_(st["exp_avg_sq"].reshape(-1))
+            steps.add(int(st["step"]))
+        assert len(steps) <= 1, "per-parameter step counts differ: not a state this fused optimizer can resume"
+        self.step_count = steps.pop() if steps else 0
+        if "ema" in sd:
+            self.num_updates, self.ema_decay = sd["ema"]["num_updates"], sd["ema"]["decay"]
+        self.refresh()      # parameters may have been loaded just before: rebuild the bf16 copy, drop packed weights
 
     # ---- LitEma interface (ema.py:46-76) ----------------------------------------------------------------------
     def ema_views(self) -> Dict[int, torch.Tensor]:

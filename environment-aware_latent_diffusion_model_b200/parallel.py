@@ -69,6 +69,7 @@ class GradBuckets:
 
     def __init__(self, unet, bucket_mb: float = 64.0, group=None):
         self.group = group
+        self.unet = unet
         self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
         late_keys = ("time_embed.", ".emb_layers.", ".in_layers.2.bias", ".attn2.to_k.", ".attn2.to_v.")
         names = {id(p): n for n, p in unet.named_parameters()}

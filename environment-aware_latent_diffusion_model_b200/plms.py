@@ -12,6 +12,7 @@ import torch
 
 from . import ops
 from .ddim import DDIMSampler
+from .util import revalidate_packed
 
 
 class PLMSSampler(DDIMSampler):
@@ -33,6 +34,7 @@ class PLMSSampler(DDIMSampler):
             if cbs != batch_size:
                 print(f"Warning: Got {cbs} conditionings but batch-size is {batch_size}")
         self.make_schedule(ddim_num_steps=S, ddim_eta=eta, verbose=verbose)
+        revalidate_packed(self.model)
         C, H, W = shape
         return self.plms_sampling(conditioning, (batch_size, C, H, W), callback=callback, img_callback=img_callback,
                                   mask=mask, x0=x0, temperature=temperature, x_T=x_T, log_every_t=log_every_t,

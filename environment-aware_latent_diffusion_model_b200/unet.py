@@ -246,6 +246,38 @@ class UNetModel(nn.Module):
         self._engine = None
         self._graphs = {}
 
+    # The packed weights (and the CUDA graphs over them) are a cache of the parameters.  `load_state_dict`, `_apply`,
+    # optim.FusedAdamWEMA and ema.LitEma invalidate it explicitly; every eval forward additionally compares the
+    # parameters' autograd version counters (bumped by torch optimizers and any in-place op; no device sync), and
+    # `revalidate_packed()` -- called by the samplers once per `sample()` -- compares a content probe, which also
+    # catches writes through `.data` (the reference's LitEma.copy_to, ema.py:46-53).
+    def _version_fingerprint(self) -> int:
+        return sum(p._version for p in self._plist)
+
+    def _content_probe(self) -> torch.Tensor:
+        with torch.no_grad():
+            return torch.stack([p.detach().reshape(-1)[0].float() for p in self._plist[::8]])   # views + ONE kernel
+
+    def revalidate_packed(self) -> bool:
+        """True if the cached engine still matches the parameters; otherwise drops it (one device sync)."""
+        if self._engine is None or torch.cuda.is_current_stream_capturing():
+            return True
+        if self._version_fingerprint() == self._engine_fp and torch.equal(self._content_probe(), self._engine_probe):
+            return True
+        self.invalidate_packed()
+        return False
+
+    def _get_engine(self) -> "UNetEngine":
+        if self._engine is not None and self._version_fingerprint() != self._engine_fp:
+            self.invalidate_packed()
+        if self._engine is None:
+            self._plist = list(self.parameters())
+            self._engine = UNetEngine(self, self._compute_dtype)
+            self._engine_fp = self._version_fingerprint()
+            if not torch.cuda.is_current_stream_capturing():
+                self._engine_probe = self._content_probe()
+        return self._engine
+
     def enable_cuda_graph(self, flag: bool = True) -> "UNetModel":
         """Replay the forward pass (~300 kernel launches) as ONE CUDA graph per input shape.  The
         launch sequence has no host synchronisation or data-dependent control flow, so capture is
@@ -301,11 +333,10 @@ class UNetModel(nn.Module):
             # training step: forward with saved activations + hand-written backward (train.py)
             from .train import unet_forward_train
             return unet_forward_train(self, x, timesteps, context)
-        if self._engine is None:
-            self._engine = UNetEngine(self, self._compute_dtype)
+        engine = self._get_engine()
         if self.use_cuda_graph and not torch.cuda.is_current_stream_capturing():
             return self._forward_graphed(x, timesteps, context)
-        return self._engine.forward(x, timesteps, context)
+        return engine.forward(x, timesteps, context)
 
 
 # ---- execution engine --------------------------------------------------------------------------------

@@ -93,3 +93,13 @@ def noise_like(shape, device, repeat=False):
     if repeat:
         return torch.randn((1, *shape[1:]), device=device).repeat(shape[0], *((1,) * (len(shape) - 1)))
     return torch.randn(shape, device=device)
+
+
+def revalidate_packed(model) -> None:
+    """Called by the samplers once per `sample()`: every sub-module that caches kernel-layout weights re-checks them
+    against its parameters (catches in-place writes through `.data`, e.g. the reference's LitEma.copy_to)."""
+    mods = model.modules() if hasattr(model, "modules") else ()
+    for m in mods:
+        fn = getattr(m, "revalidate_packed", None)
+        if callable(fn):
+            fn()

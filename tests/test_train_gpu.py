@@ -197,3 +197,116 @@ def test_fused_adamw_ema_matches_torch_adamw_and_litema():
         assert torch.equal(p._bf16_view, p.detach().to(torch.bfloat16)), n
     print(f"fused AdamW+EMA vs torch: worst rel_l2 {worst:.3e}")
     assert worst < 1e-6
+
+
+def test_eval_forward_after_weight_updates_uses_the_new_weights():
+    """the packed inference engine (and its CUDA graphs) is a cache of the parameters.  After an optimizer
+    step (version counters), a write through `.data` + revalidate_packed() (the reference LitEma.copy_to path) and
+    FusedAdamWEMA.step(), an eval forward must equal the forward of a freshly packed engine."""
+    from ealdm_b200.optim import FusedAdamWEMA
+    from ealdm_b200.parallel import GradBuckets
+    from ealdm_b200.unet import UNetModel
+    tiny = dict(image_size=8, in_channels=4, model_channels=64, out_channels=4, num_res_blocks=1,
+                attention_resolutions=[1, 2], channel_mult=(1, 2), num_head_channels=32,
+                use_spatial_transformer=True, transformer_depth=1, context_dim=64)
+    torch.manual_seed(0)
+    unet = UNetModel(**tiny).cuda().eval().enable_cuda_graph(True)
+    with torch.no_grad():
+        for p in unet.parameters():      # the zero-initialised output convs would hide every upstream change
+            if p.dim() >= 2 and float(p.abs().max()) == 0.0:
+                p.normal_(std=0.05)
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 4, 8, 8, generator=g).cuda()
+    c = torch.randn(2, 4, 64, generator=g).cuda()
+    t = torch.tensor([5, 900]).cuda()
+
+    def fresh():
+        m = UNetModel(**tiny).cuda().eval()
+        m.load_state_dict(unet.state_dict())
+        return m(x, t, context=c)
+
+    y0 = unet(x, t, context=c)
+    y0 = unet(x, t, context=c)           # graph replay
+    assert torch.equal(y0, fresh())
+    # (1) a torch optimizer step: caught by the version counters on the next forward
+    opt = torch.optim.SGD(unet.parameters(), lr=0.05)
+    for p in unet.parameters():
+        p.grad = torch.ones_like(p)
+    opt.step()
+    y1 = unet(x, t, context=c)
+    assert not torch.equal(y1, y0) and torch.equal(y1, fresh())
+    # (2) a write through .data (invisible to version counters): caught by the samplers' revalidate_packed()
+    with torch.no_grad():
+        for p in unet.parameters():
+            p.data.mul_(1.01)
+    assert unet.revalidate_packed() is False
+    y2 = unet(x, t, context=c)
+    assert not torch.equal(y2, y1) and torch.equal(y2, fresh())
+    assert unet.revalidate_packed() is True
+    # (3) the fused optimizer invalidates explicitly
+    for p in unet.parameters():
+        p.grad = None
+    gb = GradBuckets(unet, bucket_mb=1.0)
+    fopt = FusedAdamWEMA(gb, lr=1e-2)
+    y3 = unet(x, t, context=c)
+    gb.flat.fill_(0.5)
+    fopt.step()
+    assert unet._engine is None
+    y4 = unet(x, t, context=c)
+    assert not torch.equal(y4, y3) and torch.equal(y4, fresh())
+    # (4) EMA weights: copy_to / restore drop the packed weights as well
+    fopt.store()
+    fopt.copy_to()
+    y5 = unet(x, t, context=c)
+    assert torch.equal(y5, fresh()) and not torch.equal(y5, y4)
+    fopt.restore()
+    assert torch.equal(unet(x, t, context=c), y4)
+
+
+def test_fused_optimizer_and_ema_checkpoint_round_trip():
+    """FusedAdamWEMA.state_dict() has torch.optim.AdamW's per-parameter layout; LitEma.bind() exposes the fused EMA
+    buffer as `model_ema.*` (the reference's checkpoint keys); a resumed run continues bit-identically."""
+    from ealdm_b200.ema import LitEma
+    from ealdm_b200.optim import FusedAdamWEMA
+    from ealdm_b200.parallel import GradBuckets
+    from ealdm_b200.unet import UNetModel
+    tiny = dict(image_size=8, in_channels=4, model_channels=64, out_channels=4, num_res_blocks=1,
+                attention_resolutions=[1, 2], channel_mult=(1, 2), num_head_channels=32,
+                use_spatial_transformer=True, transformer_depth=1, context_dim=64)
+
+    def make(seed):
+        torch.manual_seed(seed)
+        unet = UNetModel(**tiny).cuda()
+        gb = GradBuckets(unet, bucket_mb=1.0)
+        opt = FusedAdamWEMA(gb, lr=3e-4)
+        ema = LitEma(unet).cuda().bind(opt, unet)
+        return unet, gb, opt, ema
+
+    def steps(gb, opt, n, seed):
+        gen = torch.Generator(device="cuda").manual_seed(seed)
+        for _ in range(n):
+            gb.flat.copy_(torch.randn(gb.flat.shape, generator=gen, device="cuda") * 0.1)
+            opt.step()
+
+    unet, gb, opt, ema = make(0)
+    steps(gb, opt, 3, 11)
+    ck = {"model": {k: v.clone() for k, v in unet.state_dict().items()}, "ema": ema.state_dict(), "opt": opt.state_dict()}
+    ck["ema"] = {k: v.clone() for k, v in ck["ema"].items()}
+    ref_sd = torch.optim.AdamW(unet.parameters()).state_dict()
+    assert set(ck["opt"]["param_groups"][0]) >= {"lr", "betas", "eps", "weight_decay", "params"}
+    assert ck["opt"]["param_groups"][0]["params"] == ref_sd["param_groups"][0]["params"]
+    assert set(ck["opt"]["state"][0]) == {"step", "exp_avg", "exp_avg_sq"}
+    assert int(ck["ema"]["num_updates"]) == 3 and len(ck["ema"]) == len(list(unet.parameters())) + 2
+    steps(gb, opt, 2, 12)                 # the continued run
+    want = {k: v.clone() for k, v in unet.state_dict().items()}
+    want_ema = opt.ema.clone()
+    # resume from the checkpoint in a new process' worth of objects
+    unet2, gb2, opt2, ema2 = make(1)
+    unet2.load_state_dict(ck["model"])
+    ema2.load_state_dict(ck["ema"])
+    opt2.load_state_dict(ck["opt"])
+    assert opt2.step_count == 3 and opt2.num_updates == 3
+    steps(gb2, opt2, 2, 12)
+    for k, v in unet2.state_dict().items():
+        assert torch.equal(v, want[k]), k
+    assert torch.equal(opt2.ema, want_ema)
