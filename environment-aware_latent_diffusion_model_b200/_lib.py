@@ -20,7 +20,7 @@ TC_OPT_CTA2, TC_OPT_WIDE, TC_OPT_RELAXED_WAIT, TC_OPT_BN = 0, 1, 2, 3
 
 EXPORTS = [
     "ealdm_abi_version", "ealdm_last_error", "ealdm_device_check", "ealdm_launch_count", "ealdm_tc_set_option",
-    "ealdm_conv", "ealdm_group_norm", "ealdm_group_norm_workspace_bytes", "ealdm_layer_norm", "ealdm_attention",
+    "ealdm_conv", "ealdm_ff_geglu_fused", "ealdm_group_norm", "ealdm_group_norm_workspace_bytes", "ealdm_layer_norm", "ealdm_attention",
     "ealdm_timestep_embedding", "ealdm_nchw_to_nhwc", "ealdm_nhwc_to_nchw",
     "ealdm_upsample_nearest2x", "ealdm_copy2d", "ealdm_softmax_rows", "ealdm_ddim_step",
     "ealdm_q_sample", "ealdm_cfg_mse",
@@ -50,7 +50,7 @@ class ConvArgs(C.Structure):
                 ("residual", C.c_void_p), ("ld_res", C.c_int64), ("out", C.c_void_p),
                 ("ld_out", C.c_int64), ("out_f32", C.c_int32), ("res_f32", C.c_int32),
                 ("out2", C.c_void_p), ("ld_out2", C.c_int64), ("gn_partial", C.c_void_p), ("gn_ld", C.c_int64),
-                ("weight_adjoint", C.c_int32), ("reserved2", C.c_int32), ("ld_weight", C.c_int64)]
+                ("weight_adjoint", C.c_int32), ("upsample_phases", C.c_int32), ("ld_weight", C.c_int64)]
 
 
 class GroupNormArgs(C.Structure):
@@ -59,6 +59,13 @@ class GroupNormArgs(C.Structure):
                 ("eps", C.c_float), ("gamma", C.c_void_p), ("beta", C.c_void_p), ("y", C.c_void_p),
                 ("ld_y", C.c_int64), ("workspace", C.c_void_p), ("x_f32", C.c_int32), ("reserved", C.c_int32),
                 ("stats_out", C.c_void_p), ("partial", C.c_void_p), ("partial_ld", C.c_int64)]
+
+
+class FfFusedArgs(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("rows", C.c_int64), ("ld_x", C.c_int64), ("c", C.c_int64), ("hidden", C.c_int64),
+                ("w1", C.c_void_p), ("b1", C.c_void_p), ("w2", C.c_void_p), ("b2", C.c_void_p),
+                ("residual", C.c_void_p), ("ld_res", C.c_int64), ("out", C.c_void_p), ("ld_out", C.c_int64),
+                ("out_f32", C.c_int32), ("reserved", C.c_int32)]
 
 
 class LayerNormArgs(C.Structure):
@@ -178,6 +185,7 @@ def _declare(lib):
         ("ealdm_conv", [C.POINTER(ConvArgs), vp]),
         ("ealdm_group_norm", [C.POINTER(GroupNormArgs), vp]),
         ("ealdm_layer_norm", [C.POINTER(LayerNormArgs), vp]),
+        ("ealdm_ff_geglu_fused", [C.POINTER(FfFusedArgs), vp]),
         ("ealdm_attention", [C.POINTER(AttentionArgs), vp]),
         ("ealdm_timestep_embedding", [vp, i64, i32, vp, i32, vp, vp]),
         ("ealdm_nchw_to_nhwc", [vp, i64, i64, i64, i64, i32, vp, i64, vp]),

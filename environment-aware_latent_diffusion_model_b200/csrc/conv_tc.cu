@@ -33,6 +33,7 @@
 // is a full 128-byte (fp32) or 64-byte (bf16) row segment, and M / N edges are clipped by the TMA unit.
 #include "common.cuh"
 #include "ptx.cuh"
+#include "tc_math.cuh"
 
 #include <cuda.h>
 #include <cudaTypedefs.h>
@@ -86,6 +87,14 @@ struct Params {
   // wide epilogue passes (BN = 256, no residual, no shadow): every warp fills [32 rows x 128 B] boxes for 64 (fp32) or
   // 128 (bf16) columns and pays ONE wait / fence / store-issue sequence for them instead of one per 32 columns
   int wide;
+  // nearest-2x upsampling folded into the convolution (phases = 4, else 1): output pixel (2y + py, 2x + px) of a 3x3
+  // convolution over the upsampled image only sees input rows {y + py - 1, y + py} and columns {x + px - 1, x + px},
+  // so each of the four output phases is a 2x2 convolution over the LOW-resolution input with pre-summed weights
+  // (4/9 of the FLOPs, and the 4x larger upsampled tensor is never written or read).  A work item is (phase, M tile
+  // of the low-resolution grid, N tile); the weights of phase p are the K columns [p * 4C, (p + 1) * 4C); the output
+  // (and its shadow) is addressed through 5-D tensor maps (C, px, W/2, py, N * H/2).
+  int phases;
+  int gn_phase_chunks;  // 32-pixel chunks of the low-resolution grid per image: phase p fills chunks [p * this, ...)
 };
 
 // CTA2: the tile is 256 x BN over a CTA pair (cta_group::2); each CTA stages its 128 A rows and BN/2 B rows
@@ -107,140 +116,9 @@ struct Cfg {
   static_assert(EPI_OFF % 1024 == 0 && EPI_WARP_BYTES % 1024 == 0 && BAR_OFF % 8 == 0, "alignment");
 };
 
-// ---- shared-memory unit buffers ---------------------------------------------------------------------
-// A unit is 32 rows; fp32 rows are 128 B with the TMA 128-byte swizzle (16-byte chunk j of row r lives
-// at chunk j ^ (r & 7)), bf16 rows are 64 B with the 64-byte swizzle (chunk j ^ ((r >> 1) & 3)).  One
-// thread touches one row, so each quarter-warp phase covers 8 distinct 16-byte bank groups.
-__device__ __forceinline__ void lds_row_f32(const uint8_t* buf, int lane, float (&r)[32]) {
-  const uint8_t* row = buf + lane * 128;
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const float4 t = *reinterpret_cast<const float4*>(row + ((j ^ (lane & 7)) << 4));
-    r[4 * j] = t.x; r[4 * j + 1] = t.y; r[4 * j + 2] = t.z; r[4 * j + 3] = t.w;
-  }
-}
-__device__ __forceinline__ void sts_row_f32(uint8_t* buf, int lane, const float (&v)[32]) {
-  uint8_t* row = buf + lane * 128;
-#pragma unroll
-  for (int j = 0; j < 8; ++j)
-    *reinterpret_cast<float4*>(row + ((j ^ (lane & 7)) << 4)) =
-        make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-}
-__device__ __forceinline__ uint32_t pack2_bf16(float lo, float hi) {
-  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<uint32_t*>(&t);
-}
-__device__ __forceinline__ void lds_row_bf16(const uint8_t* buf, int lane, float (&r)[32]) {
-  const uint8_t* row = buf + lane * 64;
-  const int sw = (lane >> 1) & 3;
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const uint4 u = *reinterpret_cast<const uint4*>(row + ((j ^ sw) << 4));
-    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      r[8 * j + 2 * e] = __uint_as_float(w[e] << 16);
-      r[8 * j + 2 * e + 1] = __uint_as_float(w[e] & 0xffff0000u);
-    }
-  }
-}
-// 8 consecutive bf16 (one 16-byte chunk `j` of row `lane`)
-__device__ __forceinline__ void sts_chunk_bf16(uint8_t* buf, int lane, int j, const float* v) {
-  uint4 u;
-  u.x = pack2_bf16(v[0], v[1]);
-  u.y = pack2_bf16(v[2], v[3]);
-  u.z = pack2_bf16(v[4], v[5]);
-  u.w = pack2_bf16(v[6], v[7]);
-  *reinterpret_cast<uint4*>(buf + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = u;
-}
-// 8 consecutive bf16 into 16-byte chunk j (0..7) of row `lane` of a [32 rows x 128 B] SWIZZLE_128B box
-__device__ __forceinline__ void sts_chunk_bf16_sw128(uint8_t* buf, int lane, int j, const float* v) {
-  uint4 u;
-  u.x = pack2_bf16(v[0], v[1]);
-  u.y = pack2_bf16(v[2], v[3]);
-  u.z = pack2_bf16(v[4], v[5]);
-  u.w = pack2_bf16(v[6], v[7]);
-  *reinterpret_cast<uint4*>(buf + lane * 128 + ((j ^ (lane & 7)) << 4)) = u;
-}
-__device__ __forceinline__ void sts_row_bf16(uint8_t* buf, int lane, const float (&v)[32]) {
-#pragma unroll
-  for (int j = 0; j < 4; ++j) sts_chunk_bf16(buf, lane, j, &v[8 * j]);
-}
-
-// exact-erf GELU for the bf16 tensor-core path: erf by Abramowitz-Stegun 7.1.28,
-//   erf(x) = 1 - (1 + a1 x + ... + a6 x^6)^-16,  |error| <= 3e-7 (1.7e-6 in fp32 arithmetic),
-// far below bf16 resolution; ONE MUFU (rcp) per element instead of erff's branches.  The fp32 parity
-// path (conv_simt.cu) keeps erff.
-//
-// The GEGLU epilogue is bound by instruction issue (ncu: 62 % issue-active from the 8 epilogue warps, 24
-// instructions per output), so the arithmetic runs on PAIRS of fp32 values with the packed sm_100 instructions
-// (FFMA2 / FMUL2 / FADD2: one issue slot for two lanes).  With z = -|g| and the 1/sqrt(2) of erf(g/sqrt(2))
-// folded into the coefficients, p = 1 - b1 z + b2 z^2 - ... (Horner in z), r = p^-16 and
-//   gelu(g) = g Phi(g) = 0.5 ((g + |g|) - |g| r) = 0.5 ((g - z) + z r),
-// the 0.5 being folded into the value operand ((0.5 v + 0.5 bias_v), bias pre-halved in shared memory).
-__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
-  uint64_t r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ void upk2(uint64_t v, float& lo, float& hi) {
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
-  uint64_t r;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-  return r;
-}
-__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
-  uint64_t r;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
-__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
-  uint64_t r;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
-__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) {
-  uint64_t r;
-  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
-__device__ __forceinline__ float rcp_approx(float x) {
-  float r;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return r;
-}
-// (value pair) * gelu(gate pair); `val` already holds 0.5 * (v + bias_v), `g` holds gate + bias_g
-__device__ __forceinline__ uint64_t geglu2(uint64_t val, uint64_t g) {
-  constexpr float S = 0.70710678118654752440f;
-  constexpr float B1 = -0.0705230784f * S;
-  constexpr float B2 = 0.0422820123f * S * S;
-  constexpr float B3 = -0.0092705272f * S * S * S;
-  constexpr float B4 = 0.0001520143f * S * S * S * S;
-  constexpr float B5 = -0.0002765672f * S * S * S * S * S;
-  constexpr float B6 = 0.0000430638f * S * S * S * S * S * S;
-  float g0, g1;
-  upk2(g, g0, g1);
-  const uint64_t z = pk2(__uint_as_float(__float_as_uint(g0) | 0x80000000u),
-                         __uint_as_float(__float_as_uint(g1) | 0x80000000u));
-  uint64_t p = fma2(pk2(B6, B6), z, pk2(B5, B5));
-  p = fma2(p, z, pk2(B4, B4));
-  p = fma2(p, z, pk2(B3, B3));
-  p = fma2(p, z, pk2(B2, B2));
-  p = fma2(p, z, pk2(B1, B1));
-  p = fma2(p, z, pk2(1.0f, 1.0f));
-  float p0, p1;
-  upk2(p, p0, p1);
-  uint64_t r = pk2(rcp_approx(p0), rcp_approx(p1));
-  r = mul2(r, r); r = mul2(r, r); r = mul2(r, r); r = mul2(r, r);
-  const uint64_t u = fma2(z, r, sub2(g, z));
-  return mul2(val, u);
-}
-
 // GroupNorm partial statistics of one [32 pixels x 32 channels] unit held one row per lane (see Params::gn_partial)
 __device__ __forceinline__ void gn_partial_unit(const Params& p, const float (&r)[32], int lane, bool valid, int n,
-                                                int h, int w, int col0) {
+                                                int h, int w, int col0, int chunk0 = 0) {
   // {sum, sum of squares} of the 4 channel octets of this unit over the warp's 32 pixel rows (one 32-pixel
   // chunk of one image): 8 values per thread, folded across the lanes in a fixed order with 9 shuffles
   float v8[8];
@@ -273,7 +151,7 @@ __device__ __forceinline__ void gn_partial_unit(const Params& p, const float (&r
   v8[0] += __shfl_xor_sync(0xffffffffu, v8[0], 1);
   if ((lane & 3) == 0 && n < p.Nimg && col0 < p.N) {
     const int vi = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);  // value index 0..7
-    const int chunk = (h * p.Wout + w) >> 5;
+    const int chunk = chunk0 + ((h * p.Wout + w) >> 5);
     float* dst = reinterpret_cast<float*>(p.gn_partial + (static_cast<long long>(n) * p.gn_chunks + chunk) * p.gn_ld +
                                           (col0 >> 3) + (vi >> 1));
     dst[vi & 1] = v8[0];
@@ -341,12 +219,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   // work items: tiles (one CTA each) or, for CTA pairs, super-tiles of two consecutive M tiles and one N tile
   const int tile_first = CTA2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
   const int tile_step = CTA2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
-  const int total_tiles = (CTA2 ? (p.m_tiles + 1) / 2 : p.m_tiles) * p.n_tiles;
+  const int total_tiles = (CTA2 ? (p.m_tiles + 1) / 2 : p.m_tiles) * p.n_tiles * p.phases;
   const int kblocks_total = p.seg[0].kblocks + (p.nseg > 1 ? p.seg[1].kblocks : 0);
-  auto tile_mn = [&](int tile, int& mt, int& nt) {
-    const int q = tile / p.n_tiles;
+  // tile -> (M tile, N tile, upsampling phase); the phases of one M tile are neighbours (they read the same input)
+  auto tile_mnp = [&](int tile, int& mt, int& nt, int& phase) {
+    int q = tile / p.n_tiles;
     nt = tile - q * p.n_tiles;
+    phase = 0;
+    if (p.phases > 1) {
+      phase = q & 3;
+      q >>= 2;
+    }
     mt = CTA2 ? 2 * q + static_cast<int>(cta_rank) : q;  // mt == m_tiles (odd tail): every box is out of range
+  };
+  auto tile_mn = [&](int tile, int& mt, int& nt) {
+    int phase;
+    tile_mnp(tile, mt, nt, phase);
   };
 
   if (warp == 0) {
@@ -356,12 +244,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       uint32_t phase = 0;
       const uint32_t full0 = CTA2 ? ptx::mapa_u32(&full_bar[0], 0) : 0u;  // the leader's full barriers
       for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
-        int mt, nt;
-        tile_mn(tile, mt, nt);
+        int mt, nt, uph;   // (`phase` is the mbarrier parity of the ring in this role)
+        tile_mnp(tile, mt, nt, uph);
         const int tw = mt % p.tiles_w;
         const int th = (mt / p.tiles_w) % p.tiles_h;
         const int tn = mt / (p.tiles_w * p.tiles_h);
-        const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn;
+        // an upsampling phase shifts the 2x2 taps by (py, px) and selects its own K columns of W
+        const int w0 = tw * p.bw + (uph & 1), h0 = th * p.bh + (uph >> 1), n0 = tn * p.bn;
+        const int pkoff = uph * p.seg[0].kblocks * BK;
         for (int s = 0; s < p.nseg; ++s) {
           const Segment sg = p.seg[s];
           const CUtensorMap* tmA = (s == 0) ? &tmA0 : &tmA1;
@@ -384,7 +274,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 for (int g = 0; g < BN / 128; ++g)
                   ptx::tma_load_2d_2sm(sa + C::A_BYTES + g * 8192, &tmB, fb, tcol + g * 64, cb * BK);
               } else {
-                ptx::tma_load_2d_2sm(sa + C::A_BYTES, &tmB, fb, sg.bkoff + kb * BK,
+                ptx::tma_load_2d_2sm(sa + C::A_BYTES, &tmB, fb, sg.bkoff + pkoff + kb * BK,
                                      nt * BN + static_cast<int>(cta_rank) * (BN / 2));
               }
               if (++cb == sg.cblk) { cb = 0; ++tap; }
@@ -401,7 +291,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
               for (int g = 0; g < BN / 64; ++g)
                 ptx::tma_load_2d(sa + C::A_BYTES + g * 8192, &tmB, &full_bar[stage], tcol + g * 64, cb * BK);
             } else {
-              ptx::tma_load_2d(sa + C::A_BYTES, &tmB, &full_bar[stage], sg.bkoff + kb * BK, nt * BN);
+              ptx::tma_load_2d(sa + C::A_BYTES, &tmB, &full_bar[stage], sg.bkoff + pkoff + kb * BK, nt * BN);
             }
             if (++cb == sg.cblk) { cb = 0; ++tap; }
             if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
@@ -902,8 +792,31 @@ bool supported(const ealdm_conv_args* a) {
         (a->h_out & (a->h_out - 1)) != 0 || a->n_out % 32 != 0)
       return false;
     if (a->w_out < 32 && (32 % a->w_out != 0 || a->h_out % (32 / a->w_out) != 0)) return false;
+    if (a->upsample_phases) {  // the 32-pixel chunks are those of the low-resolution grid
+      const long long wl = a->w_out / 2, hl = a->h_out / 2;
+      if (wl < 32 && (32 % wl != 0 || hl % (32 / wl) != 0)) return false;
+    }
   }
   return true;
+}
+
+// 5-D (C, px, W/2, py, N * H/2) view of an NHWC tensor at the upsampled resolution: the pixels of one output phase
+// (py, px) form a regular sub-grid, so a [32 columns x sub_w x sub_h] unit of the LOW-resolution grid is one TMA box
+static int encode_phase_map(PFN_cuTensorMapEncodeTiled_v12000 encode, CUtensorMap* tm, const void* base, bool f32,
+                            long long cols, long long ld, const ealdm_conv_args* a, const int (&sub)[3]) {
+  const cuuint64_t es = f32 ? 4 : 2;
+  const cuuint64_t wl = static_cast<cuuint64_t>(a->w_out / 2), hl = static_cast<cuuint64_t>(a->h_out / 2);
+  const cuuint64_t pix = static_cast<cuuint64_t>(ld) * es;  // bytes between horizontally adjacent output pixels
+  cuuint64_t gdim[5] = {static_cast<cuuint64_t>(cols), 2, wl, 2, hl * static_cast<cuuint64_t>(a->src[0].n)};
+  cuuint64_t gstr[4] = {pix, 2 * pix, pix * static_cast<cuuint64_t>(a->w_out), 2 * pix * static_cast<cuuint64_t>(a->w_out)};
+  cuuint32_t box[5] = {32u, 1u, static_cast<cuuint32_t>(sub[0]), 1u, static_cast<cuuint32_t>(sub[1])};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = encode(tm, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5,
+                      const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(EALDM_ECUDA, "cuTensorMapEncodeTiled(upsampling phases) failed: %d", (int)r);
+  return 0;
 }
 
 // 4-D (C, W, H, N) tensor map over an NHWC output-space tensor with a [32 columns x 32 rows] box
@@ -935,16 +848,19 @@ int launch(const ealdm_conv_args* a, cudaStream_t st) {
 
   Params p;
   memset(&p, 0, sizeof(p));
+  const bool phased = a->upsample_phases != 0;  // tiles live on the LOW-resolution grid, four output phases each
+  const long long w_grid = phased ? a->w_out / 2 : a->w_out, h_grid = phased ? a->h_out / 2 : a->h_out;
   p.nseg = a->n_src;
-  p.Wout = static_cast<int>(a->w_out);
-  p.Hout = static_cast<int>(a->h_out);
+  p.phases = phased ? 4 : 1;
+  p.Wout = static_cast<int>(w_grid);
+  p.Hout = static_cast<int>(h_grid);
   p.Nimg = static_cast<int>(a->src[0].n);
   p.N = static_cast<int>(a->n_out);
-  p.bw = pow2_ceil(a->w_out) < BM ? pow2_ceil(a->w_out) : BM;
-  p.bh = pow2_ceil(a->h_out) < BM / p.bw ? pow2_ceil(a->h_out) : BM / p.bw;
+  p.bw = pow2_ceil(w_grid) < BM ? pow2_ceil(w_grid) : BM;
+  p.bh = pow2_ceil(h_grid) < BM / p.bw ? pow2_ceil(h_grid) : BM / p.bw;
   p.bn = BM / (p.bw * p.bh);
-  p.tiles_w = static_cast<int>(ceil_div(a->w_out, p.bw));
-  p.tiles_h = static_cast<int>(ceil_div(a->h_out, p.bh));
+  p.tiles_w = static_cast<int>(ceil_div(w_grid, p.bw));
+  p.tiles_h = static_cast<int>(ceil_div(h_grid, p.bh));
   p.m_tiles = p.tiles_w * p.tiles_h * static_cast<int>(ceil_div(p.Nimg, p.bn));
   // the 32 rows of one epilogue warp form a (sub_w, sub_h, sub_n) sub-box of the tile
   int sub[3];
@@ -960,8 +876,8 @@ int launch(const ealdm_conv_args* a, cudaStream_t st) {
   } else if (a->n_out <= 128) {
     BN = 128;
   } else {
-    const long long t256 = static_cast<long long>(p.m_tiles) * ceil_div(a->n_out, 256);
-    const long long t128 = static_cast<long long>(p.m_tiles) * ceil_div(a->n_out, 128);
+    const long long t256 = static_cast<long long>(p.m_tiles) * p.phases * ceil_div(a->n_out, 256);
+    const long long t128 = static_cast<long long>(p.m_tiles) * p.phases * ceil_div(a->n_out, 128);
     const long long c256 = ceil_div(t256, num_sms()) * (256 + 48);
     const long long c128 = ceil_div(t128, num_sms()) * (128 + 48);
     BN = (c256 <= c128) ? 256 : 128;
@@ -972,7 +888,7 @@ int launch(const ealdm_conv_args* a, cudaStream_t st) {
   // and a reduction long enough (K >= 1024) to amortise the pair's cross-CTA barrier latency (measured: K = 256 / 512
   // GEMMs lose 5-25 % as pairs, K >= 1024 GEMMs and all 3x3 convs gain 3-12 %); EALDM_TC_CTA2=2 pairs regardless of K
   const bool pair = (BN == 256 || (BN == 128 && !geglu && cta2_mode() >= 2)) && cta2_mode() != 0 && p.m_tiles >= 2 && p.m_tiles % 2 == 0 &&
-                    (a->k_total >= 1024 || cta2_mode() == 2);  // 3: the K rule, 128-column tiles included
+                    ((phased ? a->k_total / 4 : a->k_total) >= 1024 || cta2_mode() == 2);  // 3: the K rule, 128-column tiles included
 
   CUtensorMap tm[6];  // A0, A1, W, out, out2, residual
   memset(tm, 0, sizeof(tm));
@@ -981,12 +897,12 @@ int launch(const ealdm_conv_args* a, cudaStream_t st) {
     const ealdm_conv_src& x = a->src[s];
     Segment& sg = p.seg[s];
     sg.cblk = static_cast<int>(x.c / BK);
-    sg.ksize = x.ksize;
-    sg.kblocks = sg.cblk * x.ksize * x.ksize;
+    sg.ksize = phased ? 2 : x.ksize;  // a phase is a 2x2 convolution whose taps start at (py - 1, px - 1)
+    sg.kblocks = sg.cblk * sg.ksize * sg.ksize;
     sg.pad = x.pad;
     sg.stride = x.stride;
     sg.bkoff = koff;
-    koff += static_cast<int>(x.c) * x.ksize * x.ksize;
+    koff += static_cast<int>(x.c) * (phased ? 16 : x.ksize * x.ksize);
     cuuint64_t gdim[4] = {static_cast<cuuint64_t>(x.c), static_cast<cuuint64_t>(x.w),
                           static_cast<cuuint64_t>(x.h), static_cast<cuuint64_t>(x.n)};
     cuuint64_t gstr[3] = {static_cast<cuuint64_t>(x.ld) * 2,
@@ -1033,15 +949,24 @@ int launch(const ealdm_conv_args* a, cudaStream_t st) {
   const long long out_cols = geglu ? a->n_out / 2 : a->n_out;
   // (measured: the GEGLU pass gains 3 % at K = 256 and loses 4 % at K >= 512, where the stores of the narrow units
   // overlap the longer main loop better)
-  const bool wide = g_opt[EALDM_TC_OPT_WIDE] != 0 && BN == 256 &&
+  const bool wide = g_opt[EALDM_TC_OPT_WIDE] != 0 && BN == 256 && !phased &&
                     (geglu ? a->k_total <= 256 : (!a->residual && !a->out2));
-  if (int e = encode_unit_map(encode, &tm[3], a->out, a->out_f32 != 0, out_cols, a->ld_out, a, sub,
-                              wide && !a->out_f32))
+  if (phased) {
+    EALDM_REQUIRE(sub[2] == 1, "tcgen05 conv: upsampling phases need at least 32 low-resolution pixels per image");
+    if (int e = encode_phase_map(encode, &tm[3], a->out, a->out_f32 != 0, out_cols, a->ld_out, a, sub)) return e;
+  } else if (int e = encode_unit_map(encode, &tm[3], a->out, a->out_f32 != 0, out_cols, a->ld_out, a, sub,
+                                     wide && !a->out_f32)) {
     return e;
+  }
   tm[4] = tm[3];
   tm[5] = tm[3];
-  if (a->out2)
-    if (int e = encode_unit_map(encode, &tm[4], a->out2, false, out_cols, a->ld_out2, a, sub)) return e;
+  if (a->out2) {
+    if (phased) {
+      if (int e = encode_phase_map(encode, &tm[4], a->out2, false, out_cols, a->ld_out2, a, sub)) return e;
+    } else if (int e = encode_unit_map(encode, &tm[4], a->out2, false, out_cols, a->ld_out2, a, sub)) {
+      return e;
+    }
+  }
   if (a->residual)
     if (int e = encode_unit_map(encode, &tm[5], a->residual, a->res_f32 != 0, out_cols, a->ld_res, a, sub)) return e;
 
@@ -1056,6 +981,7 @@ int launch(const ealdm_conv_args* a, cudaStream_t st) {
   p.gn_partial = reinterpret_cast<float2*>(a->gn_partial);
   p.gn_ld = static_cast<int>(a->gn_ld);
   p.gn_chunks = static_cast<int>(a->h_out * a->w_out / 32);
+  p.gn_phase_chunks = static_cast<int>(h_grid * w_grid / 32);
   p.b_mn = a->weight_adjoint ? 1 : 0;
   p.wide = wide ? 1 : 0;
   p.relaxed_wait = g_opt[EALDM_TC_OPT_RELAXED_WAIT];

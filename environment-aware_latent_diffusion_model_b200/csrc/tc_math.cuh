@@ -1,0 +1,142 @@
+// Epilogue helpers shared by the tcgen05 kernels (conv_tc.cu, ff_fused.cu): swizzled shared-memory unit buffers that
+// TMA loads / stores, and the packed-f32x2 GEGLU arithmetic.
+#pragma once
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace ealdm {
+namespace tc {
+
+// ---- shared-memory unit buffers ---------------------------------------------------------------------
+// A unit is 32 rows; fp32 rows are 128 B with the TMA 128-byte swizzle (16-byte chunk j of row r lives
+// at chunk j ^ (r & 7)), bf16 rows are 64 B with the 64-byte swizzle (chunk j ^ ((r >> 1) & 3)).  One
+// thread touches one row, so each quarter-warp phase covers 8 distinct 16-byte bank groups.
+__device__ __forceinline__ void lds_row_f32(const uint8_t* buf, int lane, float (&r)[32]) {
+  const uint8_t* row = buf + lane * 128;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 t = *reinterpret_cast<const float4*>(row + ((j ^ (lane & 7)) << 4));
+    r[4 * j] = t.x; r[4 * j + 1] = t.y; r[4 * j + 2] = t.z; r[4 * j + 3] = t.w;
+  }
+}
+__device__ __forceinline__ void sts_row_f32(uint8_t* buf, int lane, const float (&v)[32]) {
+  uint8_t* row = buf + lane * 128;
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    *reinterpret_cast<float4*>(row + ((j ^ (lane & 7)) << 4)) =
+        make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+}
+__device__ __forceinline__ uint32_t pack2_bf16(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ void lds_row_bf16(const uint8_t* buf, int lane, float (&r)[32]) {
+  const uint8_t* row = buf + lane * 64;
+  const int sw = (lane >> 1) & 3;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint4 u = *reinterpret_cast<const uint4*>(row + ((j ^ sw) << 4));
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      r[8 * j + 2 * e] = __uint_as_float(w[e] << 16);
+      r[8 * j + 2 * e + 1] = __uint_as_float(w[e] & 0xffff0000u);
+    }
+  }
+}
+// 8 consecutive bf16 (one 16-byte chunk `j` of row `lane`)
+__device__ __forceinline__ void sts_chunk_bf16(uint8_t* buf, int lane, int j, const float* v) {
+  uint4 u;
+  u.x = pack2_bf16(v[0], v[1]);
+  u.y = pack2_bf16(v[2], v[3]);
+  u.z = pack2_bf16(v[4], v[5]);
+  u.w = pack2_bf16(v[6], v[7]);
+  *reinterpret_cast<uint4*>(buf + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = u;
+}
+// 8 consecutive bf16 into 16-byte chunk j (0..7) of row `lane` of a [32 rows x 128 B] SWIZZLE_128B box
+__device__ __forceinline__ void sts_chunk_bf16_sw128(uint8_t* buf, int lane, int j, const float* v) {
+  uint4 u;
+  u.x = pack2_bf16(v[0], v[1]);
+  u.y = pack2_bf16(v[2], v[3]);
+  u.z = pack2_bf16(v[4], v[5]);
+  u.w = pack2_bf16(v[6], v[7]);
+  *reinterpret_cast<uint4*>(buf + lane * 128 + ((j ^ (lane & 7)) << 4)) = u;
+}
+__device__ __forceinline__ void sts_row_bf16(uint8_t* buf, int lane, const float (&v)[32]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) sts_chunk_bf16(buf, lane, j, &v[8 * j]);
+}
+
+// exact-erf GELU for the bf16 tensor-core path: erf by Abramowitz-Stegun 7.1.28,
+//   erf(x) = 1 - (1 + a1 x + ... + a6 x^6)^-16,  |error| <= 3e-7 (1.7e-6 in fp32 arithmetic),
+// far below bf16 resolution; ONE MUFU (rcp) per element instead of erff's branches.  The fp32 parity
+// path (conv_simt.cu) keeps erff.
+//
+// The GEGLU epilogue is bound by instruction issue (ncu: 62 % issue-active from the 8 epilogue warps, 24
+// instructions per output), so the arithmetic runs on PAIRS of fp32 values with the packed sm_100 instructions
+// (FFMA2 / FMUL2 / FADD2: one issue slot for two lanes).  With z = -|g| and the 1/sqrt(2) of erf(g/sqrt(2))
+// folded into the coefficients, p = 1 - b1 z + b2 z^2 - ... (Horner in z), r = p^-16 and
+//   gelu(g) = g Phi(g) = 0.5 ((g + |g|) - |g| r) = 0.5 ((g - z) + z r),
+// the 0.5 being folded into the value operand ((0.5 v + 0.5 bias_v), bias pre-halved in shared memory).
+__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+// (value pair) * gelu(gate pair); `val` already holds 0.5 * (v + bias_v), `g` holds gate + bias_g
+__device__ __forceinline__ uint64_t geglu2(uint64_t val, uint64_t g) {
+  constexpr float S = 0.70710678118654752440f;
+  constexpr float B1 = -0.0705230784f * S;
+  constexpr float B2 = 0.0422820123f * S * S;
+  constexpr float B3 = -0.0092705272f * S * S * S;
+  constexpr float B4 = 0.0001520143f * S * S * S * S;
+  constexpr float B5 = -0.0002765672f * S * S * S * S * S;
+  constexpr float B6 = 0.0000430638f * S * S * S * S * S * S;
+  float g0, g1;
+  upk2(g, g0, g1);
+  const uint64_t z = pk2(__uint_as_float(__float_as_uint(g0) | 0x80000000u),
+                         __uint_as_float(__float_as_uint(g1) | 0x80000000u));
+  uint64_t p = fma2(pk2(B6, B6), z, pk2(B5, B5));
+  p = fma2(p, z, pk2(B4, B4));
+  p = fma2(p, z, pk2(B3, B3));
+  p = fma2(p, z, pk2(B2, B2));
+  p = fma2(p, z, pk2(B1, B1));
+  p = fma2(p, z, pk2(1.0f, 1.0f));
+  float p0, p1;
+  upk2(p, p0, p1);
+  uint64_t r = pk2(rcp_approx(p0), rcp_approx(p1));
+  r = mul2(r, r); r = mul2(r, r); r = mul2(r, r); r = mul2(r, r);
+  const uint64_t u = fma2(z, r, sub2(g, z));
+  return mul2(val, u);
+}
+
+}  // namespace tc
+}  // namespace ealdm

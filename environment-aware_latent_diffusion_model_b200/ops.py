@@ -105,7 +105,8 @@ class ConvIn:
 
 def conv(srcs: Sequence[ConvIn], weight: torch.Tensor, out: Act, *, bias: Optional[torch.Tensor] = None,
          rowvec: Optional[torch.Tensor] = None, rowvec_col0: int = 0, residual: Optional[Act] = None,
-         act: int = L.ACT_NONE, impl: int = L.IMPL_AUTO, out2: Optional[Act] = None, adjoint: bool = False) -> Act:
+         act: int = L.ACT_NONE, impl: int = L.IMPL_AUTO, out2: Optional[Act] = None, adjoint: bool = False,
+         upsample_phases: bool = False) -> Act:
     """ealdm_conv: out = epilogue(sum_s im2col(src_s) @ weight[:, seg_s]^T). `weight` is [n_out, k_total].
     adjoint=True: data gradient of a forward layer -- `weight` is that layer's own packed matrix
     [src channels, ksize^2 * out.c] (may be a column window of a wider matrix); nothing is transposed or flipped."""
@@ -134,6 +135,11 @@ def conv(srcs: Sequence[ConvIn], weight: torch.Tensor, out: Act, *, bias: Option
     else:
         assert weight.is_contiguous()
         a.n_out, a.k_total = weight.shape
+    if upsample_phases:   # `weight` = packing.pack_upsample_phases(...): four 2x2 phases over the low-resolution source
+        assert len(srcs) == 1 and srcs[0].upsample == 1 and weight.shape[1] == 16 * x0.c
+        a.upsample_phases = 1
+        if impl == L.IMPL_AUTO:
+            a.impl = L.IMPL_TCGEN05
     n_cols = a.n_out // 2 if act == L.ACT_GEGLU else a.n_out
     assert out.c == n_cols, (out.c, n_cols)
     if bias is not None:
@@ -181,6 +187,25 @@ def linear(x: Act, weight: torch.Tensor, out: Act, **kw) -> Act:
     if o2 is not None:
         o2 = Act(o2.buf, 1, 1, o2.rows, o2.c, o2.c0)
     conv([ConvIn(xs)], weight, os_, residual=res, out2=o2, **kw)
+    return out
+
+
+def ff_geglu_fused(x: Act, w1: torch.Tensor, b1: torch.Tensor, w2: torch.Tensor, b2: torch.Tensor, residual: Act,
+                   out: Act) -> Act:
+    """ealdm_ff_geglu_fused: out = GEGLU(x w1^T + b1) w2^T + b2 + residual in one kernel (c = 256, hidden = 1024);
+    w1 / b1 row-interleaved by packing.geglu_interleave."""
+    lib = L.load()
+    a = L.FfFusedArgs()
+    assert x.dtype == torch.bfloat16 and w1.dtype == torch.bfloat16 and w2.dtype == torch.bfloat16
+    assert w1.is_contiguous() and w2.is_contiguous() and w1.shape == (2 * w2.shape[1], x.c) and w2.shape[0] == x.c
+    assert b1.dtype == torch.float32 and b1.numel() == w1.shape[0] and b2.dtype == torch.float32 and b2.numel() == x.c
+    assert residual.dtype == torch.float32 and residual.rows == x.rows and residual.c == x.c
+    assert out.rows == x.rows and out.c == x.c and out.dtype in (torch.float32, torch.bfloat16)
+    a.x, a.rows, a.ld_x, a.c, a.hidden = x.ptr, x.rows, x.ld, x.c, w2.shape[1]
+    a.w1, a.b1, a.w2, a.b2 = w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr()
+    a.residual, a.ld_res = residual.ptr, residual.ld
+    a.out, a.ld_out, a.out_f32 = out.ptr, out.ld, 1 if out.dtype == torch.float32 else 0
+    L.check(lib.ealdm_ff_geglu_fused(C.byref(a), _stream()))
     return out
 
 

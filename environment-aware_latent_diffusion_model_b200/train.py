@@ -60,6 +60,8 @@ class UNetTrainEngine(UNetEngine):
     build a new engine (UNetModel does so automatically) after every optimizer step."""
 
     _fused_geglu = False
+    _fused_ff = False             # the backward needs the GEGLU pre-activation
+    _phased_upsample = False      # the backward differentiates the explicit nearest-2x + 3x3 form
 
     def __init__(self, m: UNetModel, dtype: torch.dtype):
         super().__init__(m, dtype)

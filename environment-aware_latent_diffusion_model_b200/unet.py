@@ -10,6 +10,7 @@ issues libealdm_b200 kernels on NHWC activations (see DESIGN.md for the data lay
 from __future__ import annotations
 
 import math
+import os
 from typing import List, Optional
 
 import torch
@@ -18,7 +19,7 @@ import torch.nn as nn
 from . import _lib as L
 from . import ops
 from .ops import Act, ConvIn
-from .packing import geglu_interleave, pack_conv_weight
+from .packing import geglu_interleave, pack_conv_weight, pack_upsample_phases
 
 
 def zero_module(module: nn.Module) -> nn.Module:
@@ -352,6 +353,8 @@ class UNetEngine:
     sequence of libealdm_b200 launches on the current CUDA stream (CUDA-graph capturable: no host
     synchronisation, no data-dependent control flow)."""
     _fused_geglu = True   # the training engine keeps the GEGLU pre-activation instead (train.py)
+    _fused_ff = not os.environ.get("EALDM_NO_FUSED_FF")                   # A/B switch: one-kernel GEGLU FeedForward
+    _phased_upsample = not os.environ.get("EALDM_NO_PHASED_UPSAMPLE")   # A/B switch; the training engine saves `up`
 
     def __init__(self, m: UNetModel, dtype: torch.dtype):
         L.load()
@@ -447,8 +450,12 @@ class UNetEngine:
                     out.append({"kind": "down", "c": layer.channels,
                                 "conv": _PackedConv(pk(layer.op), f32(layer.op.bias), layer.out_channels)})
                 elif isinstance(layer, Upsample):
-                    out.append({"kind": "up", "c": layer.channels,
-                                "conv": _PackedConv(pk(layer.conv), f32(layer.conv.bias), layer.out_channels)})
+                    d = {"kind": "up", "c": layer.channels,
+                         "conv": _PackedConv(pk(layer.conv), f32(layer.conv.bias), layer.out_channels)}
+                    if self.dt == torch.bfloat16 and self._phased_upsample and layer.channels % 64 == 0:
+                        # nearest-2x folded into the conv: four 2x2 output phases over the low-resolution input
+                        d["w_phases"] = pack_upsample_phases(layer.conv.weight, dtype)
+                    out.append(d)
                 elif isinstance(layer, nn.Conv2d):
                     d = {"kind": "conv_in", "conv": _PackedConv(pk(layer), f32(layer.bias), layer.out_channels)}
                     if self.dt == torch.bfloat16 and layer.in_channels < 64 and layer.kernel_size == (3, 3):
@@ -582,11 +589,15 @@ class UNetEngine:
             t2 = self._new(n, h, w, C_, f32)
             ops.linear(o2, tb["o2"].w, t2, bias=tb["o2"].b, residual=t1)
             ops.layer_norm(t2, tb["ln3"][0], tb["ln3"][1], 1e-5, a)
-            gg = self._new(n, h, w, 4 * C_)
-            ops.linear(a, tb["ff1"].w, gg, bias=tb["ff1"].b, act=L.ACT_GEGLU)
             last = bi == len(d["blocks"]) - 1   # the last t feeds proj_out as a GEMM operand -> compute dtype
             t = self._new(n, h, w, C_, None if last else f32)
-            ops.linear(gg, tb["ff2"].w, t, bias=tb["ff2"].b, residual=t2)
+            if self._fused_ff and C_ == 256 and self.dt == torch.bfloat16:
+                # FF1 -> GEGLU -> FF2 -> + residual in one kernel: the 8C / 4C wide intermediates stay on the SM
+                ops.ff_geglu_fused(a, tb["ff1"].w, tb["ff1"].b, tb["ff2"].w, tb["ff2"].b, t2, t)
+            else:
+                gg = self._new(n, h, w, 4 * C_)
+                ops.linear(a, tb["ff1"].w, gg, bias=tb["ff1"].b, act=L.ACT_GEGLU)
+                ops.linear(gg, tb["ff2"].w, t, bias=tb["ff2"].b, residual=t2)
         out = dest if dest is not None else self._new_dual(n, h, w, C_)
         ops.linear(t, d["proj_out"].w, out.f, bias=d["proj_out"].b, residual=x.f, out2=self._out2(out))
         return out
@@ -628,7 +639,10 @@ class UNetEngine:
                 x = out
             elif k == "up":
                 out = dst if dst is not None else self._new_dual(n, h * 2, w * 2, d["conv"].cout)
-                if self.dt == torch.bfloat16:
+                if "w_phases" in d and h * w >= 32 and (h & (h - 1)) == 0 and (w & (w - 1)) == 0:
+                    ops.conv([ConvIn(x.h, 3, 1, 1, upsample=1)], d["w_phases"], out.f, bias=d["conv"].b,
+                             out2=self._out2(out), upsample_phases=True)
+                elif self.dt == torch.bfloat16:
                     up = self._new(n, h * 2, w * 2, x.h.c)
                     ops.upsample_nearest2x(x.h, up)
                     ops.conv([ConvIn(up, 3, 1, 1)], d["conv"].w, out.f, bias=d["conv"].b, out2=self._out2(out))

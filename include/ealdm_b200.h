@@ -131,11 +131,46 @@ typedef struct {
        out[m, j] = sum_{tap, c} src[..tap.., c] * weight[c, (ksize^2 - 1 - tap) * n_out + j]
      i.e. the transposed, tap-flipped weights are never materialised (the B operand is read MN-major). */
   int32_t weight_adjoint;
-  int32_t reserved2;
+  /* upsample_phases = 1 (tcgen05 path, n_src = 1, src[0].upsample = 1, ksize 3 / stride 1 / pad 1): the convolution over
+     the nearest-2x upsampled source (Upsample, openaimodel.py:109-119) is evaluated as its four OUTPUT PHASES: output
+     pixel (2y + py, 2x + px) only sees source rows {y + py - 1, y + py} and columns {x + px - 1, x + px}, so each phase
+     is a 2x2 convolution over the source itself with the 3x3 taps that coincide pre-summed.  `weight` is then
+     [n_out, 4 phases (py, px) x 4 taps (row, column) x src.c] (k_total = 16 * src.c); 4/9 of the FLOPs of the 3x3
+     form, and the upsampled tensor never exists.  Bias, row vector, shadow and GroupNorm partials as usual. */
+  int32_t upsample_phases;
   int64_t ld_weight;
 } ealdm_conv_args;
 
 int ealdm_conv(const ealdm_conv_args* a, ealdm_stream_t stream);
+
+/*
+ * Fused GEGLU FeedForward + residual of one transformer block at model width c = 256 (hidden = 4c = 1024):
+ *   out = (value * gelu_erf(gate)) * w2^T + b2 + residual,   [value | gate] = x * w1^T + b1
+ * in ONE kernel: the 8c-wide projection and the 4c-wide gated activation stay in TMEM / shared memory.
+ * `w1` / `b1` are the ROW-INTERLEAVED GEGLU projection (blocks of 32 rows: 16 value rows, then their 16 gate rows --
+ * the layout ealdm_conv's EALDM_ACT_GEGLU epilogue uses), [2*hidden, c] bf16 / [2*hidden] fp32; `w2` is [c, hidden]
+ * bf16, `b2` [c] fp32; `x` bf16 [rows, ld_x]; `residual` fp32 [rows, ld_res]; `out` fp32 or bf16 [rows, ld_out].
+ * Bit-identical to ealdm_conv(act = GEGLU) followed by ealdm_conv(bias, fp32 residual).
+ * Replaces: FeedForward.forward / GEGLU.forward (ldm/modules/attention.py:37-64) and the `+ x` of
+ *   BasicTransformerBlock._forward (attention.py:214).
+ */
+typedef struct {
+  const void* x;
+  int64_t rows, ld_x;
+  int64_t c, hidden;
+  const void* w1;
+  const float* b1;
+  const void* w2;
+  const float* b2;
+  const float* residual;
+  int64_t ld_res;
+  void* out;
+  int64_t ld_out;
+  int32_t out_f32;
+  int32_t reserved;
+} ealdm_ff_fused_args;
+
+int ealdm_ff_geglu_fused(const ealdm_ff_fused_args* a, ealdm_stream_t stream);
 
 /* ---- normalisation -------------------------------------------------------------------------- */
 /*

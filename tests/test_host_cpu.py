@@ -272,3 +272,22 @@ def test_gradient_buckets_gloo_world2_average_and_overlap_order():
         # mean over ranks of (i+1)*(rank+1) = 1.5*(i+1)
         assert vals == [1.5 * (i + 1) for i in range(len(vals))]
         assert 0 < early < nb      # buckets were launched while "backward" was still running
+
+
+def test_upsample_phase_weights_reproduce_nearest2x_conv3x3():
+    """packing.pack_upsample_phases: four 2x2 phases over the low-resolution input == conv3x3(pad 1) over the
+    nearest-2x upsampled input (openaimodel.py:109-119), borders included."""
+    import torch.nn.functional as F
+    from ealdm_b200.packing import pack_upsample_phases
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 5, 6, 7, generator=g, dtype=torch.float64)
+    w = torch.randn(4, 5, 3, 3, generator=g, dtype=torch.float64)
+    ref = F.conv2d(F.interpolate(x, scale_factor=2, mode="nearest"), w, padding=1)
+    wp = pack_upsample_phases(w.float(), torch.float32).double().reshape(4, 2, 2, 2, 2, 5)
+    xp = F.pad(x, (1, 1, 1, 1))
+    out = torch.empty_like(ref)
+    for py in (0, 1):
+        for px in (0, 1):
+            k = wp[:, py, px].permute(0, 3, 1, 2)
+            out[:, :, py::2, px::2] = F.conv2d(xp[:, :, py:py + 7, px:px + 8], k)
+    assert float((out - ref).abs().max()) < 1e-5

@@ -127,6 +127,48 @@ def test_conv3x3_upsample_simt(dtype):
     assert torch.equal(from_act(up), F.interpolate(from_act(xa), scale_factor=2, mode="nearest"))
 
 
+@pytest.mark.parametrize("n,c,h,w,co", [(2, 64, 8, 8, 64), (3, 128, 16, 16, 256), (4, 512, 8, 8, 1024),
+                                        (5, 256, 16, 16, 320), (2, 64, 4, 8, 128)])
+def test_conv3x3_upsample_as_four_phases_tcgen05(n, c, h, w, co):
+    """Upsample (openaimodel.py:109-119) as four 2x2 output phases over the low-resolution input (`upsample_phases`):
+    against F.interpolate(nearest) + conv2d on the same bf16-rounded input with the ORIGINAL 3x3 weights, including
+    the fp32 output + bf16 shadow pair and the GroupNorm partial statistics the UNet asks for."""
+    from ealdm_b200.packing import pack_upsample_phases
+    x = torch.randn(n, c, h, w, generator=g(112)).to(DEV)
+    wt = (torch.randn(co, c, 3, 3, generator=g(113)) / math.sqrt(9 * c)).to(DEV)
+    b = torch.randn(co, generator=g(114)).to(DEV)
+    xa = to_act(x, torch.bfloat16, ld=c + 64, c0=64)
+    out = Act.empty(n, 2 * h, 2 * w, co, torch.float32, DEV).with_gn_partial()
+    sh = Act.empty(n, 2 * h, 2 * w, co, torch.bfloat16, DEV)
+    out.buf.fill_(float("nan"))
+    wp = pack_upsample_phases(wt, torch.bfloat16)
+    assert wp.shape == (co, 16 * c)
+    ops.conv([ConvIn(xa, 3, 1, 1, upsample=1)], wp, out, bias=b, out2=sh, upsample_phases=True)
+    up = F.interpolate(from_act(xa), scale_factor=2, mode="nearest")
+    ref = F.conv2d(up, wt.to(torch.bfloat16).float(), b, padding=1)
+    err = rel_l2(from_act(out), ref)
+    print(f"upsample phases n={n} c={c} {h}x{w} -> co={co}: rel_l2 = {err:.3e}")
+    assert err < 6e-3                      # pre-summed taps are rounded to bf16 once more than the 3x3 form
+    assert torch.equal(sh.buf, out.buf.to(torch.bfloat16))
+    # exactness of the phase algebra itself: the same kernel against conv2d with the phase weights un-summed again
+    w4 = wp.float().reshape(co, 2, 2, 2, 2, c)      # [o, py, px, a, b, i]
+    xr = F.pad(from_act(xa), (1, 1, 1, 1))
+    ref2 = torch.empty_like(ref)
+    for py in (0, 1):
+        for px in (0, 1):
+            k = w4[:, py, px].permute(0, 3, 1, 2).contiguous()            # [o, i, 2, 2]
+            y = F.conv2d(xr[:, :, py:py + h + 1, px:px + w + 1], k, b)    # rows y + py - 1 + a (padded index + 1)
+            ref2[:, :, py::2, px::2] = y
+    assert rel_l2(from_act(out), ref2) < 2e-5
+    if out.gp is not None:                  # GroupNorm over the result equals torch's on the same fp32 tensor
+        gam = torch.randn(co, generator=g(115)).to(DEV)
+        bet = torch.randn(co, generator=g(116)).to(DEV)
+        y = Act.empty(n, 2 * h, 2 * w, co, torch.bfloat16, DEV)
+        ops.group_norm(out, gam, bet, 1e-5, y, silu=True)
+        yr = F.silu(F.group_norm(from_act(out), 32, gam, bet, 1e-5))
+        assert rel_l2(from_act(y), yr) < 6e-3
+
+
 @pytest.mark.parametrize("dtype,impl", [(torch.float32, L.IMPL_SIMT), (torch.bfloat16, L.IMPL_TCGEN05)])
 def test_conv_two_sources_skip_fused(dtype, impl):
     # ResBlock tail: conv3x3(h) + conv1x1(x) + biases in ONE accumulator (openaimodel.py:275)
@@ -646,3 +688,40 @@ def test_conv_feature_sweep_all_schedules(case):
         ref_s = o.reshape(n, co // 8, 8, -1).sum(dim=(2, 3))
         ref_ss = (o * o).reshape(n, co // 8, 8, -1).sum(dim=(2, 3))
         assert rel_l2(sums[..., 0], ref_s) < 1e-4 and rel_l2(sums[..., 1], ref_ss) < 1e-4
+
+
+@pytest.mark.parametrize("out_dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("M", [128, 300, 1024, 40000])
+def test_ff_geglu_fused_is_bit_identical_to_the_two_gemm_path(M, out_dtype):
+    """ealdm_ff_geglu_fused (FF1 -> GEGLU -> FF2 -> + residual in one kernel, c = 256) against the unfused pair of
+    ealdm_conv launches on the same interleaved weights (bit for bit: same k-block order, bias handling and GEGLU
+    polynomial), and against torch fp32 on the bf16-rounded operands.  M = 40000 gives every persistent CTA several
+    tiles (ring / TMEM buffer phases wrap); M = 300 ends in a partial tile."""
+    from ealdm_b200.packing import geglu_interleave
+    c, hid = 256, 1024
+    x = torch.randn(M, c, generator=g(201)).to(DEV)
+    w1 = (torch.randn(2 * hid, c, generator=g(202)) / math.sqrt(c)).to(DEV)
+    b1 = (torch.randn(2 * hid, generator=g(203)) * 0.5).to(DEV)
+    w2 = (torch.randn(c, hid, generator=g(204)) / math.sqrt(hid)).to(DEV)
+    b2 = torch.randn(c, generator=g(205)).to(DEV)
+    res = torch.randn(M, c, generator=g(206)).to(DEV)
+    xa = Act(x.to(torch.bfloat16).contiguous(), 1, 1, M)
+    ra = Act(res.contiguous(), 1, 1, M)
+    w1i, b1i = geglu_interleave(w1.to(torch.bfloat16), b1)
+    w2b = w2.to(torch.bfloat16).contiguous()
+    out = Act.empty(1, 1, M, c, out_dtype, DEV)
+    out.buf.fill_(float("nan"))
+    ops.ff_geglu_fused(xa, w1i, b1i, w2b, b2, ra, out)
+    gg = Act.empty(1, 1, M, hid, torch.bfloat16, DEV)
+    ops.linear(xa, w1i, gg, bias=b1i, act=L.ACT_GEGLU)
+    ref = Act.empty(1, 1, M, c, out_dtype, DEV)
+    ops.linear(gg, w2b, ref, bias=b2, residual=ra)
+    torch.cuda.synchronize()
+    assert torch.equal(out.buf, ref.buf)
+    xf = xa.buf.float()
+    pre = F.linear(xf, w1.to(torch.bfloat16).float(), b1)
+    h = (pre[:, :hid] * F.gelu(pre[:, hid:])).to(torch.bfloat16).float()
+    want = F.linear(h, w2b.float(), b2) + res
+    err = rel_l2(out.buf.float(), want)
+    print(f"ff_geglu_fused M={M} out={out_dtype}: rel_l2 vs torch = {err:.3e}")
+    assert err < 6e-3

@@ -206,7 +206,7 @@ def test_eval_forward_after_weight_updates_uses_the_new_weights():
     from ealdm_b200.optim import FusedAdamWEMA
     from ealdm_b200.parallel import GradBuckets
     from ealdm_b200.unet import UNetModel
-    tiny = dict(image_size=8, in_channels=4, model_channels=64, out_channels=4, num_res_blocks=1,
+    tiny = dict(image_size=8, in_channels=4, model_channels=128, out_channels=4, num_res_blocks=1,
                 attention_resolutions=[1, 2], channel_mult=(1, 2), num_head_channels=32,
                 use_spatial_transformer=True, transformer_depth=1, context_dim=64)
     torch.manual_seed(0)
@@ -270,7 +270,7 @@ def test_fused_optimizer_and_ema_checkpoint_round_trip():
     from ealdm_b200.optim import FusedAdamWEMA
     from ealdm_b200.parallel import GradBuckets
     from ealdm_b200.unet import UNetModel
-    tiny = dict(image_size=8, in_channels=4, model_channels=64, out_channels=4, num_res_blocks=1,
+    tiny = dict(image_size=8, in_channels=4, model_channels=128, out_channels=4, num_res_blocks=1,
                 attention_resolutions=[1, 2], channel_mult=(1, 2), num_head_channels=32,
                 use_spatial_transformer=True, transformer_depth=1, context_dim=64)
 
