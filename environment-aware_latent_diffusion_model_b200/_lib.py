@@ -16,7 +16,7 @@ CSRC_DIR = os.path.join(_HERE, "csrc")
 F32, BF16 = 0, 1
 ACT_NONE, ACT_SILU, ACT_GEGLU, ACT_RELU = 0, 1, 2, 3
 IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05 = 0, 1, 2
-TC_OPT_CTA2, TC_OPT_WIDE, TC_OPT_RELAXED_WAIT, TC_OPT_BN = 0, 1, 2, 3
+TC_OPT_CTA2, TC_OPT_WIDE, TC_OPT_RELAXED_WAIT, TC_OPT_BN, TC_OPT_GELU_ERF = 0, 1, 2, 3, 4
 
 EXPORTS = [
     "ealdm_abi_version", "ealdm_last_error", "ealdm_device_check", "ealdm_launch_count", "ealdm_tc_set_option",
@@ -32,6 +32,7 @@ EXPORTS = [
     "ealdm_sumpool2x2", "ealdm_cfg_mse_bwd", "ealdm_gn_partial", "ealdm_adamw_ema_step", "ealdm_plms_eps", "ealdm_vq_nearest", "ealdm_ddpm_step",
     # conditioner
     "ealdm_fourier_style", "ealdm_lstm_cell", "ealdm_adain", "ealdm_batch_norm_relu",
+    "ealdm_adain_bwd", "ealdm_batch_norm_relu_bwd", "ealdm_lstm_cell_bwd", "ealdm_relu_bwd",
 ]
 WGRAD_PACKED, WGRAD_OIHW = 0, 1
 
@@ -217,6 +218,10 @@ def _declare(lib):
         ("ealdm_lstm_cell", [vp, i64, i64, i64, vp, vp, vp, vp, vp, i64, vp, i64, vp, vp]),
         ("ealdm_adain", [vp, i64, i64, i64, i64, vp, i64, f32, vp, i64, vp]),
         ("ealdm_batch_norm_relu", [vp, i64, i64, i64, vp, vp, vp, vp, i32, f32, i32, vp, i64, vp, vp]),
+        ("ealdm_adain_bwd", [vp, i64, i64, i64, i64, vp, i64, f32, vp, i64, vp]),
+        ("ealdm_batch_norm_relu_bwd", [vp, i64, i64, i64, vp, vp, vp, i32, f32, i32, vp, i64, vp, i64, vp, i64, vp, vp, vp]),
+        ("ealdm_lstm_cell_bwd", [vp, i64, i64, i64, vp, vp, vp, vp, vp, i64, vp, i64, vp, vp, vp, vp]),
+        ("ealdm_relu_bwd", [vp, i64, vp, i64, vp, i64, i64, i64, vp, i64, vp]),
     ]:
         fn = getattr(lib, name)
         fn.restype = C.c_int

@@ -158,12 +158,20 @@ __device__ __forceinline__ void gn_partial_unit(const Params& p, const float (&r
   }
 }
 
-template <int BN, bool GEGLU, bool CTA2>
+// output maps of upsampling phases 1..3 (phase 0 uses tmOut / tmOut2): the pixels (2y + py, 2x + px) of one phase form a
+// regular sub-grid of the NHWC output, i.e. a 4-D (C, W/2, H/2, N) tensor with doubled pixel / row strides whose base
+// is shifted by (py, px)
+struct PhaseMaps {
+  CUtensorMap out[3];
+  CUtensorMap out2[3];
+};
+
+template <int BN, int GEGLU, bool CTA2>   // GEGLU: 0 none, 1 tanh-form GELU, 2 erf-form GELU (tc_math.cuh)
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
                const __grid_constant__ CUtensorMap tmOut2, const __grid_constant__ CUtensorMap tmRes,
-               const __grid_constant__ Params p) {
+               const __grid_constant__ Params p, const __grid_constant__ PhaseMaps pm) {
   using C = Cfg<BN, CTA2>;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::BAR_OFF);
@@ -394,6 +402,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
       int nt, w, h, n;
       unit_origin(tile, nt, w, h, n);
+      int uph = 0;   // upsampling phase (py, px) of this work item
+      if (p.phases > 1) uph = (tile / p.n_tiles) & 3;
       // bias of this tile's BN columns -> shared memory (one value per epilogue thread)
       if (etid < BN) {
         const int col = nt * BN + etid;
@@ -444,8 +454,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                     add2(pk2(__uint_as_float(vc[16 + 4 * j]), __uint_as_float(vc[17 + 4 * j])), pk2(g.x, g.y));
                 const uint64_t g1 =
                     add2(pk2(__uint_as_float(vc[18 + 4 * j]), __uint_as_float(vc[19 + 4 * j])), pk2(g.z, g.w));
-                upk2(geglu2(val0, g0), o[4 * j], o[4 * j + 1]);
-                upk2(geglu2(val1, g1), o[4 * j + 2], o[4 * j + 3]);
+                upk2(geglu2<GEGLU>(val0, g0), o[4 * j], o[4 * j + 1]);
+                upk2(geglu2<GEGLU>(val1, g1), o[4 * j + 2], o[4 * j + 3]);
               }
               sts_chunk_bf16_sw128(ebuf, lane, 2 * c, &o[0]);
               sts_chunk_bf16_sw128(ebuf, lane, 2 * c + 1, &o[8]);
@@ -553,7 +563,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
               const uint64_t val =
                   fma2(pk2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), half2, bv[j]);
               const uint64_t g = add2(pk2(__uint_as_float(v[16 + 2 * j]), __uint_as_float(v[17 + 2 * j])), bg[j]);
-              upk2(geglu2(val, g), o[2 * j], o[2 * j + 1]);
+              upk2(geglu2<GEGLU>(val, g), o[2 * j], o[2 * j + 1]);
             }
             sts_chunk_bf16(eb, lane, 2 * half, &o[0]);
             sts_chunk_bf16(eb, lane, 2 * half + 1, &o[8]);
@@ -608,7 +618,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
               r[j] += p.act == EALDM_ACT_RELU ? fmaxf(f, 0.f) : silu_f(f);
             }
           }
-          if (p.gn_partial != nullptr) gn_partial_unit(p, r, lane, (n - sn0) + my_dn < p.Nimg, n, h, w, nt * BN + ku * 32);
+          if (p.gn_partial != nullptr)
+            gn_partial_unit(p, r, lane, (n - sn0) + my_dn < p.Nimg, n, h, w, nt * BN + ku * 32,
+                            uph * p.gn_phase_chunks);
           if (p.out_f32) sts_row_f32(eb, lane, r);
           else sts_row_bf16(eb, lane, r);
           if (p.has_out2) sts_row_bf16(o2buf, lane, r);
@@ -617,8 +629,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         __syncwarp();
         if (lane == 0) {
           const int c0 = nt * OUT_PER_TILE + ku * 32;
-          ptx::tma_store_4d(&tmOut, eb, c0, w, h, n);
-          if (!GEGLU && p.has_out2) ptx::tma_store_4d(&tmOut2, o2buf, c0, w, h, n);
+          if (!GEGLU && uph != 0) {  // this unit's pixels of output phase (py, px): the phase's own strided map
+            ptx::tma_store_4d(&pm.out[uph - 1], eb, c0, w, h, n);
+            if (p.has_out2) ptx::tma_store_4d(&pm.out2[uph - 1], o2buf, c0, w, h, n);
+          } else {
+            ptx::tma_store_4d(&tmOut, eb, c0, w, h, n);
+            if (!GEGLU && p.has_out2) ptx::tma_store_4d(&tmOut2, o2buf, c0, w, h, n);
+          }
           ptx::bulk_commit();
         }
         ++it;
@@ -676,8 +693,8 @@ static int pow2_ceil(long long v) {
   return p;
 }
 
-template <int BN, bool GEGLU>
-static int launch_bn(const CUtensorMap* tm, const Params& p, cudaStream_t st) {
+template <int BN, int GEGLU>
+static int launch_bn(const CUtensorMap* tm, const Params& p, const PhaseMaps& pm, cudaStream_t st) {
   using C = Cfg<BN>;
   static DeviceOnce attr_set;
   if (attr_set.pending()) {
@@ -685,17 +702,17 @@ static int launch_bn(const CUtensorMap* tm, const Params& p, cudaStream_t st) {
                                     C::SMEM_BYTES));
     attr_set.done();
   }
-  const int total = p.m_tiles * p.n_tiles;
+  const int total = p.m_tiles * p.n_tiles * p.phases;
   const int grid = total < num_sms() ? total : num_sms();
   conv_tc_kernel<BN, GEGLU, false><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5],
-                                                                             p);
+                                                                             p, pm);
   EALDM_LAUNCH_CHECK();
   return 0;
 }
 
 // CTA pairs: a persistent grid of 2-CTA clusters, as many as the device can hold at once (one CTA per SM)
-template <int BN, bool GEGLU>
-static int launch_pair(const CUtensorMap* tm, const Params& p, cudaStream_t st) {
+template <int BN, int GEGLU>
+static int launch_pair(const CUtensorMap* tm, const Params& p, const PhaseMaps& pm, cudaStream_t st) {
   using C = Cfg<BN, true>;
   static int max_clusters = 0;   // devices of one process are assumed to be the same model
   static DeviceOnce attr_set;
@@ -723,16 +740,16 @@ static int launch_pair(const CUtensorMap* tm, const Params& p, cudaStream_t st) 
     EALDM_REQUIRE(n > 0, "tcgen05 conv: no 2-CTA cluster fits on this device");
     max_clusters = n < num_sms() / 2 ? n : num_sms() / 2;
   }
-  const int total = ((p.m_tiles + 1) / 2) * p.n_tiles;
+  const int total = ((p.m_tiles + 1) / 2) * p.n_tiles * p.phases;
   const int clusters = total < max_clusters ? total : max_clusters;
   cfg.gridDim = dim3(2 * clusters);
-  EALDM_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, GEGLU, true>, tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], p));
+  EALDM_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, GEGLU, true>, tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], p, pm));
   EALDM_LAUNCH_CHECK();
   return 0;
 }
 
 // schedule switches (ealdm_tc_set_option); defaults from the environment, read once
-static int g_opt[4] = {-1, -1, -1, -1};
+static int g_opt[5] = {-1, -1, -1, -1, -1};
 static int env_int(const char* name, int dflt) {
   const char* e = getenv(name);
   return e ? atoi(e) : dflt;
@@ -743,10 +760,15 @@ static void init_options() {
   g_opt[EALDM_TC_OPT_WIDE] = env_int("EALDM_TC_WIDE", 1);
   g_opt[EALDM_TC_OPT_RELAXED_WAIT] = env_int("EALDM_TC_RELAXED_WAIT", 1);
   g_opt[EALDM_TC_OPT_BN] = env_int("EALDM_TC_BN", 0);
+  g_opt[EALDM_TC_OPT_GELU_ERF] = env_int("EALDM_TC_GELU_ERF", 0);
+}
+int get_option(int option) {
+  init_options();
+  return (option >= 0 && option <= 4) ? g_opt[option] : 0;
 }
 int set_option(int option, int value) {
   init_options();
-  if (option < 0 || option > 3) return set_error(EALDM_EINVAL, "tcgen05 conv: unknown option %d", option);
+  if (option < 0 || option > 4) return set_error(EALDM_EINVAL, "tcgen05 conv: unknown option %d", option);
   const int prev = g_opt[option];
   g_opt[option] = value;
   return prev;
@@ -767,10 +789,18 @@ bool supported(const ealdm_conv_args* a) {
   for (int s = 0; s < a->n_src; ++s) {
     const ealdm_conv_src& x = a->src[s];
     if (x.c % BK != 0 || !aligned_2d(x.x, x.ld, 2)) return false;
-    if (x.upsample) return false;
+    if (x.upsample && !a->upsample_phases) return false;
     if (x.ksize != 1 && x.ksize != 3) return false;
     if (x.stride != 1 && x.stride != 2) return false;
     if (x.n != a->src[0].n) return false;
+  }
+  if (a->upsample_phases) {
+    // 3x3 / stride 1 / pad 1 over the nearest-2x upsampled source as four 2x2 phases over the source itself
+    const ealdm_conv_src& x = a->src[0];
+    if (a->n_src != 1 || !x.upsample || x.ksize != 3 || x.stride != 1 || x.pad != 1) return false;
+    if (a->weight_adjoint || a->act == EALDM_ACT_GEGLU || a->residual) return false;
+    if (a->h_out != 2 * x.h || a->w_out != 2 * x.w || a->k_total != 16 * x.c) return false;
+    if (x.h * x.w < 32 || (x.w & (x.w - 1)) != 0 || (x.h & (x.h - 1)) != 0) return false;
   }
   if (a->weight_adjoint) {
     if (a->n_src != 1 || a->act == EALDM_ACT_GEGLU || a->n_out % 64 != 0) return false;
@@ -800,19 +830,22 @@ bool supported(const ealdm_conv_args* a) {
   return true;
 }
 
-// 5-D (C, px, W/2, py, N * H/2) view of an NHWC tensor at the upsampled resolution: the pixels of one output phase
-// (py, px) form a regular sub-grid, so a [32 columns x sub_w x sub_h] unit of the LOW-resolution grid is one TMA box
+// 4-D (C, W/2, H/2, N) view of the pixels (2y + py, 2x + px) of an NHWC tensor at the upsampled resolution: doubled
+// pixel and row strides, base shifted by (py, px); a [32 columns x sub_w x sub_h x sub_n] unit of the LOW-resolution
+// grid is one TMA box
 static int encode_phase_map(PFN_cuTensorMapEncodeTiled_v12000 encode, CUtensorMap* tm, const void* base, bool f32,
-                            long long cols, long long ld, const ealdm_conv_args* a, const int (&sub)[3]) {
+                            long long cols, long long ld, const ealdm_conv_args* a, const int (&sub)[3], int py, int px) {
   const cuuint64_t es = f32 ? 4 : 2;
-  const cuuint64_t wl = static_cast<cuuint64_t>(a->w_out / 2), hl = static_cast<cuuint64_t>(a->h_out / 2);
   const cuuint64_t pix = static_cast<cuuint64_t>(ld) * es;  // bytes between horizontally adjacent output pixels
-  cuuint64_t gdim[5] = {static_cast<cuuint64_t>(cols), 2, wl, 2, hl * static_cast<cuuint64_t>(a->src[0].n)};
-  cuuint64_t gstr[4] = {pix, 2 * pix, pix * static_cast<cuuint64_t>(a->w_out), 2 * pix * static_cast<cuuint64_t>(a->w_out)};
-  cuuint32_t box[5] = {32u, 1u, static_cast<cuuint32_t>(sub[0]), 1u, static_cast<cuuint32_t>(sub[1])};
-  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = encode(tm, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5,
-                      const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  const cuuint64_t wout = static_cast<cuuint64_t>(a->w_out), hout = static_cast<cuuint64_t>(a->h_out);
+  const uint8_t* origin = static_cast<const uint8_t*>(base) + (static_cast<cuuint64_t>(py) * wout + px) * pix;
+  cuuint64_t gdim[4] = {static_cast<cuuint64_t>(cols), wout / 2, hout / 2, static_cast<cuuint64_t>(a->src[0].n)};
+  cuuint64_t gstr[3] = {2 * pix, 2 * pix * wout, pix * wout * hout};
+  cuuint32_t box[4] = {32u, static_cast<cuuint32_t>(sub[0]), static_cast<cuuint32_t>(sub[1]),
+                       static_cast<cuuint32_t>(sub[2])};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = encode(tm, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
+                      const_cast<uint8_t*>(origin), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                       f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(EALDM_ECUDA, "cuTensorMapEncodeTiled(upsampling phases) failed: %d", (int)r);
@@ -951,9 +984,14 @@ int launch(const ealdm_conv_args* a, cudaStream_t st) {
   // overlap the longer main loop better)
   const bool wide = g_opt[EALDM_TC_OPT_WIDE] != 0 && BN == 256 && !phased &&
                     (geglu ? a->k_total <= 256 : (!a->residual && !a->out2));
+  PhaseMaps pm;
+  memset(&pm, 0, sizeof(pm));
   if (phased) {
-    EALDM_REQUIRE(sub[2] == 1, "tcgen05 conv: upsampling phases need at least 32 low-resolution pixels per image");
-    if (int e = encode_phase_map(encode, &tm[3], a->out, a->out_f32 != 0, out_cols, a->ld_out, a, sub)) return e;
+    if (int e = encode_phase_map(encode, &tm[3], a->out, a->out_f32 != 0, out_cols, a->ld_out, a, sub, 0, 0)) return e;
+    for (int ph = 1; ph < 4; ++ph)
+      if (int e = encode_phase_map(encode, &pm.out[ph - 1], a->out, a->out_f32 != 0, out_cols, a->ld_out, a, sub,
+                                   ph >> 1, ph & 1))
+        return e;
   } else if (int e = encode_unit_map(encode, &tm[3], a->out, a->out_f32 != 0, out_cols, a->ld_out, a, sub,
                                      wide && !a->out_f32)) {
     return e;
@@ -962,7 +1000,11 @@ int launch(const ealdm_conv_args* a, cudaStream_t st) {
   tm[5] = tm[3];
   if (a->out2) {
     if (phased) {
-      if (int e = encode_phase_map(encode, &tm[4], a->out2, false, out_cols, a->ld_out2, a, sub)) return e;
+      if (int e = encode_phase_map(encode, &tm[4], a->out2, false, out_cols, a->ld_out2, a, sub, 0, 0)) return e;
+      for (int ph = 1; ph < 4; ++ph)
+        if (int e = encode_phase_map(encode, &pm.out2[ph - 1], a->out2, false, out_cols, a->ld_out2, a, sub, ph >> 1,
+                                     ph & 1))
+          return e;
     } else if (int e = encode_unit_map(encode, &tm[4], a->out2, false, out_cols, a->ld_out2, a, sub)) {
       return e;
     }
@@ -986,14 +1028,20 @@ int launch(const ealdm_conv_args* a, cudaStream_t st) {
   p.wide = wide ? 1 : 0;
   p.relaxed_wait = g_opt[EALDM_TC_OPT_RELAXED_WAIT];
 
+  const bool erf = g_opt[EALDM_TC_OPT_GELU_ERF] != 0;
   switch (BN) {
-    case 32: return launch_bn<32, false>(tm, p, st);
+    case 32: return launch_bn<32, 0>(tm, p, pm, st);
     case 128:
-      if (pair) return launch_pair<128, false>(tm, p, st);
-      return geglu ? launch_bn<128, true>(tm, p, st) : launch_bn<128, false>(tm, p, st);
+      if (pair) return launch_pair<128, 0>(tm, p, pm, st);
+      if (!geglu) return launch_bn<128, 0>(tm, p, pm, st);
+      return erf ? launch_bn<128, 2>(tm, p, pm, st) : launch_bn<128, 1>(tm, p, pm, st);
     default:
-      if (pair) return geglu ? launch_pair<256, true>(tm, p, st) : launch_pair<256, false>(tm, p, st);
-      return geglu ? launch_bn<256, true>(tm, p, st) : launch_bn<256, false>(tm, p, st);
+      if (pair) {
+        if (!geglu) return launch_pair<256, 0>(tm, p, pm, st);
+        return erf ? launch_pair<256, 2>(tm, p, pm, st) : launch_pair<256, 1>(tm, p, pm, st);
+      }
+      if (!geglu) return launch_bn<256, 0>(tm, p, pm, st);
+      return erf ? launch_bn<256, 2>(tm, p, pm, st) : launch_bn<256, 1>(tm, p, pm, st);
   }
 }
 

@@ -28,6 +28,9 @@
 #include <cudaTypedefs.h>
 
 namespace ealdm {
+namespace tc {
+int get_option(int option);
+}
 namespace ff {
 
 constexpr int BM = 128;
@@ -77,6 +80,7 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* s
                : "memory");
 }
 
+template <int FORM>   // GELU form, tc_math.cuh: 1 tanh, 2 erf
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 ff_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
                 const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmRes,
@@ -286,8 +290,8 @@ ff_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
                                          tc::pk2(g.x, g.y));
             const uint64_t g1 = tc::add2(tc::pk2(__uint_as_float(vc[18 + 4 * q]), __uint_as_float(vc[19 + 4 * q])),
                                          tc::pk2(g.z, g.w));
-            tc::upk2(tc::geglu2(val0, g0), o[4 * q], o[4 * q + 1]);
-            tc::upk2(tc::geglu2(val1, g1), o[4 * q + 2], o[4 * q + 3]);
+            tc::upk2(tc::geglu2<FORM>(val0, g0), o[4 * q], o[4 * q + 1]);
+            tc::upk2(tc::geglu2<FORM>(val1, g1), o[4 * q + 2], o[4 * q + 3]);
           }
           // hidden columns [32 part + 16 half, +16) of the chunk = 16-byte chunks 4 part + 2 half + {0, 1} of the row
           tc::sts_chunk_bf16_sw128(hb, row, 4 * part + 2 * half, &o[0]);
@@ -411,7 +415,8 @@ int launch(const ealdm_ff_fused_args* a, cudaStream_t st) {
                 "ff_fused: pointers and row pitches must be 16-byte aligned");
   static DeviceOnce attr_set;
   if (attr_set.pending()) {
-    EALDM_CUDA(cudaFuncSetAttribute(ff_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    EALDM_CUDA(cudaFuncSetAttribute(ff_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    EALDM_CUDA(cudaFuncSetAttribute(ff_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr_set.done();
   }
   CUtensorMap tm[5];
@@ -435,7 +440,10 @@ int launch(const ealdm_ff_fused_args* a, cudaStream_t st) {
   EALDM_CUDA(cudaGetDevice(&dev));
   EALDM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int grid = p.m_tiles < sms ? p.m_tiles : sms;
-  ff_fused_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], p);
+  if (tc::get_option(EALDM_TC_OPT_GELU_ERF))
+    ff_fused_kernel<2><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], p);
+  else
+    ff_fused_kernel<1><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], p);
   EALDM_LAUNCH_CHECK();
   return 0;
 }

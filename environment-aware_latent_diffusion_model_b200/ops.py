@@ -692,3 +692,56 @@ def batch_norm_relu(x: Act, gamma: torch.Tensor, beta: torch.Tensor, running_mea
                                       running_mean.data_ptr(), running_var.data_ptr(), int(training), float(eps),
                                       int(relu), out.ptr, out.ld, _ptr(batch_stats), _stream()))
     return out
+
+
+def adain_bwd(x: Act, dy: Act, dstyle: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
+    """ealdm_adain_bwd: style gradient [n, 2c] = [dgamma | dbeta] of AdaIN (its input x is frozen)."""
+    lib = L.load()
+    assert x.dtype == torch.float32 and dy.dtype == torch.float32 and x.c == dy.c and x.rows == dy.rows
+    assert dstyle.dtype == torch.float32 and dstyle.stride(1) == 1 and tuple(dstyle.shape) == (x.n, 2 * x.c)
+    L.check(lib.ealdm_adain_bwd(x.ptr, x.ld, x.n, x.h * x.w, x.c, dy.ptr, dy.ld, float(eps), dstyle.data_ptr(),
+                                dstyle.stride(0), _stream()))
+    return dstyle
+
+
+def batch_norm_relu_bwd(x: Act, y: Act, dy: Act, dx: Act, gamma: torch.Tensor, running_mean: torch.Tensor,
+                        running_var: torch.Tensor, *, training: bool, eps: float = 1e-5, relu: bool = True,
+                        dgamma: Optional[torch.Tensor] = None, dbeta: Optional[torch.Tensor] = None) -> Act:
+    """ealdm_batch_norm_relu_bwd; dgamma / dbeta are accumulated into."""
+    lib = L.load()
+    for t in (x, y, dy, dx):
+        assert t.dtype == torch.float32 and t.rows == x.rows and t.c == x.c
+    L.check(lib.ealdm_batch_norm_relu_bwd(x.ptr, x.ld, x.rows, x.c, gamma.data_ptr(), running_mean.data_ptr(),
+                                          running_var.data_ptr(), int(training), float(eps), int(relu), y.ptr, y.ld,
+                                          dy.ptr, dy.ld, dx.ptr, dx.ld, _ptr(dgamma), _ptr(dbeta), _stream()))
+    return dx
+
+
+def lstm_cell_bwd(x: torch.Tensor, w_ih: torch.Tensor, b_ih: torch.Tensor, b_hh: torch.Tensor, dh: torch.Tensor,
+                  dgates: torch.Tensor, rec: Optional[torch.Tensor] = None, c_prev: Optional[torch.Tensor] = None,
+                  dc_next: Optional[torch.Tensor] = None, dc_prev: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """ealdm_lstm_cell_bwd: dgates [B, 4H] (pre-activation) of one LSTM step; dc_prev [B, H] when given."""
+    lib = L.load()
+    B, n_in = x.shape
+    H = w_ih.shape[0] // 4
+    assert x.dtype == torch.float32 and x.stride(1) == 1 and dh.stride(1) == 1 and tuple(dh.shape) == (B, H)
+    assert dgates.is_contiguous() and tuple(dgates.shape) == (B, 4 * H)
+    for t in (rec, c_prev, dc_next, dc_prev):
+        assert t is None or t.is_contiguous()
+    L.check(lib.ealdm_lstm_cell_bwd(x.data_ptr(), x.stride(0), B, n_in, w_ih.data_ptr(), b_ih.data_ptr(), b_hh.data_ptr(),
+                                    _ptr(rec), _ptr(c_prev), H, dh.data_ptr(), dh.stride(0), _ptr(dc_next),
+                                    dgates.data_ptr(), _ptr(dc_prev), _stream()))
+    return dgates
+
+
+def relu_bwd(y: torch.Tensor, dy: torch.Tensor, mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """ealdm_relu_bwd on 2-D fp32 tensors: dy * (y > 0) [* mask]."""
+    lib = L.load()
+    assert y.dim() == 2 and y.dtype == torch.float32 and y.stride(1) == 1 and dy.shape == y.shape and dy.stride(1) == 1
+    dx = torch.empty_like(y)
+    if mask is not None:
+        assert mask.shape == y.shape and mask.dtype == torch.float32 and mask.stride(1) == 1
+    L.check(lib.ealdm_relu_bwd(y.data_ptr(), y.stride(0), dy.data_ptr(), dy.stride(0), _ptr(mask),
+                               0 if mask is None else mask.stride(0), y.shape[0], y.shape[1], dx.data_ptr(),
+                               dx.stride(0), _stream()))
+    return dx

@@ -62,8 +62,11 @@ enum {
   EALDM_TC_OPT_WIDE = 1,         /* EALDM_TC_WIDE: 1 (default) 128-byte-row epilogue passes when there is no
                                     residual / shadow output, 0 one 32-column unit per TMA store */
   EALDM_TC_OPT_RELAXED_WAIT = 2, /* EALDM_TC_RELAXED_WAIT: 1 (default) one TMA store group may stay in flight */
-  EALDM_TC_OPT_BN = 3            /* EALDM_TC_BN: 0 (default) N tile chosen by wave count, 128 / 256 forced (for
+  EALDM_TC_OPT_BN = 3,           /* EALDM_TC_BN: 0 (default) N tile chosen by wave count, 128 / 256 forced (for
                                     n_out > 128), so that small test problems reach the 256-wide paths */
+  EALDM_TC_OPT_GELU_ERF = 4      /* EALDM_TC_GELU_ERF: the ONE switch that changes results (by <= 4.7e-4 absolute per
+                                    gated activation): 0 (default) GEGLU epilogues evaluate GELU in its tanh form on the
+                                    hardware tanh, 1 the exact-erf form (rational approximation, error 1.7e-6) */
 };
 int ealdm_tc_set_option(int option, int value);
 
@@ -300,6 +303,26 @@ int ealdm_adain(const float* x, int64_t ld_x, int64_t n, int64_t hw, int64_t c, 
 int ealdm_batch_norm_relu(const float* x, int64_t ld_x, int64_t rows, int64_t c, const float* gamma, const float* beta,
                           const float* running_mean, const float* running_var, int32_t training, float eps,
                           int32_t relu, float* y, int64_t ld_y, float* batch_stats, ealdm_stream_t stream);
+
+/* ---- adjoints of the conditioner pieces: the reference trains UnetCond together with the UNet
+ * (`cond_stage_trainable: true`, ldm/models/diffusion/ddpm.py:1409-1415).  The encoder that feeds AdaIN is frozen, so
+ * ealdm_adain_bwd returns the STYLE gradient only: dstyle[n, 2c] = [dgamma | dbeta] (STDiff/models.py:369-377). */
+int ealdm_adain_bwd(const float* x, int64_t ld_x, int64_t n, int64_t hw, int64_t c, const float* dy, int64_t ld_dy,
+                    float eps, float* dstyle, int64_t ld_dstyle, ealdm_stream_t stream);
+/* BatchNorm2d + ReLU adjoint (nn.BatchNorm2d of conv_cat, STDiff/models.py:480-483): `y` is the forward output; dgamma /
+ * dbeta ([c], optional) are ACCUMULATED into. */
+int ealdm_batch_norm_relu_bwd(const float* x, int64_t ld_x, int64_t rows, int64_t c, const float* gamma,
+                              const float* running_mean, const float* running_var, int32_t training, float eps,
+                              int32_t relu, const float* y, int64_t ld_y, const float* dy, int64_t ld_dy, float* dx,
+                              int64_t ld_dx, float* dgamma, float* dbeta, ealdm_stream_t stream);
+/* one nn.LSTM step backwards (gates recomputed from the forward's inputs): dgates [batch, 4 hidden] (pre-activation,
+ * order i, f, g, o) and dc_prev [batch, hidden] (optional) from dh, dc_next (optional); STDiff/models.py:323-336. */
+int ealdm_lstm_cell_bwd(const float* x, int64_t ld_x, int64_t batch, int64_t n_in, const float* w_ih, const float* b_ih,
+                        const float* b_hh, const float* rec, const float* c_prev, int64_t hidden, const float* dh,
+                        int64_t ld_dh, const float* dc_next, float* dgates, float* dc_prev, ealdm_stream_t stream);
+/* dx = dy * (y > 0) [* mask]: ReLU (+ inverted-dropout mask) adjoint of the conditioner's MLPs */
+int ealdm_relu_bwd(const float* y, int64_t ld_y, const float* dy, int64_t ld_dy, const float* mask, int64_t ld_mask,
+                   int64_t rows, int64_t c, float* dx, int64_t ld_dx, ealdm_stream_t stream);
 
 /* ---- sampler / diffusion elementwise (fp32, bit-exact with the reference's op sequence) -------- */
 /*
