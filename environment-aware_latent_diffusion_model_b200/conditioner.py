@@ -151,28 +151,39 @@ class UnetCond(nn.Module):
         return P
 
     # ---- pieces ------------------------------------------------------------------------------------------------------
-    def _lstm_mlp(self, p, x: torch.Tensor) -> torch.Tensor:
+    def _dropout(self, y: torch.Tensor, p: float = 0.1):
+        """nn.Dropout(0.1) of the two MLPs (models.py:320,492) in training mode: the mask is RNG plumbing (torch's
+        generator), kept as an inverted-dropout multiplier for the backward.  Returns (y * mask, mask)."""
+        if not self.training:
+            return y, None
+        mask = (torch.rand_like(y) >= p).to(torch.float32).mul_(1.0 / (1.0 - p))
+        return y * mask, mask
+
+    def _lstm_mlp(self, p, x: torch.Tensor, save: Optional[dict] = None) -> torch.Tensor:
         """WeatherLSTM.forward: x [B, S, in] -> [B*S, emb]"""
         dev = x.device
         B, S, _ = x.shape
         H = p["w_hh"].shape[1]
         hseq = torch.empty((B, S, H), dtype=torch.float32, device=dev)
-        c = [torch.empty((B, H), dtype=torch.float32, device=dev) for _ in range(2)]
-        rec = None
+        cs = [torch.empty((B, H), dtype=torch.float32, device=dev) for _ in range(S if save is not None else min(S, 2))]
+        recs = []
         for t in range(S):
+            rec = None
             if t > 0:
                 hp = hseq[:, t - 1].contiguous()
                 rec = torch.empty((B, 4 * H), dtype=torch.float32, device=dev)
                 ops.linear(Act(hp, 1, 1, B), p["w_hh"], Act(rec, 1, 1, B))
-            ops.lstm_cell(x[:, t], p["w_ih"], p["b_ih"], p["b_hh"], hseq[:, t], c[t & 1], rec=rec,
-                          c_prev=c[(t - 1) & 1] if t > 0 else None)
+            recs.append(rec)
+            ops.lstm_cell(x[:, t], p["w_ih"], p["b_ih"], p["b_hh"], hseq[:, t], cs[t % len(cs)], rec=rec,
+                          c_prev=cs[(t - 1) % len(cs)] if t > 0 else None)
         hs = hseq.reshape(B * S, H)
         y = torch.empty((B * S, p["fc0"][0].shape[0]), dtype=torch.float32, device=dev)
         ops.linear(Act(hs, 1, 1, B * S), p["fc0"][0], Act(y, 1, 1, B * S), bias=p["fc0"][1], act=L.ACT_RELU)
-        if self.training:
-            y = F.dropout(y, 0.1)       # RNG plumbing only (models.py:320); the mask comes from torch's generator
+        yd, mask = self._dropout(y)
         o = torch.empty((B * S, p["fc3"][0].shape[0]), dtype=torch.float32, device=dev)
-        ops.linear(Act(y, 1, 1, B * S), p["fc3"][0], Act(o, 1, 1, B * S), bias=p["fc3"][1])
+        ops.linear(Act(yd, 1, 1, B * S), p["fc3"][0], Act(o, 1, 1, B * S), bias=p["fc3"][1])
+        if save is not None:
+            save.update(x=x, hseq=hseq, cs=cs, recs=recs, y=y, yd=yd, mask=mask)
         return o
 
     def _encoder_features(self, img: torch.Tensor) -> Act:
@@ -188,24 +199,29 @@ class UnetCond(nn.Module):
             z = z32
         return z
 
-    @torch.no_grad()
+    def _own_named_parameters(self):
+        """The conditioner's own parameters (`convs.*` is the frozen first stage, ddpm.py:509-512,535-536)."""
+        return [(n, p) for n, p in self.named_parameters() if not n.startswith("convs.")]
+
     def forward(self, mixed, phase="train", return_intermediates=False):
+        """models.py:500-539.  With gradients enabled and trainable parameters the call goes through `_UnetCondFn`, whose
+        backward is the hand-written adjoint below (the reference trains the conditioner with the UNet,
+        ddpm.py:1409-1415); otherwise it is the plain no-grad forward."""
+        own = self._own_named_parameters()
+        if torch.is_grad_enabled() and not return_intermediates and any(p.requires_grad for _, p in own):
+            return _UnetCondFn.apply(self, mixed, *[p for _, p in own])
+        with torch.no_grad():
+            return self._forward_impl(mixed, return_intermediates=return_intermediates)
+
+    def _forward_impl(self, mixed, return_intermediates=False, save: Optional[dict] = None):
         if len(mixed) == 4:
             img, flow, weather, time = mixed
-            have_cond = mixed[-1] is not None
         else:
             img, flow, weather, time = mixed[:4]
-            have_cond = mixed[-1] is not None     # the negative branch passes (..., None): models.py:516, ddpm.py:1322-1324
+        have_cond = mixed[-1] is not None     # the negative branch passes (..., None): models.py:516, ddpm.py:886-888
         dev = self.out_layer[1].weight.device
         if dev.type != "cuda":
             raise RuntimeError("ealdm_b200.UnetCond runs on CUDA (sm_100a) only; there is no CPU fallback")
-        if self.training and not self._warned and any(p.requires_grad for p in self.out_layer.parameters()):
-            # be loud: a `cond_stage_trainable: true` run would otherwise train the UNet only without saying so
-            import warnings
-            warnings.warn("ealdm_b200.UnetCond: only the forward pass is built; the conditioner's parameters receive no "
-                          "gradients (DESIGN.md section 7). Freeze it (cond_stage_trainable: false) or train it with the "
-                          "reference module.", RuntimeWarning, stacklevel=2)
-            self._warned = True
         P = self._pack()
         img = img.squeeze(0).to(dev)
         z = self._encoder_features(img)                                        # [B, 32, 32, mid] NHWC fp32
@@ -213,16 +229,21 @@ class UnetCond(nn.Module):
         assert z.c == md and hw == 32 * 32, "out_layer is built for a 32 x 32 x mid_dim encoder output (models.py:489)"
         inter = {}
         feat = z
+        S = save if save is not None else None
+        if S is not None:
+            S.update(P=P, z=z, have_cond=have_cond, B=B)
         if have_cond:
             weather = weather.squeeze(0).float().to(dev)
             flow = flow.squeeze(0).float().to(dev)
             time = time.squeeze(0).float().to(dev).reshape(B, 1).contiguous()
             t_sty = torch.empty((B, self.emb_dim), dtype=torch.float32, device=dev)
+            four = torch.empty((B, 2 * self._freqs.numel()), dtype=torch.float32, device=dev) if S is not None else None
             ops.fourier_style(time, self._freqs.to(dev), bool(self.cond_args.get("include_lin", False)),
                               float(self.cond_args.get("lin_lr", 0.0)), P["scale_w"],
-                              self.scaled_styles.c_to_scales.weight_gain, t_sty)
-            f_sty = self._lstm_mlp(P["f_mlp"], flow)
-            w_sty = self._lstm_mlp(P["w_mlp"], weather)
+                              self.scaled_styles.c_to_scales.weight_gain, t_sty, features=four)
+            sf, sw = ({} if S is not None else None), ({} if S is not None else None)
+            f_sty = self._lstm_mlp(P["f_mlp"], flow, sf)
+            w_sty = self._lstm_mlp(P["w_mlp"], weather, sw)
             cat = Act(torch.empty((B * hw, 4 * md), dtype=torch.float32, device=dev), z.n, z.h, z.w)
             ops.copy2d(z, cat.cols(0, md))
             for k, (name, sty) in enumerate((("wadain", w_sty), ("fadain", f_sty), ("tadain", t_sty))):
@@ -237,6 +258,9 @@ class UnetCond(nn.Module):
             y1 = Act.empty(z.n, z.h, z.w, md, torch.float32, dev)
             ops.batch_norm_relu(y0, bn.weight.detach().float(), bn.bias.detach().float(), bn.running_mean, bn.running_var,
                                 y1, training=bn_train, eps=bn.eps, relu=True, batch_stats=stats)
+            if S is not None:   # the backward re-derives the statistics the forward normalised with
+                S.update(four=four, sf=sf, sw=sw, styles=(w_sty, f_sty, t_sty), cat=cat, y0=y0, y1=y1, bn_train=bn_train,
+                         bn_mean=bn.running_mean.clone(), bn_var=bn.running_var.clone())
             if bn_train and bn.track_running_stats:     # nn.BatchNorm2d side effect: momentum update, unbiased variance
                 mom = bn.momentum if bn.momentum is not None else 0.1
                 nrow = B * hw
@@ -252,12 +276,133 @@ class UnetCond(nn.Module):
         x2 = rows.view(B * md, hw)
         h1 = torch.empty((B * md, P["out1"][0].shape[0]), dtype=torch.float32, device=dev)
         ops.linear(Act(x2, 1, 1, B * md), P["out1"][0], Act(h1, 1, 1, B * md), bias=P["out1"][1], act=L.ACT_RELU)
-        if self.training:
-            h1 = F.dropout(h1, 0.1)      # models.py:492, RNG plumbing as above
+        h1d, mask1 = self._dropout(h1)       # models.py:492
         ctx = torch.empty((B * md, self.out_dim), dtype=torch.float32, device=dev)
-        ops.linear(Act(h1, 1, 1, B * md), P["out4"][0], Act(ctx, 1, 1, B * md), bias=P["out4"][1])
+        ops.linear(Act(h1d, 1, 1, B * md), P["out4"][0], Act(ctx, 1, 1, B * md), bias=P["out4"][1])
+        if S is not None:
+            S.update(x2=x2, h1=h1, h1d=h1d, mask1=mask1)
         ctx = ctx.view(B, md, self.out_dim)
         if return_intermediates:
             inter["mixed"] = rows
             return ctx, inter
         return ctx
+
+    # ---- adjoint -----------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def _backward_impl(self, S: dict, dctx: torch.Tensor):
+        """Gradients of every own parameter (dict name -> tensor) for d(loss)/d(context) = dctx [B, mid, out_dim].
+        Linear / conv data gradients run on the same conv kernels with transposed (and tap-flipped) weights, weight
+        gradients on ealdm_conv_wgrad (fp32), bias gradients on ealdm_colsum; AdaIN / BatchNorm+ReLU / LSTM-cell / ReLU
+        adjoints are the four kernels of csrc/cond.cu.  The frozen encoder output z receives no gradient."""
+        from .train import _pack_dgrad
+        P, z, B = S["P"], S["z"], S["B"]
+        dev, md, hw = dctx.device, self.mid_dim, z.h * z.w
+        f32 = torch.float32
+        ws = ops.Workspace(dev)
+        G = {n: torch.zeros_like(p, dtype=f32) for n, p in self._own_named_parameters()}
+        act2 = lambda t2: Act(t2, 1, 1, t2.shape[0])  # noqa: E731
+
+        linear_bwd = lambda *a, **k: self._linear_bwd(G, ws, *a, **k)  # noqa: E731
+
+        d2 = dctx.reshape(B * md, self.out_dim).float().contiguous()
+        dh1 = linear_bwd(S["h1d"], d2, "out_layer.4.weight", "out_layer.4.bias")
+        dpre1 = ops.relu_bwd(S["h1"], dh1, S["mask1"])
+        dx2 = linear_bwd(S["x2"], dpre1, "out_layer.1.weight", "out_layer.1.bias", need_dx=S["have_cond"])
+        if not S["have_cond"]:
+            return G
+        dfeat = Act.empty(z.n, z.h, z.w, md, f32, dev)
+        ops.nchw_to_nhwc(dx2.view(B, md, z.h, z.w), dfeat)
+        # conv_cat[3]: 3x3, mid -> mid (+ residual z, frozen)
+        w3 = self.conv_cat[3].weight
+        ops.conv_wgrad(S["y1"], dfeat, G["conv_cat.3.weight"].view(w3.shape[0], -1), ws, ksize=3, stride=1, pad=1)
+        ops.colsum(dfeat, G["conv_cat.3.bias"], ws)
+        dy1 = Act.empty(z.n, z.h, z.w, md, f32, dev)
+        ops.conv([ConvIn(dfeat, 3, 1, 1)], _pack_dgrad(w3, f32), dy1)
+        # BatchNorm2d + ReLU
+        bn = self.conv_cat[1]
+        dy0 = Act.empty(z.n, z.h, z.w, md, f32, dev)
+        ops.batch_norm_relu_bwd(S["y0"], S["y1"], dy1, dy0, bn.weight.detach().float(), S["bn_mean"], S["bn_var"],
+                                training=S["bn_train"], eps=bn.eps, relu=True, dgamma=G["conv_cat.1.weight"],
+                                dbeta=G["conv_cat.1.bias"])
+        # conv_cat[0]: 3x3, 4 mid -> mid over [z | AdaIN_w | AdaIN_f | AdaIN_t]
+        w0 = self.conv_cat[0].weight
+        ops.conv_wgrad(S["cat"], dy0, G["conv_cat.0.weight"].view(w0.shape[0], -1), ws, ksize=3, stride=1, pad=1)
+        ops.colsum(dy0, G["conv_cat.0.bias"], ws)
+        dcat = Act.empty(z.n, z.h, z.w, 4 * md, f32, dev)
+        ops.conv([ConvIn(dy0, 3, 1, 1)], _pack_dgrad(w0, f32), dcat)
+        dsty = []
+        for k, (name, sty) in enumerate(zip(("wadain", "fadain", "tadain"), S["styles"])):
+            daff = torch.empty((B, 2 * md), dtype=f32, device=dev)
+            ops.adain_bwd(z, dcat.cols((k + 1) * md, md), daff, eps=1e-5)
+            dsty.append(linear_bwd(sty, daff, f"{name}.linear.weight", f"{name}.linear.bias"))
+        dw_sty, df_sty, dt_sty = dsty
+        # CondScale: t_sty = fourier(time) (W gain)^T
+        gw = G["scaled_styles.c_to_scales.weight"]
+        tmp = torch.zeros_like(gw)
+        ops.linear_wgrad(act2(S["four"]), act2(dt_sty), tmp, ws)
+        gw.add_(tmp, alpha=float(self.scaled_styles.c_to_scales.weight_gain))
+        for prefix, sv, do in (("f_mlp", S["sf"], df_sty), ("w_mlp", S["sw"], dw_sty)):
+            self._lstm_mlp_bwd(prefix, P[prefix], sv, do, G, ws, linear_bwd)
+        return G
+
+    def _linear_bwd(self, G, ws, x2d, dy2d, wname, bname, need_dx=True):
+        """y = x W^T + b: accumulates dW into G[wname] and db into G[bname]; returns dx = dy W."""
+        from .train import _pack_dgrad
+        w = self.get_parameter(wname)
+        act2 = lambda t2: Act(t2, 1, 1, t2.shape[0])  # noqa: E731
+        ops.linear_wgrad(act2(x2d), act2(dy2d), G[wname].view(w.shape[0], -1), ws)
+        if bname is not None:
+            ops.colsum(act2(dy2d), G[bname], ws)
+        if not need_dx:
+            return None
+        dx = torch.empty((dy2d.shape[0], w.shape[1]), dtype=torch.float32, device=dy2d.device)
+        ops.linear(act2(dy2d), _pack_dgrad(w, torch.float32), act2(dx))
+        return dx
+
+    def _lstm_mlp_bwd(self, prefix, p, sv, do, G, ws, linear_bwd):
+        """WeatherLSTM adjoint: Linear - (Dropout) - ReLU - Linear, then back-propagation through time."""
+        from .train import _pack_dgrad
+        dev, f32 = do.device, torch.float32
+        x, hseq, cs, recs = sv["x"], sv["hseq"], sv["cs"], sv["recs"]
+        B, Sq, H = hseq.shape
+        dyd = linear_bwd(sv["yd"], do, f"{prefix}.fc.3.weight", f"{prefix}.fc.3.bias")
+        dpre = ops.relu_bwd(sv["y"], dyd, sv["mask"])
+        dhs = linear_bwd(hseq.reshape(B * Sq, H), dpre, f"{prefix}.fc.0.weight", f"{prefix}.fc.0.bias").view(B, Sq, H)
+        w_hh_t = _pack_dgrad(p["w_hh"], f32) if Sq > 1 else None
+        dh_rec, dc_next = None, None
+        act2 = lambda t2: Act(t2, 1, 1, t2.shape[0])  # noqa: E731
+        for t in range(Sq - 1, -1, -1):
+            dh = dhs[:, t] if dh_rec is None else (dhs[:, t] + dh_rec)
+            dgates = torch.empty((B, 4 * H), dtype=f32, device=dev)
+            dc_prev = torch.empty((B, H), dtype=f32, device=dev) if t > 0 else None
+            ops.lstm_cell_bwd(x[:, t], p["w_ih"], p["b_ih"], p["b_hh"], dh, dgates, rec=recs[t],
+                              c_prev=cs[t - 1] if t > 0 else None, dc_next=dc_next, dc_prev=dc_prev)
+            xt = x[:, t].contiguous()
+            ops.linear_wgrad(act2(xt), act2(dgates), G[f"{prefix}.lstm.weight_ih_l0"], ws)
+            ops.colsum(act2(dgates), G[f"{prefix}.lstm.bias_ih_l0"], ws)
+            ops.colsum(act2(dgates), G[f"{prefix}.lstm.bias_hh_l0"], ws)
+            if t > 0:
+                ops.linear_wgrad(act2(hseq[:, t - 1].contiguous()), act2(dgates), G[f"{prefix}.lstm.weight_hh_l0"], ws)
+                dh_rec = torch.empty((B, H), dtype=f32, device=dev)
+                ops.linear(act2(dgates), w_hh_t, act2(dh_rec))
+            dc_next = dc_prev
+
+
+class _UnetCondFn(torch.autograd.Function):
+    """UnetCond.forward under torch.autograd: the parameters are inputs so that `loss.backward()` (the UNet's own
+    hand-written backward hands back d(loss)/d(context)) reaches them."""
+
+    @staticmethod
+    def forward(ctx, module, mixed, *params):
+        saved = {}
+        out = module._forward_impl(mixed, save=saved)
+        ctx.module, ctx.saved = module, saved
+        ctx.names = [n for n, _ in module._own_named_parameters()]
+        return out
+
+    @staticmethod
+    def backward(ctx, dctx):
+        G = ctx.module._backward_impl(ctx.saved, dctx.contiguous())
+        ctx.saved = None
+        needs = ctx.needs_input_grad[2:]
+        return (None, None) + tuple(G[n] if need else None for n, need in zip(ctx.names, needs))

@@ -181,3 +181,80 @@ def test_shipped_config_conditioner_to_sampler_pipeline():
                           unconditional_guidance_scale=2.0, unconditional_conditioning=uc)
     x = model.decode_first_stage(z)
     assert x.shape == (B, 3, 256, 256) and torch.isfinite(x).all()
+
+
+# ---- adjoint (the reference trains the conditioner with the UNet, ddpm.py:1409-1415) -----------------------------------
+def _check_grad(name, got, want, tol=2e-4):
+    """`want` is a golden entry of oracle/gen_golden_cond_grads.py: the full tensor, or {norm, 4 projections, sample}."""
+    from oracle.gen_golden_cond_grads import SAMPLE_STRIDE, direction
+    got = got.detach().cpu()
+    if "full" in want:
+        ref = want["full"]
+        if float(ref.abs().max()) == 0.0:
+            assert float(got.abs().max()) == 0.0, name
+            return 0.0
+        err = rel_l2(got, ref)
+    else:
+        gd = got.double()
+        scale = max(want["norm"], 1e-30)
+        errs = [abs(float(gd.norm()) - want["norm"]) / scale]
+        errs += [abs(float((gd * direction(name, k, got.shape).double()).sum()) - want["proj"][k]) / scale for k in range(4)]
+        errs.append(float((got.reshape(-1)[::SAMPLE_STRIDE].double() - want["sample"].double()).norm()
+                          / max(float(want["sample"].double().norm()), 1e-30)))
+        err = max(errs)
+    assert err < tol, (name, err)
+    return err
+
+
+@pytest.mark.parametrize("case", ["eval", "bn_train", "negative"])
+def test_conditioner_gradients_vs_reference_autograd(case):
+    """loss = sum(context * R): every own parameter's gradient from the hand-written adjoint (through torch.autograd:
+    `_UnetCondFn`) against torch.autograd through the reference's own UnetCond (oracle/gen_golden_cond_grads.py)."""
+    G = gold()
+    GG = torch.load(os.path.join(GOLD, "conditioner_grads.pt"), weights_only=False)
+    m = make_cond(_GivenEncoder(G["z"]))
+    m.eval()                                  # Dropout off in every case (its mask is RNG plumbing)
+    if case == "bn_train":
+        m.conv_cat[1].train()
+    T = G["T"]
+    dummy = torch.zeros(T, 3, 8, 8)
+    seed = GG["seeds"]["R_neg" if case == "negative" else "R"]
+    R = torch.randn(T, 4, 512, generator=torch.Generator().manual_seed(seed)).cuda()
+    mixed = ([dummy, G["flow"], G["weather"], G["time"], None, None, None, None] if case == "negative"
+             else (dummy, G["flow"], G["weather"], G["time"]))
+    for p in m.parameters():
+        p.grad = None
+    ctx = m(mixed)
+    assert ctx.requires_grad
+    want_ctx = GG["context_negative" if case == "negative" else f"context_{case}"]
+    assert rel_l2(ctx, want_ctx) < 1e-4
+    (ctx * R).sum().backward()
+    worst = ("", 0.0)
+    for name, p in m.named_parameters():
+        if name.startswith("convs."):
+            continue
+        got = p.grad if p.grad is not None else torch.zeros_like(p)
+        err = _check_grad(name, got, GG[case][name])
+        if err > worst[1]:
+            worst = (name, err)
+    print(f"conditioner gradients [{case}]: worst relative error {worst[1]:.3e} ({worst[0]})")
+
+
+def test_weather_lstm_backpropagation_through_time_vs_reference_autograd():
+    """WeatherLSTM over a 4-step sequence (the shipped data has one step per frame): BPTT through ealdm_lstm_cell_bwd."""
+    from ealdm_b200 import ops
+    G = gold()
+    GG = torch.load(os.path.join(GOLD, "conditioner_grads.pt"), weights_only=False)
+    m = make_cond(_GivenEncoder(G["z"])).eval()
+    seq = G["lstm_seq_in"].cuda()
+    Rs = torch.randn(seq.shape[0] * seq.shape[1], 128, generator=torch.Generator().manual_seed(GG["seeds"]["R_seq"])).cuda()
+    P = m._pack()
+    sv = {}
+    with torch.no_grad():
+        out = m._lstm_mlp(P["w_mlp"], seq, sv)
+        assert rel_l2(out, G["lstm_seq_out"]) < 1e-5
+        grads = {n: torch.zeros_like(p, dtype=torch.float32) for n, p in m._own_named_parameters()}
+        ws = ops.Workspace(seq.device)
+        m._lstm_mlp_bwd("w_mlp", P["w_mlp"], sv, Rs, grads, ws, lambda *a, **k: m._linear_bwd(grads, ws, *a, **k))
+    worst = max(_check_grad(n, grads[n], GG["lstm_seq"][n]) for n in GG["lstm_seq"])
+    print(f"WeatherLSTM BPTT over 4 steps: worst relative error {worst:.3e}")

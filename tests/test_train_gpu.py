@@ -299,7 +299,7 @@ def test_fused_optimizer_and_ema_checkpoint_round_trip():
     assert int(ck["ema"]["num_updates"]) == 3 and len(ck["ema"]) == len(list(unet.parameters())) + 2
     steps(gb, opt, 2, 12)                 # the continued run
     want = {k: v.clone() for k, v in unet.state_dict().items()}
-    want_ema = opt.ema.clone()
+    want_ema = {n: opt.ema_views()[id(p)].clone() for n, p in unet.named_parameters()}
     # resume from the checkpoint in a new process' worth of objects
     unet2, gb2, opt2, ema2 = make(1)
     unet2.load_state_dict(ck["model"])
@@ -309,4 +309,6 @@ def test_fused_optimizer_and_ema_checkpoint_round_trip():
     steps(gb2, opt2, 2, 12)
     for k, v in unet2.state_dict().items():
         assert torch.equal(v, want[k]), k
-    assert torch.equal(opt2.ema, want_ema)
+    views2 = opt2.ema_views()      # (the flat buffers also hold alignment padding, which no checkpoint carries)
+    for n, p in unet2.named_parameters():
+        assert torch.equal(views2[id(p)], want_ema[n]), n

@@ -121,6 +121,19 @@ def make_ln(rows, c, x_dt=F32):
     return run, 0.0, bsz(x.buf) + bsz(y.buf)
 
 
+def make_ff_fused(M, out_dt=BF):
+    """FF1 -> GEGLU -> FF2 -> + residual in one kernel (c = 256): algorithmic bytes = x + weights + residual + out."""
+    x = Act(rnd(M, 256, BF), 1, 1, M)
+    w1, b1 = rnd(2048, 256, BF) * 0.1, torch.randn(2048, device=DEV)
+    w2, b2 = rnd(256, 1024, BF) * 0.1, torch.randn(256, device=DEV)
+    res = Act(rnd(M, 256, F32), 1, 1, M)
+    out = Act(torch.empty(M, 256, device=DEV, dtype=out_dt), 1, 1, M)
+
+    def run():
+        ops.ff_geglu_fused(x, w1, b1, w2, b2, res, out)
+    return run, 2.0 * M * (2048 * 256 + 256 * 1024), bsz(x.buf) + bsz(w1) + bsz(w2) + bsz(res.buf) + bsz(out.buf)
+
+
 N = 128  # UNet batch of the headline config (B=64, CFG)
 CASES = {
     # level 0 transformer GEMMs (131072 tokens x 256)
@@ -130,6 +143,8 @@ CASES = {
     "gemm_projout_l0": lambda: make_gemm(N * 1024, 256, 256, out_dt=F32, res_dt=F32, out2=True),
     "gemm_ff1_l0": lambda: make_gemm(N * 1024, 256, 2048, act=L.ACT_GEGLU),
     "gemm_ff2_l0": lambda: make_gemm(N * 1024, 1024, 256, out_dt=F32, res_dt=F32),
+    "gemm_ff2bf_l0": lambda: make_gemm(N * 1024, 1024, 256, out_dt=BF, res_dt=F32),
+    "ff_fused_l0": lambda: make_ff_fused(N * 1024),
     # level 1 / 2
     "gemm_o1_l1": lambda: make_gemm(N * 256, 512, 512, out_dt=F32, res_dt=F32),
     "gemm_ff1_l1": lambda: make_gemm(N * 256, 512, 4096, act=L.ACT_GEGLU),
