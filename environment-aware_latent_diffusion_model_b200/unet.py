@@ -353,7 +353,9 @@ class UNetEngine:
     sequence of libealdm_b200 launches on the current CUDA stream (CUDA-graph capturable: no host
     synchronisation, no data-dependent control flow)."""
     _fused_geglu = True   # the training engine keeps the GEGLU pre-activation instead (train.py)
-    _fused_ff = not os.environ.get("EALDM_NO_FUSED_FF")                   # A/B switch: one-kernel GEGLU FeedForward
+    # one-kernel GEGLU FeedForward (csrc/ff_fused.cu): bit-identical to the two GEMMs and measured NOT faster yet
+    # (269 us against 140 + 95 us at level 0, DESIGN.md section 4), hence opt-in
+    _fused_ff = bool(os.environ.get("EALDM_FUSED_FF"))
     _phased_upsample = not os.environ.get("EALDM_NO_PHASED_UPSAMPLE")   # A/B switch; the training engine saves `up`
 
     def __init__(self, m: UNetModel, dtype: torch.dtype):

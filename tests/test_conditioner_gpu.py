@@ -184,8 +184,10 @@ def test_shipped_config_conditioner_to_sampler_pipeline():
 
 
 # ---- adjoint (the reference trains the conditioner with the UNet, ddpm.py:1409-1415) -----------------------------------
-def _check_grad(name, got, want, tol=2e-4):
-    """`want` is a golden entry of oracle/gen_golden_cond_grads.py: the full tensor, or {norm, 4 projections, sample}."""
+def _check_grad(name, got, want, tol=2e-4, floor=0.0):
+    """`want` is a golden entry of oracle/gen_golden_cond_grads.py: the full tensor, or {norm, 4 projections, sample}.
+    `floor`: gradients whose golden norm is below it are pure rounding noise (a bias in front of a batch-statistics
+    BatchNorm has an exactly zero gradient) and are compared on that absolute scale."""
     from oracle.gen_golden_cond_grads import SAMPLE_STRIDE, direction
     got = got.detach().cpu()
     if "full" in want:
@@ -193,7 +195,7 @@ def _check_grad(name, got, want, tol=2e-4):
         if float(ref.abs().max()) == 0.0:
             assert float(got.abs().max()) == 0.0, name
             return 0.0
-        err = rel_l2(got, ref)
+        err = float((got.double() - ref.double()).norm() / max(float(ref.double().norm()), floor))
     else:
         gd = got.double()
         scale = max(want["norm"], 1e-30)
@@ -230,11 +232,12 @@ def test_conditioner_gradients_vs_reference_autograd(case):
     assert rel_l2(ctx, want_ctx) < 1e-4
     (ctx * R).sum().backward()
     worst = ("", 0.0)
+    scale = max((float(v["full"].norm()) if "full" in v else v["norm"]) for v in GG[case].values())
     for name, p in m.named_parameters():
         if name.startswith("convs."):
             continue
         got = p.grad if p.grad is not None else torch.zeros_like(p)
-        err = _check_grad(name, got, GG[case][name])
+        err = _check_grad(name, got, GG[case][name], floor=1e-4 * scale)
         if err > worst[1]:
             worst = (name, err)
     print(f"conditioner gradients [{case}]: worst relative error {worst[1]:.3e} ({worst[0]})")
