@@ -20,7 +20,7 @@ TC_OPT_CTA2, TC_OPT_WIDE, TC_OPT_RELAXED_WAIT, TC_OPT_BN, TC_OPT_GELU_ERF = 0, 1
 
 EXPORTS = [
     "ealdm_abi_version", "ealdm_last_error", "ealdm_device_check", "ealdm_launch_count", "ealdm_tc_set_option",
-    "ealdm_conv", "ealdm_ff_geglu_fused", "ealdm_group_norm", "ealdm_group_norm_workspace_bytes", "ealdm_layer_norm", "ealdm_attention",
+    "ealdm_conv", "ealdm_conv_ln_parts", "ealdm_ff_geglu_fused", "ealdm_group_norm", "ealdm_group_norm_workspace_bytes", "ealdm_layer_norm", "ealdm_attention",
     "ealdm_timestep_embedding", "ealdm_nchw_to_nhwc", "ealdm_nhwc_to_nchw",
     "ealdm_upsample_nearest2x", "ealdm_copy2d", "ealdm_softmax_rows", "ealdm_ddim_step",
     "ealdm_q_sample", "ealdm_cfg_mse",
@@ -51,7 +51,9 @@ class ConvArgs(C.Structure):
                 ("residual", C.c_void_p), ("ld_res", C.c_int64), ("out", C.c_void_p),
                 ("ld_out", C.c_int64), ("out_f32", C.c_int32), ("res_f32", C.c_int32),
                 ("out2", C.c_void_p), ("ld_out2", C.c_int64), ("gn_partial", C.c_void_p), ("gn_ld", C.c_int64),
-                ("weight_adjoint", C.c_int32), ("upsample_phases", C.c_int32), ("ld_weight", C.c_int64)]
+                ("weight_adjoint", C.c_int32), ("upsample_phases", C.c_int32), ("ld_weight", C.c_int64),
+                ("ln_partial_out", C.c_void_p), ("ln_partial_in", C.c_void_p), ("ln_parts_in", C.c_int64),
+                ("ln_c1", C.c_void_p), ("ln_channels", C.c_int64), ("ln_eps", C.c_float), ("reserved3", C.c_int32)]
 
 
 class GroupNormArgs(C.Structure):
@@ -170,6 +172,8 @@ def _declare(lib):
     lib.ealdm_launch_count.argtypes = []
     lib.ealdm_tc_set_option.restype = C.c_int
     lib.ealdm_tc_set_option.argtypes = [C.c_int, C.c_int]
+    lib.ealdm_conv_ln_parts.restype = C.c_int64
+    lib.ealdm_conv_ln_parts.argtypes = [C.POINTER(ConvArgs)]
     lib.ealdm_group_norm_workspace_bytes.restype = C.c_int64
     lib.ealdm_group_norm_workspace_bytes.argtypes = [i64, i64, i64]
     for name, argt in [

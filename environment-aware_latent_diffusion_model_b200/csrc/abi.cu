@@ -21,6 +21,7 @@ namespace tc {
 bool supported(const ealdm_conv_args* a);
 int launch(const ealdm_conv_args* a, cudaStream_t st);
 int set_option(int option, int value);
+int ln_parts(const ealdm_conv_args* a);
 }  // namespace tc
 namespace simt {
 int launch(const ealdm_conv_args* a, cudaStream_t st);
@@ -47,6 +48,11 @@ extern "C" int ealdm_device_check(void) {
                      "device %d is sm_%d%d; libealdm_b200 contains sm_100a code only", dev, major,
                      minor);
   return 0;
+}
+
+extern "C" int64_t ealdm_conv_ln_parts(const ealdm_conv_args* a) {
+  if (a == nullptr) return set_error(EALDM_EINVAL, "conv_ln_parts: null args");
+  return tc::ln_parts(a);
 }
 
 extern "C" int ealdm_conv(const ealdm_conv_args* a, ealdm_stream_t stream) {
@@ -78,6 +84,9 @@ extern "C" int ealdm_conv(const ealdm_conv_args* a, ealdm_stream_t stream) {
                   "conv: weight_adjoint needs the tcgen05 path (bf16, one source, c %% 64 == 0, n_out %% 64 == 0)");
     return tc::launch(a, st);
   }
+  EALDM_REQUIRE(!(a->ln_partial_out || a->ln_partial_in) ||
+                    (a->impl != EALDM_IMPL_SIMT && a->dtype == EALDM_BF16 && tc::supported(a)),
+                "conv: a folded LayerNorm (ln_partial_*) needs the tcgen05 path in linear geometry");
   if (a->impl == EALDM_IMPL_SIMT) return simt::launch(a, st);
   if (a->impl == EALDM_IMPL_TCGEN05) return tc::launch(a, st);
   if (a->dtype == EALDM_BF16 && tc::supported(a)) return tc::launch(a, st);

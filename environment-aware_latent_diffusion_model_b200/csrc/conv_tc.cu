@@ -95,6 +95,19 @@ struct Params {
   // (and its shadow) is addressed through 5-D tensor maps (C, px, W/2, py, N * H/2).
   int phases;
   int gn_phase_chunks;  // 32-pixel chunks of the low-resolution grid per image: phase p fills chunks [p * this, ...)
+  // LayerNorm folded into the GEMMs around it (linear geometry only: h_out = 1, one "image", row = output pixel).
+  // PRODUCER side (ln_out): the epilogue that writes the fp32 token stream also writes, per row and per (N tile, warp
+  // half), {sum, sum of squares} of its columns: ln_out[row * ln_out_parts + 2 * nt + part].
+  // CONSUMER side (ln_in): A is the RAW stream (its bf16 shadow), W was packed as W * gamma, `bias` holds
+  // W beta (+ bias), ln_c1[col] = sum_k (W * gamma)[col, k]; with mu, rstd of the row from the partials
+  //   out = rstd * acc - rstd * mu * c1[col] + bias[col]  ==  LayerNorm(x) W^T + bias
+  float2* ln_out;
+  int ln_out_parts;
+  const float2* ln_in;
+  int ln_in_parts;
+  float ln_inv_c;   // 1 / (channels the LayerNorm runs over)
+  float ln_eps;
+  const float* ln_c1;
 };
 
 // CTA2: the tile is 256 x BN over a CTA pair (cta_group::2); each CTA stages its 128 A rows and BN/2 B rows
@@ -368,6 +381,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     uint8_t* ebuf = smem + C::EPI_OFF + ew * EPI_WARP_BYTES;
     uint8_t* o2buf = ebuf + 2 * EBUF_BYTES;
     float* bias_s = reinterpret_cast<float*>(smem + C::BIAS_OFF);
+    // c1 of a folded LayerNorm, staged like the bias; lives in epilogue warp 0's shadow buffer (ln_in excludes out2)
+    float* c1_s = reinterpret_cast<float*>(smem + C::EPI_OFF + 2 * EBUF_BYTES);
     uint64_t* rbar = res_bar + 2 * ew;
     // a unit: 32 accumulator columns (GEGLU: 64 -> 32 output columns)
     constexpr int UNITS = GEGLU ? BN / 64 : BN / 32;
@@ -410,9 +425,33 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         float bv0 = (p.bias != nullptr && col < p.N) ? __ldg(p.bias + col) : 0.f;
         if (GEGLU && (etid & 16) == 0) bv0 *= 0.5f;  // value columns: the epilogue computes 0.5 v + 0.5 bias (geglu2)
         bias_s[acc * BN + etid] = bv0;
+        if (p.ln_in != nullptr) {
+          float cv = col < p.N ? __ldg(p.ln_c1 + col) : 0.f;
+          if (GEGLU && (etid & 16) == 0) cv *= 0.5f;
+          c1_s[acc * BN + etid] = cv;
+        }
       }
+      // LayerNorm folded into this GEMM: mean / rstd of this thread's row from the producer's partial sums
+      float ln_r = 1.f, ln_nm = 0.f;   // out = ln_r * acc + ln_nm * c1 + bias
+      if (p.ln_in != nullptr) {
+        int row = w + lane;             // linear geometry: the unit's rows are consecutive output pixels
+        if (row >= p.Wout) row = p.Wout - 1;
+        const float2* lp = p.ln_in + static_cast<long long>(row) * p.ln_in_parts;
+        float s = 0.f, ss = 0.f;
+        for (int i = 0; i < p.ln_in_parts; ++i) {
+          const float2 t = __ldg(lp + i);
+          s += t.x;
+          ss += t.y;
+        }
+        const float mu = s * p.ln_inv_c;
+        const float var = fmaxf(ss * p.ln_inv_c - mu * mu, 0.f);
+        ln_r = rsqrtf(var + p.ln_eps);
+        ln_nm = -ln_r * mu;
+      }
+      float ln_s = 0.f, ln_ss = 0.f;   // producer side: this thread's row sums over the columns this warp owns
       ptx::named_bar_sync(1, 32 * EPI_WARPS);
       const float* bs = bias_s + acc * BN;
+      const float* cs = c1_s + acc * BN;
       const float* rv = nullptr;
       if (!GEGLU && p.rowvec != nullptr) {
         int img = (n - sn0) + my_dn;
@@ -434,7 +473,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             __syncwarp();
             uint32_t v[2][32];
             ptx::tmem_ld_32x32(taddr0 + (part * 4) * 32, v[0]);
-            const uint64_t half2 = pk2(0.5f, 0.5f);
+            // value = 0.5 (ln_r acc + ln_nm c1 + bias), gate = ln_r acc + ln_nm c1 + bias (without a folded LayerNorm
+            // ln_r = 1 and the c1 term is skipped; the staged value-column constants are pre-halved)
+            const bool ln = p.ln_in != nullptr;
+            const uint64_t half2 = pk2(0.5f * ln_r, 0.5f * ln_r), one2 = pk2(ln_r, ln_r), nm2 = pk2(ln_nm, ln_nm);
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
               const int ch = part * 4 + c;
@@ -446,14 +488,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
               for (int j = 0; j < 4; ++j) {
                 const float4 t = *reinterpret_cast<const float4*>(bs + ch * 32 + 4 * j);
                 const float4 g = *reinterpret_cast<const float4*>(bs + ch * 32 + 16 + 4 * j);
-                const uint64_t val0 = fma2(pk2(__uint_as_float(vc[4 * j]), __uint_as_float(vc[4 * j + 1])), half2,
-                                           pk2(t.x, t.y));
-                const uint64_t val1 = fma2(pk2(__uint_as_float(vc[4 * j + 2]), __uint_as_float(vc[4 * j + 3])), half2,
-                                           pk2(t.z, t.w));
+                uint64_t tv0 = pk2(t.x, t.y), tv1 = pk2(t.z, t.w), tg0 = pk2(g.x, g.y), tg1 = pk2(g.z, g.w);
+                if (ln) {
+                  const float4 ct = *reinterpret_cast<const float4*>(cs + ch * 32 + 4 * j);
+                  const float4 cg = *reinterpret_cast<const float4*>(cs + ch * 32 + 16 + 4 * j);
+                  tv0 = fma2(nm2, pk2(ct.x, ct.y), tv0);
+                  tv1 = fma2(nm2, pk2(ct.z, ct.w), tv1);
+                  tg0 = fma2(nm2, pk2(cg.x, cg.y), tg0);
+                  tg1 = fma2(nm2, pk2(cg.z, cg.w), tg1);
+                }
+                const uint64_t val0 = fma2(pk2(__uint_as_float(vc[4 * j]), __uint_as_float(vc[4 * j + 1])), half2, tv0);
+                const uint64_t val1 =
+                    fma2(pk2(__uint_as_float(vc[4 * j + 2]), __uint_as_float(vc[4 * j + 3])), half2, tv1);
                 const uint64_t g0 =
-                    add2(pk2(__uint_as_float(vc[16 + 4 * j]), __uint_as_float(vc[17 + 4 * j])), pk2(g.x, g.y));
+                    fma2(pk2(__uint_as_float(vc[16 + 4 * j]), __uint_as_float(vc[17 + 4 * j])), one2, tg0);
                 const uint64_t g1 =
-                    add2(pk2(__uint_as_float(vc[18 + 4 * j]), __uint_as_float(vc[19 + 4 * j])), pk2(g.z, g.w));
+                    fma2(pk2(__uint_as_float(vc[18 + 4 * j]), __uint_as_float(vc[19 + 4 * j])), one2, tg1);
                 upk2(geglu2<GEGLU>(val0, g0), o[4 * j], o[4 * j + 1]);
                 upk2(geglu2<GEGLU>(val1, g1), o[4 * j + 2], o[4 * j + 3]);
               }
@@ -498,8 +548,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                         }
                       }
                     }
+                    if (p.ln_in != nullptr) {   // folded LayerNorm: ln_r * acc + ln_nm * c1 + bias
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) r[j] += __uint_as_float(vc[j]);
+                      for (int j = 0; j < 8; ++j) {
+                        const float4 t = *reinterpret_cast<const float4*>(cs + ku * 32 + 4 * j);
+                        r[4 * j] = fmaf(ln_nm, t.x, r[4 * j]); r[4 * j + 1] = fmaf(ln_nm, t.y, r[4 * j + 1]);
+                        r[4 * j + 2] = fmaf(ln_nm, t.z, r[4 * j + 2]); r[4 * j + 3] = fmaf(ln_nm, t.w, r[4 * j + 3]);
+                      }
+#pragma unroll
+                      for (int j = 0; j < 32; ++j) r[j] = fmaf(__uint_as_float(vc[j]), ln_r, r[j]);
+                    } else {
+#pragma unroll
+                      for (int j = 0; j < 32; ++j) r[j] += __uint_as_float(vc[j]);
+                    }
                   } else {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
@@ -548,21 +609,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             uint32_t v[32];
             ptx::tmem_ld_32x32(taddr0 + ch * 32, v);
             uint64_t bv[8], bg[8];
+            const uint64_t nm2 = pk2(ln_nm, ln_nm);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const float4 t = *reinterpret_cast<const float4*>(bs + ch * 32 + 4 * j);
               bv[2 * j] = pk2(t.x, t.y); bv[2 * j + 1] = pk2(t.z, t.w);
               const float4 g = *reinterpret_cast<const float4*>(bs + ch * 32 + 16 + 4 * j);
               bg[2 * j] = pk2(g.x, g.y); bg[2 * j + 1] = pk2(g.z, g.w);
+              if (p.ln_in != nullptr) {   // folded LayerNorm: + ln_nm * c1 (value-column constants are pre-halved)
+                const float4 ct = *reinterpret_cast<const float4*>(cs + ch * 32 + 4 * j);
+                bv[2 * j] = fma2(nm2, pk2(ct.x, ct.y), bv[2 * j]); bv[2 * j + 1] = fma2(nm2, pk2(ct.z, ct.w), bv[2 * j + 1]);
+                const float4 cg = *reinterpret_cast<const float4*>(cs + ch * 32 + 16 + 4 * j);
+                bg[2 * j] = fma2(nm2, pk2(cg.x, cg.y), bg[2 * j]); bg[2 * j + 1] = fma2(nm2, pk2(cg.z, cg.w), bg[2 * j + 1]);
+              }
             }
             ptx::tmem_ld_wait();
             float o[16];
-            const uint64_t half2 = pk2(0.5f, 0.5f);
+            const uint64_t half2 = pk2(0.5f * ln_r, 0.5f * ln_r), one2 = pk2(ln_r, ln_r);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const uint64_t val =
                   fma2(pk2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), half2, bv[j]);
-              const uint64_t g = add2(pk2(__uint_as_float(v[16 + 2 * j]), __uint_as_float(v[17 + 2 * j])), bg[j]);
+              const uint64_t g = fma2(pk2(__uint_as_float(v[16 + 2 * j]), __uint_as_float(v[17 + 2 * j])), one2, bg[j]);
               upk2(geglu2<GEGLU>(val, g), o[2 * j], o[2 * j + 1]);
             }
             sts_chunk_bf16(eb, lane, 2 * half, &o[0]);
@@ -607,8 +675,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
               }
             }
             ptx::tmem_ld_wait();
+            if (p.ln_in != nullptr) {   // folded LayerNorm: ln_r * acc + ln_nm * c1 + bias
 #pragma unroll
-            for (int j = 0; j < 32; ++j) r[j] += __uint_as_float(v[j]);
+              for (int j = 0; j < 8; ++j) {
+                const float4 t = *reinterpret_cast<const float4*>(cs + ku * 32 + 4 * j);
+                r[4 * j] = fmaf(ln_nm, t.x, r[4 * j]); r[4 * j + 1] = fmaf(ln_nm, t.y, r[4 * j + 1]);
+                r[4 * j + 2] = fmaf(ln_nm, t.z, r[4 * j + 2]); r[4 * j + 3] = fmaf(ln_nm, t.w, r[4 * j + 3]);
+              }
+#pragma unroll
+              for (int j = 0; j < 32; ++j) r[j] = fmaf(__uint_as_float(v[j]), ln_r, r[j]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) r[j] += __uint_as_float(v[j]);
+            }
+            if (p.ln_out != nullptr) {  // producer of a folded LayerNorm: row sums of the fp32 result
+              float a4[4] = {0.f, 0.f, 0.f, 0.f}, b4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                if (nt * BN + ku * 32 + j < p.N) { a4[j & 3] += r[j]; b4[j & 3] = fmaf(r[j], r[j], b4[j & 3]); }
+              }
+              ln_s += (a4[0] + a4[1]) + (a4[2] + a4[3]);
+              ln_ss += (b4[0] + b4[1]) + (b4[2] + b4[3]);
+            }
           } else {  // SiLU (time-embedding MLP): act(acc + bias + rowvec) + residual
             ptx::tmem_ld_wait();
 #pragma unroll
@@ -640,6 +728,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         }
         ++it;
       }
+      if (!GEGLU && p.ln_out != nullptr && n < p.Nimg && w + lane < p.Wout)
+        p.ln_out[static_cast<long long>(w + lane) * p.ln_out_parts + 2 * nt + part] = make_float2(ln_s, ln_ss);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -816,6 +906,14 @@ bool supported(const ealdm_conv_args* a) {
                     a->n_out % 4 != 0))
     return false;
   if (a->act == EALDM_ACT_GEGLU && (a->rowvec || a->out2 || a->residual || a->n_out % 32 != 0)) return false;
+  if (a->ln_partial_out || a->ln_partial_in) {
+    // folded LayerNorm: linear geometry (rows = output pixels of ONE image row), narrow epilogue for the producer
+    if (a->h_out != 1 || a->src[0].n != 1 || a->weight_adjoint || a->upsample_phases) return false;
+    if (a->ln_partial_out && (a->act != EALDM_ACT_NONE || !a->out_f32)) return false;
+    if (a->ln_partial_in && (a->out2 || a->ln_parts_in < 1 || a->ln_parts_in > 32 || !a->ln_c1 || a->ln_channels < 1 ||
+                             (a->act != EALDM_ACT_NONE && a->act != EALDM_ACT_GEGLU)))
+      return false;
+  }
   if (a->gn_partial) {
     const long long hw = a->h_out * a->w_out;
     if (a->act == EALDM_ACT_GEGLU || hw % 32 != 0 || (a->w_out & (a->w_out - 1)) != 0 ||
@@ -873,6 +971,27 @@ static int encode_unit_map(PFN_cuTensorMapEncodeTiled_v12000 encode, CUtensorMap
   return 0;
 }
 
+// the N tile: fewest (waves x tile cost)
+static int choose_bn(const ealdm_conv_args* a, long long m_work) {
+  init_options();
+  const bool geglu = a->act == EALDM_ACT_GEGLU;
+  if (a->n_out <= 32 && !geglu && !a->weight_adjoint) return 32;
+  if (a->n_out <= 128) return 128;
+  const long long t256 = m_work * ceil_div(a->n_out, 256);
+  const long long t128 = m_work * ceil_div(a->n_out, 128);
+  const long long c256 = ceil_div(t256, num_sms()) * (256 + 48);
+  const long long c128 = ceil_div(t128, num_sms()) * (128 + 48);
+  int BN = (c256 <= c128) ? 256 : 128;
+  if (g_opt[EALDM_TC_OPT_BN] == 128 || g_opt[EALDM_TC_OPT_BN] == 256) BN = g_opt[EALDM_TC_OPT_BN];
+  return BN;
+}
+
+// number of {sum, sum of squares} partials per row a launch with ln_partial_out writes: 2 per N tile (linear geometry)
+int ln_parts(const ealdm_conv_args* a) {
+  const long long m_tiles = ceil_div(a->w_out, BM);
+  return 2 * static_cast<int>(ceil_div(a->n_out, choose_bn(a, m_tiles)));
+}
+
 int launch(const ealdm_conv_args* a, cudaStream_t st) {
   EALDM_REQUIRE(supported(a), "tcgen05 conv: unsupported shape/alignment (c%%64, 16-byte rows and pointers)");
   init_options();
@@ -901,21 +1020,8 @@ int launch(const ealdm_conv_args* a, cudaStream_t st) {
   sub[1] = p.bh < 32 / sub[0] ? p.bh : 32 / sub[0];
   sub[2] = 32 / (sub[0] * sub[1]);
 
-  // choose the N tile: fewest (waves x tile cost)
   const bool geglu = a->act == EALDM_ACT_GEGLU;
-  int BN;
-  if (a->n_out <= 32 && !geglu && !a->weight_adjoint) {
-    BN = 32;
-  } else if (a->n_out <= 128) {
-    BN = 128;
-  } else {
-    const long long t256 = static_cast<long long>(p.m_tiles) * p.phases * ceil_div(a->n_out, 256);
-    const long long t128 = static_cast<long long>(p.m_tiles) * p.phases * ceil_div(a->n_out, 128);
-    const long long c256 = ceil_div(t256, num_sms()) * (256 + 48);
-    const long long c128 = ceil_div(t128, num_sms()) * (128 + 48);
-    BN = (c256 <= c128) ? 256 : 128;
-    if (g_opt[EALDM_TC_OPT_BN] == 128 || g_opt[EALDM_TC_OPT_BN] == 256) BN = g_opt[EALDM_TC_OPT_BN];
-  }
+  const int BN = choose_bn(a, static_cast<long long>(p.m_tiles) * p.phases);
   p.n_tiles = static_cast<int>(ceil_div(a->n_out, BN));
   // CTA pairs (256 x 256 tiles, a third less operand traffic per SM) for every problem with an even number of M tiles
   // and a reduction long enough (K >= 1024) to amortise the pair's cross-CTA barrier latency (measured: K = 256 / 512
@@ -982,7 +1088,7 @@ int launch(const ealdm_conv_args* a, cudaStream_t st) {
   const long long out_cols = geglu ? a->n_out / 2 : a->n_out;
   // (measured: the GEGLU pass gains 3 % at K = 256 and loses 4 % at K >= 512, where the stores of the narrow units
   // overlap the longer main loop better)
-  const bool wide = g_opt[EALDM_TC_OPT_WIDE] != 0 && BN == 256 && !phased &&
+  const bool wide = g_opt[EALDM_TC_OPT_WIDE] != 0 && BN == 256 && !phased && !a->ln_partial_out &&
                     (geglu ? a->k_total <= 256 : (!a->residual && !a->out2));
   PhaseMaps pm;
   memset(&pm, 0, sizeof(pm));
@@ -1024,6 +1130,13 @@ int launch(const ealdm_conv_args* a, cudaStream_t st) {
   p.gn_ld = static_cast<int>(a->gn_ld);
   p.gn_chunks = static_cast<int>(a->h_out * a->w_out / 32);
   p.gn_phase_chunks = static_cast<int>(h_grid * w_grid / 32);
+  p.ln_out = reinterpret_cast<float2*>(a->ln_partial_out);
+  p.ln_out_parts = 2 * p.n_tiles;
+  p.ln_in = reinterpret_cast<const float2*>(a->ln_partial_in);
+  p.ln_in_parts = static_cast<int>(a->ln_parts_in);
+  p.ln_inv_c = a->ln_channels > 0 ? 1.0f / static_cast<float>(a->ln_channels) : 0.f;
+  p.ln_eps = a->ln_eps;
+  p.ln_c1 = a->ln_c1;
   p.b_mn = a->weight_adjoint ? 1 : 0;
   p.wide = wide ? 1 : 0;
   p.relaxed_wait = g_opt[EALDM_TC_OPT_RELAXED_WAIT];

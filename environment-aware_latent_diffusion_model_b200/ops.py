@@ -37,7 +37,7 @@ class Act:
     [n*h*w/32, ld/8, 2] fp32 = {sum, sum of squares} per (32-pixel chunk, 8-channel octet): a tcgen05 convolution
     that writes this activation fills its column window of `gp`, and a GroupNorm that reads the activation then
     skips its statistics pass."""
-    __slots__ = ("buf", "n", "h", "w", "c", "c0", "gp")
+    __slots__ = ("buf", "n", "h", "w", "c", "c0", "gp", "ln")
 
     def __init__(self, buf: torch.Tensor, n: int, h: int, w: int, c: Optional[int] = None, c0: int = 0,
                  gp: Optional[torch.Tensor] = None):
@@ -48,6 +48,7 @@ class Act:
         self.c = buf.shape[1] - c0 if c is None else c
         assert self.c0 + self.c <= buf.shape[1]
         self.gp = gp
+        self.ln = None      # [rows, parts, 2] row {sum, sum of squares} partials written by the producing GEMM (ln_stats)
 
     @staticmethod
     def empty(n, h, w, c, dtype, device) -> "Act":
@@ -106,7 +107,7 @@ class ConvIn:
 def conv(srcs: Sequence[ConvIn], weight: torch.Tensor, out: Act, *, bias: Optional[torch.Tensor] = None,
          rowvec: Optional[torch.Tensor] = None, rowvec_col0: int = 0, residual: Optional[Act] = None,
          act: int = L.ACT_NONE, impl: int = L.IMPL_AUTO, out2: Optional[Act] = None, adjoint: bool = False,
-         upsample_phases: bool = False) -> Act:
+         upsample_phases: bool = False, ln_stats: bool = False, ln: Optional[tuple] = None) -> Act:
     """ealdm_conv: out = epilogue(sum_s im2col(src_s) @ weight[:, seg_s]^T). `weight` is [n_out, k_total].
     adjoint=True: data gradient of a forward layer -- `weight` is that layer's own packed matrix
     [src channels, ksize^2 * out.c] (may be a column window of a wider matrix); nothing is transposed or flipped."""
@@ -168,6 +169,22 @@ def conv(srcs: Sequence[ConvIn], weight: torch.Tensor, out: Act, *, bias: Option
         a.gn_partial, a.gn_ld = out.gp_ptr, out.gp.shape[1]
         if impl == L.IMPL_AUTO:
             a.impl = L.IMPL_TCGEN05   # only the tcgen05 epilogue writes them: fail loudly rather than skip silently
+    if ln is not None:        # consumer of a folded LayerNorm: ln = (partials [rows, parts, 2], c1 [n_out], channels, eps)
+        part, c1, channels, eps = ln
+        assert part.dtype == torch.float32 and part.is_contiguous() and part.dim() == 3 and part.shape[0] == out.rows
+        assert c1.dtype == torch.float32 and c1.numel() == a.n_out and bias is not None and out2 is None
+        a.ln_partial_in, a.ln_parts_in, a.ln_c1 = part.data_ptr(), part.shape[1], c1.data_ptr()
+        a.ln_channels, a.ln_eps = channels, eps
+        a.impl = L.IMPL_TCGEN05
+    if ln_stats:              # producer: the epilogue also writes every row's {sum, sum of squares} partials
+        assert a.out_f32 and act == L.ACT_NONE
+        a.impl = L.IMPL_TCGEN05
+        a.ln_partial_out = 1      # (any non-null value: the query below only looks at the shape of the problem)
+        parts = int(lib.ealdm_conv_ln_parts(C.byref(a)))
+        if parts <= 0:
+            L.check(-1)
+        out.ln = torch.empty((out.rows, parts, 2), dtype=torch.float32, device=out.buf.device)
+        a.ln_partial_out = out.ln.data_ptr()
     L.check(lib.ealdm_conv(C.byref(a), _stream()))
     return out
 
@@ -187,6 +204,7 @@ def linear(x: Act, weight: torch.Tensor, out: Act, **kw) -> Act:
     if o2 is not None:
         o2 = Act(o2.buf, 1, 1, o2.rows, o2.c, o2.c0)
     conv([ConvIn(xs)], weight, os_, residual=res, out2=o2, **kw)
+    out.ln = os_.ln
     return out
 
 

@@ -61,6 +61,7 @@ class UNetTrainEngine(UNetEngine):
 
     _fused_geglu = False
     _fused_ff = False             # the backward needs the GEGLU pre-activation
+    _fold_ln = False              # ... and the LayerNorm outputs / statistics
     _phased_upsample = False      # the backward differentiates the explicit nearest-2x + 3x3 form
 
     def __init__(self, m: UNetModel, dtype: torch.dtype):

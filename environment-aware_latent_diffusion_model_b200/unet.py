@@ -353,6 +353,7 @@ class UNetEngine:
     sequence of libealdm_b200 launches on the current CUDA stream (CUDA-graph capturable: no host
     synchronisation, no data-dependent control flow)."""
     _fused_geglu = True   # the training engine keeps the GEGLU pre-activation instead (train.py)
+    _fold_ln = not os.environ.get("EALDM_NO_LN_FOLD")    # A/B switch: LayerNorm folded into the GEMMs around it
     # one-kernel GEGLU FeedForward (csrc/ff_fused.cu): bit-identical to the two GEMMs and measured NOT faster yet
     # (269 us against 140 + 95 us at level 0, DESIGN.md section 4), hence opt-in
     _fused_ff = bool(os.environ.get("EALDM_FUSED_FF"))
@@ -428,6 +429,23 @@ class UNetEngine:
                 if self._fused_geglu:   # inference: value/gate rows interleaved for the fused GEGLU epilogue
                     wi, bi = geglu_interleave(self._c(tb.ff.net[0].proj.weight), tb.ff.net[0].proj.bias)
                     t["ff1"] = _PackedConv(wi, bi, 4 * C_)
+                if self._fold_ln and self.dt == torch.bfloat16:
+                    # LayerNorm folded into the GEMM behind it: LN(x) W^T + b = rstd (x (W.gamma)^T) - rstd mu c1 + c2
+                    # with c1 = (W.gamma) 1 (from the bf16-rounded matrix the GEMM multiplies) and c2 = W beta + b
+                    def fold(w, ln, bias=None):
+                        w32 = w.detach().float()
+                        wg = (w32 * ln.weight.detach().float()[None]).to(torch.bfloat16).contiguous()
+                        c2 = w32 @ ln.bias.detach().float()
+                        if bias is not None:
+                            c2 = c2 + bias.detach().float()
+                        return wg, wg.float().sum(1).contiguous(), c2.contiguous()
+                    wqkv = torch.cat([tb.attn1.to_q.weight, tb.attn1.to_k.weight, tb.attn1.to_v.weight], dim=0)
+                    t["qkv_ln"] = fold(wqkv, tb.norm1)
+                    t["q2_ln"] = fold(tb.attn2.to_q.weight, tb.norm2)
+                    wg, c1, c2 = fold(tb.ff.net[0].proj.weight, tb.norm3, tb.ff.net[0].proj.bias)
+                    wgi, c2i = geglu_interleave(wg, c2)
+                    _, c1i = geglu_interleave(wg, c1)
+                    t["ff1_ln"] = (wgi, c1i, c2i)
                 t["ff2"] = _PackedConv(self._c(tb.ff.net[2].weight), f32(tb.ff.net[2].bias), C_)
                 d["blocks"].append(t)
             return d
@@ -567,39 +585,58 @@ class UNetEngine:
         f32 = torch.float32
         xn = self._new(n, h, w, C_)
         ops.group_norm(x.f, d["norm"][0], d["norm"][1], 1e-6, xn, self.stats, silu=False)
-        t = self._new(n, h, w, C_, f32)
-        ops.linear(xn, d["proj_in"].w, t, bias=d["proj_in"].b)
+        if kv_all is None:
+            raise RuntimeError("SpatialTransformer needs a context tensor")
+        fold = "qkv_ln" in d["blocks"][0]     # bf16 inference engine: no stand-alone LayerNorm passes (see pack_st)
+        fused_ff = self._fused_ff and C_ == 256 and self.dt == torch.bfloat16
+        nb = len(d["blocks"])
+
+        def normed(src: Act, src_h: Optional[Act], tb, i: int, key: str, w_plain, n_out: int, **kw) -> Act:
+            """LayerNorm i of the block followed by the linear layer `key`: folded into that GEMM (which then reads
+            the bf16 shadow of the raw stream and the producer's row statistics) or as a LayerNorm pass + GEMM."""
+            y = self._new(n, h, w, n_out // 2 if kw.get("act") == L.ACT_GEGLU else n_out)
+            if fold and src.ln is not None:
+                wg, c1, c2 = tb[key + "_ln"]
+                ops.linear(src_h, wg, y, bias=c2, ln=(src.ln, c1, C_, 1e-5), **kw)
+            else:
+                a = self._new(n, h, w, C_)
+                ops.layer_norm(src, tb[f"ln{i}"][0], tb[f"ln{i}"][1], 1e-5, a)
+                ops.linear(a, w_plain[0], y, bias=w_plain[1], **kw)
+            return y
+
+        def stream(last: bool = False):
+            """A token-stream tensor: fp32 master (+ its bf16 shadow when a folded LayerNorm GEMM will read it)."""
+            f = self._new(n, h, w, C_, None if last else f32)
+            return f, (self._new(n, h, w, C_) if (fold and not last) else None)
+
+        t, t_h = stream()
+        ops.linear(xn, d["proj_in"].w, t, bias=d["proj_in"].b, out2=t_h, ln_stats=fold)
         for bi, tb in enumerate(d["blocks"]):
-            a = self._new(n, h, w, C_)
-            ops.layer_norm(t, tb["ln1"][0], tb["ln1"][1], 1e-5, a)
-            qkv = self._new(n, h, w, 3 * C_)
-            ops.linear(a, tb["qkv"], qkv)
+            qkv = normed(t, t_h, tb, 1, "qkv", (tb["qkv"], None), 3 * C_)
             o = self._new(n, h, w, C_)
             ops.attention(qkv.cols(0, C_), qkv.cols(C_, C_), qkv.cols(2 * C_, C_), o, batch=n, heads=heads,
                           head_dim=dh, n_q=tok, n_kv=tok, scale=dh ** -0.5)
-            t1 = self._new(n, h, w, C_, f32)
-            ops.linear(o, tb["o1"].w, t1, bias=tb["o1"].b, residual=t)
-            ops.layer_norm(t1, tb["ln2"][0], tb["ln2"][1], 1e-5, a)
-            q2 = self._new(n, h, w, C_)
-            ops.linear(a, tb["q2"], q2)
+            t1, t1_h = stream()
+            ops.linear(o, tb["o1"].w, t1, bias=tb["o1"].b, residual=t, out2=t1_h, ln_stats=fold)
+            q2 = normed(t1, t1_h, tb, 2, "q2", (tb["q2"], None), C_)
             o2 = self._new(n, h, w, C_)
-            if kv_all is None:
-                raise RuntimeError("SpatialTransformer needs a context tensor")
             kc = tb["kv_col0"]
             ops.attention(q2, kv_all.cols(kc, C_), kv_all.cols(kc + C_, C_), o2, batch=n, heads=heads, head_dim=dh,
                           n_q=tok, n_kv=n_ctx, scale=dh ** -0.5)
+            ff_fold = fold and not fused_ff
             t2 = self._new(n, h, w, C_, f32)
-            ops.linear(o2, tb["o2"].w, t2, bias=tb["o2"].b, residual=t1)
-            ops.layer_norm(t2, tb["ln3"][0], tb["ln3"][1], 1e-5, a)
-            last = bi == len(d["blocks"]) - 1   # the last t feeds proj_out as a GEMM operand -> compute dtype
-            t = self._new(n, h, w, C_, None if last else f32)
-            if self._fused_ff and C_ == 256 and self.dt == torch.bfloat16:
+            t2_h = self._new(n, h, w, C_) if ff_fold else None
+            ops.linear(o2, tb["o2"].w, t2, bias=tb["o2"].b, residual=t1, out2=t2_h, ln_stats=ff_fold)
+            last = bi == nb - 1   # the last t feeds proj_out as a GEMM operand -> compute dtype
+            t, t_h = stream(last)
+            if fused_ff:
                 # FF1 -> GEGLU -> FF2 -> + residual in one kernel: the 8C / 4C wide intermediates stay on the SM
+                a = self._new(n, h, w, C_)
+                ops.layer_norm(t2, tb["ln3"][0], tb["ln3"][1], 1e-5, a)
                 ops.ff_geglu_fused(a, tb["ff1"].w, tb["ff1"].b, tb["ff2"].w, tb["ff2"].b, t2, t)
             else:
-                gg = self._new(n, h, w, 4 * C_)
-                ops.linear(a, tb["ff1"].w, gg, bias=tb["ff1"].b, act=L.ACT_GEGLU)
-                ops.linear(gg, tb["ff2"].w, t, bias=tb["ff2"].b, residual=t2)
+                gg = normed(t2, t2_h, tb, 3, "ff1", (tb["ff1"].w, tb["ff1"].b), 8 * C_, act=L.ACT_GEGLU)
+                ops.linear(gg, tb["ff2"].w, t, bias=tb["ff2"].b, residual=t2, out2=t_h, ln_stats=fold and not last)
         out = dest if dest is not None else self._new_dual(n, h, w, C_)
         ops.linear(t, d["proj_out"].w, out.f, bias=d["proj_out"].b, residual=x.f, out2=self._out2(out))
         return out

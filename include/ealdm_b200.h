@@ -142,9 +142,26 @@ typedef struct {
      form, and the upsampled tensor never exists.  Bias, row vector, shadow and GroupNorm partials as usual. */
   int32_t upsample_phases;
   int64_t ld_weight;
+  /* LayerNorm FOLDED into the two GEMMs around it (tcgen05 path, linear layers: h_out = 1, src[0].n = 1).  Replaces the
+     stand-alone nn.LayerNorm passes of BasicTransformerBlock._forward (ldm/modules/attention.py:203-205,211-215):
+       LayerNorm(x) W^T + b  ==  rstd (x (W . gamma)^T) - rstd mu ((W . gamma) 1) + (W beta + b)
+     PRODUCER (the GEMM that writes the fp32 token stream x, typically with its bf16 shadow in out2): ln_partial_out
+     [rows, ealdm_conv_ln_parts(args)] float2 receives {sum, sum of squares} of disjoint column sets of every row.
+     CONSUMER (the GEMM that followed the LayerNorm): src = the RAW stream (bf16), weight = W . gamma (packed by the
+     caller), bias = W beta + b, ln_c1[n_out] = row sums of the packed weight, ln_partial_in / ln_parts_in = the
+     producer's buffer, ln_channels = the LayerNorm width, ln_eps its epsilon.  Works with act NONE and GEGLU. */
+  float* ln_partial_out;
+  const float* ln_partial_in;
+  int64_t ln_parts_in;
+  const float* ln_c1;
+  int64_t ln_channels;
+  float ln_eps;
+  int32_t reserved3;
 } ealdm_conv_args;
 
 int ealdm_conv(const ealdm_conv_args* a, ealdm_stream_t stream);
+/* partials per row that a launch with these args writes to ln_partial_out (2 per N tile of the schedule it selects) */
+int64_t ealdm_conv_ln_parts(const ealdm_conv_args* a);
 
 /*
  * Fused GEGLU FeedForward + residual of one transformer block at model width c = 256 (hidden = 4c = 1024):

@@ -769,3 +769,61 @@ def test_geglu_tanh_form_against_erf_form_and_torch():
     d = rel_l2(got[0], got[1])
     print(f"GEGLU tanh form vs erf form (both rounded to bf16): rel_l2 = {d:.3e}")
     assert d < 3e-3
+
+
+@pytest.mark.parametrize("M,C,N,geglu", [(300, 256, 768, False), (4096, 256, 256, False), (2048, 512, 1536, False),
+                                         (1024, 1024, 1024, False), (4096, 256, 2048, True), (1024, 512, 4096, True),
+                                         (640, 1024, 8192, True)])
+def test_layer_norm_folded_into_the_surrounding_gemms(M, C, N, geglu):
+    """LayerNorm(x) W^T + b with the LayerNorm folded away (ealdm_conv ln_partial_out / ln_partial_in): a PRODUCER GEMM
+    writes the fp32 stream x = y Wp^T + bp + r, its bf16 shadow and per-row {sum, sum of squares} partials; the CONSUMER
+    GEMM multiplies the RAW shadow by W . gamma and corrects with the row statistics in its epilogue.  Checked against
+    torch fp32 (LayerNorm of the SAME fp32 stream, operands rounded to bf16 like the unfused path) and against the
+    unfused kernels (ealdm_layer_norm + ealdm_conv)."""
+    from ealdm_b200.packing import geglu_interleave
+    y = torch.randn(M, C, generator=g(401)).to(DEV)
+    wp = (torch.randn(C, C, generator=g(402)) / math.sqrt(C)).to(DEV)
+    bp = torch.randn(C, generator=g(403)).to(DEV)
+    r = (torch.randn(M, C, generator=g(404)) * 2 + 0.5).to(DEV)          # a stream with a non-zero mean
+    gamma = (torch.rand(C, generator=g(405)) + 0.5).to(DEV)
+    beta = (torch.randn(C, generator=g(406)) * 0.3).to(DEV)
+    W = (torch.randn(N, C, generator=g(407)) / math.sqrt(C)).to(DEV)
+    b = torch.randn(N, generator=g(408)).to(DEV)
+    ya = Act(y.to(torch.bfloat16).contiguous(), 1, 1, M)
+    ra = Act(r.contiguous(), 1, 1, M)
+    # producer: fp32 stream + bf16 shadow + row partials
+    x = Act.empty(1, 1, M, C, torch.float32, DEV)
+    xh = Act.empty(1, 1, M, C, torch.bfloat16, DEV)
+    ops.linear(ya, wp.to(torch.bfloat16).contiguous(), x, bias=bp, residual=ra, out2=xh, ln_stats=True)
+    assert x.ln is not None and x.ln.shape[0] == M and x.ln.shape[2] == 2
+    xs = x.buf.float()
+    s = x.ln.sum(1)
+    assert rel_l2(s[:, 0], xs.sum(1)) < 1e-5 and rel_l2(s[:, 1], (xs * xs).sum(1)) < 1e-5
+    assert torch.equal(xh.buf, x.buf.to(torch.bfloat16))
+    # consumer
+    wg = (W * gamma[None]).to(torch.bfloat16).contiguous()
+    c1 = wg.float().sum(1).contiguous()
+    c2 = (W @ beta + b).contiguous()
+    act = L.ACT_GEGLU if geglu else L.ACT_NONE
+    if geglu:
+        wgi, c2i = geglu_interleave(wg, c2)
+        _, c1i = geglu_interleave(wg, c1)
+    else:
+        wgi, c1i, c2i = wg, c1, c2
+    out = Act.empty(1, 1, M, N // 2 if geglu else N, torch.bfloat16, DEV)
+    ops.linear(xh, wgi, out, bias=c2i, act=act, ln=(x.ln, c1i, C, 1e-5))
+    # unfused kernels on the same stream
+    a = Act.empty(1, 1, M, C, torch.bfloat16, DEV)
+    ops.layer_norm(x, gamma, beta, 1e-5, a)
+    if geglu:
+        wi, bi = geglu_interleave(W.to(torch.bfloat16), b)
+    else:
+        wi, bi = W.to(torch.bfloat16).contiguous(), b
+    ref_k = Act.empty(1, 1, M, N // 2 if geglu else N, torch.bfloat16, DEV)
+    ops.linear(a, wi, ref_k, bias=bi, act=act)
+    # torch fp32
+    pre = F.linear(F.layer_norm(xs, (C,), gamma, beta, 1e-5), W, b)
+    want = pre[:, :N // 2] * F.gelu(pre[:, N // 2:]) if geglu else pre
+    e_fold, e_unf = rel_l2(out.buf.float(), want), rel_l2(ref_k.buf.float(), want)
+    print(f"LN fold M={M} C={C} N={N} geglu={geglu}: folded {e_fold:.3e}, unfused kernels {e_unf:.3e} (vs torch fp32)")
+    assert e_fold < 6e-3 and e_fold < 1.5 * e_unf + 1e-3
