@@ -19,7 +19,7 @@ IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05 = 0, 1, 2
 TC_OPT_CTA2, TC_OPT_WIDE, TC_OPT_RELAXED_WAIT, TC_OPT_BN, TC_OPT_GELU_ERF = 0, 1, 2, 3, 4
 
 EXPORTS = [
-    "ealdm_abi_version", "ealdm_last_error", "ealdm_device_check", "ealdm_launch_count", "ealdm_tc_set_option",
+    "ealdm_abi_version", "ealdm_last_error", "ealdm_device_check", "ealdm_launch_count", "ealdm_tc_set_option", "ealdm_set_pdl",
     "ealdm_conv", "ealdm_conv_ln_parts", "ealdm_ff_geglu_fused", "ealdm_group_norm", "ealdm_group_norm_workspace_bytes", "ealdm_layer_norm", "ealdm_attention",
     "ealdm_timestep_embedding", "ealdm_nchw_to_nhwc", "ealdm_nhwc_to_nchw",
     "ealdm_upsample_nearest2x", "ealdm_copy2d", "ealdm_softmax_rows", "ealdm_ddim_step",
@@ -172,6 +172,8 @@ def _declare(lib):
     lib.ealdm_launch_count.argtypes = []
     lib.ealdm_tc_set_option.restype = C.c_int
     lib.ealdm_tc_set_option.argtypes = [C.c_int, C.c_int]
+    lib.ealdm_set_pdl.restype = C.c_int
+    lib.ealdm_set_pdl.argtypes = [C.c_int]
     lib.ealdm_conv_ln_parts.restype = C.c_int64
     lib.ealdm_conv_ln_parts.argtypes = [C.POINTER(ConvArgs)]
     lib.ealdm_group_norm_workspace_bytes.restype = C.c_int64

@@ -2,6 +2,7 @@
 #include "common.cuh"
 
 #include <atomic>
+#include <stdlib.h>
 
 namespace ealdm {
 
@@ -16,6 +17,17 @@ int set_error(int code, const char* fmt, ...) {
   return code;
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+// programmatic dependent launch between the kernels of one stream (common.cuh); EALDM_PDL=1 / ealdm_set_pdl(1) enable it
+static std::atomic<int> g_pdl{-1};
+bool pdl_enabled() {
+  int v = g_pdl.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char* e = getenv("EALDM_PDL");
+    v = (e && atoi(e) != 0) ? 1 : 0;   // opt-in: measured neutral on the graph-replayed forward
+    g_pdl.store(v, std::memory_order_relaxed);
+  }
+  return v != 0;
+}
 
 namespace tc {
 bool supported(const ealdm_conv_args* a);
@@ -36,6 +48,11 @@ extern "C" const char* ealdm_last_error(void) { return g_err; }
 extern "C" int64_t ealdm_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 extern "C" int ealdm_tc_set_option(int option, int value) { return tc::set_option(option, value); }
+extern "C" int ealdm_set_pdl(int enabled) {
+  const int prev = pdl_enabled() ? 1 : 0;
+  g_pdl.store(enabled ? 1 : 0, std::memory_order_relaxed);
+  return prev;
+}
 
 extern "C" int ealdm_device_check(void) {
   int dev = 0;

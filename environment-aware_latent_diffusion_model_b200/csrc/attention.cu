@@ -216,6 +216,8 @@ __global__ void __launch_bounds__(XKV_THREADS)
 xattn_bf16_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const bf16* __restrict__ v,
                   long long ld_q, long long ld_kv, int c, int n_q, float scale_log2,
                   bf16* __restrict__ out, long long ld_out) {
+  pdl_wait();      // launched with programmatic serialization (common.cuh)
+  pdl_trigger();
   const int b = blockIdx.y;
   const int cpr = c >> 3;                      // 16-byte chunks per token row; divides XKV_THREADS
   const int cc = threadIdx.x % cpr;            // this thread's chunk position
@@ -306,8 +308,8 @@ static int launch_xattn_bf16(const ealdm_attention_args* a, cudaStream_t st) {
   bf16* o = reinterpret_cast<bf16*>(a->out);
 #define EALDM_XATTN(NKV)                                                                           \
   case NKV:                                                                                        \
-    xattn_bf16_kernel<NKV><<<grid, XKV_THREADS, 0, st>>>(q, k, v, a->ld_q, a->ld_kv, c, (int)a->n_q, \
-                                                         sl2, o, a->ld_out);                       \
+    EALDM_CUDA(launch_pdl(xattn_bf16_kernel<NKV>, grid, dim3(XKV_THREADS), 0, st, q, k, v, a->ld_q, a->ld_kv, c, \
+                          (int)a->n_q, sl2, o, a->ld_out));                                        \
     break
   switch (a->n_kv) {
     EALDM_XATTN(1); EALDM_XATTN(2); EALDM_XATTN(3); EALDM_XATTN(4);

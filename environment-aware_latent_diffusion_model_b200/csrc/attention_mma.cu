@@ -174,6 +174,8 @@ flash_mma_even_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, co
   const int r0 = q0 + (lane >> 2), r1 = r0 + 8;
   const int cq = (lane & 3) * 2;
 
+  pdl_wait();      // launched with programmatic serialization (common.cuh)
+  pdl_trigger();
   uint32_t qa[2][4];
   {
     const bf16* qb = q + static_cast<long long>(b) * n_q * ld_q + h * hs_q;
@@ -311,9 +313,9 @@ int launch_flash_mma(const ealdm_attention_args* a, cudaStream_t st) {
     } else {
       dim3 grid(static_cast<unsigned>(ceil_div(a->n_q, 64)), static_cast<unsigned>(a->heads),
                 static_cast<unsigned>(a->batch));
-      flash_mma_even_kernel<4><<<grid, 128, 0, st>>>(q, k, v, a->ld_q, a->ld_kv, a->head_stride_q,
-                                                     a->head_stride_kv, (int)a->n_q, (int)a->n_kv,
-                                                     scale_log2, o, a->ld_out, a->lse);
+      EALDM_CUDA(launch_pdl(flash_mma_even_kernel<4>, grid, dim3(128), 0, st, q, k, v, a->ld_q, a->ld_kv,
+                            a->head_stride_q, a->head_stride_kv, (int)a->n_q, (int)a->n_kv, scale_log2, o, a->ld_out,
+                            a->lse));
     }
   } else if (a->n_q > 64) {
     dim3 grid(static_cast<unsigned>(ceil_div(a->n_q, 128)), static_cast<unsigned>(a->heads),

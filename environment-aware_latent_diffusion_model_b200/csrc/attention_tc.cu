@@ -135,6 +135,8 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();      // programmatic dependent launch: the set-up above ran under the predecessor's tail
+  pdl_trigger();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -389,7 +391,7 @@ static int launch_t(const ealdm_attention_args* a, cudaStream_t st) {
   p.ld_out = a->ld_out;
   p.lse = a->lse;
   dim3 grid(static_cast<unsigned>(a->n_q / BM), static_cast<unsigned>(a->heads), static_cast<unsigned>(a->batch));
-  flash_tc_kernel<WIDE><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(tq, tk, tv, p);
+  EALDM_CUDA(launch_pdl(flash_tc_kernel<WIDE>, grid, dim3(NUM_THREADS), C::SMEM_BYTES, st, tq, tk, tv, p));
   EALDM_LAUNCH_CHECK();
   return 0;
 }

@@ -54,6 +54,36 @@ struct DeviceOnce {
   void done() { bits.fetch_or(1ull << device(), std::memory_order_release); }
 };
 
+// ---- programmatic dependent launch (PDL) -------------------------------------------------------------
+// The forward pass is a chain of ~260 dependent kernels.  A kernel launched with the programmatic-stream-serialization
+// attribute may become resident while its predecessor still runs: its prologue (barrier init, TMEM allocation, tensor
+// map prefetch, index arithmetic) then overlaps the predecessor's tail, and `pdl_wait()` (griddepcontrol.wait) holds it
+// until the predecessor has completed and its writes are visible.  EVERY kernel launched through `launch_pdl` must call
+// `pdl_wait()` before its first global-memory access; `pdl_trigger()` lets the NEXT kernel in the stream do the same.
+// Both instructions are no-ops in a kernel launched without the attribute.  Opt-in (EALDM_PDL=1 / ealdm_set_pdl): on the
+// CUDA-graph-replayed forward it measured neutral (63.3 vs 64.0 samples/s on one box) -- the large CTAs of consecutive
+// kernels cannot share an SM, so only launch latency is left to hide and graph replay already hides it.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                     Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---- element type helpers ----------------------------------------------------------------------
 typedef __nv_bfloat16 bf16;
 

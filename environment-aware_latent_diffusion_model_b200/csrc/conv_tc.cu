@@ -46,7 +46,9 @@ constexpr int BM = 128;
 constexpr int BK = 64;  // bf16 per K block = 128 B = one swizzle row
 constexpr int UMMA_K = 16;
 constexpr int EPI_WARPS = 8;
-constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+// warp 0 TMA, warp 1 MMA, warps 2..9 epilogue, warp 10 row statistics of a folded LayerNorm (idle otherwise; the
+// register file is allocated in units of 4 warps, so the 11th warp does not lower the 168-register ceiling)
+constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS + 32;
 constexpr int EBUF_BYTES = 4096;                  // one [32 x 32] fp32 unit (bf16 units use half)
 constexpr int O2BUF_BYTES = 2048;                 // bf16 shadow of a unit
 constexpr int EPI_WARP_BYTES = 2 * EBUF_BYTES + O2BUF_BYTES;
@@ -96,8 +98,8 @@ struct Params {
   int phases;
   int gn_phase_chunks;  // 32-pixel chunks of the low-resolution grid per image: phase p fills chunks [p * this, ...)
   // LayerNorm folded into the GEMMs around it (linear geometry only: h_out = 1, one "image", row = output pixel).
-  // PRODUCER side (ln_out): the epilogue that writes the fp32 token stream also writes, per row and per (N tile, warp
-  // half), {sum, sum of squares} of its columns: ln_out[row * ln_out_parts + 2 * nt + part].
+  // PRODUCER side (ln_out): the epilogue that writes the fp32 token stream also writes, per row and per 32-column
+  // unit, {sum, sum of squares} of its columns: ln_out[row * ln_out_parts + col / 32] (independent of the N tile).
   // CONSUMER side (ln_in): A is the RAW stream (its bf16 shadow), W was packed as W * gamma, `bias` holds
   // W beta (+ bias), ln_c1[col] = sum_k (W * gamma)[col, k]; with mu, rstd of the row from the partials
   //   out = rstd * acc - rstd * mu * c1[col] + bias[col]  ==  LayerNorm(x) W^T + bias
@@ -122,9 +124,9 @@ struct Cfg {
   static constexpr int BIAS_OFF = EPI_OFF + EPI_WARPS * EPI_WARP_BYTES;
   static constexpr int BIAS_BYTES = 2 * BN * 4;                        // per accumulator stage
   static constexpr int BAR_OFF = BIAS_OFF + BIAS_BYTES;
-  static constexpr int BAR_BYTES = 512;  // (2*STAGES + 4 + 2*EPI_WARPS) mbarriers + the TMEM base slot
+  static constexpr int BAR_BYTES = 512;  // (2*STAGES + 8 + 2*EPI_WARPS) mbarriers + the TMEM base slot
   static constexpr int SMEM_BYTES = BAR_OFF + BAR_BYTES;
-  static_assert((2 * STAGES + 4 + 2 * EPI_WARPS) * 8 + 4 <= BAR_BYTES, "barrier block too small");
+  static_assert((2 * STAGES + 8 + 2 * EPI_WARPS) * 8 + 4 <= BAR_BYTES, "barrier block too small");
   static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KiB dynamic shared memory limit");
   static_assert(EPI_OFF % 1024 == 0 && EPI_WARP_BYTES % 1024 == 0 && BAR_OFF % 8 == 0, "alignment");
 };
@@ -192,7 +194,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   uint64_t* tmem_full = empty_bar + C::STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint64_t* res_bar = tmem_empty + 2;  // [EPI_WARPS][2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 2 * EPI_WARPS);
+  uint64_t* ln_full = res_bar + 2 * EPI_WARPS;   // [2] row statistics of a folded LayerNorm, per accumulator stage
+  uint64_t* ln_empty = ln_full + 2;              // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ln_empty + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -220,6 +224,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       ptx::mbar_init(&tmem_empty[a], CTA2 ? 2 * EPI_WARPS : EPI_WARPS);
     }
     for (int a = 0; a < 2 * EPI_WARPS; ++a) ptx::mbar_init(&res_bar[a], 1);
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&ln_full[a], 1);
+      ptx::mbar_init(&ln_empty[a], EPI_WARPS);
+    }
     ptx::fence_mbar_init();
   }
   if (warp == 1) {
@@ -236,6 +244,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   if constexpr (CTA2) ptx::cluster_sync_all();  // the peer's barriers exist before anything remote touches them
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // programmatic dependent launch: everything above ran under the predecessor's tail; global memory comes next
+  pdl_wait();
+  pdl_trigger();
 
   // work items: tiles (one CTA each) or, for CTA pairs, super-tiles of two consecutive M tiles and one N tile
   const int tile_first = CTA2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
@@ -372,6 +383,51 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
+  } else if (warp == 2 + EPI_WARPS) {
+    // ===================== row statistics of a folded LayerNorm (consumer side) =====================
+    // For every tile, one or two tiles ahead of the epilogue: fold the producer's per-32-column {sum, sum of squares}
+    // partials of the tile's 128 rows (four rows per lane, fixed order) into {rstd, -rstd * mean} in shared memory,
+    // so that no epilogue thread waits for global memory at the top of a tile.
+    if (p.ln_in != nullptr) {
+      float2* rows_s = reinterpret_cast<float2*>(smem + C::EPI_OFF + EPI_WARP_BYTES + 2 * EBUF_BYTES);
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
+        int mt, nt;
+        tile_mn(tile, mt, nt);
+        ptx::mbar_wait(&ln_empty[acc], acc_phase ^ 1u);
+#pragma unroll 1
+        for (int j = 0; j < BM / 32; ++j) {
+          int row = mt * BM + j * 32 + lane;   // linear geometry: tile rows are consecutive output pixels
+          if (row >= p.Wout) row = p.Wout - 1;
+          const float2* lp = p.ln_in + static_cast<long long>(row) * p.ln_in_parts;
+          float s = 0.f, ss = 0.f;
+          if ((p.ln_in_parts & 7) == 0) {
+            const float4* lp4 = reinterpret_cast<const float4*>(lp);
+            for (int i0 = 0; 2 * i0 < p.ln_in_parts; i0 += 4) {   // 8 partials per round, four 16-byte loads in flight
+              const float4 q0 = __ldg(lp4 + i0), q1 = __ldg(lp4 + i0 + 1), q2 = __ldg(lp4 + i0 + 2),
+                           q3 = __ldg(lp4 + i0 + 3);
+              s += ((q0.x + q0.z) + (q1.x + q1.z)) + ((q2.x + q2.z) + (q3.x + q3.z));
+              ss += ((q0.y + q0.w) + (q1.y + q1.w)) + ((q2.y + q2.w) + (q3.y + q3.w));
+            }
+          } else {
+            for (int i = 0; i < p.ln_in_parts; ++i) {
+              const float2 t = __ldg(lp + i);
+              s += t.x;
+              ss += t.y;
+            }
+          }
+          const float mu = s * p.ln_inv_c;
+          const float var = fmaxf(ss * p.ln_inv_c - mu * mu, 0.f);
+          const float r = rsqrtf(var + p.ln_eps);
+          rows_s[acc * BM + j * 32 + lane] = make_float2(r, -r * mu);
+        }
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&ln_full[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
   } else {
     // ===================== epilogue (warps 2..9) =====================
     const int ew = warp - 2;
@@ -383,6 +439,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     float* bias_s = reinterpret_cast<float*>(smem + C::BIAS_OFF);
     // c1 of a folded LayerNorm, staged like the bias; lives in epilogue warp 0's shadow buffer (ln_in excludes out2)
     float* c1_s = reinterpret_cast<float*>(smem + C::EPI_OFF + 2 * EBUF_BYTES);
+    // ... and the rows' {rstd, -rstd * mean} [2][BM] in epilogue warp 1's
+    const float2* ln_rows_s = reinterpret_cast<const float2*>(smem + C::EPI_OFF + EPI_WARP_BYTES + 2 * EBUF_BYTES);
     uint64_t* rbar = res_bar + 2 * ew;
     // a unit: 32 accumulator columns (GEGLU: 64 -> 32 output columns)
     constexpr int UNITS = GEGLU ? BN / 64 : BN / 32;
@@ -431,24 +489,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           c1_s[acc * BN + etid] = cv;
         }
       }
-      // LayerNorm folded into this GEMM: mean / rstd of this thread's row from the producer's partial sums
-      float ln_r = 1.f, ln_nm = 0.f;   // out = ln_r * acc + ln_nm * c1 + bias
+      // LayerNorm folded into this GEMM: {rstd, -rstd * mean} of this thread's row, prepared by the statistics warp
+      // one or two tiles ahead (out = ln_r * acc + ln_nm * c1 + bias)
+      float ln_r = 1.f, ln_nm = 0.f;
       if (p.ln_in != nullptr) {
-        int row = w + lane;             // linear geometry: the unit's rows are consecutive output pixels
-        if (row >= p.Wout) row = p.Wout - 1;
-        const float2* lp = p.ln_in + static_cast<long long>(row) * p.ln_in_parts;
-        float s = 0.f, ss = 0.f;
-        for (int i = 0; i < p.ln_in_parts; ++i) {
-          const float2 t = __ldg(lp + i);
-          s += t.x;
-          ss += t.y;
-        }
-        const float mu = s * p.ln_inv_c;
-        const float var = fmaxf(ss * p.ln_inv_c - mu * mu, 0.f);
-        ln_r = rsqrtf(var + p.ln_eps);
-        ln_nm = -ln_r * mu;
+        ptx::mbar_wait(&ln_full[acc], acc_phase);
+        const float2 st = ln_rows_s[acc * BM + quad * 32 + lane];
+        ln_r = st.x;
+        ln_nm = st.y;
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&ln_empty[acc]);
       }
-      float ln_s = 0.f, ln_ss = 0.f;   // producer side: this thread's row sums over the columns this warp owns
       ptx::named_bar_sync(1, 32 * EPI_WARPS);
       const float* bs = bias_s + acc * BN;
       const float* cs = c1_s + acc * BN;
@@ -694,8 +745,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
               for (int j = 0; j < 32; ++j) {
                 if (nt * BN + ku * 32 + j < p.N) { a4[j & 3] += r[j]; b4[j & 3] = fmaf(r[j], r[j], b4[j & 3]); }
               }
-              ln_s += (a4[0] + a4[1]) + (a4[2] + a4[3]);
-              ln_ss += (b4[0] + b4[1]) + (b4[2] + b4[3]);
+              // one partial per 32-column unit, whatever the N tile: every schedule hands the consumer the same sums
+              if (n < p.Nimg && w + lane < p.Wout)
+                p.ln_out[static_cast<long long>(w + lane) * p.ln_out_parts + nt * (BN / 32) + ku] =
+                    make_float2((a4[0] + a4[1]) + (a4[2] + a4[3]), (b4[0] + b4[1]) + (b4[2] + b4[3]));
             }
           } else {  // SiLU (time-embedding MLP): act(acc + bias + rowvec) + residual
             ptx::tmem_ld_wait();
@@ -728,8 +781,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         }
         ++it;
       }
-      if (!GEGLU && p.ln_out != nullptr && n < p.Nimg && w + lane < p.Wout)
-        p.ln_out[static_cast<long long>(w + lane) * p.ln_out_parts + 2 * nt + part] = make_float2(ln_s, ln_ss);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -794,8 +845,8 @@ static int launch_bn(const CUtensorMap* tm, const Params& p, const PhaseMaps& pm
   }
   const int total = p.m_tiles * p.n_tiles * p.phases;
   const int grid = total < num_sms() ? total : num_sms();
-  conv_tc_kernel<BN, GEGLU, false><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5],
-                                                                             p, pm);
+  EALDM_CUDA(launch_pdl(conv_tc_kernel<BN, GEGLU, false>, dim3(grid), dim3(NUM_THREADS), C::SMEM_BYTES, st, tm[0], tm[1],
+                        tm[2], tm[3], tm[4], tm[5], p, pm));
   EALDM_LAUNCH_CHECK();
   return 0;
 }
@@ -808,16 +859,18 @@ static int launch_pair(const CUtensorMap* tm, const Params& p, const PhaseMaps& 
   static DeviceOnce attr_set;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.blockDim = dim3(NUM_THREADS);
   cfg.dynamicSmemBytes = C::SMEM_BYTES;
   cfg.stream = st;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 1;   // (the occupancy query below sees the cluster shape only)
   if (attr_set.pending()) {
     EALDM_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, GEGLU, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     C::SMEM_BYTES));
@@ -833,6 +886,7 @@ static int launch_pair(const CUtensorMap* tm, const Params& p, const PhaseMaps& 
   const int total = ((p.m_tiles + 1) / 2) * p.n_tiles * p.phases;
   const int clusters = total < max_clusters ? total : max_clusters;
   cfg.gridDim = dim3(2 * clusters);
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   EALDM_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, GEGLU, true>, tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], p, pm));
   EALDM_LAUNCH_CHECK();
   return 0;
@@ -986,11 +1040,8 @@ static int choose_bn(const ealdm_conv_args* a, long long m_work) {
   return BN;
 }
 
-// number of {sum, sum of squares} partials per row a launch with ln_partial_out writes: 2 per N tile (linear geometry)
-int ln_parts(const ealdm_conv_args* a) {
-  const long long m_tiles = ceil_div(a->w_out, BM);
-  return 2 * static_cast<int>(ceil_div(a->n_out, choose_bn(a, m_tiles)));
-}
+// number of {sum, sum of squares} partials per row a launch with ln_partial_out writes: one per 32 output columns
+int ln_parts(const ealdm_conv_args* a) { return static_cast<int>(ceil_div(a->n_out, 32)); }
 
 int launch(const ealdm_conv_args* a, cudaStream_t st) {
   EALDM_REQUIRE(supported(a), "tcgen05 conv: unsupported shape/alignment (c%%64, 16-byte rows and pointers)");
@@ -1131,7 +1182,7 @@ int launch(const ealdm_conv_args* a, cudaStream_t st) {
   p.gn_chunks = static_cast<int>(a->h_out * a->w_out / 32);
   p.gn_phase_chunks = static_cast<int>(h_grid * w_grid / 32);
   p.ln_out = reinterpret_cast<float2*>(a->ln_partial_out);
-  p.ln_out_parts = 2 * p.n_tiles;
+  p.ln_out_parts = static_cast<int>(ceil_div(a->n_out, 32));
   p.ln_in = reinterpret_cast<const float2*>(a->ln_partial_in);
   p.ln_in_parts = static_cast<int>(a->ln_parts_in);
   p.ln_inv_c = a->ln_channels > 0 ? 1.0f / static_cast<float>(a->ln_channels) : 0.f;

@@ -185,6 +185,8 @@ gn_apply_partial_kernel(const TX* __restrict__ x, long long ld_x, T* __restrict_
                         float* __restrict__ stats_out) {
   constexpr bool SILU_FAST = sizeof(T) == 2;
   __shared__ float s_mean[MAX_GROUPS], s_rstd[MAX_GROUPS];
+  pdl_wait();      // launched with programmatic serialization (common.cuh): x / partial belong to the predecessor
+  pdl_trigger();
   const int t = threadIdx.x;
   const int n = blockIdx.y;
   const int cpg = c / groups;
@@ -331,10 +333,10 @@ static int group_norm_t(const ealdm_group_norm_args* a, cudaStream_t st) {
       chunks = ceil_div(a->hw, ppc);
     }
     dim3 grid(static_cast<unsigned>(chunks), static_cast<unsigned>(a->n));
-    gn_apply_partial_kernel<TX, T><<<grid, NT, 0, st>>>(
-        reinterpret_cast<const TX*>(a->x), a->ld_x, reinterpret_cast<T*>(a->y), a->ld_y, static_cast<int>(a->hw),
-        static_cast<int>(a->c), a->groups, ppc, reinterpret_cast<const float2*>(a->partial), a->partial_ld, a->eps,
-        a->gamma, a->beta, a->act, a->stats_out);
+    EALDM_CUDA(launch_pdl(gn_apply_partial_kernel<TX, T>, grid, dim3(NT), 0, st, reinterpret_cast<const TX*>(a->x),
+                          a->ld_x, reinterpret_cast<T*>(a->y), a->ld_y, static_cast<int>(a->hw), static_cast<int>(a->c),
+                          a->groups, ppc, reinterpret_cast<const float2*>(a->partial), a->partial_ld, a->eps, a->gamma,
+                          a->beta, a->act, a->stats_out));
     EALDM_LAUNCH_CHECK();
     return 0;
   }

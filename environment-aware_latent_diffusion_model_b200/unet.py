@@ -353,7 +353,11 @@ class UNetEngine:
     sequence of libealdm_b200 launches on the current CUDA stream (CUDA-graph capturable: no host
     synchronisation, no data-dependent control flow)."""
     _fused_geglu = True   # the training engine keeps the GEGLU pre-activation instead (train.py)
-    _fold_ln = not os.environ.get("EALDM_NO_LN_FOLD")    # A/B switch: LayerNorm folded into the GEMMs around it
+    # LayerNorm folded into the GEMMs around it (producer row statistics + consumer epilogue correction): built, parity
+    # tested and measured NOT faster than the streaming LayerNorm passes it removes (same-box A/B 63.3 vs 64.0 samples/s:
+    # the producers pay for a bf16 shadow + statistics, the GEGLU epilogue for one more FMA and a shared-memory operand
+    # per element, DESIGN.md section 4), hence opt-in
+    _fold_ln = bool(os.environ.get("EALDM_LN_FOLD"))
     # one-kernel GEGLU FeedForward (csrc/ff_fused.cu): bit-identical to the two GEMMs and measured NOT faster yet
     # (269 us against 140 + 95 us at level 0, DESIGN.md section 4), hence opt-in
     _fused_ff = bool(os.environ.get("EALDM_FUSED_FF"))

@@ -69,6 +69,14 @@ enum {
                                     hardware tanh, 1 the exact-erf form (rational approximation, error 1.7e-6) */
 };
 int ealdm_tc_set_option(int option, int value);
+/*
+ * Programmatic dependent launch between consecutive kernels of one stream (default off; environment EALDM_PDL=1
+ * switches it on): the kernels of the forward path are then launched with the programmatic-stream-serialization
+ * attribute and execute griddepcontrol.wait before their first global-memory access, so that a prologue overlaps the
+ * tail of its predecessor.  Results are identical either way (measured: no gain under CUDA-graph replay).  Returns
+ * the previous setting.
+ */
+int ealdm_set_pdl(int enabled);
 
 /* ---- convolution / linear as implicit GEMM ------------------------------------------------- */
 /*
@@ -160,7 +168,8 @@ typedef struct {
 } ealdm_conv_args;
 
 int ealdm_conv(const ealdm_conv_args* a, ealdm_stream_t stream);
-/* partials per row that a launch with these args writes to ln_partial_out (2 per N tile of the schedule it selects) */
+/* partials per row that a launch with these args writes to ln_partial_out: one per 32 output columns, whatever the
+   schedule, so that every N tile / CTA-pair choice hands the consumer bit-identical sums */
 int64_t ealdm_conv_ln_parts(const ealdm_conv_args* a);
 
 /*

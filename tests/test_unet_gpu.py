@@ -86,6 +86,55 @@ def test_unet_forward_bench_schedules_vs_reference_golden(kind):
     assert torch.equal(eps, base)
 
 
+def test_unet_forward_with_folded_layer_norm(monkeypatch):
+    """The opt-in LayerNorm fold (EALDM_LN_FOLD: producer row statistics + consumer epilogue correction instead of
+    LayerNorm passes): same north-star tolerance, and the same bits under every conv schedule (the producer's partial
+    sums are per 32 columns whatever the N tile)."""
+    import ealdm_b200.unet as U
+    from ealdm_b200 import _lib as L
+    monkeypatch.setattr(U.UNetEngine, "_fold_ln", True)
+    G = gold("unet_stdiff_fwd.pt")
+    unet = make_ld("stdiff").model.diffusion_model.set_compute_dtype("bf16")
+    x, t, c = G["x"].cuda(), G["t"].cuda(), G["context"].cuda()
+    base = unet(x, t, context=c)
+    err = rel_l2(base, G["eps"])
+    print(f"unet stdiff bf16, LayerNorm folded: rel_l2 = {err:.3e}")
+    assert err < TOL["bf16"]
+    lib = L.load()
+    prev = [lib.ealdm_tc_set_option(o, v) for o, v in ((L.TC_OPT_BN, 256), (L.TC_OPT_CTA2, 2))]
+    try:
+        assert torch.equal(unet(x, t, context=c), base)
+    finally:
+        lib.ealdm_tc_set_option(L.TC_OPT_BN, prev[0])
+        lib.ealdm_tc_set_option(L.TC_OPT_CTA2, prev[1])
+
+
+def test_unet_forward_programmatic_dependent_launch_is_bit_identical():
+    """ealdm_set_pdl: the kernels of the forward are launched with programmatic stream serialization (each one waits on
+    griddepcontrol.wait before its first global access).  Eager and CUDA-graph replays with the attribute must equal
+    the plainly serialised launches bit for bit -- a kernel that starts before its predecessor's writes are visible
+    would show up here."""
+    from ealdm_b200 import _lib as L
+    G = gold("unet_stdiff_fwd.pt")
+    unet = make_ld("stdiff").model.diffusion_model.set_compute_dtype("bf16")
+    x, t, c = G["x"].cuda(), G["t"].cuda(), G["context"].cuda()
+    x = torch.cat([x] * 8); t = torch.cat([t] * 8); c = torch.cat([c] * 8)     # 16 samples: several tiles per SM
+    lib = L.load()
+    prev = lib.ealdm_set_pdl(0)
+    try:
+        base = unet(x, t, context=c)
+        lib.ealdm_set_pdl(1)
+        for _ in range(3):
+            assert torch.equal(unet(x, t, context=c), base)
+        unet.enable_cuda_graph(True)
+        for _ in range(3):
+            assert torch.equal(unet(x, t, context=c), base)
+        unet.enable_cuda_graph(False)
+    finally:
+        lib.ealdm_set_pdl(prev)
+    assert rel_l2(base[:2], G["eps"]) < TOL["bf16"]
+
+
 def test_unet_is_deterministic_and_batch_independent():
     G = gold("unet_stdiff_fwd.pt")
     unet = make_ld("stdiff").model.diffusion_model.set_compute_dtype("bf16")
