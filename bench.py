@@ -308,11 +308,15 @@ def run_train(args):
         clocks.start()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if args.ncu_window:
+        torch.cuda.profiler.start()
     e0.record()
     for _ in range(args.steps):
         lv = step()
     e1.record()
     barrier()
+    if args.ncu_window:
+        torch.cuda.profiler.stop()
     ms = e0.elapsed_time(e1)
     if world > 1:
         tt = torch.tensor([ms], device=dev)

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libealdm_b200.so")
 CSRC_DIR = os.path.join(_HERE, "csrc")
 
 F32, BF16 = 0, 1
-ACT_NONE, ACT_SILU, ACT_GEGLU, ACT_RELU = 0, 1, 2, 3
+ACT_NONE, ACT_SILU, ACT_GEGLU, ACT_RELU, ACT_SOFTMAX4 = 0, 1, 2, 3, 4
 IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05 = 0, 1, 2
 TC_OPT_CTA2, TC_OPT_WIDE, TC_OPT_RELAXED_WAIT, TC_OPT_BN, TC_OPT_GELU_ERF = 0, 1, 2, 3, 4
 
@@ -53,7 +53,8 @@ class ConvArgs(C.Structure):
                 ("out2", C.c_void_p), ("ld_out2", C.c_int64), ("gn_partial", C.c_void_p), ("gn_ld", C.c_int64),
                 ("weight_adjoint", C.c_int32), ("upsample_phases", C.c_int32), ("ld_weight", C.c_int64),
                 ("ln_partial_out", C.c_void_p), ("ln_partial_in", C.c_void_p), ("ln_parts_in", C.c_int64),
-                ("ln_c1", C.c_void_p), ("ln_channels", C.c_int64), ("ln_eps", C.c_float), ("reserved3", C.c_int32)]
+                ("ln_c1", C.c_void_p), ("ln_channels", C.c_int64), ("ln_eps", C.c_float), ("wi_tokens", C.c_int32),
+                ("wi_heads", C.c_int32), ("reserved4", C.c_int32), ("wi_ld", C.c_int64), ("wi_head_stride", C.c_int64)]
 
 
 class GroupNormArgs(C.Structure):

@@ -78,7 +78,8 @@ extern "C" int ealdm_conv(const ealdm_conv_args* a, ealdm_stream_t stream) {
   EALDM_REQUIRE(a->n_src == 1 || a->n_src == 2, "conv: n_src must be 1 or 2");
   EALDM_REQUIRE(a->weight && a->out, "conv: null weight/out");
   EALDM_REQUIRE(a->n_out > 0 && a->k_total > 0 && a->h_out > 0 && a->w_out > 0, "conv: bad sizes");
-  EALDM_REQUIRE(a->act >= EALDM_ACT_NONE && a->act <= EALDM_ACT_RELU, "conv: bad act %d", a->act);
+  EALDM_REQUIRE(a->act >= EALDM_ACT_NONE && a->act <= EALDM_ACT_SOFTMAX4, "conv: bad act %d", a->act);
+  EALDM_REQUIRE(a->act != EALDM_ACT_SOFTMAX4 || a->wi_tokens == 4, "conv: SOFTMAX4 needs per-image weights, 4 tokens");
   EALDM_REQUIRE(!(a->act == EALDM_ACT_GEGLU && (a->rowvec || a->out2)),
                 "conv: GEGLU with rowvec / out2 unsupported");
   for (int s = 0; s < a->n_src; ++s) {
@@ -96,9 +97,15 @@ extern "C" int ealdm_conv(const ealdm_conv_args* a, ealdm_stream_t stream) {
                   (long long)a->w_out);
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (a->weight_adjoint) {
+  if (a->weight_adjoint && !a->wi_tokens) {
     EALDM_REQUIRE(a->impl != EALDM_IMPL_SIMT && a->dtype == EALDM_BF16 && tc::supported(a),
                   "conv: weight_adjoint needs the tcgen05 path (bf16, one source, c %% 64 == 0, n_out %% 64 == 0)");
+    return tc::launch(a, st);
+  }
+  if (a->wi_tokens) {
+    EALDM_REQUIRE(a->impl != EALDM_IMPL_SIMT && a->dtype == EALDM_BF16 && tc::supported(a),
+                  "conv: per-image weights (wi_*) need the tcgen05 path: bf16, one 1x1 source, h*w %% 128 == 0, "
+                  "wi_heads * wi_tokens in {32, 64, 96, 128}");
     return tc::launch(a, st);
   }
   EALDM_REQUIRE(!(a->ln_partial_out || a->ln_partial_in) ||

@@ -103,6 +103,8 @@ struct Params {
   // CONSUMER side (ln_in): A is the RAW stream (its bf16 shadow), W was packed as W * gamma, `bias` holds
   // W beta (+ bias), ln_c1[col] = sum_k (W * gamma)[col, k]; with mu, rstd of the row from the partials
   //   out = rstd * acc - rstd * mu * c1[col] + bias[col]  ==  LayerNorm(x) W^T + bias
+  // per-image B operand (ealdm_conv_args::wi_*): tmB is a 4-D (c, token, head, image) map, a tile lies in one image
+  int b_img;
   float2* ln_out;
   int ln_out_parts;
   const float2* ln_in;
@@ -316,7 +318,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             ptx::mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
             ptx::tma_load_4d(sa, tmA, &full_bar[stage], cb * BK, w0 * sg.stride + kw - sg.pad,
                              h0 * sg.stride + kh - sg.pad, n0);
-            if (p.b_mn) {
+            if (p.b_img) {
+              // per-image B: the (token, head) rows of image n0 gathered by one 4-D box per [64 x 64] / [BN x 64] atom
+              if (p.b_mn) {
+#pragma unroll
+                for (int g = 0; g < BN / 64; ++g)
+                  ptx::tma_load_4d(sa + C::A_BYTES + g * 8192, &tmB, &full_bar[stage], nt * BN + g * 64, 0,
+                                   kb * (BK / p.b_img), n0);
+              } else {
+                ptx::tma_load_4d(sa + C::A_BYTES, &tmB, &full_bar[stage], kb * BK, 0, 0, n0);
+              }
+            } else if (p.b_mn) {
               // adjoint: rows = 64 source channels (K), columns = N of the flipped tap, 64 at a time (one SW128 atom)
               const int tcol = (sg.ksize * sg.ksize - 1 - tap) * p.N + nt * BN;
 #pragma unroll
@@ -750,6 +762,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 p.ln_out[static_cast<long long>(w + lane) * p.ln_out_parts + nt * (BN / 32) + ku] =
                     make_float2((a4[0] + a4[1]) + (a4[2] + a4[3]), (b4[0] + b4[1]) + (b4[2] + b4[3]));
             }
+          } else if (BN <= 128 && p.act == EALDM_ACT_SOFTMAX4) {
+            // collapsed cross-attention: the 32 columns are (head, key) base-2 logits; softmax over the 4 keys of a head
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              const float f0 = __uint_as_float(v[4 * g]) + bs[ku * 32 + 4 * g];
+              const float f1 = __uint_as_float(v[4 * g + 1]) + bs[ku * 32 + 4 * g + 1];
+              const float f2 = __uint_as_float(v[4 * g + 2]) + bs[ku * 32 + 4 * g + 2];
+              const float f3 = __uint_as_float(v[4 * g + 3]) + bs[ku * 32 + 4 * g + 3];
+              const float mx = fmaxf(fmaxf(f0, f1), fmaxf(f2, f3));
+              const float e0 = ex2_approx(f0 - mx), e1 = ex2_approx(f1 - mx), e2 = ex2_approx(f2 - mx),
+                          e3 = ex2_approx(f3 - mx);
+              const float inv = __fdividef(1.0f, (e0 + e1) + (e2 + e3));
+              r[4 * g] = e0 * inv; r[4 * g + 1] = e1 * inv; r[4 * g + 2] = e2 * inv; r[4 * g + 3] = e3 * inv;
+            }
           } else {  // SiLU (time-embedding MLP): act(acc + bias + rowvec) + residual
             ptx::tmem_ld_wait();
 #pragma unroll
@@ -930,9 +957,27 @@ static bool aligned_2d(const void* ptr, long long ld, int elem_bytes) {
 bool supported(const ealdm_conv_args* a) {
   if (a->dtype != EALDM_BF16) return false;
   if (a->n_src < 1 || a->n_src > 2) return false;
+  if (a->wi_tokens) {
+    // per-image B: one 1x1 source, a 128-row tile inside one image, (head, token) = the 32 logits / probabilities
+    const ealdm_conv_src& x = a->src[0];
+    if (a->n_src != 1 || x.ksize != 1 || x.stride != 1 || x.pad != 0 || x.upsample || a->upsample_phases) return false;
+    if ((x.h * x.w) % BM != 0 || a->h_out != x.h || a->w_out != x.w) return false;
+    const long long logits = static_cast<long long>(a->wi_tokens) * a->wi_heads;
+    if (a->wi_tokens < 1 || a->wi_heads < 1 || logits % 32 != 0 || logits > 128 || 64 % a->wi_tokens != 0) return false;
+    if (!aligned_2d(a->weight, a->wi_ld, 2) || a->wi_head_stride % 8 != 0 || a->rowvec || a->gn_partial) return false;
+    if (a->ln_partial_in || a->ln_partial_out) return false;
+    if (a->weight_adjoint) {
+      if (x.c != logits || a->n_out % 64 != 0 || a->n_out > a->wi_head_stride || a->act != EALDM_ACT_NONE) return false;
+    } else {
+      if (a->n_out != logits || x.c % BK != 0 || x.c > a->wi_head_stride || a->residual || a->out2 || a->out_f32) return false;
+      if (a->act != EALDM_ACT_SOFTMAX4 && a->act != EALDM_ACT_NONE) return false;
+    }
+  } else if (a->act == EALDM_ACT_SOFTMAX4) {
+    return false;
+  }
   for (int s = 0; s < a->n_src; ++s) {
     const ealdm_conv_src& x = a->src[s];
-    if (x.c % BK != 0 || !aligned_2d(x.x, x.ld, 2)) return false;
+    if ((x.c % BK != 0 && !(a->wi_tokens && a->weight_adjoint)) || !aligned_2d(x.x, x.ld, 2)) return false;
     if (x.upsample && !a->upsample_phases) return false;
     if (x.ksize != 1 && x.ksize != 3) return false;
     if (x.stride != 1 && x.stride != 2) return false;
@@ -946,7 +991,9 @@ bool supported(const ealdm_conv_args* a) {
     if (a->h_out != 2 * x.h || a->w_out != 2 * x.w || a->k_total != 16 * x.c) return false;
     if (x.h * x.w < 32 || (x.w & (x.w - 1)) != 0 || (x.h & (x.h - 1)) != 0) return false;
   }
-  if (a->weight_adjoint) {
+  if (a->wi_tokens) {
+    // (checked above)
+  } else if (a->weight_adjoint) {
     if (a->n_src != 1 || a->act == EALDM_ACT_GEGLU || a->n_out % 64 != 0) return false;
     const long long ldw = a->ld_weight ? a->ld_weight : a->n_out * a->src[0].ksize * a->src[0].ksize;
     if (!aligned_2d(a->weight, ldw, 2)) return false;
@@ -1077,7 +1124,7 @@ int launch(const ealdm_conv_args* a, cudaStream_t st) {
   // CTA pairs (256 x 256 tiles, a third less operand traffic per SM) for every problem with an even number of M tiles
   // and a reduction long enough (K >= 1024) to amortise the pair's cross-CTA barrier latency (measured: K = 256 / 512
   // GEMMs lose 5-25 % as pairs, K >= 1024 GEMMs and all 3x3 convs gain 3-12 %); EALDM_TC_CTA2=2 pairs regardless of K
-  const bool pair = (BN == 256 || (BN == 128 && !geglu && cta2_mode() >= 2)) && cta2_mode() != 0 && p.m_tiles >= 2 && p.m_tiles % 2 == 0 &&
+  const bool pair = !a->wi_tokens && (BN == 256 || (BN == 128 && !geglu && cta2_mode() >= 2)) && cta2_mode() != 0 && p.m_tiles >= 2 && p.m_tiles % 2 == 0 &&
                     ((phased ? a->k_total / 4 : a->k_total) >= 1024 || cta2_mode() == 2);  // 3: the K rule, 128-column tiles included
 
   CUtensorMap tm[6];  // A0, A1, W, out, out2, residual
@@ -1086,7 +1133,7 @@ int launch(const ealdm_conv_args* a, cudaStream_t st) {
   for (int s = 0; s < a->n_src; ++s) {
     const ealdm_conv_src& x = a->src[s];
     Segment& sg = p.seg[s];
-    sg.cblk = static_cast<int>(x.c / BK);
+    sg.cblk = static_cast<int>((x.c + BK - 1) / BK);  // (a 32-channel source of per-image weights: one zero-filled block)
     sg.ksize = phased ? 2 : x.ksize;  // a phase is a 2x2 convolution whose taps start at (py - 1, px - 1)
     sg.kblocks = sg.cblk * sg.ksize * sg.ksize;
     sg.pad = x.pad;
@@ -1112,7 +1159,24 @@ int launch(const ealdm_conv_args* a, cudaStream_t st) {
   EALDM_REQUIRE(koff == a->k_total, "k_total %lld does not match the sources (%d)",
                 (long long)a->k_total, koff);
   if (a->n_src == 1) tm[1] = tm[0];
-  if (a->weight_adjoint) {
+  if (a->wi_tokens) {
+    // 4-D (c, token, head, image) view of the context projection: box rows come out as (head, token), token fastest;
+    // adjoint (MN-major atoms of 64 K rows): heads beyond wi_heads are out of range and arrive as zeros
+    const cuuint64_t T = static_cast<cuuint64_t>(a->wi_tokens);
+    cuuint64_t gdim[4] = {static_cast<cuuint64_t>(a->weight_adjoint ? a->n_out : a->k_total), T,
+                          static_cast<cuuint64_t>(a->wi_heads), static_cast<cuuint64_t>(a->src[0].n)};
+    cuuint64_t gstr[3] = {static_cast<cuuint64_t>(a->wi_ld) * 2, static_cast<cuuint64_t>(a->wi_head_stride) * 2,
+                          static_cast<cuuint64_t>(a->wi_ld) * 2 * T};
+    // (N tile of the logits GEMM: 32 or 128 rows; heads beyond wi_heads are out of range -> zero rows, clipped outputs)
+    const int bn_logits = a->n_out <= 32 ? 32 : 128;
+    cuuint32_t box[4] = {64, static_cast<cuuint32_t>(T),
+                         static_cast<cuuint32_t>((a->weight_adjoint ? 64 : bn_logits) / a->wi_tokens), 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = encode(&tm[2], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(a->weight), gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(EALDM_ECUDA, "cuTensorMapEncodeTiled(per-image W) failed: %d", (int)r);
+  } else if (a->weight_adjoint) {
     const ealdm_conv_src& x = a->src[0];
     const long long wcols = a->n_out * x.ksize * x.ksize;
     const long long ldw = a->ld_weight ? a->ld_weight : wcols;
@@ -1189,6 +1253,7 @@ int launch(const ealdm_conv_args* a, cudaStream_t st) {
   p.ln_eps = a->ln_eps;
   p.ln_c1 = a->ln_c1;
   p.b_mn = a->weight_adjoint ? 1 : 0;
+  p.b_img = a->wi_tokens;
   p.wide = wide ? 1 : 0;
   p.relaxed_wait = g_opt[EALDM_TC_OPT_RELAXED_WAIT];
 

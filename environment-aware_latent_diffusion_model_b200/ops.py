@@ -107,7 +107,8 @@ class ConvIn:
 def conv(srcs: Sequence[ConvIn], weight: torch.Tensor, out: Act, *, bias: Optional[torch.Tensor] = None,
          rowvec: Optional[torch.Tensor] = None, rowvec_col0: int = 0, residual: Optional[Act] = None,
          act: int = L.ACT_NONE, impl: int = L.IMPL_AUTO, out2: Optional[Act] = None, adjoint: bool = False,
-         upsample_phases: bool = False, ln_stats: bool = False, ln: Optional[tuple] = None) -> Act:
+         upsample_phases: bool = False, ln_stats: bool = False, ln: Optional[tuple] = None,
+         wimg: Optional[tuple] = None) -> Act:
     """ealdm_conv: out = epilogue(sum_s im2col(src_s) @ weight[:, seg_s]^T). `weight` is [n_out, k_total].
     adjoint=True: data gradient of a forward layer -- `weight` is that layer's own packed matrix
     [src channels, ksize^2 * out.c] (may be a column window of a wider matrix); nothing is transposed or flipped."""
@@ -123,11 +124,28 @@ def conv(srcs: Sequence[ConvIn], weight: torch.Tensor, out: Act, *, bias: Option
         d.x, d.n, d.h, d.w, d.c, d.ld = s.x.ptr, s.x.n, s.x.h, s.x.w, s.x.c, s.x.ld
         d.ksize, d.stride, d.pad, d.upsample = s.ksize, s.stride, s.pad, s.upsample
         assert s.x.dtype == x0.dtype
-    assert weight.dim() == 2 and weight.dtype == x0.dtype
-    a.weight = weight.data_ptr()
     a.h_out, a.w_out = out.h, out.w
     assert out.n == x0.n
-    if adjoint:
+    if wimg is not None:
+        # per-image B operand (ealdm_conv_args::wi_*): `weight` is the context projection [n * tokens, ld] (one row per
+        # context token); wimg = (first column, tokens, heads, head stride).  adjoint: out = P[., heads * tokens] @ Zt_n.
+        col0, tokens, heads, hstride = wimg
+        assert len(srcs) == 1 and weight.dim() == 2 and weight.dtype == x0.dtype and weight.stride(1) == 1
+        assert weight.shape[0] == x0.n * tokens and col0 + heads * hstride <= weight.shape[1]
+        a.weight = weight.data_ptr() + col0 * weight.element_size()
+        a.wi_tokens, a.wi_heads, a.wi_ld, a.wi_head_stride = tokens, heads, weight.stride(0), hstride
+        a.impl = L.IMPL_TCGEN05
+        if adjoint:
+            assert x0.c == heads * tokens
+            a.n_out, a.k_total, a.weight_adjoint = out.c, x0.c, 1
+        else:
+            a.n_out, a.k_total = heads * tokens, x0.c
+    else:
+        assert weight.dim() == 2 and weight.dtype == x0.dtype
+        a.weight = weight.data_ptr()
+    if wimg is not None:
+        pass
+    elif adjoint:
         taps = srcs[0].ksize ** 2
         assert len(srcs) == 1 and weight.stride(1) == 1 and weight.shape == (x0.c, taps * out.c), \
             (tuple(weight.shape), x0.c, taps, out.c)

@@ -54,3 +54,25 @@ def pack_upsample_phases(w: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
                     taps.append(acc)                      # [O, I]
             phases.append(torch.stack(taps, dim=1))        # [O, 4, I]
     return torch.stack(phases, dim=1).reshape(w.shape[0], -1).to(dtype).contiguous()   # [O, 4 * 4 * I]
+
+
+def collapse_cross_attention(wq: torch.Tensor, wk: torch.Tensor, wv: torch.Tensor, wo: torch.Tensor, heads: int,
+                             scale: float, dtype: torch.dtype):
+    """CrossAttention (attention.py:170-193) on a context of a few tokens, collapsed onto the context.  With
+    q = x Wq^T, k_j = ctx_j Wk^T, v_j = ctx_j Wv^T the logits and the output projection are bilinear in (x, ctx):
+        sim[m, h, j]  = scale * sum_{d in head h} q[m, d] k_j[d]  =  x[m, :] . (ctx_j G_h),   G_h = scale Wk_h^T Wq_h
+        to_out(attn @ v)[m, :] = sum_{h, j} p[m, h, j] (ctx_j H_h) + b,                       H_h = Wv_h^T Wo_h^T
+    so ONE projection of the context by [G; H] (weights only, formed here in fp32 and rounded once) yields, per image,
+    the [heads * tokens, C] matrices the two per-image GEMMs of ealdm_conv(wi_*) multiply by.  log2(e) is folded into G:
+    the kernel's softmax runs in base 2.  Returns (G, H), each [heads * C, context_dim] with rows ordered (head, c)."""
+    inner, c = wq.shape
+    d = inner // heads
+    ctx_dim = wk.shape[1]
+    wq3 = wq.detach().float().reshape(heads, d, c)
+    wk3 = wk.detach().float().reshape(heads, d, ctx_dim)
+    wv3 = wv.detach().float().reshape(heads, d, ctx_dim)
+    wo3 = wo.detach().float().reshape(wo.shape[0], heads, d)
+    g = torch.einsum("hdc,hde->hce", wq3, wk3) * (scale * 1.4426950408889634)
+    h = torch.einsum("chd,hde->hce", wo3, wv3)
+    return (g.reshape(heads * c, ctx_dim).to(dtype).contiguous(),
+            h.reshape(heads * wo.shape[0], ctx_dim).to(dtype).contiguous())

@@ -19,7 +19,7 @@ import torch.nn as nn
 from . import _lib as L
 from . import ops
 from .ops import Act, ConvIn
-from .packing import geglu_interleave, pack_conv_weight, pack_upsample_phases
+from .packing import collapse_cross_attention, geglu_interleave, pack_conv_weight, pack_upsample_phases
 
 
 def zero_module(module: nn.Module) -> nn.Module:
@@ -362,6 +362,9 @@ class UNetEngine:
     # (269 us against 140 + 95 us at level 0), hence opt-in
     _fused_ff = bool(os.environ.get("EALDM_FUSED_FF"))
     _phased_upsample = not os.environ.get("EALDM_NO_PHASED_UPSAMPLE")   # A/B switch; the training engine saves `up`
+    # cross-attention collapsed onto the context (packing.collapse_cross_attention): to_q -> 4-key attention -> to_out
+    # become two per-image GEMMs of K = C / N = 32 and K = 32 / N = C; A/B switch, the training engine keeps q / k / v
+    _collapse_xattn = not os.environ.get("EALDM_NO_XATTN_COLLAPSE")
 
     def __init__(self, m: UNetModel, dtype: torch.dtype):
         L.load()
@@ -386,8 +389,10 @@ class UNetEngine:
         self.blocks = []          # execution list
         emb_w, emb_b = [], []     # all ResBlock emb_layers stacked into one GEMM
         kv_w = []                 # all cross-attention to_k / to_v stacked into one GEMM
+        xc_w = []                 # collapsed cross-attention: all [G; H] context projections stacked into one GEMM
         self.emb_cols = 0
         self.kv_cols = 0
+        self.xc_cols = 0
 
         def pack_res(rb: ResBlock):
             d = {"kind": "res", "cin": rb.channels, "cout": rb.out_channels}
@@ -430,6 +435,15 @@ class UNetEngine:
                 self.kv_cols += 2 * C_
                 t["o2"] = _PackedConv(self._c(tb.attn2.to_out[0].weight),
                                       f32(tb.attn2.to_out[0].bias), C_)
+                # (only where a 128-row tile lies inside one image at the model's nominal resolution: the projection of
+                # the context grows with heads * C = C^2 / 32 per layer, so unused blocks are not worth carrying)
+                if (self._collapse_xattn and self.dt == torch.bfloat16 and st.d_head == 32 and C_ % 64 == 0
+                        and (m.image_size // self._ds) ** 2 % 128 == 0 and st.n_heads * 4 <= 128):
+                    g_, h_ = collapse_cross_attention(tb.attn2.to_q.weight, tb.attn2.to_k.weight, tb.attn2.to_v.weight,
+                                                      tb.attn2.to_out[0].weight, st.n_heads, tb.attn2.scale, dtype)
+                    t["xc_col0"] = self.xc_cols          # U block at xc_col0, Zt block at xc_col0 + heads * C
+                    xc_w.extend([g_, h_])
+                    self.xc_cols += 2 * st.n_heads * C_
                 if self._fused_geglu:   # inference: value/gate rows interleaved for the fused GEGLU epilogue
                     wi, bi = geglu_interleave(self._c(tb.ff.net[0].proj.weight), tb.ff.net[0].proj.bias)
                     t["ff1"] = _PackedConv(wi, bi, 4 * C_)
@@ -473,6 +487,7 @@ class UNetEngine:
                 elif isinstance(layer, Downsample):
                     out.append({"kind": "down", "c": layer.channels,
                                 "conv": _PackedConv(pk(layer.op), f32(layer.op.bias), layer.out_channels)})
+                    self._ds *= 2
                 elif isinstance(layer, Upsample):
                     d = {"kind": "up", "c": layer.channels,
                          "conv": _PackedConv(pk(layer.conv), f32(layer.conv.bias), layer.out_channels)}
@@ -480,6 +495,7 @@ class UNetEngine:
                         # nearest-2x folded into the conv: four 2x2 output phases over the low-resolution input
                         d["w_phases"] = pack_upsample_phases(layer.conv.weight, dtype)
                     out.append(d)
+                    self._ds //= 2
                 elif isinstance(layer, nn.Conv2d):
                     d = {"kind": "conv_in", "conv": _PackedConv(pk(layer), f32(layer.bias), layer.out_channels)}
                     if self.dt == torch.bfloat16 and layer.in_channels < 64 and layer.kernel_size == (3, 3):
@@ -494,6 +510,7 @@ class UNetEngine:
                     raise TypeError(type(layer))
             return out
 
+        self._ds = 1              # downsampling factor of the level being packed (execution order)
         self.inp = [pack_layers(b) for b in m.input_blocks]
         self.mid = pack_layers(m.middle_block)
         self.outb = [pack_layers(b) for b in m.output_blocks]
@@ -502,6 +519,7 @@ class UNetEngine:
         self.emb_w = torch.cat(emb_w, dim=0)
         self.emb_b = torch.cat(emb_b, dim=0).float().contiguous()
         self.kv_w = torch.cat(kv_w, dim=0) if kv_w else None
+        self.xc_w = torch.cat(xc_w, dim=0) if xc_w else None
 
         # channel bookkeeping for the zero-copy skip concatenation
         def block_out_channels(layers, cin):
@@ -622,15 +640,26 @@ class UNetEngine:
                           head_dim=dh, n_q=tok, n_kv=tok, scale=dh ** -0.5)
             t1, t1_h = stream()
             ops.linear(o, tb["o1"].w, t1, bias=tb["o1"].b, residual=t, out2=t1_h, ln_stats=fold)
-            q2 = normed(t1, t1_h, tb, 2, "q2", (tb["q2"], None), C_)
-            o2 = self._new(n, h, w, C_)
-            kc = tb["kv_col0"]
-            ops.attention(q2, kv_all.cols(kc, C_), kv_all.cols(kc + C_, C_), o2, batch=n, heads=heads, head_dim=dh,
-                          n_q=tok, n_kv=n_ctx, scale=dh ** -0.5)
             ff_fold = fold and not fused_ff
             t2 = self._new(n, h, w, C_, f32)
             t2_h = self._new(n, h, w, C_) if ff_fold else None
-            ops.linear(o2, tb["o2"].w, t2, bias=tb["o2"].b, residual=t1, out2=t2_h, ln_stats=ff_fold)
+            xc = getattr(self, "xc_all", None)
+            if "xc_col0" in tb and xc is not None and not fold and tok % 128 == 0 and heads * n_ctx <= 128:
+                # collapsed cross-attention: logits = LN2(t1) U_n^T (softmax over the 4 keys in the epilogue), then
+                # t2 = P Zt_n + bias + t1; U_n / Zt_n are column windows of the context projection xc_all
+                a2 = self._new(n, h, w, C_)
+                ops.layer_norm(t1, tb["ln2"][0], tb["ln2"][1], 1e-5, a2)
+                pr = self._new(n, h, w, heads * n_ctx)
+                ops.conv([ConvIn(a2)], xc.buf, pr, act=L.ACT_SOFTMAX4, wimg=(tb["xc_col0"], n_ctx, heads, C_))
+                ops.conv([ConvIn(pr)], xc.buf, t2, bias=tb["o2"].b, residual=t1, adjoint=True,
+                         wimg=(tb["xc_col0"] + heads * C_, n_ctx, heads, C_))
+            else:
+                q2 = normed(t1, t1_h, tb, 2, "q2", (tb["q2"], None), C_)
+                o2 = self._new(n, h, w, C_)
+                kc = tb["kv_col0"]
+                ops.attention(q2, kv_all.cols(kc, C_), kv_all.cols(kc + C_, C_), o2, batch=n, heads=heads, head_dim=dh,
+                              n_q=tok, n_kv=n_ctx, scale=dh ** -0.5)
+                ops.linear(o2, tb["o2"].w, t2, bias=tb["o2"].b, residual=t1, out2=t2_h, ln_stats=ff_fold)
             last = bi == nb - 1   # the last t feeds proj_out as a GEMM operand -> compute dtype
             t, t_h = stream(last)
             if fused_ff:
@@ -730,6 +759,10 @@ class UNetEngine:
             ctx = ops.copy2d(csrc, Act.empty(n, 1, n_ctx, csrc.c, dt, dev)) if dt != torch.float32 else csrc
             kv_all = Act.empty(n, 1, n_ctx, self.kv_cols, dt, dev)
             ops.linear(ctx, self.kv_w, kv_all)
+            self.xc_all = None
+            if self.xc_w is not None and n_ctx == 4:
+                self.xc_all = Act.empty(n, 1, n_ctx, self.xc_cols, dt, dev)
+                ops.linear(ctx, self.xc_w, self.xc_all)
 
         # concat buffers of the output blocks: [h | skip]; producers write straight into them
         n_in = len(self.inp)

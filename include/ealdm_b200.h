@@ -35,7 +35,8 @@ extern "C" {
 typedef void* ealdm_stream_t; /* cudaStream_t */
 
 enum { EALDM_F32 = 0, EALDM_BF16 = 1 };
-enum { EALDM_ACT_NONE = 0, EALDM_ACT_SILU = 1, EALDM_ACT_GEGLU = 2, EALDM_ACT_RELU = 3 };
+enum { EALDM_ACT_NONE = 0, EALDM_ACT_SILU = 1, EALDM_ACT_GEGLU = 2, EALDM_ACT_RELU = 3,
+       EALDM_ACT_SOFTMAX4 = 4 /* softmax over every 4 consecutive output columns of base-2 logits (wi_* below) */ };
 enum { EALDM_IMPL_AUTO = 0, EALDM_IMPL_SIMT = 1, EALDM_IMPL_TCGEN05 = 2 };
 enum {
   EALDM_OK = 0,
@@ -164,7 +165,20 @@ typedef struct {
   const float* ln_c1;
   int64_t ln_channels;
   float ln_eps;
-  int32_t reserved3;
+  /* PER-IMAGE B operand (wi_tokens = T > 0; tcgen05 path, n_src = 1, ksize 1, h*w a multiple of 128 so that a 128-row
+     tile lies in one image).  Cross-attention on a short context collapses onto the context (DESIGN.md section 4;
+     replaces to_q -> einsum/softmax/einsum -> to_out of CrossAttention.forward, ldm/modules/attention.py:170-193):
+       scores[m, (h, j)] = x[m, :] . U_n[(h, j), :],     U_n[(h, j), c]  = sum_d Wq[h d, c] k_n[j, h d]  (scale folded)
+       out[m, :]         = P[m, :] Zt_n + b,             Zt_n[(h, j), c] = sum_d Wo[c, h d] v_n[j, h d]
+     with U and Zt rows of ONE projection of the context, `weight`[(n T + j) wi_ld + h wi_head_stride + c]:
+       weight_adjoint = 0:  B_n = U_n   (n_out = wi_heads * T logits: 32, 64, 96 or 128; k_total = src.c; act SOFTMAX4)
+       weight_adjoint = 1:  B_n = Zt_n  (src.c = wi_heads * T probabilities, n_out <= wi_head_stride)
+     The 4-D TMA box (c, j, h, n) gathers the (h, j) rows of image n straight from that projection. */
+  int32_t wi_tokens;
+  int32_t wi_heads;
+  int32_t reserved4;
+  int64_t wi_ld;
+  int64_t wi_head_stride;
 } ealdm_conv_args;
 
 int ealdm_conv(const ealdm_conv_args* a, ealdm_stream_t stream);

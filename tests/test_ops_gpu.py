@@ -335,6 +335,64 @@ def test_cross_attention_small_kv(dtype, nk):
     assert rel_l2(out.buf.float(), ref) < (2e-5 if dtype == torch.float32 else 4e-3)
 
 
+@pytest.mark.parametrize("n,hh,ww,C", [(3, 32, 32, 256), (2, 16, 16, 512), (2, 16, 8, 256), (1, 32, 16, 1024),
+                                       (2, 16, 16, 768)])
+def test_cross_attention_collapsed_onto_the_context(n, hh, ww, C):
+    """CrossAttention (ldm/modules/attention.py:170-193) with a 4-token context, collapsed onto the context
+    (packing.collapse_cross_attention + ealdm_conv wi_*): logits = x U_n^T with the softmax over the 4 keys in the
+    epilogue, then out = P Zt_n + bias + residual, U_n / Zt_n gathered per image from ONE projection of the context.
+    Checked against torch fp32 on the same bf16-rounded inputs and against the q / k / v kernels it replaces."""
+    from ealdm_b200.packing import collapse_cross_attention
+    heads, d, T, E = C // 32, 32, 4, 512
+    M = n * hh * ww
+    bf = torch.bfloat16
+    x = torch.randn(M, C, generator=g(901)).to(DEV).to(bf)
+    ctx = torch.randn(n * T, E, generator=g(902)).to(DEV).to(bf)
+    wq = (torch.randn(C, C, generator=g(903)) / math.sqrt(C)).to(DEV)
+    wk = (torch.randn(C, E, generator=g(904)) * (2.0 / math.sqrt(E))).to(DEV)   # logits with a spread of a few units
+    wv = (torch.randn(C, E, generator=g(905)) / math.sqrt(E)).to(DEV)
+    wo = (torch.randn(C, C, generator=g(906)) / math.sqrt(C)).to(DEV)
+    bo = torch.randn(C, generator=g(907)).to(DEV)
+    res = torch.randn(M, C, generator=g(908)).to(DEV)
+    scale = d ** -0.5
+    # torch fp32 reference
+    q = (x.float() @ wq.t()).reshape(n, hh * ww, heads, d).transpose(1, 2)
+    k = (ctx.float() @ wk.t()).reshape(n, T, heads, d).transpose(1, 2)
+    v = (ctx.float() @ wv.t()).reshape(n, T, heads, d).transpose(1, 2)
+    o = _attn_ref(q, k, v, scale).transpose(1, 2).reshape(M, C)
+    want = o @ wo.t() + bo + res
+    # collapsed path
+    G, H = collapse_cross_attention(wq, wk, wv, wo, heads, scale, bf)
+    gh = torch.cat([G, H], dim=0)
+    xc = Act.empty(n, 1, T, gh.shape[0], bf, DEV)
+    ops.linear(Act(ctx, n, 1, T), gh, xc)
+    xa = Act(x, n, hh, ww)
+    pr = Act.empty(n, hh, ww, heads * T, bf, DEV)
+    ops.conv([ConvIn(xa)], xc.buf, pr, act=L.ACT_SOFTMAX4, wimg=(0, T, heads, C))
+    psum = pr.buf.float().reshape(M, heads, T).sum(-1)
+    assert (psum - 1).abs().max() < 2e-2            # rows of probabilities (bf16-rounded)
+    pref = torch.softmax(torch.einsum("bhqd,bhkd->bhqk", q, k) * scale, dim=-1).transpose(1, 2).reshape(M, heads * T)
+    assert (pr.buf.float() - pref).abs().max() < 2.5e-2
+    ra = Act(res, n, hh, ww)
+    out = Act.empty(n, hh, ww, C, torch.float32, DEV)
+    ops.conv([ConvIn(pr)], xc.buf, out, bias=bo, residual=ra, adjoint=True, wimg=(heads * C, T, heads, C))
+    # the kernels it replaces
+    qa = Act.empty(n, hh, ww, C, bf, DEV)
+    ops.linear(xa, wq.to(bf).contiguous(), qa)
+    kv = Act.empty(n, 1, T, 2 * C, bf, DEV)
+    ops.linear(Act(ctx, n, 1, T), torch.cat([wk, wv]).to(bf).contiguous(), kv)
+    oa = Act.empty(n, hh, ww, C, bf, DEV)
+    ops.attention(qa, kv.cols(0, C), kv.cols(C, C), oa, batch=n, heads=heads, head_dim=d, n_q=hh * ww, n_kv=T,
+                  scale=scale)
+    out_k = Act.empty(n, hh, ww, C, torch.float32, DEV)
+    ops.linear(oa, wo.to(bf).contiguous(), out_k, bias=bo, residual=ra)
+    # errors of the attention term alone (the residual would mask them)
+    e_new = rel_l2(out.buf - res - bo, want - res - bo)
+    e_old = rel_l2(out_k.buf - res - bo, want - res - bo)
+    print(f"collapsed cross-attention n={n} {hh}x{ww} C={C}: {e_new:.3e} (q/k/v kernels {e_old:.3e}) vs torch fp32")
+    assert e_new < 1e-2 and e_new < 1.5 * e_old + 2e-3
+
+
 def test_timestep_embedding_and_layout():
     t = torch.tensor([1, 501, 981, 0, 999], dtype=torch.int64, device=DEV)
     half = 128
