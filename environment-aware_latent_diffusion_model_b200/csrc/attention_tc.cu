@@ -22,6 +22,9 @@
 // WIDE = false: 32-column boxes with SWIZZLE_64B (half the shared memory and L2 traffic).
 #include "common.cuh"
 #include "ptx.cuh"
+#include "tc_math.cuh"
+
+#include <stdlib.h>
 
 #include <cuda.h>
 #include <cudaTypedefs.h>
@@ -44,8 +47,8 @@ struct Cfg {
   static constexpr int KV_BYTES = BN * ROW_BYTES;
   static constexpr int STAGE_BYTES = 2 * KV_BYTES;
   static constexpr int P_BYTES = BM * BN * 2;
-  static constexpr int Q_OFF = 0;
-  static constexpr int KV_OFF = Q_OFF + Q_BYTES;
+  static constexpr int Q_OFF = 0;                       // Q is double buffered (persistent CTAs)
+  static constexpr int KV_OFF = Q_OFF + 2 * Q_BYTES;
   static constexpr int P_OFF = KV_OFF + 2 * STAGE_BYTES;
   static constexpr int BAR_OFF = P_OFF + 2 * P_BYTES;   // P is double buffered
   static constexpr int SMEM_BYTES = BAR_OFF + 128;
@@ -79,8 +82,31 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&t);
 }
 
+// 2^x for a pair of arguments on the FMA pipe (FlashAttention-4's offload of part of the exponentials: the MUFU does 16
+// ex2 per clock and SM, the FMA pipe 128 FMAs): Cody-Waite split x = n + f with the 1.5 * 2^23 rounding constant, a
+// degree-3 minimax polynomial for 2^f on [-0.5, 0.5] (relative error 7.5e-5, far below the bf16 rounding of P), and n
+// added to the exponent field with one integer shift-add per element.
+__device__ __forceinline__ uint64_t ex2_poly2(uint64_t x2) {
+  using namespace tc;
+  float x0, x1;
+  upk2(x2, x0, x1);
+  x2 = pk2(fmaxf(x0, -125.f), fmaxf(x1, -125.f));          // below 2^-125 the exponent arithmetic would wrap
+  const uint64_t magic = pk2(12582912.f, 12582912.f);
+  const uint64_t t2 = add2(x2, magic);                       // the low mantissa bits of t hold round(x)
+  const uint64_t f2 = sub2(x2, sub2(t2, magic));
+  uint64_t p2 = fma2(f2, pk2(0.0551716685f, 0.0551716685f), pk2(0.2426111251f, 0.2426111251f));
+  p2 = fma2(p2, f2, pk2(0.6932609677f, 0.6932609677f));
+  p2 = fma2(p2, f2, pk2(0.9999280572f, 0.9999280572f));
+  float t0, t1, p0, p1;
+  upk2(t2, t0, t1);
+  upk2(p2, p0, p1);
+  const float r0 = __uint_as_float(__float_as_uint(p0) + (__float_as_uint(t0) << 23));
+  const float r1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(t1) << 23));
+  return pk2(r0, r1);
+}
+
 struct Params {
-  int n_q, n_kv, heads;
+  int n_q, n_kv, heads, batch;
   int hs_q, hs_kv;      // head strides in elements
   float scale_log2;
   bf16* out;
@@ -88,25 +114,42 @@ struct Params {
   float* lse;
 };
 
-template <bool WIDE>
+// POLY: how many of every 8 exponentials run on the FMA pipe (0, 2 or 4)
+//
+// PERSISTENT: a CTA walks work items (128 queries of one (batch, head)) i = blockIdx.x, blockIdx.x + gridDim.x, ...; the
+// shared-memory rings, the S / P / O hand-offs and their mbarrier parities run on ONE global key-tile counter g across the
+// items, Q is double buffered, so the loads and the first Q K^T of item i + 1 run under the last exponentials, the O read
+// and the output stores of item i -- the per-CTA set-up (TMEM allocation, barrier init, first DRAM round trips) is paid
+// once per SM slot instead of once per 128 queries.
+template <bool WIDE, int POLY>
 __global__ void __launch_bounds__(NUM_THREADS, 2)
 flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ Params p) {
   using C = Cfg<WIDE>;
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint64_t* q_full = reinterpret_cast<uint64_t*>(smem + C::BAR_OFF);
-  uint64_t* kv_full = q_full + 1;    // [2]
+  uint64_t* q_full = reinterpret_cast<uint64_t*>(smem + C::BAR_OFF);   // [2]
+  uint64_t* q_empty = q_full + 2;    // [2]
+  uint64_t* kv_full = q_empty + 2;   // [2]
   uint64_t* kv_empty = kv_full + 2;  // [2]
   uint64_t* s_full = kv_empty + 2;
   uint64_t* s_free = s_full + 1;
   uint64_t* p_ready = s_free + 1;
   uint64_t* pv_done = p_ready + 1;   // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
+  uint64_t* o_free = pv_done + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.z, h = blockIdx.y;
-  const int q0 = blockIdx.x * BM;
   const int ntiles = p.n_kv / BN;
+  const int qtiles = p.n_q / BM;
+  const int items = qtiles * p.heads * p.batch;
+  // item -> (query tile, head, batch): the items of one (batch, head) are neighbours and share K / V through L2
+  auto item_coords = [&](int it, int& q0, int& h, int& b) {
+    const int qt = it % qtiles;
+    const int bh = it / qtiles;
+    q0 = qt * BM;
+    h = bh % p.heads;
+    b = bh / p.heads;
+  };
 
   if (warp == 0 && lane == 0) {
     if ((ptx::smem_u32(smem) & 1023u) != 0) {
@@ -116,8 +159,9 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     ptx::prefetch_tensormap(&tmQ);
     ptx::prefetch_tensormap(&tmK);
     ptx::prefetch_tensormap(&tmV);
-    ptx::mbar_init(q_full, 1);
     for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(&q_full[s], 1);
+      ptx::mbar_init(&q_empty[s], 1);
       ptx::mbar_init(&kv_full[s], 1);
       ptx::mbar_init(&kv_empty[s], 1);
       ptx::mbar_init(&pv_done[s], 1);
@@ -125,6 +169,7 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     ptx::mbar_init(s_full, 1);
     ptx::mbar_init(s_free, 4);
     ptx::mbar_init(p_ready, 4);
+    ptx::mbar_init(o_free, 4);
     ptx::fence_mbar_init();
   }
   if (warp == 1) {
@@ -141,15 +186,23 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      ptx::mbar_arrive_expect_tx(q_full, C::Q_BYTES);
-      ptx::tma_load_2d(smem + C::Q_OFF, &tmQ, q_full, h * p.hs_q, b * p.n_q + q0);
-      for (int t = 0; t < ntiles; ++t) {
-        const int s = t & 1;
-        ptx::mbar_wait(&kv_empty[s], ((t >> 1) & 1) ^ 1u);
-        ptx::mbar_arrive_expect_tx(&kv_full[s], C::STAGE_BYTES);
-        uint8_t* st = smem + C::KV_OFF + s * C::STAGE_BYTES;
-        ptx::tma_load_2d(st, &tmK, &kv_full[s], h * p.hs_kv, b * p.n_kv + t * BN);
-        ptx::tma_load_2d(st + C::KV_BYTES, &tmV, &kv_full[s], h * p.hs_kv, b * p.n_kv + t * BN);
+      uint32_t g = 0;   // global key-tile counter
+      int li = 0;       // local item counter
+      for (int it = blockIdx.x; it < items; it += gridDim.x, ++li) {
+        int q0, h, b;
+        item_coords(it, q0, h, b);
+        const int qs = li & 1;
+        ptx::mbar_wait(&q_empty[qs], ((li >> 1) & 1) ^ 1u);
+        ptx::mbar_arrive_expect_tx(&q_full[qs], C::Q_BYTES);
+        ptx::tma_load_2d(smem + C::Q_OFF + qs * C::Q_BYTES, &tmQ, &q_full[qs], h * p.hs_q, b * p.n_q + q0);
+        for (int t = 0; t < ntiles; ++t, ++g) {
+          const int s = g & 1;
+          ptx::mbar_wait(&kv_empty[s], ((g >> 1) & 1) ^ 1u);
+          ptx::mbar_arrive_expect_tx(&kv_full[s], C::STAGE_BYTES);
+          uint8_t* st = smem + C::KV_OFF + s * C::STAGE_BYTES;
+          ptx::tma_load_2d(st, &tmK, &kv_full[s], h * p.hs_kv, b * p.n_kv + t * BN);
+          ptx::tma_load_2d(st + C::KV_BYTES, &tmV, &kv_full[s], h * p.hs_kv, b * p.n_kv + t * BN);
+        }
       }
     }
   } else if (warp == 1) {
@@ -160,45 +213,55 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     constexpr uint32_t SBO = WIDE ? 1024u : 512u;
     const uint32_t q_addr = ptx::smem_u32(smem + C::Q_OFF);
     const uint32_t p_addr = ptx::smem_u32(smem + C::P_OFF);
-    auto issue_s = [&](int t) {  // S = Q K_t^T
-      const uint32_t k_addr = ptx::smem_u32(smem + C::KV_OFF + (t & 1) * C::STAGE_BYTES);
-      const uint64_t adesc = make_desc(q_addr, 16, SBO, LT);
-      const uint64_t bdesc = make_desc(k_addr, 16, SBO, LT);
-#pragma unroll
-      for (int k = 0; k < 2; ++k)  // 16 elements = 32 B further inside the swizzle row
-        ptx::umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc_s, k != 0 ? 1u : 0u);
-      ptx::umma_commit(s_full);
-    };
-    ptx::mbar_wait(q_full, 0);
-    ptx::mbar_wait(&kv_full[0], 0);
-    ptx::tc_fence_after();
-    if (lane == 0) issue_s(0);
-    __syncwarp();
-    for (int t = 0; t < ntiles; ++t) {
-      if (t + 1 < ntiles) {
-        ptx::mbar_wait(&kv_full[(t + 1) & 1], ((t + 1) >> 1) & 1);
-        ptx::mbar_wait(s_free, t & 1);  // the softmax warps have read S_t
-        ptx::tc_fence_after();
-        if (lane == 0) issue_s(t + 1);
-        __syncwarp();
-      }
-      ptx::mbar_wait(p_ready, t & 1);   // P_t is in shared memory (and O_{t-1} has been read)
+    const int my_items = blockIdx.x < static_cast<unsigned>(items)
+                             ? (items - 1 - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x) + 1 : 0;
+    const uint32_t total = static_cast<uint32_t>(my_items) * static_cast<uint32_t>(ntiles);
+    // S(g) = Q(item of g) K(g)^T; `first` / `last`: g is the first / last key tile of its item
+    auto issue_s = [&](uint32_t g, int li, bool first, bool last) {
+      if (first) ptx::mbar_wait(&q_full[li & 1], (li >> 1) & 1);
+      ptx::mbar_wait(&kv_full[g & 1], (g >> 1) & 1);
+      if (g > 0) ptx::mbar_wait(s_free, (g - 1) & 1);   // the softmax warps have read S(g - 1)
       ptx::tc_fence_after();
       if (lane == 0) {
-        const uint32_t v_addr = ptx::smem_u32(smem + C::KV_OFF + (t & 1) * C::STAGE_BYTES + C::KV_BYTES);
+        const uint32_t k_addr = ptx::smem_u32(smem + C::KV_OFF + (g & 1) * C::STAGE_BYTES);
+        const uint64_t adesc = make_desc(q_addr + (li & 1) * C::Q_BYTES, 16, SBO, LT);
+        const uint64_t bdesc = make_desc(k_addr, 16, SBO, LT);
+#pragma unroll
+        for (int k = 0; k < 2; ++k)  // 16 elements = 32 B further inside the swizzle row
+          ptx::umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+        ptx::umma_commit(s_full);
+        if (last) ptx::umma_commit(&q_empty[li & 1]);   // this item's Q tile has been multiplied for the last time
+      }
+      __syncwarp();
+    };
+    if (total > 0) issue_s(0, 0, true, ntiles == 1);
+    int li = 0, t = 0;   // item / key tile of g
+    for (uint32_t g = 0; g < total; ++g) {
+      if (g + 1 < total) {
+        const bool nfirst = t + 1 == ntiles;
+        const int nli = nfirst ? li + 1 : li;
+        const int nt = nfirst ? 0 : t + 1;
+        issue_s(g + 1, nli, nfirst, nt + 1 == ntiles);
+      }
+      ptx::mbar_wait(p_ready, g & 1);   // P(g) is in shared memory
+      if (t == 0 && li > 0) ptx::mbar_wait(o_free, (li - 1) & 1);   // the previous item's O has been read out of TMEM
+      ptx::tc_fence_after();
+      if (lane == 0) {
+        const uint32_t v_addr = ptx::smem_u32(smem + C::KV_OFF + (g & 1) * C::STAGE_BYTES + C::KV_BYTES);
         const uint32_t d_tmem = tmem_base + O_COL;
 #pragma unroll
         for (int k = 0; k < BN / 16; ++k) {
           // A: P sub-tile (k >> 2) of [128 x 64] bf16 (16 KB), 32 B per k-step inside the swizzle row
-          const uint64_t adesc = make_desc(p_addr + (t & 1) * C::P_BYTES + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024, 2);
+          const uint64_t adesc = make_desc(p_addr + (g & 1) * C::P_BYTES + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024, 2);
           // B: V rows 16k .. 16k+15 (MN-major: 16 rows of ROW_BYTES)
           const uint64_t bdesc = make_desc(v_addr + k * 16 * C::ROW_BYTES, 16, SBO, LT);
           ptx::umma_bf16(d_tmem, adesc, bdesc, idesc_o, (t | k) != 0 ? 1u : 0u);
         }
-        ptx::umma_commit(&kv_empty[t & 1]);
-        ptx::umma_commit(&pv_done[t & 1]);
+        ptx::umma_commit(&kv_empty[g & 1]);
+        ptx::umma_commit(&pv_done[g & 1]);
       }
       __syncwarp();
+      if (++t == ntiles) { t = 0; ++li; }
     }
   } else {
     // ===================== softmax (warps 2..5): one query row per thread =====================
@@ -206,14 +269,19 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int row = quad * 32 + lane;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
     const float c = p.scale_log2;
+    uint32_t g = 0;
+    int li = 0;
+    for (int it = blockIdx.x; it < items; it += gridDim.x, ++li) {
+    int q0, h, b;
+    item_coords(it, q0, h, b);
     float m_ref = -INFINITY;   // reference maximum (raw score units) the probabilities of this row are relative to
     float l = 0.f;
 
-    for (int t = 0; t < ntiles; ++t) {
-      // P is double buffered: buffer t&1 was last read by the P V product of tile t-2, which precedes S_t in the
-      // tensor pipe, so it is free as soon as S_t is
-      uint8_t* pbuf = smem + C::P_OFF + (t & 1) * C::P_BYTES;
-      ptx::mbar_wait(s_full, t & 1);
+    for (int t = 0; t < ntiles; ++t, ++g) {
+      // P is double buffered: buffer g&1 was last read by the P V product of tile g-2, which precedes S(g) in the
+      // tensor pipe, so it is free as soon as S(g) is
+      uint8_t* pbuf = smem + C::P_OFF + (g & 1) * C::P_BYTES;
+      ptx::mbar_wait(s_full, g & 1);
       ptx::tc_fence_after();
       uint32_t sv[2][32];
       ptx::tmem_ld_32x32(t_lane, sv[0]);
@@ -240,8 +308,8 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           const float corr = ex2f((m_ref - m_new) * c);           // 1 for the rows that keep their reference
           m_ref = m_new;
           l *= corr;
-          if (t > 0) {                                            // O (all previous tiles) lives in TMEM
-            ptx::mbar_wait(&pv_done[(t - 1) & 1], ((t - 1) >> 1) & 1);
+          if (t > 0) {                                            // O (all previous tiles of this item) lives in TMEM
+            ptx::mbar_wait(&pv_done[(g - 1) & 1], ((g - 1) >> 1) & 1);
             ptx::tc_fence_after();
             uint32_t vo[32];
             ptx::tmem_ld_32x32(t_lane + O_COL, vo);
@@ -250,8 +318,6 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             for (int j = 0; j < 32; ++j) vo[j] = __float_as_uint(__uint_as_float(vo[j]) * corr);
             ptx::tmem_st_32x32(t_lane + O_COL, vo);
             ptx::tmem_st_wait();
-            if (ch + 1 < 4) {   // the wait above also retired the prefetch of the next chunk: nothing to redo
-            }
           }
           for (int pc = 0; pc < ch; ++pc) {                       // probabilities of this tile already written
             uint8_t* prow = pbuf + (pc >> 1) * 16384 + row * 128;
@@ -267,26 +333,41 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             }
           }
         }
+        // p = 2^(s c - m c) on packed f32x2 arithmetic (one FFMA2 / FADD2 per element pair); POLY of every 8
+        // exponentials come from the FMA pipe (ex2_poly2), the others from the MUFU
         const float ms = -m_ref * c;
-        float s4[4] = {0.f, 0.f, 0.f, 0.f};
+        const uint64_t c2 = tc::pk2(c, c), ms2 = tc::pk2(ms, ms);
+        uint64_t sum2[2] = {0ull, 0ull};
         uint8_t* prow = pbuf + (ch >> 1) * 16384 + row * 128;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          float e[8];
+          uint32_t w[4];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            e[i] = ex2f(fmaf(__uint_as_float(v[8 * j + i]), c, ms));
-            s4[i & 3] += e[i];
+          for (int i = 0; i < 4; ++i) {
+            const uint64_t x2 =
+                tc::fma2(tc::pk2(__uint_as_float(v[8 * j + 2 * i]), __uint_as_float(v[8 * j + 2 * i + 1])), c2, ms2);
+            uint64_t e2;
+            if (2 * i < POLY) {
+              e2 = ex2_poly2(x2);
+            } else {
+              float x0, x1;
+              tc::upk2(x2, x0, x1);
+              e2 = tc::pk2(ex2f(x0), ex2f(x1));
+            }
+            sum2[i & 1] = tc::add2(sum2[i & 1], e2);
+            float e0, e1;
+            tc::upk2(e2, e0, e1);
+            w[i] = pack2(e0, e1);
           }
-          uint4 u;
-          u.x = pack2(e[0], e[1]);
-          u.y = pack2(e[2], e[3]);
-          u.z = pack2(e[4], e[5]);
-          u.w = pack2(e[6], e[7]);
           const int chunk = (ch & 1) * 4 + j;
-          *reinterpret_cast<uint4*>(prow + ((chunk ^ (row & 7)) << 4)) = u;
+          *reinterpret_cast<uint4*>(prow + ((chunk ^ (row & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
         }
-        l += (s4[0] + s4[1]) + (s4[2] + s4[3]);
+        {
+          float a0, a1, b0, b1;
+          tc::upk2(sum2[0], a0, a1);
+          tc::upk2(sum2[1], b0, b1);
+          l += (a0 + a1) + (b0 + b1);
+        }
       }
       ptx::fence_proxy_async();
       __syncwarp();
@@ -295,12 +376,15 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     // O = sum over the tiles, relative to m_ref
     float o[32];
     {
-      const int t = ntiles - 1;
-      ptx::mbar_wait(&pv_done[t & 1], (t >> 1) & 1);
+      const uint32_t gl = g - 1;
+      ptx::mbar_wait(&pv_done[gl & 1], (gl >> 1) & 1);
       ptx::tc_fence_after();
       uint32_t v[32];
       ptx::tmem_ld_32x32(t_lane + O_COL, v);
       ptx::tmem_ld_wait();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(o_free);   // the next item's first P V may overwrite O
 #pragma unroll
       for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(v[j]);
     }
@@ -319,6 +403,7 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
     if (p.lse != nullptr)
       p.lse[(static_cast<long long>(b) * p.heads + h) * p.n_q + q0 + row] = fmaf(m, c, log2f(l));
+    }
   }
 
   ptx::tc_fence_before();
@@ -366,12 +451,13 @@ bool supported(const ealdm_attention_args* a) {
   return true;
 }
 
-template <bool WIDE>
+template <bool WIDE, int POLY>
 static int launch_t(const ealdm_attention_args* a, cudaStream_t st) {
   using C = Cfg<WIDE>;
   static DeviceOnce attr_set;
   if (attr_set.pending()) {
-    EALDM_CUDA(cudaFuncSetAttribute(flash_tc_kernel<WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    EALDM_CUDA(cudaFuncSetAttribute(flash_tc_kernel<WIDE, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    C::SMEM_BYTES));
     attr_set.done();
   }
   CUtensorMap tq, tk, tv;
@@ -384,20 +470,47 @@ static int launch_t(const ealdm_attention_args* a, cudaStream_t st) {
   p.n_q = static_cast<int>(a->n_q);
   p.n_kv = static_cast<int>(a->n_kv);
   p.heads = static_cast<int>(a->heads);
+  p.batch = static_cast<int>(a->batch);
   p.hs_q = static_cast<int>(a->head_stride_q);
   p.hs_kv = static_cast<int>(a->head_stride_kv);
   p.scale_log2 = a->scale * 1.4426950408889634f;
   p.out = reinterpret_cast<bf16*>(a->out);
   p.ld_out = a->ld_out;
   p.lse = a->lse;
-  dim3 grid(static_cast<unsigned>(a->n_q / BM), static_cast<unsigned>(a->heads), static_cast<unsigned>(a->batch));
-  EALDM_CUDA(launch_pdl(flash_tc_kernel<WIDE>, grid, dim3(NUM_THREADS), C::SMEM_BYTES, st, tq, tk, tv, p));
+  // persistent: two CTAs per SM (EALDM_ATTN_PERSIST=0: one CTA per work item, for A/B measurements)
+  const long long items = (a->n_q / BM) * a->heads * a->batch;
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  static const char* e_persist = getenv("EALDM_ATTN_PERSIST");
+  const long long slots = (e_persist && atoi(e_persist) == 0) ? items : 2LL * sms;
+  dim3 grid(static_cast<unsigned>(items < slots ? items : slots));
+  EALDM_CUDA(launch_pdl(flash_tc_kernel<WIDE, POLY>, grid, dim3(NUM_THREADS), C::SMEM_BYTES, st, tq, tk, tv, p));
   EALDM_LAUNCH_CHECK();
   return 0;
 }
 
+// EALDM_ATTN_POLY = 0 / 2 / 4: exponentials per 8 on the FMA pipe (A/B switch; results differ by the polynomial's 7.5e-5)
+static int poly_mode() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("EALDM_ATTN_POLY");
+    v = e ? atoi(e) : 2;
+  }
+  return v;
+}
+
 int launch(const ealdm_attention_args* a, cudaStream_t st, bool wide) {
-  return wide ? launch_t<true>(a, st) : launch_t<false>(a, st);
+  if (wide) return launch_t<true, 0>(a, st);
+  switch (poly_mode()) {
+    case 0: return launch_t<false, 0>(a, st);
+    case 4: return launch_t<false, 4>(a, st);
+    default: return launch_t<false, 2>(a, st);
+  }
 }
 
 }  // namespace attn_tc

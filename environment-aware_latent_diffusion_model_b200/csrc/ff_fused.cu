@@ -25,6 +25,7 @@
 #include "tc_math.cuh"
 
 #include <cuda.h>
+#include <stdlib.h>
 #include <cudaTypedefs.h>
 
 namespace ealdm {
@@ -80,7 +81,11 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* s
                : "memory");
 }
 
-template <int FORM>   // GELU form, tc_math.cuh: 1 tanh, 2 erf
+// FORM: GELU form, tc_math.cuh: 1 tanh, 2 erf.  CL: thread-block cluster size.  The CTAs of a cluster work on different row
+// tiles but consume the SAME weight slots in the same order, so every CTA fetches 1 / CL of each slot and multicasts it
+// to the whole cluster (a slot is released by the MMAs of ALL its CTAs): per 128-row tile an SM pulls 64 KB of x +
+// 1536 / CL KB of weights through its TMA path instead of 1600 KB, which is what bounds the CL = 1 kernel.
+template <int FORM, int CL>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 ff_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
                 const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmRes,
@@ -117,7 +122,7 @@ ff_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     ptx::mbar_init(a_empty, 1);
     for (int s = 0; s < NSLOT; ++s) {
       ptx::mbar_init(&r_full[s], 1);
-      ptx::mbar_init(&r_empty[s], 1);
+      ptx::mbar_init(&r_empty[s], CL);
     }
     for (int b = 0; b < 2; ++b) {
       ptx::mbar_init(&d1_full[b], 1);
@@ -147,9 +152,15 @@ ff_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if constexpr (CL > 1) ptx::cluster_sync_all();   // every CTA's barriers exist before a peer multicasts to them
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // every CTA of a cluster runs the same number of tiles (the weight ring is shared); tiles >= m_tiles are dummies whose
+  // loads are zero-filled and whose stores are clipped by the TMA unit
   const int tile_first = static_cast<int>(blockIdx.x), tile_step = static_cast<int>(gridDim.x);
+  const int tile_end = static_cast<int>((p.m_tiles + gridDim.x - 1) / gridDim.x) * tile_step;
+  const uint32_t cta_rank = CL > 1 ? ptx::cluster_ctarank() : 0u;
+  constexpr uint16_t CL_MASK = static_cast<uint16_t>((1u << CL) - 1u);
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -158,10 +169,14 @@ ff_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       auto load_w = [&](const CUtensorMap* tm, int c0, int c1) {
         ptx::mbar_wait(&r_empty[slot], sphase ^ 1u);
         ptx::mbar_arrive_expect_tx(&r_full[slot], SLOT);
-        ptx::tma_load_2d(smem + RING_OFF + slot * SLOT, tm, &r_full[slot], c0, c1);
+        if constexpr (CL > 1)   // this CTA's 128 / CL rows of the box, to every CTA of the cluster
+          ptx::tma_load_2d_mcast(smem + RING_OFF + slot * SLOT + cta_rank * (SLOT / CL), tm, &r_full[slot], c0,
+                                 c1 + static_cast<int>(cta_rank) * (128 / CL), CL_MASK);
+        else
+          ptx::tma_load_2d(smem + RING_OFF + slot * SLOT, tm, &r_full[slot], c0, c1);
         if (++slot == NSLOT) { slot = 0; sphase ^= 1u; }
       };
-      for (int tile = tile_first; tile < p.m_tiles; tile += tile_step, ++tcount) {
+      for (int tile = tile_first; tile < tile_end; tile += tile_step, ++tcount) {
         ptx::mbar_wait(a_empty, (tcount & 1u) ^ 1u);
         ptx::mbar_arrive_expect_tx(a_full, 4 * SLOT);
         for (int kb = 0; kb < 4; ++kb) ptx::tma_load_2d(smem + A_OFF + kb * SLOT, &tmX, a_full, kb * 64, tile * BM);
@@ -179,7 +194,7 @@ ff_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     constexpr uint32_t idesc = ptx::make_idesc_bf16(BM, 128);
     uint32_t slot = 0, sphase = 0, tcount = 0;
     uint32_t n_d1[2] = {0, 0}, n_h[2] = {0, 0};   // completed uses of each D1 / H buffer
-    for (int tile = tile_first; tile < p.m_tiles; tile += tile_step, ++tcount) {
+    for (int tile = tile_first; tile < tile_end; tile += tile_step, ++tcount) {
       ptx::mbar_wait(a_full, tcount & 1u);
       for (int j = 0; j <= NCHUNK; ++j) {
         if (j < NCHUNK) {  // D1(j) = x_tile * W1 chunk j
@@ -195,7 +210,8 @@ ff_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
               const uint64_t bdesc = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem + RING_OFF + slot * SLOT));
 #pragma unroll
               for (int k = 0; k < 4; ++k) ptx::umma_bf16(d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-              ptx::umma_commit(&r_empty[slot]);
+              if constexpr (CL > 1) ptx::umma_commit_mcast(&r_empty[slot], CL_MASK);
+              else ptx::umma_commit(&r_empty[slot]);
               if (kb == 3) {
                 ptx::umma_commit(&d1_full[b]);
                 if (j == NCHUNK - 1) ptx::umma_commit(a_empty);   // every read of the x tile has completed
@@ -220,7 +236,8 @@ ff_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
               const uint32_t d = tmem_base + TM_D2 + half * 128;
 #pragma unroll
               for (int k = 0; k < 4; ++k) ptx::umma_bf16(d, adesc + 2 * k, bdesc + 2 * k, idesc, (jj | k) != 0 ? 1u : 0u);
-              ptx::umma_commit(&r_empty[slot]);
+              if constexpr (CL > 1) ptx::umma_commit_mcast(&r_empty[slot], CL_MASK);
+              else ptx::umma_commit(&r_empty[slot]);
               if (half == 1) {
                 ptx::umma_commit(&h_empty[b]);
                 if (jj == NCHUNK - 1) ptx::umma_commit(d2_full);
@@ -253,7 +270,7 @@ ff_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       ptx::tma_load_2d(stg + (u & 1) * 2048, &tmRes, &rbar[u & 1], part * 128 + u * 16, tile * BM + quad * 32);
     };
 
-    for (int tile = tile_first; tile < p.m_tiles; tile += tile_step, ++tcount) {
+    for (int tile = tile_first; tile < tile_end; tile += tile_step, ++tcount) {
       if (lane == 0) {   // both staging buffers are free: the previous tile waited for its stores
         issue_res(tile, 0);
         issue_res(tile, 1);
@@ -370,6 +387,7 @@ ff_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
 
   ptx::tc_fence_before();
   __syncthreads();
+  if constexpr (CL > 1) ptx::cluster_sync_all();   // no CTA leaves while a peer may still multicast into it
   if (warp == 1) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, 512);
@@ -402,6 +420,45 @@ static int encode2d(CUtensorMap* tm, CUtensorMapDataType dt, int es, const void*
   return 0;
 }
 
+template <int FORM, int CL>
+static int launch_cl(const CUtensorMap* tm, const Params& p, cudaStream_t st) {
+  static DeviceOnce attr_set;
+  static int max_clusters = 0;   // devices of one process are assumed to be the same model
+  if (attr_set.pending()) {
+    EALDM_CUDA(cudaFuncSetAttribute(ff_fused_kernel<FORM, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_set.done();
+  }
+  int dev = 0, sms = 0;
+  EALDM_CUDA(cudaGetDevice(&dev));
+  EALDM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = SMEM_BYTES;
+  cfg.stream = st;
+  cfg.attrs = attr;
+  cfg.numAttrs = CL > 1 ? 1 : 0;
+  if (!max_clusters) {
+    int n = sms / CL;
+    if (CL > 1) {
+      cfg.gridDim = dim3((sms / CL) * CL);
+      EALDM_CUDA(cudaOccupancyMaxActiveClusters(&n, ff_fused_kernel<FORM, CL>, &cfg));
+      EALDM_REQUIRE(n > 0, "ff_fused: no %d-CTA cluster fits on this device", CL);
+      if (n > sms / CL) n = sms / CL;
+    }
+    max_clusters = n;
+  }
+  const int want = static_cast<int>(ceil_div(p.m_tiles, CL));
+  cfg.gridDim = dim3(CL * (want < max_clusters ? want : max_clusters));
+  EALDM_CUDA(cudaLaunchKernelEx(&cfg, ff_fused_kernel<FORM, CL>, tm[0], tm[1], tm[2], tm[3], tm[4], p));
+  return 0;
+}
+
 int launch(const ealdm_ff_fused_args* a, cudaStream_t st) {
   auto al = [](const void* p, long long ld, int es) {
     return (reinterpret_cast<uintptr_t>(p) & 15) == 0 && (ld * es) % 16 == 0;
@@ -413,18 +470,17 @@ int launch(const ealdm_ff_fused_args* a, cudaStream_t st) {
   EALDM_REQUIRE(al(a->x, a->ld_x, 2) && al(a->w1, C, 2) && al(a->w2, HID, 2) && al(a->residual, a->ld_res, 4) &&
                     al(a->out, a->ld_out, a->out_f32 ? 4 : 2),
                 "ff_fused: pointers and row pitches must be 16-byte aligned");
-  static DeviceOnce attr_set;
-  if (attr_set.pending()) {
-    EALDM_CUDA(cudaFuncSetAttribute(ff_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    EALDM_CUDA(cudaFuncSetAttribute(ff_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_set.done();
-  }
   CUtensorMap tm[5];
   const auto BF = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   const auto F32 = CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
   if (int e = encode2d(&tm[0], BF, 2, a->x, C, a->rows, a->ld_x, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
-  if (int e = encode2d(&tm[1], BF, 2, a->w1, C, 2 * HID, C, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
-  if (int e = encode2d(&tm[2], BF, 2, a->w2, HID, C, HID, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
+  static const int cl = [] {   // EALDM_FF_CLUSTER = 1 | 2 | 4: CTAs sharing every weight slot by multicast
+    const char* e = getenv("EALDM_FF_CLUSTER");
+    const int v = e ? atoi(e) : 2;
+    return (v == 1 || v == 4) ? v : 2;
+  }();
+  if (int e = encode2d(&tm[1], BF, 2, a->w1, C, 2 * HID, C, 64, 128 / cl, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
+  if (int e = encode2d(&tm[2], BF, 2, a->w2, HID, C, HID, 64, 128 / cl, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
   if (int e = encode2d(&tm[3], F32, 4, a->residual, C, a->rows, a->ld_res, 16, 32, CU_TENSOR_MAP_SWIZZLE_64B)) return e;
   if (a->out_f32) {
     if (int e = encode2d(&tm[4], F32, 4, a->out, C, a->rows, a->ld_out, 16, 32, CU_TENSOR_MAP_SWIZZLE_64B)) return e;
@@ -436,14 +492,12 @@ int launch(const ealdm_ff_fused_args* a, cudaStream_t st) {
   p.out_f32 = a->out_f32;
   p.b1 = a->b1;
   p.b2 = a->b2;
-  int dev = 0, sms = 0;
-  EALDM_CUDA(cudaGetDevice(&dev));
-  EALDM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  const int grid = p.m_tiles < sms ? p.m_tiles : sms;
-  if (tc::get_option(EALDM_TC_OPT_GELU_ERF))
-    ff_fused_kernel<2><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], p);
-  else
-    ff_fused_kernel<1><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], p);
+  const bool erf = tc::get_option(EALDM_TC_OPT_GELU_ERF) != 0;
+  switch (cl) {
+    case 1: if (int e = erf ? launch_cl<2, 1>(tm, p, st) : launch_cl<1, 1>(tm, p, st)) return e; break;
+    case 4: if (int e = erf ? launch_cl<2, 4>(tm, p, st) : launch_cl<1, 4>(tm, p, st)) return e; break;
+    default: if (int e = erf ? launch_cl<2, 2>(tm, p, st) : launch_cl<1, 2>(tm, p, st)) return e; break;
+  }
   EALDM_LAUNCH_CHECK();
   return 0;
 }
