@@ -476,8 +476,8 @@ int launch(const ealdm_ff_fused_args* a, cudaStream_t st) {
   if (int e = encode2d(&tm[0], BF, 2, a->x, C, a->rows, a->ld_x, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
   static const int cl = [] {   // EALDM_FF_CLUSTER = 1 | 2 | 4: CTAs sharing every weight slot by multicast
     const char* e = getenv("EALDM_FF_CLUSTER");
-    const int v = e ? atoi(e) : 2;
-    return (v == 1 || v == 4) ? v : 2;
+    const int v = e ? atoi(e) : 1;   // measured at M = 131072: 271 / 273 / 305 us for 1 / 2 / 4 -- the kernel is bound by
+    return (v == 2 || v == 4) ? v : 1;   // the DEPTH of its 5-slot weight ring (80 KB in flight), not by L2 -> SM bandwidth
   }();
   if (int e = encode2d(&tm[1], BF, 2, a->w1, C, 2 * HID, C, 64, 128 / cl, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
   if (int e = encode2d(&tm[2], BF, 2, a->w2, HID, C, HID, 64, 128 / cl, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
@@ -494,9 +494,9 @@ int launch(const ealdm_ff_fused_args* a, cudaStream_t st) {
   p.b2 = a->b2;
   const bool erf = tc::get_option(EALDM_TC_OPT_GELU_ERF) != 0;
   switch (cl) {
-    case 1: if (int e = erf ? launch_cl<2, 1>(tm, p, st) : launch_cl<1, 1>(tm, p, st)) return e; break;
     case 4: if (int e = erf ? launch_cl<2, 4>(tm, p, st) : launch_cl<1, 4>(tm, p, st)) return e; break;
-    default: if (int e = erf ? launch_cl<2, 2>(tm, p, st) : launch_cl<1, 2>(tm, p, st)) return e; break;
+    case 2: if (int e = erf ? launch_cl<2, 2>(tm, p, st) : launch_cl<1, 2>(tm, p, st)) return e; break;
+    default: if (int e = erf ? launch_cl<2, 1>(tm, p, st) : launch_cl<1, 1>(tm, p, st)) return e; break;
   }
   EALDM_LAUNCH_CHECK();
   return 0;
