@@ -18,7 +18,7 @@ import torch.nn as nn
 from . import _lib as L
 from . import ops
 from .ops import Act, ConvIn
-from .packing import pack_conv_weight
+from .packing import pack_conv_weight, pack_upsample_phases
 from .unet import Dual
 from .util import instantiate_from_config
 
@@ -405,6 +405,9 @@ class AutoencoderEngine:
                     e["resample"] = pc(lvl.downsample.conv)
                 if hasattr(lvl, "upsample"):
                     e["resample"] = pc(lvl.upsample.conv)
+                    if dtype == torch.bfloat16 and lvl.upsample.conv.in_channels % 64 == 0:
+                        # nearest-2x + conv3x3 as four 2x2 output phases over the low-resolution input (4/9 of the FLOPs)
+                        e["resample_phases"] = pack_upsample_phases(lvl.upsample.conv.weight, dtype)
                 d["levels"].append(e)
             return d
 
@@ -418,8 +421,17 @@ class AutoencoderEngine:
         return Act.empty(n, h, w, c, dtype or self.dt, self.dev)
 
     def _new_dual(self, n, h, w, c) -> Dual:
-        f = self._new(n, h, w, c, torch.float32)
+        f = self._gp(self._new(n, h, w, c, torch.float32))
         return Dual(f, f if self.dt == torch.float32 else self._new(n, h, w, c))
+
+    def _gp(self, f: Act) -> Act:
+        """bf16 mode: the tcgen05 epilogue that writes this residual-stream tensor also writes its GroupNorm partial
+        statistics (per 32-pixel chunk and 8-channel octet), so the GroupNorm reading it is one streaming pass instead
+        of a statistics pass + an apply pass (as in unet.UNetEngine).  Octets resolve groups of >= 8 channels: 256 / 512
+        channel tensors; the 128-channel level (4 channels per group) keeps the two-pass kernels."""
+        if self.dt == torch.bfloat16 and f.c % 256 == 0:
+            f.with_gn_partial()
+        return f
 
     @staticmethod
     def _out2(d: Dual):
@@ -431,7 +443,7 @@ class AutoencoderEngine:
 
     def _res(self, d, x: Dual) -> Dual:
         n, h, w = x.f.n, x.f.h, x.f.w
-        h1 = self._new(n, h, w, d["cout"], torch.float32)   # bf16 here costs the encoder its 1e-2 bound (measured 1.03e-2)
+        h1 = self._gp(self._new(n, h, w, d["cout"], torch.float32))   # bf16 here costs the encoder its 1e-2 bound (measured 1.03e-2)
         ops.conv([ConvIn(self._gn(x.f, d["gn1"], True), 3, 1, 1)], d["conv1"][0], h1, bias=d["conv1"][1])
         hn2 = self._gn(h1, d["gn2"], True)
         out = self._new_dual(n, h, w, d["cout"])
@@ -468,7 +480,7 @@ class AutoencoderEngine:
         ops.linear(o, d["proj"][0], out.f, bias=d["proj"][1], residual=x.f, out2=self._out2(out))
         return out
 
-    def _conv3(self, x: Act, wb, cout, stride=1, pad=1, upsample=False) -> Dual:
+    def _conv3(self, x: Act, wb, cout, stride=1, pad=1, upsample=False, w_phases=None) -> Dual:
         """3x3 conv of a compute-dtype operand into a fresh residual-stream tensor."""
         if stride == 2:
             ho, wo = x.h // 2, x.w // 2
@@ -477,7 +489,11 @@ class AutoencoderEngine:
         else:
             ho, wo = x.h, x.w
         out = self._new_dual(x.n, ho, wo, cout)
-        if upsample and self.dt == torch.bfloat16:
+        pow2 = lambda v: v & (v - 1) == 0  # noqa: E731
+        if upsample and w_phases is not None and x.h * x.w >= 32 and pow2(x.h) and pow2(x.w):
+            ops.conv([ConvIn(x, 3, 1, 1, upsample=1)], w_phases, out.f, bias=wb[1], out2=self._out2(out),
+                     upsample_phases=True)
+        elif upsample and self.dt == torch.bfloat16:
             up = self._new(x.n, ho, wo, x.c)
             ops.upsample_nearest2x(x, up)
             ops.conv([ConvIn(up, 3, 1, 1)], wb[0], out.f, bias=wb[1], out2=self._out2(out))
@@ -556,7 +572,7 @@ class AutoencoderEngine:
                 if lvl["attn"]:
                     h = self._attn(lvl["attn"][i], h)
             if "resample" in lvl:
-                h = self._conv3(h.h, lvl["resample"], h.f.c, upsample=True)
+                h = self._conv3(h.h, lvl["resample"], h.f.c, upsample=True, w_phases=lvl.get("resample_phases"))
         hn = self._gn(h.f, D["norm_out"], True)
         co = D["conv_out"][0].shape[0]
         o = self._output(hn, D["conv_out"], co)
