@@ -291,3 +291,34 @@ def test_upsample_phase_weights_reproduce_nearest2x_conv3x3():
             k = wp[:, py, px].permute(0, 3, 1, 2)
             out[:, :, py::2, px::2] = F.conv2d(xp[:, :, py:py + 7, px:px + 8], k)
     assert float((out - ref).abs().max()) < 1e-5
+
+
+def test_collapsed_cross_attention_weights_reproduce_the_reference_layer():
+    """packing.collapse_cross_attention: with G_h = scale log2(e) Wk_h^T Wq_h and H_h = Wv_h^T Wo_h^T the layer
+    to_q -> softmax(q k^T scale) v -> to_out (CrossAttention.forward, ldm/modules/attention.py:170-193) is
+    softmax_2(x (ctx G)^T) (ctx H) + b.  Checked in fp64 against the plain q / k / v evaluation, with the row order
+    (head, key) / (head, channel) the per-image TMA gather of ealdm_conv(wi_*) assumes."""
+    from ealdm_b200.packing import collapse_cross_attention
+    g = torch.Generator().manual_seed(11)
+    n, tok, T, heads, d, E = 2, 24, 4, 8, 32, 96
+    C = heads * d
+    dd = torch.float64
+    x = torch.randn(n, tok, C, generator=g, dtype=dd)
+    ctx = torch.randn(n, T, E, generator=g, dtype=dd)
+    wq, wo = (torch.randn(C, C, generator=g, dtype=dd) / C ** 0.5 for _ in range(2))
+    wk, wv = (torch.randn(C, E, generator=g, dtype=dd) / E ** 0.5 for _ in range(2))
+    bo = torch.randn(C, generator=g, dtype=dd)
+    scale = d ** -0.5
+    q = (x @ wq.t()).reshape(n, tok, heads, d).transpose(1, 2)
+    k = (ctx @ wk.t()).reshape(n, T, heads, d).transpose(1, 2)
+    v = (ctx @ wv.t()).reshape(n, T, heads, d).transpose(1, 2)
+    p = torch.softmax(q @ k.transpose(-1, -2) * scale, dim=-1)
+    want = (p @ v).transpose(1, 2).reshape(n, tok, C) @ wo.t() + bo
+    G, H = collapse_cross_attention(wq, wk, wv, wo, heads, scale, torch.float32)
+    G, H = G.to(dd), H.to(dd)                                         # rows (head, channel)
+    U = (ctx @ G.t()).reshape(n, T, heads, C).permute(0, 2, 1, 3)     # [n, head, key, c]: B rows (head, key) of image n
+    Z = (ctx @ H.t()).reshape(n, T, heads, C).permute(0, 2, 1, 3)
+    logits2 = torch.einsum("ntc,nhjc->nthj", x, U)                    # base-2 logits (log2 e folded into G)
+    p2 = torch.softmax(logits2 * 0.6931471805599453, dim=-1)
+    got = torch.einsum("nthj,nhjc->ntc", p2, Z) + bo
+    assert float((got - want).norm() / want.norm()) < 1e-6            # G / H were rounded to fp32
