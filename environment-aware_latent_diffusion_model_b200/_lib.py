@@ -54,14 +54,14 @@ class ConvArgs(C.Structure):
                 ("weight_adjoint", C.c_int32), ("upsample_phases", C.c_int32), ("ld_weight", C.c_int64),
                 ("ln_partial_out", C.c_void_p), ("ln_partial_in", C.c_void_p), ("ln_parts_in", C.c_int64),
                 ("ln_c1", C.c_void_p), ("ln_channels", C.c_int64), ("ln_eps", C.c_float), ("wi_tokens", C.c_int32),
-                ("wi_heads", C.c_int32), ("reserved4", C.c_int32), ("wi_ld", C.c_int64), ("wi_head_stride", C.c_int64)]
+                ("wi_heads", C.c_int32), ("gn_unit", C.c_int32), ("wi_ld", C.c_int64), ("wi_head_stride", C.c_int64)]
 
 
 class GroupNormArgs(C.Structure):
     _fields_ = [("dtype", C.c_int32), ("act", C.c_int32), ("x", C.c_void_p), ("n", C.c_int64),
                 ("hw", C.c_int64), ("c", C.c_int64), ("ld_x", C.c_int64), ("groups", C.c_int32),
                 ("eps", C.c_float), ("gamma", C.c_void_p), ("beta", C.c_void_p), ("y", C.c_void_p),
-                ("ld_y", C.c_int64), ("workspace", C.c_void_p), ("x_f32", C.c_int32), ("reserved", C.c_int32),
+                ("ld_y", C.c_int64), ("workspace", C.c_void_p), ("x_f32", C.c_int32), ("partial_unit", C.c_int32),
                 ("stats_out", C.c_void_p), ("partial", C.c_void_p), ("partial_ld", C.c_int64)]
 
 

@@ -427,10 +427,12 @@ class AutoencoderEngine:
     def _gp(self, f: Act) -> Act:
         """bf16 mode: the tcgen05 epilogue that writes this residual-stream tensor also writes its GroupNorm partial
         statistics (per 32-pixel chunk and 8-channel octet), so the GroupNorm reading it is one streaming pass instead
-        of a statistics pass + an apply pass (as in unet.UNetEngine).  Octets resolve groups of >= 8 channels: 256 / 512
-        channel tensors; the 128-channel level (4 channels per group) keeps the two-pass kernels."""
+        of a statistics pass + an apply pass (as in unet.UNetEngine).  Octets resolve groups of >= 8 channels (256 / 512
+        channel tensors); the 128-channel level (4 channels per group) gets one entry per channel quad."""
         if self.dt == torch.bfloat16 and f.c % 256 == 0:
             f.with_gn_partial()
+        elif self.dt == torch.bfloat16 and f.c % 128 == 0:
+            f.with_gn_partial(unit=4)        # 4 channels per group: one partial entry per channel quad
         return f
 
     @staticmethod

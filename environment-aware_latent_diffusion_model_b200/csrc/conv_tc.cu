@@ -80,7 +80,8 @@ struct Params {
   int has_out2;
   // GroupNorm partial statistics of the output (optional)
   float2* gn_partial;
-  int gn_ld;       // octets per (image, chunk) row
+  int gn_ld;       // entries (octets, or quads with gn_quads) per (image, chunk) row
+  int gn_quads;    // partial entries are per 4 channels instead of 8 (GroupNorm groups of 4 channels)
   int gn_chunks;   // 32-pixel chunks per image
   // adjoint mode: B is read MN-major from the forward-packed matrix [K rows = src channels, taps * N columns]
   int b_mn;
@@ -172,6 +173,51 @@ __device__ __forceinline__ void gn_partial_unit(const Params& p, const float (&r
     float* dst = reinterpret_cast<float*>(p.gn_partial + (static_cast<long long>(n) * p.gn_chunks + chunk) * p.gn_ld +
                                           (col0 >> 3) + (vi >> 1));
     dst[vi & 1] = v8[0];
+  }
+}
+
+// the same per channel QUAD (GroupNorm groups of 4 channels): 16 values per thread, 15 exchange shuffles + 1
+__device__ __forceinline__ void gn_partial_unit_quads(const Params& p, const float (&r)[32], int lane, bool valid, int n,
+                                                      int h, int w, int col0, int chunk0 = 0) {
+  float v16[16];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { a += r[4 * q + j]; b = fmaf(r[4 * q + j], r[4 * q + j], b); }
+    v16[2 * q] = valid ? a : 0.f;
+    v16[2 * q + 1] = valid ? b : 0.f;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {   // lanes 16..31 keep values 8..15
+    const float send = (lane & 16) ? v16[i] : v16[i + 8];
+    const float keep = (lane & 16) ? v16[i + 8] : v16[i];
+    v16[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float send = (lane & 8) ? v16[i] : v16[i + 4];
+    const float keep = (lane & 8) ? v16[i + 4] : v16[i];
+    v16[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float send = (lane & 4) ? v16[i] : v16[i + 2];
+    const float keep = (lane & 4) ? v16[i + 2] : v16[i];
+    v16[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  {
+    const float send = (lane & 2) ? v16[0] : v16[1];
+    const float keep = (lane & 2) ? v16[1] : v16[0];
+    v16[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  v16[0] += __shfl_xor_sync(0xffffffffu, v16[0], 1);
+  if ((lane & 1) == 0 && n < p.Nimg && col0 < p.N) {
+    const int vi = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);  // 0..15
+    const int chunk = chunk0 + ((h * p.Wout + w) >> 5);
+    float* dst = reinterpret_cast<float*>(p.gn_partial + (static_cast<long long>(n) * p.gn_chunks + chunk) * p.gn_ld +
+                                          (col0 >> 2) + (vi >> 1));
+    dst[vi & 1] = v16[0];
   }
 }
 
@@ -632,8 +678,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                       r[j] = p.act == EALDM_ACT_RELU ? fmaxf(f, 0.f) : silu_f(f);
                     }
                   }
-                  if (p.gn_partial != nullptr)
-                    gn_partial_unit(p, r, lane, (n - sn0) + my_dn < p.Nimg, n, h, w, nt * BN + ku * 32);
+                  if (p.gn_partial != nullptr) {
+                    if (p.gn_quads) gn_partial_unit_quads(p, r, lane, (n - sn0) + my_dn < p.Nimg, n, h, w, nt * BN + ku * 32);
+                    else gn_partial_unit(p, r, lane, (n - sn0) + my_dn < p.Nimg, n, h, w, nt * BN + ku * 32);
+                  }
                   if (p.out_f32) {
                     sts_row_f32(ebuf + c * EBUF_BYTES, lane, r);
                   } else {
@@ -786,9 +834,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
               r[j] += p.act == EALDM_ACT_RELU ? fmaxf(f, 0.f) : silu_f(f);
             }
           }
-          if (p.gn_partial != nullptr)
-            gn_partial_unit(p, r, lane, (n - sn0) + my_dn < p.Nimg, n, h, w, nt * BN + ku * 32,
-                            uph * p.gn_phase_chunks);
+          if (p.gn_partial != nullptr) {
+            if (p.gn_quads)
+              gn_partial_unit_quads(p, r, lane, (n - sn0) + my_dn < p.Nimg, n, h, w, nt * BN + ku * 32,
+                                    uph * p.gn_phase_chunks);
+            else
+              gn_partial_unit(p, r, lane, (n - sn0) + my_dn < p.Nimg, n, h, w, nt * BN + ku * 32,
+                              uph * p.gn_phase_chunks);
+          }
           if (p.out_f32) sts_row_f32(eb, lane, r);
           else sts_row_bf16(eb, lane, r);
           if (p.has_out2) sts_row_bf16(o2buf, lane, r);
@@ -1017,6 +1070,7 @@ bool supported(const ealdm_conv_args* a) {
   }
   if (a->gn_partial) {
     const long long hw = a->h_out * a->w_out;
+    if (a->gn_unit != 0 && a->gn_unit != 8 && a->gn_unit != 4) return false;
     if (a->act == EALDM_ACT_GEGLU || hw % 32 != 0 || (a->w_out & (a->w_out - 1)) != 0 ||
         (a->h_out & (a->h_out - 1)) != 0 || a->n_out % 32 != 0)
       return false;
@@ -1243,6 +1297,7 @@ int launch(const ealdm_conv_args* a, cudaStream_t st) {
   p.has_out2 = a->out2 != nullptr;
   p.gn_partial = reinterpret_cast<float2*>(a->gn_partial);
   p.gn_ld = static_cast<int>(a->gn_ld);
+  p.gn_quads = a->gn_unit == 4 ? 1 : 0;
   p.gn_chunks = static_cast<int>(a->h_out * a->w_out / 32);
   p.gn_phase_chunks = static_cast<int>(h_grid * w_grid / 32);
   p.ln_out = reinterpret_cast<float2*>(a->ln_partial_out);

@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(NT)
 gn_apply_partial_kernel(const TX* __restrict__ x, long long ld_x, T* __restrict__ y, long long ld_y, int hw, int c,
                         int groups, int pix_per_cta, const float2* __restrict__ partial, long long pld, float eps,
                         const float* __restrict__ gamma, const float* __restrict__ beta, int act,
-                        float* __restrict__ stats_out) {
+                        float* __restrict__ stats_out, int unit_shift) {
   constexpr bool SILU_FAST = sizeof(T) == 2;
   __shared__ float s_mean[MAX_GROUPS], s_rstd[MAX_GROUPS];
   pdl_wait();      // launched with programmatic serialization (common.cuh): x / partial belong to the predecessor
@@ -193,7 +193,7 @@ gn_apply_partial_kernel(const TX* __restrict__ x, long long ld_x, T* __restrict_
   const int vpp = c >> 2;
   {
     const int chunks = hw >> 5;
-    const int opg = cpg >> 3;            // octets per group
+    const int opg = cpg >> unit_shift;   // partial entries (octets / quads) per group
     const int terms = chunks * opg;
     const float2* pn = partial + static_cast<long long>(n) * chunks * pld;
     for (int g0 = 0; g0 < groups; g0 += NT / 8) {
@@ -336,7 +336,7 @@ static int group_norm_t(const ealdm_group_norm_args* a, cudaStream_t st) {
     EALDM_CUDA(launch_pdl(gn_apply_partial_kernel<TX, T>, grid, dim3(NT), 0, st, reinterpret_cast<const TX*>(a->x),
                           a->ld_x, reinterpret_cast<T*>(a->y), a->ld_y, static_cast<int>(a->hw), static_cast<int>(a->c),
                           a->groups, ppc, reinterpret_cast<const float2*>(a->partial), a->partial_ld, a->eps, a->gamma,
-                          a->beta, a->act, a->stats_out));
+                          a->beta, a->act, a->stats_out, a->partial_unit == 4 ? 2 : 3));
     EALDM_LAUNCH_CHECK();
     return 0;
   }
@@ -762,8 +762,13 @@ extern "C" int ealdm_group_norm(const ealdm_group_norm_args* a, ealdm_stream_t s
   EALDM_REQUIRE((a->c / a->groups) % 4 == 0 && a->ld_x % 4 == 0 && a->ld_y % 4 == 0,
                 "group_norm: channels per group, ld_x and ld_y must be multiples of 4");
   EALDM_REQUIRE(a->n > 0 && a->n <= 65535 && a->hw > 0, "group_norm: bad n/hw");
-  EALDM_REQUIRE(a->partial == nullptr || (a->hw % 32 == 0 && (a->c / a->groups) % 8 == 0 && a->partial_ld >= a->c / 8),
-                "group_norm: partial statistics need hw %% 32 == 0 and channels per group %% 8 == 0");
+  {
+    const int unit = a->partial_unit == 4 ? 4 : 8;
+    EALDM_REQUIRE(a->partial == nullptr || ((a->partial_unit == 0 || a->partial_unit == 4 || a->partial_unit == 8) &&
+                                            a->hw % 32 == 0 && (a->c / a->groups) % unit == 0 &&
+                                            a->partial_ld >= a->c / unit),
+                  "group_norm: partial statistics need hw %% 32 == 0 and channels per group %% partial_unit == 0");
+  }
   EALDM_REQUIRE(a->act == EALDM_ACT_NONE || a->act == EALDM_ACT_SILU, "group_norm: bad act");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (a->dtype == EALDM_F32) return norm::group_norm_t<float, float>(a, st);

@@ -37,7 +37,7 @@ class Act:
     [n*h*w/32, ld/8, 2] fp32 = {sum, sum of squares} per (32-pixel chunk, 8-channel octet): a tcgen05 convolution
     that writes this activation fills its column window of `gp`, and a GroupNorm that reads the activation then
     skips its statistics pass."""
-    __slots__ = ("buf", "n", "h", "w", "c", "c0", "gp", "ln")
+    __slots__ = ("buf", "n", "h", "w", "c", "c0", "gp", "ln", "gunit")
 
     def __init__(self, buf: torch.Tensor, n: int, h: int, w: int, c: Optional[int] = None, c0: int = 0,
                  gp: Optional[torch.Tensor] = None):
@@ -48,6 +48,7 @@ class Act:
         self.c = buf.shape[1] - c0 if c is None else c
         assert self.c0 + self.c <= buf.shape[1]
         self.gp = gp
+        self.gunit = 8      # channels per entry of `gp`: octets, or quads for GroupNorm groups of 4 channels
         self.ln = None      # [rows, parts, 2] row {sum, sum of squares} partials written by the producing GEMM (ln_stats)
 
     @staticmethod
@@ -71,26 +72,31 @@ class Act:
         return self.buf.dtype
 
     def cols(self, c0: int, c: int) -> "Act":
-        return Act(self.buf, self.n, self.h, self.w, c, self.c0 + c0, self.gp)
+        a = Act(self.buf, self.n, self.h, self.w, c, self.c0 + c0, self.gp)
+        a.gunit = self.gunit
+        return a
 
     def reshape(self, n, h, w) -> "Act":
         assert n * h * w == self.rows
         return Act(self.buf, n, h, w, self.c, self.c0)
 
-    def with_gn_partial(self) -> "Act":
-        """Attach a (not yet filled) partial-statistics buffer; None if the shape does not qualify."""
+    def with_gn_partial(self, unit: int = 8) -> "Act":
+        """Attach a (not yet filled) partial-statistics buffer; None if the shape does not qualify.  unit = 4: one
+        entry per 4 channels (GroupNorm groups of 4 channels) instead of per octet."""
+        assert unit in (4, 8)
         if _NO_GN_PARTIAL:
             return self
         hw = self.h * self.w
         pow2 = lambda v: v & (v - 1) == 0  # noqa: E731
         if (hw % 32 == 0 and pow2(self.w) and pow2(self.h) and self.ld % 32 == 0 and self.c0 % 32 == 0
                 and self.c % 32 == 0 and (self.w >= 32 or self.h % (32 // self.w) == 0)):
-            self.gp = torch.empty((self.rows // 32, self.ld // 8, 2), dtype=torch.float32, device=self.buf.device)
+            self.gp = torch.empty((self.rows // 32, self.ld // unit, 2), dtype=torch.float32, device=self.buf.device)
+            self.gunit = unit
         return self
 
     @property
     def gp_ptr(self) -> int:
-        return self.gp.data_ptr() + (self.c0 // 8) * 8
+        return self.gp.data_ptr() + (self.c0 // self.gunit) * 8
 
     def view2d(self) -> torch.Tensor:
         return self.buf[:, self.c0:self.c0 + self.c]
@@ -184,7 +190,7 @@ def conv(srcs: Sequence[ConvIn], weight: torch.Tensor, out: Act, *, bias: Option
         a.out2, a.ld_out2 = out2.ptr, out2.ld
     if out.gp is not None:     # the epilogue also produces the GroupNorm partial statistics of `out`
         assert x0.dtype == torch.bfloat16 and act != L.ACT_GEGLU
-        a.gn_partial, a.gn_ld = out.gp_ptr, out.gp.shape[1]
+        a.gn_partial, a.gn_ld, a.gn_unit = out.gp_ptr, out.gp.shape[1], out.gunit
         if impl == L.IMPL_AUTO:
             a.impl = L.IMPL_TCGEN05   # only the tcgen05 epilogue writes them: fail loudly rather than skip silently
     if ln is not None:        # consumer of a folded LayerNorm: ln = (partials [rows, parts, 2], c1 [n_out], channels, eps)
@@ -273,8 +279,8 @@ def group_norm(x: Act, gamma: torch.Tensor, beta: torch.Tensor, eps: float, out:
     if stats_out is not None:
         assert stats_out.dtype == torch.float32 and stats_out.is_contiguous() and stats_out.numel() == x.n * groups * 2
         a.stats_out = stats_out.data_ptr()
-    if x.gp is not None and (x.c // groups) % 8 == 0:
-        a.partial, a.partial_ld = x.gp_ptr, x.gp.shape[1]
+    if x.gp is not None and (x.c // groups) % x.gunit == 0:
+        a.partial, a.partial_ld, a.partial_unit = x.gp_ptr, x.gp.shape[1], x.gunit
     L.check(lib.ealdm_group_norm(C.byref(a), _stream()))
     return out
 
@@ -282,7 +288,7 @@ def group_norm(x: Act, gamma: torch.Tensor, beta: torch.Tensor, eps: float, out:
 def gn_partial(x: Act) -> Act:
     """Fill x.gp with a stand-alone kernel (for activations that did not come out of the tcgen05 epilogue)."""
     lib = L.load()
-    assert x.gp is not None
+    assert x.gp is not None and x.gunit == 8, "the stand-alone producer writes octet partials"
     L.check(lib.ealdm_gn_partial(x.ptr, x.ld, _dt(x.dtype), x.n, x.h * x.w, x.c, x.gp_ptr, x.gp.shape[1], _stream()))
     return x
 

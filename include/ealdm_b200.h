@@ -176,7 +176,9 @@ typedef struct {
      The 4-D TMA box (c, j, h, n) gathers the (h, j) rows of image n straight from that projection. */
   int32_t wi_tokens;
   int32_t wi_heads;
-  int32_t reserved4;
+  int32_t gn_unit; /* channels per gn_partial entry: 0 or 8 = octets (above), 4 = quads (GroupNorm groups of 4 channels:
+                      the 128-channel level of the autoencoder); gn_partial then points at the entry of column 0 and
+                      gn_ld counts quads */
   int64_t wi_ld;
   int64_t wi_head_stride;
 } ealdm_conv_args;
@@ -237,7 +239,7 @@ typedef struct {
   int64_t ld_y;
   void* workspace;
   int32_t x_f32; /* 1: x is float regardless of dtype (fp32 residual stream -> bf16 GEMM operand) */
-  int32_t reserved;
+  int32_t partial_unit; /* channels per `partial` entry: 0 or 8 = octets, 4 = quads (ealdm_conv_args::gn_unit) */
   float* stats_out; /* optional [n, groups, 2] = (mean, rstd) per (image, group), saved for the backward */
   const float* partial; /* optional: partial statistics of x written by the producing ealdm_conv (gn_partial) or by
                            ealdm_gn_partial; the kernel then only streams x once (no reduction pass) */

@@ -513,6 +513,33 @@ def test_conv_epilogue_groupnorm_partials(n, c, h, w, co, silu):
         assert rel_l2(stats[..., 0], xr.reshape(n, 32, -1).mean(-1)) < 1e-4
 
 
+@pytest.mark.parametrize("n,c,h,w,co,res", [(2, 128, 32, 32, 128, True), (3, 64, 16, 64, 128, False),
+                                            (2, 128, 64, 64, 384, True)])
+def test_conv_epilogue_groupnorm_partials_per_channel_quad(n, c, h, w, co, res):
+    """gn_unit = 4: one {sum, sum of squares} entry per channel QUAD, for GroupNorm groups of 4 channels (the
+    128-channel level of the autoencoder, model.py:116-141 Normalize = GroupNorm(32, c)): the GroupNorm fed by the
+    quads equals GroupNorm of the stored fp32 output, with and without a residual in the producing epilogue."""
+    dtype = torch.bfloat16
+    x = torch.randn(n, c, h, w, generator=g(71)).to(DEV)
+    wt = (torch.randn(co, c, 3, 3, generator=g(72)) / math.sqrt(9 * c)).to(DEV)
+    b = torch.randn(co, generator=g(73)).to(DEV)
+    out = Act.empty(n, h, w, co, torch.float32, DEV).with_gn_partial(unit=4)
+    assert out.gp is not None and out.gp.shape[1] == co // 4
+    r = Act(torch.randn(n * h * w, co, generator=g(74)).to(DEV), n, h, w) if res else None
+    ops.conv([ConvIn(to_act(x, dtype), 3, 1, 1)], pack_w(wt, dtype), out, bias=b, residual=r)
+    full = from_act(out)
+    ref_p = full.reshape(n, co // 4, 4, h * w // 32, 32)
+    ref_sum = ref_p.sum(dim=(2, 4)).permute(0, 2, 1).reshape(-1, co // 4)
+    ref_sq = (ref_p ** 2).sum(dim=(2, 4)).permute(0, 2, 1).reshape(-1, co // 4)
+    assert rel_l2(out.gp[..., 0], ref_sum) < 1e-5 and rel_l2(out.gp[..., 1], ref_sq) < 1e-5
+    gamma = (1 + 0.2 * torch.randn(co, generator=g(75))).to(DEV)
+    beta = (0.2 * torch.randn(co, generator=g(76))).to(DEV)
+    y = Act.empty(n, h, w, co, dtype, DEV)
+    ops.group_norm(out, gamma, beta, 1e-6, y, silu=True)
+    ref = F.silu(F.group_norm(full, 32, gamma, beta, 1e-6))
+    assert rel_l2(from_act(y), ref) < 6e-3
+
+
 # ---- schedules of the tcgen05 conv (ealdm_tc_set_option): every setting must give the same numbers ----------------
 class _tc_option:
     """Sets one schedule switch and forces the 256-column N tile (small problems would pick 128 by wave count and
