@@ -54,7 +54,8 @@ class ConvArgs(C.Structure):
                 ("weight_adjoint", C.c_int32), ("upsample_phases", C.c_int32), ("ld_weight", C.c_int64),
                 ("ln_partial_out", C.c_void_p), ("ln_partial_in", C.c_void_p), ("ln_parts_in", C.c_int64),
                 ("ln_c1", C.c_void_p), ("ln_channels", C.c_int64), ("ln_eps", C.c_float), ("wi_tokens", C.c_int32),
-                ("wi_heads", C.c_int32), ("gn_unit", C.c_int32), ("wi_ld", C.c_int64), ("wi_head_stride", C.c_int64)]
+                ("wi_heads", C.c_int32), ("gn_unit", C.c_int32), ("wi_ld", C.c_int64), ("wi_head_stride", C.c_int64),
+                ("ln_gamma", C.c_void_p), ("ln_beta", C.c_void_p)]
 
 
 class GroupNormArgs(C.Structure):

@@ -106,6 +106,16 @@ struct Params {
   //   out = rstd * acc - rstd * mu * c1[col] + bias[col]  ==  LayerNorm(x) W^T + bias
   // per-image B operand (ealdm_conv_args::wi_*): tmB is a 4-D (c, token, head, image) map, a tile lies in one image
   int b_img;
+  // LayerNorm APPLIED by the producing epilogue (ealdm_conv_args::ln_gamma; N == BN == 256, so a CTA holds whole rows):
+  // pass 1 writes the fp32 result as usual, keeps per-row {sum, sum of squares} and stores the result back over its
+  // TMEM accumulator; the two warps that share a row exchange their sums; pass 2 re-reads TMEM and writes
+  // LayerNorm(result) * gamma + beta as bf16 rows straight to ln_y (64 contiguous bytes per thread and unit)
+  const float* ln_gamma;
+  const float* ln_beta;
+  bf16* ln_y;
+  long long ln_y_ld;
+  float ln_apply_eps;
+  int sub_w, sub_h;   // the 32 rows of an epilogue unit as a (sub_w, sub_h, 32 / (sub_w sub_h)) pixel box
   float2* ln_out;
   int ln_out_parts;
   const float2* ln_in;
@@ -524,6 +534,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       ptx::tma_load_4d(ebuf + b * EBUF_BYTES, &tmRes, &rbar[b], nt * OUT_PER_TILE + ku * 32, w, h, n);
     };
 
+    // LayerNorm applied here (Params::ln_gamma): gamma | beta live in epilogue warp 4's shadow buffer, the row-sum
+    // exchange of a warp pair in the shadow buffer of its part-0 warp (no shadow output in this mode)
+    float* const lng_s = reinterpret_cast<float*>(smem + C::EPI_OFF + 4 * EPI_WARP_BYTES + 2 * EBUF_BYTES);
+    float2* const lnx_s = reinterpret_cast<float2*>(smem + C::EPI_OFF + (ew & 3) * EPI_WARP_BYTES + 2 * EBUF_BYTES);
+    if constexpr (BN == 256 && !GEGLU) {
+      if (p.ln_gamma != nullptr) {
+        lng_s[etid] = __ldg(p.ln_gamma + etid);          // 256 epilogue threads, 256 channels
+        lng_s[256 + etid] = __ldg(p.ln_beta + etid);     // (visible after the first tile's named barrier)
+      }
+    }
+    uint32_t tcount = 0;
     uint32_t it = 0;  // units processed by this warp: buffer = it & 1, mbarrier parity = (it >> 1) & 1
     if (!GEGLU && p.has_res && lane == 0 && part < UNITS && tile_first < total_tiles)
       issue_res(tile_first, part, 0);
@@ -573,6 +594,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       ptx::tc_fence_after();
 
       bool wide_done = false;
+      float lna_s = 0.f, lna_ss = 0.f;   // LayerNorm applied here: this thread's row sums over the units of its warp
       if constexpr (BN == 256) {
         if (p.wide) {
           wide_done = true;
@@ -810,6 +832,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 p.ln_out[static_cast<long long>(w + lane) * p.ln_out_parts + nt * (BN / 32) + ku] =
                     make_float2((a4[0] + a4[1]) + (a4[2] + a4[3]), (b4[0] + b4[1]) + (b4[2] + b4[3]));
             }
+            if constexpr (BN == 256 && !GEGLU) {
+              if (p.ln_gamma != nullptr) {   // LayerNorm applied here, pass 1: row sums, result back over the accumulator
+                float a4[4] = {0.f, 0.f, 0.f, 0.f}, b4[4] = {0.f, 0.f, 0.f, 0.f};
+                uint32_t u[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  a4[j & 3] += r[j];
+                  b4[j & 3] = fmaf(r[j], r[j], b4[j & 3]);
+                  u[j] = __float_as_uint(r[j]);
+                }
+                lna_s += (a4[0] + a4[1]) + (a4[2] + a4[3]);
+                lna_ss += (b4[0] + b4[1]) + (b4[2] + b4[3]);
+                ptx::tmem_st_32x32(taddr0 + ku * 32, u);
+              }
+            }
           } else if (BN <= 128 && p.act == EALDM_ACT_SOFTMAX4) {
             // collapsed cross-attention: the 32 columns are (head, key) base-2 logits; softmax over the 4 keys of a head
             ptx::tmem_ld_wait();
@@ -861,6 +898,52 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         }
         ++it;
       }
+      if constexpr (BN == 256 && !GEGLU) {
+        if (p.ln_gamma != nullptr) {
+          // ---- LayerNorm applied here, pass 2 ----
+          ptx::tmem_st_wait();
+          float2* const xs = lnx_s + (tcount & 1u) * 64;       // [tile parity][part][lane]
+          xs[part * 32 + lane] = make_float2(lna_s, lna_ss);
+          ptx::named_bar_sync(2 + (ew & 3), 64);               // the two warps that share these 32 rows
+          const float2 o = xs[(part ^ 1) * 32 + lane];
+          const float s_all = part == 0 ? lna_s + o.x : o.x + lna_s;      // part 0 + part 1, whichever warp adds
+          const float ss_all = part == 0 ? lna_ss + o.y : o.y + lna_ss;
+          const float mu = s_all * (1.0f / 256.0f);
+          const float var = fmaxf(ss_all * (1.0f / 256.0f) - mu * mu, 0.f);
+          const float rstd = rsqrtf(var + p.ln_apply_eps);
+          const float nmu = -mu * rstd;
+          const int lw = lane % p.sub_w, lh = (lane / p.sub_w) % p.sub_h, li = lane / (p.sub_w * p.sub_h);
+          const bool rvalid = n + li < p.Nimg && h + lh < p.Hout && w + lw < p.Wout;
+          bf16* const yrow = p.ln_y + ((static_cast<long long>(n + li) * p.Hout + (h + lh)) * p.Wout + (w + lw)) * p.ln_y_ld;
+          uint32_t vv[2][32];
+          ptx::tmem_ld_32x32(taddr0 + part * 32, vv[0]);
+#pragma unroll
+          for (int ui = 0; ui < UNITS / 2; ++ui) {
+            const int ku = part + 2 * ui;
+            ptx::tmem_ld_wait();
+            if (ui + 1 < UNITS / 2) ptx::tmem_ld_32x32(taddr0 + (ku + 2) * 32, vv[(ui + 1) & 1]);   // flies under the math
+            const uint32_t(&v)[32] = vv[ui & 1];
+            uint4 q[4];
+            uint32_t* qw = reinterpret_cast<uint32_t*>(q);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 g4 = *reinterpret_cast<const float4*>(lng_s + ku * 32 + 4 * j);
+              const float4 b4 = *reinterpret_cast<const float4*>(lng_s + 256 + ku * 32 + 4 * j);
+              const float y0 = fmaf(fmaf(__uint_as_float(v[4 * j]), rstd, nmu), g4.x, b4.x);
+              const float y1 = fmaf(fmaf(__uint_as_float(v[4 * j + 1]), rstd, nmu), g4.y, b4.y);
+              const float y2 = fmaf(fmaf(__uint_as_float(v[4 * j + 2]), rstd, nmu), g4.z, b4.z);
+              const float y3 = fmaf(fmaf(__uint_as_float(v[4 * j + 3]), rstd, nmu), g4.w, b4.w);
+              qw[2 * j] = pack2_bf16(y0, y1);
+              qw[2 * j + 1] = pack2_bf16(y2, y3);
+            }
+            if (rvalid) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(yrow + ku * 32 + 8 * j) = q[j];
+            }
+          }
+        }
+      }
+      ++tcount;
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -1068,6 +1151,12 @@ bool supported(const ealdm_conv_args* a) {
                              (a->act != EALDM_ACT_NONE && a->act != EALDM_ACT_GEGLU)))
       return false;
   }
+  if (a->ln_gamma) {
+    // LayerNorm applied by the epilogue: whole rows in one 256-column tile, fp32 result, no shadow copy, narrow epilogue
+    if (a->n_out != 256 || !a->ln_beta || !a->out2 || !a->out_f32 || a->act != EALDM_ACT_NONE || a->upsample_phases ||
+        a->ln_partial_in || a->ln_partial_out || a->gn_partial || (a->wi_tokens && !a->weight_adjoint))
+      return false;
+  }
   if (a->gn_partial) {
     const long long hw = a->h_out * a->w_out;
     if (a->gn_unit != 0 && a->gn_unit != 8 && a->gn_unit != 4) return false;
@@ -1130,6 +1219,7 @@ static int encode_unit_map(PFN_cuTensorMapEncodeTiled_v12000 encode, CUtensorMap
 static int choose_bn(const ealdm_conv_args* a, long long m_work) {
   init_options();
   const bool geglu = a->act == EALDM_ACT_GEGLU;
+  if (a->ln_gamma) return 256;   // LayerNorm in the epilogue needs the whole row in one tile
   if (a->n_out <= 32 && !geglu && !a->weight_adjoint) return 32;
   if (a->n_out <= 128) return 128;
   const long long t256 = m_work * ceil_div(a->n_out, 256);
@@ -1257,7 +1347,7 @@ int launch(const ealdm_conv_args* a, cudaStream_t st) {
   const long long out_cols = geglu ? a->n_out / 2 : a->n_out;
   // (measured: the GEGLU pass gains 3 % at K = 256 and loses 4 % at K >= 512, where the stores of the narrow units
   // overlap the longer main loop better)
-  const bool wide = g_opt[EALDM_TC_OPT_WIDE] != 0 && BN == 256 && !phased && !a->ln_partial_out &&
+  const bool wide = g_opt[EALDM_TC_OPT_WIDE] != 0 && BN == 256 && !phased && !a->ln_partial_out && !a->ln_gamma &&
                     (geglu ? a->k_total <= 256 : (!a->residual && !a->out2));
   PhaseMaps pm;
   memset(&pm, 0, sizeof(pm));
@@ -1273,7 +1363,7 @@ int launch(const ealdm_conv_args* a, cudaStream_t st) {
   }
   tm[4] = tm[3];
   tm[5] = tm[3];
-  if (a->out2) {
+  if (a->out2 && !a->ln_gamma) {
     if (phased) {
       if (int e = encode_phase_map(encode, &tm[4], a->out2, false, out_cols, a->ld_out2, a, sub, 0, 0)) return e;
       for (int ph = 1; ph < 4; ++ph)
@@ -1294,7 +1384,14 @@ int launch(const ealdm_conv_args* a, cudaStream_t st) {
   p.out_f32 = a->out_f32;
   p.has_res = a->residual != nullptr;
   p.res_f32 = a->res_f32;
-  p.has_out2 = a->out2 != nullptr;
+  p.has_out2 = a->out2 != nullptr && !a->ln_gamma;
+  p.ln_gamma = a->ln_gamma;
+  p.ln_beta = a->ln_beta;
+  p.ln_y = a->ln_gamma ? reinterpret_cast<bf16*>(a->out2) : nullptr;
+  p.ln_y_ld = a->ld_out2;
+  p.ln_apply_eps = a->ln_eps;
+  p.sub_w = sub[0];
+  p.sub_h = sub[1];
   p.gn_partial = reinterpret_cast<float2*>(a->gn_partial);
   p.gn_ld = static_cast<int>(a->gn_ld);
   p.gn_quads = a->gn_unit == 4 ? 1 : 0;

@@ -37,7 +37,7 @@ class Act:
     [n*h*w/32, ld/8, 2] fp32 = {sum, sum of squares} per (32-pixel chunk, 8-channel octet): a tcgen05 convolution
     that writes this activation fills its column window of `gp`, and a GroupNorm that reads the activation then
     skips its statistics pass."""
-    __slots__ = ("buf", "n", "h", "w", "c", "c0", "gp", "ln", "gunit")
+    __slots__ = ("buf", "n", "h", "w", "c", "c0", "gp", "ln", "gunit", "lny")
 
     def __init__(self, buf: torch.Tensor, n: int, h: int, w: int, c: Optional[int] = None, c0: int = 0,
                  gp: Optional[torch.Tensor] = None):
@@ -49,6 +49,7 @@ class Act:
         assert self.c0 + self.c <= buf.shape[1]
         self.gp = gp
         self.gunit = 8      # channels per entry of `gp`: octets, or quads for GroupNorm groups of 4 channels
+        self.lny = None     # LayerNorm(self) written by the producing GEMM's epilogue (conv(..., ln_apply=...))
         self.ln = None      # [rows, parts, 2] row {sum, sum of squares} partials written by the producing GEMM (ln_stats)
 
     @staticmethod
@@ -114,7 +115,7 @@ def conv(srcs: Sequence[ConvIn], weight: torch.Tensor, out: Act, *, bias: Option
          rowvec: Optional[torch.Tensor] = None, rowvec_col0: int = 0, residual: Optional[Act] = None,
          act: int = L.ACT_NONE, impl: int = L.IMPL_AUTO, out2: Optional[Act] = None, adjoint: bool = False,
          upsample_phases: bool = False, ln_stats: bool = False, ln: Optional[tuple] = None,
-         wimg: Optional[tuple] = None) -> Act:
+         wimg: Optional[tuple] = None, ln_apply: Optional[tuple] = None) -> Act:
     """ealdm_conv: out = epilogue(sum_s im2col(src_s) @ weight[:, seg_s]^T). `weight` is [n_out, k_total].
     adjoint=True: data gradient of a forward layer -- `weight` is that layer's own packed matrix
     [src channels, ksize^2 * out.c] (may be a column window of a wider matrix); nothing is transposed or flipped."""
@@ -188,6 +189,12 @@ def conv(srcs: Sequence[ConvIn], weight: torch.Tensor, out: Act, *, bias: Option
     if out2 is not None:
         assert out2.dtype == x0.dtype and out2.rows == out.rows and out2.c == out.c
         a.out2, a.ld_out2 = out2.ptr, out2.ld
+    if ln_apply is not None:   # the epilogue also writes LayerNorm(out) * gamma + beta (bf16) to out2 instead of a copy
+        gamma, beta, eps = ln_apply
+        assert out2 is not None and a.out_f32 and act == L.ACT_NONE and out.c == 256
+        assert gamma.dtype == torch.float32 and beta.dtype == torch.float32 and gamma.numel() == 256 == beta.numel()
+        a.ln_gamma, a.ln_beta, a.ln_eps = gamma.data_ptr(), beta.data_ptr(), eps
+        a.impl = L.IMPL_TCGEN05
     if out.gp is not None:     # the epilogue also produces the GroupNorm partial statistics of `out`
         assert x0.dtype == torch.bfloat16 and act != L.ACT_GEGLU
         a.gn_partial, a.gn_ld, a.gn_unit = out.gp_ptr, out.gp.shape[1], out.gunit

@@ -64,6 +64,7 @@ class UNetTrainEngine(UNetEngine):
     _fold_ln = False              # ... and the LayerNorm outputs / statistics
     _phased_upsample = False      # the backward differentiates the explicit nearest-2x + 3x3 form
     _collapse_xattn = False       # ... and the q / k / v form of the cross-attention
+    _ln_epilogue = False          # ... and the LayerNorm inputs as separate tensors
 
     def __init__(self, m: UNetModel, dtype: torch.dtype):
         super().__init__(m, dtype)

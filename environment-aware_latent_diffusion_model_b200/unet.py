@@ -365,6 +365,8 @@ class UNetEngine:
     # cross-attention collapsed onto the context (packing.collapse_cross_attention): to_q -> 4-key attention -> to_out
     # become two per-image GEMMs of K = C / N = 32 and K = 32 / N = C; A/B switch, the training engine keeps q / k / v
     _collapse_xattn = not os.environ.get("EALDM_NO_XATTN_COLLAPSE")
+    # LayerNorm applied by the epilogue of the GEMM that produces its input (width 256: a CTA holds whole rows); A/B switch
+    _ln_epilogue = not os.environ.get("EALDM_NO_LN_EPILOGUE")
 
     def __init__(self, m: UNetModel, dtype: torch.dtype):
         L.load()
@@ -617,7 +619,9 @@ class UNetEngine:
             """LayerNorm i of the block followed by the linear layer `key`: folded into that GEMM (which then reads
             the bf16 shadow of the raw stream and the producer's row statistics) or as a LayerNorm pass + GEMM."""
             y = self._new(n, h, w, n_out // 2 if kw.get("act") == L.ACT_GEGLU else n_out)
-            if fold and src.ln is not None:
+            if src.lny is not None:       # the producing GEMM's epilogue already wrote LayerNorm(src)
+                ops.linear(src.lny, w_plain[0], y, bias=w_plain[1], **kw)
+            elif fold and src.ln is not None:
                 wg, c1, c2 = tb[key + "_ln"]
                 ops.linear(src_h, wg, y, bias=c2, ln=(src.ln, c1, C_, 1e-5), **kw)
             else:
@@ -631,15 +635,30 @@ class UNetEngine:
             f = self._new(n, h, w, C_, None if last else f32)
             return f, (self._new(n, h, w, C_) if (fold and not last) else None)
 
+        ln_epi = self._ln_epilogue and not fold and C_ == 256 and self.dt == torch.bfloat16
+
+        def ln_out(dst: Act, tb, i: int) -> dict:
+            """Keyword arguments that make the GEMM producing `dst` also write LayerNorm i of block `tb` of it."""
+            if not ln_epi or tb is None:
+                return {}
+            dst.lny = self._new(n, h, w, C_)
+            return {"out2": dst.lny, "ln_apply": (tb[f"ln{i}"][0], tb[f"ln{i}"][1], 1e-5)}
+
         t, t_h = stream()
-        ops.linear(xn, d["proj_in"].w, t, bias=d["proj_in"].b, out2=t_h, ln_stats=fold)
+        if ln_epi:
+            ops.linear(xn, d["proj_in"].w, t, bias=d["proj_in"].b, **ln_out(t, d["blocks"][0], 1))
+        else:
+            ops.linear(xn, d["proj_in"].w, t, bias=d["proj_in"].b, out2=t_h, ln_stats=fold)
         for bi, tb in enumerate(d["blocks"]):
             qkv = normed(t, t_h, tb, 1, "qkv", (tb["qkv"], None), 3 * C_)
             o = self._new(n, h, w, C_)
             ops.attention(qkv.cols(0, C_), qkv.cols(C_, C_), qkv.cols(2 * C_, C_), o, batch=n, heads=heads,
                           head_dim=dh, n_q=tok, n_kv=tok, scale=dh ** -0.5)
             t1, t1_h = stream()
-            ops.linear(o, tb["o1"].w, t1, bias=tb["o1"].b, residual=t, out2=t1_h, ln_stats=fold)
+            if ln_epi:
+                ops.linear(o, tb["o1"].w, t1, bias=tb["o1"].b, residual=t, **ln_out(t1, tb, 2))
+            else:
+                ops.linear(o, tb["o1"].w, t1, bias=tb["o1"].b, residual=t, out2=t1_h, ln_stats=fold)
             ff_fold = fold and not fused_ff
             t2 = self._new(n, h, w, C_, f32)
             t2_h = self._new(n, h, w, C_) if ff_fold else None
@@ -647,19 +666,24 @@ class UNetEngine:
             if "xc_col0" in tb and xc is not None and not fold and tok % 128 == 0 and heads * n_ctx <= 128:
                 # collapsed cross-attention: logits = LN2(t1) U_n^T (softmax over the 4 keys in the epilogue), then
                 # t2 = P Zt_n + bias + t1; U_n / Zt_n are column windows of the context projection xc_all
-                a2 = self._new(n, h, w, C_)
-                ops.layer_norm(t1, tb["ln2"][0], tb["ln2"][1], 1e-5, a2)
+                a2 = t1.lny
+                if a2 is None:
+                    a2 = self._new(n, h, w, C_)
+                    ops.layer_norm(t1, tb["ln2"][0], tb["ln2"][1], 1e-5, a2)
                 pr = self._new(n, h, w, heads * n_ctx)
                 ops.conv([ConvIn(a2)], xc.buf, pr, act=L.ACT_SOFTMAX4, wimg=(tb["xc_col0"], n_ctx, heads, C_))
                 ops.conv([ConvIn(pr)], xc.buf, t2, bias=tb["o2"].b, residual=t1, adjoint=True,
-                         wimg=(tb["xc_col0"] + heads * C_, n_ctx, heads, C_))
+                         wimg=(tb["xc_col0"] + heads * C_, n_ctx, heads, C_), **ln_out(t2, tb, 3))
             else:
                 q2 = normed(t1, t1_h, tb, 2, "q2", (tb["q2"], None), C_)
                 o2 = self._new(n, h, w, C_)
                 kc = tb["kv_col0"]
                 ops.attention(q2, kv_all.cols(kc, C_), kv_all.cols(kc + C_, C_), o2, batch=n, heads=heads, head_dim=dh,
                               n_q=tok, n_kv=n_ctx, scale=dh ** -0.5)
-                ops.linear(o2, tb["o2"].w, t2, bias=tb["o2"].b, residual=t1, out2=t2_h, ln_stats=ff_fold)
+                if ln_epi:
+                    ops.linear(o2, tb["o2"].w, t2, bias=tb["o2"].b, residual=t1, **ln_out(t2, tb, 3))
+                else:
+                    ops.linear(o2, tb["o2"].w, t2, bias=tb["o2"].b, residual=t1, out2=t2_h, ln_stats=ff_fold)
             last = bi == nb - 1   # the last t feeds proj_out as a GEMM operand -> compute dtype
             t, t_h = stream(last)
             if fused_ff:
@@ -669,7 +693,10 @@ class UNetEngine:
                 ops.ff_geglu_fused(a, tb["ff1"].w, tb["ff1"].b, tb["ff2"].w, tb["ff2"].b, t2, t)
             else:
                 gg = normed(t2, t2_h, tb, 3, "ff1", (tb["ff1"].w, tb["ff1"].b), 8 * C_, act=L.ACT_GEGLU)
-                ops.linear(gg, tb["ff2"].w, t, bias=tb["ff2"].b, residual=t2, out2=t_h, ln_stats=fold and not last)
+                if ln_epi and not last:
+                    ops.linear(gg, tb["ff2"].w, t, bias=tb["ff2"].b, residual=t2, **ln_out(t, d["blocks"][bi + 1], 1))
+                else:
+                    ops.linear(gg, tb["ff2"].w, t, bias=tb["ff2"].b, residual=t2, out2=t_h, ln_stats=fold and not last)
         out = dest if dest is not None else self._new_dual(n, h, w, C_)
         ops.linear(t, d["proj_out"].w, out.f, bias=d["proj_out"].b, residual=x.f, out2=self._out2(out))
         return out

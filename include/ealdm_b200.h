@@ -181,6 +181,13 @@ typedef struct {
                       gn_ld counts quads */
   int64_t wi_ld;
   int64_t wi_head_stride;
+  /* LayerNorm APPLIED by the producing epilogue (ln_gamma != NULL; tcgen05 path, n_out == 256 so that one CTA holds whole
+     rows, fp32 `out`, act NONE): `out` receives the fp32 result as usual and `out2` (bf16, pitch ld_out2) receives
+     LayerNorm(result) * ln_gamma + ln_beta over the 256 columns (eps = ln_eps) instead of a copy -- the stand-alone
+     nn.LayerNorm pass of BasicTransformerBlock._forward (ldm/modules/attention.py:211-215) that would re-read the fp32
+     stream disappears.  Two passes over the accumulator in TMEM; the statistics are E[x], E[x^2] in fp32. */
+  const float* ln_gamma;
+  const float* ln_beta;
 } ealdm_conv_args;
 
 int ealdm_conv(const ealdm_conv_args* a, ealdm_stream_t stream);

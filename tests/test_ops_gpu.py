@@ -540,6 +540,38 @@ def test_conv_epilogue_groupnorm_partials_per_channel_quad(n, c, h, w, co, res):
     assert rel_l2(from_act(y), ref) < 6e-3
 
 
+@pytest.mark.parametrize("M,K,res,geom", [(4096, 256, True, "linear"), (700, 256, False, "linear"),
+                                          (2048, 1024, True, "linear"), (3 * 256, 64, True, "image")])
+def test_layer_norm_applied_by_the_producing_epilogue(M, K, res, geom):
+    """ealdm_conv ln_gamma / ln_beta: the GEMM that writes the fp32 stream x = a W^T + b (+ r) also writes
+    LayerNorm(x) * gamma + beta as bf16 (two passes over the accumulator in TMEM, the two warps of a row exchanging
+    their sums): equal to ealdm_layer_norm of the stored fp32 result up to bf16 rounding, ragged row counts, CTA pairs
+    (K = 1024) and the (n, h, w) image geometry of the collapsed cross-attention included."""
+    C = 256
+    a = torch.randn(M, K, generator=g(801)).to(DEV).to(torch.bfloat16)
+    W = (torch.randn(C, K, generator=g(802)) / math.sqrt(K)).to(DEV).to(torch.bfloat16)
+    b = torch.randn(C, generator=g(803)).to(DEV)
+    r = (torch.randn(M, C, generator=g(804)) * 2 + 0.7).to(DEV) if res else None
+    gamma = (torch.rand(C, generator=g(805)) + 0.5).to(DEV)
+    beta = (torch.randn(C, generator=g(806)) * 0.3).to(DEV)
+    shape = (1, 1, M) if geom == "linear" else (3, 16, 16)
+    aa = Act(a, *shape)
+    x = Act.empty(*shape, C, torch.float32, DEV)
+    y = Act.empty(*shape, C, torch.bfloat16, DEV)
+    y.buf.fill_(float("nan"))
+    ra = None if r is None else Act(r, *shape)
+    ops.conv([ConvIn(aa)], W, x, bias=b, residual=ra, out2=y, ln_apply=(gamma, beta, 1e-5))
+    want_x = a.float() @ W.float().t() + b + (r if res else 0)
+    assert rel_l2(x.buf, want_x) < 1e-5 * 50
+    ref = Act.empty(*shape, C, torch.bfloat16, DEV)
+    ops.layer_norm(x, gamma, beta, 1e-5, ref)
+    want = F.layer_norm(x.buf, (C,), gamma, beta, 1e-5)
+    e_epi, e_ker = rel_l2(y.buf.float(), want), rel_l2(ref.buf.float(), want)
+    print(f"LN in the epilogue M={M} K={K} res={res} {geom}: {e_epi:.3e} (LayerNorm kernel {e_ker:.3e}) vs torch fp32")
+    assert e_epi < 4e-3 and e_epi < 1.2 * e_ker + 1e-4
+    assert (y.buf.float() - ref.buf.float()).abs().max() < 0.07    # at most an ulp or two of bf16 apart
+
+
 # ---- schedules of the tcgen05 conv (ealdm_tc_set_option): every setting must give the same numbers ----------------
 class _tc_option:
     """Sets one schedule switch and forces the 256-column N tile (small problems would pick 128 by wave count and
