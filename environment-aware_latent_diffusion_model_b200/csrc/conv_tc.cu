@@ -109,13 +109,11 @@ struct Params {
   // LayerNorm APPLIED by the producing epilogue (ealdm_conv_args::ln_gamma; N == BN == 256, so a CTA holds whole rows):
   // pass 1 writes the fp32 result as usual, keeps per-row {sum, sum of squares} and stores the result back over its
   // TMEM accumulator; the two warps that share a row exchange their sums; pass 2 re-reads TMEM and writes
-  // LayerNorm(result) * gamma + beta as bf16 rows straight to ln_y (64 contiguous bytes per thread and unit)
+  // LayerNorm(result) * gamma + beta as bf16 units through the shadow-output map (tmOut2) -- staged in shared memory and
+  // stored by TMA: direct 16-byte stores from registers (32 rows per instruction) measured 3x slower
   const float* ln_gamma;
   const float* ln_beta;
-  bf16* ln_y;
-  long long ln_y_ld;
   float ln_apply_eps;
-  int sub_w, sub_h;   // the 32 rows of an epilogue unit as a (sub_w, sub_h, 32 / (sub_w sub_h)) pixel box
   float2* ln_out;
   int ln_out_parts;
   const float2* ln_in;
@@ -912,9 +910,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           const float var = fmaxf(ss_all * (1.0f / 256.0f) - mu * mu, 0.f);
           const float rstd = rsqrtf(var + p.ln_apply_eps);
           const float nmu = -mu * rstd;
-          const int lw = lane % p.sub_w, lh = (lane / p.sub_w) % p.sub_h, li = lane / (p.sub_w * p.sub_h);
-          const bool rvalid = n + li < p.Nimg && h + lh < p.Hout && w + lw < p.Wout;
-          bf16* const yrow = p.ln_y + ((static_cast<long long>(n + li) * p.Hout + (h + lh)) * p.Wout + (w + lw)) * p.ln_y_ld;
+          // staging: the unit buffer of pass 1's last unit, as two bf16 [32 rows x 64 B] halves (the OTHER unit buffer
+          // may already hold the next tile's first residual unit); free once every pass-1 store has read its box
+          uint8_t* const fb = ebuf + ((it - 1u) & 1u) * EBUF_BYTES;
+          if (lane == 0) ptx::bulk_wait_read<0>();
+          __syncwarp();
           uint32_t vv[2][32];
           ptx::tmem_ld_32x32(taddr0 + part * 32, vv[0]);
 #pragma unroll
@@ -923,22 +923,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             ptx::tmem_ld_wait();
             if (ui + 1 < UNITS / 2) ptx::tmem_ld_32x32(taddr0 + (ku + 2) * 32, vv[(ui + 1) & 1]);   // flies under the math
             const uint32_t(&v)[32] = vv[ui & 1];
-            uint4 q[4];
-            uint32_t* qw = reinterpret_cast<uint32_t*>(q);
+            float y[32];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const float4 g4 = *reinterpret_cast<const float4*>(lng_s + ku * 32 + 4 * j);
               const float4 b4 = *reinterpret_cast<const float4*>(lng_s + 256 + ku * 32 + 4 * j);
-              const float y0 = fmaf(fmaf(__uint_as_float(v[4 * j]), rstd, nmu), g4.x, b4.x);
-              const float y1 = fmaf(fmaf(__uint_as_float(v[4 * j + 1]), rstd, nmu), g4.y, b4.y);
-              const float y2 = fmaf(fmaf(__uint_as_float(v[4 * j + 2]), rstd, nmu), g4.z, b4.z);
-              const float y3 = fmaf(fmaf(__uint_as_float(v[4 * j + 3]), rstd, nmu), g4.w, b4.w);
-              qw[2 * j] = pack2_bf16(y0, y1);
-              qw[2 * j + 1] = pack2_bf16(y2, y3);
+              y[4 * j] = fmaf(fmaf(__uint_as_float(v[4 * j]), rstd, nmu), g4.x, b4.x);
+              y[4 * j + 1] = fmaf(fmaf(__uint_as_float(v[4 * j + 1]), rstd, nmu), g4.y, b4.y);
+              y[4 * j + 2] = fmaf(fmaf(__uint_as_float(v[4 * j + 2]), rstd, nmu), g4.z, b4.z);
+              y[4 * j + 3] = fmaf(fmaf(__uint_as_float(v[4 * j + 3]), rstd, nmu), g4.w, b4.w);
             }
-            if (rvalid) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(yrow + ku * 32 + 8 * j) = q[j];
+            uint8_t* const sb = fb + (ui & 1) * O2BUF_BYTES;
+            if (ui >= 2) {   // the store issued two units ago has read this half
+              if (lane == 0) ptx::bulk_wait_read<1>();
+              __syncwarp();
+            }
+            sts_row_bf16(sb, lane, y);
+            ptx::fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              ptx::tma_store_4d(&tmOut2, sb, nt * BN + ku * 32, w, h, n);
+              ptx::bulk_commit();
             }
           }
         }
@@ -1363,7 +1368,7 @@ int launch(const ealdm_conv_args* a, cudaStream_t st) {
   }
   tm[4] = tm[3];
   tm[5] = tm[3];
-  if (a->out2 && !a->ln_gamma) {
+  if (a->out2) {
     if (phased) {
       if (int e = encode_phase_map(encode, &tm[4], a->out2, false, out_cols, a->ld_out2, a, sub, 0, 0)) return e;
       for (int ph = 1; ph < 4; ++ph)
@@ -1387,11 +1392,7 @@ int launch(const ealdm_conv_args* a, cudaStream_t st) {
   p.has_out2 = a->out2 != nullptr && !a->ln_gamma;
   p.ln_gamma = a->ln_gamma;
   p.ln_beta = a->ln_beta;
-  p.ln_y = a->ln_gamma ? reinterpret_cast<bf16*>(a->out2) : nullptr;
-  p.ln_y_ld = a->ld_out2;
   p.ln_apply_eps = a->ln_eps;
-  p.sub_w = sub[0];
-  p.sub_h = sub[1];
   p.gn_partial = reinterpret_cast<float2*>(a->gn_partial);
   p.gn_ld = static_cast<int>(a->gn_ld);
   p.gn_quads = a->gn_unit == 4 ? 1 : 0;
