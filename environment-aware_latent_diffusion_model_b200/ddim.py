@@ -13,7 +13,7 @@ import numpy as np
 import torch
 
 from . import ops
-from .util import make_ddim_sampling_parameters, make_ddim_timesteps, revalidate_packed
+from .util import GuidancePair, make_ddim_sampling_parameters, make_ddim_timesteps, revalidate_packed, sampling_scope
 
 
 class DDIMSampler(object):
@@ -24,6 +24,7 @@ class DDIMSampler(object):
         self.schedule = schedule
         # test hook: callable(shape, device) -> noise replacing the per-step torch.randn draw
         self.noise_fn = kwargs.get("noise_fn", None)
+        self._pair = GuidancePair(model)
 
     def register_buffer(self, name, attr):
         setattr(self, name, attr)
@@ -113,6 +114,15 @@ class DDIMSampler(object):
         # all timestep vectors of the loop in one upload (the reference builds one per step)
         ts_all = torch.as_tensor(np.ascontiguousarray(np.asarray(time_range, dtype=np.int64))).to(device)
         ts_all = ts_all[:, None].expand(total_steps, b).contiguous()
+        with sampling_scope(self.model):   # the conditioning is loop-invariant: the UNet projects it once
+            return self._ddim_loop(img, cond, ts_all, total_steps, mask, x0, ddim_use_original_steps, quantize_denoised,
+                                   temperature, noise_dropout, score_corrector, corrector_kwargs,
+                                   unconditional_guidance_scale, unconditional_conditioning, callback, img_callback,
+                                   log_every_t, intermediates)
+
+    def _ddim_loop(self, img, cond, ts_all, total_steps, mask, x0, ddim_use_original_steps, quantize_denoised,
+                   temperature, noise_dropout, score_corrector, corrector_kwargs, unconditional_guidance_scale,
+                   unconditional_conditioning, callback, img_callback, log_every_t, intermediates):
         for i in range(total_steps):
             index = total_steps - i - 1
             ts = ts_all[i]
@@ -144,10 +154,7 @@ class DDIMSampler(object):
         if unconditional_conditioning is None or unconditional_guidance_scale == 1.:
             e_c = self.model.apply_model(x, t, c)
         else:
-            x_in = torch.cat([x] * 2)
-            t_in = torch.cat([t] * 2)
-            c_in = torch.cat([unconditional_conditioning, c])
-            e_u, e_c = self.model.apply_model(x_in, t_in, c_in).chunk(2)
+            e_u, e_c = self._pair(x, t, unconditional_conditioning, c)
         sc = self.step_scalars(index, use_original_steps)
         generic = score_corrector is not None or quantize_denoised or noise_dropout > 0. or repeat_noise
         if generic:

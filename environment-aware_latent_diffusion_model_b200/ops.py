@@ -77,6 +77,18 @@ class Act:
         a.gunit = self.gunit
         return a
 
+    def images(self, i0: int, cnt: int) -> "Act":
+        """Images i0 .. i0+cnt of the batch as a view (rows of the same buffer; the statistics buffer follows)."""
+        assert 0 <= i0 and i0 + cnt <= self.n
+        hw = self.h * self.w
+        gp = None
+        if self.gp is not None:
+            assert hw % 32 == 0
+            gp = self.gp[i0 * hw // 32:(i0 + cnt) * hw // 32]
+        a = Act(self.buf[i0 * hw:(i0 + cnt) * hw], cnt, self.h, self.w, self.c, self.c0, gp)
+        a.gunit = self.gunit
+        return a
+
     def reshape(self, n, h, w) -> "Act":
         assert n * h * w == self.rows
         return Act(self.buf, n, h, w, self.c, self.c0)

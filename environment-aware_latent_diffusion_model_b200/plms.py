@@ -12,7 +12,7 @@ import torch
 
 from . import ops
 from .ddim import DDIMSampler
-from .util import revalidate_packed
+from .util import revalidate_packed, sampling_scope
 
 
 class PLMSSampler(DDIMSampler):
@@ -59,34 +59,35 @@ class PLMSSampler(DDIMSampler):
         ts_all = torch.as_tensor(np.ascontiguousarray(np.asarray(time_range, dtype=np.int64))).to(device)
         ts_all = ts_all[:, None].expand(total_steps, b).contiguous()
         old_eps = []
-        for i in range(total_steps):
-            index = total_steps - i - 1
-            ts, ts_next = ts_all[i], ts_all[min(i + 1, total_steps - 1)]
-            if mask is not None:
-                assert x0 is not None
-                img_orig = self.model.q_sample(x0, ts)
-                img = img_orig * mask + (1. - mask) * img
-            img, pred_x0, e_t = self.p_sample_plms(img, cond, ts, index=index, temperature=temperature,
-                                                   unconditional_guidance_scale=unconditional_guidance_scale,
-                                                   unconditional_conditioning=unconditional_conditioning,
-                                                   old_eps=old_eps, t_next=ts_next)
-            old_eps.append(e_t)
-            if len(old_eps) >= 4:
-                old_eps.pop(0)
-            if callback:
-                callback(i)
-            if img_callback:
-                img_callback(pred_x0, i)
-            if index % log_every_t == 0 or index == total_steps - 1:
-                intermediates["x_inter"].append(img)
-                intermediates["pred_x0"].append(pred_x0)
+        with sampling_scope(self.model):     # the conditioning is loop-invariant: the UNet projects it once
+            for i in range(total_steps):
+                index = total_steps - i - 1
+                ts, ts_next = ts_all[i], ts_all[min(i + 1, total_steps - 1)]
+                if mask is not None:
+                    assert x0 is not None
+                    img_orig = self.model.q_sample(x0, ts)
+                    img = img_orig * mask + (1. - mask) * img
+                img, pred_x0, e_t = self.p_sample_plms(img, cond, ts, index=index, temperature=temperature,
+                                                       unconditional_guidance_scale=unconditional_guidance_scale,
+                                                       unconditional_conditioning=unconditional_conditioning,
+                                                       old_eps=old_eps, t_next=ts_next)
+                old_eps.append(e_t)
+                if len(old_eps) >= 4:
+                    old_eps.pop(0)
+                if callback:
+                    callback(i)
+                if img_callback:
+                    img_callback(pred_x0, i)
+                if index % log_every_t == 0 or index == total_steps - 1:
+                    intermediates["x_inter"].append(img)
+                    intermediates["pred_x0"].append(pred_x0)
         return img, intermediates
 
     def _model_eps(self, x, c, t, ugs, uc):
         """(e_uncond or None, e_cond): plms.py:181-189 without the combine (done inside ealdm_plms_eps)."""
         if uc is None or ugs == 1.:
             return None, self.model.apply_model(x, t, c).contiguous()
-        e_u, e_c = self.model.apply_model(torch.cat([x] * 2), torch.cat([t] * 2), torch.cat([uc, c])).chunk(2)
+        e_u, e_c = self._pair(x, t, uc, c)
         return e_u.contiguous(), e_c.contiguous()
 
     def _x_prev(self, x, e, index, temperature):

@@ -9,6 +9,7 @@ issues libealdm_b200 kernels on NHWC activations (see DESIGN.md for the data lay
 """
 from __future__ import annotations
 
+import contextlib
 import math
 import os
 from typing import List, Optional
@@ -234,6 +235,9 @@ class UNetModel(nn.Module):
         self.use_cuda_graph = False   # see enable_cuda_graph
         self.grad_ready_hook = None   # set by parallel.GradBuckets (data-parallel training)
         self._graphs = {}
+        self._loop_scope = False      # see sampling_scope / cfg_pair
+        self._pair_hint = False
+        self._ctx_seen = None
         self.register_load_state_dict_post_hook(lambda m, keys: m.invalidate_packed())
 
     # ---- engine management -------------------------------------------------------------------------
@@ -246,6 +250,7 @@ class UNetModel(nn.Module):
         """Drop the packed kernel-layout weights (call after modifying parameters in place)."""
         self._engine = None
         self._graphs = {}
+        self._ctx_seen = None
 
     # The packed weights (and the CUDA graphs over them) are a cache of the parameters.  `load_state_dict`, `_apply`,
     # optim.FusedAdamWEMA and ema.LitEma invalidate it explicitly; every eval forward additionally compares the
@@ -293,30 +298,76 @@ class UNetModel(nn.Module):
         self._graphs = {}
         return super()._apply(fn, *a, **k)
 
-    def _forward_graphed(self, x, timesteps, context):
-        key = (tuple(x.shape), None if context is None else tuple(context.shape), self._compute_dtype)
+    # ---- hints from the samplers -----------------------------------------------------------------------
+    @contextlib.contextmanager
+    def sampling_scope(self):
+        """Entered by the samplers around one denoising loop: inside it a context tensor that is the SAME object (and
+        autograd version) as in the previous call is not projected again -- the K / V rows and the collapsed
+        cross-attention operands depend on the context and the weights only (ddim.py:118-131 passes one `cond` to
+        every step).  Outside the scope every forward projects its context."""
+        prev = self._loop_scope
+        self._loop_scope = True
+        try:
+            yield self
+        finally:
+            self._loop_scope = prev
+            if not prev:
+                self._ctx_seen = None
+                for ent in self._graphs.values():
+                    ent["ctx_ref"] = None
+
+    @contextlib.contextmanager
+    def cfg_pair(self):
+        """Entered by the samplers around `apply_model(torch.cat([x] * 2), torch.cat([t] * 2), cat([uc, c]))`
+        (ddim.py:176-179): both halves of the batch carry the same images and timesteps, so the layers in front of
+        the first cross-attention are computed once (UNetEngine.forward(shared_halves=True))."""
+        prev = self._pair_hint
+        self._pair_hint = True
+        try:
+            yield self
+        finally:
+            self._pair_hint = prev
+
+    def _projection(self, engine, context, holder: dict, static_ctx=None):
+        """The context projection for this call: reused inside a sampling_scope when `context` is the tensor seen last."""
+        same = (self._loop_scope and holder.get("ctx_ref") is context and holder.get("ctx_ver") == context._version
+                and not os.environ.get("EALDM_NO_CTX_REUSE"))
+        if not same:
+            src = context
+            if static_ctx is not None:
+                static_ctx.copy_(context)
+                src = static_ctx
+            holder["proj"] = engine.project_context(src, into=holder.get("proj") if static_ctx is not None else None)
+            holder["ctx_ref"] = context if self._loop_scope else None
+            holder["ctx_ver"] = context._version
+        return holder["proj"]
+
+    def _forward_graphed(self, x, timesteps, context, pair: bool):
+        key = (tuple(x.shape), None if context is None else tuple(context.shape), self._compute_dtype, pair)
         ent = self._graphs.get(key)
         if ent is None:
             sx = x.detach().float().contiguous().clone()
             st = timesteps.detach().to(device=x.device, dtype=torch.int64).contiguous().clone()
             sc = None if context is None else context.detach().float().contiguous().clone()
+            ent = {"sx": sx, "st": st, "sc": sc, "ctx_ref": None}
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):       # warm-up outside capture (lazy attributes, allocator)
-                self._engine.forward(sx, st, sc)
+                proj = None if sc is None else self._engine.project_context(sc)
+                self._engine.forward(sx, st, sc, ctx_proj=proj, shared_halves=pair)
             torch.cuda.current_stream().wait_stream(side)
+            ent["proj"] = proj      # static: refilled outside the graph whenever the context changes
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                sy = self._engine.forward(sx, st, sc)
-            ent = (graph, sx, st, sc, sy)
+                ent["sy"] = self._engine.forward(sx, st, sc, ctx_proj=proj, shared_halves=pair)
+            ent["graph"] = graph
             self._graphs[key] = ent
-        graph, sx, st, sc, sy = ent
-        sx.copy_(x)
-        st.copy_(timesteps)
-        if sc is not None:
-            sc.copy_(context)
-        graph.replay()
-        return sy.clone()
+        ent["sx"].copy_(x)
+        ent["st"].copy_(timesteps)
+        if context is not None:
+            self._projection(self._engine, context, ent, static_ctx=ent["sc"])
+        ent["graph"].replay()
+        return ent["sy"].clone()
 
     def convert_to_fp16(self):  # reference stubs (openaimodel.py:694-708): no-ops there as well
         pass
@@ -335,9 +386,15 @@ class UNetModel(nn.Module):
             from .train import unet_forward_train
             return unet_forward_train(self, x, timesteps, context)
         engine = self._get_engine()
+        pair = self._pair_hint and x.shape[0] % 2 == 0
         if self.use_cuda_graph and not torch.cuda.is_current_stream_capturing():
-            return self._forward_graphed(x, timesteps, context)
-        return engine.forward(x, timesteps, context)
+            return self._forward_graphed(x, timesteps, context, pair)
+        proj = None
+        if context is not None and self._loop_scope and not torch.cuda.is_current_stream_capturing():
+            if self._ctx_seen is None:
+                self._ctx_seen = {}
+            proj = self._projection(engine, context, self._ctx_seen)
+        return engine.forward(x, timesteps, context, ctx_proj=proj, shared_halves=pair)
 
 
 # ---- execution engine --------------------------------------------------------------------------------
@@ -533,6 +590,9 @@ class UNetEngine:
                     c = d["conv"].cout
             return c
 
+        self._overlap_emb = (type(self) is UNetEngine and not os.environ.get("EALDM_NO_EMB_OVERLAP")
+                             and len(self.inp) > 1 and self.inp[0][0]["kind"] == "conv_in")
+        self._side = torch.cuda.Stream(device=dev) if self._overlap_emb else None
         self.skip_ch = []
         c = m.in_channels
         for layers in self.inp:
@@ -602,7 +662,10 @@ class UNetEngine:
                      out2=self._out2(out))
         return out
 
-    def _st(self, d, x: "Dual", kv_all: Optional[Act], n_ctx: int, dest: Optional["Dual"]) -> "Dual":
+    def _st(self, d, x: "Dual", kv_all: Optional[Act], n_ctx: int, dest: Optional["Dual"],
+            share_full: Optional["Dual"] = None) -> "Dual":
+        """share_full (classifier-free-guidance pair, see forward): `x` is the first-half view of `share_full`; up to
+        the first cross-attention the block runs on that half, then the token stream is duplicated."""
         C_, heads, dh = d["c"], d["heads"], d["dh"]
         n, h, w = x.f.n, x.f.h, x.f.w
         tok = h * w
@@ -655,7 +718,22 @@ class UNetEngine:
             ops.attention(qkv.cols(0, C_), qkv.cols(C_, C_), qkv.cols(2 * C_, C_), o, batch=n, heads=heads,
                           head_dim=dh, n_q=tok, n_kv=tok, scale=dh ** -0.5)
             t1, t1_h = stream()
-            if ln_epi:
+            if share_full is not None and bi == 0:
+                # everything so far saw x and t only: the second half of the batch is a copy of the first
+                nf = share_full.f.n
+                t1 = self._new(nf, h, w, C_, f32)
+                t1v = t1.images(0, n)
+                kw = {}
+                if ln_epi:
+                    t1.lny = self._new(nf, h, w, C_)
+                    t1v.lny = t1.lny.images(0, n)
+                    kw = {"out2": t1v.lny, "ln_apply": (tb["ln2"][0], tb["ln2"][1], 1e-5)}
+                ops.linear(o, tb["o1"].w, t1v, bias=tb["o1"].b, residual=t, **kw)
+                for a in (t1, t1.lny, share_full.f):
+                    if a is not None:
+                        _dup_first_half(a)
+                x, n = share_full, nf
+            elif ln_epi:
                 ops.linear(o, tb["o1"].w, t1, bias=tb["o1"].b, residual=t, **ln_out(t1, tb, 2))
             else:
                 ops.linear(o, tb["o1"].w, t1, bias=tb["o1"].b, residual=t, out2=t1_h, ln_stats=fold)
@@ -752,9 +830,47 @@ class UNetEngine:
                 raise ValueError(k)
         return x
 
+    def _shareable(self, n: int) -> bool:
+        """The classifier-free-guidance prefix is shared when the first block after the input conv is
+        [ResBlock, SpatialTransformer] (every shipped config) and LayerNorm is not folded into the GEMMs."""
+        k = [[d["kind"] for d in layers] for layers in self.inp[:2]]
+        return (n % 2 == 0 and n >= 2 and self.dt == torch.bfloat16 and type(self) is UNetEngine and not self._fold_ln
+                and not os.environ.get("EALDM_NO_CFG_SHARE") and k == [["conv_in"], ["res", "st"]])
+
+    def _run_shared(self, layers, x: "Dual", emb_all, kv_all, n_ctx, dest: "Dual") -> "Dual":
+        """input_blocks.1 of a guidance pair: ResBlock, GroupNorm, proj_in and the first self-attention run on the
+        first half of the batch (the second half holds the same images and timesteps; only the context differs)."""
+        n2 = x.f.n // 2
+        xh = Dual(x.f.images(0, n2), x.h.images(0, n2))
+        r = self._new_dual(x.f.n, x.f.h, x.f.w, layers[0]["cout"], gn=True)
+        rh = Dual(r.f.images(0, n2), r.h.images(0, n2))
+        self._res(layers[0], xh, emb_all[:n2], rh)
+        return self._st(layers[1], rh, kv_all, n_ctx, dest, share_full=r)
+
     # ---- forward ----------------------------------------------------------------------------------------
     @torch.no_grad()
-    def forward(self, x: torch.Tensor, timesteps: torch.Tensor, context: Optional[torch.Tensor]) -> torch.Tensor:
+    def project_context(self, context: torch.Tensor, into: Optional[tuple] = None) -> tuple:
+        """(kv_all, xc_all): the K / V rows of every cross-attention layer and the collapsed-attention operands
+        [G; H] x context of the layers that use them, each as ONE GEMM over the context.  `into`: buffers of an
+        earlier call to refill (the CUDA graph of the forward reads them)."""
+        dt, dev = self.dt, self.dev
+        n, n_ctx = context.shape[0], context.shape[1]
+        csrc = Act(context.float().reshape(n * n_ctx, -1).contiguous(), n, 1, n_ctx)
+        ctx = ops.copy2d(csrc, Act.empty(n, 1, n_ctx, csrc.c, dt, dev)) if dt != torch.float32 else csrc
+        kv_all = into[0] if into is not None else Act.empty(n, 1, n_ctx, self.kv_cols, dt, dev)
+        ops.linear(ctx, self.kv_w, kv_all)
+        xc_all = None
+        if self.xc_w is not None and n_ctx == 4:
+            xc_all = into[1] if into is not None else Act.empty(n, 1, n_ctx, self.xc_cols, dt, dev)
+            ops.linear(ctx, self.xc_w, xc_all)
+        return kv_all, xc_all
+
+    def forward(self, x: torch.Tensor, timesteps: torch.Tensor, context: Optional[torch.Tensor],
+                ctx_proj: Optional[tuple] = None, shared_halves: bool = False) -> torch.Tensor:
+        """ctx_proj: `project_context(context)` made earlier (the context is loop-invariant in a sampling run).
+        shared_halves: the caller guarantees x[:n/2] == x[n/2:] and timesteps[:n/2] == timesteps[n/2:] (classifier-free
+        guidance: `torch.cat([x] * 2)`, ddim.py:176-178) -- everything in front of the first cross-attention then
+        depends on the first half only and is computed once (bit-identical results, see _run_shared)."""
         m, dt, dev = self.m, self.dt, self.dev
         n, cin, H, W = x.shape
         assert cin == m.in_channels
@@ -764,32 +880,35 @@ class UNetEngine:
         # one GroupNorm scratch for the whole forward, sized for the widest concat at the finest level
         self.stats = ops.group_norm_workspace(n, H * W, 2 * self.mid_ch, dev)
 
-        # timestep embedding -> time_embed MLP -> SiLU(emb) -> every ResBlock's emb_layers in ONE GEMM
+        # timestep embedding -> time_embed MLP -> SiLU(emb) -> every ResBlock's emb_layers in ONE GEMM.  Four tiny
+        # launches (M = n rows) that nothing needs before the first ResBlock: they run on a side stream next to the
+        # input convolution (a fork / join the CUDA graph keeps).  Buffers are allocated on the main stream and stay
+        # referenced until the join, so the caching allocator cannot hand them out early.
         temb = torch.empty((n, m.model_channels), dtype=dt, device=dev)
-        ops.timestep_embedding(timesteps, m.model_channels, self.freqs, temb)
         ted = self.te0.w.shape[0]
         e1 = Act.empty(1, 1, n, ted, dt, dev)
-        ops.linear(Act(temb, 1, 1, n), self.te0.w, e1, bias=self.te0.b, act=L.ACT_SILU)
         semb = Act.empty(1, 1, n, ted, dt, dev)
-        ops.linear(e1, self.te2.w, semb, bias=self.te2.b, act=L.ACT_SILU)
         emb_all = Act.empty(1, 1, n, self.emb_cols, torch.float32, dev)
-        ops.linear(semb, self.emb_w, emb_all, bias=self.emb_b)
+        main = torch.cuda.current_stream()
+        side = self._side if self._overlap_emb else main
+        if side is not main:
+            side.wait_stream(main)
+        with torch.cuda.stream(side):
+            ops.timestep_embedding(timesteps, m.model_channels, self.freqs, temb)
+            ops.linear(Act(temb, 1, 1, n), self.te0.w, e1, bias=self.te0.b, act=L.ACT_SILU)
+            ops.linear(e1, self.te2.w, semb, bias=self.te2.b, act=L.ACT_SILU)
+            ops.linear(semb, self.emb_w, emb_all, bias=self.emb_b)
+        emb_ready = side.record_event() if side is not main else None
 
-        # context -> K/V of every cross-attention layer in ONE GEMM (loop-invariant across DDIM steps)
+        # context -> K/V of every cross-attention layer in ONE GEMM (loop-invariant across DDIM steps: the samplers
+        # hand in the projection they made once per `sample()`, see UNetModel.sampling_scope)
         kv_all, n_ctx = None, 0
         if self.kv_w is not None:
             if context is None:
                 raise RuntimeError("this UNet was built with context_dim: pass context=[N, T, context_dim]")
             assert context.shape[0] == n and context.shape[2] == self.kv_w.shape[1]
             n_ctx = context.shape[1]
-            csrc = Act(context.float().reshape(n * n_ctx, -1).contiguous(), n, 1, n_ctx)
-            ctx = ops.copy2d(csrc, Act.empty(n, 1, n_ctx, csrc.c, dt, dev)) if dt != torch.float32 else csrc
-            kv_all = Act.empty(n, 1, n_ctx, self.kv_cols, dt, dev)
-            ops.linear(ctx, self.kv_w, kv_all)
-            self.xc_all = None
-            if self.xc_w is not None and n_ctx == 4:
-                self.xc_all = Act.empty(n, 1, n_ctx, self.xc_cols, dt, dev)
-                ops.linear(ctx, self.xc_w, self.xc_all)
+            kv_all, self.xc_all = ctx_proj if ctx_proj is not None else self.project_context(context)
 
         # concat buffers of the output blocks: [h | skip]; producers write straight into them
         n_in = len(self.inp)
@@ -816,8 +935,15 @@ class UNetEngine:
             xin = self._new(n, H, W, cin)
         ops.nchw_to_nhwc(x, xin)
         h = Dual(xin, xin)
+        share = shared_halves and self._shareable(n)
         for i, layers in enumerate(self.inp):
-            h = self._run(layers, h, emb_all.buf, kv_all, n_ctx, skip_dst[i])
+            if i == 1 and emb_ready is not None:
+                main.wait_event(emb_ready)
+                emb_ready = None
+            if share and i == 1:
+                h = self._run_shared(layers, h, emb_all.buf, kv_all, n_ctx, skip_dst[i])
+            else:
+                h = self._run(layers, h, emb_all.buf, kv_all, n_ctx, skip_dst[i])
         h = self._run(self.mid, h, emb_all.buf, kv_all, n_ctx, window(0, 0, self.mid_ch))
         for j, layers in enumerate(self.outb):
             if j + 1 < len(self.outb):
@@ -835,6 +961,16 @@ class UNetEngine:
         y = torch.empty((n, co, H, W), dtype=torch.float32, device=dev)
         ops.nhwc_to_nchw(obuf.cols(0, co), y)
         return y
+
+
+def _dup_first_half(a: Act) -> None:
+    """Images n/2 .. n of `a` := images 0 .. n/2 (one device-to-device copy; the statistics buffer follows)."""
+    half = a.rows // 2
+    v = a.view2d()
+    v[half:].copy_(v[:half])
+    if a.gp is not None:
+        g = a.gp.shape[0] // 2
+        a.gp[g:].copy_(a.gp[:g])
 
 
 class Dual:

@@ -103,3 +103,38 @@ def revalidate_packed(model) -> None:
         fn = getattr(m, "revalidate_packed", None)
         if callable(fn):
             fn()
+
+
+def _hosted_unet(model):
+    unet = getattr(getattr(model, "model", None), "diffusion_model", None)
+    return unet if hasattr(unet, "sampling_scope") else None
+
+
+def sampling_scope(model):
+    """Context manager around one denoising loop: the hosted UNet projects a loop-invariant context once
+    (unet.UNetModel.sampling_scope); a no-op for any other model."""
+    import contextlib
+    unet = _hosted_unet(model)
+    return unet.sampling_scope() if unet is not None else contextlib.nullcontext()
+
+
+class GuidancePair:
+    """`apply_model(torch.cat([x] * 2), torch.cat([t] * 2), torch.cat([uc, c]))` of the reference's guided step
+    (ddim.py:176-179, plms.py:184-187): the concatenated conditioning is built once per loop while `uc` and `c` stay
+    the same tensors (so that the UNet recognises it), and the UNet is told that both halves share x and t."""
+
+    def __init__(self, model):
+        self.model, self.unet = model, _hosted_unet(model)
+        self._key, self._held, self._c_in = None, (None, None), None
+
+    def __call__(self, x, t, uc, c):
+        import contextlib
+        if isinstance(c, torch.Tensor) and isinstance(uc, torch.Tensor):
+            key = (id(uc), uc._version, id(c), c._version)
+            if key != self._key or self._held[0] is not uc or self._held[1] is not c:
+                self._key, self._held, self._c_in = key, (uc, c), torch.cat([uc, c])
+            c_in = self._c_in
+        else:
+            c_in = torch.cat([uc, c])
+        with (self.unet.cfg_pair() if self.unet is not None else contextlib.nullcontext()):
+            return self.model.apply_model(torch.cat([x] * 2), torch.cat([t] * 2), c_in).chunk(2)

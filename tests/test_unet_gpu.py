@@ -135,6 +135,54 @@ def test_unet_forward_programmatic_dependent_launch_is_bit_identical():
     assert rel_l2(base[:2], G["eps"]) < TOL["bf16"]
 
 
+def test_unet_forward_guidance_pair_shares_the_prefix_bit_identical():
+    """Classifier-free guidance evaluates cat([x] * 2), cat([t] * 2), cat([uc, c]) (ddim.py:176-179): under
+    `unet.cfg_pair()` the layers in front of the first cross-attention run once on the first half of the batch and the
+    token stream is duplicated.  Must equal the plain forward of the duplicated batch bit for bit, eager and graphed,
+    and (with `sampling_scope`) a context that is the same tensor is projected once, a modified one again."""
+    from ealdm_b200 import ops
+    G = gold("unet_stdiff_fwd.pt")
+    unet = make_ld("stdiff").model.diffusion_model.set_compute_dtype("bf16")
+    g = torch.Generator().manual_seed(5)
+    x = torch.cat([G["x"].cuda()] * 4)                   # 8 images
+    x = x + 0.1 * torch.randn(x.shape, generator=g).cuda()
+    t = torch.cat([G["t"].cuda()] * 4)
+    c = torch.randn(16, 4, 512, generator=g).cuda()      # uc rows, then c rows
+    x2, t2 = torch.cat([x] * 2), torch.cat([t] * 2)
+    base = unet(x2, t2, context=c)
+    assert not torch.equal(base[:8], base[8:])           # the halves do differ (through the context only)
+    with unet.cfg_pair():
+        n0 = ops.launch_count()
+        shared = unet(x2, t2, context=c)
+        n_shared = ops.launch_count() - n0
+    n0 = ops.launch_count()
+    again = unet(x2, t2, context=c)
+    n_plain = ops.launch_count() - n0
+    assert torch.equal(shared, base) and torch.equal(again, base)
+    assert n_shared == n_plain                            # same launches, the prefix on half the rows
+    for graph in (False, True):
+        unet.enable_cuda_graph(graph)
+        with unet.sampling_scope():
+            with unet.cfg_pair():
+                a = unet(x2, t2, context=c)
+                n0 = ops.launch_count()
+                b = unet(x2, t2, context=c)               # same context tensor: not projected again
+                n_reuse = ops.launch_count() - n0
+                c.mul_(1.0)                               # in-place write: version bump, same values
+                n0 = ops.launch_count()
+                d = unet(x2, t2, context=c)
+                n_again = ops.launch_count() - n0
+                c2 = torch.cat([c[8:], c[:8]])            # another tensor: uc and c rows swapped
+                e = unet(x2, t2, context=c2)
+        assert torch.equal(a, base) and torch.equal(b, base) and torch.equal(d, base)
+        assert torch.equal(e, torch.cat([base[8:], base[:8]]))
+        if not graph:
+            assert n_again - n_reuse >= 2                 # the context copy + projection GEMMs came back
+        outside = unet(x2, t2, context=c2)                # outside the scope nothing is remembered
+        assert torch.equal(outside, e)
+    unet.enable_cuda_graph(False)
+
+
 def test_unet_is_deterministic_and_batch_independent():
     G = gold("unet_stdiff_fwd.pt")
     unet = make_ld("stdiff").model.diffusion_model.set_compute_dtype("bf16")
