@@ -16,7 +16,7 @@ CSRC_DIR = os.path.join(_HERE, "csrc")
 F32, BF16 = 0, 1
 ACT_NONE, ACT_SILU, ACT_GEGLU, ACT_RELU, ACT_SOFTMAX4 = 0, 1, 2, 3, 4
 IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05 = 0, 1, 2
-TC_OPT_CTA2, TC_OPT_WIDE, TC_OPT_RELAXED_WAIT, TC_OPT_BN, TC_OPT_GELU_ERF = 0, 1, 2, 3, 4
+TC_OPT_CTA2, TC_OPT_WIDE, TC_OPT_RELAXED_WAIT, TC_OPT_BN, TC_OPT_GELU_ERF, TC_OPT_STREAMK = 0, 1, 2, 3, 4, 5
 
 EXPORTS = [
     "ealdm_abi_version", "ealdm_last_error", "ealdm_device_check", "ealdm_launch_count", "ealdm_tc_set_option", "ealdm_set_pdl",

@@ -6,6 +6,8 @@
 // (PyTorch .grad semantics).
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace ealdm {
 namespace bwd {
 
@@ -515,6 +517,101 @@ colsum_final_kernel(const float* __restrict__ part, int chunks, int c, float* __
   }
 }
 
+// ---- the same in ONE launch (c % 4 == 0): a CTA sums 128 columns (4 per lane) of one row chunk, 8 rows at a time,
+// writes its partial, and the LAST CTA of a (segment, column block) to finish -- found with a ticket counter, no spinning
+// -- adds the partials in chunk order (fixed, so the sums are reproducible) and writes / accumulates the result.  The
+// 183 column sums of a training step were 2 launches each; the second one (~8 us of latency for a few KB) is gone.
+template <typename T>
+__global__ void __launch_bounds__(NT)
+colsum_ticket_kernel(const T* __restrict__ x, long long ld, long long rows_per_seg, int c, int rows_per_cta,
+                     float* __restrict__ part, unsigned int* __restrict__ tickets, float* __restrict__ out,
+                     long long ld_out, int accumulate) {
+  __shared__ float4 red[NT / 32][32];
+  __shared__ unsigned int ticket_s;
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  const int cb = blockIdx.x, chunk = blockIdx.y, seg = blockIdx.z;
+  const int chunks = gridDim.y;
+  const int col = cb * 128 + lane * 4;
+  const bool live = col < c;
+  const long long r0 = static_cast<long long>(chunk) * rows_per_cta;
+  const long long r1 = min(r0 + rows_per_cta, rows_per_seg);
+  const T* xb = x + static_cast<long long>(seg) * rows_per_seg * ld + col;
+  float s[4] = {0.f, 0.f, 0.f, 0.f};
+  if (live) {
+    constexpr int U = 8;
+    for (long long r = r0 + wp; r < r1; r += static_cast<long long>(U) * (NT / 32)) {
+      Vec4<T> q[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long rr = r + static_cast<long long>(u) * (NT / 32);
+        if (rr < r1) q[u].load(xb + rr * ld);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (r + static_cast<long long>(u) * (NT / 32) < r1) {
+          float f[4];
+          q[u].get(f);
+          s[0] += f[0]; s[1] += f[1]; s[2] += f[2]; s[3] += f[3];
+        }
+      }
+    }
+  }
+  red[wp][lane] = make_float4(s[0], s[1], s[2], s[3]);
+  __syncthreads();
+  float* pbase = part + (static_cast<long long>(seg) * gridDim.x + cb) * chunks * 128;
+  if (wp == 0) {
+    float4 a = red[0][lane];
+#pragma unroll
+    for (int k = 1; k < NT / 32; ++k) {
+      const float4 e = red[k][lane];
+      a.x += e.x; a.y += e.y; a.z += e.z; a.w += e.w;
+    }
+    __stcg(reinterpret_cast<float4*>(pbase + static_cast<long long>(chunk) * 128) + lane, a);
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) ticket_s = atomicAdd(tickets + seg * gridDim.x + cb, 1u);
+  }
+  __syncthreads();
+  if (ticket_s != static_cast<unsigned int>(chunks - 1)) return;
+  __threadfence();   // the last CTA: every partial of this (segment, column block) is visible
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int k = wp; k < chunks; k += NT / 32) {
+    const float4 e = __ldcg(reinterpret_cast<const float4*>(pbase + static_cast<long long>(k) * 128) + lane);
+    a.x += e.x; a.y += e.y; a.z += e.z; a.w += e.w;
+  }
+  __syncthreads();
+  red[wp][lane] = a;
+  __syncthreads();
+  if (wp == 0) {
+    a = red[0][lane];
+#pragma unroll
+    for (int k = 1; k < NT / 32; ++k) {
+      const float4 e = red[k][lane];
+      a.x += e.x; a.y += e.y; a.z += e.z; a.w += e.w;
+    }
+    if (live) {
+      float* o = out + static_cast<long long>(seg) * ld_out + col;
+      if (accumulate) { o[0] += a.x; o[1] += a.y; o[2] += a.z; o[3] += a.w; }
+      else { o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; }
+    }
+    if (lane == 0) tickets[seg * gridDim.x + cb] = 0u;   // re-armed for the next launch on this stream
+  }
+}
+static void colsum_ticket_chunking(long long segs, long long rows_per_seg, long long c, int* rows_per_cta,
+                                   long long* chunks) {
+  const long long cbs = ceil_div(c, 128);
+  long long ch = ceil_div(592, segs * cbs);   // ~4 CTAs per SM over all segments and column blocks
+  const long long max_chunks = ceil_div(rows_per_seg, 64);
+  if (ch > max_chunks) ch = max_chunks;
+  if (ch < 1) ch = 1;
+  const int rpc = static_cast<int>(ceil_div(rows_per_seg, ch));
+  *rows_per_cta = rpc;
+  *chunks = ceil_div(rows_per_seg, rpc);
+}
+constexpr int COLSUM_TICKETS = 1 << 16;
+static StreamScratch g_colsum_tickets(COLSUM_TICKETS * sizeof(unsigned int));   // see common.cuh
+static unsigned int* colsum_tickets(cudaStream_t st) { return static_cast<unsigned int*>(g_colsum_tickets.get(st)); }
+
 // ---- resampling adjoints ------------------------------------------------------------------------------------
 // z[n, 2*oh, 2*ow, :] = dy[n, oh, ow, :], zero elsewhere (adjoint of reading every second pixel)
 template <typename T>
@@ -766,9 +863,12 @@ extern "C" int ealdm_silu_bwd(const float* x, int64_t ld_x, const void* dy, int6
 extern "C" int64_t ealdm_colsum_workspace_bytes(int64_t segs, int64_t rows_per_seg, int64_t c) {
   if (segs <= 0 || rows_per_seg <= 0 || c <= 0) return 0;
   int ppc;
-  long long chunks;
+  long long chunks, chunks_t;
   bwd::colsum_chunking(segs, rows_per_seg, &ppc, &chunks);
-  return segs * chunks * c * 4;
+  bwd::colsum_ticket_chunking(segs, rows_per_seg, c, &ppc, &chunks_t);
+  const int64_t two_kernel = segs * chunks * c * 4;
+  const int64_t ticket = segs * ceil_div(c, 128) * chunks_t * 128 * 4;
+  return two_kernel > ticket ? two_kernel : ticket;
 }
 
 extern "C" int ealdm_colsum(const void* x, int64_t ld_x, int32_t dtype, int64_t segs, int64_t rows_per_seg, int64_t c,
@@ -779,9 +879,25 @@ extern "C" int ealdm_colsum(const void* x, int64_t ld_x, int32_t dtype, int64_t 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int ppc;
   long long chunks;
+  float* part = reinterpret_cast<float*>(workspace);
+  static const bool one_kernel = getenv("EALDM_COLSUM_TWO_KERNELS") == nullptr;
+  const long long cbs = ceil_div(c, 128);
+  if (one_kernel && c % 4 == 0 && segs * cbs <= bwd::COLSUM_TICKETS && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0) {
+    if (unsigned int* tickets = bwd::colsum_tickets(st)) {
+      bwd::colsum_ticket_chunking(segs, rows_per_seg, c, &ppc, &chunks);
+      dim3 grid(static_cast<unsigned>(cbs), static_cast<unsigned>(chunks), static_cast<unsigned>(segs));
+      if (dtype == EALDM_F32)
+        bwd::colsum_ticket_kernel<float><<<grid, bwd::NT, 0, st>>>(reinterpret_cast<const float*>(x), ld_x, rows_per_seg,
+                                                                   (int)c, ppc, part, tickets, out, ld_out, accumulate);
+      else
+        bwd::colsum_ticket_kernel<bf16><<<grid, bwd::NT, 0, st>>>(reinterpret_cast<const bf16*>(x), ld_x, rows_per_seg,
+                                                                  (int)c, ppc, part, tickets, out, ld_out, accumulate);
+      EALDM_LAUNCH_CHECK();
+      return 0;
+    }
+  }
   bwd::colsum_chunking(segs, rows_per_seg, &ppc, &chunks);
   dim3 grid(static_cast<unsigned>(chunks), static_cast<unsigned>(segs));
-  float* part = reinterpret_cast<float*>(workspace);
   if (dtype == EALDM_F32)
     bwd::colsum_partial_kernel<float><<<grid, bwd::NT, 0, st>>>(reinterpret_cast<const float*>(x), ld_x, rows_per_seg,
                                                                 (int)c, ppc, part);

@@ -10,6 +10,7 @@
 #include "../../include/ealdm_b200.h"
 
 #include <atomic>
+#include <mutex>
 
 namespace ealdm {
 
@@ -52,6 +53,55 @@ struct DeviceOnce {
   }
   bool pending() const { return ((bits.load(std::memory_order_acquire) >> device()) & 1ull) == 0; }
   void done() { bits.fetch_or(1ull << device(), std::memory_order_release); }
+};
+
+// ---- library-owned scratch that must start out zeroed (ticket counters, stream-K parking slots) ----------------------
+// One allocation per device, made on the first request that arrives OUTSIDE a stream capture and cut into SLOTS equal
+// slots; a stream gets the next free slot the first time it asks (pure bookkeeping, so it also works while the stream
+// is being captured -- a CUDA graph's kernels keep the slot of their capture stream).  Kernels that use a slot leave it
+// zeroed again.  Launches on different streams never share a slot; two graphs captured on the SAME stream do, and must
+// not be replayed concurrently.  nullptr (caller falls back to a path without scratch) if the pool cannot be created
+// now (first request inside a capture) or more than SLOTS streams asked.
+class StreamScratch {
+ public:
+  explicit StreamScratch(size_t slot_bytes) : slot_bytes_((slot_bytes + 255) & ~static_cast<size_t>(255)) {}
+  void* get(cudaStream_t st) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    std::lock_guard<std::mutex> lock(mu_);
+    Pool& p = pool_[dev];
+    if (!p.base) {
+      cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+      if (cudaStreamIsCapturing(st, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) {
+        cudaGetLastError();
+        return nullptr;
+      }
+      void* b = nullptr;
+      if (cudaMalloc(&b, slot_bytes_ * SLOTS) != cudaSuccess || cudaMemset(b, 0, slot_bytes_ * SLOTS) != cudaSuccess) {
+        cudaGetLastError();
+        if (b) cudaFree(b);
+        return nullptr;
+      }
+      p.base = static_cast<uint8_t*>(b);
+    }
+    for (int i = 0; i < p.used; ++i)
+      if (p.owner[i] == st) return p.base + i * slot_bytes_;
+    if (p.used == SLOTS) return nullptr;
+    p.owner[p.used] = st;
+    return p.base + (p.used++) * slot_bytes_;
+  }
+
+ private:
+  static constexpr int SLOTS = 6;
+  struct Pool {
+    uint8_t* base = nullptr;
+    int used = 0;
+    cudaStream_t owner[SLOTS];
+  };
+  size_t slot_bytes_;
+  std::mutex mu_;
+  Pool pool_[64];
 };
 
 // ---- programmatic dependent launch (PDL) -------------------------------------------------------------

@@ -121,6 +121,14 @@ struct Params {
   float ln_inv_c;   // 1 / (channels the LayerNorm runs over)
   float ln_eps;
   const float* ln_c1;
+  // stream-K over the tail of the tile list (CTA pairs, 256-column tiles): the k-blocks of the LAST sk_tiles work items
+  // are dealt evenly to the clusters, so that a launch of 1.73 waves costs 1.73 and not 2.  A cluster's share is
+  // [end of a tile | whole tiles | beginning of a tile]; it computes the BEGINNING first and parks that accumulator in
+  // `sk_ws` (fp32, exact), and the END last: its epilogue warps load the neighbour's parked accumulator into TMEM and
+  // the MMAs continue on it, so every output is the same k-ordered fp32 sum as without the split (bit-identical).
+  int sk_tiles;
+  float4* sk_ws;          // [cluster][CTA of the pair][32-column unit][8][128 rows] float4
+  unsigned int* sk_flags; // [cluster][CTA][epilogue warp]: 1 = parked (reset by the reader)
 };
 
 // CTA2: the tile is 256 x BN over a CTA pair (cta_group::2); each CTA stages its 128 A rows and BN/2 B rows
@@ -137,7 +145,7 @@ struct Cfg {
   static constexpr int BAR_OFF = BIAS_OFF + BIAS_BYTES;
   static constexpr int BAR_BYTES = 512;  // (2*STAGES + 8 + 2*EPI_WARPS) mbarriers + the TMEM base slot
   static constexpr int SMEM_BYTES = BAR_OFF + BAR_BYTES;
-  static_assert((2 * STAGES + 8 + 2 * EPI_WARPS) * 8 + 4 <= BAR_BYTES, "barrier block too small");
+  static_assert((2 * STAGES + 9 + 2 * EPI_WARPS) * 8 + 4 <= BAR_BYTES, "barrier block too small");
   static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KiB dynamic shared memory limit");
   static_assert(EPI_OFF % 1024 == 0 && EPI_WARP_BYTES % 1024 == 0 && BAR_OFF % 8 == 0, "alignment");
 };
@@ -252,7 +260,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   uint64_t* res_bar = tmem_empty + 2;  // [EPI_WARPS][2]
   uint64_t* ln_full = res_bar + 2 * EPI_WARPS;   // [2] row statistics of a folded LayerNorm, per accumulator stage
   uint64_t* ln_empty = ln_full + 2;              // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ln_empty + 2);
+  uint64_t* seed_bar = ln_empty + 2;             // stream-K: the accumulator of the resumed tile is loaded
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(seed_bar + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -284,6 +293,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       ptx::mbar_init(&ln_full[a], 1);
       ptx::mbar_init(&ln_empty[a], EPI_WARPS);
     }
+    ptx::mbar_init(seed_bar, CTA2 ? 2 * EPI_WARPS : EPI_WARPS);
     ptx::fence_mbar_init();
   }
   if (warp == 1) {
@@ -324,14 +334,51 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     int phase;
     tile_mnp(tile, mt, nt, phase);
   };
+  // work items of this CTA (pair), the same list in every role.  kind 0: a whole tile; stream-K (Params::sk_tiles):
+  // kind 1 = the first k-blocks of a tile (item 0: the accumulator is parked for the next cluster), kind 2 = the
+  // remaining k-blocks of the tile the previous cluster began (the last item: resumed from its parked accumulator)
+  int n_items, n_dp, n_full = 0, full0 = 0, head_tile = -1, head_kb1 = 0, tail_tile = -1, tail_kb0 = 0;
+  if (p.sk_tiles == 0) {
+    n_dp = tile_first < total_tiles ? (total_tiles - tile_first + tile_step - 1) / tile_step : 0;
+    n_items = n_dp;
+  } else {
+    const int dp_tiles = total_tiles - p.sk_tiles;   // a multiple of the number of clusters
+    n_dp = dp_tiles / tile_step;
+    const long long units = static_cast<long long>(p.sk_tiles) * kblocks_total;
+    const long long u0 = units * tile_first / tile_step, u1 = units * (tile_first + 1) / tile_step;
+    const int ta = static_cast<int>(u0 / kblocks_total), ka = static_cast<int>(u0 % kblocks_total);
+    const int tb = static_cast<int>(u1 / kblocks_total), kb_end = static_cast<int>(u1 % kblocks_total);
+    full0 = dp_tiles + ta;
+    if (ka > 0) { tail_tile = dp_tiles + ta; tail_kb0 = ka; ++full0; }
+    n_full = dp_tiles + tb - full0;
+    if (kb_end > 0) { head_tile = dp_tiles + tb; head_kb1 = kb_end; }
+    n_items = (head_tile >= 0 ? 1 : 0) + n_dp + n_full + (tail_tile >= 0 ? 1 : 0);
+  }
+  auto get_item = [&](int i, int& tile, int& kb0, int& kb1, int& kind) {
+    kb0 = 0;
+    kb1 = kblocks_total;
+    kind = 0;
+    if (head_tile >= 0) {
+      if (i == 0) { tile = head_tile; kb1 = head_kb1; kind = 1; return; }
+      --i;
+    }
+    if (i < n_dp) { tile = tile_first + i * tile_step; return; }
+    i -= n_dp;
+    if (i < n_full) { tile = full0 + i; return; }
+    tile = tail_tile;
+    kb0 = tail_kb0;
+    kind = 2;
+  };
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t full0 = CTA2 ? ptx::mapa_u32(&full_bar[0], 0) : 0u;  // the leader's full barriers
-      for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
+      const uint32_t full0b = CTA2 ? ptx::mapa_u32(&full_bar[0], 0) : 0u;  // the leader's full barriers
+      for (int item = 0; item < n_items; ++item) {
+        int tile, kb0, kb1, kind;
+        get_item(item, tile, kb0, kb1, kind);
         int mt, nt, uph;   // (`phase` is the mbarrier parity of the ring in this role)
         tile_mnp(tile, mt, nt, uph);
         const int tw = mt % p.tiles_w;
@@ -340,11 +387,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         // an upsampling phase shifts the 2x2 taps by (py, px) and selects its own K columns of W
         const int w0 = tw * p.bw + (uph & 1), h0 = th * p.bh + (uph >> 1), n0 = tn * p.bn;
         const int pkoff = uph * p.seg[0].kblocks * BK;
-        for (int s = 0; s < p.nseg; ++s) {
-          const Segment sg = p.seg[s];
-          const CUtensorMap* tmA = (s == 0) ? &tmA0 : &tmA1;
-          int tap = 0, cb = 0;
-          for (int kb = 0; kb < sg.kblocks; ++kb) {
+        // position of k-block kb0 in the walk over (segment, tap, channel block)
+        int s = 0, kb = kb0;   // kb: k-block inside the segment
+        if (kb >= p.seg[0].kblocks) { kb -= p.seg[0].kblocks; s = 1; }
+        Segment sg = p.seg[s];
+        const CUtensorMap* tmA = (s == 0) ? &tmA0 : &tmA1;
+        int tap = kb / sg.cblk, cb = kb - tap * sg.cblk;
+        for (int kbt = kb0; kbt < kb1; ++kbt, ++kb) {
+          if (kb == sg.kblocks) {   // (only ever from segment 0 into segment 1)
+            s = 1; sg = p.seg[1]; tmA = &tmA1; kb = 0; tap = 0; cb = 0;
+          }
+          {
             ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
             const int kh = tap / sg.ksize;
             const int kw = tap - kh * sg.ksize;
@@ -352,7 +405,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             if constexpr (CTA2) {
               // both CTAs' boxes complete on the LEADER's full barrier, which expects the bytes of the pair
               if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
-              const uint32_t fb = full0 + static_cast<uint32_t>(stage) * 8u;
+              const uint32_t fb = full0b + static_cast<uint32_t>(stage) * 8u;
               ptx::tma_load_4d_2sm(sa, tmA, fb, cb * BK, w0 * sg.stride + kw - sg.pad, h0 * sg.stride + kh - sg.pad,
                                    n0);
               if (p.b_mn) {
@@ -405,11 +458,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = tile_first; tile < total_tiles && leader; tile += tile_step) {
+    for (int item = 0; item < n_items && leader; ++item) {
+      int tile, kb0, kb1, kind;
+      get_item(item, tile, kb0, kb1, kind);
       ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
+      if (kind == 2) ptx::mbar_wait(seed_bar, 0);   // the parked accumulator is back in TMEM (both CTAs of a pair)
       ptx::tc_fence_after();
       const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
-      for (int kb = 0; kb < kblocks_total; ++kb) {
+      const uint32_t resumed = kind == 2 ? 1u : 0u;
+      for (int kbt = kb0; kbt < kb1; ++kbt) {
+        const int kb = (kbt - kb0) | static_cast<int>(resumed);   // 0 only for the MMA that starts a fresh accumulator
         ptx::mbar_wait(&full_bar[stage], phase);
         ptx::tc_fence_after();
         if (lane == 0) {
@@ -423,7 +481,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             for (int k = 0; k < BK / UMMA_K; ++k)
               ptx::umma_bf16_2sm(d_tmem, adesc + 2 * k, bdesc + bstep * k, idesc, (kb | k) != 0 ? 1u : 0u);
             ptx::umma_commit_2sm(&empty_bar[stage], 3);  // frees this stage in both CTAs
-            if (kb == kblocks_total - 1) ptx::umma_commit_2sm(&tmem_full[acc], 3);
+            if (kbt == kb1 - 1) ptx::umma_commit_2sm(&tmem_full[acc], 3);
           } else if (p.b_mn) {
             // MN-major B: 64-column groups 8192 B apart (LBO), 8-row K groups 1024 B apart; 16 K rows = 2048 B
             const uint64_t bdesc = ptx::make_sw128_mnmajor_desc(sa + C::A_BYTES, 8192);
@@ -440,7 +498,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           }
           if constexpr (!CTA2) {
             ptx::umma_commit(&empty_bar[stage]);
-            if (kb == kblocks_total - 1) ptx::umma_commit(&tmem_full[acc]);
+            if (kbt == kb1 - 1) ptx::umma_commit(&tmem_full[acc]);
           }
         }
         __syncwarp();
@@ -544,12 +602,95 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     }
     uint32_t tcount = 0;
     uint32_t it = 0;  // units processed by this warp: buffer = it & 1, mbarrier parity = (it >> 1) & 1
-    if (!GEGLU && p.has_res && lane == 0 && part < UNITS && tile_first < total_tiles)
-      issue_res(tile_first, part, 0);
+    const int first_epi = head_tile >= 0 ? 1 : 0;   // (a parked beginning of a tile has no epilogue)
+    if (!GEGLU && p.has_res && lane == 0 && part < UNITS && first_epi < n_items) {
+      int t0, a0, a1, a2;
+      get_item(first_epi, t0, a0, a1, a2);
+      issue_res(t0, part, 0);
+    }
+
+    // ---- stream-K: parking / resuming an accumulator (Params::sk_tiles) ----
+    // unit ku of the tile as [8][128 rows] float4: the thread that owns accumulator row r moves float4 j of its 32
+    // columns to / from entry j * 128 + r, so a warp instruction covers 512 contiguous bytes
+    constexpr int SK_CTA_F4 = (BN / 32) * 8 * BM;
+    auto sk_park = [&](uint32_t taddr) {   // this CTA's 128 x BN accumulator -> sk_ws slot of this cluster
+      float4* dst = p.sk_ws + static_cast<size_t>(tile_first * 2 + static_cast<int>(cta_rank)) * SK_CTA_F4 + quad * 32 + lane;
+#pragma unroll 1
+      for (int ku = part; ku < BN / 32; ku += 2) {
+        uint32_t v[32];
+        ptx::tmem_ld_32x32(taddr + ku * 32, v);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          __stcg(dst + (ku * 8 + j) * BM, make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                                      __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])));
+      }
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) {
+        unsigned int* fl = p.sk_flags + (tile_first * 2 + static_cast<int>(cta_rank)) * EPI_WARPS + ew;
+        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(fl), "r"(1u) : "memory");
+      }
+    };
+    auto sk_resume = [&](int item) {   // the previous cluster's parked accumulator -> TMEM stage of `item`
+      const int slot = (tile_first - 1) * 2 + static_cast<int>(cta_rank);
+      unsigned int* fl = p.sk_flags + slot * EPI_WARPS + ew;
+      if (lane == 0) {
+        unsigned int f;
+        do {
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(f) : "l"(fl) : "memory");
+        } while (f == 0u);
+      }
+      __syncwarp();
+      const float4* src = p.sk_ws + static_cast<size_t>(slot) * SK_CTA_F4 + quad * 32 + lane;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>((item & 1) * BN);
+#pragma unroll 1
+      for (int ku = part; ku < BN / 32; ku += 2) {
+        uint32_t v[32];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 t = __ldcg(src + (ku * 8 + j) * BM);
+          v[4 * j] = __float_as_uint(t.x); v[4 * j + 1] = __float_as_uint(t.y);
+          v[4 * j + 2] = __float_as_uint(t.z); v[4 * j + 3] = __float_as_uint(t.w);
+        }
+        ptx::tmem_st_32x32(taddr + ku * 32, v);
+      }
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        *reinterpret_cast<volatile unsigned int*>(fl) = 0u;   // (the next launch parks here again)
+        if constexpr (CTA2) ptx::mbar_arrive_cluster(ptx::mapa_u32(seed_bar, 0));
+        else ptx::mbar_arrive(seed_bar);
+      }
+    };
+    // the resumed tile is the LAST item; its TMEM stage is free once item (last - 2) has been drained, so the load
+    // runs at the top of iteration (last - 1), under that item's main loop -- unless that item is the parked beginning
+    // (two items in all): then right behind the parking, so that no cluster ever waits before it has parked its own
+    const int last = n_items - 1;
+    const int resume_top = tail_tile < 0 ? -1 : (last == 0 ? 0 : ((head_tile >= 0 && last == 1) ? -1 : last - 1));
+    const bool resume_after_park = tail_tile >= 0 && head_tile >= 0 && last == 1;
 
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
+    for (int item = 0; item < n_items; ++item) {
+      int tile, kb0_, kb1_, kind;
+      get_item(item, tile, kb0_, kb1_, kind);
+      if (kind == 1) {
+        ptx::mbar_wait(&tmem_full[acc], acc_phase);
+        ptx::tc_fence_after();
+        sk_park(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * BN));
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (CTA2) ptx::mbar_arrive_cluster(tmem_empty0 + static_cast<uint32_t>(acc) * 8u);
+          else ptx::mbar_arrive(&tmem_empty[acc]);
+        }
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+        if (resume_after_park) sk_resume(last);
+        continue;
+      }
       int nt, w, h, n;
       unit_origin(tile, nt, w, h, n);
       int uph = 0;   // upsampling phase (py, px) of this work item
@@ -578,6 +719,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         if (lane == 0) ptx::mbar_arrive(&ln_empty[acc]);
       }
       ptx::named_bar_sync(1, 32 * EPI_WARPS);
+      // (behind the barrier: every epilogue warp has finished reading the stage's previous accumulator)
+      if (item == resume_top) sk_resume(last);
       const float* bs = bias_s + acc * BN;
       const float* cs = c1_s + acc * BN;
       const float* rv = nullptr;
@@ -784,7 +927,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             else ptx::bulk_wait_read<0>();
             if (p.has_res) {
               if (ku + 2 < UNITS) issue_res(tile, ku + 2, b ^ 1);
-              else if (tile + tile_step < total_tiles) issue_res(tile + tile_step, part, b ^ 1);
+              else if (item + 1 < n_items) {
+                int t1, a0, a1, a2;
+                get_item(item + 1, t1, a0, a1, a2);
+                issue_res(t1, part, b ^ 1);
+              }
             }
           }
           __syncwarp();
@@ -1019,6 +1166,59 @@ static int launch_bn(const CUtensorMap* tm, const Params& p, const PhaseMaps& pm
   return 0;
 }
 
+// ---- stream-K (Params::sk_tiles) -----------------------------------------------------------------------
+// Workspace for the parked accumulators and their flags: a StreamScratch slot (common.cuh) -- per stream, zeroed at
+// creation and re-armed by the kernel; a launch that gets none runs the plain schedule (same bits).
+constexpr int SK_MAX_CLUSTERS = 80;
+constexpr size_t SK_WS_BYTES = static_cast<size_t>(SK_MAX_CLUSTERS) * 2 * (256 / 32) * 8 * BM * sizeof(float4);
+constexpr size_t SK_FLAG_BYTES = static_cast<size_t>(SK_MAX_CLUSTERS) * 2 * EPI_WARPS * sizeof(unsigned int);
+static StreamScratch g_sk_scratch(SK_WS_BYTES + SK_FLAG_BYTES);
+static int g_opt_sk = -1;
+static bool sk_workspace(int clusters, cudaStream_t st, float4** ws, unsigned int** flags) {
+  if (clusters > SK_MAX_CLUSTERS) return false;
+  uint8_t* base = static_cast<uint8_t*>(g_sk_scratch.get(st));
+  if (!base) return false;
+  *ws = reinterpret_cast<float4*>(base);
+  *flags = reinterpret_cast<unsigned int*>(base + SK_WS_BYTES);
+  return true;
+}
+
+// decide the stream-K region of a CTA-pair launch of `total` super-tiles on `clusters` clusters
+static void sk_plan(Params& p, int total, int clusters, cudaStream_t st) {
+  if (g_opt_sk < 0) {
+    const char* e = getenv("EALDM_TC_STREAMK");
+    g_opt_sk = e ? atoi(e) : 0;
+  }
+  p.sk_tiles = 0;
+  if (g_opt_sk == 2 && total > clusters && total % clusters != 0) {   // 2: whenever it applies (tests)
+    const int kb2 = p.seg[0].kblocks + (p.nseg > 1 ? p.seg[1].kblocks : 0);
+    float4* ws2 = nullptr;
+    unsigned int* fl2 = nullptr;
+    if (kb2 >= 2 && p.phases == 1 && !p.ln_in && !p.ln_out && !p.ln_gamma && !p.b_img && sk_workspace(clusters, st, &ws2, &fl2)) {
+      p.sk_tiles = clusters + total % clusters;
+      p.sk_ws = ws2;
+      p.sk_flags = fl2;
+    }
+    return;
+  }
+  const int rem = total % clusters;
+  const int kblocks = p.seg[0].kblocks + (p.nseg > 1 ? p.seg[1].kblocks : 0);
+  // worth it when the last wave leaves a good part of the device idle and a tile is long enough to split
+  // (measured at the 8x8 / 16x16 levels' shapes: timed alone, 3x3 convs of 144 k-blocks gain 3-4 % -- less than the
+  // 13 % of idle clusters, because a partly idle last wave also runs faster -- and a K = 1024 GEMM of 16 k-blocks LOSES
+  // 6 us to parking and resuming, hence the floor of 36 k-blocks = a 3x3 conv.  Inside the power-capped forward the
+  // gain is gone: 68.34 / 68.39 samples/s with, 68.45 without, SM clock 1700 against 1728 MHz -- busy SMs in the last
+  // wave are paid for in clock.  Hence opt-in: EALDM_TC_STREAMK=1.)
+  if (!g_opt_sk || total <= clusters || rem == 0 || rem * 8 > clusters * 7 || kblocks < 36) return;
+  if (p.phases != 1 || p.ln_in != nullptr || p.ln_out != nullptr || p.ln_gamma != nullptr || p.b_img) return;
+  float4* ws = nullptr;
+  unsigned int* flags = nullptr;
+  if (!sk_workspace(clusters, st, &ws, &flags)) return;
+  p.sk_tiles = clusters + rem;
+  p.sk_ws = ws;
+  p.sk_flags = flags;
+}
+
 // CTA pairs: a persistent grid of 2-CTA clusters, as many as the device can hold at once (one CTA per SM)
 template <int BN, int GEGLU>
 static int launch_pair(const CUtensorMap* tm, const Params& p, const PhaseMaps& pm, cudaStream_t st) {
@@ -1055,7 +1255,9 @@ static int launch_pair(const CUtensorMap* tm, const Params& p, const PhaseMaps& 
   const int clusters = total < max_clusters ? total : max_clusters;
   cfg.gridDim = dim3(2 * clusters);
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  EALDM_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, GEGLU, true>, tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], p, pm));
+  Params ps = p;
+  if constexpr (BN == 256 && GEGLU == 0) sk_plan(ps, total, clusters, st);
+  EALDM_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, GEGLU, true>, tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], ps, pm));
   EALDM_LAUNCH_CHECK();
   return 0;
 }
@@ -1074,12 +1276,23 @@ static void init_options() {
   g_opt[EALDM_TC_OPT_BN] = env_int("EALDM_TC_BN", 0);
   g_opt[EALDM_TC_OPT_GELU_ERF] = env_int("EALDM_TC_GELU_ERF", 0);
 }
+static void sk_init_option() {
+  if (g_opt_sk < 0) g_opt_sk = env_int("EALDM_TC_STREAMK", 0);
+}
 int get_option(int option) {
   init_options();
+  sk_init_option();
+  if (option == EALDM_TC_OPT_STREAMK) return g_opt_sk;
   return (option >= 0 && option <= 4) ? g_opt[option] : 0;
 }
 int set_option(int option, int value) {
   init_options();
+  sk_init_option();
+  if (option == EALDM_TC_OPT_STREAMK) {
+    const int prev = g_opt_sk;
+    g_opt_sk = value;
+    return prev;
+  }
   if (option < 0 || option > 4) return set_error(EALDM_EINVAL, "tcgen05 conv: unknown option %d", option);
   const int prev = g_opt[option];
   g_opt[option] = value;

@@ -642,7 +642,7 @@ class UNetEngine:
     def _out2(self, d: "Dual"):
         return None if d.h is d.f else d.h
 
-    def _res(self, d, x: "Dual", emb_all: torch.Tensor, dest: Optional["Dual"]) -> "Dual":
+    def _res(self, d, x: "Dual", emb_all: torch.Tensor, dest: Optional["Dual"], shadow: bool = True) -> "Dual":
         n, h, w = x.f.n, x.f.h, x.f.w
         hn = self._new(n, h, w, x.f.c)
         ops.group_norm(x.f, d["gn1"][0], d["gn1"][1], 1e-5, hn, self.stats, silu=True)
@@ -653,7 +653,15 @@ class UNetEngine:
                  rowvec_col0=d["emb_col0"])
         hn2 = self._new(n, h, w, d["cout"])
         ops.group_norm(h1, d["gn2"][0], d["gn2"][1], 1e-5, hn2, self.stats, silu=True)
-        out = dest if dest is not None else self._new_dual(n, h, w, d["cout"])
+        if dest is not None:
+            out = dest
+        elif shadow:
+            out = self._new_dual(n, h, w, d["cout"])
+        else:   # only the fp32 master is read downstream (GroupNorm + residual of a SpatialTransformer)
+            f = self._new(n, h, w, d["cout"], torch.float32)
+            if self.dt == torch.bfloat16:
+                f.with_gn_partial()
+            out = Dual(f, f)
         if d["skip"]:
             ops.conv([ConvIn(hn2, 3, 1, 1), ConvIn(x.h, 1, 1, 0)], d["conv2"].w, out.f, bias=d["conv2"].b,
                      out2=self._out2(out))
@@ -802,7 +810,10 @@ class UNetEngine:
             k = d["kind"]
             n, h, w = x.f.n, x.f.h, x.f.w
             if k == "res":
-                x = self._res(d, x, emb_all, dst)
+                # the bf16 operand shadow of the result is written only if the next layer reads it (a transformer
+                # block reads the fp32 master alone)
+                nxt = layers[i + 1]["kind"] if i + 1 < len(layers) else None
+                x = self._res(d, x, emb_all, dst, shadow=nxt not in ("st", "ab"))
             elif k == "st":
                 x = self._st(d, x, kv_all, n_ctx, dst)
             elif k == "ab":
@@ -842,8 +853,10 @@ class UNetEngine:
         first half of the batch (the second half holds the same images and timesteps; only the context differs)."""
         n2 = x.f.n // 2
         xh = Dual(x.f.images(0, n2), x.h.images(0, n2))
-        r = self._new_dual(x.f.n, x.f.h, x.f.w, layers[0]["cout"], gn=True)
-        rh = Dual(r.f.images(0, n2), r.h.images(0, n2))
+        rf = self._new(x.f.n, x.f.h, x.f.w, layers[0]["cout"], torch.float32).with_gn_partial()
+        r = Dual(rf, rf)      # (no bf16 shadow: the transformer block reads the fp32 master alone)
+        rv = rf.images(0, n2)
+        rh = Dual(rv, rv)
         self._res(layers[0], xh, emb_all[:n2], rh)
         return self._st(layers[1], rh, kv_all, n_ctx, dest, share_full=r)
 

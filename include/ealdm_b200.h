@@ -65,9 +65,15 @@ enum {
   EALDM_TC_OPT_RELAXED_WAIT = 2, /* EALDM_TC_RELAXED_WAIT: 1 (default) one TMA store group may stay in flight */
   EALDM_TC_OPT_BN = 3,           /* EALDM_TC_BN: 0 (default) N tile chosen by wave count, 128 / 256 forced (for
                                     n_out > 128), so that small test problems reach the 256-wide paths */
-  EALDM_TC_OPT_GELU_ERF = 4      /* EALDM_TC_GELU_ERF: the ONE switch that changes results (by <= 4.7e-4 absolute per
+  EALDM_TC_OPT_GELU_ERF = 4,     /* EALDM_TC_GELU_ERF: the ONE switch that changes results (by <= 4.7e-4 absolute per
                                     gated activation): 0 (default) GEGLU epilogues evaluate GELU in its tanh form on the
                                     hardware tanh, 1 the exact-erf form (rational approximation, error 1.7e-6) */
+  EALDM_TC_OPT_STREAMK = 5       /* EALDM_TC_STREAMK: 0 (default) off; 1 CTA-pair launches of 3x3 convolutions whose last
+                                    wave would leave more than 1/8 of the clusters idle deal the k-blocks of their last
+                                    (clusters + remainder) tiles evenly to the clusters (a split tile is resumed from
+                                    its parked fp32 accumulator: results bit-identical to the unsplit schedule);
+                                    measured +3-4 % on such a launch timed alone and neutral inside the power-capped
+                                    forward, hence opt-in; 2 whenever there is a remainder (tests) */
 };
 int ealdm_tc_set_option(int option, int value);
 /*

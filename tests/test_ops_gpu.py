@@ -619,6 +619,87 @@ def test_conv_cta_pairs_match_single_cta(n, c, h, w, co, res, bn):
     assert torch.equal(outs[0], outs[1])
 
 
+@pytest.mark.parametrize("n,c,h,w,co,feat", [
+    (128, 128, 8, 8, 1024, "rowvec"),        # 128 super-tiles on 74 clusters (the 8x8 level's shape): 1.73 tiles each
+    (40, 128, 16, 16, 512, "res+out2+gn"),   # 80 super-tiles: remainder 6, every cluster parks and resumes
+    (64, 128, 16, 16, 1024, "skip1x1"),      # 256 super-tiles: two whole waves + a dealt tail, two K segments
+    (76, 128, 8, 8, 512, "res"),             # 19 x 2 = 38 < clusters: stream-K must decline
+    (152, 128, 8, 8, 512, "plain"),          # 38 x 2 = 76 super-tiles: remainder 2
+])
+def test_conv_stream_k_is_bit_identical(n, c, h, w, co, feat):
+    """Stream-K over the tail of the tile list (ealdm_tc_set_option STREAMK): the k-blocks of the last (clusters +
+    remainder) super-tiles are dealt evenly; a split tile is begun by one cluster (accumulator parked in fp32) and
+    resumed by the next from that accumulator, so the fp32 sums keep their k order.  Must equal the plain CTA-pair
+    schedule bit for bit with every epilogue feature, run after run (the parking flags are re-armed by the reader)."""
+    dtype = torch.bfloat16
+    x = torch.randn(n, c, h, w, generator=g(170)).to(DEV)
+    wt = (torch.randn(co, c, 3, 3, generator=g(171)) / math.sqrt(9 * c)).to(DEV)
+    b = torch.randn(co, generator=g(172)).to(DEV)
+    xa = to_act(x, dtype)
+    kw, srcs, wp = {}, [ConvIn(xa, 3, 1, 1)], pack_w(wt, dtype)
+    if "res" in feat:
+        kw["residual"] = to_act(torch.randn(n, co, h, w, generator=g(173)).to(DEV), torch.float32)
+    if "rowvec" in feat:
+        kw["rowvec"] = torch.randn(n, co, generator=g(174)).to(DEV)
+    if "skip1x1" in feat:
+        xs = to_act(torch.randn(n, 192, h, w, generator=g(175)).to(DEV), dtype)
+        ws = (torch.randn(co, 192, 1, 1, generator=g(176)) / math.sqrt(192)).to(DEV)
+        srcs.append(ConvIn(xs, 1, 1, 0))
+        wp = torch.cat([wp, pack_w(ws, dtype)], dim=1).contiguous()
+    outs = []
+    for mode in (0, 2, 2, 1):
+        out = Act.empty(n, h, w, co, torch.float32, DEV)
+        if "gn" in feat:
+            out.with_gn_partial()
+        o2 = Act.empty(n, h, w, co, dtype, DEV) if "out2" in feat else None
+        with _tc_option(L.TC_OPT_STREAMK, mode, bn=256):
+            ops.conv(srcs, wp, out, bias=b, out2=o2, impl=L.IMPL_TCGEN05, **kw)
+        torch.cuda.synchronize()
+        outs.append((from_act(out), None if o2 is None else from_act(o2), None if out.gp is None else out.gp.clone()))
+    for o in outs[1:]:
+        assert torch.equal(o[0], outs[0][0])
+        assert (o[1] is None) or torch.equal(o[1], outs[0][1])
+        assert (o[2] is None) or torch.equal(o[2], outs[0][2])
+    if feat in ("plain", "rowvec"):
+        ref = F.conv2d(from_act(xa), wt.to(dtype).float(), b, padding=1)
+        if "rowvec" in feat:
+            ref = ref + kw["rowvec"][:, :, None, None]
+        assert rel_l2(outs[1][0], ref) < 2e-5
+
+
+def test_linear_and_dgrad_stream_k_are_bit_identical():
+    """The same for a K = 1024 linear layer with the fp32 residual stream (the 8x8 level's out-projection) and for the
+    data-gradient mode (MN-major B operand, taps walked backwards)."""
+    dtype = torch.bfloat16
+    M, K, N = 8192 + 1024, 1024, 1024     # 36 x 4 = 144 super-tiles
+    x = Act(torch.randn(M, K, generator=g(180)).to(DEV).to(dtype), 1, 1, M)
+    w = (torch.randn(N, K, generator=g(181)) / math.sqrt(K)).to(DEV).to(dtype)
+    b = torch.randn(N, generator=g(182)).to(DEV)
+    res = Act(torch.randn(M, N, generator=g(183)).to(DEV), 1, 1, M)
+    outs = []
+    for mode in (0, 2, 2):
+        out = Act.empty(1, 1, M, N, torch.float32, DEV)
+        o2 = Act.empty(1, 1, M, N, dtype, DEV)
+        with _tc_option(L.TC_OPT_STREAMK, mode, bn=256):
+            ops.linear(x, w, out, bias=b, residual=res, out2=o2)
+        torch.cuda.synchronize()
+        outs.append((out.buf.clone(), o2.buf.clone()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    assert torch.equal(outs[0][0], outs[2][0])
+    n, c, h, w_, co = 160, 512, 8, 8, 128    # dX [160, 8, 8, 512]: 40 x 2 super-tiles of the adjoint GEMM, K = 1152
+    wt = (torch.randn(co, c, 3, 3, generator=g(184)) / math.sqrt(9 * c)).to(DEV).to(dtype)
+    dya = to_act(torch.randn(n, co, h, w_, generator=g(185)).to(DEV), dtype)
+    packed = wt.permute(0, 2, 3, 1).reshape(co, -1).contiguous()
+    douts = []
+    for mode in (0, 2):
+        dx = Act.empty(n, h, w_, c, torch.float32, DEV)
+        with _tc_option(L.TC_OPT_STREAMK, mode, bn=256):
+            ops.conv([ConvIn(dya, 3, 1, 1)], packed, dx, adjoint=True)
+        torch.cuda.synchronize()
+        douts.append(from_act(dx))
+    assert torch.equal(douts[0], douts[1])
+
+
 @pytest.mark.parametrize("M,K,N", [(4096, 1024, 512), (2048, 2048, 1024)])
 def test_geglu_cta_pairs_match_single_cta(M, K, N):
     from ealdm_b200.packing import geglu_interleave
