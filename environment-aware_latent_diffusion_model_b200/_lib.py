@@ -55,7 +55,8 @@ class ConvArgs(C.Structure):
                 ("ln_partial_out", C.c_void_p), ("ln_partial_in", C.c_void_p), ("ln_parts_in", C.c_int64),
                 ("ln_c1", C.c_void_p), ("ln_channels", C.c_int64), ("ln_eps", C.c_float), ("wi_tokens", C.c_int32),
                 ("wi_heads", C.c_int32), ("gn_unit", C.c_int32), ("wi_ld", C.c_int64), ("wi_head_stride", C.c_int64),
-                ("ln_gamma", C.c_void_p), ("ln_beta", C.c_void_p)]
+                ("ln_gamma", C.c_void_p), ("ln_beta", C.c_void_p), ("gn_gamma", C.c_void_p), ("gn_beta", C.c_void_p),
+                ("gn_eps", C.c_float), ("gn_groups", C.c_int32), ("gn_silu", C.c_int32), ("gn_only", C.c_int32)]
 
 
 class GroupNormArgs(C.Structure):

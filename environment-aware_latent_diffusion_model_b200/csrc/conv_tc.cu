@@ -121,6 +121,25 @@ struct Params {
   float ln_inv_c;   // 1 / (channels the LayerNorm runs over)
   float ln_eps;
   const float* ln_c1;
+  // GroupNorm (+ SiLU) APPLIED by the producing epilogue (ealdm_conv_args::gn_gamma; 256-column tiles).  Pass 1 is the
+  // usual epilogue: it writes the {sum, sum of squares} partials of its [32 pixels x 8 channels] blocks (gn_partial) and
+  // -- unless gna_only -- the fp32 result, and stores the result back over its TMEM accumulator.  Every epilogue warp
+  // then counts itself in at the (image, N tile) its 32 rows belong to and waits until the image's other tiles -- in
+  // flight on neighbouring CTAs, or the next items of CTAs that do not wait for this one -- have counted in too
+  // (gna_expected warps); pass 2 folds the image's partials (fp64, chunk order), and writes
+  // act((x - mean) rstd gamma + beta) as bf16 through tmOut2 (gna_only: through tmOut -- the un-normalised tensor is
+  // never written).  The counters return to zero with the last reader.  The stand-alone GroupNorm pass over the tensor
+  // (and, with gna_only, the tensor itself) disappears.
+  const float* gna_gamma;
+  const float* gna_beta;
+  float gna_eps;
+  int gna_silu;
+  int gna_only;
+  int gna_debug;              // timing experiments (EALDM_GNA_DEBUG): 1 no wait, 2 no fold, 4 no pass 2, 8 no count-in
+  int gna_octets;             // channel octets per group: 1, 2 or 4
+  double gna_inv_count;       // 1 / (pixels per image * channels per group)
+  unsigned int gna_expected;  // epilogue warps per (image, N tile): 2 * pixels per image / 32
+  unsigned int* gna_counters; // [image][N tile]{counted in, read}
   // stream-K over the tail of the tile list (CTA pairs, 256-column tiles): the k-blocks of the LAST sk_tiles work items
   // are dealt evenly to the clusters, so that a launch of 1.73 waves costs 1.73 and not 2.  A cluster's share is
   // [end of a tile | whole tiles | beginning of a tile]; it computes the BEGINNING first and parks that accumulator in
@@ -1024,6 +1043,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
               gn_partial_unit(p, r, lane, (n - sn0) + my_dn < p.Nimg, n, h, w, nt * BN + ku * 32,
                               uph * p.gn_phase_chunks);
           }
+          if constexpr (BN == 256 && !GEGLU) {
+            if (p.gna_gamma != nullptr) {   // GroupNorm applied here, pass 1: the result back over the accumulator
+              uint32_t u[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) u[j] = __float_as_uint(r[j]);
+              ptx::tmem_st_32x32(taddr0 + ku * 32, u);
+              if (p.gna_only) {   // (no un-normalised output at all)
+                ++it;
+                continue;
+              }
+            }
+          }
           if (p.out_f32) sts_row_f32(eb, lane, r);
           else sts_row_bf16(eb, lane, r);
           if (p.has_out2) sts_row_bf16(o2buf, lane, r);
@@ -1095,6 +1126,124 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           }
         }
       }
+      if constexpr (BN == 256 && !GEGLU) {
+        if (p.gna_gamma != nullptr) {
+          // ---- GroupNorm applied here, pass 2 (Params::gna_gamma) ----
+          ptx::tmem_st_wait();
+          __threadfence();      // this warp's partials are visible before it counts itself in
+          __syncwarp();
+          if (n < p.Nimg) {     // (n: the image of this warp's 32 rows)
+            unsigned int* cnt = p.gna_counters + 2 * (static_cast<size_t>(n) * p.n_tiles + nt);
+            // lane = channel octet of this tile's 256 columns; its gamma / beta are requested before the wait
+            const int oct = nt * (BN / 8) + lane;
+            const bool live = oct * 8 < p.N;
+            float4 gq[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)}, bq[2] = {gq[0], gq[0]};
+            if (live) {
+              gq[0] = __ldg(reinterpret_cast<const float4*>(p.gna_gamma + oct * 8));
+              gq[1] = __ldg(reinterpret_cast<const float4*>(p.gna_gamma + oct * 8) + 1);
+              bq[0] = __ldg(reinterpret_cast<const float4*>(p.gna_beta + oct * 8));
+              bq[1] = __ldg(reinterpret_cast<const float4*>(p.gna_beta + oct * 8) + 1);
+            }
+            if (lane == 0 && !(p.gna_debug & 8)) {
+              unsigned int f = atomicAdd(cnt, 1u) + 1u, spins = 0;
+              while (f < p.gna_expected && !(p.gna_debug & 1)) {
+                __nanosleep(200);   // (a busy spin measurably slows the MMA / TMA warps of the same CTA)
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(f) : "l"(cnt) : "memory");
+                if (++spins > (1u << 27)) {
+                  printf("ealdm: GroupNorm epilogue waited too long for image %d\n", n);
+                  __trap();
+                }
+              }
+              __threadfence();   // (the counter was read with acquire semantics in the loop; this covers the atomic's value)
+            }
+            __syncwarp();
+            // fold the octet's partials over the image's 32-pixel chunks
+            double s = 0.0, ss = 0.0;
+            if (live && !(p.gna_debug & 2)) {
+              const float2* pp = p.gn_partial + static_cast<long long>(n) * p.gn_chunks * p.gn_ld + oct;
+              // sixteen loads in flight per round (one L2 round trip per round, not per chunk); chunk order kept
+              for (int c0 = 0; c0 < p.gn_chunks; c0 += 16) {
+                float2 t[16];
+#pragma unroll
+                for (int u = 0; u < 16; ++u)
+                  t[u] = c0 + u < p.gn_chunks ? __ldcg(pp + static_cast<long long>(c0 + u) * p.gn_ld) : make_float2(0.f, 0.f);
+#pragma unroll
+                for (int u = 0; u < 16; ++u) {
+                  s += static_cast<double>(t[u].x);
+                  ss += static_cast<double>(t[u].y);
+                }
+              }
+            }
+            for (int d = 1; d < p.gna_octets; d <<= 1) {   // the octets of one group, lower octet first
+              const double os = __shfl_xor_sync(0xffffffffu, s, d), oss = __shfl_xor_sync(0xffffffffu, ss, d);
+              s = (lane & d) ? os + s : s + os;
+              ss = (lane & d) ? oss + ss : ss + oss;
+            }
+            const double mean = s * p.gna_inv_count;
+            double var = ss * p.gna_inv_count - mean * mean;
+            if (var < 0.0) var = 0.0;
+            const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(p.gna_eps)));
+            const float mu = static_cast<float>(mean);
+            float2* const tab = reinterpret_cast<float2*>(o2buf);   // [256 columns]{scale, shift} (no shadow output here)
+            if (live) {
+              const float gv[8] = {gq[0].x, gq[0].y, gq[0].z, gq[0].w, gq[1].x, gq[1].y, gq[1].z, gq[1].w};
+              const float bv[8] = {bq[0].x, bq[0].y, bq[0].z, bq[0].w, bq[1].x, bq[1].y, bq[1].z, bq[1].w};
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float a = rstd * gv[j];
+                tab[lane * 8 + j] = make_float2(a, fmaf(-mu, a, bv[j]));
+              }
+            }
+            __syncwarp();
+            if (lane == 0 && !(p.gna_debug & 8) && atomicAdd(cnt + 1, 1u) == p.gna_expected - 1u) {   // the last reader re-arms the pair
+              cnt[1] = 0u;
+              __threadfence();
+              cnt[0] = 0u;
+            }
+            const CUtensorMap* const tmN = p.gna_only ? &tmOut : &tmOut2;
+            uint8_t* const fb = ebuf + ((it - 1u) & 1u) * EBUF_BYTES;   // (staging as in the LayerNorm pass 2)
+            if (lane == 0) ptx::bulk_wait_read<0>();
+            __syncwarp();
+            uint32_t vv[2][32];
+            ptx::tmem_ld_32x32(taddr0 + part * 32, vv[0]);
+#pragma unroll
+            for (int ui = 0; ui < UNITS / 2; ++ui) {
+              const int ku = part + 2 * ui;
+              ptx::tmem_ld_wait();
+              if (ui + 1 < UNITS / 2) ptx::tmem_ld_32x32(taddr0 + (ku + 2) * 32, vv[(ui + 1) & 1]);
+              if (p.gna_debug & 4) continue;
+              const uint32_t(&v)[32] = vv[ui & 1];
+              float y[32];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const float4 c2 = *reinterpret_cast<const float4*>(tab + ku * 32 + 2 * j);   // two columns' {scale, shift}
+                y[2 * j] = fmaf(__uint_as_float(v[2 * j]), c2.x, c2.y);
+                y[2 * j + 1] = fmaf(__uint_as_float(v[2 * j + 1]), c2.z, c2.w);
+              }
+              if (p.gna_silu) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {   // x sigmoid(x) = 0.5 x (1 + tanh(0.5 x)): one MUFU per element
+                  const float hx = 0.5f * y[j];
+                  y[j] = fmaf(hx, tanh_approx(hx), hx);
+                }
+              }
+              uint8_t* const sb = fb + (ui & 1) * O2BUF_BYTES;
+              if (ui >= 2) {   // the store issued two units ago has read this half
+                if (lane == 0) ptx::bulk_wait_read<1>();
+                __syncwarp();
+              }
+              sts_row_bf16(sb, lane, y);
+              ptx::fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) {
+                ptx::tma_store_4d(tmN, sb, nt * BN + ku * 32, w, h, n);
+                ptx::bulk_commit();
+              }
+            }
+          }
+        }
+      }
+      if (p.gna_debug >= 1000) __nanosleep(static_cast<unsigned>(p.gna_debug));   // timing experiment: a longer epilogue
       ++tcount;
       ptx::tc_fence_before();
       __syncwarp();
@@ -1149,6 +1298,8 @@ static int pow2_ceil(long long v) {
   return p;
 }
 
+static int env_int(const char* name, int dflt);
+
 template <int BN, int GEGLU>
 static int launch_bn(const CUtensorMap* tm, const Params& p, const PhaseMaps& pm, cudaStream_t st) {
   using C = Cfg<BN>;
@@ -1183,6 +1334,10 @@ static bool sk_workspace(int clusters, cudaStream_t st, float4** ws, unsigned in
   return true;
 }
 
+// {counted in, read} counters of the GroupNorm epilogue (Params::gna_counters), per stream, zero between launches
+constexpr size_t GNA_COUNTER_BYTES = 1 << 18;
+static StreamScratch g_gna_counters(GNA_COUNTER_BYTES);
+
 // decide the stream-K region of a CTA-pair launch of `total` super-tiles on `clusters` clusters
 static void sk_plan(Params& p, int total, int clusters, cudaStream_t st) {
   if (g_opt_sk < 0) {
@@ -1194,7 +1349,7 @@ static void sk_plan(Params& p, int total, int clusters, cudaStream_t st) {
     const int kb2 = p.seg[0].kblocks + (p.nseg > 1 ? p.seg[1].kblocks : 0);
     float4* ws2 = nullptr;
     unsigned int* fl2 = nullptr;
-    if (kb2 >= 2 && p.phases == 1 && !p.ln_in && !p.ln_out && !p.ln_gamma && !p.b_img && sk_workspace(clusters, st, &ws2, &fl2)) {
+    if (kb2 >= 2 && p.phases == 1 && !p.ln_in && !p.ln_out && !p.ln_gamma && !p.gna_gamma && !p.b_img && sk_workspace(clusters, st, &ws2, &fl2)) {
       p.sk_tiles = clusters + total % clusters;
       p.sk_ws = ws2;
       p.sk_flags = fl2;
@@ -1210,7 +1365,7 @@ static void sk_plan(Params& p, int total, int clusters, cudaStream_t st) {
   // gain is gone: 68.34 / 68.39 samples/s with, 68.45 without, SM clock 1700 against 1728 MHz -- busy SMs in the last
   // wave are paid for in clock.  Hence opt-in: EALDM_TC_STREAMK=1.)
   if (!g_opt_sk || total <= clusters || rem == 0 || rem * 8 > clusters * 7 || kblocks < 36) return;
-  if (p.phases != 1 || p.ln_in != nullptr || p.ln_out != nullptr || p.ln_gamma != nullptr || p.b_img) return;
+  if (p.phases != 1 || p.ln_in != nullptr || p.ln_out != nullptr || p.ln_gamma != nullptr || p.gna_gamma != nullptr || p.b_img) return;
   float4* ws = nullptr;
   unsigned int* flags = nullptr;
   if (!sk_workspace(clusters, st, &ws, &flags)) return;
@@ -1375,6 +1530,18 @@ bool supported(const ealdm_conv_args* a) {
         a->ln_partial_in || a->ln_partial_out || a->gn_partial || (a->wi_tokens && !a->weight_adjoint))
       return false;
   }
+  if (a->gn_gamma) {
+    // GroupNorm applied by the epilogue: 256-column tiles, groups of 8 / 16 / 32 channels inside one tile, the 32 rows
+    // of an epilogue warp inside one image, partial statistics as channel octets
+    if (!a->gn_beta || !a->gn_partial || (a->gn_unit != 0 && a->gn_unit != 8) || a->gn_groups < 1) return false;
+    if (a->n_out < 256 || a->n_out % a->gn_groups != 0) return false;
+    const long long cg = a->n_out / a->gn_groups;
+    if (cg != 8 && cg != 16 && cg != 32) return false;
+    if (a->act != EALDM_ACT_NONE || a->upsample_phases || a->wi_tokens || a->ln_gamma || a->ln_partial_in ||
+        a->ln_partial_out || (a->h_out * a->w_out) % 32 != 0)
+      return false;
+    if (a->gn_only ? (a->out_f32 || a->out2) : (!a->out2)) return false;
+  }
   if (a->gn_partial) {
     const long long hw = a->h_out * a->w_out;
     if (a->gn_unit != 0 && a->gn_unit != 8 && a->gn_unit != 4) return false;
@@ -1438,6 +1605,7 @@ static int choose_bn(const ealdm_conv_args* a, long long m_work) {
   init_options();
   const bool geglu = a->act == EALDM_ACT_GEGLU;
   if (a->ln_gamma) return 256;   // LayerNorm in the epilogue needs the whole row in one tile
+  if (a->gn_gamma) return 256;   // GroupNorm in the epilogue: written for the 256-column tile
   if (a->n_out <= 32 && !geglu && !a->weight_adjoint) return 32;
   if (a->n_out <= 128) return 128;
   const long long t256 = m_work * ceil_div(a->n_out, 256);
@@ -1565,7 +1733,7 @@ int launch(const ealdm_conv_args* a, cudaStream_t st) {
   const long long out_cols = geglu ? a->n_out / 2 : a->n_out;
   // (measured: the GEGLU pass gains 3 % at K = 256 and loses 4 % at K >= 512, where the stores of the narrow units
   // overlap the longer main loop better)
-  const bool wide = g_opt[EALDM_TC_OPT_WIDE] != 0 && BN == 256 && !phased && !a->ln_partial_out && !a->ln_gamma &&
+  const bool wide = g_opt[EALDM_TC_OPT_WIDE] != 0 && BN == 256 && !phased && !a->ln_partial_out && !a->ln_gamma && !a->gn_gamma &&
                     (geglu ? a->k_total <= 256 : (!a->residual && !a->out2));
   PhaseMaps pm;
   memset(&pm, 0, sizeof(pm));
@@ -1602,7 +1770,26 @@ int launch(const ealdm_conv_args* a, cudaStream_t st) {
   p.out_f32 = a->out_f32;
   p.has_res = a->residual != nullptr;
   p.res_f32 = a->res_f32;
-  p.has_out2 = a->out2 != nullptr && !a->ln_gamma;
+  p.has_out2 = a->out2 != nullptr && !a->ln_gamma && !a->gn_gamma;
+  p.gna_debug = env_int("EALDM_GNA_DEBUG", 0);
+  if (a->gn_gamma) {
+    const long long hw = a->h_out * a->w_out, cg = a->n_out / a->gn_groups;
+    const long long entries = static_cast<long long>(p.Nimg) * p.n_tiles * 2;
+    EALDM_REQUIRE(entries * 4 <= static_cast<long long>(GNA_COUNTER_BYTES), "tcgen05 conv: too many images for the GroupNorm epilogue");
+    unsigned int* counters = static_cast<unsigned int*>(g_gna_counters.get(st));
+    EALDM_REQUIRE(counters != nullptr, "tcgen05 conv: no counter scratch for the GroupNorm epilogue on this stream (first "
+                                       "use inside a stream capture, or too many streams)");
+    p.gna_gamma = a->gn_gamma;
+    p.gna_beta = a->gn_beta;
+    p.gna_eps = a->gn_eps;
+    p.gna_silu = a->gn_silu;
+    p.gna_only = a->gn_only;
+    p.gna_debug = env_int("EALDM_GNA_DEBUG", 0);
+    p.gna_octets = static_cast<int>(cg / 8);
+    p.gna_inv_count = 1.0 / static_cast<double>(hw * cg);
+    p.gna_expected = static_cast<unsigned int>(2 * hw / 32);
+    p.gna_counters = counters;
+  }
   p.ln_gamma = a->ln_gamma;
   p.ln_beta = a->ln_beta;
   p.ln_apply_eps = a->ln_eps;

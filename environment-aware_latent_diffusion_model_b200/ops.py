@@ -37,7 +37,7 @@ class Act:
     [n*h*w/32, ld/8, 2] fp32 = {sum, sum of squares} per (32-pixel chunk, 8-channel octet): a tcgen05 convolution
     that writes this activation fills its column window of `gp`, and a GroupNorm that reads the activation then
     skips its statistics pass."""
-    __slots__ = ("buf", "n", "h", "w", "c", "c0", "gp", "ln", "gunit", "lny")
+    __slots__ = ("buf", "n", "h", "w", "c", "c0", "gp", "ln", "gunit", "lny", "gny")
 
     def __init__(self, buf: torch.Tensor, n: int, h: int, w: int, c: Optional[int] = None, c0: int = 0,
                  gp: Optional[torch.Tensor] = None):
@@ -50,6 +50,7 @@ class Act:
         self.gp = gp
         self.gunit = 8      # channels per entry of `gp`: octets, or quads for GroupNorm groups of 4 channels
         self.lny = None     # LayerNorm(self) written by the producing GEMM's epilogue (conv(..., ln_apply=...))
+        self.gny = None     # GroupNorm(self) written by the producing conv's epilogue (conv(..., gn_apply=...))
         self.ln = None      # [rows, parts, 2] row {sum, sum of squares} partials written by the producing GEMM (ln_stats)
 
     @staticmethod
@@ -127,7 +128,7 @@ def conv(srcs: Sequence[ConvIn], weight: torch.Tensor, out: Act, *, bias: Option
          rowvec: Optional[torch.Tensor] = None, rowvec_col0: int = 0, residual: Optional[Act] = None,
          act: int = L.ACT_NONE, impl: int = L.IMPL_AUTO, out2: Optional[Act] = None, adjoint: bool = False,
          upsample_phases: bool = False, ln_stats: bool = False, ln: Optional[tuple] = None,
-         wimg: Optional[tuple] = None, ln_apply: Optional[tuple] = None) -> Act:
+         wimg: Optional[tuple] = None, ln_apply: Optional[tuple] = None, gn_apply: Optional[tuple] = None) -> Act:
     """ealdm_conv: out = epilogue(sum_s im2col(src_s) @ weight[:, seg_s]^T). `weight` is [n_out, k_total].
     adjoint=True: data gradient of a forward layer -- `weight` is that layer's own packed matrix
     [src channels, ksize^2 * out.c] (may be a column window of a wider matrix); nothing is transposed or flipped."""
@@ -206,6 +207,17 @@ def conv(srcs: Sequence[ConvIn], weight: torch.Tensor, out: Act, *, bias: Option
         assert out2 is not None and a.out_f32 and act == L.ACT_NONE and out.c == 256
         assert gamma.dtype == torch.float32 and beta.dtype == torch.float32 and gamma.numel() == 256 == beta.numel()
         a.ln_gamma, a.ln_beta, a.ln_eps = gamma.data_ptr(), beta.data_ptr(), eps
+        a.impl = L.IMPL_TCGEN05
+    if gn_apply is not None:
+        # GroupNorm (+ SiLU) applied by the epilogue: gn_apply = (gamma, beta, eps, groups, silu, only).  only=False: `out`
+        # (fp32) as usual and `out2` (bf16) = act(GroupNorm(out)); only=True: `out` (bf16) = act(GroupNorm(result)) and
+        # the result itself is never written.  `out.gp` (with_gn_partial) carries the statistics between the passes.
+        gamma, beta, eps, groups, silu, only = gn_apply
+        assert out.gp is not None and out.gunit == 8 and act == L.ACT_NONE and ln_apply is None
+        assert gamma.dtype == torch.float32 and beta.dtype == torch.float32 and gamma.numel() == out.c == beta.numel()
+        assert (out2 is None and not a.out_f32) if only else (out2 is not None)
+        a.gn_gamma, a.gn_beta, a.gn_eps = gamma.data_ptr(), beta.data_ptr(), eps
+        a.gn_groups, a.gn_silu, a.gn_only = groups, int(bool(silu)), int(bool(only))
         a.impl = L.IMPL_TCGEN05
     if out.gp is not None:     # the epilogue also produces the GroupNorm partial statistics of `out`
         assert x0.dtype == torch.bfloat16 and act != L.ACT_GEGLU

@@ -424,6 +424,10 @@ class UNetEngine:
     _collapse_xattn = not os.environ.get("EALDM_NO_XATTN_COLLAPSE")
     # LayerNorm applied by the epilogue of the GEMM that produces its input (width 256: a CTA holds whole rows); A/B switch
     _ln_epilogue = not os.environ.get("EALDM_NO_LN_EPILOGUE")
+    # GroupNorm (+ SiLU) applied by the epilogue of the conv that produces its input (the ResBlock's second GroupNorm:
+    # conv1's result is never written un-normalised; the GroupNorm in front of a transformer block: second output of
+    # the ResBlock's conv2); A/B switch
+    _gn_epilogue = not os.environ.get("EALDM_NO_GN_EPILOGUE")
 
     def __init__(self, m: UNetModel, dtype: torch.dtype):
         L.load()
@@ -642,17 +646,34 @@ class UNetEngine:
     def _out2(self, d: "Dual"):
         return None if d.h is d.f else d.h
 
-    def _res(self, d, x: "Dual", emb_all: torch.Tensor, dest: Optional["Dual"], shadow: bool = True) -> "Dual":
+    _gna_maxhw = (int(os.environ.get("EALDM_GNA_A_MAXHW", "1024")), int(os.environ.get("EALDM_GNA_B_MAXHW", "1024")))
+
+    def _gn_epilogue_ok(self, c: int, h: int, w: int, variant: int = 0) -> bool:
+        """GroupNorm32 over c channels can run in the producing conv's epilogue (ops.conv(gn_apply=...))."""
+        return (self._gn_epilogue and self.dt == torch.bfloat16 and type(self) is UNetEngine and c >= 256
+                and c % 32 == 0 and c // 32 in (8, 16, 32) and (h * w) % 32 == 0 and h * w <= self._gna_maxhw[variant])
+
+    def _res(self, d, x: "Dual", emb_all: torch.Tensor, dest: Optional["Dual"], shadow: bool = True,
+             norm_next: Optional[tuple] = None) -> "Dual":
+        """norm_next = (gamma, beta, eps) of the GroupNorm (without SiLU) the NEXT layer starts with: conv2's epilogue
+        then also writes it (result.f.gny)."""
         n, h, w = x.f.n, x.f.h, x.f.w
         hn = self._new(n, h, w, x.f.c)
         ops.group_norm(x.f, d["gn1"][0], d["gn1"][1], 1e-5, hn, self.stats, silu=True)
-        h1 = self._new(n, h, w, d["cout"], torch.float32)   # bf16 here costs ~40 % of the 1e-2 eps budget (measured)
-        if self.dt == torch.bfloat16:
-            h1.with_gn_partial()
-        ops.conv([ConvIn(hn, 3, 1, 1)], d["conv1"].w, h1, bias=d["conv1"].b, rowvec=emb_all,
-                 rowvec_col0=d["emb_col0"])
         hn2 = self._new(n, h, w, d["cout"])
-        ops.group_norm(h1, d["gn2"][0], d["gn2"][1], 1e-5, hn2, self.stats, silu=True)
+        gna = self._gn_epilogue_ok(d["cout"], h, w) and hn2.with_gn_partial().gp is not None
+        if gna:
+            # conv1 + emb -> GroupNorm -> SiLU in one kernel: the fp32 intermediate h1 is never written
+            ops.conv([ConvIn(hn, 3, 1, 1)], d["conv1"].w, hn2, bias=d["conv1"].b, rowvec=emb_all,
+                     rowvec_col0=d["emb_col0"], gn_apply=(d["gn2"][0], d["gn2"][1], 1e-5, 32, True, True))
+        else:
+            hn2.gp = None
+            h1 = self._new(n, h, w, d["cout"], torch.float32)   # bf16 here costs ~40 % of the 1e-2 eps budget (measured)
+            if self.dt == torch.bfloat16:
+                h1.with_gn_partial()
+            ops.conv([ConvIn(hn, 3, 1, 1)], d["conv1"].w, h1, bias=d["conv1"].b, rowvec=emb_all,
+                     rowvec_col0=d["emb_col0"])
+            ops.group_norm(h1, d["gn2"][0], d["gn2"][1], 1e-5, hn2, self.stats, silu=True)
         if dest is not None:
             out = dest
         elif shadow:
@@ -662,12 +683,15 @@ class UNetEngine:
             if self.dt == torch.bfloat16:
                 f.with_gn_partial()
             out = Dual(f, f)
+        kw = {"out2": self._out2(out)}
+        if (norm_next is not None and kw["out2"] is None and out.f.gp is not None and out.f.gunit == 8
+                and self._gn_epilogue_ok(d["cout"], h, w, 1)):
+            out.f.gny = self._new(n, h, w, d["cout"])
+            kw = {"out2": out.f.gny, "gn_apply": (norm_next[0], norm_next[1], norm_next[2], 32, False, False)}
         if d["skip"]:
-            ops.conv([ConvIn(hn2, 3, 1, 1), ConvIn(x.h, 1, 1, 0)], d["conv2"].w, out.f, bias=d["conv2"].b,
-                     out2=self._out2(out))
+            ops.conv([ConvIn(hn2, 3, 1, 1), ConvIn(x.h, 1, 1, 0)], d["conv2"].w, out.f, bias=d["conv2"].b, **kw)
         else:
-            ops.conv([ConvIn(hn2, 3, 1, 1)], d["conv2"].w, out.f, bias=d["conv2"].b, residual=x.f,
-                     out2=self._out2(out))
+            ops.conv([ConvIn(hn2, 3, 1, 1)], d["conv2"].w, out.f, bias=d["conv2"].b, residual=x.f, **kw)
         return out
 
     def _st(self, d, x: "Dual", kv_all: Optional[Act], n_ctx: int, dest: Optional["Dual"],
@@ -678,8 +702,10 @@ class UNetEngine:
         n, h, w = x.f.n, x.f.h, x.f.w
         tok = h * w
         f32 = torch.float32
-        xn = self._new(n, h, w, C_)
-        ops.group_norm(x.f, d["norm"][0], d["norm"][1], 1e-6, xn, self.stats, silu=False)
+        xn = x.f.gny          # written by the producing conv's epilogue (see _res)
+        if xn is None:
+            xn = self._new(n, h, w, C_)
+            ops.group_norm(x.f, d["norm"][0], d["norm"][1], 1e-6, xn, self.stats, silu=False)
         if kv_all is None:
             raise RuntimeError("SpatialTransformer needs a context tensor")
         fold = "qkv_ln" in d["blocks"][0]     # bf16 inference engine: no stand-alone LayerNorm passes (see pack_st)
@@ -791,8 +817,10 @@ class UNetEngine:
         C_, heads = d["c"], d["heads"]
         dh = C_ // heads
         n, h, w = x.f.n, x.f.h, x.f.w
-        xn = self._new(n, h, w, C_)
-        ops.group_norm(x.f, d["norm"][0], d["norm"][1], 1e-5, xn, self.stats, silu=False)
+        xn = x.f.gny
+        if xn is None:
+            xn = self._new(n, h, w, C_)
+            ops.group_norm(x.f, d["norm"][0], d["norm"][1], 1e-5, xn, self.stats, silu=False)
         qkv = self._new(n, h, w, 3 * C_)
         ops.linear(xn, d["qkv"].w, qkv, bias=d["qkv"].b)
         o = self._new(n, h, w, C_)
@@ -812,8 +840,10 @@ class UNetEngine:
             if k == "res":
                 # the bf16 operand shadow of the result is written only if the next layer reads it (a transformer
                 # block reads the fp32 master alone)
-                nxt = layers[i + 1]["kind"] if i + 1 < len(layers) else None
-                x = self._res(d, x, emb_all, dst, shadow=nxt not in ("st", "ab"))
+                nxt = layers[i + 1] if i + 1 < len(layers) else None
+                nk = None if nxt is None else nxt["kind"]
+                nn_ = None if nk not in ("st", "ab") else (nxt["norm"][0], nxt["norm"][1], 1e-6 if nk == "st" else 1e-5)
+                x = self._res(d, x, emb_all, dst, shadow=nk not in ("st", "ab"), norm_next=nn_)
             elif k == "st":
                 x = self._st(d, x, kv_all, n_ctx, dst)
             elif k == "ab":
@@ -857,7 +887,8 @@ class UNetEngine:
         r = Dual(rf, rf)      # (no bf16 shadow: the transformer block reads the fp32 master alone)
         rv = rf.images(0, n2)
         rh = Dual(rv, rv)
-        self._res(layers[0], xh, emb_all[:n2], rh)
+        self._res(layers[0], xh, emb_all[:n2], rh, shadow=False,
+                  norm_next=(layers[1]["norm"][0], layers[1]["norm"][1], 1e-6))
         return self._st(layers[1], rh, kv_all, n_ctx, dest, share_full=r)
 
     # ---- forward ----------------------------------------------------------------------------------------

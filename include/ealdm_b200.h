@@ -194,6 +194,20 @@ typedef struct {
      stream disappears.  Two passes over the accumulator in TMEM; the statistics are E[x], E[x^2] in fp32. */
   const float* ln_gamma;
   const float* ln_beta;
+  /* GroupNorm (+ SiLU) APPLIED by the producing epilogue (gn_gamma != NULL; tcgen05 path, n_out >= 256 in 256-column
+     tiles, gn_groups groups of 8 / 16 / 32 channels, h_out * w_out a multiple of 32, gn_partial given, act NONE).
+     Replaces the stand-alone GroupNorm32 + SiLU pass in front of a ResBlock's second convolution and the GroupNorm in
+     front of a SpatialTransformer (ldm/modules/diffusionmodules/openaimodel.py:255-275, ldm/modules/attention.py:254):
+       gn_only = 0:  `out` (fp32) receives the result as usual, `out2` (bf16) act(GroupNorm(result) * gamma + beta)
+       gn_only = 1:  `out` (bf16) receives act(GroupNorm(result) * gamma + beta); the result itself is never written
+     with act = SiLU if gn_silu.  The statistics are the fp64 fold of the epilogue's own fp32 {sum, sum of squares}
+     partials (gn_partial); tiles of one image wait for each other through counters in library-owned scratch. */
+  const float* gn_gamma;
+  const float* gn_beta;
+  float gn_eps;
+  int32_t gn_groups;
+  int32_t gn_silu;
+  int32_t gn_only;
 } ealdm_conv_args;
 
 int ealdm_conv(const ealdm_conv_args* a, ealdm_stream_t stream);

@@ -620,6 +620,60 @@ def test_conv_cta_pairs_match_single_cta(n, c, h, w, co, res, bn):
 
 
 @pytest.mark.parametrize("n,c,h,w,co,feat", [
+    (40, 64, 32, 32, 256, "only"),            # 320 tiles of one CTA on 148 SMs: images straddle the waves; groups of 8
+    (40, 128, 32, 32, 256, "only+rowvec"),    # 160 super-tiles of CTA pairs (K = 1152)
+    (24, 128, 16, 16, 512, "out2+res"),       # two N tiles, groups of 16, fp32 result + normalised copy
+    (40, 128, 8, 8, 1024, "only+rowvec"),     # two images per tile, four N tiles, groups of 32
+    (36, 128, 8, 8, 1024, "out2+skip1x1"),    # the ResBlock -> transformer case with the 1x1 skip accumulated
+    (3, 64, 16, 16, 256, "only"),             # a few tiles only
+])
+def test_group_norm_applied_by_the_producing_epilogue(n, c, h, w, co, feat):
+    """ealdm_conv_args::gn_gamma: GroupNorm32 (+ SiLU) of the conv's result written by the conv's own epilogue -- the
+    tiles of an image exchange their partial statistics through global memory and wait for each other.  Against
+    F.group_norm of the un-fused conv's fp32 result (reference: GroupNorm32 + SiLU in front of a ResBlock's second conv,
+    openaimodel.py:255-275) and against the stand-alone GroupNorm kernel; three runs (the counters re-arm themselves)."""
+    dtype = torch.bfloat16
+    x = torch.randn(n, c, h, w, generator=g(190)).to(DEV)
+    wt = (torch.randn(co, c, 3, 3, generator=g(191)) / math.sqrt(9 * c)).to(DEV)
+    b = torch.randn(co, generator=g(192)).to(DEV)
+    gamma = (1.0 + 0.3 * torch.randn(co, generator=g(193))).to(DEV)
+    beta = (0.3 * torch.randn(co, generator=g(194))).to(DEV)
+    xa = to_act(x, dtype)
+    kw, srcs, wp = {}, [ConvIn(xa, 3, 1, 1)], pack_w(wt, dtype)
+    if "res" in feat:
+        kw["residual"] = to_act(torch.randn(n, co, h, w, generator=g(195)).to(DEV), torch.float32)
+    if "rowvec" in feat:
+        kw["rowvec"] = 2.0 * torch.randn(n, co, generator=g(196)).to(DEV)     # per-image offsets: non-zero group means
+    if "skip1x1" in feat:
+        xs = to_act(torch.randn(n, 192, h, w, generator=g(197)).to(DEV), dtype)
+        ws = (torch.randn(co, 192, 1, 1, generator=g(198)) / math.sqrt(192)).to(DEV)
+        srcs.append(ConvIn(xs, 1, 1, 0))
+        wp = torch.cat([wp, pack_w(ws, dtype)], dim=1).contiguous()
+    only, silu = "only" in feat, "only" in feat
+    plain = Act.empty(n, h, w, co, torch.float32, DEV).with_gn_partial()
+    ops.conv(srcs, wp, plain, bias=b, impl=L.IMPL_TCGEN05, **kw)
+    sep = Act.empty(n, h, w, co, dtype, DEV)
+    ops.group_norm(plain, gamma, beta, 1e-5, sep, silu=silu)
+    ref = F.group_norm(from_act(plain), 32, gamma, beta, 1e-5)
+    ref = F.silu(ref) if silu else ref
+    for _ in range(3):
+        if only:
+            y = Act.empty(n, h, w, co, dtype, DEV).with_gn_partial()
+            ops.conv(srcs, wp, y, bias=b, gn_apply=(gamma, beta, 1e-5, 32, silu, True), **kw)
+        else:
+            f = Act.empty(n, h, w, co, torch.float32, DEV).with_gn_partial()
+            y = Act.empty(n, h, w, co, dtype, DEV)
+            ops.conv(srcs, wp, f, bias=b, out2=y, gn_apply=(gamma, beta, 1e-5, 32, silu, False), **kw)
+            torch.cuda.synchronize()
+            assert torch.equal(f.buf, plain.buf) and torch.equal(f.gp, plain.gp)
+        torch.cuda.synchronize()
+        got = from_act(y)
+        assert rel_l2(got, ref) < 3e-3, rel_l2(got, ref)                       # bf16 rounding of the output
+        assert rel_l2(got, from_act(sep)) < 2e-3, rel_l2(got, from_act(sep))   # the stand-alone kernel: an ulp here and there
+        assert (got - from_act(sep)).abs().max() <= 0.04 * from_act(sep).abs().max()
+
+
+@pytest.mark.parametrize("n,c,h,w,co,feat", [
     (128, 128, 8, 8, 1024, "rowvec"),        # 128 super-tiles on 74 clusters (the 8x8 level's shape): 1.73 tiles each
     (40, 128, 16, 16, 512, "res+out2+gn"),   # 80 super-tiles: remainder 6, every cluster parks and resumes
     (64, 128, 16, 16, 1024, "skip1x1"),      # 256 super-tiles: two whole waves + a dealt tail, two K segments

@@ -64,6 +64,29 @@ def make_conv3(n, h, w_, cin, cout, *, out_dt=F32, rowvec=True, res_dt=None, ski
     return run, 2.0 * n * h * w_ * cout * K, nbytes
 
 
+def make_conv3_gna(n, h, w_, cin, cout, *, only=True, res=False):
+    """3x3 conv whose epilogue applies GroupNorm32 (+ SiLU): only=True writes just the normalised bf16 tensor (a
+    ResBlock's conv1 -> GroupNorm -> SiLU), only=False the fp32 result + the normalised copy (conv2 -> transformer norm)."""
+    x = Act(rnd(n * h * w_, cin, BF), n, h, w_)
+    wt = rnd(cout, 9 * cin, BF) * 0.05
+    b = torch.randn(cout, device=DEV)
+    gamma, beta = torch.ones(cout, device=DEV), torch.zeros(cout, device=DEV)
+    rv = torch.randn(n, cout, device=DEV) if only else None
+    r = Act(rnd(n * h * w_, cout, F32), n, h, w_) if res else None
+    if only:
+        out = Act.empty(n, h, w_, cout, BF, DEV).with_gn_partial()
+        o2 = None
+    else:
+        out = Act.empty(n, h, w_, cout, F32, DEV).with_gn_partial()
+        o2 = Act.empty(n, h, w_, cout, BF, DEV)
+    nbytes = bsz(x.buf) + bsz(wt) + bsz(out.buf) + (bsz(r.buf) if r else 0) + (bsz(o2.buf) if o2 else 0)
+
+    def run():
+        ops.conv([ConvIn(x, 3, 1, 1)], wt, out, bias=b, rowvec=rv, residual=r, out2=o2,
+                 gn_apply=(gamma, beta, 1e-5, 32, only, only))
+    return run, 2.0 * n * h * w_ * cout * 9 * cin, nbytes
+
+
 def make_attn(b, heads, n, dh=32):
     C_ = heads * dh
     qkv = Act(rnd(b * n, 3 * C_, BF), b, 1, n)
@@ -153,6 +176,10 @@ CASES = {
     # ResBlock convs
     "conv3_256_l0": lambda: make_conv3(N, 32, 32, 256, 256),
     "conv3_256_l0_res": lambda: make_conv3(N, 32, 32, 256, 256, rowvec=False, res_dt=F32),
+    "conv3_256_l0_gna": lambda: make_conv3_gna(N, 32, 32, 256, 256),
+    "conv3_256_l0_res_gna": lambda: make_conv3_gna(N, 32, 32, 256, 256, only=False, res=True),
+    "conv3_512_l1_gna": lambda: make_conv3_gna(N, 16, 16, 512, 512),
+    "conv3_1024_l2_gna": lambda: make_conv3_gna(N, 8, 8, 1024, 1024),
     "conv3_512_l0": lambda: make_conv3(N, 32, 32, 512, 256),
     "conv3_512_l1": lambda: make_conv3(N, 16, 16, 512, 512),
     "conv3_1024_l2": lambda: make_conv3(N, 8, 8, 1024, 1024),

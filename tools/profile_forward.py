@@ -19,18 +19,28 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--breakdown", action="store_true")
+    ap.add_argument("--plain", action="store_true", help="a plain forward (no guidance pair, context projected inside)")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     unet = UNetModel(**CFG.UNET_STDIFF).to(dev).eval()
     init_synthetic_(unet, 0)
     n = 2 * args.batch
     g = torch.Generator().manual_seed(1)
-    x = torch.randn(n, 4, 32, 32, generator=g).to(dev)
+    x = torch.cat([torch.randn(args.batch, 4, 32, 32, generator=g).to(dev)] * 2)   # as the guided sampler: cat([x] * 2)
     c = torch.randn(n, 4, 512, generator=g).to(dev)
     t = torch.full((n,), 981, device=dev, dtype=torch.long)
-    for _ in range(2):
-        unet(x, t, context=c)
-    torch.cuda.synchronize()
+    import contextlib
+    with contextlib.ExitStack() as stack:
+        if not args.plain:   # the forward of one guided DDIM step: shared prefix, context projected by the warm-up
+            stack.enter_context(unet.sampling_scope())
+            stack.enter_context(unet.cfg_pair())
+        for _ in range(2):
+            unet(x, t, context=c)
+        torch.cuda.synchronize()
+        run(args, unet, x, t, c, n)
+
+
+def run(args, unet, x, t, c, n):
     if args.breakdown:
         rec = defaultdict(list)
         import ealdm_b200.unet as U
