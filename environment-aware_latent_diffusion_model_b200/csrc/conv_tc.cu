@@ -946,7 +946,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             else ptx::bulk_wait_read<0>();
             if (p.has_res) {
               if (ku + 2 < UNITS) issue_res(tile, ku + 2, b ^ 1);
-              else if (item + 1 < n_items) {
+              else if (item + 1 < n_items && p.gna_gamma == nullptr) {   // (GroupNorm epilogue: issued after its pass 2)
                 int t1, a0, a1, a2;
                 get_item(item + 1, t1, a0, a1, a2);
                 issue_res(t1, part, b ^ 1);
@@ -1130,7 +1130,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         if (p.gna_gamma != nullptr) {
           // ---- GroupNorm applied here, pass 2 (Params::gna_gamma) ----
           ptx::tmem_st_wait();
-          __threadfence();      // this warp's partials are visible before it counts itself in
+          ptx::tc_fence_before();   // (pass 2 reads columns that the other warp of this lane quadrant stored)
+          __threadfence();          // this warp's partials are visible before it counts itself in
           __syncwarp();
           if (n < p.Nimg) {     // (n: the image of this warp's 32 rows)
             unsigned int* cnt = p.gna_counters + 2 * (static_cast<size_t>(n) * p.n_tiles + nt);
@@ -1161,14 +1162,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             double s = 0.0, ss = 0.0;
             if (live && !(p.gna_debug & 2)) {
               const float2* pp = p.gn_partial + static_cast<long long>(n) * p.gn_chunks * p.gn_ld + oct;
-              // sixteen loads in flight per round (one L2 round trip per round, not per chunk); chunk order kept
-              for (int c0 = 0; c0 < p.gn_chunks; c0 += 16) {
-                float2 t[16];
+              // up to 32 loads in flight per round (one L2 round trip per round, not per chunk); chunk order kept
+              for (int c0 = 0; c0 < p.gn_chunks; c0 += 32) {
+                float2 t[32];
 #pragma unroll
-                for (int u = 0; u < 16; ++u)
+                for (int u = 0; u < 32; ++u)
                   t[u] = c0 + u < p.gn_chunks ? __ldcg(pp + static_cast<long long>(c0 + u) * p.gn_ld) : make_float2(0.f, 0.f);
 #pragma unroll
-                for (int u = 0; u < 16; ++u) {
+                for (int u = 0; u < 32; ++u) {
                   s += static_cast<double>(t[u].x);
                   ss += static_cast<double>(t[u].y);
                 }
@@ -1201,18 +1202,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
               cnt[0] = 0u;
             }
             const CUtensorMap* const tmN = p.gna_only ? &tmOut : &tmOut2;
-            uint8_t* const fb = ebuf + ((it - 1u) & 1u) * EBUF_BYTES;   // (staging as in the LayerNorm pass 2)
+            // this warp normalises the 128 columns [part * 128, +128) of its 32 rows (pass 1 owned every second unit:
+            // the other warp of the quadrant has counted in, so its TMEM stores are complete) and stores them as two
+            // [32 rows x 64 columns] boxes of 128-byte rows, one from each unit buffer
+            ptx::tc_fence_after();
             if (lane == 0) ptx::bulk_wait_read<0>();
             __syncwarp();
             uint32_t vv[2][32];
-            ptx::tmem_ld_32x32(taddr0 + part * 32, vv[0]);
+            ptx::tmem_ld_32x32(taddr0 + (part * 4) * 32, vv[0]);
 #pragma unroll
-            for (int ui = 0; ui < UNITS / 2; ++ui) {
-              const int ku = part + 2 * ui;
+            for (int u = 0; u < 4; ++u) {
+              const int ku = part * 4 + u;
               ptx::tmem_ld_wait();
-              if (ui + 1 < UNITS / 2) ptx::tmem_ld_32x32(taddr0 + (ku + 2) * 32, vv[(ui + 1) & 1]);
+              if (u + 1 < 4) ptx::tmem_ld_32x32(taddr0 + (ku + 1) * 32, vv[(u + 1) & 1]);
               if (p.gna_debug & 4) continue;
-              const uint32_t(&v)[32] = vv[ui & 1];
+              const uint32_t(&v)[32] = vv[u & 1];
               float y[32];
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
@@ -1227,19 +1231,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                   y[j] = fmaf(hx, tanh_approx(hx), hx);
                 }
               }
-              uint8_t* const sb = fb + (ui & 1) * O2BUF_BYTES;
-              if (ui >= 2) {   // the store issued two units ago has read this half
-                if (lane == 0) ptx::bulk_wait_read<1>();
+              // the unit buffer the NEXT tile's first residual unit will use (it & 1) is filled and stored first
+              uint8_t* const box = ebuf + (((it + (u >> 1)) & 1u)) * EBUF_BYTES;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) sts_chunk_bf16_sw128(box, lane, 4 * (u & 1) + j, &y[8 * j]);
+              if (u & 1) {
+                ptx::fence_proxy_async();
                 __syncwarp();
-              }
-              sts_row_bf16(sb, lane, y);
-              ptx::fence_proxy_async();
-              __syncwarp();
-              if (lane == 0) {
-                ptx::tma_store_4d(tmN, sb, nt * BN + ku * 32, w, h, n);
-                ptx::bulk_commit();
+                if (lane == 0) {
+                  ptx::tma_store_4d(tmN, box, nt * BN + part * 128 + (u >> 1) * 64, w, h, n);
+                  ptx::bulk_commit();
+                }
               }
             }
+          }
+          // the next tile's first residual unit (pass 1 left it to us): its buffer is free once the FIRST box is read
+          if (p.has_res && lane == 0 && item + 1 < n_items) {
+            ptx::bulk_wait_read<1>();
+            int t1, a0, a1, a2;
+            get_item(item + 1, t1, a0, a1, a2);
+            issue_res(t1, part, static_cast<int>(it & 1u));
           }
         }
       }
@@ -1534,7 +1545,7 @@ bool supported(const ealdm_conv_args* a) {
     // GroupNorm applied by the epilogue: 256-column tiles, groups of 8 / 16 / 32 channels inside one tile, the 32 rows
     // of an epilogue warp inside one image, partial statistics as channel octets
     if (!a->gn_beta || !a->gn_partial || (a->gn_unit != 0 && a->gn_unit != 8) || a->gn_groups < 1) return false;
-    if (a->n_out < 256 || a->n_out % a->gn_groups != 0) return false;
+    if (a->n_out < 256 || a->n_out % 64 != 0 || a->n_out % a->gn_groups != 0) return false;
     const long long cg = a->n_out / a->gn_groups;
     if (cg != 8 && cg != 16 && cg != 32) return false;
     if (a->act != EALDM_ACT_NONE || a->upsample_phases || a->wi_tokens || a->ln_gamma || a->ln_partial_in ||
@@ -1744,7 +1755,7 @@ int launch(const ealdm_conv_args* a, cudaStream_t st) {
                                    ph >> 1, ph & 1))
         return e;
   } else if (int e = encode_unit_map(encode, &tm[3], a->out, a->out_f32 != 0, out_cols, a->ld_out, a, sub,
-                                     wide && !a->out_f32)) {
+                                     (wide || (a->gn_gamma && a->gn_only)) && !a->out_f32)) {
     return e;
   }
   tm[4] = tm[3];
@@ -1756,7 +1767,8 @@ int launch(const ealdm_conv_args* a, cudaStream_t st) {
         if (int e = encode_phase_map(encode, &pm.out2[ph - 1], a->out2, false, out_cols, a->ld_out2, a, sub, ph >> 1,
                                      ph & 1))
           return e;
-    } else if (int e = encode_unit_map(encode, &tm[4], a->out2, false, out_cols, a->ld_out2, a, sub)) {
+    } else if (int e = encode_unit_map(encode, &tm[4], a->out2, false, out_cols, a->ld_out2, a, sub,
+                                       a->gn_gamma != nullptr)) {   // (the GroupNorm epilogue stores 64-column boxes)
       return e;
     }
   }

@@ -646,7 +646,10 @@ class UNetEngine:
     def _out2(self, d: "Dual"):
         return None if d.h is d.f else d.h
 
-    _gna_maxhw = (int(os.environ.get("EALDM_GNA_A_MAXHW", "1024")), int(os.environ.get("EALDM_GNA_B_MAXHW", "1024")))
+    # largest image (pixels) for the two variants: conv1 -> GroupNorm -> SiLU (the un-normalised tensor is never written)
+    # pays at every level; conv2 + the transformer block's GroupNorm as a second output pays where an image lies in ONE
+    # tile (16x16, 8x8) and loses 7 us per launch at 32x32, where four CTA pairs wait for each other
+    _gna_maxhw = (int(os.environ.get("EALDM_GNA_A_MAXHW", "1024")), int(os.environ.get("EALDM_GNA_B_MAXHW", "256")))
 
     def _gn_epilogue_ok(self, c: int, h: int, w: int, variant: int = 0) -> bool:
         """GroupNorm32 over c channels can run in the producing conv's epilogue (ops.conv(gn_apply=...))."""
