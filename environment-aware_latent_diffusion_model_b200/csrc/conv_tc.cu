@@ -1552,6 +1552,9 @@ bool supported(const ealdm_conv_args* a) {
         a->ln_partial_out || (a->h_out * a->w_out) % 32 != 0)
       return false;
     if (a->gn_only ? (a->out_f32 || a->out2) : (!a->out2)) return false;
+    // the tiles of an image wait for each other while they hold their accumulators: they must be in flight together,
+    // i.e. neighbours in one wave of the persistent schedule (or two adjacent waves) -- at most 16 tiles per image
+    if (a->h_out * a->w_out > 16 * BM) return false;
   }
   if (a->gn_partial) {
     const long long hw = a->h_out * a->w_out;

@@ -195,7 +195,8 @@ typedef struct {
   const float* ln_gamma;
   const float* ln_beta;
   /* GroupNorm (+ SiLU) APPLIED by the producing epilogue (gn_gamma != NULL; tcgen05 path, n_out >= 256 in 256-column
-     tiles, gn_groups groups of 8 / 16 / 32 channels, h_out * w_out a multiple of 32, gn_partial given, act NONE).
+     tiles, gn_groups groups of 8 / 16 / 32 channels, h_out * w_out a multiple of 32 and at most 2048 -- the tiles of an
+     image wait for each other and must be in flight together --, gn_partial given, act NONE).
      Replaces the stand-alone GroupNorm32 + SiLU pass in front of a ResBlock's second convolution and the GroupNorm in
      front of a SpatialTransformer (ldm/modules/diffusionmodules/openaimodel.py:255-275, ldm/modules/attention.py:254):
        gn_only = 0:  `out` (fp32) receives the result as usual, `out2` (bf16) act(GroupNorm(result) * gamma + beta)

@@ -626,6 +626,7 @@ def test_conv_cta_pairs_match_single_cta(n, c, h, w, co, res, bn):
     (40, 128, 8, 8, 1024, "only+rowvec"),     # two images per tile, four N tiles, groups of 32
     (36, 128, 8, 8, 1024, "out2+skip1x1"),    # the ResBlock -> transformer case with the 1x1 skip accumulated
     (3, 64, 16, 16, 256, "only"),             # a few tiles only
+    (5, 128, 8, 8, 1024, "out2+res"),         # odd image count: the last tile's second image does not exist
 ])
 def test_group_norm_applied_by_the_producing_epilogue(n, c, h, w, co, feat):
     """ealdm_conv_args::gn_gamma: GroupNorm32 (+ SiLU) of the conv's result written by the conv's own epilogue -- the
