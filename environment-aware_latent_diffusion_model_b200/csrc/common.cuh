@@ -56,15 +56,16 @@ struct DeviceOnce {
 };
 
 // ---- library-owned scratch that must start out zeroed (ticket counters, stream-K parking slots) ----------------------
-// One allocation per device, made on the first request that arrives OUTSIDE a stream capture and cut into SLOTS equal
+// One allocation per device, made on the first request that arrives OUTSIDE a stream capture and cut into equal
 // slots; a stream gets the next free slot the first time it asks (pure bookkeeping, so it also works while the stream
 // is being captured -- a CUDA graph's kernels keep the slot of their capture stream).  Kernels that use a slot leave it
 // zeroed again.  Launches on different streams never share a slot; two graphs captured on the SAME stream do, and must
 // not be replayed concurrently.  nullptr (caller falls back to a path without scratch) if the pool cannot be created
-// now (first request inside a capture) or more than SLOTS streams asked.
+// now (first request inside a capture) or more streams asked than there are slots (16 unless stated).
 class StreamScratch {
  public:
-  explicit StreamScratch(size_t slot_bytes) : slot_bytes_((slot_bytes + 255) & ~static_cast<size_t>(255)) {}
+  explicit StreamScratch(size_t slot_bytes, int slots = MAX_SLOTS)
+      : slot_bytes_((slot_bytes + 255) & ~static_cast<size_t>(255)), slots_(slots < MAX_SLOTS ? slots : MAX_SLOTS) {}
   void* get(cudaStream_t st) {
     int dev = 0;
     cudaGetDevice(&dev);
@@ -78,7 +79,7 @@ class StreamScratch {
         return nullptr;
       }
       void* b = nullptr;
-      if (cudaMalloc(&b, slot_bytes_ * SLOTS) != cudaSuccess || cudaMemset(b, 0, slot_bytes_ * SLOTS) != cudaSuccess) {
+      if (cudaMalloc(&b, slot_bytes_ * slots_) != cudaSuccess || cudaMemset(b, 0, slot_bytes_ * slots_) != cudaSuccess) {
         cudaGetLastError();
         if (b) cudaFree(b);
         return nullptr;
@@ -87,19 +88,20 @@ class StreamScratch {
     }
     for (int i = 0; i < p.used; ++i)
       if (p.owner[i] == st) return p.base + i * slot_bytes_;
-    if (p.used == SLOTS) return nullptr;
+    if (p.used == slots_) return nullptr;
     p.owner[p.used] = st;
     return p.base + (p.used++) * slot_bytes_;
   }
 
  private:
-  static constexpr int SLOTS = 6;
+  static constexpr int MAX_SLOTS = 16;
   struct Pool {
     uint8_t* base = nullptr;
     int used = 0;
-    cudaStream_t owner[SLOTS];
+    cudaStream_t owner[MAX_SLOTS];
   };
   size_t slot_bytes_;
+  int slots_;
   std::mutex mu_;
   Pool pool_[64];
 };

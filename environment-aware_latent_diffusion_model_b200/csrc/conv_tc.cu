@@ -1334,7 +1334,7 @@ static int launch_bn(const CUtensorMap* tm, const Params& p, const PhaseMaps& pm
 constexpr int SK_MAX_CLUSTERS = 80;
 constexpr size_t SK_WS_BYTES = static_cast<size_t>(SK_MAX_CLUSTERS) * 2 * (256 / 32) * 8 * BM * sizeof(float4);
 constexpr size_t SK_FLAG_BYTES = static_cast<size_t>(SK_MAX_CLUSTERS) * 2 * EPI_WARPS * sizeof(unsigned int);
-static StreamScratch g_sk_scratch(SK_WS_BYTES + SK_FLAG_BYTES);
+static StreamScratch g_sk_scratch(SK_WS_BYTES + SK_FLAG_BYTES, 4);   // (19 MB per slot)
 static int g_opt_sk = -1;
 static bool sk_workspace(int clusters, cudaStream_t st, float4** ws, unsigned int** flags) {
   if (clusters > SK_MAX_CLUSTERS) return false;
