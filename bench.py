@@ -705,7 +705,7 @@ def main():
             nbytes += kw["bias"].numel() * 4
         if kw.get("rowvec") is not None:
             nbytes += srcs[0].x.n * weight.shape[0] * 4
-        rec.append((e0, e1, 2.0 * out.rows * n_eff * k_eff, tc, nbytes))
+        rec.append((e0, e1, 2.0 * out.rows * n_eff * k_eff, tc, nbytes, kw.get("gn_apply") is not None))
         return r
 
     xin = torch.cat([x_T_d] * 2)
@@ -731,9 +731,13 @@ def main():
         ops.conv = orig_conv
         _unet_mod.ops.conv = orig_conv
     launches_per_forward = ops.launch_count() - l0
-    tc_ms = sum(e0.elapsed_time(e1) for e0, e1, _, tc, _ in rec if tc)
-    tc_flops = sum(f for _, _, f, tc, _ in rec if tc)
-    tc_bytes = sum(nb for _, _, _, tc, nb in rec if tc)
+    tc_ms = sum(r_[0].elapsed_time(r_[1]) for r_ in rec if r_[3])
+    tc_flops = sum(r_[2] for r_ in rec if r_[3])
+    tc_bytes = sum(r_[4] for r_ in rec if r_[3])
+    # the launches whose epilogue also applies a GroupNorm (+ SiLU) do the work of a second kernel: reported apart
+    gn_ms = sum(r_[0].elapsed_time(r_[1]) for r_ in rec if r_[3] and r_[5])
+    gn_flops = sum(r_[2] for r_ in rec if r_[3] and r_[5])
+    n_gn = sum(1 for r_ in rec if r_[3] and r_[5])
     n_tc = sum(1 for r_ in rec if r_[3])
     fwd_ms = f0.elapsed_time(f1)
     achieved = tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
@@ -743,6 +747,10 @@ def main():
                 "traffic": None, "algorithmic_bytes": tc_bytes / max(n_tc, 1),
                 "algorithmic_bytes_per_forward": tc_bytes, "algorithmic_flops_per_forward": tc_flops,
                 "launches_per_forward": n_tc, "avg_launch_ms": tc_ms / max(n_tc, 1),
+                "launches_with_groupnorm_epilogue": n_gn,
+                "achieved_without_groupnorm_epilogue": ((tc_flops - gn_flops) / ((tc_ms - gn_ms) * 1e-3) / 1e12
+                                                        if tc_ms > gn_ms else None),
+                "achieved_with_groupnorm_epilogue": gn_flops / (gn_ms * 1e-3) / 1e12 if gn_ms > 0 else None,
                 # share of one DDIM step of the timed (CUDA-graph) run; the instrumented eager forward itself is
                 # host-bound (an event pair per launch), so its own duration is reported separately
                 "share_of_forward": tc_ms / (ms_per_step / S) if ms_per_step > 0 else None,
