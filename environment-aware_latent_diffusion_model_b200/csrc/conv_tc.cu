@@ -106,6 +106,11 @@ struct Params {
   //   out = rstd * acc - rstd * mu * c1[col] + bias[col]  ==  LayerNorm(x) W^T + bias
   // per-image B operand (ealdm_conv_args::wi_*): tmB is a 4-D (c, token, head, image) map, a tile lies in one image
   int b_img;
+  // ... or in TWO (64-token images, 128 (head, key) logits each): the logits GEMM runs 128-column tiles, N tile nt of an
+  // M tile multiplies by the operand of the tile's image nt and its epilogue zeroes the rows of the OTHER image, so every
+  // row carries [its probabilities | zeros] (or the reverse) over 256 columns; the output GEMM then reads those 256
+  // columns as K against [Zt of image 0; Zt of image 1] -- a block-diagonal product
+  int b_img2;
   // LayerNorm APPLIED by the producing epilogue (ealdm_conv_args::ln_gamma; N == BN == 256, so a CTA holds whole rows):
   // pass 1 writes the fp32 result as usual, keeps per-row {sum, sum of squares} and stores the result back over its
   // TMEM accumulator; the two warps that share a row exchange their sums; pass 2 re-reads TMEM and writes
@@ -450,9 +455,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 #pragma unroll
                 for (int g = 0; g < BN / 64; ++g)
                   ptx::tma_load_4d(sa + C::A_BYTES + g * 8192, &tmB, &full_bar[stage], nt * BN + g * 64, 0,
-                                   kb * (BK / p.b_img), n0);
+                                   (p.b_img2 ? (kb & 1) : kb) * (BK / p.b_img), n0 + (p.b_img2 ? (kb >> 1) : 0));
               } else {
-                ptx::tma_load_4d(sa + C::A_BYTES, &tmB, &full_bar[stage], kb * BK, 0, 0, n0);
+                ptx::tma_load_4d(sa + C::A_BYTES, &tmB, &full_bar[stage], kb * BK, 0, 0, n0 + (p.b_img2 ? nt : 0));
               }
             } else if (p.b_mn) {
               // adjoint: rows = 64 source channels (K), columns = N of the flipped tap, 64 at a time (one SW128 atom)
@@ -1026,6 +1031,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
               const float inv = __fdividef(1.0f, (e0 + e1) + (e2 + e3));
               r[4 * g] = e0 * inv; r[4 * g + 1] = e1 * inv; r[4 * g + 2] = e2 * inv; r[4 * g + 3] = e3 * inv;
             }
+            if (p.b_img2 && (quad >> 1) != nt) {   // rows of the tile's other image: their half of the K range is zero
+#pragma unroll
+              for (int j = 0; j < 32; ++j) r[j] = 0.f;
+            }
           } else {  // SiLU (time-embedding MLP): act(acc + bias + rowvec) + residual
             ptx::tmem_ld_wait();
 #pragma unroll
@@ -1481,15 +1490,20 @@ bool supported(const ealdm_conv_args* a) {
     // per-image B: one 1x1 source, a 128-row tile inside one image, (head, token) = the 32 logits / probabilities
     const ealdm_conv_src& x = a->src[0];
     if (a->n_src != 1 || x.ksize != 1 || x.stride != 1 || x.pad != 0 || x.upsample || a->upsample_phases) return false;
-    if ((x.h * x.w) % BM != 0 || a->h_out != x.h || a->w_out != x.w) return false;
+    const bool two = x.h * x.w == BM / 2;   // two 64-token images per tile (Params::b_img2)
+    if (((x.h * x.w) % BM != 0 && !two) || a->h_out != x.h || a->w_out != x.w) return false;
     const long long logits = static_cast<long long>(a->wi_tokens) * a->wi_heads;
+    if (two && (logits != 128 || x.w != 8 || x.h != 8)) return false;
     if (a->wi_tokens < 1 || a->wi_heads < 1 || logits % 32 != 0 || logits > 128 || 64 % a->wi_tokens != 0) return false;
     if (!aligned_2d(a->weight, a->wi_ld, 2) || a->wi_head_stride % 8 != 0 || a->rowvec || a->gn_partial) return false;
     if (a->ln_partial_in || a->ln_partial_out) return false;
     if (a->weight_adjoint) {
-      if (x.c != logits || a->n_out % 64 != 0 || a->n_out > a->wi_head_stride || a->act != EALDM_ACT_NONE) return false;
+      if (x.c != (two ? 2 : 1) * logits || a->n_out % 64 != 0 || a->n_out > a->wi_head_stride || a->act != EALDM_ACT_NONE)
+        return false;
     } else {
-      if (a->n_out != logits || x.c % BK != 0 || x.c > a->wi_head_stride || a->residual || a->out2 || a->out_f32) return false;
+      if (a->n_out != (two ? 2 : 1) * logits || x.c % BK != 0 || x.c > a->wi_head_stride || a->residual || a->out2 ||
+          a->out_f32)
+        return false;
       if (a->act != EALDM_ACT_SOFTMAX4 && a->act != EALDM_ACT_NONE) return false;
     }
   } else if (a->act == EALDM_ACT_SOFTMAX4) {
@@ -1620,6 +1634,7 @@ static int choose_bn(const ealdm_conv_args* a, long long m_work) {
   const bool geglu = a->act == EALDM_ACT_GEGLU;
   if (a->ln_gamma) return 256;   // LayerNorm in the epilogue needs the whole row in one tile
   if (a->gn_gamma) return 256;   // GroupNorm in the epilogue: written for the 256-column tile
+  if (a->wi_tokens && !a->weight_adjoint && a->src[0].h * a->src[0].w == BM / 2) return 128;   // one image's logits per N tile
   if (a->n_out <= 32 && !geglu && !a->weight_adjoint) return 32;
   if (a->n_out <= 128) return 128;
   const long long t256 = m_work * ceil_div(a->n_out, 256);
@@ -1822,6 +1837,7 @@ int launch(const ealdm_conv_args* a, cudaStream_t st) {
   p.ln_c1 = a->ln_c1;
   p.b_mn = a->weight_adjoint ? 1 : 0;
   p.b_img = a->wi_tokens;
+  p.b_img2 = (a->wi_tokens && a->src[0].h * a->src[0].w == BM / 2) ? 1 : 0;
   p.wide = wide ? 1 : 0;
   p.relaxed_wait = g_opt[EALDM_TC_OPT_RELAXED_WAIT];
 

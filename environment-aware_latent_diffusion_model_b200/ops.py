@@ -155,11 +155,15 @@ def conv(srcs: Sequence[ConvIn], weight: torch.Tensor, out: Act, *, bias: Option
         a.weight = weight.data_ptr() + col0 * weight.element_size()
         a.wi_tokens, a.wi_heads, a.wi_ld, a.wi_head_stride = tokens, heads, weight.stride(0), hstride
         a.impl = L.IMPL_TCGEN05
+        # 64-token images (8x8): two images per 128-row tile -- the logits tensor is 2 * heads * tokens wide, every row
+        # holding its image's probabilities in one half and zeros in the other (ealdm_conv_args::wi_*, Params::b_img2)
+        width = heads * tokens * (2 if x0.h * x0.w == 64 else 1)
         if adjoint:
-            assert x0.c == heads * tokens
+            assert x0.c == width
             a.n_out, a.k_total, a.weight_adjoint = out.c, x0.c, 1
         else:
-            a.n_out, a.k_total = heads * tokens, x0.c
+            assert out.c == width
+            a.n_out, a.k_total = width, x0.c
     else:
         assert weight.dim() == 2 and weight.dtype == x0.dtype
         a.weight = weight.data_ptr()

@@ -422,6 +422,11 @@ class UNetEngine:
     # cross-attention collapsed onto the context (packing.collapse_cross_attention): to_q -> 4-key attention -> to_out
     # become two per-image GEMMs of K = C / N = 32 and K = 32 / N = C; A/B switch, the training engine keeps q / k / v
     _collapse_xattn = not os.environ.get("EALDM_NO_XATTN_COLLAPSE")
+    # ... also at the 8x8 level (64 tokens per image, two images per tile).  There the projection of the context by
+    # heads * C = 32768 columns per layer costs more than the 64 tokens of an image save -- unless it is made once per
+    # sampling loop (UNetModel.sampling_scope), which the samplers do: -0.3 ms per DDIM step for 0.25 ms per loop and
+    # 0.8 GB of projection weights / operands; a stand-alone forward pays the 0.25 ms every time.  A/B switch
+    _collapse_xattn_8x8 = not os.environ.get("EALDM_NO_XATTN_COLLAPSE_8X8")
     # LayerNorm applied by the epilogue of the GEMM that produces its input (width 256: a CTA holds whole rows); A/B switch
     _ln_epilogue = not os.environ.get("EALDM_NO_LN_EPILOGUE")
     # GroupNorm (+ SiLU) applied by the epilogue of the conv that produces its input (the ResBlock's second GroupNorm:
@@ -500,8 +505,10 @@ class UNetEngine:
                                       f32(tb.attn2.to_out[0].bias), C_)
                 # (only where a 128-row tile lies inside one image at the model's nominal resolution: the projection of
                 # the context grows with heads * C = C^2 / 32 per layer, so unused blocks are not worth carrying)
+                tok_ = (m.image_size // self._ds) ** 2
                 if (self._collapse_xattn and self.dt == torch.bfloat16 and st.d_head == 32 and C_ % 64 == 0
-                        and (m.image_size // self._ds) ** 2 % 128 == 0 and st.n_heads * 4 <= 128):
+                        and (tok_ % 128 == 0 or (tok_ == 64 and st.n_heads * 4 == 128 and self._collapse_xattn_8x8))
+                        and st.n_heads * 4 <= 128):
                     g_, h_ = collapse_cross_attention(tb.attn2.to_q.weight, tb.attn2.to_k.weight, tb.attn2.to_v.weight,
                                                       tb.attn2.to_out[0].weight, st.n_heads, tb.attn2.scale, dtype)
                     t["xc_col0"] = self.xc_cols          # U block at xc_col0, Zt block at xc_col0 + heads * C
@@ -778,14 +785,15 @@ class UNetEngine:
             t2 = self._new(n, h, w, C_, f32)
             t2_h = self._new(n, h, w, C_) if ff_fold else None
             xc = getattr(self, "xc_all", None)
-            if "xc_col0" in tb and xc is not None and not fold and tok % 128 == 0 and heads * n_ctx <= 128:
+            two = tok == 64 and heads * n_ctx == 128 and h == 8 and w == 8     # two images per 128-row tile
+            if "xc_col0" in tb and xc is not None and not fold and (tok % 128 == 0 or two) and heads * n_ctx <= 128:
                 # collapsed cross-attention: logits = LN2(t1) U_n^T (softmax over the 4 keys in the epilogue), then
                 # t2 = P Zt_n + bias + t1; U_n / Zt_n are column windows of the context projection xc_all
                 a2 = t1.lny
                 if a2 is None:
                     a2 = self._new(n, h, w, C_)
                     ops.layer_norm(t1, tb["ln2"][0], tb["ln2"][1], 1e-5, a2)
-                pr = self._new(n, h, w, heads * n_ctx)
+                pr = self._new(n, h, w, heads * n_ctx * (2 if two else 1))
                 ops.conv([ConvIn(a2)], xc.buf, pr, act=L.ACT_SOFTMAX4, wimg=(tb["xc_col0"], n_ctx, heads, C_))
                 ops.conv([ConvIn(pr)], xc.buf, t2, bias=tb["o2"].b, residual=t1, adjoint=True,
                          wimg=(tb["xc_col0"] + heads * C_, n_ctx, heads, C_), **ln_out(t2, tb, 3))

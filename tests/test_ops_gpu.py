@@ -336,7 +336,7 @@ def test_cross_attention_small_kv(dtype, nk):
 
 
 @pytest.mark.parametrize("n,hh,ww,C", [(3, 32, 32, 256), (2, 16, 16, 512), (2, 16, 8, 256), (1, 32, 16, 1024),
-                                       (2, 16, 16, 768)])
+                                       (2, 16, 16, 768), (6, 8, 8, 1024), (5, 8, 8, 1024)])
 def test_cross_attention_collapsed_onto_the_context(n, hh, ww, C):
     """CrossAttention (ldm/modules/attention.py:170-193) with a 4-token context, collapsed onto the context
     (packing.collapse_cross_attention + ealdm_conv wi_*): logits = x U_n^T with the softmax over the 4 keys in the
@@ -367,12 +367,19 @@ def test_cross_attention_collapsed_onto_the_context(n, hh, ww, C):
     xc = Act.empty(n, 1, T, gh.shape[0], bf, DEV)
     ops.linear(Act(ctx, n, 1, T), gh, xc)
     xa = Act(x, n, hh, ww)
-    pr = Act.empty(n, hh, ww, heads * T, bf, DEV)
+    two = hh * ww == 64      # two 64-token images per tile: [probabilities | zeros] or [zeros | probabilities] per row
+    pr = Act.empty(n, hh, ww, heads * T * (2 if two else 1), bf, DEV)
     ops.conv([ConvIn(xa)], xc.buf, pr, act=L.ACT_SOFTMAX4, wimg=(0, T, heads, C))
-    psum = pr.buf.float().reshape(M, heads, T).sum(-1)
+    pbuf = pr.buf.float()
+    if two:
+        odd = ((torch.arange(M, device=DEV) // 64) % 2 == 1)[:, None]
+        halves = pbuf.reshape(M, 2, heads * T)
+        assert (torch.where(odd, halves[:, 0], halves[:, 1]) == 0).all()     # the other image's half is exactly zero
+        pbuf = torch.where(odd, halves[:, 1], halves[:, 0])
+    psum = pbuf.reshape(M, heads, T).sum(-1)
     assert (psum - 1).abs().max() < 2e-2            # rows of probabilities (bf16-rounded)
     pref = torch.softmax(torch.einsum("bhqd,bhkd->bhqk", q, k) * scale, dim=-1).transpose(1, 2).reshape(M, heads * T)
-    assert (pr.buf.float() - pref).abs().max() < 2.5e-2
+    assert (pbuf - pref).abs().max() < 2.5e-2
     ra = Act(res, n, hh, ww)
     out = Act.empty(n, hh, ww, C, torch.float32, DEV)
     ops.conv([ConvIn(pr)], xc.buf, out, bias=bo, residual=ra, adjoint=True, wimg=(heads * C, T, heads, C))
