@@ -322,3 +322,72 @@ def test_collapsed_cross_attention_weights_reproduce_the_reference_layer():
     p2 = torch.softmax(logits2 * 0.6931471805599453, dim=-1)
     got = torch.einsum("nthj,nhjc->ntc", p2, Z) + bo
     assert float((got - want).norm() / want.norm()) < 1e-6            # G / H were rounded to fp32
+
+
+def test_guidance_pair_and_sampling_scope_host_logic():
+    """util.GuidancePair / UNetModel.sampling_scope (the hints the samplers give the UNet): the concatenated conditioning
+    is built once while `uc` and `c` stay the same tensors at the same version, rebuilt when either changes, the hosted
+    UNet sees the guidance-pair flag only inside the call, and a model without the hooks is driven exactly like the
+    reference drives it (ddim.py:173-179)."""
+    import contextlib
+
+    from ealdm_b200.util import GuidancePair, sampling_scope
+
+    class FakeUNet:
+        def __init__(self):
+            self.pair, self.scope, self.seen = False, False, []
+
+        @contextlib.contextmanager
+        def cfg_pair(self):
+            self.pair = True
+            try:
+                yield self
+            finally:
+                self.pair = False
+
+        @contextlib.contextmanager
+        def sampling_scope(self):
+            self.scope = True
+            try:
+                yield self
+            finally:
+                self.scope = False
+
+    class Holder:
+        pass
+
+    class FakeModel:
+        def __init__(self, unet):
+            self.model = Holder()
+            self.model.diffusion_model = unet
+            self.calls = []
+
+        def apply_model(self, x, t, c):
+            u = self.model.diffusion_model
+            self.calls.append((x, t, c, getattr(u, "pair", None), getattr(u, "scope", None)))
+            return torch.cat([x[: x.shape[0] // 2] * 0 + 1, x[x.shape[0] // 2:] * 0 + 2])
+
+    unet = FakeUNet()
+    model = FakeModel(unet)
+    pair = GuidancePair(model)
+    x, t = torch.randn(3, 4, 2, 2), torch.tensor([5, 5, 5])
+    uc, c = torch.randn(3, 4, 8), torch.randn(3, 4, 8)
+    with sampling_scope(model):
+        e_u, e_c = pair(x, t, uc, c)
+        pair(x + 1, t, uc, c)
+    assert torch.equal(e_u, torch.ones_like(x)) and torch.equal(e_c, 2 * torch.ones_like(x))
+    (x0, t0, c0, p0, s0), (x1, t1, c1, p1, s1) = model.calls
+    assert torch.equal(x0, torch.cat([x, x])) and torch.equal(t0, torch.cat([t, t])) and torch.equal(c0, torch.cat([uc, c]))
+    assert p0 and s0 and p1 and s1 and not unet.pair and not unet.scope      # flags only inside the calls
+    assert c1 is c0                                                          # same uc / c objects: the same c_in tensor
+    c.add_(1.0)                                                              # in-place change: version bump
+    pair(x, t, uc, c)
+    assert model.calls[2][2] is not c0 and torch.equal(model.calls[2][2], torch.cat([uc, c]))
+    uc2 = uc.clone()
+    pair(x, t, uc2, c)
+    assert model.calls[3][2] is not model.calls[2][2]
+    # a model that does not host the B200 UNet: no hooks, same calls
+    plain = FakeModel(object())
+    with sampling_scope(plain):
+        GuidancePair(plain)(x, t, uc, c)
+    assert plain.calls[0][3] is None and torch.equal(plain.calls[0][2], torch.cat([uc, c]))
