@@ -114,6 +114,7 @@ class DDIMSampler(object):
         # all timestep vectors of the loop in one upload (the reference builds one per step)
         ts_all = torch.as_tensor(np.ascontiguousarray(np.asarray(time_range, dtype=np.int64))).to(device)
         ts_all = ts_all[:, None].expand(total_steps, b).contiguous()
+        self._pair.reset()
         with sampling_scope(self.model):   # the conditioning is loop-invariant: the UNet projects it once
             return self._ddim_loop(img, cond, ts_all, total_steps, mask, x0, ddim_use_original_steps, quantize_denoised,
                                    temperature, noise_dropout, score_corrector, corrector_kwargs,

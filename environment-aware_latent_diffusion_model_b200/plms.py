@@ -59,6 +59,7 @@ class PLMSSampler(DDIMSampler):
         ts_all = torch.as_tensor(np.ascontiguousarray(np.asarray(time_range, dtype=np.int64))).to(device)
         ts_all = ts_all[:, None].expand(total_steps, b).contiguous()
         old_eps = []
+        self._pair.reset()
         with sampling_scope(self.model):     # the conditioning is loop-invariant: the UNet projects it once
             for i in range(total_steps):
                 index = total_steps - i - 1

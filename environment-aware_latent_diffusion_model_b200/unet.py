@@ -299,6 +299,7 @@ class UNetModel(nn.Module):
         return super()._apply(fn, *a, **k)
 
     # ---- hints from the samplers -----------------------------------------------------------------------
+    # (attributes of the module, not thread-local: one sampling loop per model at a time)
     @contextlib.contextmanager
     def sampling_scope(self):
         """Entered by the samplers around one denoising loop: inside it a context tensor that is the SAME object (and
@@ -387,6 +388,10 @@ class UNetModel(nn.Module):
             return unet_forward_train(self, x, timesteps, context)
         engine = self._get_engine()
         pair = self._pair_hint and x.shape[0] % 2 == 0
+        if pair and os.environ.get("EALDM_CHECK_CFG_PAIR"):   # debugging aid (one device sync): the caller's guarantee
+            hb = x.shape[0] // 2
+            assert torch.equal(x[:hb], x[hb:]) and torch.equal(timesteps[:hb], timesteps[hb:]), \
+                "cfg_pair(): the two halves of the batch must hold the same images and timesteps"
         if self.use_cuda_graph and not torch.cuda.is_current_stream_capturing():
             return self._forward_graphed(x, timesteps, context, pair)
         proj = None

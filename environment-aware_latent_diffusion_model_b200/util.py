@@ -127,6 +127,10 @@ class GuidancePair:
         self.model, self.unet = model, _hosted_unet(model)
         self._key, self._held, self._c_in = None, (None, None), None
 
+    def reset(self):
+        """Drop the cached concatenation (and the references to `uc` / `c` that keep it valid)."""
+        self._key, self._held, self._c_in = None, (None, None), None
+
     def __call__(self, x, t, uc, c):
         import contextlib
         if isinstance(c, torch.Tensor) and isinstance(uc, torch.Tensor):
