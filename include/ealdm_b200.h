@@ -16,7 +16,11 @@
  *  - `dtype` selects the storage type of activations and weights: EALDM_F32 (parity mode, FFMA
  *    kernels) or EALDM_BF16 (tcgen05 tensor-core kernels, fp32 accumulation).  Biases, norm
  *    affine parameters, per-image row vectors and statistics are always fp32/fp64;
- *  - nothing is allocated or freed inside the library; workspaces are passed in;
+ *  - tensors, weights and workspaces are the caller's and are passed in; the library itself keeps only three small
+ *    zero-initialised scratch pools per device, created by cudaMalloc on first use OUTSIDE a stream capture and handed
+ *    out per stream: the counters of the GroupNorm epilogue (ealdm_conv_args::gn_gamma), the ticket counters of
+ *    ealdm_colsum, and the parking slots of the opt-in stream-K schedule.  Kernels leave them zeroed.  Launches on
+ *    different streams never share a slot; CUDA graphs captured on the same stream do and must not replay concurrently;
  *  - every function is asynchronous on `stream` (a cudaStream_t), re-entrant per stream, and
  *    returns 0 on success or a negative EALDM_E* code; ealdm_last_error() returns the message of
  *    the last failure on the calling thread.
