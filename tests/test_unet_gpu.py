@@ -183,6 +183,41 @@ def test_unet_forward_guidance_pair_shares_the_prefix_bit_identical():
     unet.enable_cuda_graph(False)
 
 
+def test_guided_ddim_sampling_is_bit_identical_with_and_without_the_sampler_hints(monkeypatch):
+    """End to end: `DDIMSampler.sample` with classifier-free guidance through the hinted path (shared prefix of the
+    cond / uncond halves, context projected once per loop, CUDA-graph replay) against the same call with the hints
+    switched off -- the latents must be the same bits (the hints remove duplicated work, they change no arithmetic)."""
+    ld = make_ld("stdiff")
+    unet = ld.model.diffusion_model.set_compute_dtype("bf16")
+    g = torch.Generator().manual_seed(11)
+    B = 6
+    x_T = torch.randn(B, 4, 32, 32, generator=g).cuda()
+    c = torch.randn(B, 4, 512, generator=g).cuda()
+    uc = torch.randn(B, 4, 512, generator=g).cuda()
+
+    def run():
+        torch.manual_seed(3)      # the per-step noise draw (eta = 0.5)
+        z, _ = DDIMSampler(ld).sample(S=6, batch_size=B, shape=(4, 32, 32), conditioning=c, eta=0.5, x_T=x_T,
+                                      verbose=False, unconditional_guidance_scale=2.0, unconditional_conditioning=uc)
+        return z
+
+    outs = {}
+    for graph in (False, True):
+        unet.enable_cuda_graph(graph)
+        outs["hints", graph] = run()
+        outs["hints again", graph] = run()
+        monkeypatch.setenv("EALDM_NO_CFG_SHARE", "1")
+        monkeypatch.setenv("EALDM_NO_CTX_REUSE", "1")
+        outs["plain", graph] = run()
+        monkeypatch.delenv("EALDM_NO_CFG_SHARE")
+        monkeypatch.delenv("EALDM_NO_CTX_REUSE")
+    unet.enable_cuda_graph(False)
+    base = outs["plain", False]
+    assert torch.isfinite(base).all()
+    for k, v in outs.items():
+        assert torch.equal(v, base), k
+
+
 def test_unet_is_deterministic_and_batch_independent():
     G = gold("unet_stdiff_fwd.pt")
     unet = make_ld("stdiff").model.diffusion_model.set_compute_dtype("bf16")
