@@ -724,6 +724,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const int col = nt * BN + etid;
         float bv0 = (p.bias != nullptr && col < p.N) ? __ldg(p.bias + col) : 0.f;
         if (GEGLU && (etid & 16) == 0) bv0 *= 0.5f;  // value columns: the epilogue computes 0.5 v + 0.5 bias (geglu2)
+        // (one image per tile, no residual: the per-image row vector joins the bias here -- (0 + bias) + rowvec, the
+        // epilogue's own order -- instead of four L2 round trips per tile inside the unit loop)
+        if (!GEGLU && p.rowvec != nullptr && p.bn == 1 && !p.has_res && p.act == EALDM_ACT_NONE && col < p.N && n < p.Nimg)
+          bv0 += __ldg(p.rowvec + static_cast<long long>(n) * p.ld_rowvec + col);
         bias_s[acc * BN + etid] = bv0;
         if (p.ln_in != nullptr) {
           float cv = col < p.N ? __ldg(p.ln_c1 + col) : 0.f;
@@ -748,7 +752,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       const float* bs = bias_s + acc * BN;
       const float* cs = c1_s + acc * BN;
       const float* rv = nullptr;
-      if (!GEGLU && p.rowvec != nullptr) {
+      if (!GEGLU && p.rowvec != nullptr && !(p.bn == 1 && !p.has_res && p.act == EALDM_ACT_NONE)) {
         int img = (n - sn0) + my_dn;
         if (img >= p.Nimg) img = p.Nimg - 1;
         rv = p.rowvec + static_cast<long long>(img) * p.ld_rowvec + nt * BN;
@@ -757,6 +761,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * BN);
       ptx::mbar_wait(&tmem_full[acc], acc_phase);
       ptx::tc_fence_after();
+      // EALDM_GNA_DEBUG & 16: clock64 trace of this epilogue's phases (first CTA, first epilogue warp), printed per tile
+      const bool trace = (p.gna_debug & 16) != 0 && blockIdx.x == 0 && ew == 0 && lane == 0;
+      long long tq[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      if (trace) tq[0] = clock64();
 
       bool wide_done = false;
       float lna_s = 0.f, lna_ss = 0.f;   // LayerNorm applied here: this thread's row sums over the units of its warp
@@ -1138,10 +1146,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       if constexpr (BN == 256 && !GEGLU) {
         if (p.gna_gamma != nullptr) {
           // ---- GroupNorm applied here, pass 2 (Params::gna_gamma) ----
+          if (trace) tq[1] = clock64();
           ptx::tmem_st_wait();
           ptx::tc_fence_before();   // (pass 2 reads columns that the other warp of this lane quadrant stored)
           __threadfence();          // this warp's partials are visible before it counts itself in
           __syncwarp();
+          if (trace) tq[2] = clock64();
           if (n < p.Nimg) {     // (n: the image of this warp's 32 rows)
             unsigned int* cnt = p.gna_counters + 2 * (static_cast<size_t>(n) * p.n_tiles + nt);
             // lane = channel octet of this tile's 256 columns; its gamma / beta are requested before the wait
@@ -1167,32 +1177,39 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
               __threadfence();   // (the counter was read with acquire semantics in the loop; this covers the atomic's value)
             }
             __syncwarp();
-            // fold the octet's partials over the image's 32-pixel chunks
-            double s = 0.0, ss = 0.0;
+            if (trace) tq[3] = clock64();
+            // fold the octet's partials over the image's 32-pixel chunks.  fp32 pairwise sums (fp64 adds and the fp64
+            // reciprocal square root cost ~10,000 clk per tile here -- clock64 trace, DESIGN.md section 4 --, five times
+            // the whole second pass); only mean^2 is subtracted in fp64
+            float s = 0.f, ss = 0.f;
             if (live && !(p.gna_debug & 2)) {
               const float2* pp = p.gn_partial + static_cast<long long>(n) * p.gn_chunks * p.gn_ld + oct;
-              // up to 32 loads in flight per round (one L2 round trip per round, not per chunk); chunk order kept
+              // up to 32 loads in flight per round (one L2 round trip per round, not per chunk); fixed summation tree
               for (int c0 = 0; c0 < p.gn_chunks; c0 += 32) {
                 float2 t[32];
 #pragma unroll
                 for (int u = 0; u < 32; ++u)
                   t[u] = c0 + u < p.gn_chunks ? __ldcg(pp + static_cast<long long>(c0 + u) * p.gn_ld) : make_float2(0.f, 0.f);
 #pragma unroll
-                for (int u = 0; u < 32; ++u) {
-                  s += static_cast<double>(t[u].x);
-                  ss += static_cast<double>(t[u].y);
+                for (int w2 = 16; w2 >= 1; w2 >>= 1) {
+#pragma unroll
+                  for (int u = 0; u < w2; ++u) {
+                    t[u].x += t[u + w2].x;
+                    t[u].y += t[u + w2].y;
+                  }
                 }
+                s += t[0].x;
+                ss += t[0].y;
               }
             }
             for (int d = 1; d < p.gna_octets; d <<= 1) {   // the octets of one group, lower octet first
-              const double os = __shfl_xor_sync(0xffffffffu, s, d), oss = __shfl_xor_sync(0xffffffffu, ss, d);
+              const float os = __shfl_xor_sync(0xffffffffu, s, d), oss = __shfl_xor_sync(0xffffffffu, ss, d);
               s = (lane & d) ? os + s : s + os;
               ss = (lane & d) ? oss + ss : ss + oss;
             }
-            const double mean = s * p.gna_inv_count;
-            double var = ss * p.gna_inv_count - mean * mean;
-            if (var < 0.0) var = 0.0;
-            const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(p.gna_eps)));
+            const double mean = static_cast<double>(s) * p.gna_inv_count;
+            const float var = fmaxf(static_cast<float>(static_cast<double>(ss) * p.gna_inv_count - mean * mean), 0.f);
+            const float rstd = rsqrtf(var + p.gna_eps);
             const float mu = static_cast<float>(mean);
             float2* const tab = reinterpret_cast<float2*>(o2buf);   // [256 columns]{scale, shift} (no shadow output here)
             if (live) {
@@ -1210,6 +1227,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
               __threadfence();
               cnt[0] = 0u;
             }
+            if (trace) tq[4] = clock64();
             const CUtensorMap* const tmN = p.gna_only ? &tmOut : &tmOut2;
             // this warp normalises the 128 columns [part * 128, +128) of its 32 rows (pass 1 owned every second unit:
             // the other warp of the quadrant has counted in, so its TMEM stores are complete) and stores them as two
@@ -1253,6 +1271,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 }
               }
             }
+          }
+          if (trace) {
+            tq[5] = clock64();
+            printf("gna trace tile %d: pass1 %lld  st_wait+fence %lld  count+wait %lld  fold+table %lld  pass2 %lld clk\n", tile,
+                   tq[1] - tq[0], tq[2] - tq[1], tq[3] - tq[2], tq[4] - tq[3], tq[5] - tq[4]);
           }
           // the next tile's first residual unit (pass 1 left it to us): its buffer is free once the FIRST box is read
           if (p.has_res && lane == 0 && item + 1 < n_items) {
