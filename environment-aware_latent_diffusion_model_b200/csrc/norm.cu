@@ -199,13 +199,22 @@ gn_apply_partial_kernel(const TX* __restrict__ x, long long ld_x, T* __restrict_
     for (int g0 = 0; g0 < groups; g0 += NT / 8) {
       const int g = g0 + (t >> 3);
       const int sub = t & 7;
+      // Eight loads in flight per thread and round, added pairwise in fp32; the rounds are accumulated in fp64 (one
+      // add per round and component).  A chain of dependent (load -> fp64 add) steps per term, and the fp64 reciprocal
+      // square root behind it, made this prologue 5-12 us per CTA at the UNet's shapes (180 us at 256 x 256): fp64
+      // arithmetic is slow on this part (clock64 trace of the same fold in the conv epilogue)
       double s = 0.0, ss = 0.0;
       if (g < groups) {
-        for (int k = sub; k < terms; k += 8) {
-          const int ch = k / opg, oo = k - ch * opg;
-          const float2 p = pn[static_cast<long long>(ch) * pld + g * opg + oo];
-          s += static_cast<double>(p.x);
-          ss += static_cast<double>(p.y);
+        for (int k0 = sub; k0 < terms; k0 += 64) {
+          float2 q[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int k = k0 + 8 * u;
+            const int ch = k / opg, oo = k - ch * opg;
+            q[u] = k < terms ? pn[static_cast<long long>(ch) * pld + g * opg + oo] : make_float2(0.f, 0.f);
+          }
+          s += static_cast<double>(((q[0].x + q[1].x) + (q[2].x + q[3].x)) + ((q[4].x + q[5].x) + (q[6].x + q[7].x)));
+          ss += static_cast<double>(((q[0].y + q[1].y) + (q[2].y + q[3].y)) + ((q[4].y + q[5].y) + (q[6].y + q[7].y)));
         }
       }
 #pragma unroll
@@ -214,12 +223,11 @@ gn_apply_partial_kernel(const TX* __restrict__ x, long long ld_x, T* __restrict_
         ss += __shfl_xor_sync(0xffffffffu, ss, o);
       }
       if (g < groups && sub == 0) {
-        const double cnt = static_cast<double>(hw) * cpg;
-        const double mean = s / cnt;
-        double var = ss / cnt - mean * mean;
-        if (var < 0.0) var = 0.0;
+        const double inv_cnt = 1.0 / (static_cast<double>(hw) * cpg);
+        const double mean = s * inv_cnt;
+        const float var = fmaxf(static_cast<float>(ss * inv_cnt - mean * mean), 0.f);
         s_mean[g] = static_cast<float>(mean);
-        s_rstd[g] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+        s_rstd[g] = rsqrtf(var + eps);
         if (stats_out != nullptr && blockIdx.x == 0) {
           stats_out[(static_cast<long long>(n) * groups + g) * 2] = s_mean[g];
           stats_out[(static_cast<long long>(n) * groups + g) * 2 + 1] = s_rstd[g];
