@@ -391,3 +391,20 @@ def test_guidance_pair_and_sampling_scope_host_logic():
     with sampling_scope(plain):
         GuidancePair(plain)(x, t, uc, c)
     assert plain.calls[0][3] is None and torch.equal(plain.calls[0][2], torch.cat([uc, c]))
+
+
+def test_activation_views_follow_the_statistics_buffer():
+    """ops.Act.images / cols: views of an NHWC activation share its storage, and the GroupNorm partial-statistics buffer
+    (one row per 32-pixel chunk) is sliced with the images (the guidance-pair prefix runs on the first half of a batch)."""
+    from ealdm_b200.ops import Act
+    a = Act(torch.arange(4 * 8 * 8 * 64, dtype=torch.float32).reshape(4 * 64, 64), 4, 8, 8)
+    a.gp = torch.arange(4 * 2 * 8 * 2, dtype=torch.float32).reshape(4 * 2, 8, 2)     # 2 chunks per image, 8 octets
+    v = a.images(1, 2)
+    assert (v.n, v.h, v.w, v.c, v.c0, v.rows) == (2, 8, 8, 64, 0, 128)
+    assert v.buf.data_ptr() == a.buf[64:].data_ptr() and v.gp.data_ptr() == a.gp[2:].data_ptr() and v.gp.shape[0] == 4
+    w = a.cols(32, 16).images(2, 1)
+    assert (w.c0, w.c, w.n) == (32, 16, 1) and torch.equal(w.view2d(), a.buf[128:192, 32:48])
+    w.view2d().zero_()
+    assert float(a.buf[128:192, 32:48].abs().sum()) == 0.0 and float(a.buf[128:192, :32].abs().sum()) > 0
+    with pytest.raises(AssertionError):
+        a.images(3, 2)
