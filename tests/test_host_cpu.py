@@ -408,3 +408,21 @@ def test_activation_views_follow_the_statistics_buffer():
     assert float(a.buf[128:192, 32:48].abs().sum()) == 0.0 and float(a.buf[128:192, :32].abs().sum()) > 0
     with pytest.raises(AssertionError):
         a.images(3, 2)
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the GPU arm): one JSON line with the same metric /
+    unit / config keys as the GPU arm plus impl, cpu_baseline {kind, cores, sample, value} and an e2e object with zero
+    copy bytes; it must run without a GPU and without /root/reference."""
+    import json
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"].startswith("latent samples/sec") and line["unit"] == "samples/s"
+    assert line["higher_is_better"] is True and line["n_gpus"] == 1 and line["steps"] == 1
+    cb = line["cpu_baseline"]
+    assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["sample"] and cb["value"] == line["value"] > 0
+    e = line["e2e"]
+    assert e["value"] == line["value"] and e["h2d_bytes_per_step"] == 0 and e["d2h_bytes_per_step"] == 0
+    assert "workload" in line["config"] and line["config"].get("same_config") is False
